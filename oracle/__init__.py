@@ -1,0 +1,175 @@
+"""ctypes/numpy front end of the CPU oracle (oracle/apo_oracle.c).
+
+TEST INFRASTRUCTURE ONLY — importable from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py; never from the product package.
+PARITY UNPINNED (see apo_oracle.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libapo_oracle.so")
+
+NDIM, NPAT, NMODE = 9, 6, 5
+STREAM_CORPUS, STREAM_ROLLOUT = 1, 2
+
+RECORD_DTYPE = np.dtype([
+    ("feedback", "u1"), ("flags", "u1"), ("mode", "u1"), ("pad", "u1"),
+    ("userMsgs", "<u2"), ("asstMsgs", "<u2"),
+    ("toolCalls", "<u4"), ("toolSucc", "<u4"), ("toolFail", "<u4"),
+    ("llmCalls", "<u4"), ("tokens", "<u4"), ("toolDurMs", "<f4"),
+])
+assert RECORD_DTYPE.itemsize == 32
+
+
+class Pattern(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("flag", C.c_uint8), ("severity", C.c_uint8), ("examples", C.c_int64 * 3)]
+
+
+class DimStat(C.Structure):
+    _fields_ = [("sum", C.c_double), ("count", C.c_uint64), ("avg", C.c_double),
+                ("low_flag", C.c_uint8), ("low_severity", C.c_uint8), ("sugg_flag", C.c_uint8), ("sugg_priority", C.c_uint8)]
+
+
+class Report(C.Structure):
+    _fields_ = [("total", C.c_uint64), ("good", C.c_uint64), ("bad", C.c_uint64), ("none", C.c_uint64),
+                ("goodRate", C.c_double), ("byMode", (C.c_uint64 * 3) * NMODE), ("byModeGoodRate", C.c_double * NMODE),
+                ("withReward", C.c_uint64), ("rewardSum", C.c_double), ("avgReward", C.c_double),
+                ("dim", DimStat * NDIM), ("pat", Pattern * NPAT),
+                ("toolCalls", C.c_uint64), ("toolSucc", C.c_uint64), ("toolFail", C.c_uint64),
+                ("toolSuccessRate", C.c_double)]
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, f) for f in ("apo_oracle.c", "apo_oracle.h")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "libapo_oracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        vp, u32, u64, dp, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_int
+        L.orc_reward_dims.restype = u32
+        L.orc_reward_dims.argtypes = [vp, dp]
+        L.orc_final_reward.restype = i32
+        L.orc_final_reward.argtypes = [dp, u32, dp, dp]
+        L.orc_final_reward_f32.restype = i32
+        L.orc_final_reward_f32.argtypes = [vp, dp, dp]
+        L.orc_score_dims.argtypes = [vp, u32, u64, u64, dp, dp, vp]
+        L.orc_score_records.argtypes = [vp, u32, u64, u64, dp, dp, vp]
+        L.orc_score_dims_mt.argtypes = [vp, u32, u64, u64, dp, dp, vp, i32]
+        L.orc_score_records_mt.argtypes = [vp, u32, u64, u64, dp, dp, vp, i32]
+        L.orc_topk.argtypes = [dp, u32, u32, vp]
+        L.orc_report_build.argtypes = [vp, u64, u64, dp, C.POINTER(Report)]
+        L.orc_gen_record.argtypes = [u64, u32, u32, u64, u32, vp]
+        L.orc_gen_dims_row.argtypes = [u64, u32, u64, u32, vp]
+        L.orc_gen_dims.argtypes = [u64, u32, u32, u64, u64, u64, u32, vp, i32]
+        L.orc_gen_records.argtypes = [u64, u32, u32, u32, u64, u64, u64, u32, vp, i32]
+        for f in (L.orc_score_dims, L.orc_score_records, L.orc_score_dims_mt, L.orc_score_records_mt, L.orc_topk,
+                  L.orc_report_build, L.orc_gen_record, L.orc_gen_dims_row, L.orc_gen_dims, L.orc_gen_records):
+            f.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def weights() -> np.ndarray:
+    return np.array((C.c_double * NDIM).in_dll(lib(), "orc_weights"), dtype=np.float64)
+
+
+def reward_dims(rec: np.ndarray):
+    """One Form-R record -> (dims[9] float64 with NaN = absent, mask)."""
+    rec = np.ascontiguousarray(rec, dtype=RECORD_DTYPE).reshape(1)
+    d = np.empty(NDIM, np.float64)
+    m = lib().orc_reward_dims(_p(rec), _p(d))
+    return d, int(m)
+
+
+def final_reward(dims: np.ndarray, mask: int, w: np.ndarray | None = None):
+    w = weights() if w is None else np.ascontiguousarray(w, np.float64)
+    dims = np.ascontiguousarray(dims, np.float64)
+    out = C.c_double()
+    ok = lib().orc_final_reward(_p(dims), mask, _p(w), C.addressof(out))
+    return out.value if ok else None
+
+
+def reward_one(rec: np.ndarray, w: np.ndarray | None = None):
+    """(dims, mask, finalReward|None) for one record, honouring the VALID flag."""
+    d, m = reward_dims(rec)
+    rec = np.ascontiguousarray(rec, dtype=RECORD_DTYPE).reshape(1)
+    if not (int(rec["flags"][0]) & 0x08):
+        return d, m, None
+    return d, m, final_reward(d, m, w)
+
+
+def score_dims(dims: np.ndarray, T: int | None = None, w=None, nthreads: int = 0):
+    """dims float32 [C][pitch][9] -> (scores f64[C], counts u64[C])."""
+    dims = np.ascontiguousarray(dims, np.float32)
+    Cn, pitch, nd = dims.shape
+    assert nd == NDIM
+    T = pitch if T is None else T
+    w = weights() if w is None else np.ascontiguousarray(w, np.float64)
+    s = np.empty(Cn, np.float64)
+    n = np.empty(Cn, np.uint64)
+    if nthreads > 0:
+        lib().orc_score_dims_mt(_p(dims), Cn, T, pitch, _p(w), _p(s), _p(n), nthreads)
+    else:
+        lib().orc_score_dims(_p(dims), Cn, T, pitch, _p(w), _p(s), _p(n))
+    return s, n
+
+
+def score_records(recs: np.ndarray, T: int | None = None, w=None, nthreads: int = 0):
+    recs = np.ascontiguousarray(recs, RECORD_DTYPE)
+    Cn, pitch = recs.shape
+    T = pitch if T is None else T
+    w = weights() if w is None else np.ascontiguousarray(w, np.float64)
+    s = np.empty(Cn, np.float64)
+    n = np.empty(Cn, np.uint64)
+    if nthreads > 0:
+        lib().orc_score_records_mt(_p(recs), Cn, T, pitch, _p(w), _p(s), _p(n), nthreads)
+    else:
+        lib().orc_score_records(_p(recs), Cn, T, pitch, _p(w), _p(s), _p(n))
+    return s, n
+
+
+def topk(scores: np.ndarray, K: int) -> np.ndarray:
+    scores = np.ascontiguousarray(scores, np.float64)
+    out = np.empty(K, np.int32)
+    lib().orc_topk(_p(scores), scores.shape[0], K, _p(out))
+    return out
+
+
+def report(recs: np.ndarray, idx_base: int = 0, w=None) -> Report:
+    recs = np.ascontiguousarray(recs, RECORD_DTYPE).reshape(-1)
+    w = weights() if w is None else np.ascontiguousarray(w, np.float64)
+    r = Report()
+    lib().orc_report_build(_p(recs), recs.shape[0], idx_base, _p(w), C.byref(r))
+    return r
+
+
+def gen_records(seed: int, stream: int, c0: int, Cn: int, t0: int, T: int, agent_permille: int = 300,
+                nthreads: int = 8) -> np.ndarray:
+    out = np.empty((Cn, T), RECORD_DTYPE)
+    lib().orc_gen_records(seed, stream, c0, Cn, t0, T, T, agent_permille, _p(out), nthreads)
+    return out
+
+
+def gen_dims(seed: int, c0: int, Cn: int, t0: int, T: int, agent_permille: int = 300, nthreads: int = 8) -> np.ndarray:
+    out = np.empty((Cn, T, NDIM), np.float32)
+    lib().orc_gen_dims(seed, c0, Cn, t0, T, T, agent_permille, _p(out), nthreads)
+    return out

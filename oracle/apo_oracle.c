@@ -1,0 +1,510 @@
+/*
+ * apo_oracle.c — CPU ORACLE (test infrastructure only; see apo_oracle.h header).
+ *
+ * PARITY UNPINNED (no reference tests / golden vectors / runnable reference exist).
+ * Plain C, IEEE-754 binary64 throughout (JS `number`), compiled with
+ * -ffp-contract=off so no multiply-add is fused: every `a*b + c` below rounds twice,
+ * exactly like the TypeScript it restates.
+ *
+ * TCS = src/vs/workbench/contrib/senweaver/common/traceCollectorService.ts
+ * APO = src/vs/workbench/contrib/senweaver/common/apoService.ts
+ */
+#include "apo_oracle.h"
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* TCS:766-776, in the order the dims are pushed (TCS:679,692,698,708,718,728,736,748,762). */
+const double orc_weights[ORC_NDIM] = {
+	0.25, /* user_feedback            */
+	0.18, /* task_completion          */
+	0.12, /* tool_success_rate        */
+	0.08, /* tool_call_reliability    */
+	0.05, /* tool_call_efficiency     */
+	0.05, /* tool_duration_efficiency */
+	0.08, /* response_efficiency      */
+	0.08, /* token_efficiency         */
+	0.11, /* conversation_efficiency  */
+};
+
+/* ---------------------------------------------------------------- TCS:668-763 */
+uint32_t orc_reward_dims(const orc_record *r, double dims[ORC_NDIM])
+{
+	uint32_t mask = 0;
+	for (int i = 0; i < ORC_NDIM; i++) dims[i] = NAN;
+
+	/* TCS:673-674: only the literal 'agent' selects the agent thresholds. */
+	const int isAgent = (r->mode == 2);
+	const int hasErrors = (r->flags & ORC_F_ERRORS) != 0;
+	const int ended = (r->flags & ORC_F_ENDED) != 0;
+
+	/* d0 user_feedback, TCS:677-679 */
+	dims[0] = r->feedback == 1 ? 1.0 : (r->feedback == 2 ? -1.0 : 0.0);
+	mask |= 1u << 0;
+
+	/* d1 task_completion, TCS:682-692 — later rule wins */
+	double completion = 0.5;
+	if (ended && !hasErrors) completion = 0.8;
+	if (hasErrors) completion = -0.5;
+	if (r->feedback == 1) completion = 1.0;
+	dims[1] = completion;
+	mask |= 1u << 1;
+
+	/* d2..d5, TCS:695-730 */
+	if (r->toolCalls > 0) {
+		const double total = (double)r->toolCalls;
+		const double rate = (double)r->toolSucc / total;   /* TCS:697 */
+		dims[2] = rate * 2 - 1;                              /* TCS:698 */
+		mask |= 1u << 2;
+
+		/* TCS:701-708, '>=' comparisons */
+		const uint32_t sev = isAgent ? 5 : 3, mod = isAgent ? 3 : 2, mnr = isAgent ? 2 : 1;
+		double pen = 1.0;
+		if (r->toolFail >= sev) pen = -1.0;
+		else if (r->toolFail >= mod) pen = -0.5;
+		else if (r->toolFail >= mnr) pen = -0.2;
+		dims[3] = pen;
+		mask |= 1u << 3;
+
+		/* TCS:711-718, strict '>' */
+		const uint32_t exc = isAgent ? 8 : 3, good = isAgent ? 15 : 6, fair = isAgent ? 25 : 10;
+		double cnt = 1.0;
+		if (r->toolCalls > fair) cnt = -0.8;
+		else if (r->toolCalls > good) cnt = -0.3;
+		else if (r->toolCalls > exc) cnt = 0.3;
+		dims[4] = cnt;
+		mask |= 1u << 4;
+
+		/* TCS:721-729 */
+		const double dur = (double)r->toolDurMs;
+		if (dur > 0) {
+			const double avg = dur / total;
+			double ds = 1.0;
+			if (avg > 10000) ds = -0.5;
+			else if (avg > 3000) ds = 0.0;
+			else if (avg > 1000) ds = 0.5;
+			dims[5] = ds;
+			mask |= 1u << 5;
+		}
+	}
+
+	/* d6 response_efficiency, TCS:733-737 */
+	if (r->llmCalls > 0) {
+		const double thr = isAgent ? 3 : 1;
+		double over = (double)r->llmCalls - thr;
+		if (!(over > 0)) over = 0;                 /* Math.max(0, n - thr) */
+		double e = 1 - over * 0.4;
+		if (e < -1) e = -1;                        /* Math.max(-1, ...) */
+		dims[6] = e;
+		mask |= 1u << 6;
+	}
+
+	/* d7 token_efficiency, TCS:740-749 */
+	if (r->tokens > 0) {
+		const uint32_t exc = isAgent ? 5000 : 2000, good = isAgent ? 15000 : 5000, fair = isAgent ? 30000 : 10000;
+		double ts = 1.0;
+		if (r->tokens > fair) ts = -0.5;
+		else if (r->tokens > good) ts = 0.0;
+		else if (r->tokens > exc) ts = 0.5;
+		dims[7] = ts;
+		mask |= 1u << 7;
+	}
+
+	/* d8 conversation_efficiency, TCS:752-763 */
+	const uint32_t turns = r->userMsgs < r->asstMsgs ? r->userMsgs : r->asstMsgs;
+	if (turns > 0) {
+		const uint32_t thr = isAgent ? 3 : 2;
+		double tsc = 1.0;
+		if (turns > thr * 3) tsc = -0.8;
+		else if (turns > thr * 2) tsc = -0.3;
+		else if (turns > thr) tsc = 0.3;
+		dims[8] = tsc;
+		mask |= 1u << 8;
+	}
+	return mask;
+}
+
+/* ---------------------------------------------------------------- TCS:777-784 */
+int orc_final_reward(const double dims[ORC_NDIM], uint32_t mask, const double w[ORC_NDIM], double *out)
+{
+	double weightedSum = 0, totalWeight = 0;
+	for (int i = 0; i < ORC_NDIM; i++) {
+		if (!(mask & (1u << i))) continue;
+		weightedSum += dims[i] * w[i];
+		totalWeight += w[i];
+	}
+	if (!(totalWeight > 0)) return 0;
+	*out = weightedSum / totalWeight;
+	return 1;
+}
+
+int orc_final_reward_f32(const float row[ORC_NDIM], const double w[ORC_NDIM], double *out)
+{
+	double d[ORC_NDIM];
+	uint32_t mask = 0;
+	for (int i = 0; i < ORC_NDIM; i++) {
+		d[i] = (double)row[i];
+		if (!isnan(row[i])) mask |= 1u << i;
+	}
+	return orc_final_reward(d, mask, w, out);
+}
+
+static int record_final(const orc_record *r, const double w[ORC_NDIM], double *out)
+{
+	if (!(r->flags & ORC_F_VALID)) return 0;   /* finalReward === null, TCS:397 */
+	double d[ORC_NDIM];
+	uint32_t mask = orc_reward_dims(r, d);
+	return orc_final_reward(d, mask, w, out);
+}
+
+/* ---------------------------------------------------------------- APO:550-553 per candidate */
+static void score_dims_range(const float *row0, uint64_t t0, uint64_t t1, const double w[ORC_NDIM],
+                             double *sum, uint64_t *n)
+{
+	double s = 0; uint64_t k = 0;
+	for (uint64_t t = t0; t < t1; t++) {
+		double fr;
+		if (orc_final_reward_f32(row0 + t * ORC_NDIM, w, &fr)) { s += fr; k++; }
+	}
+	*sum = s; *n = k;
+}
+
+static void score_recs_range(const orc_record *row0, uint64_t t0, uint64_t t1, const double w[ORC_NDIM],
+                             double *sum, uint64_t *n)
+{
+	double s = 0; uint64_t k = 0;
+	for (uint64_t t = t0; t < t1; t++) {
+		double fr;
+		if (record_final(row0 + t, w, &fr)) { s += fr; k++; }
+	}
+	*sum = s; *n = k;
+}
+
+void orc_score_dims(const float *dims, uint32_t C, uint64_t T, uint64_t pitch_evals,
+                    const double w[ORC_NDIM], double *scores, uint64_t *counts)
+{
+	for (uint32_t c = 0; c < C; c++) {
+		double s; uint64_t n;
+		score_dims_range(dims + (uint64_t)c * pitch_evals * ORC_NDIM, 0, T, w, &s, &n);
+		counts[c] = n;
+		scores[c] = n > 0 ? s / (double)n : -INFINITY;
+	}
+}
+
+void orc_score_records(const orc_record *recs, uint32_t C, uint64_t T, uint64_t pitch,
+                       const double w[ORC_NDIM], double *scores, uint64_t *counts)
+{
+	for (uint32_t c = 0; c < C; c++) {
+		double s; uint64_t n;
+		score_recs_range(recs + (uint64_t)c * pitch, 0, T, w, &s, &n);
+		counts[c] = n;
+		scores[c] = n > 0 ? s / (double)n : -INFINITY;
+	}
+}
+
+/* ---- multi-threaded baseline: (candidate, T-slice) work items, merged in slice order ---- */
+typedef struct {
+	const float *dims; const orc_record *recs;
+	uint32_t C; uint64_t T, pitch; const double *w;
+	int nslice; double *psum; uint64_t *pcnt;
+	int tid, nthreads;
+} mt_job;
+
+static void *mt_worker(void *arg)
+{
+	mt_job *j = (mt_job *)arg;
+	const uint64_t nitems = (uint64_t)j->C * (uint64_t)j->nslice;
+	for (uint64_t it = (uint64_t)j->tid; it < nitems; it += (uint64_t)j->nthreads) {
+		const uint32_t c = (uint32_t)(it / (uint64_t)j->nslice);
+		const int s = (int)(it % (uint64_t)j->nslice);
+		const uint64_t t0 = j->T * (uint64_t)s / (uint64_t)j->nslice;
+		const uint64_t t1 = j->T * (uint64_t)(s + 1) / (uint64_t)j->nslice;
+		if (j->dims)
+			score_dims_range(j->dims + (uint64_t)c * j->pitch * ORC_NDIM, t0, t1, j->w, &j->psum[it], &j->pcnt[it]);
+		else
+			score_recs_range(j->recs + (uint64_t)c * j->pitch, t0, t1, j->w, &j->psum[it], &j->pcnt[it]);
+	}
+	return NULL;
+}
+
+static void score_mt(const float *dims, const orc_record *recs, uint32_t C, uint64_t T, uint64_t pitch,
+                     const double w[ORC_NDIM], double *scores, uint64_t *counts, int nthreads)
+{
+	if (nthreads < 1) nthreads = 1;
+	int nslice = nthreads;            /* every candidate is cut into nthreads T-slices */
+	const uint64_t nitems = (uint64_t)C * (uint64_t)nslice;
+	double *psum = (double *)calloc(nitems ? nitems : 1, sizeof(double));
+	uint64_t *pcnt = (uint64_t *)calloc(nitems ? nitems : 1, sizeof(uint64_t));
+	pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+	mt_job *jobs = (mt_job *)malloc(sizeof(mt_job) * (size_t)nthreads);
+	for (int i = 0; i < nthreads; i++) {
+		jobs[i] = (mt_job){dims, recs, C, T, pitch, w, nslice, psum, pcnt, i, nthreads};
+		pthread_create(&th[i], NULL, mt_worker, &jobs[i]);
+	}
+	for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+	for (uint32_t c = 0; c < C; c++) {
+		double s = 0; uint64_t n = 0;
+		for (int k = 0; k < nslice; k++) { s += psum[(uint64_t)c * nslice + k]; n += pcnt[(uint64_t)c * nslice + k]; }
+		counts[c] = n;
+		scores[c] = n > 0 ? s / (double)n : -INFINITY;
+	}
+	free(psum); free(pcnt); free(th); free(jobs);
+}
+
+void orc_score_dims_mt(const float *dims, uint32_t C, uint64_t T, uint64_t pitch_evals,
+                       const double w[ORC_NDIM], double *scores, uint64_t *counts, int nthreads)
+{ score_mt(dims, NULL, C, T, pitch_evals, w, scores, counts, nthreads); }
+
+void orc_score_records_mt(const orc_record *recs, uint32_t C, uint64_t T, uint64_t pitch,
+                          const double w[ORC_NDIM], double *scores, uint64_t *counts, int nthreads)
+{ score_mt(NULL, recs, C, T, pitch, w, scores, counts, nthreads); }
+
+/* ---------------------------------------------------------------- top-K */
+void orc_topk(const double *scores, uint32_t C, uint32_t K, int32_t *out_idx)
+{
+	/* stable insertion-selection: K passes, strict '>' keeps the lower index on ties */
+	uint8_t *taken = (uint8_t *)calloc(C ? C : 1, 1);
+	for (uint32_t k = 0; k < K; k++) {
+		int64_t best = -1;
+		for (uint32_t c = 0; c < C; c++) {
+			if (taken[c]) continue;
+			if (best < 0 || scores[c] > scores[best]) best = c;
+		}
+		out_idx[k] = (int32_t)best;
+		if (best >= 0) taken[best] = 1;
+	}
+	free(taken);
+}
+
+/* ---------------------------------------------------------------- APO:498-625, 635-773 */
+static void pat_hit(orc_pattern *p, uint64_t idx)
+{
+	if (p->count < 3) p->examples[p->count] = (int64_t)idx;   /* slice(0,3), APO:652 ... */
+	p->count++;
+}
+
+void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
+                      const double w[ORC_NDIM], orc_report *out)
+{
+	memset(out, 0, sizeof(*out));
+	for (int p = 0; p < ORC_NPAT; p++) for (int k = 0; k < 3; k++) out->pat[p].examples[k] = -1;
+	out->total = T;
+
+	/* pass 1, APO:509-538 + TCS:602-610 */
+	for (uint64_t t = 0; t < T; t++) {
+		const orc_record *r = &recs[t];
+		if (r->feedback == 1) out->good++;
+		else if (r->feedback == 2) out->bad++;
+		else out->none++;
+		const int m = r->mode < ORC_NMODE ? r->mode : 0;      /* APO:627-633 */
+		out->byMode[m][0]++;
+		if (r->feedback == 1) out->byMode[m][1]++;
+		if (r->feedback == 2) out->byMode[m][2]++;
+		out->toolCalls += r->toolCalls;
+		out->toolSucc += r->toolSucc;
+		out->toolFail += r->toolFail;
+	}
+	for (int m = 0; m < ORC_NMODE; m++) {                     /* APO:541-544 */
+		const uint64_t tot = out->byMode[m][1] + out->byMode[m][2];
+		out->byModeGoodRate[m] = tot > 0 ? (double)out->byMode[m][1] / (double)tot : 0;
+	}
+	{
+		const uint64_t tot = out->good + out->bad;              /* APO:546-547 */
+		out->goodRate = tot > 0 ? (double)out->good / (double)tot : 0;
+	}
+	out->toolSuccessRate = out->toolCalls > 0 ? (double)out->toolSucc / (double)out->toolCalls : NAN; /* TCS:624 */
+
+	/* APO:550-568: sequential sums over traces with non-null finalReward */
+	for (uint64_t t = 0; t < T; t++) {
+		const orc_record *r = &recs[t];
+		if (!(r->flags & ORC_F_VALID)) continue;
+		double d[ORC_NDIM], fr;
+		const uint32_t mask = orc_reward_dims(r, d);
+		if (!orc_final_reward(d, mask, w, &fr)) continue;
+		out->rewardSum += fr;
+		out->withReward++;
+		for (int i = 0; i < ORC_NDIM; i++) {
+			if (!(mask & (1u << i))) continue;
+			out->dim[i].sum += d[i];
+			out->dim[i].count++;
+		}
+	}
+	out->avgReward = out->withReward > 0 ? out->rewardSum / (double)out->withReward : NAN;
+	for (int i = 0; i < ORC_NDIM; i++) {
+		orc_dimstat *ds = &out->dim[i];
+		ds->avg = ds->count > 0 ? ds->sum / (double)ds->count : 0;         /* APO:567 */
+		ds->low_flag = (ds->count > 0 && ds->avg < -0.3 && ds->count >= 5);  /* APO:575 */
+		ds->low_severity = ds->avg < -0.5 ? 2 : 1;                           /* APO:591 */
+		ds->sugg_flag = (ds->count > 0 && ds->avg < 0 && ds->count >= 3);    /* APO:802 */
+		ds->sugg_priority = ds->avg < -0.5 ? 2 : 1;                          /* APO:819 */
+	}
+
+	/* APO:635-773.  APO:641: no bad examples -> no patterns at all. */
+	if (out->bad == 0) return;
+	for (uint64_t t = 0; t < T; t++) {
+		const orc_record *r = &recs[t];
+		if (r->feedback != 2) continue;                       /* every predicate ANDs userFeedback==='bad' */
+		const uint64_t gi = idx_base + t;
+		if (r->flags & ORC_F_ERRORS) pat_hit(&out->pat[0], gi);          /* P1 APO:644 */
+		if (r->flags & ORC_F_FAILSPAN) pat_hit(&out->pat[1], gi);        /* P2 APO:666-670 */
+		if (r->tokens > 10000) pat_hit(&out->pat[2], gi);                /* P3 APO:692-694 */
+		if (r->llmCalls > 2) pat_hit(&out->pat[3], gi);                  /* P4 APO:712-714 */
+		if (r->userMsgs >= 4) pat_hit(&out->pat[4], gi);                 /* P5 APO:732-735 */
+		if ((double)r->toolDurMs > 15000) pat_hit(&out->pat[5], gi);     /* P6 APO:753-755 */
+	}
+	/* thresholds and severities: APO:645,650 / 671,676 / 695,700 / 715,720 / 736,741 / 756,761 */
+	static const uint64_t minc[ORC_NPAT] = {2, 2, 3, 2, 2, 2};
+	for (int p = 0; p < ORC_NPAT; p++) {
+		orc_pattern *pp = &out->pat[p];
+		pp->flag = pp->count >= minc[p];
+		switch (p) {
+		case 0: case 1: pp->severity = pp->count >= 5 ? 2 : 1; break;
+		case 2: pp->severity = 1; break;
+		case 3: pp->severity = 2; break;
+		case 4: pp->severity = pp->count >= 4 ? 2 : 1; break;
+		default: pp->severity = 1; break;
+		}
+	}
+}
+
+/* ================================================================ synthetic generator
+ * Build-defined (not from the reference).  Integer-only field derivation so the CUDA
+ * generator and this one agree bit for bit.  Spec: DESIGN.md "Generator". */
+#define GOLD 0x9E3779B97F4A7C15ull
+
+static inline uint64_t mix64(uint64_t z)
+{
+	z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+	z ^= z >> 27; z *= 0x94D049BB133111EBull;
+	z ^= z >> 31;
+	return z;
+}
+
+static inline uint32_t ctz64(uint64_t x) { return (uint32_t)__builtin_ctzll(x); }
+
+void orc_gen_record(uint64_t seed, uint32_t stream, uint32_t c, uint64_t t,
+                    uint32_t agent_permille, orc_record *out)
+{
+	const uint64_t base = mix64(mix64(seed ^ ((uint64_t)stream * GOLD)) ^ mix64(((uint64_t)c + 1) * GOLD)) + t * GOLD;
+	const uint64_t h1 = mix64(base + GOLD);
+	const uint64_t h2 = mix64(base + 2 * GOLD);
+	const uint64_t h3 = mix64(base + 3 * GOLD);
+	const uint64_t h4 = mix64(base + 4 * GOLD);
+	const uint32_t qc = stream == ORC_STREAM_CORPUS ? 512u
+	                  : (uint32_t)(mix64(seed ^ 0xC0FFEEull ^ ((uint64_t)c * GOLD)) & 1023);
+
+	const uint32_t r = (uint32_t)(h1 & 1023);
+	const uint32_t pgood = 192 + (qc >> 2);
+	const uint32_t pbad = 256 - (qc >> 3);
+	const uint8_t feedback = r < pgood ? 1 : (r < pgood + pbad ? 2 : 0);
+	const int hasErrors = ((h1 >> 10) & 1023) < 102;
+	const int ended = ((h1 >> 20) & 1023) < 973;
+	uint8_t mode;
+	if (((h1 >> 30) & 1023) < agent_permille) mode = 2;
+	else {
+		const uint32_t k = (uint32_t)((h1 >> 40) & 15);
+		mode = k < 10 ? 1 : (k < 12 ? 3 : (k < 14 ? 4 : 0));
+	}
+	const int agent = mode == 2;
+
+	uint32_t toolCalls = 0, toolFail = 0;
+	float dur = 0.0f;
+	if (!(((h1 >> 44) & 1023) < 307)) {
+		const uint32_t g = ctz64(h2 | (1ull << 20));
+		toolCalls = agent ? 1 + (uint32_t)((h2 >> 21) & 15) + g : 1 + g;
+		const uint32_t n = toolCalls < 16 ? toolCalls : 16;
+		for (uint32_t i = 0; i < n; i++) if (((h3 >> (4 * i)) & 15) == 0) toolFail++;
+		if (((h2 >> 25) & 15) != 0) {
+			const uint32_t e = (uint32_t)((h2 >> 29) & 15) % 10;
+			const uint32_t basems = 50u << e;
+			const uint32_t frac = (uint32_t)((h2 >> 33) & 4095);
+			const uint32_t avg = basems + ((basems * frac) >> 12);
+			dur = (float)(avg * toolCalls);
+		}
+	}
+	uint32_t llm = 0;
+	if (((h2 >> 45) & 31) != 0)
+		llm = 1 + ctz64((h2 >> 50) | (1ull << 13)) + (agent ? (uint32_t)((h2 >> 48) & 3) : 0);
+	uint32_t tokens = 0;
+	if (!((h4 & 1023) < 205)) {
+		const uint32_t e = (uint32_t)((h4 >> 10) & 15) % 9;
+		const uint32_t b = 200u << e;
+		const uint32_t f = (uint32_t)((h4 >> 14) & 4095);
+		tokens = b + ((b * f) >> 12);
+	}
+	uint32_t userMsgs = 0;
+	if (((h4 >> 40) & 63) != 0) userMsgs = 1 + ctz64((h4 >> 26) | (1ull << 12));
+
+	out->feedback = feedback;
+	out->flags = (uint8_t)((hasErrors ? ORC_F_ERRORS : 0) | (ended ? ORC_F_ENDED : 0) |
+	                       ((ended || feedback) ? ORC_F_VALID : 0) | (toolFail > 0 ? ORC_F_FAILSPAN : 0));
+	out->mode = mode;
+	out->pad = 0;
+	out->userMsgs = (uint16_t)userMsgs;
+	out->asstMsgs = (uint16_t)(llm < 65535 ? llm : 65535);
+	out->toolCalls = toolCalls;
+	out->toolSucc = toolCalls - toolFail;
+	out->toolFail = toolFail;
+	out->llmCalls = llm;
+	out->tokens = tokens;
+	out->toolDurMs = dur;
+}
+
+void orc_gen_dims_row(uint64_t seed, uint32_t c, uint64_t t, uint32_t agent_permille, float out[ORC_NDIM])
+{
+	orc_record r;
+	orc_gen_record(seed, ORC_STREAM_ROLLOUT, c, t, agent_permille, &r);
+	double d[ORC_NDIM];
+	const uint32_t mask = orc_reward_dims(&r, d);
+	for (int i = 0; i < ORC_NDIM; i++)
+		out[i] = ((r.flags & ORC_F_VALID) && (mask & (1u << i))) ? (float)d[i] : NAN;
+}
+
+typedef struct {
+	uint64_t seed; uint32_t stream, c0, C; uint64_t t0, T, pitch; uint32_t ap;
+	float *dims; orc_record *recs; int tid, nthreads;
+} gen_job;
+
+static void *gen_worker(void *arg)
+{
+	gen_job *j = (gen_job *)arg;
+	for (uint32_t c = 0; c < j->C; c++) {
+		const uint64_t a = j->T * (uint64_t)j->tid / (uint64_t)j->nthreads;
+		const uint64_t b = j->T * (uint64_t)(j->tid + 1) / (uint64_t)j->nthreads;
+		for (uint64_t t = a; t < b; t++) {
+			if (j->dims)
+				orc_gen_dims_row(j->seed, j->c0 + c, j->t0 + t, j->ap, j->dims + ((uint64_t)c * j->pitch + t) * ORC_NDIM);
+			else
+				orc_gen_record(j->seed, j->stream, j->c0 + c, j->t0 + t, j->ap, j->recs + (uint64_t)c * j->pitch + t);
+		}
+	}
+	return NULL;
+}
+
+static void gen_mt(gen_job proto, int nthreads)
+{
+	if (nthreads < 1) nthreads = 1;
+	pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+	gen_job *jobs = (gen_job *)malloc(sizeof(gen_job) * (size_t)nthreads);
+	for (int i = 0; i < nthreads; i++) {
+		jobs[i] = proto; jobs[i].tid = i; jobs[i].nthreads = nthreads;
+		pthread_create(&th[i], NULL, gen_worker, &jobs[i]);
+	}
+	for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+	free(th); free(jobs);
+}
+
+void orc_gen_dims(uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T, uint64_t pitch_evals,
+                  uint32_t agent_permille, float *out, int nthreads)
+{
+	gen_job p = {seed, ORC_STREAM_ROLLOUT, c0, C, t0, T, pitch_evals, agent_permille, out, NULL, 0, 1};
+	gen_mt(p, nthreads);
+}
+
+void orc_gen_records(uint64_t seed, uint32_t stream, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,
+                     uint64_t pitch, uint32_t agent_permille, orc_record *out, int nthreads)
+{
+	gen_job p = {seed, stream, c0, C, t0, T, pitch, agent_permille, NULL, out, 0, 1};
+	gen_mt(p, nthreads);
+}

@@ -1,0 +1,180 @@
+/*
+ * apo_b200.h — C ABI of the B200-native APO scoring engine (libapo_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of senweaver/senweaver-ide: the 9-dimension reward
+ * -> finalReward aggregation, the 6-pattern problem detector and the top-K beam
+ * selection behind APOService / TraceCollectorService.  Plain C types only; no C++,
+ * torch or CUDA types cross this boundary.  Every entry point below names the reference
+ * code it replaces:
+ *   TCS = src/vs/workbench/contrib/senweaver/common/traceCollectorService.ts
+ *   APO = src/vs/workbench/contrib/senweaver/common/apoService.ts
+ *
+ * Conventions (reference error behaviour, TCS:438, APO:1211-1214: never throw into the
+ * caller): every function returns 0 on success or a negative APO_E_* code; the message
+ * is available from apo_last_error().  Nothing is retained from host pointers after a
+ * call returns.  A handle is not re-entrant (one in-flight call per handle); distinct
+ * handles are independent.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with APO_E_CUDA.
+ */
+#ifndef APO_B200_H
+#define APO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APO_ABI_VERSION 1
+#define APO_NDIM  9   /* reward dimensions, push order of TCS:679..762 */
+#define APO_NPAT  6   /* problem patterns, APO:643-770 */
+#define APO_NMODE 5   /* 0 no metadata ('unknown', APO:632), 1 normal, 2 agent, 3 gather, 4 designer */
+
+#define APO_OK          0
+#define APO_E_ARG      -1   /* bad argument                       */
+#define APO_E_CUDA     -2   /* CUDA runtime / no device           */
+#define APO_E_STATE    -3   /* call order (nothing uploaded, ...) */
+#define APO_E_NOMEM    -4
+#define APO_E_NCCL     -5
+
+/* Form R — one trace-summary record = the fields of ConversationTrace.summary that the
+ * path reads (TCS:94-108) + endTime (TCS:87) + metadata.chatMode (TCS:91) + the span
+ * counts of TCS:752-753 / APO:667-669,733.  32 bytes, little endian. */
+typedef struct apo_record {
+	uint8_t  feedback;   /* 0 null, 1 'good', 2 'bad' */
+	uint8_t  flags;      /* APO_F_* */
+	uint8_t  mode;       /* chat mode code, see APO_NMODE */
+	uint8_t  pad;
+	uint16_t userMsgs;   /* # user_message spans */
+	uint16_t asstMsgs;   /* # assistant_message spans */
+	uint32_t toolCalls, toolSucc, toolFail, llmCalls, tokens;
+	float    toolDurMs;
+} apo_record;
+#define APO_F_ERRORS   0x01u  /* summary.hasErrors                                   */
+#define APO_F_ENDED    0x02u  /* endTime set                                         */
+#define APO_F_VALID    0x08u  /* summary.finalReward !== null (TCS:606, APO:550)     */
+#define APO_F_FAILSPAN 0x10u  /* a tool_call span with toolSuccess===false exists    */
+
+typedef struct apo_pattern {      /* one of the six patterns of APO:635-773 */
+	uint64_t count;               /* frequency                              */
+	uint8_t  flag;                /* emitted (count >= minimum)             */
+	uint8_t  severity;            /* 0 low, 1 medium, 2 high                */
+	uint8_t  pad[6];
+	int64_t  examples[3];         /* first 3 matching record indices (corpus order), -1 = none */
+} apo_pattern;
+
+typedef struct apo_dimstat {      /* APO:556-568 + rules APO:575,591,802,819 */
+	double   sum; uint64_t count; double avg;
+	uint8_t  low_flag, low_severity, sugg_flag, sugg_priority;
+	uint8_t  pad[4];
+} apo_dimstat;
+
+typedef struct apo_corpus_report { /* numeric content of APO._buildReport + TCS.getStats */
+	uint64_t total, good, bad, none;          /* APO:509-516 */
+	double   goodRate;                        /* APO:546-547 */
+	uint64_t byMode[APO_NMODE][3];            /* total, good, bad (APO:519-525) */
+	double   byModeGoodRate[APO_NMODE];       /* APO:541-544 */
+	uint64_t withReward;                      /* APO:550 */
+	double   rewardSum;
+	double   avgReward;                       /* NaN = null */
+	apo_dimstat dim[APO_NDIM];
+	apo_pattern pat[APO_NPAT];
+	uint64_t toolCalls, toolSucc, toolFail;   /* TCS:603-605 */
+	double   toolSuccessRate;                 /* TCS:624, NaN = null */
+} apo_corpus_report;
+
+typedef struct apo_timing {       /* device time of the stages of the last apo_score*, ms (CUDA events) */
+	float reward_ms;              /* K1 reward9 / reward9_raw                 */
+	float corpus_ms;              /* K2 detect6 (+ fused finalize at 1 rank)  */
+	float allreduce_ms;           /* ncclAllReduce of the packed partials     */
+	float finalize_ms;            /* K3 segmented sum + radix top-K (>1 rank) */
+	float total_ms;               /* first launch -> last kernel end          */
+	uint32_t launches;            /* kernels launched by the call             */
+	uint32_t pad;
+} apo_timing;
+
+typedef struct apo_engine apo_engine;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+int  apo_abi_version(void);
+/* One engine drives one GPU (one process per GPU).  device = CUDA ordinal. */
+int  apo_create(int device, apo_engine **out);
+void apo_destroy(apo_engine *e);
+/* Message of the last failure on this engine (e == NULL: last apo_create failure). */
+const char *apo_last_error(const apo_engine *e);
+/* Launch all work on this CUDA stream (a cudaStream_t passed as an integer); 0 = the
+ * engine's own stream.  Lets a host harness bracket calls with its own events. */
+int  apo_set_stream(apo_engine *e, uint64_t cuda_stream);
+/* Replace the TCS:766-776 weights (default = reference values). */
+int  apo_set_weights(apo_engine *e, const double w[APO_NDIM]);
+int  apo_get_weights(const apo_engine *e, double w[APO_NDIM]);
+
+/* ---- single-trace path: TraceCollectorService._computeRewardSignals (TCS:668-788) --
+ * dims: n x 9 binary64, NaN where the dimension is not pushed; masks: 9-bit presence;
+ * finals: finalReward, NaN where it stays null (VALID flag clear). Computed on the GPU. */
+int apo_reward_batch(apo_engine *e, const apo_record *recs, uint64_t n,
+                     double *dims, uint32_t *masks, double *finals);
+int apo_reward_one(apo_engine *e, const apo_record *rec, double dims[APO_NDIM],
+                   uint32_t *mask, double *final_reward);
+
+/* ---- corpus = the T trace records APOService._buildReport walks (APO:498-625) ------
+ * idx_base = global index of recs[0] (shard offset); example indices are global. */
+int apo_corpus_upload(apo_engine *e, const apo_record *recs, uint64_t T, uint64_t idx_base);
+int apo_corpus_generate(apo_engine *e, uint64_t seed, uint64_t t0, uint64_t T, uint32_t agent_permille);
+int apo_corpus_download(apo_engine *e, apo_record *out, uint64_t first, uint64_t n);
+
+/* ---- candidate x record evaluations ------------------------------------------------
+ * Form D: fp32 dims[C][T][9], NaN = dimension absent, all-NaN = finalReward null.
+ * Form R: one apo_record per (candidate, record); dims derived on device (TCS:668-763). */
+int apo_dims_upload(apo_engine *e, const float *dims, uint32_t C, uint64_t T);
+int apo_dims_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,
+                      uint32_t agent_permille);
+int apo_dims_download(apo_engine *e, float *out, uint32_t c, uint64_t first, uint64_t n);
+/* Use a caller-owned device buffer (row pitch in evals, >= T rounded up to 4; 16-byte
+ * aligned base).  The engine never frees it. */
+int apo_dims_attach(apo_engine *e, uint64_t device_ptr, uint32_t C, uint64_t T, uint64_t pitch_evals);
+int apo_rollouts_upload(apo_engine *e, const apo_record *recs, uint32_t C, uint64_t T);
+int apo_rollouts_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,
+                          uint32_t agent_permille);
+int apo_rollouts_download(apo_engine *e, apo_record *out, uint32_t c, uint64_t first, uint64_t n);
+
+/* ---- scoring: score[c] = mean_t finalReward[c,t] (APO:550-553 per candidate), top-K
+ * (score desc, ties -> lower index; replaces the server-side beam selection consumed at
+ * APO:1138-1166) and, when a corpus is loaded and APO_SCORE_CORPUS is set, the corpus
+ * report (APO:498-625, 635-773; TCS:596-626). */
+#define APO_SRC_DIMS      0u
+#define APO_SRC_ROLLOUTS  1u
+#define APO_SCORE_CORPUS  0x1u   /* also run the 6-pattern scan over the corpus */
+#define APO_SCORE_RECIP   0x2u   /* finalReward = ws * (1/tw) from a LUT instead of ws / tw (<= 1 ulp apart) */
+typedef struct apo_score_opts {
+	uint32_t K;          /* beam width (top-K), 0..C */
+	uint32_t source;     /* APO_SRC_* */
+	uint32_t flags;      /* APO_SCORE_* */
+	uint32_t variant;    /* kernel variant, 0 = default (tuning / A-B only) */
+	uint64_t first;      /* window [first, first+count) of the record axis, first % 4 == 0; */
+	uint64_t count;      /* count == 0 -> all records */
+} apo_score_opts;
+/* scores[C] (-inf when a candidate has no non-null evaluation), counts[C], topk[K];
+ * any output pointer may be NULL. */
+int apo_score(apo_engine *e, const apo_score_opts *o, double *scores, uint64_t *counts,
+              int32_t *topk, apo_corpus_report *report);
+/* End to end from host memory without keeping the evaluations resident: streams
+ * dims[C][T][9] through a double-buffered device window (H2D overlapped with K1). */
+int apo_score_host(apo_engine *e, const apo_score_opts *o, const float *dims, uint32_t C, uint64_t T,
+                   double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report);
+int apo_last_timing(const apo_engine *e, apo_timing *out);
+/* Exact partial sums of the last apo_score: per candidate the integer
+ * sum_t rint(finalReward * 2^52) as three int64 limbs (value = l2*2^64 + l1*2^32 + l0)
+ * and the count; 4*C int64 words.  Order-independent, hence identical for any grid,
+ * shard or rank count. */
+int apo_debug_partials(apo_engine *e, int64_t *out, uint32_t C);
+
+/* ---- multi-GPU: the record axis is sharded across ranks (one process per GPU); one
+ * ncclAllReduce(sum,int64) of the packed partial vector joins the shards. */
+#define APO_UNIQUE_ID_BYTES 128
+int apo_comm_unique_id(uint8_t out[APO_UNIQUE_ID_BYTES]);
+int apo_comm_init(apo_engine *e, int nranks, int rank, const uint8_t id[APO_UNIQUE_ID_BYTES]);
+int apo_comm_destroy(apo_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

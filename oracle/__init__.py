@@ -71,13 +71,15 @@ def lib() -> C.CDLL:
         L.orc_score_records.argtypes = [vp, u32, u64, u64, dp, dp, vp]
         L.orc_score_dims_mt.argtypes = [vp, u32, u64, u64, dp, dp, vp, i32]
         L.orc_score_records_mt.argtypes = [vp, u32, u64, u64, dp, dp, vp, i32]
+        L.orc_score_dims_fx.argtypes = [vp, u32, u64, u64, dp, vp, vp, vp]
+        L.orc_score_records_fx.argtypes = [vp, u32, u64, u64, dp, vp, vp, vp]
         L.orc_topk.argtypes = [dp, u32, u32, vp]
         L.orc_report_build.argtypes = [vp, u64, u64, dp, C.POINTER(Report)]
         L.orc_gen_record.argtypes = [u64, u32, u32, u64, u32, vp]
         L.orc_gen_dims_row.argtypes = [u64, u32, u64, u32, vp]
         L.orc_gen_dims.argtypes = [u64, u32, u32, u64, u64, u64, u32, vp, i32]
         L.orc_gen_records.argtypes = [u64, u32, u32, u32, u64, u64, u64, u32, vp, i32]
-        for f in (L.orc_score_dims, L.orc_score_records, L.orc_score_dims_mt, L.orc_score_records_mt, L.orc_topk,
+        for f in (L.orc_score_dims_fx, L.orc_score_records_fx, L.orc_score_dims, L.orc_score_records, L.orc_score_dims_mt, L.orc_score_records_mt, L.orc_topk,
                   L.orc_report_build, L.orc_gen_record, L.orc_gen_dims_row, L.orc_gen_dims, L.orc_gen_records):
             f.restype = None
         _lib = L
@@ -145,6 +147,27 @@ def score_records(recs: np.ndarray, T: int | None = None, w=None, nthreads: int 
     else:
         lib().orc_score_records(_p(recs), Cn, T, pitch, _p(w), _p(s), _p(n))
     return s, n
+
+
+def score_dims_fx(dims: np.ndarray, T: int | None = None, w=None):
+    """Exact per-candidate integer sums sum_t rint(fr*2^52) (Python ints) and counts."""
+    dims = np.ascontiguousarray(dims, np.float32)
+    Cn, pitch, _ = dims.shape
+    T = pitch if T is None else T
+    w = weights() if w is None else np.ascontiguousarray(w, np.float64)
+    lo = np.empty(Cn, np.uint64); hi = np.empty(Cn, np.int64); n = np.empty(Cn, np.uint64)
+    lib().orc_score_dims_fx(_p(dims), Cn, T, pitch, _p(w), _p(lo), _p(hi), _p(n))
+    return [(int(h) << 64) + int(l) for l, h in zip(lo, hi)], [int(x) for x in n]
+
+
+def score_records_fx(recs: np.ndarray, T: int | None = None, w=None):
+    recs = np.ascontiguousarray(recs, RECORD_DTYPE)
+    Cn, pitch = recs.shape
+    T = pitch if T is None else T
+    w = weights() if w is None else np.ascontiguousarray(w, np.float64)
+    lo = np.empty(Cn, np.uint64); hi = np.empty(Cn, np.int64); n = np.empty(Cn, np.uint64)
+    lib().orc_score_records_fx(_p(recs), Cn, T, pitch, _p(w), _p(lo), _p(hi), _p(n))
+    return [(int(h) << 64) + int(l) for l, h in zip(lo, hi)], [int(x) for x in n]
 
 
 def topk(scores: np.ndarray, K: int) -> np.ndarray:

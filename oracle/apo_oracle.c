@@ -203,6 +203,34 @@ void orc_score_records(const orc_record *recs, uint32_t C, uint64_t T, uint64_t 
 	}
 }
 
+/* ---- exact fixed-point sums (mirrors the engine's accumulator definition) ---- */
+void orc_score_dims_fx(const float *dims, uint32_t C, uint64_t T, uint64_t pitch_evals,
+                       const double w[ORC_NDIM], uint64_t *lo, int64_t *hi, uint64_t *counts)
+{
+	for (uint32_t c = 0; c < C; c++) {
+		__int128 acc = 0; uint64_t n = 0;
+		const float *row0 = dims + (uint64_t)c * pitch_evals * ORC_NDIM;
+		for (uint64_t t = 0; t < T; t++) {
+			double fr;
+			if (orc_final_reward_f32(row0 + t * ORC_NDIM, w, &fr)) { acc += (__int128)llrint(fr * 4503599627370496.0); n++; }
+		}
+		lo[c] = (uint64_t)acc; hi[c] = (int64_t)(acc >> 64); counts[c] = n;
+	}
+}
+
+void orc_score_records_fx(const orc_record *recs, uint32_t C, uint64_t T, uint64_t pitch,
+                          const double w[ORC_NDIM], uint64_t *lo, int64_t *hi, uint64_t *counts)
+{
+	for (uint32_t c = 0; c < C; c++) {
+		__int128 acc = 0; uint64_t n = 0;
+		for (uint64_t t = 0; t < T; t++) {
+			double fr;
+			if (record_final(recs + (uint64_t)c * pitch + t, w, &fr)) { acc += (__int128)llrint(fr * 4503599627370496.0); n++; }
+		}
+		lo[c] = (uint64_t)acc; hi[c] = (int64_t)(acc >> 64); counts[c] = n;
+	}
+}
+
 /* ---- multi-threaded baseline: (candidate, T-slice) work items, merged in slice order ---- */
 typedef struct {
 	const float *dims; const orc_record *recs;
@@ -442,7 +470,8 @@ void orc_gen_record(uint64_t seed, uint32_t stream, uint32_t c, uint64_t t,
 	out->mode = mode;
 	out->pad = 0;
 	out->userMsgs = (uint16_t)userMsgs;
-	out->asstMsgs = (uint16_t)(llm < 65535 ? llm : 65535);
+	const uint32_t asst = llm + ((((h4 >> 46) & 15) == 0) ? 1u : 0u);   /* 1/16: an assistant span without an llm_call record */
+	out->asstMsgs = (uint16_t)(asst < 65535 ? asst : 65535);
 	out->toolCalls = toolCalls;
 	out->toolSucc = toolCalls - toolFail;
 	out->toolFail = toolFail;

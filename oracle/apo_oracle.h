@@ -76,6 +76,15 @@ void orc_score_dims(const float *dims, uint32_t C, uint64_t T, uint64_t pitch_ev
 void orc_score_records(const orc_record *recs, uint32_t C, uint64_t T, uint64_t pitch,
                        const double w[ORC_NDIM], double *scores, uint64_t *counts);
 
+/* Exact integer restatement of the engine's accumulator: per candidate
+ * sum_t rint(finalReward[c,t] * 2^52) as a 128-bit integer (lo, hi) + the non-null count.
+ * rint = round-half-even of the binary64 product (exact scaling by a power of two).
+ * Lets tests compare the GPU partial sums with NO tolerance. */
+void orc_score_dims_fx(const float *dims, uint32_t C, uint64_t T, uint64_t pitch_evals,
+                       const double w[ORC_NDIM], uint64_t *lo, int64_t *hi, uint64_t *counts);
+void orc_score_records_fx(const orc_record *recs, uint32_t C, uint64_t T, uint64_t pitch,
+                          const double w[ORC_NDIM], uint64_t *lo, int64_t *hi, uint64_t *counts);
+
 /* Multi-threaded variants for the CPU baseline: contiguous T-slices per thread,
  * per-slice sequential partials merged in slice order. */
 void orc_score_dims_mt(const float *dims, uint32_t C, uint64_t T, uint64_t pitch_evals,

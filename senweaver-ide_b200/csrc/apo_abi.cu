@@ -1,0 +1,570 @@
+// apo_abi.cu — the C ABI of libapo_b200.so (include/apo_b200.h): engine state, device
+// memory ownership, launch sequencing, the NCCL join of record-axis shards.
+//
+// One engine = one GPU = one host thread at a time.  No CPU fallback anywhere: every
+// compute entry point launches the sm_100a kernels of apo_kernels.cu or fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <string>
+
+#include "../../include/apo_b200.h"
+#include "apo_kernels.h"
+
+namespace {
+
+constexpr int ACC_PER_CAND = 4, CORP_FIXED = 68;
+inline uint64_t acc_words(uint32_t C, int nranks) { return (uint64_t)ACC_PER_CAND * C + CORP_FIXED + 18ull * nranks; }
+
+std::string g_create_error;
+
+// TCS:766-776 in push order d0..d8
+const double kDefaultWeights[APO_NDIM] = {0.25, 0.18, 0.12, 0.08, 0.05, 0.05, 0.08, 0.08, 0.11};
+
+// ---- NCCL through dlopen: the library loads (and every single-GPU path works) without it
+struct NcclId { char b[APO_UNIQUE_ID_BYTES]; };
+struct NcclApi {
+	void *h = nullptr;
+	int (*GetUniqueId)(NcclId *) = nullptr;
+	int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+	int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+	int (*CommDestroy)(void *) = nullptr;
+	const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool nccl_load(std::string &err) {
+	if (g_nccl.h) return true;
+	const char *names[] = {"libnccl.so.2", "libnccl.so"};
+	for (const char *n : names) {
+		g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+		if (g_nccl.h) break;
+	}
+	if (!g_nccl.h) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+	g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.h, "ncclGetUniqueId");
+	g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.h, "ncclCommInitRank");
+	g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.h, "ncclAllReduce");
+	g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.h, "ncclCommDestroy");
+	g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.h, "ncclGetErrorString");
+	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+		err = "libnccl is missing a required symbol"; g_nccl.h = nullptr; return false;
+	}
+	return true;
+}
+constexpr int kNcclInt64 = 4, kNcclSum = 0;
+
+template <class T>
+struct DevBuf {
+	T *p = nullptr; uint64_t cap = 0;   // capacity in elements
+	cudaError_t reserve(uint64_t n) {
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+		if (e == cudaSuccess) cap = n;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct apo_engine {
+	int device = 0, sm_count = 148;
+	cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+	std::string err;
+	apo::Weights W;
+	double lut_tw[512], lut_rc[512];
+	DevBuf<double> d_lut;          // [0,512) total weight, [512,1024) reciprocal
+
+	DevBuf<apo_record> corpus; uint64_t corpus_T = 0, corpus_base = 0;
+	DevBuf<float> dims; const float *dims_ptr = nullptr; uint32_t dims_C = 0; uint64_t dims_T = 0, dims_pitch = 0;
+	DevBuf<apo_record> roll; uint32_t roll_C = 0; uint64_t roll_T = 0, roll_pitch = 0;
+
+	DevBuf<long long> acc; uint32_t last_C = 0;
+	DevBuf<unsigned long long> misc;     // [0,18) example scratch, [18] ticket
+	DevBuf<uint8_t> result;              // scores | counts | topk | report
+	DevBuf<unsigned long long> keys, sel_key; DevBuf<int32_t> sel_idx;
+	uint8_t *h_result = nullptr; uint64_t h_result_cap = 0;
+	DevBuf<float> win[2]; cudaEvent_t win_free[2] = {nullptr, nullptr}, win_ready[2] = {nullptr, nullptr};
+	DevBuf<apo_record> batch_in; DevBuf<double> batch_out; DevBuf<uint32_t> batch_mask;
+
+	void *comm = nullptr; int nranks = 1, rank = 0;
+	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	apo_timing timing{};
+};
+
+namespace {
+
+int fail(apo_engine *e, int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+	if (e) e->err = buf; else g_create_error = buf;
+	return code;
+}
+#define CK(call)                                                                                    \
+	do {                                                                                            \
+		cudaError_t _c = (call);                                                                    \
+		if (_c != cudaSuccess) return fail(e, APO_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_c), __FILE__, __LINE__); \
+	} while (0)
+
+void build_luts(apo_engine *e) {
+	for (uint32_t m = 0; m < 512; m++) {
+		double tw = 0.0;                            // TCS:777-783: totalWeight += w in push order
+		for (int i = 0; i < APO_NDIM; i++) if (m & (1u << i)) tw += e->W.w[i];
+		if (!(tw > 0.0)) tw = 1.0;                  // finalReward stays null; kernels never count it
+		e->lut_tw[m] = tw;
+		e->lut_rc[m] = 1.0 / tw;
+	}
+}
+
+int upload_luts(apo_engine *e) {
+	CK(e->d_lut.reserve(1024));
+	CK(cudaMemcpyAsync(e->d_lut.p, e->lut_tw, 512 * 8, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaMemcpyAsync(e->d_lut.p + 512, e->lut_rc, 512 * 8, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return APO_OK;
+}
+
+struct ResultLayout { uint64_t off_scores, off_counts, off_topk, off_report, bytes; };
+ResultLayout result_layout(uint32_t C, uint32_t K) {
+	ResultLayout L;
+	L.off_scores = 0;
+	L.off_counts = L.off_scores + 8ull * C;
+	L.off_topk = L.off_counts + 8ull * C;
+	L.off_report = round_up(L.off_topk + 4ull * K, 16);
+	L.bytes = L.off_report + sizeof(apo_corpus_report);
+	return L;
+}
+
+int ensure_scratch(apo_engine *e, uint32_t C, uint32_t K) {
+	CK(e->acc.reserve(acc_words(C, e->nranks)));
+	CK(e->misc.reserve(32));
+	const ResultLayout L = result_layout(C, K);
+	CK(e->result.reserve(L.bytes));
+	CK(e->keys.reserve(C ? C : 1));
+	CK(e->sel_key.reserve(K ? K : 1));
+	CK(e->sel_idx.reserve(K ? K : 1));
+	if (e->h_result_cap < L.bytes) {
+		if (e->h_result) cudaFreeHost(e->h_result);
+		e->h_result = nullptr; e->h_result_cap = 0;
+		CK(cudaMallocHost((void **)&e->h_result, L.bytes));
+		e->h_result_cap = L.bytes;
+	}
+	return APO_OK;
+}
+
+apo::FinalizeParams make_fin(apo_engine *e, uint32_t C, uint32_t K, int with_corpus) {
+	const ResultLayout L = result_layout(C, K);
+	apo::FinalizeParams F;
+	F.acc = e->acc.p; F.C = C; F.K = K; F.nranks = e->nranks; F.with_corpus = with_corpus;
+	F.scores = (double *)(e->result.p + L.off_scores);
+	F.counts = (uint64_t *)(e->result.p + L.off_counts);
+	F.keys = e->keys.p; F.sel_key = e->sel_key.p; F.sel_idx = e->sel_idx.p;
+	F.topk = (int32_t *)(e->result.p + L.off_topk);
+	F.report = (apo_corpus_report *)(e->result.p + L.off_report);
+	return F;
+}
+
+// zero the accumulators, arm the example scratch and the ticket
+int begin_score(apo_engine *e, uint32_t C) {
+	CK(cudaMemsetAsync(e->acc.p, 0, acc_words(C, e->nranks) * 8, e->stream));
+	CK(cudaMemsetAsync(e->misc.p, 0xFF, 18 * 8, e->stream));
+	CK(cudaMemsetAsync(e->misc.p + 18, 0, 8, e->stream));
+	e->last_C = C;
+	return APO_OK;
+}
+
+// K2 (+fused finalize) / allreduce / K3, then bring the result block home
+int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *scores, uint64_t *counts, int32_t *topk,
+                 apo_corpus_report *report) {
+	const uint32_t K = o->K;
+	const bool with_corpus = (o->flags & APO_SCORE_CORPUS) && e->corpus_T > 0;
+	apo::FinalizeParams F = make_fin(e, C, K, with_corpus ? 1 : 0);
+	CK(cudaEventRecord(e->ev[1], e->stream));
+	bool finalized = false;
+	if (with_corpus) {
+		apo::K2Params P{};
+		P.recs = e->corpus.p; P.T = e->corpus_T; P.idx_base = e->corpus_base; P.C = C; P.rank = e->rank;
+		P.acc = e->acc.p; P.ex_scratch = e->misc.p; P.ticket = (unsigned int *)(e->misc.p + 18);
+		P.lut = e->d_lut.p; P.W = e->W; P.fuse_finalize = e->nranks == 1 ? 1 : 0; P.fin = F;
+		CK(apo::run_detect6(P, e->sm_count, e->stream));
+		e->timing.launches++;
+		finalized = P.fuse_finalize != 0;
+	}
+	CK(cudaEventRecord(e->ev[2], e->stream));
+	if (e->nranks > 1) {
+		const int rc = g_nccl.AllReduce(e->acc.p, e->acc.p, (size_t)acc_words(C, e->nranks), kNcclInt64, kNcclSum, e->comm, e->stream);
+		if (rc != 0) return fail(e, APO_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+		e->timing.launches++;
+	}
+	CK(cudaEventRecord(e->ev[3], e->stream));
+	if (!finalized) {
+		CK(apo::run_finalize(F, e->stream));
+		e->timing.launches++;
+	}
+	CK(cudaEventRecord(e->ev[4], e->stream));
+	const ResultLayout L = result_layout(C, K);
+	CK(cudaMemcpyAsync(e->h_result, e->result.p, L.bytes, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	if (scores) memcpy(scores, e->h_result + L.off_scores, 8ull * C);
+	if (counts) memcpy(counts, e->h_result + L.off_counts, 8ull * C);
+	if (topk && K) memcpy(topk, e->h_result + L.off_topk, 4ull * (K < C ? K : C));
+	if (report) {
+		if (with_corpus) memcpy(report, e->h_result + L.off_report, sizeof(apo_corpus_report));
+		else memset(report, 0, sizeof(apo_corpus_report));
+	}
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->timing.reward_ms = ms;
+	cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->timing.corpus_ms = ms;
+	cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->timing.allreduce_ms = ms;
+	cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->timing.finalize_ms = ms;
+	cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]); e->timing.total_ms = ms;
+	return APO_OK;
+}
+
+int check_opts(apo_engine *e, const apo_score_opts *o, uint32_t C, uint64_t T, uint64_t *first, uint64_t *count) {
+	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
+	if (o->K > C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, C);
+	if (o->first % 4) return fail(e, APO_E_ARG, "window start must be a multiple of 4");
+	if (o->first > T || (o->count && o->first + o->count > T)) return fail(e, APO_E_ARG, "window outside [0,%llu)", (unsigned long long)T);
+	*first = o->first;
+	*count = o->count ? o->count : T - o->first;
+	return APO_OK;
+}
+
+}  // namespace
+
+// =============================================================================== lifecycle
+extern "C" int apo_abi_version(void) { return APO_ABI_VERSION; }
+
+extern "C" int apo_create(int device, apo_engine **out) {
+	if (!out) return fail(nullptr, APO_E_ARG, "out is NULL");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t c = cudaGetDeviceCount(&n);
+	if (c != cudaSuccess || n == 0)
+		return fail(nullptr, APO_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", c != cudaSuccess ? cudaGetErrorString(c) : "device count is 0");
+	if (device < 0 || device >= n) return fail(nullptr, APO_E_ARG, "device %d out of range [0,%d)", device, n);
+	apo_engine *e = new (std::nothrow) apo_engine();
+	if (!e) return fail(nullptr, APO_E_NOMEM, "out of host memory");
+	e->device = device;
+	auto bail = [&](const char *what, cudaError_t ce) { fail(nullptr, APO_E_CUDA, "%s: %s", what, cudaGetErrorString(ce)); apo_destroy(e); return APO_E_CUDA; };
+	if ((c = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", c);
+	cudaDeviceProp prop;
+	if ((c = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", c);
+	if (prop.major != 10) { fail(nullptr, APO_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); apo_destroy(e); return APO_E_CUDA; }
+	e->sm_count = prop.multiProcessorCount;
+	if ((c = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", c);
+	if ((c = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", c);
+	e->stream = e->own_stream;
+	for (auto &ev : e->ev) if ((c = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", c);
+	for (int i = 0; i < 2; i++) {
+		if ((c = cudaEventCreateWithFlags(&e->win_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", c);
+		if ((c = cudaEventCreateWithFlags(&e->win_ready[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", c);
+	}
+	memcpy(e->W.w, kDefaultWeights, sizeof kDefaultWeights);
+	build_luts(e);
+	if (upload_luts(e) != APO_OK) { g_create_error = e->err; apo_destroy(e); return APO_E_CUDA; }
+	*out = e;
+	return APO_OK;
+}
+
+extern "C" void apo_destroy(apo_engine *e) {
+	if (!e) return;
+	cudaSetDevice(e->device);
+	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+	if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->misc.release();
+	e->result.release(); e->keys.release(); e->sel_key.release(); e->sel_idx.release();
+	e->win[0].release(); e->win[1].release(); e->batch_in.release(); e->batch_out.release(); e->batch_mask.release();
+	if (e->h_result) cudaFreeHost(e->h_result);
+	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+	for (int i = 0; i < 2; i++) { if (e->win_free[i]) cudaEventDestroy(e->win_free[i]); if (e->win_ready[i]) cudaEventDestroy(e->win_ready[i]); }
+	if (e->own_stream) cudaStreamDestroy(e->own_stream);
+	if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+	delete e;
+}
+
+extern "C" const char *apo_last_error(const apo_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int apo_set_stream(apo_engine *e, uint64_t cuda_stream) {
+	if (!e) return APO_E_ARG;
+	e->stream = cuda_stream ? (cudaStream_t)(uintptr_t)cuda_stream : e->own_stream;
+	return APO_OK;
+}
+
+extern "C" int apo_set_weights(apo_engine *e, const double w[APO_NDIM]) {
+	if (!e || !w) return fail(e, APO_E_ARG, "NULL argument");
+	for (int i = 0; i < APO_NDIM; i++) if (!(w[i] >= 0.0) || !std::isfinite(w[i])) return fail(e, APO_E_ARG, "weights must be finite and >= 0");
+	CK(cudaSetDevice(e->device));
+	memcpy(e->W.w, w, sizeof e->W.w);
+	build_luts(e);
+	return upload_luts(e);
+}
+
+extern "C" int apo_get_weights(const apo_engine *e, double w[APO_NDIM]) {
+	if (!e || !w) return APO_E_ARG;
+	memcpy(w, e->W.w, sizeof e->W.w);
+	return APO_OK;
+}
+
+// =============================================================================== single-trace path
+extern "C" int apo_reward_batch(apo_engine *e, const apo_record *recs, uint64_t n, double *dims, uint32_t *masks, double *finals) {
+	if (!e) return APO_E_ARG;
+	if (n == 0) return APO_OK;
+	if (!recs) return fail(e, APO_E_ARG, "recs is NULL");
+	CK(cudaSetDevice(e->device));
+	CK(e->batch_in.reserve(n));
+	CK(e->batch_out.reserve(n * (APO_NDIM + 1)));
+	CK(e->batch_mask.reserve(n));
+	CK(cudaMemcpyAsync(e->batch_in.p, recs, n * sizeof(apo_record), cudaMemcpyHostToDevice, e->stream));
+	CK(apo::run_reward_batch(e->batch_in.p, n, e->W, e->d_lut.p, e->batch_out.p, e->batch_mask.p, e->batch_out.p + n * APO_NDIM, e->stream));
+	if (dims) CK(cudaMemcpyAsync(dims, e->batch_out.p, n * APO_NDIM * 8, cudaMemcpyDeviceToHost, e->stream));
+	if (masks) CK(cudaMemcpyAsync(masks, e->batch_mask.p, n * 4, cudaMemcpyDeviceToHost, e->stream));
+	if (finals) CK(cudaMemcpyAsync(finals, e->batch_out.p + n * APO_NDIM, n * 8, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return APO_OK;
+}
+
+extern "C" int apo_reward_one(apo_engine *e, const apo_record *rec, double dims[APO_NDIM], uint32_t *mask, double *final_reward) {
+	return apo_reward_batch(e, rec, 1, dims, mask, final_reward);
+}
+
+// =============================================================================== corpus
+extern "C" int apo_corpus_upload(apo_engine *e, const apo_record *recs, uint64_t T, uint64_t idx_base) {
+	if (!e) return APO_E_ARG;
+	if (T && !recs) return fail(e, APO_E_ARG, "recs is NULL");
+	CK(cudaSetDevice(e->device));
+	CK(e->corpus.reserve(T ? T : 1));
+	if (T) CK(cudaMemcpyAsync(e->corpus.p, recs, T * sizeof(apo_record), cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	e->corpus_T = T; e->corpus_base = idx_base;
+	return APO_OK;
+}
+
+extern "C" int apo_corpus_generate(apo_engine *e, uint64_t seed, uint64_t t0, uint64_t T, uint32_t agent_permille) {
+	if (!e) return APO_E_ARG;
+	CK(cudaSetDevice(e->device));
+	CK(e->corpus.reserve(T ? T : 1));
+	CK(apo::run_gen_records(e->corpus.p, T, seed, 1u, 0, 1, t0, T, agent_permille, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	e->corpus_T = T; e->corpus_base = t0;
+	return APO_OK;
+}
+
+extern "C" int apo_corpus_download(apo_engine *e, apo_record *out, uint64_t first, uint64_t n) {
+	if (!e || !out) return fail(e, APO_E_ARG, "NULL argument");
+	if (first + n > e->corpus_T) return fail(e, APO_E_ARG, "range outside the corpus");
+	CK(cudaSetDevice(e->device));
+	CK(cudaMemcpyAsync(out, e->corpus.p + first, n * sizeof(apo_record), cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return APO_OK;
+}
+
+// =============================================================================== evaluations
+extern "C" int apo_dims_upload(apo_engine *e, const float *dims, uint32_t C, uint64_t T) {
+	if (!e) return APO_E_ARG;
+	if (C && T && !dims) return fail(e, APO_E_ARG, "dims is NULL");
+	CK(cudaSetDevice(e->device));
+	const uint64_t pitch = round_up(T ? T : 1, 32);
+	CK(e->dims.reserve((uint64_t)(C ? C : 1) * pitch * APO_NDIM));
+	if (C && T) {
+		// pad evaluations of every row are all-NaN = finalReward null
+		if (pitch != T) CK(cudaMemsetAsync(e->dims.p, 0xFF, (uint64_t)C * pitch * APO_NDIM * 4, e->stream));
+		CK(cudaMemcpy2DAsync(e->dims.p, pitch * APO_NDIM * 4, dims, T * APO_NDIM * 4, T * APO_NDIM * 4, C, cudaMemcpyHostToDevice, e->stream));
+	}
+	CK(cudaStreamSynchronize(e->stream));
+	e->dims_ptr = e->dims.p; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch;
+	return APO_OK;
+}
+
+extern "C" int apo_dims_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T, uint32_t agent_permille) {
+	if (!e) return APO_E_ARG;
+	CK(cudaSetDevice(e->device));
+	const uint64_t pitch = round_up(T ? T : 1, 32);
+	CK(e->dims.reserve((uint64_t)(C ? C : 1) * pitch * APO_NDIM));
+	if (pitch != T && C) CK(cudaMemsetAsync(e->dims.p, 0xFF, (uint64_t)C * pitch * APO_NDIM * 4, e->stream));
+	CK(apo::run_gen_dims(e->dims.p, pitch, seed, c0, C, t0, T, agent_permille, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	e->dims_ptr = e->dims.p; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch;
+	return APO_OK;
+}
+
+extern "C" int apo_dims_download(apo_engine *e, float *out, uint32_t c, uint64_t first, uint64_t n) {
+	if (!e || !out) return fail(e, APO_E_ARG, "NULL argument");
+	if (!e->dims_ptr || c >= e->dims_C || first + n > e->dims_T) return fail(e, APO_E_ARG, "range outside the evaluations");
+	CK(cudaSetDevice(e->device));
+	CK(cudaMemcpyAsync(out, e->dims_ptr + ((uint64_t)c * e->dims_pitch + first) * APO_NDIM, n * APO_NDIM * 4, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return APO_OK;
+}
+
+extern "C" int apo_dims_attach(apo_engine *e, uint64_t device_ptr, uint32_t C, uint64_t T, uint64_t pitch_evals) {
+	if (!e) return APO_E_ARG;
+	if (!device_ptr || device_ptr % 16) return fail(e, APO_E_ARG, "device pointer must be non-NULL and 16-byte aligned");
+	if (pitch_evals % 4 || pitch_evals < round_up(T, 4)) return fail(e, APO_E_ARG, "pitch must be a multiple of 4 evaluations and >= T rounded up to 4");
+	e->dims_ptr = (const float *)(uintptr_t)device_ptr; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch_evals;
+	return APO_OK;
+}
+
+extern "C" int apo_rollouts_upload(apo_engine *e, const apo_record *recs, uint32_t C, uint64_t T) {
+	if (!e) return APO_E_ARG;
+	if (C && T && !recs) return fail(e, APO_E_ARG, "recs is NULL");
+	CK(cudaSetDevice(e->device));
+	const uint64_t pitch = round_up(T ? T : 1, 4);
+	CK(e->roll.reserve((uint64_t)(C ? C : 1) * pitch));
+	if (C && T) {
+		if (pitch != T) CK(cudaMemsetAsync(e->roll.p, 0, (uint64_t)C * pitch * sizeof(apo_record), e->stream));   // VALID clear
+		CK(cudaMemcpy2DAsync(e->roll.p, pitch * sizeof(apo_record), recs, T * sizeof(apo_record), T * sizeof(apo_record), C, cudaMemcpyHostToDevice, e->stream));
+	}
+	CK(cudaStreamSynchronize(e->stream));
+	e->roll_C = C; e->roll_T = T; e->roll_pitch = pitch;
+	return APO_OK;
+}
+
+extern "C" int apo_rollouts_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T, uint32_t agent_permille) {
+	if (!e) return APO_E_ARG;
+	CK(cudaSetDevice(e->device));
+	const uint64_t pitch = round_up(T ? T : 1, 4);
+	CK(e->roll.reserve((uint64_t)(C ? C : 1) * pitch));
+	if (pitch != T && C) CK(cudaMemsetAsync(e->roll.p, 0, (uint64_t)C * pitch * sizeof(apo_record), e->stream));
+	CK(apo::run_gen_records(e->roll.p, pitch, seed, 2u, c0, C, t0, T, agent_permille, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	e->roll_C = C; e->roll_T = T; e->roll_pitch = pitch;
+	return APO_OK;
+}
+
+extern "C" int apo_rollouts_download(apo_engine *e, apo_record *out, uint32_t c, uint64_t first, uint64_t n) {
+	if (!e || !out) return fail(e, APO_E_ARG, "NULL argument");
+	if (!e->roll.p || c >= e->roll_C || first + n > e->roll_T) return fail(e, APO_E_ARG, "range outside the rollouts");
+	CK(cudaSetDevice(e->device));
+	CK(cudaMemcpyAsync(out, e->roll.p + (uint64_t)c * e->roll_pitch + first, n * sizeof(apo_record), cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return APO_OK;
+}
+
+// =============================================================================== scoring
+extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+	if (!e) return APO_E_ARG;
+	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
+	const bool raw = o->source == APO_SRC_ROLLOUTS;
+	if (o->source > APO_SRC_ROLLOUTS) return fail(e, APO_E_ARG, "unknown source %u", o->source);
+	if (raw ? (e->roll.p == nullptr || e->roll_C == 0) : (e->dims_ptr == nullptr || e->dims_C == 0))
+		return fail(e, APO_E_STATE, "no %s loaded", raw ? "rollouts" : "dims");
+	const uint32_t C = raw ? e->roll_C : e->dims_C;
+	const uint64_t T = raw ? e->roll_T : e->dims_T;
+	uint64_t first, count;
+	int rc = check_opts(e, o, C, T, &first, &count);
+	if (rc) return rc;
+	CK(cudaSetDevice(e->device));
+	if ((rc = ensure_scratch(e, C, o->K))) return rc;
+	e->timing = apo_timing{};
+	if ((rc = begin_score(e, C))) return rc;
+	CK(cudaEventRecord(e->ev[0], e->stream));
+	apo::K1Params P{};
+	const int row = raw ? 32 : 36;
+	const uint64_t pitch = raw ? e->roll_pitch : e->dims_pitch;
+	P.base = (raw ? (const uint8_t *)e->roll.p : (const uint8_t *)e->dims_ptr) + first * row;
+	P.pitch_bytes = pitch * row;
+	P.C = C; P.T = count; P.acc = e->acc.p;
+	const bool recip = (o->flags & APO_SCORE_RECIP) != 0;
+	P.lut = e->d_lut.p + (recip ? 512 : 0);
+	P.W = e->W;
+	if (count) { CK(apo::run_reward9(P, row, (int)o->variant, recip, e->sm_count, e->stream)); e->timing.launches++; }
+	return finish_score(e, o, C, scores, counts, topk, report);
+}
+
+extern "C" int apo_score_host(apo_engine *e, const apo_score_opts *o, const float *dims, uint32_t C, uint64_t T,
+                              double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+	if (!e) return APO_E_ARG;
+	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
+	if (!dims || C == 0) return fail(e, APO_E_ARG, "dims is NULL or C == 0");
+	if (o->K > C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, C);
+	if (o->first || o->count) return fail(e, APO_E_ARG, "windows are not supported by apo_score_host");
+	CK(cudaSetDevice(e->device));
+	int rc;
+	if ((rc = ensure_scratch(e, C, o->K))) return rc;
+	// window of ~256 MB per buffer, a multiple of the K1 tile so chunks never split a tile
+	const int tile = apo::k1_tile_evals(36, (int)o->variant);
+	uint64_t Tc = (256ull << 20) / ((uint64_t)C * 36);
+	Tc = Tc / tile * tile;
+	if (Tc < (uint64_t)tile) Tc = tile;
+	if (Tc > round_up(T, tile)) Tc = round_up(T ? T : 1, tile);
+	for (int i = 0; i < 2; i++) CK(e->win[i].reserve((uint64_t)C * Tc * APO_NDIM));
+	e->timing = apo_timing{};
+	if ((rc = begin_score(e, C))) return rc;
+	CK(cudaEventRecord(e->ev[0], e->stream));
+	const bool recip = (o->flags & APO_SCORE_RECIP) != 0;
+	int nchunk = 0;
+	for (uint64_t t0 = 0; t0 < T; t0 += Tc, nchunk++) {
+		const int b = nchunk & 1;
+		const uint64_t n = T - t0 < Tc ? T - t0 : Tc;
+		if (nchunk >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->win_free[b], 0));
+		CK(cudaMemcpy2DAsync(e->win[b].p, Tc * APO_NDIM * 4, dims + t0 * APO_NDIM, T * APO_NDIM * 4, n * APO_NDIM * 4, C, cudaMemcpyHostToDevice, e->copy_stream));
+		CK(cudaEventRecord(e->win_ready[b], e->copy_stream));
+		CK(cudaStreamWaitEvent(e->stream, e->win_ready[b], 0));
+		apo::K1Params P{};
+		P.base = (const uint8_t *)e->win[b].p; P.pitch_bytes = Tc * 36; P.C = C; P.T = n; P.acc = e->acc.p;
+		P.lut = e->d_lut.p + (recip ? 512 : 0); P.W = e->W;
+		CK(apo::run_reward9(P, 36, (int)o->variant, recip, e->sm_count, e->stream));
+		e->timing.launches++;
+		CK(cudaEventRecord(e->win_free[b], e->stream));
+	}
+	return finish_score(e, o, C, scores, counts, topk, report);
+}
+
+extern "C" int apo_last_timing(const apo_engine *e, apo_timing *out) {
+	if (!e || !out) return APO_E_ARG;
+	*out = e->timing;
+	return APO_OK;
+}
+
+extern "C" int apo_debug_partials(apo_engine *e, int64_t *out, uint32_t C) {
+	if (!e || !out) return fail(e, APO_E_ARG, "NULL argument");
+	if (C != e->last_C || !e->acc.p) return fail(e, APO_E_STATE, "no scoring call with C=%u to read back", C);
+	CK(cudaSetDevice(e->device));
+	CK(cudaMemcpyAsync(out, e->acc.p, 8ull * ACC_PER_CAND * C, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return APO_OK;
+}
+
+// =============================================================================== multi-GPU
+extern "C" int apo_comm_unique_id(uint8_t out[APO_UNIQUE_ID_BYTES]) {
+	if (!out) return fail(nullptr, APO_E_ARG, "out is NULL");
+	std::string err;
+	if (!nccl_load(err)) return fail(nullptr, APO_E_NCCL, "%s", err.c_str());
+	NcclId id;
+	const int rc = g_nccl.GetUniqueId(&id);
+	if (rc != 0) return fail(nullptr, APO_E_NCCL, "ncclGetUniqueId failed (%d)", rc);
+	memcpy(out, id.b, APO_UNIQUE_ID_BYTES);
+	return APO_OK;
+}
+
+extern "C" int apo_comm_init(apo_engine *e, int nranks, int rank, const uint8_t id[APO_UNIQUE_ID_BYTES]) {
+	if (!e || !id) return fail(e, APO_E_ARG, "NULL argument");
+	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(e, APO_E_ARG, "bad rank %d of %d", rank, nranks);
+	CK(cudaSetDevice(e->device));
+	if (e->comm) { g_nccl.CommDestroy(e->comm); e->comm = nullptr; }
+	e->nranks = 1; e->rank = 0;
+	if (nranks == 1) return APO_OK;
+	std::string err;
+	if (!nccl_load(err)) return fail(e, APO_E_NCCL, "%s", err.c_str());
+	NcclId nid; memcpy(nid.b, id, APO_UNIQUE_ID_BYTES);
+	void *comm = nullptr;
+	const int rc = g_nccl.CommInitRank(&comm, nranks, nid, rank);
+	if (rc != 0) return fail(e, APO_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+	e->comm = comm; e->nranks = nranks; e->rank = rank;
+	return APO_OK;
+}
+
+extern "C" int apo_comm_destroy(apo_engine *e) {
+	if (!e) return APO_E_ARG;
+	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+	e->comm = nullptr; e->nranks = 1; e->rank = 0;
+	return APO_OK;
+}

@@ -1,0 +1,268 @@
+// apo_device.cuh — device-side building blocks shared by the kernels of libapo_b200.
+//
+// Reward arithmetic mirrors the reference statement by statement with explicit
+// round-to-nearest binary64 intrinsics (no FMA contraction), so per-evaluation results
+// are bit-identical to a JS `number` evaluation of
+//   TCS = src/vs/workbench/contrib/senweaver/common/traceCollectorService.ts :668-788.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/apo_b200.h"
+#include "apo_kernels.h"
+
+namespace apo {
+
+// ---------------------------------------------------------------- accumulator vector
+// One int64 vector holds every partial of a scoring call so that a single
+// ncclAllReduce(sum,int64) joins record-axis shards.  Fixed-point sums use 2^-52 units
+// kept as three limbs (value = l2*2^64 + l1*2^32 + l0): integer addition is associative,
+// so results do not depend on grid size, scheduling, shard or rank count.
+constexpr int ACC_PER_CAND = 4;            // l0,l1,l2,count
+constexpr int CORP_REWARD  = 0;            // l0,l1,l2,count
+constexpr int CORP_DIM     = 4;            // 9 x (l0,l1,l2,count)
+constexpr int CORP_TALLY   = 40;           // good,bad,none
+constexpr int CORP_MODE    = 43;           // [5][3] total,good,bad
+constexpr int CORP_PAT     = 58;           // [6]
+constexpr int CORP_TOOL    = 64;           // calls,succ,fail
+constexpr int CORP_NREC    = 67;
+constexpr int CORP_EX      = 68;           // [nranks][6][3] (index+1, 0 = none); rank r fills its own slot
+constexpr int CORP_FIXED   = 68;
+__host__ __device__ inline uint64_t acc_words(uint32_t C, int nranks) { return (uint64_t)ACC_PER_CAND * C + CORP_FIXED + 18ull * nranks; }
+
+constexpr double FX_SCALE = 4503599627370496.0;        // 2^52
+constexpr double FX_INV   = 1.0 / 4503599627370496.0;  // 2^-52
+
+// ---------------------------------------------------------------- 128-bit lane accumulator
+struct Acc128 {
+	unsigned long long lo; long long hi;
+	__device__ __forceinline__ void zero() { lo = 0; hi = 0; }
+	__device__ __forceinline__ void add(long long x) {
+		const unsigned long long n = lo + (unsigned long long)x;
+		hi += (x >> 63) + (long long)(n < lo);
+		lo = n;
+	}
+};
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// Warp-reduce a lane accumulator into three limb sums and add them to acc[0..2] (global atomics).
+__device__ __forceinline__ void flush_acc128(const Acc128 &a, long long *dst, int lane) {
+	const unsigned long long s0 = warp_sum_u64(a.lo & 0xffffffffull);
+	const unsigned long long s1 = warp_sum_u64(a.lo >> 32);
+	const unsigned long long s2 = warp_sum_u64((unsigned long long)a.hi);
+	if (lane == 0) {
+		if (s0) atomicAdd((unsigned long long *)dst + 0, s0);
+		if (s1) atomicAdd((unsigned long long *)dst + 1, s1);
+		if (s2) atomicAdd((unsigned long long *)dst + 2, s2);
+	}
+}
+
+// limbs -> binary64 (one rounding of the 128-bit magnitude, then exact scaling by 2^-52)
+__device__ inline double limbs_to_double(const long long *l) {
+	__int128 v = ((__int128)l[2] << 64) + ((__int128)l[1] << 32) + (__int128)l[0];
+	const bool neg = v < 0;
+	unsigned __int128 m = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+	const unsigned long long hi = (unsigned long long)(m >> 64), lo = (unsigned long long)m;
+	double d;
+	if (hi == 0) d = (double)lo;
+	else {
+		// keep 64 significant bits + sticky, then a single correctly rounded conversion
+		const int sh = 64 - __clzll((long long)hi);
+		unsigned long long top = (unsigned long long)(m >> sh);
+		const bool sticky = (m & ((((unsigned __int128)1) << sh) - 1)) != 0;
+		top |= sticky ? 1ull : 0ull;
+		d = ldexp((double)top, sh);
+	}
+	d *= FX_INV;
+	return neg ? -d : d;
+}
+
+// ---------------------------------------------------------------- TCS:668-763 on device
+// dims[i] is valid only where bit i of the returned mask is set.
+__device__ __forceinline__ uint32_t reward_dims(const apo_record &r, double dims[APO_NDIM]) {
+	uint32_t mask = 3u;
+	const bool agent = r.mode == 2;                                   // TCS:673-674
+	const bool err = (r.flags & APO_F_ERRORS) != 0;
+	const bool ended = (r.flags & APO_F_ENDED) != 0;
+	dims[0] = r.feedback == 1 ? 1.0 : (r.feedback == 2 ? -1.0 : 0.0); // TCS:677-678
+	double comp = 0.5;                                                // TCS:682-691
+	if (ended && !err) comp = 0.8;
+	if (err) comp = -0.5;
+	if (r.feedback == 1) comp = 1.0;
+	dims[1] = comp;
+#pragma unroll
+	for (int i = 2; i < APO_NDIM; i++) dims[i] = 0.0;
+	if (r.toolCalls > 0) {                                            // TCS:695
+		const double total = (double)r.toolCalls;
+		const double rate = __ddiv_rn((double)r.toolSucc, total);     // TCS:697
+		dims[2] = __dadd_rn(__dmul_rn(rate, 2.0), -1.0);              // TCS:698
+		const uint32_t sev = agent ? 5u : 3u, mod = agent ? 3u : 2u, mnr = agent ? 2u : 1u;   // TCS:702-704
+		dims[3] = r.toolFail >= sev ? -1.0 : (r.toolFail >= mod ? -0.5 : (r.toolFail >= mnr ? -0.2 : 1.0));
+		const uint32_t exc = agent ? 8u : 3u, good = agent ? 15u : 6u, fair = agent ? 25u : 10u; // TCS:711-713
+		dims[4] = r.toolCalls > fair ? -0.8 : (r.toolCalls > good ? -0.3 : (r.toolCalls > exc ? 0.3 : 1.0));
+		mask |= 0x1cu;
+		const double dur = (double)r.toolDurMs;
+		if (dur > 0.0) {                                              // TCS:721-728
+			const double avg = __ddiv_rn(dur, total);
+			dims[5] = avg > 10000.0 ? -0.5 : (avg > 3000.0 ? 0.0 : (avg > 1000.0 ? 0.5 : 1.0));
+			mask |= 0x20u;
+		}
+	}
+	if (r.llmCalls > 0) {                                             // TCS:733-736
+		const double thr = agent ? 3.0 : 1.0;
+		double over = __dadd_rn((double)r.llmCalls, -thr);
+		if (!(over > 0.0)) over = 0.0;
+		double ef = __dadd_rn(1.0, -__dmul_rn(over, 0.4));
+		if (ef < -1.0) ef = -1.0;
+		dims[6] = ef;
+		mask |= 0x40u;
+	}
+	if (r.tokens > 0) {                                               // TCS:740-748
+		const uint32_t exc = agent ? 5000u : 2000u, good = agent ? 15000u : 5000u, fair = agent ? 30000u : 10000u;
+		dims[7] = r.tokens > fair ? -0.5 : (r.tokens > good ? 0.0 : (r.tokens > exc ? 0.5 : 1.0));
+		mask |= 0x80u;
+	}
+	const uint32_t turns = r.userMsgs < r.asstMsgs ? r.userMsgs : r.asstMsgs;   // TCS:752-754
+	if (turns > 0) {                                                  // TCS:755-762
+		const uint32_t thr = agent ? 3u : 2u;
+		dims[8] = turns > thr * 3 ? -0.8 : (turns > thr * 2 ? -0.3 : (turns > thr ? 0.3 : 1.0));
+		mask |= 0x100u;
+	}
+	return mask;
+}
+
+// TCS:777-784.  lut[mask] = sum of the present weights added in push order (host-built,
+// same sequential binary64 adds); lut[0] = 1 so an empty mask yields 0 without a NaN.
+// dims of absent dimensions must be +0.0 (adding +0.0*w leaves the running sum unchanged).
+template <bool RECIP>
+__device__ __forceinline__ double final_reward(const double dims[APO_NDIM], uint32_t mask, const Weights &W,
+                                               const double *lut) {
+	double ws = 0.0;
+#pragma unroll
+	for (int i = 0; i < APO_NDIM; i++) ws = __dadd_rn(ws, __dmul_rn(dims[i], W.w[i]));
+	const double tw = lut[mask];
+	return RECIP ? __dmul_rn(ws, tw) : __ddiv_rn(ws, tw);
+}
+
+__device__ __forceinline__ long long to_fx(double v) { return __double2ll_rn(v * FX_SCALE); }
+
+// ---------------------------------------------------------------- synthetic generator
+// Build-defined; integer-only so host restatements agree bit for bit.
+// Spec: DESIGN.md "Generator".
+constexpr unsigned long long GOLD = 0x9E3779B97F4A7C15ull;
+constexpr uint32_t STREAM_CORPUS = 1, STREAM_ROLLOUT = 2;
+
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+	z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+	z ^= z >> 27; z *= 0x94D049BB133111EBull;
+	z ^= z >> 31;
+	return z;
+}
+__device__ __forceinline__ uint32_t ctz64(unsigned long long x) { return (uint32_t)(__ffsll((long long)x) - 1); }
+
+// key0 = mix64(mix64(seed ^ stream*GOLD) ^ mix64((c+1)*GOLD)) is hoisted by callers.
+__device__ __forceinline__ unsigned long long gen_key(unsigned long long seed, uint32_t stream, uint32_t c) {
+	return mix64(mix64(seed ^ ((unsigned long long)stream * GOLD)) ^ mix64(((unsigned long long)c + 1) * GOLD));
+}
+__device__ __forceinline__ uint32_t gen_quality(unsigned long long seed, uint32_t stream, uint32_t c) {
+	return stream == STREAM_CORPUS ? 512u : (uint32_t)(mix64(seed ^ 0xC0FFEEull ^ ((unsigned long long)c * GOLD)) & 1023);
+}
+
+__device__ __forceinline__ apo_record gen_record(unsigned long long key, uint32_t qc, unsigned long long t,
+                                                 uint32_t agent_permille) {
+	const unsigned long long base = key + t * GOLD;
+	const unsigned long long h1 = mix64(base + GOLD), h2 = mix64(base + 2 * GOLD);
+	const unsigned long long h3 = mix64(base + 3 * GOLD), h4 = mix64(base + 4 * GOLD);
+	const uint32_t r = (uint32_t)(h1 & 1023);
+	const uint32_t pgood = 192 + (qc >> 2), pbad = 256 - (qc >> 3);
+	const uint32_t feedback = r < pgood ? 1u : (r < pgood + pbad ? 2u : 0u);
+	const bool err = ((h1 >> 10) & 1023) < 102;
+	const bool ended = ((h1 >> 20) & 1023) < 973;
+	uint32_t mode;
+	if (((h1 >> 30) & 1023) < agent_permille) mode = 2;
+	else {
+		const uint32_t k = (uint32_t)((h1 >> 40) & 15);
+		mode = k < 10 ? 1u : (k < 12 ? 3u : (k < 14 ? 4u : 0u));
+	}
+	const bool agent = mode == 2;
+	uint32_t tool = 0, fail = 0;
+	float dur = 0.0f;
+	if (!(((h1 >> 44) & 1023) < 307)) {
+		const uint32_t g = ctz64(h2 | (1ull << 20));
+		tool = agent ? 1 + (uint32_t)((h2 >> 21) & 15) + g : 1 + g;
+		const uint32_t n = tool < 16 ? tool : 16;
+		for (uint32_t i = 0; i < n; i++) fail += (((h3 >> (4 * i)) & 15) == 0) ? 1u : 0u;
+		if (((h2 >> 25) & 15) != 0) {
+			const uint32_t e = (uint32_t)((h2 >> 29) & 15) % 10;
+			const uint32_t basems = 50u << e;
+			const uint32_t frac = (uint32_t)((h2 >> 33) & 4095);
+			const uint32_t avg = basems + ((basems * frac) >> 12);
+			dur = (float)(avg * tool);
+		}
+	}
+	uint32_t llm = 0;
+	if (((h2 >> 45) & 31) != 0) llm = 1 + ctz64((h2 >> 50) | (1ull << 13)) + (agent ? (uint32_t)((h2 >> 48) & 3) : 0u);
+	uint32_t tokens = 0;
+	if (!((h4 & 1023) < 205)) {
+		const uint32_t e = (uint32_t)((h4 >> 10) & 15) % 9;
+		const uint32_t b = 200u << e;
+		const uint32_t f = (uint32_t)((h4 >> 14) & 4095);
+		tokens = b + ((b * f) >> 12);
+	}
+	uint32_t user = 0;
+	if (((h4 >> 40) & 63) != 0) user = 1 + ctz64((h4 >> 26) | (1ull << 12));
+	apo_record o;
+	o.feedback = (uint8_t)feedback;
+	o.flags = (uint8_t)((err ? APO_F_ERRORS : 0u) | (ended ? APO_F_ENDED : 0u) |
+	                    ((ended || feedback) ? APO_F_VALID : 0u) | (fail > 0 ? APO_F_FAILSPAN : 0u));
+	o.mode = (uint8_t)mode;
+	o.pad = 0;
+	o.userMsgs = (uint16_t)user;
+	const uint32_t asst = llm + ((((h4 >> 46) & 15) == 0) ? 1u : 0u);
+	o.asstMsgs = (uint16_t)(asst < 65535u ? asst : 65535u);
+	o.toolCalls = tool; o.toolSucc = tool - fail; o.toolFail = fail;
+	o.llmCalls = llm; o.tokens = tokens; o.toolDurMs = dur;
+	return o;
+}
+
+// ---------------------------------------------------------------- mbarrier / bulk-copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "WAIT_%=:\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+	    "@p bra DONE_%=;\n\t"
+	    "bra WAIT_%=;\n\t"
+	    "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+	asm volatile(
+	    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+	        smem_u32(dst)),
+	    "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+	    : "memory");
+}
+
+}  // namespace apo

@@ -1,0 +1,308 @@
+"""ctypes binding of libapo_b200.so (include/apo_b200.h) — the host side of the C ABI.
+
+This module is plumbing only: it loads the in-tree shared library, declares every entry
+point of the header and wraps the engine handle in a small class that moves numpy buffers
+across the boundary.  There is no CPU path here: if the library is missing or no B200 is
+visible, construction raises (`ApoError`), it never falls back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libapo_b200.so")
+
+NDIM, NPAT, NMODE = 9, 6, 5
+SRC_DIMS, SRC_ROLLOUTS = 0, 1
+SCORE_CORPUS, SCORE_RECIP = 0x1, 0x2
+F_ERRORS, F_ENDED, F_VALID, F_FAILSPAN = 0x01, 0x02, 0x08, 0x10
+UNIQUE_ID_BYTES = 128
+
+DIM_NAMES = (
+    "user_feedback", "task_completion", "tool_success_rate", "tool_call_reliability",
+    "tool_call_efficiency", "tool_duration_efficiency", "response_efficiency",
+    "token_efficiency", "conversation_efficiency",
+)
+MODE_NAMES = ("unknown", "normal", "agent", "gather", "designer")
+
+RECORD_DTYPE = np.dtype([
+    ("feedback", "u1"), ("flags", "u1"), ("mode", "u1"), ("pad", "u1"),
+    ("userMsgs", "<u2"), ("asstMsgs", "<u2"),
+    ("toolCalls", "<u4"), ("toolSucc", "<u4"), ("toolFail", "<u4"),
+    ("llmCalls", "<u4"), ("tokens", "<u4"), ("toolDurMs", "<f4"),
+])
+assert RECORD_DTYPE.itemsize == 32
+
+
+class Pattern(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("flag", C.c_uint8), ("severity", C.c_uint8), ("pad", C.c_uint8 * 6),
+                ("examples", C.c_int64 * 3)]
+
+
+class DimStat(C.Structure):
+    _fields_ = [("sum", C.c_double), ("count", C.c_uint64), ("avg", C.c_double),
+                ("low_flag", C.c_uint8), ("low_severity", C.c_uint8), ("sugg_flag", C.c_uint8),
+                ("sugg_priority", C.c_uint8), ("pad", C.c_uint8 * 4)]
+
+
+class CorpusReport(C.Structure):
+    _fields_ = [("total", C.c_uint64), ("good", C.c_uint64), ("bad", C.c_uint64), ("none", C.c_uint64),
+                ("goodRate", C.c_double), ("byMode", (C.c_uint64 * 3) * NMODE), ("byModeGoodRate", C.c_double * NMODE),
+                ("withReward", C.c_uint64), ("rewardSum", C.c_double), ("avgReward", C.c_double),
+                ("dim", DimStat * NDIM), ("pat", Pattern * NPAT),
+                ("toolCalls", C.c_uint64), ("toolSucc", C.c_uint64), ("toolFail", C.c_uint64),
+                ("toolSuccessRate", C.c_double)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("reward_ms", C.c_float), ("corpus_ms", C.c_float), ("allreduce_ms", C.c_float),
+                ("finalize_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("pad", C.c_uint32)]
+
+
+class ScoreOpts(C.Structure):
+    _fields_ = [("K", C.c_uint32), ("source", C.c_uint32), ("flags", C.c_uint32), ("variant", C.c_uint32),
+                ("first", C.c_uint64), ("count", C.c_uint64)]
+
+
+class ApoError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"apo_b200 error {code}: {msg}")
+        self.code = code
+
+
+# every symbol include/apo_b200.h declares (tests/test_abi_symbols.py checks the .so against this list)
+ABI_SYMBOLS = (
+    "apo_abi_version", "apo_create", "apo_destroy", "apo_last_error", "apo_set_stream", "apo_set_weights",
+    "apo_get_weights", "apo_reward_batch", "apo_reward_one", "apo_corpus_upload", "apo_corpus_generate",
+    "apo_corpus_download", "apo_dims_upload", "apo_dims_generate", "apo_dims_download", "apo_dims_attach",
+    "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_score", "apo_score_host",
+    "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy",
+)
+
+
+def build_library(force: bool = False) -> str:
+    """Compile csrc/ for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in ("apo_kernels.cu", "apo_abi.cu", "apo_kernels.h", "apo_device.cuh")]
+    srcs.append(os.path.join(_HERE, "..", "include", "apo_b200.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", csrc], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ApoError(-2, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.apo_abi_version.restype = i32
+    L.apo_create.argtypes = [i32, C.POINTER(vp)]
+    L.apo_destroy.argtypes = [vp]
+    L.apo_destroy.restype = None
+    L.apo_last_error.argtypes = [vp]
+    L.apo_last_error.restype = C.c_char_p
+    L.apo_set_stream.argtypes = [vp, u64]
+    L.apo_set_weights.argtypes = [vp, vp]
+    L.apo_get_weights.argtypes = [vp, vp]
+    L.apo_reward_batch.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.apo_reward_one.argtypes = [vp, vp, vp, vp, vp]
+    L.apo_corpus_upload.argtypes = [vp, vp, u64, u64]
+    L.apo_corpus_generate.argtypes = [vp, u64, u64, u64, u32]
+    L.apo_corpus_download.argtypes = [vp, vp, u64, u64]
+    L.apo_dims_upload.argtypes = [vp, vp, u32, u64]
+    L.apo_dims_generate.argtypes = [vp, u64, u32, u32, u64, u64, u32]
+    L.apo_dims_download.argtypes = [vp, vp, u32, u64, u64]
+    L.apo_dims_attach.argtypes = [vp, u64, u32, u64, u64]
+    L.apo_rollouts_upload.argtypes = [vp, vp, u32, u64]
+    L.apo_rollouts_generate.argtypes = [vp, u64, u32, u32, u64, u64, u32]
+    L.apo_rollouts_download.argtypes = [vp, vp, u32, u64, u64]
+    L.apo_score.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp]
+    L.apo_score_host.argtypes = [vp, C.POINTER(ScoreOpts), vp, u32, u64, vp, vp, vp, vp]
+    L.apo_last_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.apo_debug_partials.argtypes = [vp, vp, u32]
+    L.apo_comm_unique_id.argtypes = [vp]
+    L.apo_comm_init.argtypes = [vp, i32, i32, vp]
+    L.apo_comm_destroy.argtypes = [vp]
+    for name in ABI_SYMBOLS:
+        f = getattr(L, name)
+        if name not in ("apo_destroy", "apo_last_error"):
+            f.restype = i32
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class ScoreResult:
+    __slots__ = ("scores", "counts", "topk", "report", "timing")
+
+    def __init__(self, scores, counts, topk, report, timing):
+        self.scores, self.counts, self.topk, self.report, self.timing = scores, counts, topk, report, timing
+
+
+class Engine:
+    """One GPU, one handle.  Mirrors the C ABI one to one."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.apo_create(device, C.byref(h))
+        if rc != 0:
+            raise ApoError(rc, (self._L.apo_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    # -- plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.apo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise ApoError(rc, (self._L.apo_last_error(self._h) or b"").decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._L.apo_set_stream(self._h, cuda_stream))
+
+    def set_weights(self, w):
+        w = np.ascontiguousarray(w, np.float64)
+        assert w.shape == (NDIM,)
+        self._ck(self._L.apo_set_weights(self._h, _p(w)))
+
+    def get_weights(self) -> np.ndarray:
+        w = np.empty(NDIM, np.float64)
+        self._ck(self._L.apo_get_weights(self._h, _p(w)))
+        return w
+
+    # -- single-trace path (TCS:668-788)
+    def reward_batch(self, recs: np.ndarray):
+        recs = np.ascontiguousarray(recs, RECORD_DTYPE).reshape(-1)
+        n = recs.shape[0]
+        dims = np.empty((n, NDIM), np.float64)
+        masks = np.empty(n, np.uint32)
+        finals = np.empty(n, np.float64)
+        self._ck(self._L.apo_reward_batch(self._h, _p(recs), n, _p(dims), _p(masks), _p(finals)))
+        return dims, masks, finals
+
+    # -- corpus
+    def corpus_upload(self, recs: np.ndarray, idx_base: int = 0):
+        recs = np.ascontiguousarray(recs, RECORD_DTYPE).reshape(-1)
+        self._ck(self._L.apo_corpus_upload(self._h, _p(recs), recs.shape[0], idx_base))
+
+    def corpus_generate(self, seed: int, t0: int, T: int, agent_permille: int = 300):
+        self._ck(self._L.apo_corpus_generate(self._h, seed, t0, T, agent_permille))
+
+    def corpus_download(self, first: int, n: int) -> np.ndarray:
+        out = np.empty(n, RECORD_DTYPE)
+        self._ck(self._L.apo_corpus_download(self._h, _p(out), first, n))
+        return out
+
+    # -- evaluations
+    def dims_upload(self, dims: np.ndarray):
+        dims = np.ascontiguousarray(dims, np.float32)
+        Cn, T, nd = dims.shape
+        assert nd == NDIM
+        self._ck(self._L.apo_dims_upload(self._h, _p(dims), Cn, T))
+
+    def dims_generate(self, seed: int, c0: int, Cn: int, t0: int, T: int, agent_permille: int = 300):
+        self._ck(self._L.apo_dims_generate(self._h, seed, c0, Cn, t0, T, agent_permille))
+
+    def dims_download(self, c: int, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, NDIM), np.float32)
+        self._ck(self._L.apo_dims_download(self._h, _p(out), c, first, n))
+        return out
+
+    def dims_attach(self, device_ptr: int, Cn: int, T: int, pitch_evals: int):
+        self._ck(self._L.apo_dims_attach(self._h, device_ptr, Cn, T, pitch_evals))
+
+    def rollouts_upload(self, recs: np.ndarray):
+        recs = np.ascontiguousarray(recs, RECORD_DTYPE)
+        Cn, T = recs.shape
+        self._ck(self._L.apo_rollouts_upload(self._h, _p(recs), Cn, T))
+
+    def rollouts_generate(self, seed: int, c0: int, Cn: int, t0: int, T: int, agent_permille: int = 300):
+        self._ck(self._L.apo_rollouts_generate(self._h, seed, c0, Cn, t0, T, agent_permille))
+
+    def rollouts_download(self, c: int, first: int, n: int) -> np.ndarray:
+        out = np.empty(n, RECORD_DTYPE)
+        self._ck(self._L.apo_rollouts_download(self._h, _p(out), c, first, n))
+        return out
+
+    # -- scoring
+    def _opts(self, K, source, corpus, recip, variant, first, count) -> ScoreOpts:
+        return ScoreOpts(K, source, (SCORE_CORPUS if corpus else 0) | (SCORE_RECIP if recip else 0), variant, first, count)
+
+    def score(self, Cn: int, K: int, source: int = SRC_DIMS, corpus: bool = False, recip: bool = False,
+              variant: int = 0, first: int = 0, count: int = 0) -> ScoreResult:
+        o = self._opts(K, source, corpus, recip, variant, first, count)
+        scores = np.empty(Cn, np.float64)
+        counts = np.empty(Cn, np.uint64)
+        topk = np.empty(K, np.int32)
+        rep = CorpusReport() if corpus else None
+        self._ck(self._L.apo_score(self._h, C.byref(o), _p(scores), _p(counts), _p(topk),
+                                   C.byref(rep) if rep is not None else None))
+        return ScoreResult(scores, counts, topk, rep, self.last_timing())
+
+    def score_host(self, dims: np.ndarray, K: int, corpus: bool = False, recip: bool = False, variant: int = 0) -> ScoreResult:
+        """dims: C-contiguous float32 [C][T][9] in (preferably pinned) host memory."""
+        assert dims.dtype == np.float32 and dims.flags.c_contiguous and dims.ndim == 3 and dims.shape[2] == NDIM
+        Cn, T, _ = dims.shape
+        o = self._opts(K, SRC_DIMS, corpus, recip, variant, 0, 0)
+        scores = np.empty(Cn, np.float64)
+        counts = np.empty(Cn, np.uint64)
+        topk = np.empty(K, np.int32)
+        rep = CorpusReport() if corpus else None
+        self._ck(self._L.apo_score_host(self._h, C.byref(o), _p(dims), Cn, T, _p(scores), _p(counts), _p(topk),
+                                        C.byref(rep) if rep is not None else None))
+        return ScoreResult(scores, counts, topk, rep, self.last_timing())
+
+    def last_timing(self) -> Timing:
+        t = Timing()
+        self._ck(self._L.apo_last_timing(self._h, C.byref(t)))
+        return t
+
+    def debug_partials(self, Cn: int):
+        """Exact per-candidate (sum_t rint(finalReward*2^52), count) as Python ints."""
+        raw = np.empty((Cn, 4), np.int64)
+        self._ck(self._L.apo_debug_partials(self._h, _p(raw), Cn))
+        sums = [(int(r[2]) << 64) + (int(r[1]) << 32) + int(r[0]) for r in raw]
+        return sums, [int(r[3]) for r in raw]
+
+    # -- multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = load_library()
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES)()
+        rc = L.apo_comm_unique_id(buf)
+        if rc != 0:
+            raise ApoError(rc, (L.apo_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, nranks: int, rank: int, uid: bytes):
+        assert len(uid) == UNIQUE_ID_BYTES
+        buf = (C.c_uint8 * UNIQUE_ID_BYTES).from_buffer_copy(uid)
+        self._ck(self._L.apo_comm_init(self._h, nranks, rank, buf))
+
+    def comm_destroy(self):
+        self._ck(self._L.apo_comm_destroy(self._h))

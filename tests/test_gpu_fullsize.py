@@ -1,0 +1,87 @@
+"""BASELINE.json-size runs (-m gpu), checked through size-independent properties and
+oracle spot windows — the oracle cannot sweep 2.56 G evaluations in test time.
+
+  * config 2 (64 x 1M) and config 3 (256 x 10M, 92 GB resident) are generated on device
+    by the integer-only generator the oracle restates bit for bit;
+  * oracle windows: exact integer partial sums over sampled record windows;
+  * additivity: partial sums of disjoint windows add up to the whole, exactly;
+  * tie-break: a duplicated candidate scores identically and the lower index wins;
+  * determinism: two runs (different kernel variants) give identical integer sums.
+"""
+from importlib import import_module
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def run_config(engine, orc, seed, C, T, K, windows):
+    engine.dims_generate(seed, 0, C, 0, T, 300)
+    engine.corpus_generate(seed, 0, T, 300)
+    res = engine.score(C, K, corpus=True)
+    total, tcount = engine.debug_partials(C)
+    # determinism across kernel variants
+    res1 = engine.score(C, K, variant=1)
+    t1, c1 = engine.debug_partials(C)
+    assert t1 == total and c1 == tcount and np.array_equal(res1.topk, res.topk)
+    # oracle spot windows (exact)
+    for first, count, cands in windows:
+        engine.score(C, 1, first=first, count=count)
+        s, n = engine.debug_partials(C)
+        for c in cands:
+            d = orc.gen_dims(seed, c, 1, first, count, 300, 8)
+            es, en = orc.score_dims_fx(d)
+            assert s[c] == es[0] and n[c] == en[0], (first, c)
+    # additivity over a 3-way split
+    a, b = (T // 3) // 4 * 4, (2 * T // 3) // 4 * 4
+    acc = [0] * C
+    cnt = [0] * C
+    for first, count in [(0, a), (a, b - a), (b, T - b)]:
+        engine.score(C, 1, first=first, count=count)
+        s, n = engine.debug_partials(C)
+        acc = [x + y for x, y in zip(acc, s)]
+        cnt = [x + y for x, y in zip(cnt, n)]
+    assert acc == total and cnt == tcount
+    # scores and top-K follow from the exact sums
+    sh = import_module("senweaver-ide_b200").sharding
+    exp_scores = sh.scores_from_partials(total, tcount)
+    assert np.array_equal(exp_scores, res.scores)
+    assert np.array_equal(sh.topk_indices(exp_scores, K), res.topk)
+    rep = res.report
+    assert rep.total == T and rep.good + rep.bad + rep.none == T
+    assert sum(int(rep.byMode[m][0]) for m in range(5)) == T
+    for p in range(6):
+        ex = [x for x in rep.pat[p].examples if x >= 0]
+        assert ex == sorted(ex) and len(ex) == min(3, rep.pat[p].count)
+    return res
+
+
+def test_config2_64x1M(engine, orc):
+    res = run_config(engine, orc, 0x5EED0002, 64, 1_000_000, 16,
+                     [(0, 4096, [0, 63]), (500_000, 2048, [17]), (999_000, 1000, [5, 40])])
+    # whole-corpus report against the oracle (1M records is seconds of CPU work)
+    recs = orc.gen_records(0x5EED0002, orc.STREAM_CORPUS, 0, 1, 0, 1_000_000, 300, 8).reshape(-1)
+    ref = orc.report(recs)
+    rep = res.report
+    assert (rep.good, rep.bad, rep.none, rep.withReward) == (ref.good, ref.bad, ref.none, ref.withReward)
+    for p in range(6):
+        assert rep.pat[p].count == ref.pat[p].count and rep.pat[p].flag == ref.pat[p].flag
+        assert list(rep.pat[p].examples) == list(ref.pat[p].examples)
+    for i in range(9):
+        assert rep.dim[i].count == ref.dim[i].count
+        assert abs(rep.dim[i].avg - ref.dim[i].avg) <= 1e-5 * max(abs(ref.dim[i].avg), 1e-6)
+    assert abs(rep.avgReward - ref.avgReward) <= 1e-5 * max(abs(ref.avgReward), 1e-6)
+
+
+def test_config3_256x10M_resident(engine, orc):
+    run_config(engine, orc, 0x5EED0003, 256, 10_000_000, 64,
+               [(0, 2048, [0, 255]), (5_000_000, 2048, [128]), (9_999_000, 1000, [77])])
+
+
+def test_duplicate_candidates_tie_break(engine, orc):
+    engine.dims_generate(0x5EED0002, 7, 1, 0, 1_000_000, 300)
+    row = engine.dims_download(0, 0, 1_000_000)
+    engine.dims_upload(np.stack([row, row, row]))
+    res = engine.score(3, 3)
+    assert res.scores[0] == res.scores[1] == res.scores[2] and list(res.topk) == [0, 1, 2]

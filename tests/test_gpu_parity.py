@@ -1,0 +1,269 @@
+"""Parity of the sm_100a path against the CPU oracle, through the C ABI (-m gpu).
+
+Bars (BASELINE.json north_star / SURVEY 8d): top-K indices, pattern flags/counts/examples,
+tallies, per-evaluation dims/finalReward and the integer partial sums are BIT-EXACT;
+score[c] / avgReward / per-dimension means are within 1e-5 relative of the oracle's
+sequential binary64 sums (abs(d) <= 1e-5 * max(abs(ref), 1e-6)); in practice they agree to
+~1e-13, which the tests also assert as a tighter secondary bound.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL, EPS = 1e-5, 1e-6
+
+
+def close(a, b, rtol=RTOL):
+    return abs(a - b) <= rtol * max(abs(b), EPS)
+
+
+def assert_scores(res, ref_scores, ref_counts, tight=1e-11):
+    assert np.array_equal(res.counts, ref_counts)
+    for c, (a, b) in enumerate(zip(res.scores, ref_scores)):
+        if math.isinf(b):
+            assert a == b, c
+        else:
+            assert close(a, b), (c, a, b)
+            assert abs(a - b) <= tight * max(abs(b), 1.0), (c, a, b)
+
+
+# ------------------------------------------------------------------ single-trace path
+def test_reward_batch_golden_bit_exact(engine, orc):
+    with open(os.path.join(GOLD, "reward_cases.json")) as f:
+        g = json.load(f)
+    cases = list(g["kats"].values()) + g["random"]
+    recs = np.frombuffer(b"".join(bytes.fromhex(c["record_hex"]) for c in cases), orc.RECORD_DTYPE)
+    dims, masks, finals = engine.reward_batch(recs)
+    for i, c in enumerate(cases):
+        for k in range(9):
+            exp = math.nan if c["dims"][k] == "nan" else float.fromhex(c["dims"][k])
+            assert (math.isnan(exp) and math.isnan(dims[i, k])) or dims[i, k] == exp, (i, k)
+            assert bool(masks[i] & (1 << k)) == (c["dims"][k] != "nan")
+        assert finals[i] == float.fromhex(c["finalReward"]), i
+
+
+def test_reward_batch_generated_bit_exact(engine, orc):
+    recs = orc.gen_records(0xABCDEF, orc.STREAM_ROLLOUT, 9, 1, 0, 30000, 500, 8).reshape(-1)
+    dims, masks, finals = engine.reward_batch(recs)
+    for i in range(0, len(recs), 7):
+        d, m, fr = orc.reward_one(recs[i])
+        assert m == masks[i]
+        assert np.array_equal(np.isnan(d), np.isnan(dims[i])) and np.array_equal(d[~np.isnan(d)], dims[i][~np.isnan(d)])
+        assert (fr is None and math.isnan(finals[i])) or fr == finals[i]
+
+
+# ------------------------------------------------------------------ generators agree bit for bit
+def test_generators_match_oracle(engine, orc):
+    seed, ap = 0x5EED0003, 300
+    engine.corpus_generate(seed, 1000, 5000, ap)
+    assert engine.corpus_download(0, 5000).tobytes() == orc.gen_records(seed, orc.STREAM_CORPUS, 0, 1, 1000, 5000, ap, 8).tobytes()
+    engine.rollouts_generate(seed, 3, 4, 96, 3001, ap)
+    ref = orc.gen_records(seed, orc.STREAM_ROLLOUT, 3, 4, 96, 3001, ap, 8)
+    for c in range(4):
+        assert engine.rollouts_download(c, 0, 3001).tobytes() == ref[c].tobytes()
+    engine.dims_generate(seed, 3, 4, 96, 3001, ap)
+    refd = orc.gen_dims(seed, 3, 4, 96, 3001, ap, 8)
+    for c in range(4):
+        assert engine.dims_download(c, 0, 3001).tobytes() == refd[c].tobytes()
+    with open(os.path.join(GOLD, "generator_case.json")) as f:
+        g = json.load(f)
+    engine.dims_generate(g["seed"], 5, 1, 1000, 64, g["agent_permille"])
+    assert engine.dims_download(0, 0, 64).tobytes().hex() == g["dims_c5_t1000"]
+
+
+# ------------------------------------------------------------------ K1 + top-K, Form D
+@pytest.mark.parametrize("C,T,K", [(4, 1000, 4), (3, 1, 1), (5, 4099, 2), (7, 1023, 7), (64, 20001, 16), (2, 1025, 1)])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_score_dims_matches_oracle(engine, orc, C, T, K, variant):
+    dims = orc.gen_dims(0x5EED0000 + C, 0, C, 0, T, 300, 8)
+    engine.dims_upload(dims)
+    res = engine.score(C, K, variant=variant)
+    ref_s, ref_n = orc.score_dims(dims)
+    assert_scores(res, ref_s, ref_n)
+    assert np.array_equal(res.topk, orc.topk(ref_s, K))
+    # the integer partial sums are exact: no tolerance
+    sums, counts = engine.debug_partials(C)
+    esums, ecounts = orc.score_dims_fx(dims)
+    assert sums == esums and counts == ecounts
+
+
+def test_score_dims_nan_patterns_and_null_candidates(engine, orc):
+    rng = np.random.default_rng(5)
+    C, T = 6, 3000
+    dims = rng.uniform(-1, 1, (C, T, 9)).astype(np.float32)
+    dims[rng.random((C, T, 9)) < 0.35] = np.nan          # arbitrary presence masks (all 512 possible)
+    dims[2] = np.nan                                      # candidate with no non-null evaluation
+    dims[4] = dims[1]                                     # exact duplicate -> tie -> lower index wins
+    dims[:, 100:140, :] = np.nan                          # null evaluations
+    engine.dims_upload(dims)
+    res = engine.score(C, C)
+    ref_s, ref_n = orc.score_dims(dims)
+    assert_scores(res, ref_s, ref_n)
+    assert res.scores[2] == -np.inf and res.counts[2] == 0
+    assert res.scores[1] == res.scores[4]
+    assert np.array_equal(res.topk, orc.topk(ref_s, C))
+    assert list(res.topk).index(1) < list(res.topk).index(4)
+    assert res.topk[-1] == 2
+    sums, counts = engine.debug_partials(C)
+    esums, ecounts = orc.score_dims_fx(dims)
+    assert sums == esums and counts == ecounts
+
+
+def test_score_windows_add_up_exactly(engine, orc):
+    C, T = 5, 50000
+    dims = orc.gen_dims(77, 0, C, 0, T, 300, 8)
+    engine.dims_upload(dims)
+    engine.score(C, 1)
+    total, tcount = engine.debug_partials(C)
+    acc, cnt = [0] * C, [0] * C
+    for first, count in [(0, 12000), (12000, 20004), (32004, 17996)]:
+        engine.score(C, 1, first=first, count=count)
+        s, n = engine.debug_partials(C)
+        es, en = orc.score_dims_fx(dims[:, first:first + count])
+        assert s == es and n == en
+        acc = [a + b for a, b in zip(acc, s)]
+        cnt = [a + b for a, b in zip(cnt, n)]
+    assert acc == total and cnt == tcount
+
+
+def test_recip_variant_within_tolerance(engine, orc):
+    C, T = 8, 30000
+    dims = orc.gen_dims(99, 0, C, 0, T, 300, 8)
+    engine.dims_upload(dims)
+    res = engine.score(C, 4, recip=True)
+    ref_s, ref_n = orc.score_dims(dims)
+    assert_scores(res, ref_s, ref_n)
+    assert np.array_equal(res.topk, orc.topk(ref_s, 4))
+
+
+def test_custom_weights(engine, orc):
+    w = np.array([0.3, 0.1, 0.05, 0.05, 0.1, 0.1, 0.1, 0.1, 0.1])
+    dims = orc.gen_dims(5, 0, 4, 0, 2000, 300, 8)
+    try:
+        engine.set_weights(w)
+        engine.dims_upload(dims)
+        res = engine.score(4, 2)
+        ref_s, ref_n = orc.score_dims(dims, w=w)
+        assert_scores(res, ref_s, ref_n)
+        sums, _ = engine.debug_partials(4)
+        assert sums == orc.score_dims_fx(dims, w=w)[0]
+    finally:
+        engine.set_weights(orc.weights())
+
+
+def test_score_host_streaming_matches_resident(engine, orc):
+    C, T = 16, 70001
+    dims = orc.gen_dims(123, 0, C, 0, T, 300, 8)
+    r = engine.score_host(dims, 4)
+    sums, counts = engine.debug_partials(C)
+    esums, ecounts = orc.score_dims_fx(dims)
+    assert sums == esums and counts == ecounts
+    ref_s, _ = orc.score_dims(dims)
+    assert np.array_equal(r.topk, orc.topk(ref_s, 4))
+
+
+# ------------------------------------------------------------------ K1r, Form R per evaluation
+@pytest.mark.parametrize("ap", [0, 1024, 512])
+def test_score_rollouts_matches_oracle(engine, orc, ap):
+    C, T = 6, 9001
+    recs = orc.gen_records(0x5EED0004, orc.STREAM_ROLLOUT, 0, C, 0, T, ap, 8)
+    engine.rollouts_upload(recs)
+    res = engine.score(C, 3, source=1)
+    ref_s, ref_n = orc.score_records(recs)
+    assert_scores(res, ref_s, ref_n)
+    assert np.array_equal(res.topk, orc.topk(ref_s, 3))
+    sums, counts = engine.debug_partials(C)
+    esums, ecounts = orc.score_records_fx(recs)
+    assert sums == esums and counts == ecounts
+
+
+# ------------------------------------------------------------------ K2 detect6 + report
+def check_report(rep, ref):
+    assert (rep.total, rep.good, rep.bad, rep.none) == (ref.total, ref.good, ref.bad, ref.none)
+    assert rep.goodRate == ref.goodRate
+    for m in range(5):
+        assert list(rep.byMode[m]) == list(ref.byMode[m])
+        assert rep.byModeGoodRate[m] == ref.byModeGoodRate[m]
+    assert rep.withReward == ref.withReward
+    if ref.withReward:
+        assert close(rep.avgReward, ref.avgReward) and abs(rep.avgReward - ref.avgReward) < 1e-12
+    else:
+        assert math.isnan(rep.avgReward)
+    for i in range(9):
+        assert rep.dim[i].count == ref.dim[i].count
+        assert close(rep.dim[i].sum, ref.dim[i].sum) and close(rep.dim[i].avg, ref.dim[i].avg)
+        assert (rep.dim[i].low_flag, rep.dim[i].sugg_flag) == (ref.dim[i].low_flag, ref.dim[i].sugg_flag)
+        if ref.dim[i].low_flag:
+            assert rep.dim[i].low_severity == ref.dim[i].low_severity
+        if ref.dim[i].sugg_flag:
+            assert rep.dim[i].sugg_priority == ref.dim[i].sugg_priority
+    for p in range(6):
+        assert (rep.pat[p].count, rep.pat[p].flag) == (ref.pat[p].count, ref.pat[p].flag), p
+        assert list(rep.pat[p].examples) == list(ref.pat[p].examples), p
+        if ref.pat[p].flag:
+            assert rep.pat[p].severity == ref.pat[p].severity
+    assert (rep.toolCalls, rep.toolSucc, rep.toolFail) == (ref.toolCalls, ref.toolSucc, ref.toolFail)
+    assert (math.isnan(rep.toolSuccessRate) and math.isnan(ref.toolSuccessRate)) or rep.toolSuccessRate == ref.toolSuccessRate
+
+
+@pytest.mark.parametrize("T,base", [(1000, 0), (1, 5), (100003, 1 << 33), (37, 0)])
+def test_corpus_report_matches_oracle(engine, orc, T, base):
+    recs = orc.gen_records(0x5EED0003, orc.STREAM_CORPUS, 0, 1, base, T, 300, 8).reshape(-1)
+    engine.corpus_upload(recs, idx_base=base)
+    dims = orc.gen_dims(1, 0, 2, 0, 64, 300, 2)
+    engine.dims_upload(dims)
+    res = engine.score(2, 1, corpus=True)
+    check_report(res.report, orc.report(recs, idx_base=base))
+    assert np.array_equal(res.topk, orc.topk(orc.score_dims(dims)[0], 1))
+
+
+def test_corpus_without_bad_feedback_has_no_patterns(engine, orc):
+    recs = orc.gen_records(3, orc.STREAM_CORPUS, 0, 1, 0, 5000, 300, 8).reshape(-1).copy()
+    recs["feedback"][recs["feedback"] == 2] = 0              # APO:641 early-out
+    engine.corpus_upload(recs)
+    engine.dims_upload(orc.gen_dims(1, 0, 1, 0, 8, 300, 1))
+    res = engine.score(1, 1, corpus=True)
+    ref = orc.report(recs)
+    check_report(res.report, ref)
+    assert all(res.report.pat[p].count == 0 and res.report.pat[p].flag == 0 for p in range(6))
+
+
+def test_corpus_golden_report(engine, orc):
+    with open(os.path.join(GOLD, "reward_cases.json")) as f:
+        g = json.load(f)
+    recs = np.frombuffer(b"".join(bytes.fromhex(c["record_hex"]) for c in g["random"]), orc.RECORD_DTYPE)
+    engine.corpus_upload(recs)
+    engine.dims_upload(orc.gen_dims(1, 0, 1, 0, 8, 300, 1))
+    res = engine.score(1, 1, corpus=True)
+    check_report(res.report, orc.report(recs))
+
+
+# ------------------------------------------------------------------ top-K at larger C
+@pytest.mark.parametrize("C,K", [(1024, 256), (1000, 1000), (300, 1), (4096, 64)])
+def test_radix_topk_many_candidates(engine, orc, C, K):
+    rng = np.random.default_rng(C)
+    dims = np.full((C, 8, 9), np.nan, np.float32)
+    vals = rng.integers(-50, 50, C).astype(np.float32) / 64.0     # many exact ties
+    dims[:, :, 0] = vals[:, None]
+    dims[::17] = np.nan                                           # -inf candidates
+    engine.dims_upload(dims)
+    res = engine.score(C, K)
+    ref_s, ref_n = orc.score_dims(dims)
+    assert_scores(res, ref_s, ref_n)
+    assert np.array_equal(res.topk, orc.topk(ref_s, K))
+
+
+def test_error_behaviour(engine, apo):
+    dims = np.zeros((2, 16, 9), np.float32)
+    engine.dims_upload(dims)
+    with pytest.raises(apo.ApoError):
+        engine.score(2, 1, first=2)                       # window start not a multiple of 4
+    with pytest.raises(apo.ApoError):
+        engine.score(2, 3)                                # K > C
+    res = engine.score(2, 2)                              # the handle stays usable after an error
+    assert list(res.topk) == [0, 1]

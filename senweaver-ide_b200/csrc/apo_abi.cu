@@ -300,7 +300,19 @@ extern "C" int apo_set_stream(apo_engine *e, uint64_t cuda_stream) {
 
 extern "C" int apo_set_weights(apo_engine *e, const double w[APO_NDIM]) {
 	if (!e || !w) return fail(e, APO_E_ARG, "NULL argument");
-	for (int i = 0; i < APO_NDIM; i++) if (!(w[i] >= 0.0) || !std::isfinite(w[i])) return fail(e, APO_E_ARG, "weights must be finite and >= 0");
+	for (int i = 0; i < APO_NDIM; i++)
+		if (!std::isfinite(w[i]) || !(w[i] == 0.0 || (w[i] >= 1e-100 && w[i] <= 1e100)))
+			return fail(e, APO_E_ARG, "weights must be 0 or within [1e-100, 1e100]");
+	{   // the LUT division (csrc/apo_kernels.cu div_lut) needs RN(1/tw) to be within the Markstein bound
+		apo::Weights t; memcpy(t.w, w, sizeof t.w);
+		for (uint32_t m = 1; m < 512; m++) {
+			double tw = 0.0;
+			for (int i = 0; i < APO_NDIM; i++) if (m & (1u << i)) tw += t.w[i];
+			uint64_t bits; memcpy(&bits, &tw, 8);
+			if (tw > 0.0 && (bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull)
+				return fail(e, APO_E_ARG, "weights produce a total weight whose significand is all ones (mask %u)", m);
+		}
+	}
 	CK(cudaSetDevice(e->device));
 	memcpy(e->W.w, w, sizeof e->W.w);
 	build_luts(e);
@@ -473,7 +485,7 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	P.pitch_bytes = pitch * row;
 	P.C = C; P.T = count; P.acc = e->acc.p;
 	const bool recip = (o->flags & APO_SCORE_RECIP) != 0;
-	P.lut = e->d_lut.p + (recip ? 512 : 0);
+	P.lut = e->d_lut.p;
 	P.W = e->W;
 	if (count) { CK(apo::run_reward9(P, row, (int)o->variant, recip, e->sm_count, e->stream)); e->timing.launches++; }
 	return finish_score(e, o, C, scores, counts, topk, report);
@@ -510,7 +522,7 @@ extern "C" int apo_score_host(apo_engine *e, const apo_score_opts *o, const floa
 		CK(cudaStreamWaitEvent(e->stream, e->win_ready[b], 0));
 		apo::K1Params P{};
 		P.base = (const uint8_t *)e->win[b].p; P.pitch_bytes = Tc * 36; P.C = C; P.T = n; P.acc = e->acc.p;
-		P.lut = e->d_lut.p + (recip ? 512 : 0); P.W = e->W;
+		P.lut = e->d_lut.p; P.W = e->W;
 		CK(apo::run_reward9(P, 36, (int)o->variant, recip, e->sm_count, e->stream));
 		e->timing.launches++;
 		CK(cudaEventRecord(e->win_free[b], e->stream));

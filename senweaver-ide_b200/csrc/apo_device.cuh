@@ -37,9 +37,8 @@ struct Acc128 {
 	unsigned long long lo; long long hi;
 	__device__ __forceinline__ void zero() { lo = 0; hi = 0; }
 	__device__ __forceinline__ void add(long long x) {
-		const unsigned long long n = lo + (unsigned long long)x;
-		hi += (x >> 63) + (long long)(n < lo);
-		lo = n;
+		const long long sx = x >> 63;
+		asm("add.cc.u64 %0, %0, %2;\n\taddc.s64 %1, %1, %3;" : "+l"(lo), "+l"(hi) : "l"(x), "l"(sx));
 	}
 };
 

@@ -26,7 +26,7 @@ struct K1Cfg {
 	static constexpr int NCONS = CW * 32;
 	static constexpr int TILE = NCONS * EPT;            // evaluations per tile
 	static constexpr int STAGE_BYTES = TILE * ROW;
-	static constexpr int LUT_BYTES = 512 * 8;
+	static constexpr int LUT_BYTES = 512 * 16;          // {total weight, its reciprocal} per presence mask
 	static constexpr int BAR_OFF = STAGES * STAGE_BYTES + LUT_BYTES;
 	static constexpr int META_OFF = BAR_OFF + 2 * STAGES * 8;
 	static constexpr int SMEM = META_OFF + STAGES * 8;
@@ -34,8 +34,31 @@ struct K1Cfg {
 };
 
 // One Form-D evaluation: 9 fp32 (NaN = absent) -> fixed-point finalReward.
+// ws / tw, correctly rounded, without the generic division's special-case branch (which
+// would serialise the four evaluations a thread interleaves): y = RN(1/tw) comes from the
+// LUT, q = RN(ws*y), r = ws - tw*q (exact, one FMA), result = RN(q + r*y).  By Markstein's
+// theorem this is the correctly rounded quotient when y is the correctly rounded reciprocal
+// and nothing underflows — guaranteed here: tw is one of <= 511 sums of validated weights
+// (apo_set_weights rejects nonzero weights below 1e-100, and LUT entries whose significand is
+// all ones) and |ws| is 0 or >= 2^-160 (fp32 inputs x weights).
 template <bool RECIP>
-__device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const Weights &W, const double *lut,
+__device__ __forceinline__ double div_lut(double ws, double2 t) {
+	const double q = __dmul_rn(ws, t.y);
+	if (RECIP) return q;
+	const double r = __fma_rn(-t.x, q, ws);
+	return __fma_rn(r, t.y, q);
+}
+
+// The shared-memory LUT is indexed by a bit-rotated presence mask: dims 5..8 (the ones that
+// vary independently in real data; d0,d1 are always present and d2..d4 come together) land
+// in the low bits, so lanes with different masks mostly hit different banks.
+__host__ __device__ constexpr int lut_bit(int dim) { return (dim + 4) % APO_NDIM; }
+__device__ __forceinline__ uint32_t lut_index(uint32_t natural_mask) {
+	return ((natural_mask >> 5) | (natural_mask << 4)) & 511u;
+}
+
+template <bool RECIP>
+__device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const Weights &W, const double2 *lut,
                                                uint32_t &valid) {
 	double ws = 0.0;
 	uint32_t mask = 0;
@@ -45,24 +68,22 @@ __device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const
 		const bool p = (f == f);
 		const float g = p ? f : 0.0f;                 // +0.0 * w leaves the running sum unchanged
 		ws = __dadd_rn(ws, __dmul_rn((double)g, W.w[i]));
-		mask |= (p ? 1u : 0u) << i;
+		mask |= (p ? 1u : 0u) << lut_bit(i);
 	}
-	const double tw = lut[mask];                      // lut[0] == 1: ws == 0 -> 0
-	const double fr = RECIP ? __dmul_rn(ws, tw) : __ddiv_rn(ws, tw);
+	const double fr = div_lut<RECIP>(ws, lut[mask]);  // lut[0] == {1,1}: ws == 0 -> 0
 	valid = mask != 0 ? 1u : 0u;
 	return to_fx(fr);
 }
 
 template <bool RECIP>
-__device__ __forceinline__ long long eval_record(const apo_record &r, const Weights &W, const double *lut,
+__device__ __forceinline__ long long eval_record(const apo_record &r, const Weights &W, const double2 *lut,
                                                  uint32_t &valid) {
 	double d[APO_NDIM];
 	const uint32_t mask = reward_dims(r, d);
-	const double tw = lut[mask];
 	double ws = 0.0;
 #pragma unroll
 	for (int i = 0; i < APO_NDIM; i++) ws = __dadd_rn(ws, __dmul_rn(d[i], W.w[i]));
-	const double fr = RECIP ? __dmul_rn(ws, tw) : __ddiv_rn(ws, tw);
+	const double fr = div_lut<RECIP>(ws, lut[lut_index(mask)]);
 	valid = (r.flags & APO_F_VALID) ? 1u : 0u;
 	return valid ? to_fx(fr) : 0ll;
 }
@@ -72,13 +93,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1)
 k_reward9(const K1Params P) {
 	using Cfg = K1Cfg<ROW, CW, STAGES>;
 	extern __shared__ __align__(128) uint8_t smem[];
-	double *s_lut = reinterpret_cast<double *>(smem + STAGES * Cfg::STAGE_BYTES);
+	double2 *s_lut = reinterpret_cast<double2 *>(smem + STAGES * Cfg::STAGE_BYTES);
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::BAR_OFF);
 	uint64_t *empty = full + STAGES;
 	StageMeta *meta = reinterpret_cast<StageMeta *>(smem + Cfg::META_OFF);
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	for (int i = tid; i < 512; i += blockDim.x) s_lut[i] = P.lut[i];
+	for (int i = tid; i < 512; i += blockDim.x) s_lut[lut_index(i)] = make_double2(P.lut[i], P.lut[512 + i]);
 	if (tid == 0) {
 		for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
 		mbar_fence_init();
@@ -141,9 +162,28 @@ k_reward9(const K1Params P) {
 		if (ROW == 36) {
 			// thread owns 4 consecutive evaluations = 144 B = 9 x LDS.128 (conflict-free: 144 B lane stride)
 			const int e0 = tid * 4;
-			if (e0 < n) {
+			const float4 *src = reinterpret_cast<const float4 *>(st + (size_t)e0 * 36);
+			if (n == Cfg::TILE) {
+				// full tile: branch-free, the four evaluations are independent chains the scheduler interleaves
 				float f[36];
-				const float4 *src = reinterpret_cast<const float4 *>(st + (size_t)e0 * 36);
+#pragma unroll
+				for (int q = 0; q < 9; q++) {
+					const float4 x = src[q];
+					f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
+				}
+				long long x4 = 0;
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					float v[APO_NDIM];
+#pragma unroll
+					for (int i = 0; i < APO_NDIM; i++) v[i] = f[9 * k + i];
+					uint32_t ok;
+					x4 += eval_dims<RECIP>(v, W, s_lut, ok);      // |fr| <= 512 -> |x| < 2^61: four terms fit int64
+					cnt += ok;
+				}
+				acc.add(x4);
+			} else if (e0 < n) {
+				float f[36];
 #pragma unroll
 				for (int q = 0; q < 9; q++) {
 					const float4 x = src[q];
@@ -204,6 +244,8 @@ int k1_tile_evals(int row, int variant) {
 	(void)row;
 	switch (variant) {
 	case 1: return K1Cfg<36, 16, 3>::TILE;
+	case 2: return K1Cfg<36, 12, 4>::TILE;
+	case 3: return K1Cfg<36, 20, 2>::TILE;
 	default: return K1Cfg<36, 8, 5>::TILE;
 	}
 }
@@ -218,11 +260,15 @@ cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_cou
 	if (row == 36) {
 		switch (variant) {
 		case 1: return launch_k1<36, 16, 3>(P, grid, recip, st);
+		case 2: return launch_k1<36, 12, 4>(P, grid, recip, st);
+		case 3: return launch_k1<36, 20, 2>(P, grid, recip, st);
 		default: return launch_k1<36, 8, 5>(P, grid, recip, st);
 		}
 	} else {
 		switch (variant) {
 		case 1: return launch_k1<32, 16, 3>(P, grid, recip, st);
+		case 2: return launch_k1<32, 12, 4>(P, grid, recip, st);
+		case 3: return launch_k1<32, 20, 2>(P, grid, recip, st);
 		default: return launch_k1<32, 8, 5>(P, grid, recip, st);
 		}
 	}
@@ -249,11 +295,9 @@ __device__ void finalize_block(const FinalizeParams &F);
 __global__ void __launch_bounds__(K2_THREADS)
 k_detect6(const K2Params P) {
 	__shared__ unsigned long long s_ex[APO_NPAT * 3];
-	__shared__ unsigned long long s_u64[3];
 	__shared__ bool s_last;
 	const int tid = threadIdx.x, lane = tid & 31;
 	if (tid < APO_NPAT * 3) s_ex[tid] = ~0ull;
-	if (tid < 3) s_u64[tid] = 0;
 	__syncthreads();
 
 	uint32_t cn[CN_TOTAL];

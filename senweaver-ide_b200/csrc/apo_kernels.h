@@ -16,7 +16,7 @@ struct K1Params {
 	uint64_t T;                 // evaluations per candidate in this launch
 	uint64_t total_tiles;       // filled by run_reward9
 	long long *acc;             // accumulator vector (see apo_device.cuh)
-	const double *lut;          // 512-entry total-weight (or reciprocal) table
+	const double *lut;          // [0,512) total weight per presence mask, [512,1024) its reciprocal
 	Weights W;
 };
 

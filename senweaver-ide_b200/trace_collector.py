@@ -1,0 +1,327 @@
+"""Host-side mirror of the reference's TraceCollectorService API (TCS:133-210).
+
+Same method names, argument meaning and error behaviour as
+src/vs/workbench/contrib/senweaver/common/traceCollectorService.ts, with the arithmetic
+delegated to the B200 engine through the C ABI:
+
+    _computeRewardSignals (TCS:668-788)      -> Engine.reward_batch   (k_reward_batch)
+    getStats means / tool totals (TCS:596-626) -> Engine.score(corpus=True) (k_detect6)
+
+Recorders never raise into the caller (TCS:438 `catch { /* silent */ }`); engine failures
+leave the trace untouched.  The reference defers recorders with queueMicrotask; this mirror
+runs them immediately (single-threaded host, same FIFO order).  Storage / HTTP upload are
+injected collaborators exactly as in the reference constructor (storage, product, request)
+and are optional here — the scoring engine itself is stateless.
+"""
+from __future__ import annotations
+
+import json
+import time
+import uuid
+
+import numpy as np
+
+from .engine import DIM_NAMES, F_ENDED, F_ERRORS, F_FAILSPAN, F_VALID, RECORD_DTYPE, Engine
+
+MAX_CONTENT_PREVIEW = 500          # TCS:218
+MAX_TRACES = 1000                  # TCS:219
+MAX_SPANS_PER_TRACE = 200          # TCS:220
+TRACE_STORAGE_KEY = "senweaver.traceCollector.data"          # TCS:216
+TRACE_FEEDBACK_KEY = "senweaver.traceCollector.feedbacks"    # TCS:217
+MODE_CODE = {"normal": 1, "agent": 2, "gather": 3, "designer": 4}
+FB_CODE = {None: 0, "good": 1, "bad": 2}
+U32 = 0xFFFFFFFF
+
+
+def encode_trace(trace: dict, valid: bool | None = None) -> np.ndarray:
+    """ConversationTrace -> Form R (include/apo_b200.h apo_record): the fields the scoring
+    path reads (TCS:94-108, :87, :91) plus the span-derived counts of TCS:752-753, APO:667-669."""
+    s = trace["summary"]
+    md = trace.get("metadata") or {}
+    spans = trace["spans"]
+    user = sum(1 for sp in spans if sp["type"] == "user_message")
+    asst = sum(1 for sp in spans if sp["type"] == "assistant_message")
+    failspan = any(sp["type"] == "tool_call" and sp["data"].get("toolSuccess") is False for sp in spans)
+    if valid is None:
+        valid = s["finalReward"] is not None
+    rec = np.zeros(1, RECORD_DTYPE)
+    rec["feedback"] = FB_CODE.get(s["userFeedback"], 0)
+    rec["flags"] = ((F_ERRORS if s["hasErrors"] else 0) | (F_ENDED if trace.get("endTime") else 0) |
+                    (F_VALID if valid else 0) | (F_FAILSPAN if failspan else 0))
+    rec["mode"] = MODE_CODE.get(md.get("chatMode") or "", 0)
+    rec["userMsgs"], rec["asstMsgs"] = min(user, 65535), min(asst, 65535)
+    rec["toolCalls"] = min(int(s["totalToolCalls"]), U32)
+    rec["toolSucc"] = min(int(s["toolCallsSucceeded"]), U32)
+    rec["toolFail"] = min(int(s["toolCallsFailed"]), U32)
+    rec["llmCalls"] = min(int(s["totalLLMCalls"]), U32)
+    rec["tokens"] = min(int(s["totalTokens"]), U32)
+    rec["toolDurMs"] = float(s["totalToolDurationMs"])
+    return rec
+
+
+class TraceCollectorService:
+    def __init__(self, engine: Engine, storageService=None, productService=None, requestService=None):
+        self._engine = engine
+        self._storage, self._product, self._request = storageService, productService, requestService
+        self._listeners = []
+        self._traces: dict[str, dict] = {}
+        self._active: dict[str, str] = {}
+        self._feedbacks: dict[str, str | None] = {}
+        self._scored: dict[str, np.ndarray] = {}       # Form R snapshot taken when the reward was computed
+        self._dirty = False
+        api = (getattr(productService, "senweaverApiConfig", None) or {}).get("apiBaseUrl") if productService else None
+        self._traceApiUrl = f"{api or 'https://ide-api.senweaver.com'}/api/traces"     # TCS:245-246
+        self._autoUploadConfig = {"enabled": False, "intervalMs": 300000}              # TCS:792
+        self._uploadedIds: set[str] = set()
+        self._loadFromStorage()
+
+    # ---- events
+    def onDidChangeState(self, listener):
+        self._listeners.append(listener)
+
+    def _fire(self):
+        for fn in list(self._listeners):
+            try:
+                fn()
+            except Exception:
+                pass
+
+    # ---- storage (TCS:296-359)
+    def _loadFromStorage(self):
+        if not self._storage:
+            return
+        try:
+            for t in json.loads(self._storage.get(TRACE_STORAGE_KEY, "[]")):
+                self._traces[t["id"]] = t
+            self._feedbacks.update(json.loads(self._storage.get(TRACE_FEEDBACK_KEY, "{}")))
+        except Exception as e:                      # TCS:311 warn and continue
+            print("[TraceCollector] Failed to load from storage:", e)
+
+    def _saveToStorage(self):
+        if not self._dirty:
+            return
+        try:
+            if len(self._traces) > MAX_TRACES:      # keep the newest MAX_TRACES by startTime (TCS:337-345)
+                keep = sorted(self._traces.values(), key=lambda t: -(t.get("startTime") or 0))[:MAX_TRACES]
+                self._traces = {t["id"]: t for t in keep}
+            if self._storage is not None:
+                self._storage[TRACE_STORAGE_KEY] = json.dumps(list(self._traces.values()))
+                self._storage[TRACE_FEEDBACK_KEY] = json.dumps(self._feedbacks)
+            self._dirty = False
+        except Exception as e:
+            print("[TraceCollector] Failed to save to storage:", e)
+
+    # ---- helpers
+    @staticmethod
+    def _truncate(s, n=MAX_CONTENT_PREVIEW):
+        if not s:
+            return ""
+        return s[:n] + "..." if len(s) > n else s
+
+    def _getOrCreateTrace(self, threadId):
+        tid = self._active.get(threadId)
+        if tid and tid in self._traces:
+            return self._traces[tid]
+        return self._traces[self.startTrace(threadId)]          # auto-created: no metadata (TCS:264-272)
+
+    def _addSpan(self, trace, type_, messageIdx, data, duration=None):
+        if len(trace["spans"]) >= MAX_SPANS_PER_TRACE:          # TCS:275-277: counters still advance
+            return
+        span = {"id": str(uuid.uuid4()), "traceId": trace["id"], "threadId": trace["threadId"], "messageIdx": messageIdx,
+                "type": type_, "timestamp": time.time() * 1000.0, "data": data}
+        if duration is not None:
+            span["duration"] = duration
+        trace["spans"].append(span)
+        self._dirty = True
+
+    # ---- lifecycle (TCS:380-425)
+    def startTrace(self, threadId, metadata=None):
+        tid = str(uuid.uuid4())
+        self._traces[tid] = {
+            "id": tid, "threadId": threadId, "startTime": time.time() * 1000.0, "spans": [],
+            "summary": {"totalLLMCalls": 0, "totalToolCalls": 0, "totalTokens": 0, "userFeedback": None, "hasErrors": False,
+                        "toolCallsSucceeded": 0, "toolCallsFailed": 0, "toolCallsByName": {}, "totalToolDurationMs": 0,
+                        "finalReward": None, "rewardDimensions": []},
+            "metadata": metadata}
+        self._active[threadId] = tid
+        self._dirty = True
+        return tid
+
+    def endTrace(self, traceId):
+        t = self._traces.get(traceId)
+        if t:
+            t["endTime"] = time.time() * 1000.0
+            self._computeRewardSignals(t)
+            self._dirty = True
+            self._saveToStorage()
+
+    def endTraceForThread(self, threadId):
+        tid = self._active.get(threadId)
+        if tid:
+            self.endTrace(tid)
+
+    # ---- recorders (TCS:429-569): fire-and-forget, never raise
+    def recordUserMessage(self, threadId, messageIdx, content):
+        try:
+            t = self._getOrCreateTrace(threadId)
+            self._addSpan(t, "user_message", messageIdx, {"contentPreview": self._truncate(content), "contentLength": len(content)})
+        except Exception:
+            pass
+
+    def recordAssistantMessage(self, threadId, messageIdx, content, model=None, provider=None):
+        try:
+            t = self._getOrCreateTrace(threadId)
+            self._addSpan(t, "assistant_message", messageIdx, {"contentPreview": self._truncate(content),
+                                                               "contentLength": len(content), "model": model, "provider": provider})
+        except Exception:
+            pass
+
+    def recordLLMCall(self, threadId, messageIdx, data):
+        try:
+            t = self._getOrCreateTrace(threadId)
+            self._addSpan(t, "llm_call", messageIdx, {k: data.get(k) for k in ("model", "provider", "inputTokens", "outputTokens", "temperature")},
+                          duration=data.get("duration"))
+            t["summary"]["totalLLMCalls"] += 1
+            t["summary"]["totalTokens"] += (data.get("inputTokens") or 0) + (data.get("outputTokens") or 0)
+        except Exception:
+            pass
+
+    def recordToolCall(self, threadId, messageIdx, data):
+        try:
+            t = self._getOrCreateTrace(threadId)
+            self._addSpan(t, "tool_call", messageIdx, {"toolName": data["toolName"], "toolParams": self._truncate(data.get("toolParams")),
+                                                       "toolResult": self._truncate(data.get("toolResult")),
+                                                       "toolSuccess": bool(data["toolSuccess"])}, duration=data.get("duration"))
+            s = t["summary"]
+            s["totalToolCalls"] += 1
+            key = "toolCallsSucceeded" if data["toolSuccess"] else "toolCallsFailed"
+            s[key] += 1
+            by = s["toolCallsByName"].setdefault(data["toolName"], {"total": 0, "succeeded": 0, "failed": 0})
+            by["total"] += 1
+            by["succeeded" if data["toolSuccess"] else "failed"] += 1
+            if data.get("duration") and data["duration"] > 0:
+                s["totalToolDurationMs"] += data["duration"]
+            self._dirty = True
+        except Exception:
+            pass
+
+    def recordUserFeedback(self, threadId, messageIdx, feedback):
+        try:
+            self._feedbacks[f"{threadId}:{messageIdx}"] = feedback
+            t = self._getOrCreateTrace(threadId)             # the thread's *active* trace (TCS:538)
+            self._addSpan(t, "user_feedback", messageIdx, {"feedback": feedback})
+            t["summary"]["userFeedback"] = feedback
+            self._dirty = True
+            self._computeRewardSignals(t)                     # TCS:547
+            self._fire()
+            self._saveToStorage()
+        except Exception:
+            pass
+
+    def recordError(self, threadId, messageIdx, errorMessage):
+        try:
+            t = self._getOrCreateTrace(threadId)
+            self._addSpan(t, "error", messageIdx, {"errorMessage": self._truncate(errorMessage, 1000)})
+            t["summary"]["hasErrors"] = True
+        except Exception:
+            pass
+
+    # ---- the hot step: TCS:668-788 on the GPU
+    def _computeRewardSignals(self, trace):
+        rec = encode_trace(trace, valid=True)
+        dims, masks, finals = self._engine.reward_batch(rec)
+        m = int(masks[0])
+        trace["summary"]["rewardDimensions"] = [{"name": DIM_NAMES[i], "value": float(dims[0, i])} for i in range(9) if m & (1 << i)]
+        trace["summary"]["finalReward"] = float(finals[0])
+        self._scored[trace["id"]] = rec
+
+    # ---- queries
+    def getFeedback(self, threadId, messageIdx):
+        return self._feedbacks.get(f"{threadId}:{messageIdx}")
+
+    def getAllTraces(self):
+        return list(self._traces.values())
+
+    def corpus_records(self, traces=None, scored: bool = False) -> np.ndarray:
+        """Form R for a list of traces.  scored=True returns the snapshot taken when each reward was
+        computed (late events mutate counters without re-scoring, TCS:420-425)."""
+        traces = self.getAllTraces() if traces is None else traces
+        out = np.zeros(len(traces), RECORD_DTYPE)
+        for i, t in enumerate(traces):
+            snap = self._scored.get(t["id"]) if scored else None
+            if snap is not None and t["summary"]["finalReward"] is not None:
+                out[i] = snap[0]
+            else:
+                out[i] = encode_trace(t)[0]
+        return out
+
+    def getStats(self):
+        traces = self.getAllTraces()
+        total_spans = sum(len(t["spans"]) for t in traces)
+        starts = [t["startTime"] for t in traces]
+        good = sum(1 for v in self._feedbacks.values() if v == "good")
+        bad = sum(1 for v in self._feedbacks.values() if v == "bad")
+        tool = (0, 0, 0)
+        avg, with_reward, rate = None, 0, None
+        if traces:
+            # tool totals from the live counters, reward mean from the scored snapshots (TCS:602-610)
+            self._engine.corpus_upload(self.corpus_records(traces))
+            self._engine.dims_upload(np.full((1, 4, 9), np.nan, np.float32))
+            rep = self._engine.score(1, 0, corpus=True).report
+            tool = (int(rep.toolCalls), int(rep.toolSucc), int(rep.toolFail))
+            rate = None if rep.toolCalls == 0 else float(rep.toolSuccessRate)
+            vals = [t["summary"]["finalReward"] for t in traces if t["summary"]["finalReward"] is not None]
+            with_reward = len(vals)
+            if vals:
+                self._engine.corpus_upload(self.corpus_records(traces, scored=True))
+                rep2 = self._engine.score(1, 0, corpus=True).report
+                avg = float(rep2.avgReward)
+        return {"totalTraces": len(traces), "totalSpans": total_spans, "totalFeedbacks": good + bad, "goodFeedbacks": good,
+                "badFeedbacks": bad, "storageUsedBytes": self._estimateStorageBytes(),
+                "oldestTraceTime": min(starts) if starts else None, "newestTraceTime": max(starts) if starts else None,
+                "totalToolCalls": tool[0], "totalToolSucceeded": tool[1], "totalToolFailed": tool[2], "toolSuccessRate": rate,
+                "avgFinalReward": avg, "tracesWithReward": with_reward}
+
+    def _estimateStorageBytes(self):
+        try:
+            return len(json.dumps(list(self._traces.values()))) + len(json.dumps(self._feedbacks))
+        except Exception:
+            return 0
+
+    def exportData(self):
+        return json.dumps({"version": "1.0.0", "exportTime": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()),
+                           "stats": self.getStats(), "traces": self.getAllTraces(), "feedbacks": self._feedbacks}, indent=2)
+
+    def clearAllData(self):
+        self._traces.clear(); self._active.clear(); self._feedbacks.clear(); self._scored.clear()
+        self._dirty = True
+        self._saveToStorage()
+        self._fire()
+
+    # ---- backend upload (TCS:797-898): payload assembly only; HTTP goes through the injected request service
+    def uploadToServer(self):
+        try:
+            new = [t for t in self._traces.values() if t["id"] not in self._uploadedIds]
+            if not new:
+                return {"success": True, "message": "No new traces to upload", "uploadedCount": 0}
+            if self._request is None:
+                return {"success": False, "message": "no request service configured", "uploadedCount": 0}
+            self._engine.corpus_upload(self.corpus_records(new, scored=True))
+            self._engine.dims_upload(np.full((1, 4, 9), np.nan, np.float32))
+            rep = self._engine.score(1, 0, corpus=True).report
+            payload = {"version": "2.0.0", "traces": new, "rewardSummary": {
+                "totalWithReward": int(rep.withReward), "avgFinalReward": None if rep.withReward == 0 else float(rep.avgReward),
+                "rewardDimensionAvg": {DIM_NAMES[i]: float(rep.dim[i].avg) for i in range(9) if rep.dim[i].count}}}
+            ok = self._request(self._traceApiUrl, payload)
+            if ok:
+                self._uploadedIds.update(t["id"] for t in new)
+            return {"success": bool(ok), "message": "uploaded" if ok else "upload failed", "uploadedCount": len(new) if ok else 0}
+        except Exception as e:                          # TCS:894-898
+            print("[TraceCollector] Upload failed:", e)
+            return {"success": False, "message": str(e), "uploadedCount": 0}
+
+    def setAutoUploadConfig(self, config):
+        self._autoUploadConfig = {"enabled": bool(config.get("enabled")), "intervalMs": config.get("intervalMs") or self._autoUploadConfig["intervalMs"]}
+
+    def getAutoUploadConfig(self):
+        return {**self._autoUploadConfig, "traceApiUrl": self._traceApiUrl}

@@ -1,0 +1,394 @@
+"""Host-side mirror of the reference's APOService API (APO:203-267).
+
+Same method names, argument meaning and error behaviour as
+src/vs/workbench/contrib/senweaver/common/apoService.ts; the reductions run on the B200
+engine through the C ABI:
+
+    _buildReport / _analyzePatterns (APO:498-625, 635-773) -> Engine.score(corpus=True)   (k_detect6)
+    beam evaluation + top-K (server side in the reference, consumed at APO:1138-1166)
+                                                         -> Engine.score                 (k_reward9 + radix top-K)
+
+Everything that is text or CRUD (descriptions, suggestions, segments, config) stays on the
+host, as in the reference.  Async reference methods are plain methods here; failures are
+swallowed with a `[APO]` warning and an empty result, never raised (APO:1211-1214).
+"""
+from __future__ import annotations
+
+import copy
+import json
+import math
+import time
+import uuid
+
+import numpy as np
+
+from .engine import DIM_NAMES, MODE_NAMES, SRC_DIMS, SRC_ROLLOUTS, Engine
+from .trace_collector import TraceCollectorService
+
+APO_STORAGE_KEY, APO_CONFIG_KEY, APO_SEGMENTS_KEY = "senweaver.apo.data", "senweaver.apo.config", "senweaver.apo.segments"
+MAX_REPORTS, MAX_SUGGESTIONS = 50, 200                                   # APO:276-277
+DEFAULT_APO_CONFIG = {                                                   # APO:279-292
+    "enabled": True, "autoAnalyzeEnabled": True, "autoAnalyzeIntervalMs": 3600000, "minTracesForAnalysis": 20,
+    "minFeedbacksForAnalysis": 10, "autoApplySuggestions": False, "uploadOptimizationsToServer": True,
+    "beamWidth": 4, "branchFactor": 4, "beamRounds": 3, "gradientBatchSize": 4,
+}
+SEVERITY = ("low", "medium", "high")
+DIM_CATEGORY = {                                                         # APO:576-586
+    "tool_success_rate": "tool_usage", "tool_call_reliability": "tool_usage", "tool_call_efficiency": "tool_usage",
+    "tool_duration_efficiency": "tool_usage", "token_efficiency": "context_management",
+    "response_efficiency": "core_behavior", "conversation_efficiency": "core_behavior",
+    "task_completion": "core_behavior", "user_feedback": "core_behavior",
+}
+PATTERN_TEXT = (                                                          # order of APO:643-770
+    ("Negative feedback follows conversations in which errors occurred", "core_behavior"),
+    ("Failed tool calls precede user dissatisfaction", "tool_usage"),
+    ("High token consumption coincides with poor feedback", "context_management"),
+    ("Several LLM calls (likely retries) still end in dissatisfaction", "core_behavior"),
+    ("Long multi-turn conversations still end in dissatisfaction", "core_behavior"),
+    ("Slow tool execution (>15 s total) coincides with dissatisfaction", "tool_usage"),
+)
+
+
+def _first_preview(trace, type_):
+    for sp in trace["spans"]:
+        if sp["type"] == type_:
+            return sp["data"].get("contentPreview") or ""
+    return ""
+
+
+class APOService:
+    def __init__(self, engine: Engine, traceCollectorService: TraceCollectorService, storageService=None,
+                 productService=None, requestService=None):
+        self._engine, self._tc = engine, traceCollectorService
+        self._storage, self._product, self._request = storageService, productService, requestService
+        self._reports, self._suggestions, self._segments = [], [], []
+        self._config = dict(DEFAULT_APO_CONFIG)
+        self._beamState, self._textualGradients = None, []
+        self._stateListeners, self._suggestionListeners = [], []
+        self._dirty = False
+        api = (getattr(productService, "senweaverApiConfig", None) or {}).get("apiBaseUrl") if productService else None
+        self._apoApiUrl = f"{api or 'https://ide-api.senweaver.com'}/api/apo"          # APO:328-329
+
+    # ---- events
+    def onDidChangeState(self, fn):
+        self._stateListeners.append(fn)
+
+    def onDidGenerateSuggestions(self, fn):
+        self._suggestionListeners.append(fn)
+
+    def _fire(self, listeners, *a):
+        for fn in list(listeners):
+            try:
+                fn(*a)
+            except Exception:
+                pass
+
+    # ---- analysis (APO:477-496)
+    def analyzePromptEffectiveness(self):
+        report = self._buildReport(self._tc.getAllTraces())
+        self._reports.append(report)
+        self._reports = self._reports[-MAX_REPORTS:]
+        self._dirty = True
+        self._fire(self._stateListeners)
+        return report
+
+    def _corpus_report(self, traces):
+        """Two corpus passes when some trace changed after it was scored (reward statistics use the
+        snapshot the reward was computed from, tallies and patterns the live counters); one otherwise."""
+        eng = self._engine
+        eng.dims_upload(np.full((1, 4, 9), np.nan, np.float32))
+        live = self._tc.corpus_records(traces)
+        eng.corpus_upload(live)
+        rep = eng.score(1, 0, corpus=True).report
+        snap = self._tc.corpus_records(traces, scored=True)
+        if snap.tobytes() != live.tobytes():
+            eng.corpus_upload(snap)
+            rew = eng.score(1, 0, corpus=True).report
+        else:
+            rew = rep
+        return rep, rew
+
+    def _buildReport(self, traces):
+        now = time.time() * 1000.0
+        starts = [t["startTime"] for t in traces]
+        if traces:
+            rep, rew = self._corpus_report(traces)
+            good, bad, none = int(rep.good), int(rep.bad), int(rep.none)
+            goodRate = float(rep.goodRate)
+            byMode = {}
+            for m, name in enumerate(MODE_NAMES):
+                tot, g, b = (int(x) for x in rep.byMode[m])
+                if tot:
+                    byMode[name] = {"total": tot, "good": g, "bad": b, "goodRate": float(rep.byModeGoodRate[m])}
+            avgReward = None if rew.withReward == 0 else float(rew.avgReward)
+            rewardByDimension = {DIM_NAMES[i]: {"sum": float(rew.dim[i].sum), "count": int(rew.dim[i].count), "avg": float(rew.dim[i].avg)}
+                                 for i in range(9) if rew.dim[i].count}
+        else:
+            rep = rew = None
+            good = bad = none = 0
+            goodRate, byMode, avgReward, rewardByDimension = 0, {}, None, {}
+
+        patterns = []
+        if rep is not None:
+            for p in range(6):                                              # APO:643-770
+                q = rep.pat[p]
+                if not q.flag:
+                    continue
+                text, cat = PATTERN_TEXT[p]
+                ex = []
+                for gi in q.examples:
+                    if gi < 0:
+                        continue
+                    t = traces[int(gi)]
+                    ex.append({"threadId": t["threadId"], "userMessagePreview": _first_preview(t, "user_message"),
+                               "assistantMessagePreview": self._example_detail(p, t), "feedback": t["summary"]["userFeedback"]})
+                patterns.append({"id": str(uuid.uuid4()), "description": text, "frequency": int(q.count),
+                                 "severity": SEVERITY[q.severity], "relatedCategory": cat, "examples": ex})
+            for i, name in enumerate(DIM_NAMES):                            # APO:574-596
+                d = rew.dim[i]
+                if d.count and d.low_flag:
+                    patterns.append({"id": str(uuid.uuid4()),
+                                     "description": f"{name} dimension reward signal consistently low (avg: {d.avg:.3f})",
+                                     "frequency": int(d.count), "severity": SEVERITY[d.low_severity],
+                                     "relatedCategory": DIM_CATEGORY.get(name, "core_behavior"), "examples": []})
+
+        suggestions = self._generateLocalSuggestions(goodRate, patterns, byMode, avgReward, rew)
+        report = {"id": str(uuid.uuid4()), "generatedAt": now,
+                  "period": {"from": min(starts) if starts else now, "to": (max(starts) if starts else 0) or now},
+                  "totalConversations": len(traces), "goodFeedbackCount": good, "badFeedbackCount": bad,
+                  "noFeedbackCount": none, "goodRate": goodRate, "byMode": byMode, "patterns": patterns,
+                  "suggestions": suggestions, "avgReward": avgReward, "rewardByDimension": rewardByDimension}
+        self._suggestions.extend(suggestions)
+        self._suggestions = self._suggestions[-MAX_SUGGESTIONS:]
+        if suggestions:
+            self._fire(self._suggestionListeners, suggestions)
+        return report
+
+    @staticmethod
+    def _example_detail(p, t):
+        s = t["summary"]
+        if p == 0:
+            return _first_preview(t, "assistant_message")
+        if p == 1:
+            for sp in t["spans"]:
+                if sp["type"] == "tool_call" and sp["data"].get("toolSuccess") is False:
+                    return f"Tool {sp['data'].get('toolName')} failed: {(sp['data'].get('toolResult') or '')[:100]}"
+            return "Tool undefined failed: "
+        if p == 2:
+            return f"Total tokens: {s['totalTokens']}"
+        if p == 3:
+            return f"LLM calls: {s['totalLLMCalls']}"
+        if p == 4:
+            return f"Conversation turns: {sum(1 for sp in t['spans'] if sp['type'] == 'user_message')}"
+        return f"Tool duration: {s['totalToolDurationMs'] / 1000:.1f}s"
+
+    def _generateLocalSuggestions(self, goodRate, patterns, byMode, avgReward, rew):
+        """APO:775-862: thresholds from the engine's flags, text on the host."""
+        out = []
+
+        def add(cat, prio, desc, why, impact):
+            out.append({"id": str(uuid.uuid4()), "targetCategory": cat, "type": "modify", "priority": prio,
+                        "description": desc, "reasoning": why, "estimatedImpact": impact, "status": "pending"})
+
+        if 0 < goodRate < 0.5:                                               # APO:785
+            extra = f" (avg reward: {avgReward:.3f})" if avgReward is not None else ""
+            add("core_behavior", "high", f"Overall approval rate is only {goodRate * 100:.1f}%{extra}; the prompt needs a broad revision",
+                "An approval rate under 50% points at a systemic prompt problem", "approval rate +10-20%")
+        if rew is not None:
+            for i, name in enumerate(DIM_NAMES):                             # APO:800-827
+                d = rew.dim[i]
+                if d.count and d.sugg_flag:
+                    add(DIM_CATEGORY.get(name, "core_behavior"), SEVERITY[d.sugg_priority],
+                        f"{name} dimension performing poorly (avg: {d.avg:.3f}, n={d.count})",
+                        f"The {name} reward dimension is negative on average", f"{name} reward +0.2-0.5")
+        for p in patterns:                                                   # APO:830-843
+            if p["severity"] == "high":
+                add(p["relatedCategory"], "high", f"High-frequency issue: {p['description']} (occurred {p['frequency']} times)",
+                    "Frequent, severe pattern: tighten the related prompt rules", f"about {min(p['frequency'], 5)} fewer such cases")
+        for mode, st in byMode.items():                                      # APO:846-859
+            if st["total"] >= 5 and st["goodRate"] < 0.3:
+                o = {"id": str(uuid.uuid4()), "targetCategory": "mode_specific", "type": "modify", "priority": "medium",
+                     "description": f"{mode} mode approval rate is only {st['goodRate'] * 100:.1f}%",
+                     "reasoning": "This mode is well below the average approval rate", "estimatedImpact": f"better {mode} mode approval",
+                     "status": "pending"}
+                out.append(o)
+        return out
+
+    # ---- beam evaluation: the step the reference delegates to its backend --------------------------------
+    def evaluateBeam(self, candidates, dims=None, rollouts=None):
+        """Score a beam of VersionedPromptTemplate candidates on their rollout outcomes and keep the
+        top `beamWidth` (score desc, ties -> lower index), then apply the APO:1138-1166 update with the
+        strict `>` adoption rule (APO:1159).  dims: float32 [C][T][9] (NaN = absent) or rollouts:
+        apo_record [C][T]."""
+        try:
+            C = len(candidates)
+            K = min(self._config["beamWidth"], C)
+            if dims is not None:
+                self._engine.dims_upload(np.ascontiguousarray(dims, np.float32))
+                res = self._engine.score(C, K, source=SRC_DIMS)
+            else:
+                self._engine.rollouts_upload(rollouts)
+                res = self._engine.score(C, K, source=SRC_ROLLOUTS)
+            beam = []
+            for c in res.topk:
+                tpl = dict(candidates[int(c)])
+                tpl["score"] = None if math.isinf(res.scores[c]) else float(res.scores[c])
+                beam.append(tpl)
+            best = beam[0] if beam and beam[0]["score"] is not None else None
+            self._applyBeamUpdate({"beam": beam, "bestPrompt": best, "bestScore": best["score"] if best else None,
+                                   "round": (self._beamState["currentRound"] + 1) if self._beamState else 1})
+            return res
+        except Exception as e:
+            print("[APO] Beam evaluation failed:", e)
+            return None
+
+    def _applyBeamUpdate(self, bu):
+        now = time.time() * 1000.0
+        if self._beamState is None:                                          # APO:1141-1152
+            self._beamState = {"currentRound": 0, "totalRounds": self._config["beamRounds"], "beam": [],
+                               "historyBestPrompt": None, "historyBestScore": -math.inf, "versionCounter": 0,
+                               "startedAt": now, "lastUpdatedAt": now}
+        st = self._beamState
+        if bu.get("beam"):
+            st["beam"] = bu["beam"]
+        if bu.get("round") is not None:
+            st["currentRound"] = bu["round"]
+        if bu.get("bestPrompt") and bu.get("bestScore") is not None and bu["bestScore"] > st["historyBestScore"]:   # APO:1159
+            st["historyBestPrompt"], st["historyBestScore"] = bu["bestPrompt"], bu["bestScore"]
+            self._applyBeamBestPrompt(bu["bestPrompt"])
+        st["lastUpdatedAt"] = now
+        self._dirty = True
+        self._fire(self._stateListeners)
+
+    def _applyBeamBestPrompt(self, best):
+        """APO:1219-1264: '- ' lines become individual optimized segments; otherwise replace/add one."""
+        now = time.time() * 1000.0
+        rules = [ln for ln in best["content"].split("\n") if ln.strip().startswith("- ")]
+
+        def new_seg(content):
+            return {"id": str(uuid.uuid4()), "category": "core_behavior", "content": content, "isActive": True,
+                    "isOptimized": True, "version": 1, "createdAt": now, "updatedAt": now}
+
+        if not rules:
+            seg = next((s for s in self._segments if s["category"] == "core_behavior" and s["isActive"]), None)
+            if seg:
+                seg["originalContent"] = seg.get("originalContent") or seg["content"]
+                seg.update(content=best["content"], isOptimized=True, version=seg["version"] + 1, updatedAt=now)
+            else:
+                self._segments.append(new_seg(best["content"]))
+            return
+        for r in rules:
+            text = r.strip()[1:].strip()
+            if text and not any(s["isActive"] and s["content"] == text for s in self._segments):
+                self._segments.append(new_seg(text))
+
+    def requestOptimizationFromServer(self):
+        """APO:992-1215.  Needs the closed backend; without a request service it returns [] like any
+        failed request in the reference.  A reply's beamUpdate goes through the same update rule."""
+        try:
+            if not self._reports:
+                self.analyzePromptEffectiveness()
+            if self._request is None:
+                print("[APO] Server optimization request failed: no request service")
+                return []
+            reply = self._request(f"{self._apoApiUrl}/optimize", {"version": "2.0.0", "report": self._reports[-1],
+                                  "beamConfig": {k: self._config[k] for k in ("beamWidth", "branchFactor", "beamRounds")}}) or {}
+            sugg = reply.get("suggestions") or []
+            for s in sugg:
+                s["id"] = s.get("id") or str(uuid.uuid4())
+                s["status"] = "pending"
+                self._suggestions.append(s)
+            if reply.get("beamUpdate"):
+                self._applyBeamUpdate(reply["beamUpdate"])
+            return sugg
+        except Exception as e:
+            print("[APO] Server optimization request failed:", e)
+            return []
+
+    def requestTextualGradient(self):
+        return None                                                           # LLM critique lives on the backend (APO:1268-1343)
+
+    # ---- segments / suggestions (APO:1360-1458)
+    def getActiveSegments(self):
+        return [s for s in self._segments if s["isActive"]]
+
+    def getOptimizedPromptForCategory(self, category):
+        segs = [s["content"] for s in self._segments if s["isActive"] and s["isOptimized"] and s["category"] == category]
+        return "\n".join(segs) if segs else None
+
+    def getOptimizedRules(self):
+        return [s["content"] for s in self._segments if s["isActive"] and s["isOptimized"]]
+
+    def _find(self, sid):
+        return next((s for s in self._suggestions if s["id"] == sid), None)
+
+    def applySuggestion(self, suggestionId):
+        s = self._find(suggestionId)
+        if not s or s["status"] != "pending":
+            return
+        if s.get("suggestedContent"):
+            now = time.time() * 1000.0
+            self._segments.append({"id": str(uuid.uuid4()), "category": s["targetCategory"], "content": s["suggestedContent"],
+                                   "isActive": True, "isOptimized": True, "version": 1, "createdAt": now, "updatedAt": now,
+                                   "fromSuggestion": s["id"]})
+        s["status"], s["appliedAt"] = "applied", time.time() * 1000.0
+        self._fire(self._stateListeners)
+
+    def rejectSuggestion(self, suggestionId):
+        s = self._find(suggestionId)
+        if s and s["status"] == "pending":
+            s["status"] = "rejected"
+            self._fire(self._stateListeners)
+
+    def revertSuggestion(self, suggestionId):
+        s = self._find(suggestionId)
+        if s and s["status"] == "applied":
+            self._segments = [g for g in self._segments if g.get("fromSuggestion") != s["id"]]
+            s["status"] = "reverted"
+            self._fire(self._stateListeners)
+
+    # ---- queries
+    def getLatestReport(self):
+        return self._reports[-1] if self._reports else None
+
+    def getPendingSuggestions(self):
+        return [s for s in self._suggestions if s["status"] == "pending"]
+
+    def getStats(self):
+        """APO:1470-1508; avgFinalReward = mean over the 20 most recent traces by startTime desc
+        (stable) with a non-null finalReward (APO:1478-1487) — 20 values, host side."""
+        traces = [t for t in self._tc.getAllTraces() if t["summary"]["finalReward"] is not None]
+        recent = sorted(traces, key=lambda t: -t["startTime"])[:20]
+        acc = 0
+        for t in recent:
+            acc = acc + t["summary"]["finalReward"]
+        last = self.getLatestReport()
+        st = self._beamState
+        return {"totalReports": len(self._reports), "totalSuggestions": len(self._suggestions),
+                "appliedSuggestions": sum(1 for s in self._suggestions if s["status"] == "applied"),
+                "rejectedSuggestions": sum(1 for s in self._suggestions if s["status"] == "rejected"),
+                "activeSegments": len(self.getActiveSegments()),
+                "optimizedSegments": sum(1 for s in self._segments if s["isActive"] and s["isOptimized"]),
+                "lastAnalysisTime": last["generatedAt"] if last else None, "currentGoodRate": last["goodRate"] if last else None,
+                "beamSearchActive": st is not None and st["currentRound"] < st["totalRounds"],
+                "beamCurrentRound": st["currentRound"] if st else None,
+                "beamBestScore": st["historyBestScore"] if st and st["historyBestScore"] != -math.inf else None,
+                "totalTextualGradients": len(self._textualGradients),
+                "avgFinalReward": acc / len(recent) if recent else None}
+
+    def getConfig(self):
+        return dict(self._config)
+
+    def setConfig(self, config):
+        self._config.update(config)
+        self._dirty = True
+
+    def getBeamState(self):
+        return copy.deepcopy(self._beamState)
+
+    def getTextualGradients(self, limit=None):
+        return self._textualGradients[-(limit or 10):]
+
+    def exportState(self):
+        return json.dumps({"reports": self._reports, "suggestions": self._suggestions, "segments": self._segments,
+                           "beamState": self._beamState, "config": self._config}, default=str)

@@ -118,7 +118,12 @@ void build_luts(apo_engine *e) {
 		for (int i = 0; i < APO_NDIM; i++) if (m & (1u << i)) tw += e->W.w[i];
 		if (!(tw > 0.0)) tw = 1.0;                  // finalReward stays null; kernels never count it
 		e->lut_tw[m] = tw;
-		e->lut_rc[m] = 1.0 / tw;
+		// K1 divides by multiplying with RN(1/tw) + one FMA correction (Markstein); that is only
+		// proven correctly rounded when the significand of tw is not all ones — flag those masks
+		// with a negative reciprocal so the kernel takes the generic IEEE division for them.
+		uint64_t bits; memcpy(&bits, &tw, 8);
+		const bool all_ones = (bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull;
+		e->lut_rc[m] = all_ones ? -(1.0 / tw) : 1.0 / tw;
 	}
 }
 
@@ -303,16 +308,6 @@ extern "C" int apo_set_weights(apo_engine *e, const double w[APO_NDIM]) {
 	for (int i = 0; i < APO_NDIM; i++)
 		if (!std::isfinite(w[i]) || !(w[i] == 0.0 || (w[i] >= 1e-100 && w[i] <= 1e100)))
 			return fail(e, APO_E_ARG, "weights must be 0 or within [1e-100, 1e100]");
-	{   // the LUT division (csrc/apo_kernels.cu div_lut) needs RN(1/tw) to be within the Markstein bound
-		apo::Weights t; memcpy(t.w, w, sizeof t.w);
-		for (uint32_t m = 1; m < 512; m++) {
-			double tw = 0.0;
-			for (int i = 0; i < APO_NDIM; i++) if (m & (1u << i)) tw += t.w[i];
-			uint64_t bits; memcpy(&bits, &tw, 8);
-			if (tw > 0.0 && (bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull)
-				return fail(e, APO_E_ARG, "weights produce a total weight whose significand is all ones (mask %u)", m);
-		}
-	}
 	CK(cudaSetDevice(e->device));
 	memcpy(e->W.w, w, sizeof e->W.w);
 	build_luts(e);

@@ -37,16 +37,24 @@ struct K1Cfg {
 // ws / tw, correctly rounded, without the generic division's special-case branch (which
 // would serialise the four evaluations a thread interleaves): y = RN(1/tw) comes from the
 // LUT, q = RN(ws*y), r = ws - tw*q (exact, one FMA), result = RN(q + r*y).  By Markstein's
-// theorem this is the correctly rounded quotient when y is the correctly rounded reciprocal
-// and nothing underflows — guaranteed here: tw is one of <= 511 sums of validated weights
-// (apo_set_weights rejects nonzero weights below 1e-100, and LUT entries whose significand is
-// all ones) and |ws| is 0 or >= 2^-160 (fp32 inputs x weights).
+// theorem this is the correctly rounded quotient when y is the correctly rounded reciprocal,
+// the significand of tw is not all ones, and nothing underflows — tw is one of <= 511 sums of
+// validated weights (apo_set_weights: 0 or within [1e-100,1e100]) and |ws| is 0 or >= 2^-160
+// (fp32 inputs x weights).  Masks whose total weight has an all-ones significand (e.g. weights
+// that sum to 0.9999999999999999) are flagged by the host with a NEGATIVE reciprocal and take
+// the generic IEEE division instead.
 template <bool RECIP>
-__device__ __forceinline__ double div_lut(double ws, double2 t) {
-	const double q = __dmul_rn(ws, t.y);
+__device__ __forceinline__ double div_fast(double ws, double2 t) {
+	const double y = fabs(t.y);
+	const double q = __dmul_rn(ws, y);
 	if (RECIP) return q;
 	const double r = __fma_rn(-t.x, q, ws);
-	return __fma_rn(r, t.y, q);
+	return __fma_rn(r, y, q);
+}
+template <bool RECIP>
+__device__ __forceinline__ double div_lut(double ws, double2 t) {
+	if (!RECIP && t.y < 0.0) return __ddiv_rn(ws, t.x);
+	return div_fast<RECIP>(ws, t);
 }
 
 // The shared-memory LUT is indexed by a bit-rotated presence mask: dims 5..8 (the ones that
@@ -57,9 +65,10 @@ __device__ __forceinline__ uint32_t lut_index(uint32_t natural_mask) {
 	return ((natural_mask >> 5) | (natural_mask << 4)) & 511u;
 }
 
-template <bool RECIP>
-__device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const Weights &W, const double2 *lut,
-                                               uint32_t &valid) {
+// One Form-D evaluation, first half: 9 fp32 (NaN = absent) -> weighted sum in push order and
+// the LUT entry {total weight, reciprocal} of its presence mask (TCS:777-783).
+__device__ __forceinline__ void eval_ws(const float (&v)[APO_NDIM], const Weights &W, const double2 *lut,
+                                        double &ws_out, double2 &t_out, uint32_t &valid) {
 	double ws = 0.0;
 	uint32_t mask = 0;
 #pragma unroll
@@ -70,9 +79,17 @@ __device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const
 		ws = __dadd_rn(ws, __dmul_rn((double)g, W.w[i]));
 		mask |= (p ? 1u : 0u) << lut_bit(i);
 	}
-	const double fr = div_lut<RECIP>(ws, lut[mask]);  // lut[0] == {1,1}: ws == 0 -> 0
+	ws_out = ws;
+	t_out = lut[mask];                                // lut[0] == {1,1}: ws == 0 -> 0
 	valid = mask != 0 ? 1u : 0u;
-	return to_fx(fr);
+}
+
+template <bool RECIP>
+__device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const Weights &W, const double2 *lut,
+                                               uint32_t &valid) {
+	double ws; double2 t;
+	eval_ws(v, W, lut, ws, t, valid);
+	return to_fx(div_lut<RECIP>(ws, t));              // TCS:784
 }
 
 template <bool RECIP>
@@ -171,15 +188,26 @@ k_reward9(const K1Params P) {
 					const float4 x = src[q];
 					f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
 				}
-				long long x4 = 0;
+				double ws4[4]; double2 t4[4];
 #pragma unroll
 				for (int k = 0; k < 4; k++) {
 					float v[APO_NDIM];
 #pragma unroll
 					for (int i = 0; i < APO_NDIM; i++) v[i] = f[9 * k + i];
 					uint32_t ok;
-					x4 += eval_dims<RECIP>(v, W, s_lut, ok);      // |fr| <= 512 -> |x| < 2^61: four terms fit int64
+					eval_ws(v, W, s_lut, ws4[k], t4[k], ok);
 					cnt += ok;
+				}
+				// one uniform check for the (rare) flagged masks keeps the four divisions branch-free
+				const bool generic = !RECIP && ((__double2hiint(t4[0].y) | __double2hiint(t4[1].y) |
+				                                 __double2hiint(t4[2].y) | __double2hiint(t4[3].y)) < 0);
+				long long x4 = 0;                         // |fr| <= 512 -> |x| < 2^61: four terms fit int64
+				if (!generic) {
+#pragma unroll
+					for (int k = 0; k < 4; k++) x4 += to_fx(div_fast<RECIP>(ws4[k], t4[k]));
+				} else {
+#pragma unroll
+					for (int k = 0; k < 4; k++) x4 += to_fx(div_lut<RECIP>(ws4[k], t4[k]));
 				}
 				acc.add(x4);
 			} else if (e0 < n) {
@@ -246,6 +274,7 @@ int k1_tile_evals(int row, int variant) {
 	case 1: return K1Cfg<36, 16, 3>::TILE;
 	case 2: return K1Cfg<36, 12, 4>::TILE;
 	case 3: return K1Cfg<36, 20, 2>::TILE;
+	case 4: return K1Cfg<36, 24, 2>::TILE;
 	default: return K1Cfg<36, 8, 5>::TILE;
 	}
 }
@@ -262,6 +291,7 @@ cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_cou
 		case 1: return launch_k1<36, 16, 3>(P, grid, recip, st);
 		case 2: return launch_k1<36, 12, 4>(P, grid, recip, st);
 		case 3: return launch_k1<36, 20, 2>(P, grid, recip, st);
+		case 4: return launch_k1<36, 24, 2>(P, grid, recip, st);
 		default: return launch_k1<36, 8, 5>(P, grid, recip, st);
 		}
 	} else {
@@ -269,6 +299,7 @@ cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_cou
 		case 1: return launch_k1<32, 16, 3>(P, grid, recip, st);
 		case 2: return launch_k1<32, 12, 4>(P, grid, recip, st);
 		case 3: return launch_k1<32, 20, 2>(P, grid, recip, st);
+		case 4: return launch_k1<32, 24, 2>(P, grid, recip, st);
 		default: return launch_k1<32, 8, 5>(P, grid, recip, st);
 		}
 	}
@@ -292,7 +323,11 @@ __device__ __forceinline__ void ex_insert(unsigned long long *slots, unsigned lo
 
 __device__ void finalize_block(const FinalizeParams &F);
 
-__global__ void __launch_bounds__(K2_THREADS)
+// Lane-local sums are plain int64 (|term| <= 2^52) and are flushed every K2_CHUNK records per
+// thread, so they cannot overflow; the flush adds exact limb sums with integer atomics.
+constexpr int K2_CHUNK = 256;
+
+__global__ void __launch_bounds__(K2_THREADS, 2)
 k_detect6(const K2Params P) {
 	__shared__ unsigned long long s_ex[APO_NPAT * 3];
 	__shared__ bool s_last;
@@ -300,85 +335,99 @@ k_detect6(const K2Params P) {
 	if (tid < APO_NPAT * 3) s_ex[tid] = ~0ull;
 	__syncthreads();
 
-	uint32_t cn[CN_TOTAL];
-#pragma unroll
-	for (int i = 0; i < CN_TOTAL; i++) cn[i] = 0;
-	Acc128 fx[1 + APO_NDIM];
-#pragma unroll
-	for (int i = 0; i < 1 + APO_NDIM; i++) fx[i].zero();
-	unsigned long long tool[3] = {0, 0, 0};
 	const Weights W = P.W;
-
+	long long *corp = P.acc + (uint64_t)ACC_PER_CAND * P.C;
 	const uint4 *src = reinterpret_cast<const uint4 *>(P.recs);
-	for (uint64_t t = (uint64_t)blockIdx.x * K2_THREADS + tid; t < P.T; t += (uint64_t)gridDim.x * K2_THREADS) {
-		union { uint4 q[2]; apo_record r; } u;
-		u.q[0] = __ldg(src + 2 * t); u.q[1] = __ldg(src + 2 * t + 1);
-		const apo_record &r = u.r;
-		const bool good = r.feedback == 1, bad = r.feedback == 2;
-		cn[CN_GOOD] += good; cn[CN_BAD] += bad; cn[CN_NONE] += (!good && !bad);     // APO:513-516
-		const uint32_t m = r.mode < APO_NMODE ? r.mode : 0u;                         // APO:519-525, 627-633
-#pragma unroll
-		for (int k = 0; k < APO_NMODE; k++) {
-			const bool is = (m == (uint32_t)k);
-			cn[CN_MODE + 3 * k] += is; cn[CN_MODE + 3 * k + 1] += (is && good); cn[CN_MODE + 3 * k + 2] += (is && bad);
-		}
-		tool[0] += r.toolCalls; tool[1] += r.toolSucc; tool[2] += r.toolFail;       // TCS:603-605
+	const uint64_t stride = (uint64_t)gridDim.x * K2_THREADS;
+	uint64_t t = (uint64_t)blockIdx.x * K2_THREADS + tid;
+	// every warp runs the same number of chunk rounds (the flush uses full-warp collectives)
+	const uint64_t per_thread = (P.T + stride - 1) / stride;
+	const uint64_t rounds = (per_thread + K2_CHUNK - 1) / K2_CHUNK;
 
-		if (r.flags & APO_F_VALID) {                                                 // APO:550, TCS:606
-			double d[APO_NDIM];
-			const uint32_t mask = reward_dims(r, d);
-			const double fr = final_reward<false>(d, mask, W, P.lut);
-			fx[0].add(to_fx(fr));
-			cn[CN_RW]++;
+	for (uint64_t round = 0; round < rounds; round++) {
+		uint32_t cn[CN_TOTAL];
 #pragma unroll
-			for (int i = 0; i < APO_NDIM; i++) {                                     // APO:556-565
-				const bool p = (mask >> i) & 1u;
-				fx[1 + i].add(p ? to_fx(d[i]) : 0ll);
-				cn[CN_DIM + i] += p;
+		for (int i = 0; i < CN_TOTAL; i++) cn[i] = 0;
+		long long fx[1 + APO_NDIM];
+#pragma unroll
+		for (int i = 0; i < 1 + APO_NDIM; i++) fx[i] = 0;
+		unsigned long long tool[3] = {0, 0, 0};
+
+		for (int it = 0; it < K2_CHUNK && t < P.T; it++, t += stride) {
+			union { uint4 q[2]; apo_record r; } u;
+			u.q[0] = __ldg(src + 2 * t); u.q[1] = __ldg(src + 2 * t + 1);
+			const apo_record &r = u.r;
+			const bool good = r.feedback == 1, bad = r.feedback == 2;
+			cn[CN_GOOD] += good; cn[CN_BAD] += bad; cn[CN_NONE] += (!good && !bad);     // APO:513-516
+			const uint32_t m = r.mode < APO_NMODE ? r.mode : 0u;                         // APO:519-525, 627-633
+#pragma unroll
+			for (int k = 0; k < APO_NMODE; k++) {
+				const bool is = (m == (uint32_t)k);
+				cn[CN_MODE + 3 * k] += is; cn[CN_MODE + 3 * k + 1] += (is && good); cn[CN_MODE + 3 * k + 2] += (is && bad);
 			}
-		}
-		if (bad) {                                                                   // APO:644-755: every predicate ANDs 'bad'
-			const unsigned long long gi = P.idx_base + t;
-			const bool hit[APO_NPAT] = {
-			    (r.flags & APO_F_ERRORS) != 0,       // P1 APO:644
-			    (r.flags & APO_F_FAILSPAN) != 0,     // P2 APO:666-670
-			    r.tokens > 10000u,                   // P3 APO:693
-			    r.llmCalls > 2u,                     // P4 APO:713
-			    r.userMsgs >= 4u,                    // P5 APO:733-734
-			    (double)r.toolDurMs > 15000.0,       // P6 APO:754
-			};
+			tool[0] += r.toolCalls; tool[1] += r.toolSucc; tool[2] += r.toolFail;       // TCS:603-605
+
+			if (r.flags & APO_F_VALID) {                                                 // APO:550, TCS:606
+				double d[APO_NDIM];
+				const uint32_t mask = reward_dims(r, d);
+				double ws = 0.0;
 #pragma unroll
-			for (int p = 0; p < APO_NPAT; p++) {
-				if (hit[p]) {
-					cn[CN_PAT + p]++;
-					if (gi < *((volatile unsigned long long *)&s_ex[3 * p + 2])) ex_insert(&s_ex[3 * p], gi);           // slice(0,3): first three in corpus order
+				for (int i = 0; i < APO_NDIM; i++) ws = __dadd_rn(ws, __dmul_rn(d[i], W.w[i]));
+				const double fr = div_lut<false>(ws, make_double2(__ldg(P.lut + mask), __ldg(P.lut + 512 + mask)));
+				fx[0] += to_fx(fr);
+				cn[CN_RW]++;
+#pragma unroll
+				for (int i = 0; i < APO_NDIM; i++) {                                     // APO:556-565
+					const bool p = (mask >> i) & 1u;
+					fx[1 + i] += p ? to_fx(d[i]) : 0ll;
+					cn[CN_DIM + i] += p;
+				}
+			}
+			if (bad) {                                                                   // APO:644-755: every predicate ANDs 'bad'
+				const unsigned long long gi = P.idx_base + t;
+				const bool hit[APO_NPAT] = {
+				    (r.flags & APO_F_ERRORS) != 0,       // P1 APO:644
+				    (r.flags & APO_F_FAILSPAN) != 0,     // P2 APO:666-670
+				    r.tokens > 10000u,                   // P3 APO:693
+				    r.llmCalls > 2u,                     // P4 APO:713
+				    r.userMsgs >= 4u,                    // P5 APO:733-734
+				    (double)r.toolDurMs > 15000.0,       // P6 APO:754
+				};
+#pragma unroll
+				for (int p = 0; p < APO_NPAT; p++) {
+					if (hit[p]) {
+						cn[CN_PAT + p]++;
+						// slice(0,3): first three in corpus order
+						if (gi < *((volatile unsigned long long *)&s_ex[3 * p + 2])) ex_insert(&s_ex[3 * p], gi);
+					}
 				}
 			}
 		}
-	}
 
-	// ---- block-level: warp reduce, then global integer atomics
-	long long *corp = P.acc + (uint64_t)ACC_PER_CAND * P.C;
+		// ---- flush this chunk: warp reduce, then global integer atomics
 #pragma unroll
-	for (int i = 0; i < CN_TOTAL; i++) {
-		const uint32_t s = warp_sum_u32(cn[i]);
-		if (lane == 0 && s) {
-			int w;
-			if (i < 3) w = CORP_TALLY + i;
-			else if (i < CN_PAT) w = CORP_MODE + (i - CN_MODE);
-			else if (i < CN_DIM) w = CORP_PAT + (i - CN_PAT);
-			else if (i < CN_RW) w = CORP_DIM + 4 * (i - CN_DIM) + 3;
-			else w = CORP_REWARD + 3;
-			atomicAdd((unsigned long long *)corp + w, (unsigned long long)s);
+		for (int i = 0; i < CN_TOTAL; i++) {
+			const uint32_t s = warp_sum_u32(cn[i]);
+			if (lane == 0 && s) {
+				int w;
+				if (i < 3) w = CORP_TALLY + i;
+				else if (i < CN_PAT) w = CORP_MODE + (i - CN_MODE);
+				else if (i < CN_DIM) w = CORP_PAT + (i - CN_PAT);
+				else if (i < CN_RW) w = CORP_DIM + 4 * (i - CN_DIM) + 3;
+				else w = CORP_REWARD + 3;
+				atomicAdd((unsigned long long *)corp + w, (unsigned long long)s);
+			}
 		}
-	}
-	flush_acc128(fx[0], corp + CORP_REWARD, lane);
 #pragma unroll
-	for (int i = 0; i < APO_NDIM; i++) flush_acc128(fx[1 + i], corp + CORP_DIM + 4 * i, lane);
+		for (int i = 0; i < 1 + APO_NDIM; i++) {
+			Acc128 a; a.lo = (unsigned long long)fx[i]; a.hi = fx[i] >> 63;
+			flush_acc128(a, i == 0 ? corp + CORP_REWARD : corp + CORP_DIM + 4 * (i - 1), lane);
+		}
 #pragma unroll
-	for (int i = 0; i < 3; i++) {
-		const unsigned long long s = warp_sum_u64(tool[i]);
-		if (lane == 0 && s) atomicAdd((unsigned long long *)corp + CORP_TOOL + i, s);
+		for (int i = 0; i < 3; i++) {
+			const unsigned long long s = warp_sum_u64(tool[i]);
+			if (lane == 0 && s) atomicAdd((unsigned long long *)corp + CORP_TOOL + i, s);
+		}
 	}
 	__syncthreads();
 	if (tid < APO_NPAT) {
@@ -411,7 +460,7 @@ k_detect6(const K2Params P) {
 
 cudaError_t run_detect6(const K2Params &P, int sm_count, cudaStream_t st) {
 	uint64_t want = (P.T + K2_THREADS - 1) / K2_THREADS;
-	int grid = sm_count * 4;
+	int grid = sm_count * 2;            // two resident CTAs per SM (launch bounds), one wave
 	if ((uint64_t)grid > want) grid = (int)(want ? want : 1);
 	k_detect6<<<grid, K2_THREADS, 0, st>>>(P);
 	return cudaGetLastError();

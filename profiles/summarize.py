@@ -1,0 +1,47 @@
+"""Condense an .ncu-rep (ncu --set full) into the handful of metrics the roofline argument uses.
+    python profiles/summarize.py gpurun_out/prof.ncu-rep > profiles/<name>.txt
+"""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "sm__cycles_elapsed.avg", "lts__t_sector_hit_rate.pct",
+]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        print(f"== {name}")
+        for i, h in enumerate(hdr):
+            if h in KEYS or ("issue_stalled" in h and h.endswith("per_issue_active.ratio")):
+                try:
+                    v = float(r[i].replace(",", ""))
+                except ValueError:
+                    continue
+                if "issue_stalled" in h and v < 0.05:
+                    continue
+                print(f"{h:95s} {units[i]:12s} {r[i]}")
+        t = float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))
+        tu = units[hdr.index("gpu__time_duration.sum")]
+        scale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(tu, 1e-9)
+        rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", ""))
+        ru = units[hdr.index("dram__bytes_read.sum")]
+        bs = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(ru, 1)
+        print(f"derived: dram read {rd * bs / 1e9:.3f} GB in {t * scale * 1e3:.3f} ms (under ncu, cold) = {rd * bs / (t * scale) / 1e9:.1f} GB/s")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -78,7 +78,7 @@ def test_generators_match_oracle(engine, orc):
 
 # ------------------------------------------------------------------ K1 + top-K, Form D
 @pytest.mark.parametrize("C,T,K", [(4, 1000, 4), (3, 1, 1), (5, 4099, 2), (7, 1023, 7), (64, 20001, 16), (2, 1025, 1)])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_score_dims_matches_oracle(engine, orc, C, T, K, variant):
     dims = orc.gen_dims(0x5EED0000 + C, 0, C, 0, T, 300, 8)
     engine.dims_upload(dims)

@@ -1,0 +1,66 @@
+"""Record-axis sharding over >= 2 B200s through the C ABI's own NCCL join (-m gpu; skipped on
+a 1-GPU box).  Every rank must return the same scores / top-K / report as the unsharded
+single-GPU call, and the joined integer partials must be bit-identical to it."""
+import os
+import socket
+import sys
+from importlib import import_module
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+C, T, K, SEED = 12, 400_003, 5, 0x5EED0005
+
+
+def worker(rank, world, uid_path, out_dir):
+    sys.path.insert(0, ROOT)
+    pkg = import_module("senweaver-ide_b200")
+    torch.cuda.set_device(rank)
+    eng = pkg.Engine(rank)
+    uid = open(uid_path, "rb").read()
+    eng.comm_init(world, rank, uid)
+    first, last = pkg.sharding.shard_range(T, world, rank)
+    eng.dims_generate(SEED, 0, C, first, last - first, 300)
+    eng.corpus_generate(SEED, first, last - first, 300)
+    res = eng.score(C, K, corpus=True)
+    sums, counts = eng.debug_partials(C)            # after the allreduce: the joined integers
+    rep = res.report
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), scores=res.scores, counts=res.counts, topk=res.topk,
+             sums=np.array([str(s) for s in sums]), pat=np.array([[rep.pat[p].count, *rep.pat[p].examples] for p in range(6)]),
+             tallies=np.array([rep.total, rep.good, rep.bad, rep.none, rep.withReward]), avg=np.array([rep.avgReward]),
+             launches=np.array([res.timing.launches]))
+    eng.close()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_score_equals_single_gpu(tmp_path, engine, orc, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    pkg = import_module("senweaver-ide_b200")
+    uid_path = tmp_path / "uid.bin"
+    uid_path.write_bytes(pkg.Engine.comm_unique_id())
+    mp.spawn(worker, args=(world, str(uid_path), str(tmp_path)), nprocs=world, join=True)
+    engine.dims_generate(SEED, 0, C, 0, T, 300)
+    engine.corpus_generate(SEED, 0, T, 300)
+    ref = engine.score(C, K, corpus=True)
+    rsums, rcounts = engine.debug_partials(C)
+    for r in range(world):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert [int(s) for s in z["sums"]] == rsums
+        assert np.array_equal(z["counts"], ref.counts) and np.array_equal(z["scores"], ref.scores)
+        assert np.array_equal(z["topk"], ref.topk)
+        assert list(z["tallies"]) == [ref.report.total, ref.report.good, ref.report.bad, ref.report.none, ref.report.withReward]
+        assert z["avg"][0] == ref.report.avgReward
+        for p in range(6):
+            assert list(z["pat"][p]) == [ref.report.pat[p].count, *ref.report.pat[p].examples]
+        assert z["launches"][0] == 4                 # K1, K2, ncclAllReduce, K3
+    # and the single-GPU result itself is pinned to the oracle on a window
+    d = orc.gen_dims(SEED, 3, 1, 0, 50_000, 300, 8)
+    engine.score(C, 1, first=0, count=50_000)
+    s, n = engine.debug_partials(C)
+    es, en = orc.score_dims_fx(d)
+    assert s[3] == es[0] and n[3] == en[0]

@@ -156,6 +156,16 @@ typedef struct apo_score_opts {
  * any output pointer may be NULL. */
 int apo_score(apo_engine *e, const apo_score_opts *o, double *scores, uint64_t *counts,
               int32_t *topk, apo_corpus_report *report);
+/* Chunked form of apo_score for evaluation sets that exceed device memory (BASELINE
+ * configs[4]: 1024 x 100M = 3.7 TB): begin zeroes the accumulators for C_total candidates;
+ * each accumulate streams the currently loaded dims/rollouts (a chunk of candidates and/or
+ * a window of records) into candidates [cand_offset, cand_offset + C_loaded); finish runs the
+ * corpus scan, the cross-rank join and the top-K over all C_total.  apo_score ==
+ * begin + one accumulate + finish. */
+int apo_score_begin(apo_engine *e, uint32_t C_total);
+int apo_score_accumulate(apo_engine *e, const apo_score_opts *o, uint32_t cand_offset);
+int apo_score_finish(apo_engine *e, const apo_score_opts *o, double *scores, uint64_t *counts,
+                     int32_t *topk, apo_corpus_report *report);
 /* End to end from host memory without keeping the evaluations resident: streams
  * dims[C][T][9] through a double-buffered device window (H2D overlapped with K1). */
 int apo_score_host(apo_engine *e, const apo_score_opts *o, const float *dims, uint32_t C, uint64_t T,

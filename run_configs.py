@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Runs the five BASELINE.json configs through the C ABI and prints one JSON line per config
+(device-time of K1/K1r from CUDA events, achieved GB/s against the measured HBM peak).
+
+    python run_configs.py [--configs 1,2,3,4,5]
+    python -m torch.distributed.run --nproc-per-node N ... run_configs.py --configs 3,5
+
+bench.py is the driver-facing benchmark (configs[2]); this script covers the other rows:
+  1  4 x 1k   Form R records -> single-trace path + score                       (plumbing)
+  2  64 x 1M  Form D resident, fused finalReward + radix top-K (K=4 and K=16)
+  3  256 x 10M Form D + 10M-record corpus, 6-pattern detector fused
+  4  128 x 5M per-(c,t) Form R (K1r: dims derived on device), normal / agent / mixed thresholds
+  5  1024 x 100M Form D sharded over the ranks, candidate-chunked passes (3.7 TB does not fit),
+     generation excluded from (and reported beside) the kernel time
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,3,4")
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module("senweaver-ide_b200")
+    eng = pkg.Engine(local)
+    if world > 1:
+        box = [pkg.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(world, rank, box[0])
+    PK = peak()
+
+    def emit(d):
+        if rank == 0:
+            print(json.dumps(d), flush=True)
+
+    def timed(fn, reps):
+        fn()
+        k1, tot = [], []
+        for _ in range(reps):
+            r = fn()
+            k1.append(r.timing.reward_ms); tot.append(r.timing.total_ms)
+        return r, float(np.mean(k1)), float(np.mean(tot))
+
+    for cfg in [int(x) for x in args.configs.split(",")]:
+        seed = 0x5EED0000 + cfg
+        if cfg == 1:
+            C, T = 4, 1000
+            eng.rollouts_generate(seed, 0, C, 0, T, 300)
+            recs = np.stack([eng.rollouts_download(c, 0, T) for c in range(C)])
+            t0 = time.perf_counter()
+            dims, masks, finals = eng.reward_batch(recs.reshape(-1))            # TCS:668-788 per trace
+            f32 = np.where(np.isnan(finals)[:, None], np.nan, dims).astype(np.float32).reshape(C, T, 9)
+            eng.dims_upload(f32)
+            eng.corpus_upload(recs[0])
+            r = eng.score(C, 2, corpus=True)
+            emit({"config": 1, "C": C, "T": T, "wall_ms": (time.perf_counter() - t0) * 1e3, "topk": r.topk.tolist(),
+                  "scores": r.scores.tolist(), "note": "plumbing: Form R -> apo_reward_batch -> Form D -> apo_score (GPU path; Node.js itself is unavailable here)"})
+        elif cfg in (2, 3):
+            C, T = (64, 1_000_000) if cfg == 2 else (256, 10_000_000)
+            first, last = pkg.sharding.shard_range(T * world, world, rank) if cfg == 3 else (0, T)
+            if cfg == 3:
+                T = last - first
+            eng.dims_generate(seed, 0, C, first, T, 300)
+            eng.corpus_generate(seed, first, T, 300)
+            for K in ((4, 16) if cfg == 2 else (64,)):
+                r, k1, tot = timed(lambda: eng.score(C, K, corpus=(cfg == 3)), args.reps)
+                gbs = 36.0 * C * T / (k1 * 1e-3) / 1e9
+                emit({"config": cfg, "C": C, "T_per_gpu": T, "n_gpus": world, "K": K, "k1_ms": k1, "step_ms": tot,
+                      "evals_per_s": C * T * world / (tot * 1e-3), "k1_GBps": gbs, "frac_of_measured_peak": gbs / PK,
+                      "frac_of_8TBps": gbs / 8000.0, "topk_head": r.topk[:4].tolist()})
+        elif cfg == 4:
+            C, T = 128, 5_000_000
+            for name, apm in (("all-normal", 0), ("all-agent", 1024), ("mixed 50/50", 512)):
+                eng.rollouts_generate(seed, 0, C, 0, T, apm)
+                r, k1, tot = timed(lambda: eng.score(C, 32, source=pkg.SRC_ROLLOUTS), args.reps)
+                gbs = 32.0 * C * T / (k1 * 1e-3) / 1e9
+                emit({"config": 4, "thresholds": name, "C": C, "T": T, "k1r_ms": k1, "step_ms": tot, "evals_per_s": C * T / (tot * 1e-3),
+                      "k1r_GBps": gbs, "frac_of_measured_peak": gbs / PK, "topk_head": r.topk[:4].tolist()})
+        elif cfg == 5:
+            C, Tg = 1024, 100_000_000
+            first, last = pkg.sharding.shard_range(Tg, world, rank)
+            T = last - first
+            free, _ = torch.cuda.mem_get_info()
+            Cc = max(1, min(C, int((free - (6 << 30)) // (((T + 31) // 32 * 32) * 36))))
+            Cc = 1 << (Cc.bit_length() - 1)                                   # power of two chunk
+            gen_s, passes = 0.0, 0
+            eng.score_begin(C)
+            for c0 in range(0, C, Cc):
+                g0 = time.perf_counter()
+                eng.dims_generate(seed, c0, Cc, first, T, 300)
+                gen_s += time.perf_counter() - g0
+                eng.score_accumulate(c0)
+                passes += 1
+            r = eng.score_finish(C, 256)
+            k1 = r.timing.reward_ms
+            gbs = 36.0 * C * T / (k1 * 1e-3) / 1e9
+            join = r.timing.allreduce_ms + r.timing.finalize_ms + r.timing.corpus_ms
+            emit({"config": 5, "C": C, "T_global": Tg, "T_per_gpu": T, "n_gpus": world, "chunk_candidates": Cc, "passes": passes,
+                  "k1_ms_sum": k1, "join_ms": join, "evals_per_s_kernels": C * Tg / ((k1 + join) * 1e-3),
+                  "k1_GBps_per_gpu": gbs, "frac_of_measured_peak": gbs / PK, "generation_s_excluded": gen_s,
+                  "topk_head": r.topk[:4].tolist(), "counts_ok": bool((r.counts > 0).all())})
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/apo_b200.h"
 #include "apo_kernels.h"
@@ -95,6 +96,9 @@ struct apo_engine {
 
 	void *comm = nullptr; int nranks = 1, rank = 0;
 	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+	std::vector<cudaEvent_t> k1_ev;      // start/stop pairs of the K1 launches of the current scoring call
+	size_t k1_used = 0;
+	uint32_t score_C = 0; bool scoring = false;
 	apo_timing timing{};
 };
 
@@ -180,7 +184,33 @@ int begin_score(apo_engine *e, uint32_t C) {
 	CK(cudaMemsetAsync(e->acc.p, 0, acc_words(C, e->nranks) * 8, e->stream));
 	CK(cudaMemsetAsync(e->misc.p, 0xFF, 18 * 8, e->stream));
 	CK(cudaMemsetAsync(e->misc.p + 18, 0, 8, e->stream));
-	e->last_C = C;
+	e->last_C = C; e->score_C = C; e->scoring = true; e->k1_used = 0;
+	e->timing = apo_timing{};
+	CK(cudaEventRecord(e->ev[0], e->stream));
+	return APO_OK;
+}
+
+// one K1 launch over [first, first+count) of the loaded source into candidates [cand_offset, ...)
+int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_offset, uint64_t first, uint64_t count) {
+	const bool raw = o->source == APO_SRC_ROLLOUTS;
+	const uint32_t C = raw ? e->roll_C : e->dims_C;
+	apo::K1Params P{};
+	const int row = raw ? 32 : 36;
+	const uint64_t pitch = raw ? e->roll_pitch : e->dims_pitch;
+	P.base = (raw ? (const uint8_t *)e->roll.p : (const uint8_t *)e->dims_ptr) + first * row;
+	P.pitch_bytes = pitch * row;
+	P.C = C; P.T = count; P.acc = e->acc.p + (uint64_t)ACC_PER_CAND * cand_offset;
+	P.lut = e->d_lut.p;
+	P.W = e->W;
+	if (!count) return APO_OK;
+	if (e->k1_used + 2 > e->k1_ev.size()) {
+		for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
+	}
+	CK(cudaEventRecord(e->k1_ev[e->k1_used], e->stream));
+	CK(apo::run_reward9(P, row, (int)o->variant, (o->flags & APO_SCORE_RECIP) != 0, e->sm_count, e->stream));
+	CK(cudaEventRecord(e->k1_ev[e->k1_used + 1], e->stream));
+	e->k1_used += 2;
+	e->timing.launches++;
 	return APO_OK;
 }
 
@@ -224,7 +254,9 @@ int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *sco
 		else memset(report, 0, sizeof(apo_corpus_report));
 	}
 	float ms = 0;
-	cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->timing.reward_ms = ms;
+	e->timing.reward_ms = 0;
+	for (size_t i = 0; i + 1 < e->k1_used; i += 2) { cudaEventElapsedTime(&ms, e->k1_ev[i], e->k1_ev[i + 1]); e->timing.reward_ms += ms; }
+	e->scoring = false;
 	cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->timing.corpus_ms = ms;
 	cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->timing.allreduce_ms = ms;
 	cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->timing.finalize_ms = ms;
@@ -289,6 +321,7 @@ extern "C" void apo_destroy(apo_engine *e) {
 	e->win[0].release(); e->win[1].release(); e->batch_in.release(); e->batch_out.release(); e->batch_mask.release();
 	if (e->h_result) cudaFreeHost(e->h_result);
 	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+	for (auto &ev : e->k1_ev) cudaEventDestroy(ev);
 	for (int i = 0; i < 2; i++) { if (e->win_free[i]) cudaEventDestroy(e->win_free[i]); if (e->win_ready[i]) cudaEventDestroy(e->win_ready[i]); }
 	if (e->own_stream) cudaStreamDestroy(e->own_stream);
 	if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -456,33 +489,60 @@ extern "C" int apo_rollouts_download(apo_engine *e, apo_record *out, uint32_t c,
 }
 
 // =============================================================================== scoring
-extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
-	if (!e) return APO_E_ARG;
+static int source_shape(apo_engine *e, const apo_score_opts *o, uint32_t *C, uint64_t *T) {
 	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
-	const bool raw = o->source == APO_SRC_ROLLOUTS;
 	if (o->source > APO_SRC_ROLLOUTS) return fail(e, APO_E_ARG, "unknown source %u", o->source);
+	const bool raw = o->source == APO_SRC_ROLLOUTS;
 	if (raw ? (e->roll.p == nullptr || e->roll_C == 0) : (e->dims_ptr == nullptr || e->dims_C == 0))
 		return fail(e, APO_E_STATE, "no %s loaded", raw ? "rollouts" : "dims");
-	const uint32_t C = raw ? e->roll_C : e->dims_C;
-	const uint64_t T = raw ? e->roll_T : e->dims_T;
-	uint64_t first, count;
-	int rc = check_opts(e, o, C, T, &first, &count);
+	*C = raw ? e->roll_C : e->dims_C;
+	*T = raw ? e->roll_T : e->dims_T;
+	return APO_OK;
+}
+
+extern "C" int apo_score_begin(apo_engine *e, uint32_t C_total) {
+	if (!e) return APO_E_ARG;
+	if (C_total == 0) return fail(e, APO_E_ARG, "C_total is 0");
+	CK(cudaSetDevice(e->device));
+	int rc = ensure_scratch(e, C_total, C_total);
 	if (rc) return rc;
+	return begin_score(e, C_total);
+}
+
+extern "C" int apo_score_accumulate(apo_engine *e, const apo_score_opts *o, uint32_t cand_offset) {
+	if (!e) return APO_E_ARG;
+	if (!e->scoring) return fail(e, APO_E_STATE, "apo_score_begin has not been called");
+	uint32_t C = 0; uint64_t T = 0, first = 0, count = 0;
+	int rc = source_shape(e, o, &C, &T);
+	if (rc) return rc;
+	if ((uint64_t)cand_offset + C > e->score_C) return fail(e, APO_E_ARG, "candidates [%u,%u) exceed C_total=%u", cand_offset, cand_offset + C, e->score_C);
+	if (o->first % 4) return fail(e, APO_E_ARG, "window start must be a multiple of 4");
+	if (o->first > T || (o->count && o->first + o->count > T)) return fail(e, APO_E_ARG, "window outside [0,%llu)", (unsigned long long)T);
+	first = o->first; count = o->count ? o->count : T - o->first;
+	CK(cudaSetDevice(e->device));
+	return launch_k1_resident(e, o, cand_offset, first, count);
+}
+
+extern "C" int apo_score_finish(apo_engine *e, const apo_score_opts *o, double *scores, uint64_t *counts, int32_t *topk,
+                                apo_corpus_report *report) {
+	if (!e) return APO_E_ARG;
+	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
+	if (!e->scoring) return fail(e, APO_E_STATE, "apo_score_begin has not been called");
+	if (o->K > e->score_C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, e->score_C);
+	CK(cudaSetDevice(e->device));
+	return finish_score(e, o, e->score_C, scores, counts, topk, report);
+}
+
+extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+	if (!e) return APO_E_ARG;
+	uint32_t C = 0; uint64_t T = 0, first = 0, count = 0;
+	int rc = source_shape(e, o, &C, &T);
+	if (rc) return rc;
+	if ((rc = check_opts(e, o, C, T, &first, &count))) return rc;
 	CK(cudaSetDevice(e->device));
 	if ((rc = ensure_scratch(e, C, o->K))) return rc;
-	e->timing = apo_timing{};
 	if ((rc = begin_score(e, C))) return rc;
-	CK(cudaEventRecord(e->ev[0], e->stream));
-	apo::K1Params P{};
-	const int row = raw ? 32 : 36;
-	const uint64_t pitch = raw ? e->roll_pitch : e->dims_pitch;
-	P.base = (raw ? (const uint8_t *)e->roll.p : (const uint8_t *)e->dims_ptr) + first * row;
-	P.pitch_bytes = pitch * row;
-	P.C = C; P.T = count; P.acc = e->acc.p;
-	const bool recip = (o->flags & APO_SCORE_RECIP) != 0;
-	P.lut = e->d_lut.p;
-	P.W = e->W;
-	if (count) { CK(apo::run_reward9(P, row, (int)o->variant, recip, e->sm_count, e->stream)); e->timing.launches++; }
+	if ((rc = launch_k1_resident(e, o, 0, first, count))) return rc;
 	return finish_score(e, o, C, scores, counts, topk, report);
 }
 
@@ -503,9 +563,7 @@ extern "C" int apo_score_host(apo_engine *e, const apo_score_opts *o, const floa
 	if (Tc < (uint64_t)tile) Tc = tile;
 	if (Tc > round_up(T, tile)) Tc = round_up(T ? T : 1, tile);
 	for (int i = 0; i < 2; i++) CK(e->win[i].reserve((uint64_t)C * Tc * APO_NDIM));
-	e->timing = apo_timing{};
 	if ((rc = begin_score(e, C))) return rc;
-	CK(cudaEventRecord(e->ev[0], e->stream));
 	const bool recip = (o->flags & APO_SCORE_RECIP) != 0;
 	int nchunk = 0;
 	for (uint64_t t0 = 0; t0 < T; t0 += Tc, nchunk++) {
@@ -518,7 +576,13 @@ extern "C" int apo_score_host(apo_engine *e, const apo_score_opts *o, const floa
 		apo::K1Params P{};
 		P.base = (const uint8_t *)e->win[b].p; P.pitch_bytes = Tc * 36; P.C = C; P.T = n; P.acc = e->acc.p;
 		P.lut = e->d_lut.p; P.W = e->W;
+		if (e->k1_used + 2 > e->k1_ev.size()) {
+			for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
+		}
+		CK(cudaEventRecord(e->k1_ev[e->k1_used], e->stream));
 		CK(apo::run_reward9(P, 36, (int)o->variant, recip, e->sm_count, e->stream));
+		CK(cudaEventRecord(e->k1_ev[e->k1_used + 1], e->stream));
+		e->k1_used += 2;
 		e->timing.launches++;
 		CK(cudaEventRecord(e->win_free[b], e->stream));
 	}

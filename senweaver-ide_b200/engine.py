@@ -79,7 +79,8 @@ ABI_SYMBOLS = (
     "apo_abi_version", "apo_create", "apo_destroy", "apo_last_error", "apo_set_stream", "apo_set_weights",
     "apo_get_weights", "apo_reward_batch", "apo_reward_one", "apo_corpus_upload", "apo_corpus_generate",
     "apo_corpus_download", "apo_dims_upload", "apo_dims_generate", "apo_dims_download", "apo_dims_attach",
-    "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_score", "apo_score_host",
+    "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_score", "apo_score_begin",
+    "apo_score_accumulate", "apo_score_finish", "apo_score_host",
     "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy",
 )
 
@@ -129,6 +130,9 @@ def load_library() -> C.CDLL:
     L.apo_rollouts_generate.argtypes = [vp, u64, u32, u32, u64, u64, u32]
     L.apo_rollouts_download.argtypes = [vp, vp, u32, u64, u64]
     L.apo_score.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp]
+    L.apo_score_begin.argtypes = [vp, u32]
+    L.apo_score_accumulate.argtypes = [vp, C.POINTER(ScoreOpts), u32]
+    L.apo_score_finish.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp]
     L.apo_score_host.argtypes = [vp, C.POINTER(ScoreOpts), vp, u32, u64, vp, vp, vp, vp]
     L.apo_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.apo_debug_partials.argtypes = [vp, vp, u32]
@@ -262,6 +266,25 @@ class Engine:
         rep = CorpusReport() if corpus else None
         self._ck(self._L.apo_score(self._h, C.byref(o), _p(scores), _p(counts), _p(topk),
                                    C.byref(rep) if rep is not None else None))
+        return ScoreResult(scores, counts, topk, rep, self.last_timing())
+
+    # chunked form: begin / accumulate (per candidate chunk or record window) / finish
+    def score_begin(self, C_total: int):
+        self._ck(self._L.apo_score_begin(self._h, C_total))
+
+    def score_accumulate(self, cand_offset: int = 0, source: int = SRC_DIMS, recip: bool = False, variant: int = 0,
+                         first: int = 0, count: int = 0):
+        o = self._opts(0, source, False, recip, variant, first, count)
+        self._ck(self._L.apo_score_accumulate(self._h, C.byref(o), cand_offset))
+
+    def score_finish(self, C_total: int, K: int, corpus: bool = False) -> ScoreResult:
+        o = self._opts(K, SRC_DIMS, corpus, False, 0, 0, 0)
+        scores = np.empty(C_total, np.float64)
+        counts = np.empty(C_total, np.uint64)
+        topk = np.empty(K, np.int32)
+        rep = CorpusReport() if corpus else None
+        self._ck(self._L.apo_score_finish(self._h, C.byref(o), _p(scores), _p(counts), _p(topk),
+                                          C.byref(rep) if rep is not None else None))
         return ScoreResult(scores, counts, topk, rep, self.last_timing())
 
     def score_host(self, dims: np.ndarray, K: int, corpus: bool = False, recip: bool = False, variant: int = 0) -> ScoreResult:

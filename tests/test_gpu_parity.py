@@ -267,3 +267,28 @@ def test_error_behaviour(engine, apo):
         engine.score(2, 3)                                # K > C
     res = engine.score(2, 2)                              # the handle stays usable after an error
     assert list(res.topk) == [0, 1]
+
+
+def test_chunked_scoring_matches_single_call(engine, orc):
+    """begin / accumulate per candidate chunk and record window / finish == one apo_score."""
+    C, T, K, seed = 10, 30_000, 4, 0x5EED0005
+    dims = orc.gen_dims(seed, 0, C, 0, T, 300, 8)
+    engine.dims_upload(dims)
+    engine.corpus_upload(orc.gen_records(seed, orc.STREAM_CORPUS, 0, 1, 0, T, 300, 8).reshape(-1))
+    ref = engine.score(C, K, corpus=True)
+    rsums, rcounts = engine.debug_partials(C)
+    engine.score_begin(C)
+    for c0, cn in [(0, 4), (4, 4), (8, 2)]:                     # candidate chunks of <= 4
+        engine.dims_upload(dims[c0:c0 + cn])
+        for first, count in [(0, 10_000), (10_000, 20_000)]:     # two record windows each
+            engine.score_accumulate(c0, first=first, count=count)
+    res = engine.score_finish(C, K, corpus=True)
+    sums, counts = engine.debug_partials(C)
+    assert sums == rsums and counts == rcounts
+    assert np.array_equal(res.scores, ref.scores) and np.array_equal(res.topk, ref.topk)
+    assert res.report.bad == ref.report.bad and res.report.avgReward == ref.report.avgReward
+    assert res.timing.launches == 6 + 1
+    engine.score_begin(C)
+    engine.dims_upload(dims[0:4])
+    with pytest.raises(Exception):
+        engine.score_accumulate(8)                                # [8,12) exceeds C_total = 10

@@ -33,6 +33,19 @@ UNIT = "evals/s"
 SEED = 0x5EED0003
 
 
+def read_traffic(C, T):
+    """DRAM bytes of one K1 launch from the committed ncu capture (profiles/traffic.json); None when the
+    benchmarked configuration is not the profiled one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)["k_reward9"]
+        if (t["C"], t["T"]) == (C, T):
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def read_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -269,7 +282,7 @@ def main():
                        "l2": "inputs (>= 2.3 GB per step) exceed the 126 MB L2; no flush needed", "variant": args.variant,
                        "recip": args.recip, "note": note},
             "roofline": {"bound": "hbm", "kernel": "k_reward9 (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": read_traffic(C, T), "peak_source": peak_src,
                          "alg_bytes_per_launch": alg_bytes, "k1_ms": k1, "k2_ms": float(np.mean(k2_ms)),
                          "join_ms": float(np.mean(ar_ms))},
             "e2e": {"value": Ce * Te * world / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 36 + Te * 32,

@@ -81,58 +81,82 @@ __device__ inline double limbs_to_double(const long long *l) {
 	return neg ? -d : d;
 }
 
+// a / b for integer-valued binary64 operands, 0 <= a, 1 <= b <= 2^32, correctly rounded and
+// branch-free (the generic IEEE division carries a special-case branch that serialises
+// independent evaluations).  y0 = rcp.approx (rel. error <= 2^-23), two Newton steps in FMA
+// arithmetic leave y within 2^-104 of 1/b before the final rounding; 1/b for an integer b with
+// <= 33 significant bits is never closer than 2^-86 (relative) to a rounding boundary unless it
+// is exact, hence y == RN(1/b).  Then q = RN(a*y), r = a - b*q (exact), q' = RN(q + r*y) is the
+// correctly rounded quotient (Markstein; the significand of b is never all ones).
+__device__ __forceinline__ double div_small_int(double a, double b) {
+	double y;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+	double e = __fma_rn(-b, y, 1.0);
+	e = __fma_rn(e, e, e);
+	y = __fma_rn(y, e, y);
+	e = __fma_rn(-b, y, 1.0);
+	y = __fma_rn(y, e, y);
+	const double q = __dmul_rn(a, y);
+	const double r = __fma_rn(-b, q, a);
+	return __fma_rn(r, y, q);
+}
+
 // ---------------------------------------------------------------- TCS:668-763 on device
-// dims[i] is valid only where bit i of the returned mask is set.
+// p ? x : +0.0 as a bit mask, so the compiler keeps x unconditional instead of branching around it
+__device__ __forceinline__ double keep_if(bool p, double x) {
+	return __longlong_as_double(__double_as_longlong(x) & (p ? -1ll : 0ll));
+}
+
+// dims[i] is the pushed value where bit i of the returned mask is set and +0.0 elsewhere.
+// Written select-style (no data-dependent branches) so that independent evaluations of one
+// thread interleave and warps do not diverge; every conditional push of the reference becomes a
+// mask bit.
 __device__ __forceinline__ uint32_t reward_dims(const apo_record &r, double dims[APO_NDIM]) {
-	uint32_t mask = 3u;
 	const bool agent = r.mode == 2;                                   // TCS:673-674
 	const bool err = (r.flags & APO_F_ERRORS) != 0;
 	const bool ended = (r.flags & APO_F_ENDED) != 0;
 	dims[0] = r.feedback == 1 ? 1.0 : (r.feedback == 2 ? -1.0 : 0.0); // TCS:677-678
-	double comp = 0.5;                                                // TCS:682-691
-	if (ended && !err) comp = 0.8;
-	if (err) comp = -0.5;
-	if (r.feedback == 1) comp = 1.0;
+	double comp = (ended && !err) ? 0.8 : 0.5;                        // TCS:682-685
+	comp = err ? -0.5 : comp;                                         // TCS:686-688
+	comp = r.feedback == 1 ? 1.0 : comp;                              // TCS:689-691
 	dims[1] = comp;
-#pragma unroll
-	for (int i = 2; i < APO_NDIM; i++) dims[i] = 0.0;
-	if (r.toolCalls > 0) {                                            // TCS:695
-		const double total = (double)r.toolCalls;
-		const double rate = __ddiv_rn((double)r.toolSucc, total);     // TCS:697
-		dims[2] = __dadd_rn(__dmul_rn(rate, 2.0), -1.0);              // TCS:698
-		const uint32_t sev = agent ? 5u : 3u, mod = agent ? 3u : 2u, mnr = agent ? 2u : 1u;   // TCS:702-704
-		dims[3] = r.toolFail >= sev ? -1.0 : (r.toolFail >= mod ? -0.5 : (r.toolFail >= mnr ? -0.2 : 1.0));
-		const uint32_t exc = agent ? 8u : 3u, good = agent ? 15u : 6u, fair = agent ? 25u : 10u; // TCS:711-713
-		dims[4] = r.toolCalls > fair ? -0.8 : (r.toolCalls > good ? -0.3 : (r.toolCalls > exc ? 0.3 : 1.0));
-		mask |= 0x1cu;
-		const double dur = (double)r.toolDurMs;
-		if (dur > 0.0) {                                              // TCS:721-728
-			const double avg = __ddiv_rn(dur, total);
-			dims[5] = avg > 10000.0 ? -0.5 : (avg > 3000.0 ? 0.0 : (avg > 1000.0 ? 0.5 : 1.0));
-			mask |= 0x20u;
-		}
-	}
-	if (r.llmCalls > 0) {                                             // TCS:733-736
-		const double thr = agent ? 3.0 : 1.0;
-		double over = __dadd_rn((double)r.llmCalls, -thr);
-		if (!(over > 0.0)) over = 0.0;
-		double ef = __dadd_rn(1.0, -__dmul_rn(over, 0.4));
-		if (ef < -1.0) ef = -1.0;
-		dims[6] = ef;
-		mask |= 0x40u;
-	}
-	if (r.tokens > 0) {                                               // TCS:740-748
-		const uint32_t exc = agent ? 5000u : 2000u, good = agent ? 15000u : 5000u, fair = agent ? 30000u : 10000u;
-		dims[7] = r.tokens > fair ? -0.5 : (r.tokens > good ? 0.0 : (r.tokens > exc ? 0.5 : 1.0));
-		mask |= 0x80u;
-	}
+
+	const bool tool = r.toolCalls > 0;                                // TCS:695
+	const double total = (double)(tool ? r.toolCalls : 1u);
+	const double rate = div_small_int((double)r.toolSucc, total);     // TCS:697 (correctly rounded quotient)
+	dims[2] = keep_if(tool, __dadd_rn(__dmul_rn(rate, 2.0), -1.0));   // TCS:698
+	const uint32_t sev = agent ? 5u : 3u, mod = agent ? 3u : 2u, mnr = agent ? 2u : 1u;          // TCS:702-704
+	const double rel = r.toolFail >= sev ? -1.0 : (r.toolFail >= mod ? -0.5 : (r.toolFail >= mnr ? -0.2 : 1.0));
+	dims[3] = keep_if(tool, rel);
+	const uint32_t cexc = agent ? 8u : 3u, cgood = agent ? 15u : 6u, cfair = agent ? 25u : 10u;  // TCS:711-713
+	const double eff = r.toolCalls > cfair ? -0.8 : (r.toolCalls > cgood ? -0.3 : (r.toolCalls > cexc ? 0.3 : 1.0));
+	dims[4] = keep_if(tool, eff);
+	// TCS:721-728.  avg = dur / total; `avg > thr`  <=>  dur > thr * total (exact product): a quotient of
+	// an fp32 value by an integer <= 2^32 cannot lie in (thr, thr + ulp/2].
+	const double dur = (double)r.toolDurMs;
+	const bool hasdur = tool && dur > 0.0;
+	const double ds = dur > __dmul_rn(10000.0, total) ? -0.5 : (dur > __dmul_rn(3000.0, total) ? 0.0 : (dur > __dmul_rn(1000.0, total) ? 0.5 : 1.0));
+	dims[5] = keep_if(hasdur, ds);
+
+	const bool llm = r.llmCalls > 0;                                  // TCS:733-736
+	double over = __dadd_rn((double)r.llmCalls, agent ? -3.0 : -1.0);
+	over = over > 0.0 ? over : 0.0;
+	double ef = __dadd_rn(1.0, -__dmul_rn(over, 0.4));
+	ef = ef < -1.0 ? -1.0 : ef;
+	dims[6] = keep_if(llm, ef);
+
+	const bool tok = r.tokens > 0;                                    // TCS:740-748
+	const uint32_t texc = agent ? 5000u : 2000u, tgood = agent ? 15000u : 5000u, tfair = agent ? 30000u : 10000u;
+	const double tks = r.tokens > tfair ? -0.5 : (r.tokens > tgood ? 0.0 : (r.tokens > texc ? 0.5 : 1.0));
+	dims[7] = keep_if(tok, tks);
+
 	const uint32_t turns = r.userMsgs < r.asstMsgs ? r.userMsgs : r.asstMsgs;   // TCS:752-754
-	if (turns > 0) {                                                  // TCS:755-762
-		const uint32_t thr = agent ? 3u : 2u;
-		dims[8] = turns > thr * 3 ? -0.8 : (turns > thr * 2 ? -0.3 : (turns > thr ? 0.3 : 1.0));
-		mask |= 0x100u;
-	}
-	return mask;
+	const bool conv = turns > 0;                                      // TCS:755-762
+	const uint32_t thr = agent ? 3u : 2u;
+	const double cs = turns > thr * 3 ? -0.8 : (turns > thr * 2 ? -0.3 : (turns > thr ? 0.3 : 1.0));
+	dims[8] = keep_if(conv, cs);
+
+	return 3u | (tool ? 0x1cu : 0u) | (hasdur ? 0x20u : 0u) | (llm ? 0x40u : 0u) | (tok ? 0x80u : 0u) | (conv ? 0x100u : 0u);
 }
 
 // TCS:777-784.  lut[mask] = sum of the present weights added in push order (host-built,

@@ -11,6 +11,7 @@
 // K1/K1r move tiles with 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) through an
 // mbarrier full/empty ring fed by a dedicated producer warp; consumers read the staged
 // tile with conflict-free LDS.128.
+#include <cstdlib>
 #include "apo_device.cuh"
 #include "apo_kernels.h"
 
@@ -92,17 +93,25 @@ __device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const
 	return to_fx(div_lut<RECIP>(ws, t));              // TCS:784
 }
 
-template <bool RECIP>
-__device__ __forceinline__ long long eval_record(const apo_record &r, const Weights &W, const double2 *lut,
-                                                 uint32_t &valid) {
+// One Form-R evaluation, first half (TCS:668-783): record -> weighted sum + LUT entry.
+__device__ __forceinline__ void record_ws(const apo_record &r, const Weights &W, const double2 *lut,
+                                          double &ws_out, double2 &t_out) {
 	double d[APO_NDIM];
 	const uint32_t mask = reward_dims(r, d);
 	double ws = 0.0;
 #pragma unroll
 	for (int i = 0; i < APO_NDIM; i++) ws = __dadd_rn(ws, __dmul_rn(d[i], W.w[i]));
-	const double fr = div_lut<RECIP>(ws, lut[lut_index(mask)]);
+	ws_out = ws;
+	t_out = lut[lut_index(mask)];
+}
+
+template <bool RECIP>
+__device__ __forceinline__ long long eval_record(const apo_record &r, const Weights &W, const double2 *lut,
+                                                 uint32_t &valid) {
+	double ws; double2 t;
+	record_ws(r, W, lut, ws, t);
 	valid = (r.flags & APO_F_VALID) ? 1u : 0u;
-	return valid ? to_fx(fr) : 0ll;
+	return valid ? to_fx(div_lut<RECIP>(ws, t)) : 0ll;
 }
 
 template <int ROW, int CW, int STAGES, bool RECIP>
@@ -232,17 +241,41 @@ k_reward9(const K1Params P) {
 			}
 		} else {
 			// Form R: evaluation e = k*NCONS + tid, 32 B = 2 x LDS.128
+			if (n == Cfg::TILE) {
+				double ws4[Cfg::EPT]; double2 t4[Cfg::EPT]; uint32_t ok4[Cfg::EPT];
 #pragma unroll
-			for (int k = 0; k < Cfg::EPT; k++) {
-				const int e = k * Cfg::NCONS + tid;
-				if (e < n) {
-					const uint4 *src = reinterpret_cast<const uint4 *>(st + (size_t)e * 32);
+				for (int k = 0; k < Cfg::EPT; k++) {
+					const uint4 *src = reinterpret_cast<const uint4 *>(st + (size_t)(k * Cfg::NCONS + tid) * 32);
 					union { uint4 q[2]; apo_record r; } u;
 					u.q[0] = src[0]; u.q[1] = src[1];
-					uint32_t ok;
-					const long long x = eval_record<RECIP>(u.r, W, s_lut, ok);
-					acc.add(x);
-					cnt += ok;
+					record_ws(u.r, W, s_lut, ws4[k], t4[k]);
+					ok4[k] = (u.r.flags & APO_F_VALID) ? 1u : 0u;
+					cnt += ok4[k];
+				}
+				const bool generic = !RECIP && ((__double2hiint(t4[0].y) | __double2hiint(t4[1].y) |
+				                                 __double2hiint(t4[2].y) | __double2hiint(t4[3].y)) < 0);
+				long long x4 = 0;
+				if (!generic) {
+#pragma unroll
+					for (int k = 0; k < Cfg::EPT; k++) { const long long x = to_fx(div_fast<RECIP>(ws4[k], t4[k])); x4 += ok4[k] ? x : 0ll; }
+				} else {
+#pragma unroll
+					for (int k = 0; k < Cfg::EPT; k++) { const long long x = to_fx(div_lut<RECIP>(ws4[k], t4[k])); x4 += ok4[k] ? x : 0ll; }
+				}
+				acc.add(x4);
+			} else {
+#pragma unroll
+				for (int k = 0; k < Cfg::EPT; k++) {
+					const int e = k * Cfg::NCONS + tid;
+					if (e < n) {
+						const uint4 *src = reinterpret_cast<const uint4 *>(st + (size_t)e * 32);
+						union { uint4 q[2]; apo_record r; } u;
+						u.q[0] = src[0]; u.q[1] = src[1];
+						uint32_t ok;
+						const long long x = eval_record<RECIP>(u.r, W, s_lut, ok);
+						acc.add(x);
+						cnt += ok;
+					}
 				}
 			}
 		}
@@ -288,6 +321,7 @@ cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_cou
 	P.total_tiles = (uint64_t)P.tiles_per_cand * P.C;
 	if (P.total_tiles == 0) return cudaSuccess;
 	int grid = sm_count;
+	if (const char *g = getenv("APO_K1_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }   // tuning experiments only
 	if ((uint64_t)grid > P.total_tiles) grid = (int)P.total_tiles;
 	if (row == 36) {
 		switch (variant) {

@@ -292,3 +292,41 @@ def test_chunked_scoring_matches_single_call(engine, orc):
     engine.dims_upload(dims[0:4])
     with pytest.raises(Exception):
         engine.score_accumulate(8)                                # [8,12) exceeds C_total = 10
+
+
+def test_branch_free_divisions_are_correctly_rounded(engine, orc):
+    """d2 = succ/total*2-1 uses a Newton/Markstein quotient and d5 compares dur > thr*total instead
+    of dividing (csrc/apo_device.cuh); both must equal the oracle's IEEE divisions bit for bit."""
+    rng = np.random.default_rng(11)
+    n = 400_000
+    recs = np.zeros(n, orc.RECORD_DTYPE)
+    total = np.concatenate([rng.integers(1, 50, n // 4), rng.integers(1, 1 << 16, n // 4),
+                            rng.integers(1, 1 << 32, n // 4, dtype=np.uint64), (1 << 32) - rng.integers(1, 1000, n // 4)]).astype(np.uint64)
+    succ = (rng.random(n) * (total + 1)).astype(np.uint64).clip(0, total)
+    recs["toolCalls"], recs["toolSucc"] = total.astype(np.uint32), succ.astype(np.uint32)
+    recs["toolFail"] = (total - succ).astype(np.uint32)
+    # durations straddling the three thresholds of TCS:725-727, to the fp32 ulp
+    thr = rng.choice([1000.0, 3000.0, 10000.0], n)
+    base = (thr * total.astype(np.float64)).astype(np.float32)
+    step = rng.integers(-2, 3, n)
+    dur = base.copy()
+    for k in (1, 2):
+        dur = np.where(step >= k, np.nextafter(dur, np.float32(np.inf)), dur)
+        dur = np.where(step <= -k, np.nextafter(dur, np.float32(0)), dur)
+    recs["toolDurMs"] = dur
+    recs["flags"] = 0x0A
+    dims, masks, finals = engine.reward_batch(recs)
+    ref = np.empty((n, 9)); refm = np.empty(n, np.uint32)
+    for i in range(0, n, 1):
+        if i % 40 and i > 2000:          # the oracle loop is Python-slow: full check on 2000, then every 40th
+            continue
+        d, m = orc.reward_dims(recs[i])
+        assert m == masks[i]
+        assert d[2] == dims[i, 2], (i, int(succ[i]), int(total[i]))
+        assert (np.isnan(d[5]) and np.isnan(dims[i, 5])) or d[5] == dims[i, 5], (i, float(dur[i]), int(total[i]))
+    # and the whole batch through the exact-sum path (C loop, every record)
+    engine.rollouts_upload(recs.reshape(1, n))
+    engine.score(1, 1, source=1)
+    sums, counts = engine.debug_partials(1)
+    esums, ecounts = orc.score_records_fx(recs.reshape(1, n))
+    assert sums == esums and counts == ecounts

@@ -308,6 +308,75 @@ class APOService:
     def requestTextualGradient(self):
         return None                                                           # LLM critique lives on the backend (APO:1268-1343)
 
+    # ---- wire formats after the path ---------------------------------------------------
+    def _convertTracesToRolloutResults(self, traces):
+        """APO:866-914: trace -> RolloutResultForAPO (field for field)."""
+        out = []
+        for t in traces:
+            msgs = []
+            for sp in t["spans"]:
+                d = sp["data"]
+                if sp["type"] == "user_message":
+                    msgs.append({"role": "user", "content": d.get("contentPreview") or ""})
+                elif sp["type"] == "assistant_message":
+                    msgs.append({"role": "assistant", "content": d.get("contentPreview") or ""})
+                elif sp["type"] == "tool_call":
+                    msgs.append({"role": "tool", "content": d.get("toolResult") or "", "toolName": d.get("toolName"),
+                                 "toolSuccess": d.get("toolSuccess")})
+            sm = t["summary"]
+            fb = sm["userFeedback"]
+            status = "succeeded" if fb == "good" else ("failed" if fb == "bad" or sm["hasErrors"] else "unknown")
+            total = sm["toolCallsSucceeded"] + sm["toolCallsFailed"]
+            md = t.get("metadata") or {}
+            out.append({"traceId": t["id"], "threadId": t["threadId"], "status": status, "finalReward": sm["finalReward"],
+                        "rewardDimensions": sm.get("rewardDimensions") or [], "messages": msgs,
+                        "chatMode": md.get("chatMode") or "unknown",
+                        "toolCallStats": {"totalCalls": total, "succeeded": sm["toolCallsSucceeded"], "failed": sm["toolCallsFailed"],
+                                          "successRate": sm["toolCallsSucceeded"] / total if total > 0 else None,
+                                          "byToolName": sm["toolCallsByName"], "totalDurationMs": sm["totalToolDurationMs"]},
+                        "llmStats": {"totalCalls": sm["totalLLMCalls"], "totalTokens": sm["totalTokens"]}})
+        return out
+
+    def buildOptimizePayload(self):
+        """The v2.0.0 /api/apo/optimize payload of APO:1011-1100; its rewardSummary / toolCallSummary
+        reductions (APO:1051-1099) run on the engine over the same recent-feedback selection
+        (feedback != null, startTime desc, first gradientBatchSize*4; APO:1003-1007)."""
+        report = self.getLatestReport() or self.analyzePromptEffectiveness()
+        recent = sorted([t for t in self._tc.getAllTraces() if t["summary"]["userFeedback"] is not None],
+                        key=lambda t: -t["startTime"])[: self._config["gradientBatchSize"] * 4]
+        rollouts = self._convertTracesToRolloutResults(recent)
+        reward_summary = {"totalWithReward": 0, "avgFinalReward": None, "rewardDimensionAvg": {}}
+        tool_summary = {"totalCalls": 0, "totalSucceeded": 0, "totalFailed": 0, "successRate": None, "totalDurationMs": 0, "byToolName": {}}
+        if recent:
+            self._engine.dims_upload(np.full((1, 4, 9), np.nan, np.float32))
+            self._engine.corpus_upload(self._tc.corpus_records(recent, scored=True))
+            rep = self._engine.score(1, 0, corpus=True).report
+            reward_summary = {"totalWithReward": int(rep.withReward),
+                              "avgFinalReward": None if rep.withReward == 0 else float(rep.avgReward),
+                              "rewardDimensionAvg": {DIM_NAMES[i]: float(rep.dim[i].avg) for i in range(9) if rep.dim[i].count}}
+            by = {}
+            for r in rollouts:
+                for name, st in r["toolCallStats"]["byToolName"].items():
+                    e = by.setdefault(name, {"total": 0, "succeeded": 0, "failed": 0})
+                    for k in e:
+                        e[k] += st[k]
+            succ, fail = int(rep.toolSucc), int(rep.toolFail)
+            tool_summary = {"totalCalls": succ + fail, "totalSucceeded": succ, "totalFailed": fail,
+                            "successRate": succ / (succ + fail) if succ + fail > 0 else None,
+                            "totalDurationMs": sum(r["toolCallStats"]["totalDurationMs"] for r in rollouts), "byToolName": by}
+        st = self._beamState
+        return {"version": "2.0.0",
+                "report": {k: report[k] for k in ("id", "generatedAt", "totalConversations", "goodRate", "goodFeedbackCount",
+                                                  "badFeedbackCount", "byMode", "patterns")},
+                "rolloutResults": rollouts[:20],
+                "currentSegments": [{"id": s["id"], "category": s["category"], "content": s["content"][:1000],
+                                     "isOptimized": s["isOptimized"], "version": s["version"]} for s in self.getActiveSegments()],
+                "beamConfig": {k: self._config[k] for k in ("beamWidth", "branchFactor", "beamRounds")},
+                "beamState": None if st is None else {"currentRound": st["currentRound"], "historyBestScore": st["historyBestScore"],
+                                                      "beamSize": len(st["beam"])},
+                "badExamples": [e for p in report["patterns"] for e in p["examples"]][:10],
+                "rewardSummary": reward_summary, "toolCallSummary": tool_summary}
+
     # ---- segments / suggestions (APO:1360-1458)
     def getActiveSegments(self):
         return [s for s in self._segments if s["isActive"]]
@@ -346,6 +415,22 @@ class APOService:
             self._segments = [g for g in self._segments if g.get("fromSuggestion") != s["id"]]
             s["status"] = "reverted"
             self._fire(self._stateListeners)
+
+    # ---- rule injection: the consumer of getOptimizedRules in the system-prompt builder
+    def packOptimizedRules(self, maxChars: int = 2000):
+        """Greedy pack under the 2000-character budget of
+        browser/convertToLLMMessageService.ts:832-854 -> the '# APO Optimized Rules' block ('' if none)."""
+        rules = self.getOptimizedRules()
+        content, included = "", 0
+        for r in rules:
+            cand = content + ("\n" if content else "") + r
+            if len(cand) > maxChars:
+                break
+            content, included = cand, included + 1
+        if not content:
+            return ""
+        note = f" ({included}/{len(rules)} rules, budget limited)" if included < len(rules) else ""
+        return f"\n\n# APO Optimized Rules{note}\n" + content
 
     # ---- queries
     def getLatestReport(self):

@@ -142,3 +142,23 @@ def test_engine_failure_never_raises_into_callers(services, monkeypatch):
     tc.recordUserFeedback("x", 0, "good")                     # swallowed (TCS:554)
     assert tc.getAllTraces()[0]["summary"]["finalReward"] is None
     assert apo.evaluateBeam([{"version": "v0", "content": "c"}], dims=None, rollouts=None) is None
+
+
+def test_payload_and_rule_budget(services):
+    _, tc, apo = services
+    drive(tc, random.Random(3), n_threads=40)
+    pay = apo.buildOptimizePayload()
+    recent = sorted([t for t in tc.getAllTraces() if t["summary"]["userFeedback"] is not None], key=lambda t: -t["startTime"])[:16]
+    assert [r["traceId"] for r in pay["rolloutResults"]] == [t["id"] for t in recent]
+    vals = [t["summary"]["finalReward"] for t in recent if t["summary"]["finalReward"] is not None]
+    assert pay["rewardSummary"]["totalWithReward"] == len(vals)
+    if vals:
+        assert abs(pay["rewardSummary"]["avgFinalReward"] - sum(vals) / len(vals)) < 1e-12
+    for r, t in zip(pay["rolloutResults"], recent):
+        fb = t["summary"]["userFeedback"]
+        assert r["status"] == ("succeeded" if fb == "good" else "failed")
+    # rule budget (C2L:832-854)
+    apo._segments = [{"id": str(i), "category": "core_behavior", "content": "x" * 300, "isActive": True, "isOptimized": True,
+                      "version": 1, "createdAt": 0, "updatedAt": 0} for i in range(10)]
+    block = apo.packOptimizedRules()
+    assert "(6/10 rules, budget limited)" in block and len(block.split("\n", 3)[3]) <= 2000

@@ -120,14 +120,14 @@ void build_luts(apo_engine *e) {
 	for (uint32_t m = 0; m < 512; m++) {
 		double tw = 0.0;                            // TCS:777-783: totalWeight += w in push order
 		for (int i = 0; i < APO_NDIM; i++) if (m & (1u << i)) tw += e->W.w[i];
-		if (!(tw > 0.0)) tw = 1.0;                  // finalReward stays null; kernels never count it
+		if (!(tw > 0.0)) tw = -1.0;                 // totalWeight == 0: finalReward stays null (TCS:784); a negative entry tells the kernels not to count it
 		e->lut_tw[m] = tw;
 		// K1 divides by multiplying with RN(1/tw) + one FMA correction (Markstein); that is only
 		// proven correctly rounded when the significand of tw is not all ones — flag those masks
 		// with a negative reciprocal so the kernel takes the generic IEEE division for them.
 		uint64_t bits; memcpy(&bits, &tw, 8);
 		const bool all_ones = (bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull;
-		e->lut_rc[m] = all_ones ? -(1.0 / tw) : 1.0 / tw;
+		e->lut_rc[m] = tw < 0.0 ? 1.0 : (all_ones ? -(1.0 / tw) : 1.0 / tw);
 	}
 }
 

@@ -160,7 +160,7 @@ __device__ __forceinline__ uint32_t reward_dims(const apo_record &r, double dims
 }
 
 // TCS:777-784.  lut[mask] = sum of the present weights added in push order (host-built,
-// same sequential binary64 adds); lut[0] = 1 so an empty mask yields 0 without a NaN.
+// same sequential binary64 adds); entries whose total weight is 0 hold -1 (finalReward null).
 // dims of absent dimensions must be +0.0 (adding +0.0*w leaves the running sum unchanged).
 template <bool RECIP>
 __device__ __forceinline__ double final_reward(const double dims[APO_NDIM], uint32_t mask, const Weights &W,

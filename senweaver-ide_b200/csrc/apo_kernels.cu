@@ -81,8 +81,8 @@ __device__ __forceinline__ void eval_ws(const float (&v)[APO_NDIM], const Weight
 		mask |= (p ? 1u : 0u) << lut_bit(i);
 	}
 	ws_out = ws;
-	t_out = lut[mask];                                // lut[0] == {1,1}: ws == 0 -> 0
-	valid = mask != 0 ? 1u : 0u;
+	t_out = lut[mask];                                // total weight 0 -> {-1, -1}: ws == 0 -> quotient 0, not counted
+	valid = t_out.x > 0.0 ? 1u : 0u;                  // TCS:784: totalWeight > 0 ? ... : null
 }
 
 template <bool RECIP>
@@ -110,7 +110,7 @@ __device__ __forceinline__ long long eval_record(const apo_record &r, const Weig
                                                  uint32_t &valid) {
 	double ws; double2 t;
 	record_ws(r, W, lut, ws, t);
-	valid = (r.flags & APO_F_VALID) ? 1u : 0u;
+	valid = ((r.flags & APO_F_VALID) && t.x > 0.0) ? 1u : 0u;
 	return valid ? to_fx(div_lut<RECIP>(ws, t)) : 0ll;
 }
 
@@ -249,7 +249,7 @@ k_reward9(const K1Params P) {
 					union { uint4 q[2]; apo_record r; } u;
 					u.q[0] = src[0]; u.q[1] = src[1];
 					record_ws(u.r, W, s_lut, ws4[k], t4[k]);
-					ok4[k] = (u.r.flags & APO_F_VALID) ? 1u : 0u;
+					ok4[k] = ((u.r.flags & APO_F_VALID) && t4[k].x > 0.0) ? 1u : 0u;
 					cnt += ok4[k];
 				}
 				const bool generic = !RECIP && ((__double2hiint(t4[0].y) | __double2hiint(t4[1].y) |
@@ -410,12 +410,14 @@ k_detect6(const K2Params P) {
 				double ws = 0.0;
 #pragma unroll
 				for (int i = 0; i < APO_NDIM; i++) ws = __dadd_rn(ws, __dmul_rn(d[i], W.w[i]));
-				const double fr = div_lut<false>(ws, make_double2(__ldg(P.lut + mask), __ldg(P.lut + 512 + mask)));
-				fx[0] += to_fx(fr);
-				cn[CN_RW]++;
+				const double2 tw = make_double2(__ldg(P.lut + mask), __ldg(P.lut + 512 + mask));
+				const bool has = tw.x > 0.0;                                             // TCS:784 totalWeight > 0
+				const double fr = div_lut<false>(ws, tw);
+				fx[0] += has ? to_fx(fr) : 0ll;
+				cn[CN_RW] += has;
 #pragma unroll
 				for (int i = 0; i < APO_NDIM; i++) {                                     // APO:556-565
-					const bool p = (mask >> i) & 1u;
+					const bool p = has && ((mask >> i) & 1u);
 					fx[1 + i] += p ? to_fx(d[i]) : 0ll;
 					cn[CN_DIM + i] += p;
 				}
@@ -732,12 +734,13 @@ k_reward_batch(const apo_record *recs, uint64_t n, const Weights W, const double
 	const apo_record r = recs[i];
 	double d[APO_NDIM];
 	const uint32_t mask = reward_dims(r, d);
+	const double tw = lut[mask];
 	const double fr = final_reward<false>(d, mask, W, lut);
 	const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 #pragma unroll
 	for (int k = 0; k < APO_NDIM; k++) dims[i * APO_NDIM + k] = ((mask >> k) & 1u) ? d[k] : qnan;
 	masks[i] = mask;
-	finals[i] = (r.flags & APO_F_VALID) ? fr : qnan;
+	finals[i] = ((r.flags & APO_F_VALID) && tw > 0.0) ? fr : qnan;
 }
 
 cudaError_t run_reward_batch(const apo_record *recs, uint64_t n, const Weights &W, const double *lut, double *dims,

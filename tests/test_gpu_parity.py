@@ -330,3 +330,103 @@ def test_branch_free_divisions_are_correctly_rounded(engine, orc):
     sums, counts = engine.debug_partials(1)
     esums, ecounts = orc.score_records_fx(recs.reshape(1, n))
     assert sums == esums and counts == ecounts
+
+
+# ------------------------------------------------------------------ edge cases of the boundary
+def test_degenerate_shapes(engine, orc):
+    # one candidate, one record, K = 0 / K = C
+    dims = orc.gen_dims(2, 0, 1, 0, 1, 300, 1)
+    engine.dims_upload(dims)
+    r = engine.score(1, 0)
+    assert r.topk.shape == (0,) and r.counts[0] in (0, 1)
+    r = engine.score(1, 1)
+    assert list(r.topk) == [0]
+    # empty window
+    engine.dims_upload(orc.gen_dims(2, 0, 3, 0, 64, 300, 1))
+    r = engine.score(3, 3, first=64, count=0)            # count 0 at the end = empty remainder
+    assert list(r.counts) == [0, 0, 0] and all(np.isneginf(r.scores)) and list(r.topk) == [0, 1, 2]
+    # empty corpus: report stays zeroed, scoring unaffected
+    engine.corpus_upload(np.empty(0, orc.RECORD_DTYPE))
+    r = engine.score(3, 1, corpus=True)
+    assert r.report.total == 0 and r.report.pat[0].count == 0
+
+
+def test_special_values(engine, orc):
+    """Signed zeros, subnormals, large magnitudes inside the documented domain, infinities outside it."""
+    C, T = 2, 256
+    dims = np.zeros((C, T, 9), np.float32)
+    dims[0, :, 0] = -0.0
+    dims[0, :, 1] = np.float32(1e-45)                     # subnormal fp32
+    dims[0, :, 2] = np.nan
+    dims[1, :, :] = np.linspace(-500, 500, T * 9, dtype=np.float32).reshape(T, 9)
+    engine.dims_upload(dims)
+    r = engine.score(C, C)
+    ref_s, ref_n = orc.score_dims(dims)
+    assert_scores(r, ref_s, ref_n)
+    sums, counts = engine.debug_partials(C)
+    assert (sums, counts) == orc.score_dims_fx(dims)
+
+
+def test_zero_weight_dimensions(engine, orc):
+    w = np.array([0.5, 0.0, 0.25, 0.0, 0.0, 0.25, 0.0, 0.0, 0.0])
+    rng = np.random.default_rng(3)
+    dims = rng.uniform(-1, 1, (3, 2000, 9)).astype(np.float32)
+    dims[rng.random(dims.shape) < 0.4] = np.nan
+    try:
+        engine.set_weights(w)
+        engine.dims_upload(dims)
+        r = engine.score(3, 3)
+        # rows whose present dims all carry weight 0 have totalWeight == 0 -> finalReward null (TCS:784)
+        ref_s, ref_n = orc.score_dims(dims, w=w)
+        assert np.array_equal(r.counts, ref_n)
+        assert_scores(r, ref_s, ref_n)
+        assert np.array_equal(r.topk, orc.topk(ref_s, 3))
+    finally:
+        engine.set_weights(orc.weights())
+
+
+def test_attach_caller_owned_device_buffer(engine, orc):
+    import torch
+    C, T, pitch = 3, 1000, 1024
+    dims = orc.gen_dims(8, 0, C, 0, T, 300, 2)
+    buf = torch.full((C, pitch, 9), float("nan"), dtype=torch.float32, device="cuda")
+    buf[:, :T] = torch.from_numpy(dims).cuda()
+    torch.cuda.synchronize()
+    engine.dims_attach(buf.data_ptr(), C, T, pitch)
+    r = engine.score(C, 2)
+    sums, counts = engine.debug_partials(C)
+    assert (sums, counts) == orc.score_dims_fx(dims)
+    stream = torch.cuda.Stream()
+    engine.set_stream(stream.cuda_stream)                  # caller-provided stream
+    try:
+        r2 = engine.score(C, 2)
+    finally:
+        engine.set_stream(0)
+    assert np.array_equal(r.scores, r2.scores) and np.array_equal(r.topk, r2.topk)
+    engine.dims_upload(dims)                               # back to engine-owned storage
+
+
+def test_random_shapes_property(engine, orc):
+    """Randomised shapes / windows / variants / K: exact sums, scores, top-K vs the oracle."""
+    rng = np.random.default_rng(2026)
+    for trial in range(40):
+        C = int(rng.integers(1, 40))
+        T = int(rng.choice([1, 2, 3, 5, 127, 128, 129, 2559, 2560, 2561, 5000, 12345]))
+        K = int(rng.integers(0, C + 1))
+        variant = int(rng.integers(0, 5))
+        if rng.random() < 0.5:
+            dims = orc.gen_dims(int(rng.integers(1, 1 << 30)), int(rng.integers(0, 100)), C, int(rng.integers(0, 1 << 20)), T, int(rng.integers(0, 1025)), 4)
+        else:
+            dims = rng.uniform(-1, 1, (C, T, 9)).astype(np.float32)
+            dims[rng.random(dims.shape) < rng.random()] = np.nan
+        engine.dims_upload(dims)
+        first = int(rng.integers(0, T // 4 + 1)) * 4 if T >= 4 and rng.random() < 0.5 else 0
+        count = int(rng.integers(0, T - first + 1)) if rng.random() < 0.5 else 0
+        r = engine.score(C, K, variant=variant, first=first, count=count)
+        sub = dims[:, first:first + count] if count else dims[:, first:]
+        ref_s, ref_n = orc.score_dims(sub) if sub.shape[1] else (np.full(C, -np.inf), np.zeros(C, np.uint64))
+        assert_scores(r, ref_s, ref_n)
+        assert np.array_equal(r.topk, orc.topk(ref_s, K)), (trial, C, T, K)
+        if sub.shape[1]:
+            sums, counts = engine.debug_partials(C)
+            assert (sums, counts) == orc.score_dims_fx(sub)

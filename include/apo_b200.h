@@ -53,6 +53,22 @@ typedef struct apo_record {
 #define APO_F_VALID    0x08u  /* summary.finalReward !== null (TCS:606, APO:550)     */
 #define APO_F_FAILSPAN 0x10u  /* a tool_call span with toolSuccess===false exists    */
 
+/* Form R16 — the same record packed into 16 bytes for transport over PCIe / storage.
+ * Saturating fields keep every output of the path unchanged: userMsgs/asstMsgs only meet
+ * thresholds <= 9 (TCS:756-761, APO:734), llmCalls saturates the reward at n >= 8 (TCS:735),
+ * tokens only meets thresholds <= 30000 (TCS:741-747, APO:693).  toolSucc is implied by
+ * toolCalls - toolFail (they are incremented together, TCS:505-510).  Records that do not
+ * satisfy that, or whose toolCalls/toolFail exceed 65535, are rejected by apo_record_pack16
+ * and must travel as Form R. */
+typedef struct apo_record16 {
+	uint16_t hdr;        /* bits 0-1 feedback, 2 hasErrors, 3 ended, 4 valid, 5 failspan, 6-8 mode */
+	uint8_t  userMsgs, asstMsgs;
+	uint16_t toolCalls, toolFail;
+	uint8_t  llmCalls, pad;
+	uint16_t tokens;
+	float    toolDurMs;
+} apo_record16;
+
 typedef struct apo_pattern {      /* one of the six patterns of APO:635-773 */
 	uint64_t count;               /* frequency                              */
 	uint8_t  flag;                /* emitted (count >= minimum)             */
@@ -135,6 +151,15 @@ int apo_rollouts_upload(apo_engine *e, const apo_record *recs, uint32_t C, uint6
 int apo_rollouts_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,
                           uint32_t agent_permille);
 int apo_rollouts_download(apo_engine *e, apo_record *out, uint32_t c, uint64_t first, uint64_t n);
+/* Packed rollouts (Form R16, 16 B per evaluation): same scoring source APO_SRC_ROLLOUTS. */
+int apo_rollouts16_upload(apo_engine *e, const apo_record16 *recs, uint32_t C, uint64_t T);
+int apo_rollouts16_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,
+                            uint32_t agent_permille);
+int apo_rollouts16_download(apo_engine *e, apo_record16 *out, uint32_t c, uint64_t first, uint64_t n);
+/* Host-side format helpers (no device work).  pack returns APO_E_ARG and the index of the first
+ * unrepresentable record in *bad (may be NULL). */
+int apo_record_pack16(const apo_record *in, uint64_t n, apo_record16 *out, uint64_t *bad);
+int apo_record_unpack16(const apo_record16 *in, uint64_t n, apo_record *out);
 
 /* ---- scoring: score[c] = mean_t finalReward[c,t] (APO:550-553 per candidate), top-K
  * (score desc, ties -> lower index; replaces the server-side beam selection consumed at
@@ -170,6 +195,11 @@ int apo_score_finish(apo_engine *e, const apo_score_opts *o, double *scores, uin
  * dims[C][T][9] through a double-buffered device window (H2D overlapped with K1). */
 int apo_score_host(apo_engine *e, const apo_score_opts *o, const float *dims, uint32_t C, uint64_t T,
                    double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report);
+/* Same for per-(candidate, record) rollouts in host memory: row_bytes = 32 (apo_record) or
+ * 16 (apo_record16); recs is [C][T] rows.  Dims are derived on the device (TCS:668-763). */
+int apo_score_host_records(apo_engine *e, const apo_score_opts *o, const void *recs, uint32_t row_bytes,
+                           uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
+                           apo_corpus_report *report);
 int apo_last_timing(const apo_engine *e, apo_timing *out);
 /* Exact partial sums of the last apo_score: per candidate the integer
  * sum_t rint(finalReward * 2^52) as three int64 limbs (value = l2*2^64 + l1*2^32 + l0)

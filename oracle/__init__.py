@@ -25,6 +25,11 @@ RECORD_DTYPE = np.dtype([
     ("llmCalls", "<u4"), ("tokens", "<u4"), ("toolDurMs", "<f4"),
 ])
 assert RECORD_DTYPE.itemsize == 32
+RECORD16_DTYPE = np.dtype([
+    ("hdr", "<u2"), ("userMsgs", "u1"), ("asstMsgs", "u1"), ("toolCalls", "<u2"), ("toolFail", "<u2"),
+    ("llmCalls", "u1"), ("pad", "u1"), ("tokens", "<u2"), ("toolDurMs", "<f4"),
+])
+assert RECORD16_DTYPE.itemsize == 16
 
 
 class Pattern(C.Structure):
@@ -73,6 +78,8 @@ def lib() -> C.CDLL:
         L.orc_score_records_mt.argtypes = [vp, u32, u64, u64, dp, dp, vp, i32]
         L.orc_score_dims_fx.argtypes = [vp, u32, u64, u64, dp, vp, vp, vp]
         L.orc_score_records_fx.argtypes = [vp, u32, u64, u64, dp, vp, vp, vp]
+        L.orc_unpack16.argtypes = [vp, u64, vp]
+        L.orc_unpack16.restype = None
         L.orc_topk.argtypes = [dp, u32, u32, vp]
         L.orc_report_build.argtypes = [vp, u64, u64, dp, C.POINTER(Report)]
         L.orc_gen_record.argtypes = [u64, u32, u32, u64, u32, vp]
@@ -168,6 +175,13 @@ def score_records_fx(recs: np.ndarray, T: int | None = None, w=None):
     lo = np.empty(Cn, np.uint64); hi = np.empty(Cn, np.int64); n = np.empty(Cn, np.uint64)
     lib().orc_score_records_fx(_p(recs), Cn, T, pitch, _p(w), _p(lo), _p(hi), _p(n))
     return [(int(h) << 64) + int(l) for l, h in zip(lo, hi)], [int(x) for x in n]
+
+
+def unpack16(recs16: np.ndarray) -> np.ndarray:
+    recs16 = np.ascontiguousarray(recs16, RECORD16_DTYPE)
+    out = np.empty(recs16.shape, RECORD_DTYPE)
+    lib().orc_unpack16(_p(recs16), recs16.size, _p(out))
+    return out
 
 
 def topk(scores: np.ndarray, K: int) -> np.ndarray:

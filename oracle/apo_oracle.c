@@ -396,6 +396,23 @@ void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
 	}
 }
 
+/* ---------------------------------------------------------------- Form R16 -> Form R */
+void orc_unpack16(const orc_record16 *in, uint64_t n, orc_record *out)
+{
+	for (uint64_t i = 0; i < n; i++) {
+		const orc_record16 *p = &in[i];
+		orc_record *r = &out[i];
+		memset(r, 0, sizeof *r);
+		r->feedback = (uint8_t)(p->hdr & 3);
+		r->flags = (uint8_t)(((p->hdr >> 2) & 1 ? ORC_F_ERRORS : 0) | ((p->hdr >> 3) & 1 ? ORC_F_ENDED : 0) |
+		                     ((p->hdr >> 4) & 1 ? ORC_F_VALID : 0) | ((p->hdr >> 5) & 1 ? ORC_F_FAILSPAN : 0));
+		r->mode = (uint8_t)((p->hdr >> 6) & 7);
+		r->userMsgs = p->userMsgs; r->asstMsgs = p->asstMsgs;
+		r->toolCalls = p->toolCalls; r->toolFail = p->toolFail; r->toolSucc = (uint32_t)p->toolCalls - p->toolFail;
+		r->llmCalls = p->llmCalls; r->tokens = p->tokens; r->toolDurMs = p->toolDurMs;
+	}
+}
+
 /* ================================================================ synthetic generator
  * Build-defined (not from the reference).  Integer-only field derivation so the CUDA
  * generator and this one agree bit for bit.  Spec: DESIGN.md "Generator". */

@@ -130,6 +130,12 @@ typedef struct {
 void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
                       const double w[ORC_NDIM], orc_report *out);
 
+/* Form R16 (include/apo_b200.h apo_record16): independent restatement of the 16-byte unpacking. */
+typedef struct {
+	uint16_t hdr; uint8_t userMsgs, asstMsgs; uint16_t toolCalls, toolFail; uint8_t llmCalls, pad; uint16_t tokens; float toolDurMs;
+} orc_record16;
+void orc_unpack16(const orc_record16 *in, uint64_t n, orc_record *out);
+
 /* ---- synthetic generator (build-defined; spec in DESIGN.md "Generator") ---- */
 #define ORC_STREAM_CORPUS  1u
 #define ORC_STREAM_ROLLOUT 2u

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/apo_b200.h"
+#include "apo_format.h"
 #include "apo_kernels.h"
 
 namespace {
@@ -84,14 +85,14 @@ struct apo_engine {
 
 	DevBuf<apo_record> corpus; uint64_t corpus_T = 0, corpus_base = 0;
 	DevBuf<float> dims; const float *dims_ptr = nullptr; uint32_t dims_C = 0; uint64_t dims_T = 0, dims_pitch = 0;
-	DevBuf<apo_record> roll; uint32_t roll_C = 0; uint64_t roll_T = 0, roll_pitch = 0;
+	DevBuf<uint8_t> roll; uint32_t roll_C = 0, roll_row = 32; uint64_t roll_T = 0, roll_pitch = 0;   // Form R (32 B) or R16 (16 B) rows
 
 	DevBuf<long long> acc; uint32_t last_C = 0;
 	DevBuf<unsigned long long> misc;     // [0,18) example scratch, [18] ticket
 	DevBuf<uint8_t> result;              // scores | counts | topk | report
 	DevBuf<unsigned long long> keys, sel_key; DevBuf<int32_t> sel_idx;
 	uint8_t *h_result = nullptr; uint64_t h_result_cap = 0;
-	DevBuf<float> win[2]; cudaEvent_t win_free[2] = {nullptr, nullptr}, win_ready[2] = {nullptr, nullptr};
+	DevBuf<uint8_t> win[2]; cudaEvent_t win_free[2] = {nullptr, nullptr}, win_ready[2] = {nullptr, nullptr};
 	DevBuf<apo_record> batch_in; DevBuf<double> batch_out; DevBuf<uint32_t> batch_mask;
 
 	void *comm = nullptr; int nranks = 1, rank = 0;
@@ -195,7 +196,7 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 	const bool raw = o->source == APO_SRC_ROLLOUTS;
 	const uint32_t C = raw ? e->roll_C : e->dims_C;
 	apo::K1Params P{};
-	const int row = raw ? 32 : 36;
+	const int row = raw ? (int)e->roll_row : 36;
 	const uint64_t pitch = raw ? e->roll_pitch : e->dims_pitch;
 	P.base = (raw ? (const uint8_t *)e->roll.p : (const uint8_t *)e->dims_ptr) + first * row;
 	P.pitch_bytes = pitch * row;
@@ -452,39 +453,66 @@ extern "C" int apo_dims_attach(apo_engine *e, uint64_t device_ptr, uint32_t C, u
 	return APO_OK;
 }
 
-extern "C" int apo_rollouts_upload(apo_engine *e, const apo_record *recs, uint32_t C, uint64_t T) {
+namespace {
+int rollouts_upload_rows(apo_engine *e, const void *recs, uint32_t row, uint32_t C, uint64_t T) {
 	if (!e) return APO_E_ARG;
 	if (C && T && !recs) return fail(e, APO_E_ARG, "recs is NULL");
 	CK(cudaSetDevice(e->device));
 	const uint64_t pitch = round_up(T ? T : 1, 4);
-	CK(e->roll.reserve((uint64_t)(C ? C : 1) * pitch));
+	CK(e->roll.reserve((uint64_t)(C ? C : 1) * pitch * row));
 	if (C && T) {
-		if (pitch != T) CK(cudaMemsetAsync(e->roll.p, 0, (uint64_t)C * pitch * sizeof(apo_record), e->stream));   // VALID clear
-		CK(cudaMemcpy2DAsync(e->roll.p, pitch * sizeof(apo_record), recs, T * sizeof(apo_record), T * sizeof(apo_record), C, cudaMemcpyHostToDevice, e->stream));
+		if (pitch != T) CK(cudaMemsetAsync(e->roll.p, 0, (uint64_t)C * pitch * row, e->stream));   // VALID clear
+		CK(cudaMemcpy2DAsync(e->roll.p, pitch * row, recs, T * row, T * row, C, cudaMemcpyHostToDevice, e->stream));
 	}
 	CK(cudaStreamSynchronize(e->stream));
-	e->roll_C = C; e->roll_T = T; e->roll_pitch = pitch;
+	e->roll_C = C; e->roll_T = T; e->roll_pitch = pitch; e->roll_row = row;
 	return APO_OK;
 }
-
-extern "C" int apo_rollouts_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T, uint32_t agent_permille) {
+int rollouts_generate_rows(apo_engine *e, uint32_t row, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T, uint32_t agent_permille) {
 	if (!e) return APO_E_ARG;
 	CK(cudaSetDevice(e->device));
 	const uint64_t pitch = round_up(T ? T : 1, 4);
-	CK(e->roll.reserve((uint64_t)(C ? C : 1) * pitch));
-	if (pitch != T && C) CK(cudaMemsetAsync(e->roll.p, 0, (uint64_t)C * pitch * sizeof(apo_record), e->stream));
-	CK(apo::run_gen_records(e->roll.p, pitch, seed, 2u, c0, C, t0, T, agent_permille, e->stream));
+	CK(e->roll.reserve((uint64_t)(C ? C : 1) * pitch * row));
+	if (pitch != T && C) CK(cudaMemsetAsync(e->roll.p, 0, (uint64_t)C * pitch * row, e->stream));
+	if (row == 32) CK(apo::run_gen_records((apo_record *)e->roll.p, pitch, seed, 2u, c0, C, t0, T, agent_permille, e->stream));
+	else CK(apo::run_gen_records16((apo_record16 *)e->roll.p, pitch, seed, 2u, c0, C, t0, T, agent_permille, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
-	e->roll_C = C; e->roll_T = T; e->roll_pitch = pitch;
+	e->roll_C = C; e->roll_T = T; e->roll_pitch = pitch; e->roll_row = row;
 	return APO_OK;
 }
-
-extern "C" int apo_rollouts_download(apo_engine *e, apo_record *out, uint32_t c, uint64_t first, uint64_t n) {
+int rollouts_download_rows(apo_engine *e, void *out, uint32_t row, uint32_t c, uint64_t first, uint64_t n) {
 	if (!e || !out) return fail(e, APO_E_ARG, "NULL argument");
-	if (!e->roll.p || c >= e->roll_C || first + n > e->roll_T) return fail(e, APO_E_ARG, "range outside the rollouts");
+	if (!e->roll.p || e->roll_row != row) return fail(e, APO_E_STATE, "no rollouts of that row size loaded");
+	if (c >= e->roll_C || first + n > e->roll_T) return fail(e, APO_E_ARG, "range outside the rollouts");
 	CK(cudaSetDevice(e->device));
-	CK(cudaMemcpyAsync(out, e->roll.p + (uint64_t)c * e->roll_pitch + first, n * sizeof(apo_record), cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaMemcpyAsync(out, e->roll.p + ((uint64_t)c * e->roll_pitch + first) * row, n * row, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
+	return APO_OK;
+}
+}  // namespace
+
+extern "C" int apo_rollouts_upload(apo_engine *e, const apo_record *recs, uint32_t C, uint64_t T) { return rollouts_upload_rows(e, recs, 32, C, T); }
+extern "C" int apo_rollouts16_upload(apo_engine *e, const apo_record16 *recs, uint32_t C, uint64_t T) { return rollouts_upload_rows(e, recs, 16, C, T); }
+extern "C" int apo_rollouts_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T, uint32_t agent_permille) {
+	return rollouts_generate_rows(e, 32, seed, c0, C, t0, T, agent_permille);
+}
+extern "C" int apo_rollouts16_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T, uint32_t agent_permille) {
+	return rollouts_generate_rows(e, 16, seed, c0, C, t0, T, agent_permille);
+}
+extern "C" int apo_rollouts_download(apo_engine *e, apo_record *out, uint32_t c, uint64_t first, uint64_t n) { return rollouts_download_rows(e, out, 32, c, first, n); }
+extern "C" int apo_rollouts16_download(apo_engine *e, apo_record16 *out, uint32_t c, uint64_t first, uint64_t n) { return rollouts_download_rows(e, out, 16, c, first, n); }
+
+extern "C" int apo_record_pack16(const apo_record *in, uint64_t n, apo_record16 *out, uint64_t *bad) {
+	if ((!in || !out) && n) return APO_E_ARG;
+	for (uint64_t i = 0; i < n; i++) {
+		if (!apo::representable16(in[i])) { if (bad) *bad = i; return APO_E_ARG; }
+		out[i] = apo::pack16(in[i]);
+	}
+	return APO_OK;
+}
+extern "C" int apo_record_unpack16(const apo_record16 *in, uint64_t n, apo_record *out) {
+	if ((!in || !out) && n) return APO_E_ARG;
+	for (uint64_t i = 0; i < n; i++) out[i] = apo::unpack16(in[i]);
 	return APO_OK;
 }
 
@@ -546,23 +574,26 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	return finish_score(e, o, C, scores, counts, topk, report);
 }
 
-extern "C" int apo_score_host(apo_engine *e, const apo_score_opts *o, const float *dims, uint32_t C, uint64_t T,
-                              double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+namespace {
+// Streams host rows [C][T] (row bytes 36 = Form D, 32 = Form R, 16 = Form R16) through two device
+// windows: the H2D copy of chunk i+1 (copy stream) overlaps K1 on chunk i (compute stream).
+int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows, uint32_t row, uint32_t C, uint64_t T,
+                    double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
 	if (!e) return APO_E_ARG;
 	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
-	if (!dims || C == 0) return fail(e, APO_E_ARG, "dims is NULL or C == 0");
+	if (!rows || C == 0) return fail(e, APO_E_ARG, "input is NULL or C == 0");
 	if (o->K > C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, C);
-	if (o->first || o->count) return fail(e, APO_E_ARG, "windows are not supported by apo_score_host");
+	if (o->first || o->count) return fail(e, APO_E_ARG, "windows are not supported by the host-streaming calls");
 	CK(cudaSetDevice(e->device));
 	int rc;
 	if ((rc = ensure_scratch(e, C, o->K))) return rc;
 	// window of ~256 MB per buffer, a multiple of the K1 tile so chunks never split a tile
-	const int tile = apo::k1_tile_evals(36, (int)o->variant);
-	uint64_t Tc = (256ull << 20) / ((uint64_t)C * 36);
+	const int tile = apo::k1_tile_evals((int)row, (int)o->variant);
+	uint64_t Tc = (256ull << 20) / ((uint64_t)C * row);
 	Tc = Tc / tile * tile;
 	if (Tc < (uint64_t)tile) Tc = tile;
-	if (Tc > round_up(T, tile)) Tc = round_up(T ? T : 1, tile);
-	for (int i = 0; i < 2; i++) CK(e->win[i].reserve((uint64_t)C * Tc * APO_NDIM));
+	if (Tc > round_up(T ? T : 1, tile)) Tc = round_up(T ? T : 1, tile);
+	for (int i = 0; i < 2; i++) CK(e->win[i].reserve((uint64_t)C * Tc * row));
 	if ((rc = begin_score(e, C))) return rc;
 	const bool recip = (o->flags & APO_SCORE_RECIP) != 0;
 	int nchunk = 0;
@@ -570,23 +601,35 @@ extern "C" int apo_score_host(apo_engine *e, const apo_score_opts *o, const floa
 		const int b = nchunk & 1;
 		const uint64_t n = T - t0 < Tc ? T - t0 : Tc;
 		if (nchunk >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->win_free[b], 0));
-		CK(cudaMemcpy2DAsync(e->win[b].p, Tc * APO_NDIM * 4, dims + t0 * APO_NDIM, T * APO_NDIM * 4, n * APO_NDIM * 4, C, cudaMemcpyHostToDevice, e->copy_stream));
+		CK(cudaMemcpy2DAsync(e->win[b].p, Tc * row, rows + t0 * row, T * row, n * row, C, cudaMemcpyHostToDevice, e->copy_stream));
 		CK(cudaEventRecord(e->win_ready[b], e->copy_stream));
 		CK(cudaStreamWaitEvent(e->stream, e->win_ready[b], 0));
 		apo::K1Params P{};
-		P.base = (const uint8_t *)e->win[b].p; P.pitch_bytes = Tc * 36; P.C = C; P.T = n; P.acc = e->acc.p;
+		P.base = e->win[b].p; P.pitch_bytes = Tc * row; P.C = C; P.T = n; P.acc = e->acc.p;
 		P.lut = e->d_lut.p; P.W = e->W;
 		if (e->k1_used + 2 > e->k1_ev.size()) {
 			for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
 		}
 		CK(cudaEventRecord(e->k1_ev[e->k1_used], e->stream));
-		CK(apo::run_reward9(P, 36, (int)o->variant, recip, e->sm_count, e->stream));
+		CK(apo::run_reward9(P, (int)row, (int)o->variant, recip, e->sm_count, e->stream));
 		CK(cudaEventRecord(e->k1_ev[e->k1_used + 1], e->stream));
 		e->k1_used += 2;
 		e->timing.launches++;
 		CK(cudaEventRecord(e->win_free[b], e->stream));
 	}
 	return finish_score(e, o, C, scores, counts, topk, report);
+}
+}  // namespace
+
+extern "C" int apo_score_host(apo_engine *e, const apo_score_opts *o, const float *dims, uint32_t C, uint64_t T,
+                              double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+	return score_host_rows(e, o, (const uint8_t *)dims, 36, C, T, scores, counts, topk, report);
+}
+
+extern "C" int apo_score_host_records(apo_engine *e, const apo_score_opts *o, const void *recs, uint32_t row_bytes, uint32_t C, uint64_t T,
+                                      double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+	if (row_bytes != 32 && row_bytes != 16) return fail(e, APO_E_ARG, "row_bytes must be 32 (apo_record) or 16 (apo_record16)");
+	return score_host_rows(e, o, (const uint8_t *)recs, row_bytes, C, T, scores, counts, topk, report);
 }
 
 extern "C" int apo_last_timing(const apo_engine *e, apo_timing *out) {
@@ -630,6 +673,12 @@ extern "C" int apo_comm_init(apo_engine *e, int nranks, int rank, const uint8_t 
 	const int rc = g_nccl.CommInitRank(&comm, nranks, nid, rank);
 	if (rc != 0) return fail(e, APO_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
 	e->comm = comm; e->nranks = nranks; e->rank = rank;
+	// one tiny allreduce now so that the first scoring call does not pay NCCL's lazy connection setup (~1 s)
+	CK(e->misc.reserve(32));
+	CK(cudaMemsetAsync(e->misc.p + 24, 0, 8, e->stream));
+	const int wrc = g_nccl.AllReduce(e->misc.p + 24, e->misc.p + 24, 1, kNcclInt64, kNcclSum, e->comm, e->stream);
+	if (wrc != 0) return fail(e, APO_E_NCCL, "ncclAllReduce (warm-up): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(wrc) : "error");
+	CK(cudaStreamSynchronize(e->stream));
 	return APO_OK;
 }
 

@@ -13,6 +13,7 @@
 // tile with conflict-free LDS.128.
 #include <cstdlib>
 #include "apo_device.cuh"
+#include "apo_format.h"
 #include "apo_kernels.h"
 
 namespace apo {
@@ -240,16 +241,26 @@ k_reward9(const K1Params P) {
 				}
 			}
 		} else {
-			// Form R: evaluation e = k*NCONS + tid, 32 B = 2 x LDS.128
+			// Form R / R16: evaluation e = k*NCONS + tid, 32 B = 2 x LDS.128 or 16 B = 1 x LDS.128
+			auto load_record = [&](int e) -> apo_record {
+				if (ROW == 32) {
+					const uint4 *src = reinterpret_cast<const uint4 *>(st + (size_t)e * 32);
+					union { uint4 q[2]; apo_record r; } u;
+					u.q[0] = src[0]; u.q[1] = src[1];
+					return u.r;
+				} else {
+					union { uint4 q; apo_record16 p; } u;
+					u.q = *reinterpret_cast<const uint4 *>(st + (size_t)e * 16);
+					return unpack16(u.p);
+				}
+			};
 			if (n == Cfg::TILE) {
 				double ws4[Cfg::EPT]; double2 t4[Cfg::EPT]; uint32_t ok4[Cfg::EPT];
 #pragma unroll
 				for (int k = 0; k < Cfg::EPT; k++) {
-					const uint4 *src = reinterpret_cast<const uint4 *>(st + (size_t)(k * Cfg::NCONS + tid) * 32);
-					union { uint4 q[2]; apo_record r; } u;
-					u.q[0] = src[0]; u.q[1] = src[1];
-					record_ws(u.r, W, s_lut, ws4[k], t4[k]);
-					ok4[k] = ((u.r.flags & APO_F_VALID) && t4[k].x > 0.0) ? 1u : 0u;
+					const apo_record r = load_record(k * Cfg::NCONS + tid);
+					record_ws(r, W, s_lut, ws4[k], t4[k]);
+					ok4[k] = ((r.flags & APO_F_VALID) && t4[k].x > 0.0) ? 1u : 0u;
 					cnt += ok4[k];
 				}
 				const bool generic = !RECIP && ((__double2hiint(t4[0].y) | __double2hiint(t4[1].y) |
@@ -268,11 +279,9 @@ k_reward9(const K1Params P) {
 				for (int k = 0; k < Cfg::EPT; k++) {
 					const int e = k * Cfg::NCONS + tid;
 					if (e < n) {
-						const uint4 *src = reinterpret_cast<const uint4 *>(st + (size_t)e * 32);
-						union { uint4 q[2]; apo_record r; } u;
-						u.q[0] = src[0]; u.q[1] = src[1];
+						const apo_record r = load_record(e);
 						uint32_t ok;
-						const long long x = eval_record<RECIP>(u.r, W, s_lut, ok);
+						const long long x = eval_record<RECIP>(r, W, s_lut, ok);
 						acc.add(x);
 						cnt += ok;
 					}
@@ -330,6 +339,14 @@ cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_cou
 		case 3: return launch_k1<36, 8, 5>(P, grid, recip, st);
 		case 4: return launch_k1<36, 24, 2>(P, grid, recip, st);
 		default: return launch_k1<36, 20, 2>(P, grid, recip, st);
+		}
+	} else if (row == 16) {
+		switch (variant) {
+		case 1: return launch_k1<16, 16, 3>(P, grid, recip, st);
+		case 2: return launch_k1<16, 12, 4>(P, grid, recip, st);
+		case 3: return launch_k1<16, 8, 5>(P, grid, recip, st);
+		case 4: return launch_k1<16, 24, 2>(P, grid, recip, st);
+		default: return launch_k1<16, 20, 2>(P, grid, recip, st);
 		}
 	} else {
 		switch (variant) {
@@ -698,6 +715,32 @@ k_gen_records(apo_record *out, uint64_t pitch, unsigned long long seed, uint32_t
 		uint4 *dst = reinterpret_cast<uint4 *>(out + (uint64_t)c * pitch + t);
 		dst[0] = u.q[0]; dst[1] = u.q[1];
 	}
+}
+
+__global__ void __launch_bounds__(256)
+k_gen_records16(apo_record16 *out, uint64_t pitch, unsigned long long seed, uint32_t stream, uint32_t c0, uint32_t C,
+                uint64_t t0, uint64_t T, uint32_t agent_permille) {
+	const uint32_t c = blockIdx.y;
+	if (c >= C) return;
+	const unsigned long long key = gen_key(seed, stream, c0 + c);
+	const uint32_t qc = gen_quality(seed, stream, c0 + c);
+	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x) {
+		union { uint4 q; apo_record16 p; } u;
+		u.p = pack16(gen_record(key, qc, t0 + t, agent_permille));      // generator records are always representable
+		*reinterpret_cast<uint4 *>(out + (uint64_t)c * pitch + t) = u.q;
+	}
+}
+
+cudaError_t run_gen_records16(apo_record16 *out, uint64_t pitch, uint64_t seed, uint32_t stream, uint32_t c0, uint32_t C,
+                              uint64_t t0, uint64_t T, uint32_t agent_permille, cudaStream_t st) {
+	if (C == 0 || T == 0) return cudaSuccess;
+	uint64_t gx = (T + 255) / 256;
+	if (gx > 148ull * 64) gx = 148ull * 64;
+	for (uint32_t cb = 0; cb < C; cb += 32768) {
+		const uint32_t cn = C - cb < 32768 ? C - cb : 32768;
+		k_gen_records16<<<dim3((unsigned)gx, cn), 256, 0, st>>>(out + (uint64_t)cb * pitch, pitch, seed, stream, c0 + cb, cn, t0, T, agent_permille);
+	}
+	return cudaGetLastError();
 }
 
 cudaError_t run_gen_dims(float *out, uint64_t pitch_evals, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,

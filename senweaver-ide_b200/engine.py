@@ -36,6 +36,11 @@ RECORD_DTYPE = np.dtype([
     ("llmCalls", "<u4"), ("tokens", "<u4"), ("toolDurMs", "<f4"),
 ])
 assert RECORD_DTYPE.itemsize == 32
+RECORD16_DTYPE = np.dtype([
+    ("hdr", "<u2"), ("userMsgs", "u1"), ("asstMsgs", "u1"), ("toolCalls", "<u2"), ("toolFail", "<u2"),
+    ("llmCalls", "u1"), ("pad", "u1"), ("tokens", "<u2"), ("toolDurMs", "<f4"),
+])
+assert RECORD16_DTYPE.itemsize == 16
 
 
 class Pattern(C.Structure):
@@ -79,8 +84,9 @@ ABI_SYMBOLS = (
     "apo_abi_version", "apo_create", "apo_destroy", "apo_last_error", "apo_set_stream", "apo_set_weights",
     "apo_get_weights", "apo_reward_batch", "apo_reward_one", "apo_corpus_upload", "apo_corpus_generate",
     "apo_corpus_download", "apo_dims_upload", "apo_dims_generate", "apo_dims_download", "apo_dims_attach",
-    "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_score", "apo_score_begin",
-    "apo_score_accumulate", "apo_score_finish", "apo_score_host",
+    "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_rollouts16_upload",
+    "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_score",
+    "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records",
     "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy",
 )
 
@@ -129,6 +135,12 @@ def load_library() -> C.CDLL:
     L.apo_rollouts_upload.argtypes = [vp, vp, u32, u64]
     L.apo_rollouts_generate.argtypes = [vp, u64, u32, u32, u64, u64, u32]
     L.apo_rollouts_download.argtypes = [vp, vp, u32, u64, u64]
+    L.apo_rollouts16_upload.argtypes = [vp, vp, u32, u64]
+    L.apo_rollouts16_generate.argtypes = [vp, u64, u32, u32, u64, u64, u32]
+    L.apo_rollouts16_download.argtypes = [vp, vp, u32, u64, u64]
+    L.apo_record_pack16.argtypes = [vp, u64, vp, vp]
+    L.apo_record_unpack16.argtypes = [vp, u64, vp]
+    L.apo_score_host_records.argtypes = [vp, C.POINTER(ScoreOpts), vp, u32, u32, u64, vp, vp, vp, vp]
     L.apo_score.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp]
     L.apo_score_begin.argtypes = [vp, u32]
     L.apo_score_accumulate.argtypes = [vp, C.POINTER(ScoreOpts), u32]
@@ -253,6 +265,32 @@ class Engine:
         self._ck(self._L.apo_rollouts_download(self._h, _p(out), c, first, n))
         return out
 
+    def rollouts16_upload(self, recs: np.ndarray):
+        recs = np.ascontiguousarray(recs, RECORD16_DTYPE)
+        Cn, T = recs.shape
+        self._ck(self._L.apo_rollouts16_upload(self._h, _p(recs), Cn, T))
+
+    def rollouts16_generate(self, seed: int, c0: int, Cn: int, t0: int, T: int, agent_permille: int = 300):
+        self._ck(self._L.apo_rollouts16_generate(self._h, seed, c0, Cn, t0, T, agent_permille))
+
+    def rollouts16_download(self, c: int, first: int, n: int) -> np.ndarray:
+        out = np.empty(n, RECORD16_DTYPE)
+        self._ck(self._L.apo_rollouts16_download(self._h, _p(out), c, first, n))
+        return out
+
+    def score_host_records(self, recs: np.ndarray, K: int, corpus: bool = False, recip: bool = False, variant: int = 0) -> ScoreResult:
+        """recs: C-contiguous [C][T] of RECORD_DTYPE (32 B) or RECORD16_DTYPE (16 B) in host memory."""
+        assert recs.flags.c_contiguous and recs.ndim == 2 and recs.dtype.itemsize in (32, 16)
+        Cn, T = recs.shape
+        o = self._opts(K, SRC_ROLLOUTS, corpus, recip, variant, 0, 0)
+        scores = np.empty(Cn, np.float64)
+        counts = np.empty(Cn, np.uint64)
+        topk = np.empty(K, np.int32)
+        rep = CorpusReport() if corpus else None
+        self._ck(self._L.apo_score_host_records(self._h, C.byref(o), _p(recs), recs.dtype.itemsize, Cn, T, _p(scores), _p(counts),
+                                                _p(topk), C.byref(rep) if rep is not None else None))
+        return ScoreResult(scores, counts, topk, rep, self.last_timing())
+
     # -- scoring
     def _opts(self, K, source, corpus, recip, variant, first, count) -> ScoreOpts:
         return ScoreOpts(K, source, (SCORE_CORPUS if corpus else 0) | (SCORE_RECIP if recip else 0), variant, first, count)
@@ -329,3 +367,25 @@ class Engine:
 
     def comm_destroy(self):
         self._ck(self._L.apo_comm_destroy(self._h))
+
+
+def pack16(recs: np.ndarray) -> np.ndarray:
+    """Form R -> Form R16 (host helper of the C ABI); raises when a record is not representable."""
+    L = load_library()
+    recs = np.ascontiguousarray(recs, RECORD_DTYPE)
+    out = np.empty(recs.shape, RECORD16_DTYPE)
+    bad = C.c_uint64(0)
+    rc = L.apo_record_pack16(_p(recs), recs.size, _p(out), C.addressof(bad))
+    if rc != 0:
+        raise ApoError(rc, f"record {bad.value} is not representable in Form R16")
+    return out
+
+
+def unpack16(recs16: np.ndarray) -> np.ndarray:
+    L = load_library()
+    recs16 = np.ascontiguousarray(recs16, RECORD16_DTYPE)
+    out = np.empty(recs16.shape, RECORD_DTYPE)
+    rc = L.apo_record_unpack16(_p(recs16), recs16.size, _p(out))
+    if rc != 0:
+        raise ApoError(rc, "unpack16 failed")
+    return out

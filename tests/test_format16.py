@@ -1,0 +1,60 @@
+"""Form R16 (16-byte packed record): the product's host pack/unpack helpers against the oracle's
+independent unpacking, and the claim of include/apo_b200.h that packing leaves every output of
+the path unchanged (dims, finalReward, the six pattern predicates, tallies)."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+
+def rec_strategy():
+    return st.tuples(st.integers(0, 2), st.booleans(), st.booleans(), st.booleans(), st.integers(0, 4),
+                     st.integers(0, 65535), st.integers(0, 65535), st.integers(0, 65535), st.integers(0, 65535),
+                     st.integers(0, 2**32 - 1), st.integers(0, 2**32 - 1), st.floats(0, 1e9, width=32, allow_nan=False))
+
+
+def build(orc, t):
+    fb, err, ended, valid, mode, um, am, calls, fail, llm, tok, dur = t
+    fail = min(fail, calls)
+    r = np.zeros(1, orc.RECORD_DTYPE)
+    r["feedback"], r["mode"], r["userMsgs"], r["asstMsgs"] = fb, mode, um, am
+    r["flags"] = (1 if err else 0) | (2 if ended else 0) | (8 if valid else 0) | (16 if fail > 0 else 0)
+    r["toolCalls"], r["toolFail"], r["toolSucc"], r["llmCalls"], r["tokens"] = calls, fail, calls - fail, llm, tok
+    r["toolDurMs"] = dur if calls else 0.0
+    return r
+
+
+@settings(max_examples=400, deadline=None)
+@given(rec_strategy())
+def test_pack16_preserves_every_output_of_the_path(apo, orc, t):
+    apo.build_library()
+    r = build(orc, t)
+    back = orc.unpack16(apo.pack16(r))               # product pack -> oracle unpack (independent restatements)
+    assert np.array_equal(apo.unpack16(apo.pack16(r)), back)
+    d0, m0, f0 = orc.reward_one(r[0])
+    d1, m1, f1 = orc.reward_one(back[0])
+    assert m0 == m1 and f0 == f1
+    assert np.array_equal(np.nan_to_num(d0, nan=9.0), np.nan_to_num(d1, nan=9.0))
+    ra, rb = orc.report(r), orc.report(back)
+    assert [ra.pat[p].count for p in range(6)] == [rb.pat[p].count for p in range(6)]
+    assert (ra.good, ra.bad, ra.none, ra.withReward) == (rb.good, rb.bad, rb.none, rb.withReward)
+    assert list(ra.byMode[int(r["mode"][0])]) == list(rb.byMode[int(r["mode"][0])])
+
+
+def test_pack16_rejects_unrepresentable(apo, orc):
+    apo.build_library()
+    r = np.zeros(3, orc.RECORD_DTYPE)
+    r["toolCalls"], r["toolSucc"], r["toolFail"] = [5, 70000, 4], [4, 70000, 1], [1, 0, 1]   # 2nd too large, 3rd succ+fail != calls
+    assert apo.pack16(r[:1]).shape == (1,)
+    for bad in (r[1:2], r[2:3]):
+        with pytest.raises(apo.ApoError):
+            apo.pack16(bad)
+
+
+def test_generator_records_roundtrip(apo, orc):
+    apo.build_library()
+    recs = orc.gen_records(9, orc.STREAM_ROLLOUT, 0, 2, 0, 5000, 500, 4)
+    back = orc.unpack16(apo.pack16(recs))
+    exp = recs.copy()
+    exp["tokens"] = np.minimum(recs["tokens"], 65535)                # the only saturating field the generator reaches
+    assert np.array_equal(back, exp)
+    assert orc.score_records_fx(back) == orc.score_records_fx(recs)  # and it does not change a single evaluation

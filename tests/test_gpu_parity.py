@@ -430,3 +430,33 @@ def test_random_shapes_property(engine, orc):
         if sub.shape[1]:
             sums, counts = engine.debug_partials(C)
             assert (sums, counts) == orc.score_dims_fx(sub)
+
+
+# ------------------------------------------------------------------ Form R16 (packed) and host-record streaming
+def test_rollouts16_matches_oracle(engine, orc, apo):
+    C, T, seed = 5, 12_345, 0x5EED0006
+    recs = orc.gen_records(seed, orc.STREAM_ROLLOUT, 2, C, 64, T, 400, 8)
+    engine.rollouts16_generate(seed, 2, C, 64, T, 400)
+    packed = apo.pack16(recs)
+    for c in range(C):
+        assert engine.rollouts16_download(c, 0, T).tobytes() == packed[c].tobytes()
+    res = engine.score(C, 2, source=1)
+    unpacked = orc.unpack16(packed)
+    ref_s, ref_n = orc.score_records(unpacked)
+    assert_scores(res, ref_s, ref_n)
+    sums, counts = engine.debug_partials(C)
+    assert (sums, counts) == orc.score_records_fx(unpacked) == orc.score_records_fx(recs)
+    engine.rollouts16_upload(packed)                               # uploaded == generated
+    engine.score(C, 2, source=1)
+    assert engine.debug_partials(C) == (sums, counts)
+
+
+@pytest.mark.parametrize("row", [32, 16])
+def test_score_host_records_streaming(engine, orc, apo, row):
+    C, T = 12, 90_001
+    recs = orc.gen_records(0x5EED0007, orc.STREAM_ROLLOUT, 0, C, 0, T, 300, 8)
+    host = recs if row == 32 else apo.pack16(recs)
+    r = engine.score_host_records(host, 3)
+    sums, counts = engine.debug_partials(C)
+    assert (sums, counts) == orc.score_records_fx(recs)
+    assert np.array_equal(r.topk, orc.topk(orc.score_records(recs)[0], 3))

@@ -265,6 +265,31 @@ def main():
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e_ms = float(ems.item())
     d2h = 16 * Ce + 4 * Ke + 1024
+
+    # ---- the same call with the evaluations as packed trace records (Form R16, 16 B/eval): dims are
+    # derived on the device (TCS:668-763), 2.25x fewer bytes cross PCIe.  Reported beside the Form D number.
+    eng2.rollouts16_generate(SEED, 0, Ce, t0, Te, 300)
+    host16_t = torch.empty((Ce * Te * 16,), dtype=torch.uint8, pin_memory=True)
+    host16 = host16_t.numpy().view(pkg.RECORD16_DTYPE).reshape(Ce, Te)
+    for c in range(Ce):
+        host16[c] = eng2.rollouts16_download(c, 0, Te)
+
+    def e2e16_step():
+        eng2.corpus_upload(hrec, idx_base=t0)
+        return eng2.score_host_records(host16, Ke, corpus=True, variant=args.variant, recip=bool(args.recip))
+
+    for _ in range(2):
+        e2e16_step()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e16_step()
+    torch.cuda.synchronize()
+    e16_ms = (time.perf_counter() - e0) * 1e3 / args.e2e_steps
+    ems = torch.tensor([e16_ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e16_ms = float(ems.item())
     eng2.close()
 
     if rank == 0:
@@ -288,6 +313,9 @@ def main():
             "e2e": {"value": Ce * Te * world / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 36 + Te * 32,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e_ms,
                     "workload": f"{Ce} x {Te} Form D + {Te}-record corpus from pinned host memory per rank via apo_corpus_upload + apo_score_host"},
+            "e2e_records16": {"value": Ce * Te * world / (e16_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 16 + Te * 32,
+                              "d2h_bytes_per_step": d2h, "ms_per_step": e16_ms,
+                              "workload": f"{Ce} x {Te} packed trace records (Form R16, 16 B/eval) + corpus from pinned host memory per rank via apo_score_host_records"},
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -80,8 +80,8 @@ struct apo_engine {
 	cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
 	std::string err;
 	apo::Weights W;
-	double lut_tw[512], lut_rc[512];
-	DevBuf<double> d_lut;          // [0,512) total weight, [512,1024) reciprocal
+	double lut_tw[512], lut_rc[512], lut_cat[64];
+	DevBuf<double> d_lut;          // [0,512) total weight, [512,1024) reciprocal, [1024,1088) categorical products
 
 	DevBuf<apo_record> corpus; uint64_t corpus_T = 0, corpus_base = 0;
 	DevBuf<float> dims; const float *dims_ptr = nullptr; uint32_t dims_C = 0; uint64_t dims_T = 0, dims_pitch = 0;
@@ -130,10 +130,41 @@ void build_luts(apo_engine *e) {
 		const bool all_ones = (bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull;
 		e->lut_rc[m] = tw < 0.0 ? 1.0 : (all_ones ? -(1.0 / tw) : 1.0 / tw);
 	}
+	// categorical product table (csrc/apo_device.cuh CAT_*): value * weight with the same IEEE
+	// multiplications the reference performs at TCS:781, tabulated once per weight vector
+	const double *w = e->W.w;
+	double *c = e->lut_cat;
+	for (int i = 0; i < 64; i++) c[i] = 0.0;
+	for (int ended = 0; ended < 2; ended++)
+		for (int err = 0; err < 2; err++)
+			for (int fb = 0; fb < 3; fb++) {
+				const double d0 = fb == 1 ? 1.0 : (fb == 2 ? -1.0 : 0.0);                       // TCS:677-678
+				double d1 = 0.5;                                                                 // TCS:682-691
+				if (ended && !err) d1 = 0.8;
+				if (err) d1 = -0.5;
+				if (fb == 1) d1 = 1.0;
+				volatile double s = 0.0;
+				s = s + d0 * w[0];
+				s = s + d1 * w[1];
+				c[0 + fb + 3 * err + 6 * ended] = s;
+			}
+	const double lv_rel[4] = {1.0, -0.2, -0.5, -1.0}, lv_cnt[4] = {1.0, 0.3, -0.3, -0.8}, lv_dur[4] = {1.0, 0.5, 0.0, -0.5};
+	for (int k = 0; k < 4; k++) {
+		c[12 + k] = lv_rel[k] * w[3]; c[17 + k] = lv_cnt[k] * w[4]; c[22 + k] = lv_dur[k] * w[5];
+		c[34 + k] = lv_dur[k] * w[7]; c[39 + k] = lv_cnt[k] * w[8];
+	}
+	for (int k = 0; k < 6; k++) {
+		volatile double over = (double)k;
+		volatile double m = over * 0.4;
+		double ef = 1 - m;                                                                       // TCS:735
+		if (ef < -1) ef = -1;
+		c[27 + k] = ef * w[6];
+	}
 }
 
 int upload_luts(apo_engine *e) {
-	CK(e->d_lut.reserve(1024));
+	CK(e->d_lut.reserve(1024 + 64));
+	CK(cudaMemcpyAsync(e->d_lut.p + 1024, e->lut_cat, 64 * 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaMemcpyAsync(e->d_lut.p, e->lut_tw, 512 * 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaMemcpyAsync(e->d_lut.p + 512, e->lut_rc, 512 * 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaStreamSynchronize(e->stream));

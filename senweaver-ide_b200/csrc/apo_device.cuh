@@ -159,6 +159,56 @@ __device__ __forceinline__ uint32_t reward_dims(const apo_record &r, double dims
 	return 3u | (tool ? 0x1cu : 0u) | (hasdur ? 0x20u : 0u) | (llm ? 0x40u : 0u) | (tok ? 0x80u : 0u) | (conv ? 0x100u : 0u);
 }
 
+// ---------------------------------------------------------------- categorical product table
+// Seven of the nine dimensions take one of <= 4 values (TCS:677-761), so value*weight is one of
+// a handful of binary64 products.  The host tabulates them with the same IEEE multiplications
+// (apo_abi.cu build_luts); K1r then adds table entries in push order instead of running select
+// chains + DMULs.  The last slot of every group is +0.0 = "dimension not pushed".
+constexpr int CAT_D01 = 0;    // [fb + 3*err + 6*ended] -> fl(fl(0 + d0*w0) + d1*w1)      (12)
+constexpr int CAT_D3 = 12;    // thresholds met 0..3 -> {1,-0.2,-0.5,-1}*w3, [4] = 0       (5)
+constexpr int CAT_D4 = 17;    // {1,0.3,-0.3,-0.8}*w4                                      (5)
+constexpr int CAT_D5 = 22;    // {1,0.5,0,-0.5}*w5                                         (5)
+constexpr int CAT_D6 = 27;    // k = clamp(llm - thr, 0, 5) -> max(-1, 1 - k*0.4)*w6, [6] = 0 (7)
+constexpr int CAT_D7 = 34;    // {1,0.5,0,-0.5}*w7                                         (5)
+constexpr int CAT_D8 = 39;    // {1,0.3,-0.3,-0.8}*w8                                      (5)
+constexpr int CAT_WORDS = 64;
+
+// TCS:668-783 for one record through the product table: weighted sum in push order + mask.
+__device__ __forceinline__ uint32_t record_ws_table(const apo_record &r, double w2, const double *cat, double &ws_out) {
+	const bool agent = r.mode == 2;
+	const uint32_t err = (r.flags & APO_F_ERRORS) ? 1u : 0u, ended = (r.flags & APO_F_ENDED) ? 1u : 0u;
+	double ws = cat[CAT_D01 + (r.feedback < 3 ? r.feedback : 0u) + 3u * err + 6u * ended];
+	const bool tool = r.toolCalls > 0;
+	const double total = (double)(tool ? r.toolCalls : 1u);
+	const double rate = div_small_int((double)r.toolSucc, total);
+	ws = __dadd_rn(ws, keep_if(tool, __dmul_rn(__dadd_rn(__dmul_rn(rate, 2.0), -1.0), w2)));
+	const uint32_t sev = agent ? 5u : 3u, mod = agent ? 3u : 2u, mnr = agent ? 2u : 1u;
+	const uint32_t i3 = (r.toolFail >= mnr) + (r.toolFail >= mod) + (r.toolFail >= sev);
+	ws = __dadd_rn(ws, cat[CAT_D3 + (tool ? i3 : 4u)]);
+	const uint32_t cexc = agent ? 8u : 3u, cgood = agent ? 15u : 6u, cfair = agent ? 25u : 10u;
+	const uint32_t i4 = (r.toolCalls > cexc) + (r.toolCalls > cgood) + (r.toolCalls > cfair);
+	ws = __dadd_rn(ws, cat[CAT_D4 + (tool ? i4 : 4u)]);
+	const double dur = (double)r.toolDurMs;
+	const bool hasdur = tool && dur > 0.0;
+	const uint32_t i5 = (dur > __dmul_rn(1000.0, total)) + (dur > __dmul_rn(3000.0, total)) + (dur > __dmul_rn(10000.0, total));
+	ws = __dadd_rn(ws, cat[CAT_D5 + (hasdur ? i5 : 4u)]);
+	const bool llm = r.llmCalls > 0;
+	const uint32_t thr6 = agent ? 3u : 1u;
+	const uint32_t over = r.llmCalls > thr6 ? r.llmCalls - thr6 : 0u;
+	ws = __dadd_rn(ws, cat[CAT_D6 + (llm ? (over < 5u ? over : 5u) : 6u)]);
+	const bool tok = r.tokens > 0;
+	const uint32_t texc = agent ? 5000u : 2000u, tgood = agent ? 15000u : 5000u, tfair = agent ? 30000u : 10000u;
+	const uint32_t i7 = (r.tokens > texc) + (r.tokens > tgood) + (r.tokens > tfair);
+	ws = __dadd_rn(ws, cat[CAT_D7 + (tok ? i7 : 4u)]);
+	const uint32_t turns = r.userMsgs < r.asstMsgs ? r.userMsgs : r.asstMsgs;
+	const bool conv = turns > 0;
+	const uint32_t thr8 = agent ? 3u : 2u;
+	const uint32_t i8 = (turns > thr8) + (turns > thr8 * 2) + (turns > thr8 * 3);
+	ws = __dadd_rn(ws, cat[CAT_D8 + (conv ? i8 : 4u)]);
+	ws_out = ws;
+	return 3u | (tool ? 0x1cu : 0u) | (hasdur ? 0x20u : 0u) | (llm ? 0x40u : 0u) | (tok ? 0x80u : 0u) | (conv ? 0x100u : 0u);
+}
+
 // TCS:777-784.  lut[mask] = sum of the present weights added in push order (host-built,
 // same sequential binary64 adds); entries whose total weight is 0 hold -1 (finalReward null).
 // dims of absent dimensions must be +0.0 (adding +0.0*w leaves the running sum unchanged).

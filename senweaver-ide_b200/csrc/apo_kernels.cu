@@ -28,7 +28,7 @@ struct K1Cfg {
 	static constexpr int NCONS = CW * 32;
 	static constexpr int TILE = NCONS * EPT;            // evaluations per tile
 	static constexpr int STAGE_BYTES = TILE * ROW;
-	static constexpr int LUT_BYTES = 512 * 16;          // {total weight, its reciprocal} per presence mask
+	static constexpr int LUT_BYTES = 512 * 16 + CAT_WORDS * 8;   // {total weight, reciprocal} per presence mask + categorical products
 	static constexpr int BAR_OFF = STAGES * STAGE_BYTES + LUT_BYTES;
 	static constexpr int META_OFF = BAR_OFF + 2 * STAGES * 8;
 	static constexpr int SMEM = META_OFF + STAGES * 8;
@@ -94,15 +94,12 @@ __device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const
 	return to_fx(div_lut<RECIP>(ws, t));              // TCS:784
 }
 
-// One Form-R evaluation, first half (TCS:668-783): record -> weighted sum + LUT entry.
+// One Form-R evaluation, first half (TCS:668-783): record -> weighted sum + LUT entry.  The
+// categorical product table sits right behind the 512-entry LUT in shared memory.
 __device__ __forceinline__ void record_ws(const apo_record &r, const Weights &W, const double2 *lut,
                                           double &ws_out, double2 &t_out) {
-	double d[APO_NDIM];
-	const uint32_t mask = reward_dims(r, d);
-	double ws = 0.0;
-#pragma unroll
-	for (int i = 0; i < APO_NDIM; i++) ws = __dadd_rn(ws, __dmul_rn(d[i], W.w[i]));
-	ws_out = ws;
+	const double *cat = reinterpret_cast<const double *>(lut + 512);
+	const uint32_t mask = record_ws_table(r, W.w[2], cat, ws_out);
 	t_out = lut[lut_index(mask)];
 }
 
@@ -127,6 +124,7 @@ k_reward9(const K1Params P) {
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	for (int i = tid; i < 512; i += blockDim.x) s_lut[lut_index(i)] = make_double2(P.lut[i], P.lut[512 + i]);
+	for (int i = tid; i < CAT_WORDS; i += blockDim.x) reinterpret_cast<double *>(s_lut + 512)[i] = P.lut[1024 + i];
 	if (tid == 0) {
 		for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
 		mbar_fence_init();

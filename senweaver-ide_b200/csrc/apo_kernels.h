@@ -16,7 +16,8 @@ struct K1Params {
 	uint64_t T;                 // evaluations per candidate in this launch
 	uint64_t total_tiles;       // filled by run_reward9
 	long long *acc;             // accumulator vector (see apo_device.cuh)
-	const double *lut;          // [0,512) total weight per presence mask, [512,1024) its reciprocal
+	const double *lut;          // [0,512) total weight per presence mask, [512,1024) its reciprocal,
+	                            // [1024,1088) categorical product table (apo_device.cuh CAT_*)
 	Weights W;
 };
 

@@ -460,3 +460,18 @@ def test_score_host_records_streaming(engine, orc, apo, row):
     sums, counts = engine.debug_partials(C)
     assert (sums, counts) == orc.score_records_fx(recs)
     assert np.array_equal(r.topk, orc.topk(orc.score_records(recs)[0], 3))
+
+
+def test_rollouts_custom_weights_use_rebuilt_tables(engine, orc):
+    """K1r reads value*weight products from a table built per weight vector (apo_abi.cu build_luts)."""
+    w = np.array([0.2, 0.15, 0.1, 0.05, 0.07, 0.03, 0.2, 0.1, 0.1])
+    recs = orc.gen_records(0x5EED0008, orc.STREAM_ROLLOUT, 0, 4, 0, 20_000, 512, 8)
+    try:
+        engine.set_weights(w)
+        engine.rollouts_upload(recs)
+        r = engine.score(4, 2, source=1)
+        sums, counts = engine.debug_partials(4)
+        assert (sums, counts) == orc.score_records_fx(recs, w=w)
+        assert np.array_equal(r.topk, orc.topk(orc.score_records(recs, w=w)[0], 2))
+    finally:
+        engine.set_weights(orc.weights())

@@ -242,6 +242,29 @@ class APOService:
             print("[APO] Beam evaluation failed:", e)
             return None
 
+    def runBeamSearch(self, seedPrompt, proposeCandidates, rolloutDims, rounds=None):
+        """Client-side round driver around the GPU top-K: each round expands every beam
+        member into `branchFactor` children through the caller's `proposeCandidates(parent, n) -> [content]`
+        hook (the LLM critique/edit step of APO:918-988 lives there), scores parents + children on
+        `rolloutDims(candidates) -> float32 [C][T][9]`, keeps the top `beamWidth` and applies the
+        APO:1138-1166 update.  Returns the final beam state."""
+        rounds = rounds or self._config["beamRounds"]
+        beam = [{"version": "v0", "content": seedPrompt, "score": None, "createdAt": time.time() * 1000.0}]
+        counter = 0
+        for _ in range(rounds):
+            cands = list(beam)
+            for parent in beam:
+                for content in proposeCandidates(parent, self._config["branchFactor"]):
+                    counter += 1
+                    cands.append({"version": f"v{counter}", "content": content, "score": None,
+                                  "parentVersion": parent["version"], "createdAt": time.time() * 1000.0})
+            res = self.evaluateBeam(cands, dims=rolloutDims(cands))
+            if res is None:
+                break
+            beam = self._beamState["beam"]
+            self._beamState["versionCounter"] = counter
+        return self.getBeamState()
+
     def _applyBeamUpdate(self, bu):
         now = time.time() * 1000.0
         if self._beamState is None:                                          # APO:1141-1152

@@ -162,3 +162,25 @@ def test_payload_and_rule_budget(services):
                       "version": 1, "createdAt": 0, "updatedAt": 0} for i in range(10)]
     block = apo.packOptimizedRules()
     assert "(6/10 rules, budget limited)" in block and len(block.split("\n", 3)[3]) <= 2000
+
+
+def test_beam_search_round_driver(services):
+    """A toy search space: candidate quality = number of 'good' tokens in its text; the driver must climb."""
+    _, tc, apo = services
+    rng = np.random.default_rng(4)
+
+    def propose(parent, n):
+        return [parent["content"] + (" good" if rng.random() < 0.6 else " bad") for _ in range(n)]
+
+    def rollouts(cands):
+        out = np.full((len(cands), 256, 9), np.nan, np.float32)
+        for i, c in enumerate(cands):
+            q = (c["content"].count("good") - c["content"].count("bad")) / 10.0
+            out[i, :, 0] = np.clip(q + rng.normal(0, 0.01, 256), -1, 1)
+        return out
+
+    st = apo.runBeamSearch("- be helpful", propose, rollouts, rounds=3)
+    assert st["currentRound"] == 3 and len(st["beam"]) == 4
+    scores = [b["score"] for b in st["beam"]]
+    assert scores == sorted(scores, reverse=True) and st["historyBestScore"] >= scores[0]
+    assert st["historyBestPrompt"]["content"].count("good") >= 1

@@ -144,6 +144,20 @@ int apo_dims_upload(apo_engine *e, const float *dims, uint32_t C, uint64_t T);
 int apo_dims_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,
                       uint32_t agent_permille);
 int apo_dims_download(apo_engine *e, float *out, uint32_t c, uint64_t first, uint64_t n);
+/* Form Q — compact resident layout (csrc/apo_compact.cu): 8 one-byte codebook indices + the
+ * fp32 tool_success_rate per evaluation (12 B instead of 36 B), lossless.  Available when every
+ * dimension except d2 takes <= 255 distinct values (true for dims produced by TCS:668-763).
+ * apo_dims_compact transcodes the loaded Form D in place (the fp32 copy is released);
+ * the *_compact generate/upload variants never materialise the full fp32 tensor.  When the data
+ * is not categorical they return APO_E_STATE: apo_dims_compact keeps the loaded Form D usable, the
+ * streaming variants leave nothing loaded.  Scores, counts, top-K and the integer partial sums are
+ * bit-identical between the two layouts. */
+int apo_dims_compact(apo_engine *e);
+int apo_dims_generate_compact(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,
+                              uint32_t agent_permille);
+int apo_dims_upload_compact(apo_engine *e, const float *dims, uint32_t C, uint64_t T);
+/* 0 nothing loaded, 1 Form D (fp32), 2 Form Q (compact) */
+int apo_dims_layout(const apo_engine *e);
 /* Use a caller-owned device buffer (row pitch in evals, >= T rounded up to 4; 16-byte
  * aligned base).  The engine never frees it. */
 int apo_dims_attach(apo_engine *e, uint64_t device_ptr, uint32_t C, uint64_t T, uint64_t pitch_evals);

@@ -85,6 +85,10 @@ struct apo_engine {
 
 	DevBuf<apo_record> corpus; uint64_t corpus_T = 0, corpus_base = 0;
 	DevBuf<float> dims; const float *dims_ptr = nullptr; uint32_t dims_C = 0; uint64_t dims_T = 0, dims_pitch = 0;
+	// Form Q (compact) copy of the evaluations: replaces dims/dims_ptr when `compact` is set
+	DevBuf<unsigned long long> q8; DevBuf<float> qd2; DevBuf<uint32_t> qbook;   // qbook: [8][256] codebook + [8] overflow flags
+	DevBuf<double> d_ptab; DevBuf<float> stage;
+	uint32_t qbook_host[8 * 256]; bool compact = false;
 	DevBuf<uint8_t> roll; uint32_t roll_C = 0, roll_row = 32; uint64_t roll_T = 0, roll_pitch = 0;   // Form R (32 B) or R16 (16 B) rows
 
 	DevBuf<long long> acc; uint32_t last_C = 0;
@@ -171,6 +175,54 @@ int upload_luts(apo_engine *e) {
 	return APO_OK;
 }
 
+// value*weight per code for the eight coded dimensions (csrc/apo_compact.cu); table 0 = fl(0 + d0*w0)
+int upload_ptab(apo_engine *e) {
+	static const int dim_of[8] = {0, 1, 3, 4, 5, 6, 7, 8};
+	std::vector<double> tab(8 * 256, 0.0);
+	for (int j = 0; j < 8; j++)
+		for (int c = 0; c < 255; c++) {
+			const uint32_t bits = e->qbook_host[256 * j + c];
+			if (bits == 0xFFFFFFFFu) continue;
+			float f; memcpy(&f, &bits, 4);
+			volatile double p = (double)f * e->W.w[dim_of[j]];          // TCS:781 value * weight
+			if (j == 0) { volatile double z = 0.0; p = z + p; }          // weightedSum = 0 + first product
+			tab[256 * j + c] = p;
+		}
+	CK(e->d_ptab.reserve(8 * 256));
+	CK(cudaMemcpyAsync(e->d_ptab.p, tab.data(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return APO_OK;
+}
+
+int compact_begin(apo_engine *e, uint32_t C, uint64_t pitch) {
+	CK(e->q8.reserve((uint64_t)(C ? C : 1) * pitch));
+	CK(e->qd2.reserve((uint64_t)(C ? C : 1) * pitch));
+	CK(e->qbook.reserve(8 * 256 + 8));
+	CK(cudaMemsetAsync(e->qbook.p, 0xFF, 8 * 256 * 4, e->stream));
+	CK(cudaMemsetAsync(e->qbook.p + 8 * 256, 0, 8 * 4, e->stream));
+	// pad evaluations of every row: all codes 255 + NaN = finalReward null
+	CK(cudaMemsetAsync(e->q8.p, 0xFF, (uint64_t)(C ? C : 1) * pitch * 8, e->stream));
+	CK(cudaMemsetAsync(e->qd2.p, 0xFF, (uint64_t)(C ? C : 1) * pitch * 4, e->stream));
+	return APO_OK;
+}
+
+// returns APO_E_STATE when a coded dimension has more than 255 distinct values
+int compact_finish(apo_engine *e, uint32_t C, uint64_t T, uint64_t pitch) {
+	uint32_t host[8 * 256 + 8];
+	CK(cudaMemcpyAsync(host, e->qbook.p, sizeof host, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	for (int j = 0; j < 8; j++)
+		if (host[8 * 256 + j]) {
+			e->q8.release(); e->qd2.release();
+			return fail(e, APO_E_STATE, "evaluations are not categorical: coded dimension %d has more than 255 distinct values; Form D is kept", j < 2 ? j : j + 1);
+		}
+	memcpy(e->qbook_host, host, sizeof e->qbook_host);
+	int rc = upload_ptab(e);
+	if (rc) return rc;
+	e->compact = true; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch; e->dims_ptr = nullptr;
+	return APO_OK;
+}
+
 struct ResultLayout { uint64_t off_scores, off_counts, off_topk, off_report, bytes; };
 ResultLayout result_layout(uint32_t C, uint32_t K) {
 	ResultLayout L;
@@ -226,6 +278,21 @@ int begin_score(apo_engine *e, uint32_t C) {
 int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_offset, uint64_t first, uint64_t count) {
 	const bool raw = o->source == APO_SRC_ROLLOUTS;
 	const uint32_t C = raw ? e->roll_C : e->dims_C;
+	if (!raw && e->compact) {
+		if (!count) return APO_OK;
+		apo::KqParams Q{};
+		Q.q8 = e->q8.p + first; Q.d2 = e->qd2.p + first; Q.pitch_evals = e->dims_pitch; Q.C = C; Q.T = count;
+		Q.acc = e->acc.p + (uint64_t)ACC_PER_CAND * cand_offset; Q.lut = e->d_lut.p; Q.ptab = e->d_ptab.p; Q.w2 = e->W.w[2];
+		if (e->k1_used + 2 > e->k1_ev.size()) {
+			for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
+		}
+		CK(cudaEventRecord(e->k1_ev[e->k1_used], e->stream));
+		CK(apo::run_reward9q(Q, (int)o->variant, (o->flags & APO_SCORE_RECIP) != 0, e->sm_count, e->stream));
+		CK(cudaEventRecord(e->k1_ev[e->k1_used + 1], e->stream));
+		e->k1_used += 2;
+		e->timing.launches++;
+		return APO_OK;
+	}
 	apo::K1Params P{};
 	const int row = raw ? (int)e->roll_row : 36;
 	const uint64_t pitch = raw ? e->roll_pitch : e->dims_pitch;
@@ -348,6 +415,7 @@ extern "C" void apo_destroy(apo_engine *e) {
 	cudaSetDevice(e->device);
 	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+	e->q8.release(); e->qd2.release(); e->qbook.release(); e->d_ptab.release(); e->stage.release();
 	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->misc.release();
 	e->result.release(); e->keys.release(); e->sel_key.release(); e->sel_idx.release();
 	e->win[0].release(); e->win[1].release(); e->batch_in.release(); e->batch_out.release(); e->batch_mask.release();
@@ -376,7 +444,9 @@ extern "C" int apo_set_weights(apo_engine *e, const double w[APO_NDIM]) {
 	CK(cudaSetDevice(e->device));
 	memcpy(e->W.w, w, sizeof e->W.w);
 	build_luts(e);
-	return upload_luts(e);
+	int rc = upload_luts(e);
+	if (rc == APO_OK && e->compact) rc = upload_ptab(e);
+	return rc;
 }
 
 extern "C" int apo_get_weights(const apo_engine *e, double w[APO_NDIM]) {
@@ -451,7 +521,7 @@ extern "C" int apo_dims_upload(apo_engine *e, const float *dims, uint32_t C, uin
 		CK(cudaMemcpy2DAsync(e->dims.p, pitch * APO_NDIM * 4, dims, T * APO_NDIM * 4, T * APO_NDIM * 4, C, cudaMemcpyHostToDevice, e->stream));
 	}
 	CK(cudaStreamSynchronize(e->stream));
-	e->dims_ptr = e->dims.p; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch;
+	e->dims_ptr = e->dims.p; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch; e->compact = false;
 	return APO_OK;
 }
 
@@ -463,14 +533,22 @@ extern "C" int apo_dims_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint
 	if (pitch != T && C) CK(cudaMemsetAsync(e->dims.p, 0xFF, (uint64_t)C * pitch * APO_NDIM * 4, e->stream));
 	CK(apo::run_gen_dims(e->dims.p, pitch, seed, c0, C, t0, T, agent_permille, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
-	e->dims_ptr = e->dims.p; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch;
+	e->dims_ptr = e->dims.p; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch; e->compact = false;
 	return APO_OK;
 }
 
 extern "C" int apo_dims_download(apo_engine *e, float *out, uint32_t c, uint64_t first, uint64_t n) {
 	if (!e || !out) return fail(e, APO_E_ARG, "NULL argument");
-	if (!e->dims_ptr || c >= e->dims_C || first + n > e->dims_T) return fail(e, APO_E_ARG, "range outside the evaluations");
+	if ((!e->dims_ptr && !e->compact) || c >= e->dims_C || first + n > e->dims_T) return fail(e, APO_E_ARG, "range outside the evaluations");
 	CK(cudaSetDevice(e->device));
+	if (e->compact) {
+		CK(e->stage.reserve((n ? n : 1) * APO_NDIM));
+		const uint64_t off = (uint64_t)c * e->dims_pitch + first;
+		CK(apo::run_decode(e->q8.p + off, e->qd2.p + off, n, e->qbook.p, e->stage.p, e->stream));
+		CK(cudaMemcpyAsync(out, e->stage.p, n * APO_NDIM * 4, cudaMemcpyDeviceToHost, e->stream));
+		CK(cudaStreamSynchronize(e->stream));
+		return APO_OK;
+	}
 	CK(cudaMemcpyAsync(out, e->dims_ptr + ((uint64_t)c * e->dims_pitch + first) * APO_NDIM, n * APO_NDIM * 4, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	return APO_OK;
@@ -480,8 +558,74 @@ extern "C" int apo_dims_attach(apo_engine *e, uint64_t device_ptr, uint32_t C, u
 	if (!e) return APO_E_ARG;
 	if (!device_ptr || device_ptr % 16) return fail(e, APO_E_ARG, "device pointer must be non-NULL and 16-byte aligned");
 	if (pitch_evals % 4 || pitch_evals < round_up(T, 4)) return fail(e, APO_E_ARG, "pitch must be a multiple of 4 evaluations and >= T rounded up to 4");
-	e->dims_ptr = (const float *)(uintptr_t)device_ptr; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch_evals;
+	e->dims_ptr = (const float *)(uintptr_t)device_ptr; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch_evals; e->compact = false;
 	return APO_OK;
+}
+
+extern "C" int apo_dims_layout(const apo_engine *e) {
+	if (!e) return 0;
+	if (e->compact) return 2;
+	return (e->dims_ptr && e->dims_C) ? 1 : 0;
+}
+
+extern "C" int apo_dims_compact(apo_engine *e) {
+	if (!e) return APO_E_ARG;
+	if (e->compact) return APO_OK;
+	if (!e->dims_ptr || e->dims_C == 0) return fail(e, APO_E_STATE, "no dims loaded");
+	CK(cudaSetDevice(e->device));
+	const uint32_t C = e->dims_C; const uint64_t T = e->dims_T, pitch_in = e->dims_pitch, pitch = round_up(T ? T : 1, 32);
+	int rc = compact_begin(e, C, pitch);
+	if (rc) return rc;
+	CK(apo::run_transcode(e->dims_ptr, pitch_in, C, T, e->q8.p, e->qd2.p, pitch, e->qbook.p, e->qbook.p + 8 * 256, e->stream));
+	const float *keep = e->dims_ptr;
+	if ((rc = compact_finish(e, C, T, pitch))) { e->dims_ptr = keep; return rc; }
+	e->dims.release();                                  // the fp32 copy (if engine-owned) is no longer needed
+	return APO_OK;
+}
+
+namespace {
+// chunked producer -> transcoder: at most ~2 GB of fp32 staging, never the whole tensor
+template <class Fill>
+int compact_stream(apo_engine *e, uint32_t C, uint64_t T, Fill fill) {
+	CK(cudaSetDevice(e->device));
+	const uint64_t pitch = round_up(T ? T : 1, 32);
+	uint64_t Cc = (2ull << 30) / (pitch * 36);
+	if (Cc < 1) Cc = 1;
+	if (Cc > C) Cc = C ? C : 1;
+	CK(e->stage.reserve(Cc * pitch * APO_NDIM));
+	int rc = compact_begin(e, C, pitch);
+	if (rc) return rc;
+	for (uint32_t c0 = 0; c0 < C; c0 += (uint32_t)Cc) {
+		const uint32_t cn = C - c0 < Cc ? C - c0 : (uint32_t)Cc;
+		if ((rc = fill(c0, cn, e->stage.p, pitch))) return rc;
+		CK(apo::run_transcode(e->stage.p, pitch, cn, T, e->q8.p + (uint64_t)c0 * pitch, e->qd2.p + (uint64_t)c0 * pitch, pitch,
+		                      e->qbook.p, e->qbook.p + 8 * 256, e->stream));
+	}
+	e->compact = false; e->dims_ptr = nullptr; e->dims_C = 0;          // whatever was loaded before is superseded
+	rc = compact_finish(e, C, T, pitch);
+	e->stage.release();
+	if (rc == APO_OK) e->dims.release();
+	return rc;
+}
+}  // namespace
+
+extern "C" int apo_dims_generate_compact(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T, uint32_t agent_permille) {
+	if (!e) return APO_E_ARG;
+	return compact_stream(e, C, T, [&](uint32_t cb, uint32_t cn, float *stage, uint64_t pitch) -> int {
+		CK(apo::run_gen_dims(stage, pitch, seed, c0 + cb, cn, t0, T, agent_permille, e->stream));
+		return APO_OK;
+	});
+}
+
+extern "C" int apo_dims_upload_compact(apo_engine *e, const float *dims, uint32_t C, uint64_t T) {
+	if (!e) return APO_E_ARG;
+	if (C && T && !dims) return fail(e, APO_E_ARG, "dims is NULL");
+	return compact_stream(e, C, T, [&](uint32_t cb, uint32_t cn, float *stage, uint64_t pitch) -> int {
+		CK(cudaMemcpy2DAsync(stage, pitch * APO_NDIM * 4, dims + (uint64_t)cb * T * APO_NDIM, T * APO_NDIM * 4, T * APO_NDIM * 4, cn,
+		                     cudaMemcpyHostToDevice, e->stream));
+		CK(cudaStreamSynchronize(e->stream));              // the host chunk may be reused by the caller after return
+		return APO_OK;
+	});
 }
 
 namespace {
@@ -552,7 +696,7 @@ static int source_shape(apo_engine *e, const apo_score_opts *o, uint32_t *C, uin
 	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
 	if (o->source > APO_SRC_ROLLOUTS) return fail(e, APO_E_ARG, "unknown source %u", o->source);
 	const bool raw = o->source == APO_SRC_ROLLOUTS;
-	if (raw ? (e->roll.p == nullptr || e->roll_C == 0) : (e->dims_ptr == nullptr || e->dims_C == 0))
+	if (raw ? (e->roll.p == nullptr || e->roll_C == 0) : ((e->dims_ptr == nullptr && !e->compact) || e->dims_C == 0))
 		return fail(e, APO_E_STATE, "no %s loaded", raw ? "rollouts" : "dims");
 	*C = raw ? e->roll_C : e->dims_C;
 	*T = raw ? e->roll_T : e->dims_T;

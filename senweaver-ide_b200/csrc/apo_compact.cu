@@ -1,0 +1,301 @@
+// apo_compact.cu — Form Q: a lossless compact HBM layout for resident evaluations, and K1q.
+//
+// The path is HBM-bound (36 B per evaluation in Form D).  Eight of the nine reward dimensions
+// of the reference take a handful of values (TCS:677-761: user_feedback, task_completion,
+// tool_call_reliability, tool_call_efficiency, tool_duration_efficiency, response_efficiency,
+// token_efficiency, conversation_efficiency); only tool_success_rate (d2 = succ/total*2-1,
+// TCS:698) is a ratio.  Form Q therefore keeps, per evaluation,
+//     q8  : 8 one-byte codes (dims 0,1,3,4,5,6,7,8; 255 = dimension absent)       8 B
+//     d2  : the fp32 value of dim 2 (NaN = absent)                                 4 B
+// = 12 B instead of 36 B, plus one codebook of <= 255 fp32 bit patterns per coded dimension.
+// The transcoder (k_transcode) builds the codebooks with a find-or-insert hash and refuses
+// data with more than 255 distinct values in a coded dimension — the engine then simply keeps
+// Form D.  It is lossless: decoding returns the original fp32 bit patterns (absent = NaN).
+//
+// K1q reads value*weight straight from a shared-memory product table indexed by code (built on
+// the host with the same IEEE multiplications as TCS:781), so a coded dimension costs one LDS.64
+// and one DADD; sums, division and the exact fixed-point accumulation are those of K1, hence the
+// integer partial sums are bit-identical to K1's and to the oracle's.
+#include <cstdlib>
+#include "apo_device.cuh"
+#include "apo_kernels.h"
+
+namespace apo {
+
+// dims held as codes, in byte order of q8: 0,1,3,4,5,6,7,8 (byte j <-> dim j < 2 ? j : j + 1)
+constexpr uint32_t SLOT_EMPTY = 0xFFFFFFFFu;     // an fp32 NaN pattern: never a stored value
+
+// =================================================================== transcoder Form D -> Form Q
+// codebook: [8][256] uint32 (fp32 bit patterns, SLOT_EMPTY = free; slot 255 is never used),
+// overflow: [8] flags.  Slots are only ever filled, never moved: a code handed out stays valid.
+__device__ __forceinline__ uint32_t find_or_insert(uint32_t *s_slots, uint32_t *g_slots, uint32_t bits, uint32_t *overflow) {
+	uint32_t h = (bits * 2654435761u) >> 24;                 // 0..255
+	if (h == 255) h = 0;
+	for (int probe = 0; probe < 255; probe++) {
+		uint32_t cur = s_slots[h];
+		if (cur == bits) return h;
+		if (cur == SLOT_EMPTY) {
+			// not in this CTA's copy: consult / claim the global slot
+			cur = atomicCAS(&g_slots[h], SLOT_EMPTY, bits);
+			if (cur == SLOT_EMPTY) cur = bits;
+			s_slots[h] = cur;                                 // benign race: every writer stores the global truth
+			if (cur == bits) return h;
+		}
+		h = h == 254 ? 0 : h + 1;
+	}
+	*overflow = 1u;
+	return 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_transcode(const float *dims, uint64_t pitch_in, uint32_t C, uint64_t T, unsigned long long *q8, float *d2,
+            uint64_t pitch_out, uint32_t *codebook, uint32_t *overflow) {
+	__shared__ uint32_t s_slots[8 * 256];
+	for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) s_slots[i] = ((volatile uint32_t *)codebook)[i];
+	__syncthreads();
+	const uint32_t c = blockIdx.y;
+	if (c >= C) return;
+	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x) {
+		const float *row = dims + ((uint64_t)c * pitch_in + t) * APO_NDIM;
+		unsigned long long q = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const int dim = j < 2 ? j : j + 1;
+			const float f = row[dim];
+			uint32_t code = 255u;
+			if (f == f) code = find_or_insert(s_slots + 256 * j, codebook + 256 * j, __float_as_uint(f), overflow + j);
+			q |= (unsigned long long)code << (8 * j);
+		}
+		q8[(uint64_t)c * pitch_out + t] = q;
+		const float f2 = row[2];
+		d2[(uint64_t)c * pitch_out + t] = (f2 == f2) ? f2 : __int_as_float(0x7fc00000);
+	}
+}
+
+cudaError_t run_transcode(const float *dims, uint64_t pitch_in, uint32_t C, uint64_t T, unsigned long long *q8, float *d2,
+                          uint64_t pitch_out, uint32_t *codebook, uint32_t *overflow, cudaStream_t st) {
+	if (C == 0 || T == 0) return cudaSuccess;
+	uint64_t gx = (T + 255) / 256;
+	if (gx > 148ull * 16) gx = 148ull * 16;
+	for (uint32_t cb = 0; cb < C; cb += 32768) {
+		const uint32_t cn = C - cb < 32768 ? C - cb : 32768;
+		k_transcode<<<dim3((unsigned)gx, cn), 256, 0, st>>>(dims + (uint64_t)cb * pitch_in * APO_NDIM, pitch_in, cn, T,
+		                                                   q8 + (uint64_t)cb * pitch_out, d2 + (uint64_t)cb * pitch_out, pitch_out, codebook, overflow);
+	}
+	return cudaGetLastError();
+}
+
+// Form Q -> Form D (tests, apo_dims_download)
+__global__ void __launch_bounds__(256)
+k_decode(const unsigned long long *q8, const float *d2, uint64_t n, const uint32_t *codebook, float *out) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const unsigned long long q = q8[i];
+	float *row = out + i * APO_NDIM;
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		const int dim = j < 2 ? j : j + 1;
+		const uint32_t code = (uint32_t)(q >> (8 * j)) & 255u;
+		row[dim] = code == 255u ? __int_as_float(0x7fc00000) : __uint_as_float(codebook[256 * j + code]);
+	}
+	row[2] = d2[i];
+}
+
+cudaError_t run_decode(const unsigned long long *q8, const float *d2, uint64_t n, const uint32_t *codebook, float *out, cudaStream_t st) {
+	if (n == 0) return cudaSuccess;
+	k_decode<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q8, d2, n, codebook, out);
+	return cudaGetLastError();
+}
+
+// =================================================================== K1q
+struct QMeta { int32_t cand; int32_t n; };
+
+template <int CW, int EPT, int STAGES>
+struct KqCfg {
+	static constexpr int NCONS = CW * 32;
+	static constexpr int TILE = NCONS * EPT;
+	static constexpr int Q8_BYTES = TILE * 8, D2_BYTES = TILE * 4;
+	static constexpr int STAGE_BYTES = Q8_BYTES + D2_BYTES;
+	static constexpr int LUT_OFF = STAGES * STAGE_BYTES;          // double2[512]
+	static constexpr int PTAB_OFF = LUT_OFF + 512 * 16;           // double[8][256]
+	static constexpr int BAR_OFF = PTAB_OFF + 8 * 256 * 8;
+	static constexpr int META_OFF = BAR_OFF + 2 * STAGES * 8;
+	static constexpr int SMEM = META_OFF + STAGES * 8;
+	static_assert(EPT % 4 == 0, "evaluations are processed in interleaved groups of four");
+};
+
+// One Form-Q evaluation, first half: weighted sum in push order (TCS:777-783) + LUT entry.
+__device__ __forceinline__ void evalq_ws(unsigned long long q, float d2f, const double *ptab, double w2, const double2 *lut,
+                                         double &ws_out, double2 &t_out, uint32_t &valid) {
+	const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
+	double ws = ptab[0 * 256 + (lo & 255u)];                          // table 0 holds fl(0 + d0*w0)
+	ws = __dadd_rn(ws, ptab[1 * 256 + ((lo >> 8) & 255u)]);
+	const bool p2 = (d2f == d2f);
+	ws = __dadd_rn(ws, __dmul_rn((double)(p2 ? d2f : 0.0f), w2));
+	ws = __dadd_rn(ws, ptab[2 * 256 + ((lo >> 16) & 255u)]);
+	ws = __dadd_rn(ws, ptab[3 * 256 + (lo >> 24)]);
+	ws = __dadd_rn(ws, ptab[4 * 256 + (hi & 255u)]);
+	ws = __dadd_rn(ws, ptab[5 * 256 + ((hi >> 8) & 255u)]);
+	ws = __dadd_rn(ws, ptab[6 * 256 + ((hi >> 16) & 255u)]);
+	ws = __dadd_rn(ws, ptab[7 * 256 + (hi >> 24)]);
+	// presence bits: byte != 255, gathered four at a time (bits 0,8,16,24 -> a nibble)
+	const uint32_t nlo = ((__vcmpne4(lo, 0xFFFFFFFFu) & 0x01010101u) * 0x01020408u) >> 24;   // dims 0,1,3,4 -> bits 0..3
+	const uint32_t nhi = ((__vcmpne4(hi, 0xFFFFFFFFu) & 0x01010101u) * 0x01020408u) >> 24;   // dims 5,6,7,8 -> bits 0..3
+	// rotated LUT index (apo_device.cuh lut_bit): dims 5..8 -> bits 0..3, dims 0,1 -> 4,5, dim 2 -> 6, dims 3,4 -> 7,8
+	const uint32_t idx = (nhi & 15u) | ((nlo & 3u) << 4) | ((p2 ? 1u : 0u) << 6) | (((nlo >> 2) & 3u) << 7);
+	ws_out = ws;
+	t_out = lut[idx];
+	valid = t_out.x > 0.0 ? 1u : 0u;
+}
+
+template <int CW, int EPT, int STAGES, bool RECIP>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
+k_reward9q(const KqParams P) {
+	using Cfg = KqCfg<CW, EPT, STAGES>;
+	extern __shared__ __align__(128) uint8_t smem[];
+	double2 *s_lut = reinterpret_cast<double2 *>(smem + Cfg::LUT_OFF);
+	double *s_ptab = reinterpret_cast<double *>(smem + Cfg::PTAB_OFF);
+	uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::BAR_OFF);
+	uint64_t *empty = full + STAGES;
+	QMeta *meta = reinterpret_cast<QMeta *>(smem + Cfg::META_OFF);
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	for (int i = tid; i < 512; i += blockDim.x) s_lut[lut_index(i)] = make_double2(P.lut[i], P.lut[512 + i]);
+	for (int i = tid; i < 8 * 256; i += blockDim.x) s_ptab[i] = P.ptab[i];
+	if (tid == 0) {
+		for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
+		mbar_fence_init();
+	}
+	__syncthreads();
+
+	const uint64_t lo_t = P.total_tiles * blockIdx.x / gridDim.x;
+	const uint64_t hi_t = P.total_tiles * (blockIdx.x + 1ull) / gridDim.x;
+
+	if (warp == CW) {
+		if (lane == 0) {
+			const uint64_t pol = policy_evict_first();
+			uint32_t it = 0;
+			for (uint64_t tile = lo_t; tile <= hi_t; ++tile, ++it) {
+				const int s = it % STAGES;
+				const uint32_t ph = (it / STAGES) & 1u;
+				mbar_wait(&empty[s], ph ^ 1u);
+				if (tile == hi_t) { meta[s].cand = -1; meta[s].n = 0; mbar_arrive(&full[s]); break; }
+				const uint32_t c = (uint32_t)(tile / P.tiles_per_cand);
+				const uint64_t j = tile - (uint64_t)c * P.tiles_per_cand;
+				const uint64_t e0 = j * Cfg::TILE;
+				const uint64_t rem = P.T - e0;
+				const uint32_t n = rem < (uint64_t)Cfg::TILE ? (uint32_t)rem : (uint32_t)Cfg::TILE;
+				const uint32_t n4 = (n + 3u) & ~3u;                         // 32 B / 16 B multiples for the two bulk copies
+				meta[s].cand = (int32_t)c; meta[s].n = (int32_t)n;
+				mbar_expect_tx(&full[s], n4 * 12u);
+				uint8_t *st = smem + s * Cfg::STAGE_BYTES;
+				bulk_g2s(st, P.q8 + (uint64_t)c * P.pitch_evals + e0, n4 * 8u, &full[s], pol);
+				bulk_g2s(st + Cfg::Q8_BYTES, P.d2 + (uint64_t)c * P.pitch_evals + e0, n4 * 4u, &full[s], pol);
+			}
+		}
+		return;
+	}
+
+	Acc128 acc; acc.zero();
+	uint32_t cnt = 0;
+	int cur = -1;
+	const double w2 = P.w2;
+	auto flush = [&](int c) {
+		long long *dst = P.acc + (uint64_t)ACC_PER_CAND * c;
+		flush_acc128(acc, dst, lane);
+		const uint32_t n = warp_sum_u32(cnt);
+		if (lane == 0 && n) atomicAdd((unsigned long long *)dst + 3, (unsigned long long)n);
+		acc.zero(); cnt = 0;
+	};
+
+	for (uint32_t it = 0;; ++it) {
+		const int s = it % STAGES;
+		const uint32_t ph = (it / STAGES) & 1u;
+		mbar_wait(&full[s], ph);
+		const int c = meta[s].cand, n = meta[s].n;
+		if (n == 0) break;
+		if (c != cur) { if (cur >= 0) flush(cur); cur = c; }
+		const unsigned long long *sq = reinterpret_cast<const unsigned long long *>(smem + s * Cfg::STAGE_BYTES);
+		const float *sd = reinterpret_cast<const float *>(smem + s * Cfg::STAGE_BYTES + Cfg::Q8_BYTES);
+		if (n == Cfg::TILE) {
+#pragma unroll
+			for (int g = 0; g < EPT / 4; g++) {
+				double ws4[4]; double2 t4[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const int e = (4 * g + k) * Cfg::NCONS + tid;              // 8 B / 4 B lane stride: conflict-free
+					uint32_t ok;
+					evalq_ws(sq[e], sd[e], s_ptab, w2, s_lut, ws4[k], t4[k], ok);
+					cnt += ok;
+				}
+				const bool generic = !RECIP && ((__double2hiint(t4[0].y) | __double2hiint(t4[1].y) |
+				                                 __double2hiint(t4[2].y) | __double2hiint(t4[3].y)) < 0);
+				long long x4 = 0;
+				if (!generic) {
+#pragma unroll
+					for (int k = 0; k < 4; k++) x4 += to_fx(div_fast<RECIP>(ws4[k], t4[k]));
+				} else {
+#pragma unroll
+					for (int k = 0; k < 4; k++) x4 += to_fx(div_lut<RECIP>(ws4[k], t4[k]));
+				}
+				acc.add(x4);
+			}
+		} else {
+			for (int k = 0; k < EPT; k++) {
+				const int e = k * Cfg::NCONS + tid;
+				if (e < n) {
+					double ws; double2 t; uint32_t ok;
+					evalq_ws(sq[e], sd[e], s_ptab, w2, s_lut, ws, t, ok);
+					acc.add(to_fx(div_lut<RECIP>(ws, t)));
+					cnt += ok;
+				}
+			}
+		}
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&empty[s]);
+	}
+	if (cur >= 0) flush(cur);
+}
+
+template <int CW, int EPT, int STAGES>
+static cudaError_t launch_kq(const KqParams &P, int grid, bool recip, cudaStream_t st) {
+	using Cfg = KqCfg<CW, EPT, STAGES>;
+	cudaError_t err;
+	if (recip) {
+		auto k = k_reward9q<CW, EPT, STAGES, true>;
+		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
+		k<<<grid, (CW + 1) * 32, Cfg::SMEM, st>>>(P);
+	} else {
+		auto k = k_reward9q<CW, EPT, STAGES, false>;
+		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
+		k<<<grid, (CW + 1) * 32, Cfg::SMEM, st>>>(P);
+	}
+	return cudaGetLastError();
+}
+
+int kq_tile_evals(int variant) {
+	switch (variant) {
+	case 1: return KqCfg<16, 8, 4>::TILE;
+	case 2: return KqCfg<24, 4, 5>::TILE;
+	case 3: return KqCfg<20, 4, 6>::TILE;
+	default: return KqCfg<20, 8, 3>::TILE;
+	}
+}
+
+cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cudaStream_t st) {
+	const int tile = kq_tile_evals(variant);
+	P.tiles_per_cand = (uint32_t)((P.T + tile - 1) / tile);
+	P.total_tiles = (uint64_t)P.tiles_per_cand * P.C;
+	if (P.total_tiles == 0) return cudaSuccess;
+	int grid = sm_count;
+	if (const char *g = getenv("APO_K1_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }
+	if ((uint64_t)grid > P.total_tiles) grid = (int)P.total_tiles;
+	switch (variant) {
+	case 1: return launch_kq<16, 8, 4>(P, grid, recip, st);
+	case 2: return launch_kq<24, 4, 5>(P, grid, recip, st);
+	case 3: return launch_kq<20, 4, 6>(P, grid, recip, st);
+	default: return launch_kq<20, 8, 3>(P, grid, recip, st);
+	}
+}
+
+}  // namespace apo

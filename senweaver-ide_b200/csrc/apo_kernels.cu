@@ -36,37 +36,6 @@ struct K1Cfg {
 };
 
 // One Form-D evaluation: 9 fp32 (NaN = absent) -> fixed-point finalReward.
-// ws / tw, correctly rounded, without the generic division's special-case branch (which
-// would serialise the four evaluations a thread interleaves): y = RN(1/tw) comes from the
-// LUT, q = RN(ws*y), r = ws - tw*q (exact, one FMA), result = RN(q + r*y).  By Markstein's
-// theorem this is the correctly rounded quotient when y is the correctly rounded reciprocal,
-// the significand of tw is not all ones, and nothing underflows — tw is one of <= 511 sums of
-// validated weights (apo_set_weights: 0 or within [1e-100,1e100]) and |ws| is 0 or >= 2^-160
-// (fp32 inputs x weights).  Masks whose total weight has an all-ones significand (e.g. weights
-// that sum to 0.9999999999999999) are flagged by the host with a NEGATIVE reciprocal and take
-// the generic IEEE division instead.
-template <bool RECIP>
-__device__ __forceinline__ double div_fast(double ws, double2 t) {
-	const double y = fabs(t.y);
-	const double q = __dmul_rn(ws, y);
-	if (RECIP) return q;
-	const double r = __fma_rn(-t.x, q, ws);
-	return __fma_rn(r, y, q);
-}
-template <bool RECIP>
-__device__ __forceinline__ double div_lut(double ws, double2 t) {
-	if (!RECIP && t.y < 0.0) return __ddiv_rn(ws, t.x);
-	return div_fast<RECIP>(ws, t);
-}
-
-// The shared-memory LUT is indexed by a bit-rotated presence mask: dims 5..8 (the ones that
-// vary independently in real data; d0,d1 are always present and d2..d4 come together) land
-// in the low bits, so lanes with different masks mostly hit different banks.
-__host__ __device__ constexpr int lut_bit(int dim) { return (dim + 4) % APO_NDIM; }
-__device__ __forceinline__ uint32_t lut_index(uint32_t natural_mask) {
-	return ((natural_mask >> 5) | (natural_mask << 4)) & 511u;
-}
-
 // One Form-D evaluation, first half: 9 fp32 (NaN = absent) -> weighted sum in push order and
 // the LUT entry {total weight, reciprocal} of its presence mask (TCS:777-783).
 __device__ __forceinline__ void eval_ws(const float (&v)[APO_NDIM], const Weights &W, const double2 *lut,

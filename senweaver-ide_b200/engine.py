@@ -84,6 +84,7 @@ ABI_SYMBOLS = (
     "apo_abi_version", "apo_create", "apo_destroy", "apo_last_error", "apo_set_stream", "apo_set_weights",
     "apo_get_weights", "apo_reward_batch", "apo_reward_one", "apo_corpus_upload", "apo_corpus_generate",
     "apo_corpus_download", "apo_dims_upload", "apo_dims_generate", "apo_dims_download", "apo_dims_attach",
+    "apo_dims_compact", "apo_dims_generate_compact", "apo_dims_upload_compact", "apo_dims_layout",
     "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_rollouts16_upload",
     "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_score",
     "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records",
@@ -132,6 +133,10 @@ def load_library() -> C.CDLL:
     L.apo_dims_generate.argtypes = [vp, u64, u32, u32, u64, u64, u32]
     L.apo_dims_download.argtypes = [vp, vp, u32, u64, u64]
     L.apo_dims_attach.argtypes = [vp, u64, u32, u64, u64]
+    L.apo_dims_compact.argtypes = [vp]
+    L.apo_dims_generate_compact.argtypes = [vp, u64, u32, u32, u64, u64, u32]
+    L.apo_dims_upload_compact.argtypes = [vp, vp, u32, u64]
+    L.apo_dims_layout.argtypes = [vp]
     L.apo_rollouts_upload.argtypes = [vp, vp, u32, u64]
     L.apo_rollouts_generate.argtypes = [vp, u64, u32, u32, u64, u64, u32]
     L.apo_rollouts_download.argtypes = [vp, vp, u32, u64, u64]
@@ -248,6 +253,23 @@ class Engine:
         out = np.empty((n, NDIM), np.float32)
         self._ck(self._L.apo_dims_download(self._h, _p(out), c, first, n))
         return out
+
+    # Form Q: compact resident layout (12 B per evaluation), lossless for categorical dims
+    def dims_compact(self):
+        self._ck(self._L.apo_dims_compact(self._h))
+
+    def dims_generate_compact(self, seed: int, c0: int, Cn: int, t0: int, T: int, agent_permille: int = 300):
+        self._ck(self._L.apo_dims_generate_compact(self._h, seed, c0, Cn, t0, T, agent_permille))
+
+    def dims_upload_compact(self, dims: np.ndarray):
+        dims = np.ascontiguousarray(dims, np.float32)
+        Cn, T, nd = dims.shape
+        assert nd == NDIM
+        self._ck(self._L.apo_dims_upload_compact(self._h, _p(dims), Cn, T))
+
+    def dims_layout(self) -> int:
+        """0 nothing loaded, 1 Form D (fp32), 2 Form Q (compact)."""
+        return int(self._L.apo_dims_layout(self._h))
 
     def dims_attach(self, device_ptr: int, Cn: int, T: int, pitch_evals: int):
         self._ck(self._L.apo_dims_attach(self._h, device_ptr, Cn, T, pitch_evals))

@@ -1,0 +1,109 @@
+"""Form Q — the compact resident layout (12 B per evaluation) and its kernel K1q (-m gpu).
+Lossless: decoding returns the original fp32 bit patterns, and the integer partial sums equal
+those of the fp32 kernel and of the oracle with no tolerance."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def same_bits(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    nan = np.isnan(a)
+    return np.array_equal(nan, np.isnan(b)) and np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32))
+
+
+@pytest.mark.parametrize("C,T", [(4, 1000), (3, 1), (7, 5121), (16, 40_003), (2, 5120)])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_compact_matches_fp32_and_oracle(engine, orc, C, T, variant):
+    dims = orc.gen_dims(0x5EED0010 + C, 3, C, 100, T, 400, 8)
+    engine.dims_upload(dims)
+    ref = engine.score(C, min(C, 3))
+    rs, rc = engine.debug_partials(C)
+    assert engine.dims_layout() == 1
+    engine.dims_compact()
+    assert engine.dims_layout() == 2
+    for c in range(C):
+        assert same_bits(engine.dims_download(c, 0, T), dims[c])          # lossless
+    res = engine.score(C, min(C, 3), variant=variant)
+    assert engine.debug_partials(C) == (rs, rc) == orc.score_dims_fx(dims)
+    assert np.array_equal(res.scores, ref.scores) and np.array_equal(res.topk, ref.topk)
+
+
+def test_compact_generate_and_upload_variants(engine, orc):
+    C, T, seed = 9, 33_333, 0x5EED0011
+    dims = orc.gen_dims(seed, 0, C, 64, T, 300, 8)
+    exp = orc.score_dims_fx(dims)
+    engine.dims_generate_compact(seed, 0, C, 64, T, 300)
+    assert engine.dims_layout() == 2
+    engine.score(C, 2)
+    assert engine.debug_partials(C) == exp
+    assert same_bits(engine.dims_download(4, 10, 500), dims[4, 10:510])
+    engine.dims_upload_compact(dims)
+    engine.score(C, 2)
+    assert engine.debug_partials(C) == exp
+    # windows and chunked accumulation work on the compact layout too
+    engine.score(C, 1, first=1000, count=20_000)
+    assert engine.debug_partials(C) == orc.score_dims_fx(dims[:, 1000:21_000])
+    engine.score_begin(C + 2)
+    engine.score_accumulate(2)
+    r = engine.score_finish(C + 2, 3)
+    assert r.counts[0] == 0 and r.counts[1] == 0 and engine.debug_partials(C + 2)[0][2:] == exp[0]
+
+
+def test_compact_all_presence_masks_and_custom_weights(engine, orc):
+    rng = np.random.default_rng(17)
+    C, T = 5, 20_000
+    levels = np.array([-1.0, -0.8, -0.5, -0.3, -0.2, 0.0, -0.0, 0.3, 0.5, 0.8, 1.0], np.float32)
+    dims = levels[rng.integers(0, len(levels), (C, T, 9))]
+    dims[:, :, 2] = rng.uniform(-1, 1, (C, T)).astype(np.float32)        # d2 stays free-form fp32
+    dims[rng.random(dims.shape) < 0.3] = np.nan
+    dims[3] = np.nan
+    w = np.array([0.3, 0.1, 0.05, 0.05, 0.1, 0.1, 0.1, 0.1, 0.1])          # total weight with an all-ones significand
+    try:
+        for weights in (orc.weights(), w):
+            engine.set_weights(weights)
+            engine.dims_upload(dims)
+            engine.dims_compact()
+            r = engine.score(C, C)
+            assert engine.debug_partials(C) == orc.score_dims_fx(dims, w=weights)
+            assert np.array_equal(r.topk, orc.topk(orc.score_dims(dims, w=weights)[0], C))
+        # changing the weights after compaction rebuilds the product tables
+        engine.set_weights(orc.weights())
+        engine.score(C, 1)
+        assert engine.debug_partials(C) == orc.score_dims_fx(dims)
+    finally:
+        engine.set_weights(orc.weights())
+
+
+def test_non_categorical_data_keeps_form_d(engine, orc, apo):
+    rng = np.random.default_rng(1)
+    dims = rng.uniform(-1, 1, (3, 4000, 9)).astype(np.float32)           # > 255 distinct values per dimension
+    engine.dims_upload(dims)
+    with pytest.raises(apo.ApoError):
+        engine.dims_compact()
+    assert engine.dims_layout() == 1
+    engine.score(3, 1)
+    assert engine.debug_partials(3) == orc.score_dims_fx(dims)
+    with pytest.raises(apo.ApoError):
+        engine.dims_upload_compact(dims)
+    assert engine.dims_layout() == 0
+    # exactly 255 distinct values still fit, 256 do not
+    base = np.full((1, 512, 9), np.nan, np.float32)
+    base[0, :255, 0] = np.arange(255, dtype=np.float32) / 256
+    engine.dims_upload_compact(base)
+    assert engine.dims_layout() == 2
+    base[0, 255, 0] = 0.999
+    with pytest.raises(apo.ApoError):
+        engine.dims_upload_compact(base)
+
+
+def test_compact_full_size_config2(engine, orc):
+    C, T, seed = 64, 1_000_000, 0x5EED0002
+    engine.dims_generate(seed, 0, C, 0, T, 300)
+    ref = engine.score(C, 16)
+    exp = engine.debug_partials(C)
+    engine.dims_generate_compact(seed, 0, C, 0, T, 300)
+    res = engine.score(C, 16)
+    assert engine.debug_partials(C) == exp
+    assert np.array_equal(res.scores, ref.scores) and np.array_equal(res.topk, ref.topk)

@@ -39,6 +39,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3,4")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--layout", default="fp32", choices=["fp32", "compact"], help="resident layout for configs 2, 3, 5")
+    ap.add_argument("--variant", type=int, default=0)
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -85,12 +87,13 @@ def main():
             first, last = pkg.sharding.shard_range(T * world, world, rank) if cfg == 3 else (0, T)
             if cfg == 3:
                 T = last - first
-            eng.dims_generate(seed, 0, C, first, T, 300)
+            bpe = 36.0 if args.layout == "fp32" else 12.0
+            (eng.dims_generate if args.layout == "fp32" else eng.dims_generate_compact)(seed, 0, C, first, T, 300)
             eng.corpus_generate(seed, first, T, 300)
             for K in ((4, 16) if cfg == 2 else (64,)):
-                r, k1, tot = timed(lambda: eng.score(C, K, corpus=(cfg == 3)), args.reps)
-                gbs = 36.0 * C * T / (k1 * 1e-3) / 1e9
-                emit({"config": cfg, "C": C, "T_per_gpu": T, "n_gpus": world, "K": K, "k1_ms": k1, "step_ms": tot,
+                r, k1, tot = timed(lambda: eng.score(C, K, corpus=(cfg == 3), variant=args.variant), args.reps)
+                gbs = bpe * C * T / (k1 * 1e-3) / 1e9
+                emit({"config": cfg, "layout": args.layout, "bytes_per_eval": bpe, "variant": args.variant, "C": C, "T_per_gpu": T, "n_gpus": world, "K": K, "k1_ms": k1, "step_ms": tot,
                       "evals_per_s": C * T * world / (tot * 1e-3), "k1_GBps": gbs, "frac_of_measured_peak": gbs / PK,
                       "frac_of_8TBps": gbs / 8000.0, "topk_head": r.topk[:4].tolist()})
         elif cfg == 4:

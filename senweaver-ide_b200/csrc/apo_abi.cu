@@ -9,7 +9,9 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <new>
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/apo_b200.h"
@@ -216,7 +218,28 @@ int compact_finish(apo_engine *e, uint32_t C, uint64_t T, uint64_t pitch) {
 			e->q8.release(); e->qd2.release();
 			return fail(e, APO_E_STATE, "evaluations are not categorical: coded dimension %d has more than 255 distinct values; Form D is kept", j < 2 ? j : j + 1);
 		}
-	memcpy(e->qbook_host, host, sizeof e->qbook_host);
+	// hash-slot codes -> dense codes ordered by value (deterministic, bank-conflict-free table reads)
+	uint8_t remap[8 * 256];
+	uint32_t dense[8 * 256];
+	for (int j = 0; j < 8; j++) {
+		std::vector<std::pair<float, int>> used;
+		for (int s = 0; s < 255; s++) {
+			const uint32_t bits = host[256 * j + s];
+			if (bits != 0xFFFFFFFFu) { float f; memcpy(&f, &bits, 4); used.push_back({f, s}); }
+		}
+		std::sort(used.begin(), used.end(), [&](const std::pair<float, int> &a, const std::pair<float, int> &b) {
+			if (a.first != b.first) return a.first < b.first;
+			return host[256 * j + a.second] > host[256 * j + b.second];      // -0.0 (sign bit set) before +0.0
+		});
+		for (int c = 0; c < 256; c++) { remap[256 * j + c] = 255; dense[256 * j + c] = 0xFFFFFFFFu; }
+		for (size_t r = 0; r < used.size(); r++) { remap[256 * j + used[r].second] = (uint8_t)r; dense[256 * j + r] = host[256 * j + used[r].second]; }
+	}
+	CK(e->stage.reserve(1024));
+	CK(cudaMemcpyAsync(e->stage.p, remap, sizeof remap, cudaMemcpyHostToDevice, e->stream));
+	CK(apo::run_recode(e->q8.p, (uint64_t)C * pitch, (const uint8_t *)e->stage.p, e->stream));
+	CK(cudaMemcpyAsync(e->qbook.p, dense, sizeof dense, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	memcpy(e->qbook_host, dense, sizeof e->qbook_host);
 	int rc = upload_ptab(e);
 	if (rc) return rc;
 	e->compact = true; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch; e->dims_ptr = nullptr;

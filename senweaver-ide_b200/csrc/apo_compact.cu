@@ -85,6 +85,31 @@ cudaError_t run_transcode(const float *dims, uint64_t pitch_in, uint32_t C, uint
 	return cudaGetLastError();
 }
 
+// Hash-slot codes -> dense codes (rank of the value inside its dimension), in place.  Dense codes
+// keep the product-table entries of a dimension in adjacent shared-memory banks, so a warp whose
+// lanes carry different codes reads them without bank conflicts (<= 16 values per dimension).
+__global__ void __launch_bounds__(256)
+k_recode(unsigned long long *q8, uint64_t n, const uint8_t *remap /* [8][256] */) {
+	__shared__ uint8_t s_map[8 * 256];
+	for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) s_map[i] = remap[i];
+	__syncthreads();
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		const unsigned long long q = q8[i];
+		unsigned long long o = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) o |= (unsigned long long)s_map[256 * j + ((uint32_t)(q >> (8 * j)) & 255u)] << (8 * j);
+		q8[i] = o;
+	}
+}
+
+cudaError_t run_recode(unsigned long long *q8, uint64_t n, const uint8_t *remap, cudaStream_t st) {
+	if (n == 0) return cudaSuccess;
+	uint64_t g = (n + 255) / 256;
+	if (g > 148ull * 32) g = 148ull * 32;
+	k_recode<<<(unsigned)g, 256, 0, st>>>(q8, n, remap);
+	return cudaGetLastError();
+}
+
 // Form Q -> Form D (tests, apo_dims_download)
 __global__ void __launch_bounds__(256)
 k_decode(const unsigned long long *q8, const float *d2, uint64_t n, const uint32_t *codebook, float *out) {

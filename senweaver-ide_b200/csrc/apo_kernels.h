@@ -68,6 +68,7 @@ int kq_tile_evals(int variant);
 cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cudaStream_t st);
 cudaError_t run_transcode(const float *dims, uint64_t pitch_in, uint32_t C, uint64_t T, unsigned long long *q8, float *d2,
                           uint64_t pitch_out, uint32_t *codebook, uint32_t *overflow, cudaStream_t st);
+cudaError_t run_recode(unsigned long long *q8, uint64_t n, const uint8_t *remap, cudaStream_t st);
 cudaError_t run_decode(const unsigned long long *q8, const float *d2, uint64_t n, const uint32_t *codebook, float *out, cudaStream_t st);
 
 int k1_tile_evals(int row, int variant);

@@ -145,7 +145,7 @@ int apo_dims_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uin
                       uint32_t agent_permille);
 int apo_dims_download(apo_engine *e, float *out, uint32_t c, uint64_t first, uint64_t n);
 /* Form Q — compact resident layout (csrc/apo_compact.cu): 8 one-byte codebook indices + the
- * fp32 tool_success_rate per evaluation (12 B instead of 36 B), lossless.  Available when every
+ * fp32 tool_success_rate + a 2-byte presence index per evaluation (14 B instead of 36 B), lossless.  Available when every
  * dimension except d2 takes <= 255 distinct values (true for dims produced by TCS:668-763).
  * apo_dims_compact transcodes the loaded Form D in place (the fp32 copy is released);
  * the *_compact generate/upload variants never materialise the full fp32 tensor.  When the data
@@ -188,7 +188,7 @@ typedef struct apo_score_opts {
 	uint32_t source;     /* APO_SRC_* */
 	uint32_t flags;      /* APO_SCORE_* */
 	uint32_t variant;    /* kernel variant, 0 = default (tuning / A-B only) */
-	uint64_t first;      /* window [first, first+count) of the record axis, first % 4 == 0; */
+	uint64_t first;      /* window [first, first+count) of the record axis, first % 4 == 0 (% 8 for Form Q); */
 	uint64_t count;      /* count == 0 -> all records */
 } apo_score_opts;
 /* scores[C] (-inf when a candidate has no non-null evaluation), counts[C], topk[K];

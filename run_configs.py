@@ -87,7 +87,7 @@ def main():
             first, last = pkg.sharding.shard_range(T * world, world, rank) if cfg == 3 else (0, T)
             if cfg == 3:
                 T = last - first
-            bpe = 36.0 if args.layout == "fp32" else 12.0
+            bpe = 36.0 if args.layout == "fp32" else 14.0
             (eng.dims_generate if args.layout == "fp32" else eng.dims_generate_compact)(seed, 0, C, first, T, 300)
             eng.corpus_generate(seed, first, T, 300)
             for K in ((4, 16) if cfg == 2 else (64,)):

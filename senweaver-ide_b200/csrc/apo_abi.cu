@@ -88,7 +88,7 @@ struct apo_engine {
 	DevBuf<apo_record> corpus; uint64_t corpus_T = 0, corpus_base = 0;
 	DevBuf<float> dims; const float *dims_ptr = nullptr; uint32_t dims_C = 0; uint64_t dims_T = 0, dims_pitch = 0;
 	// Form Q (compact) copy of the evaluations: replaces dims/dims_ptr when `compact` is set
-	DevBuf<unsigned long long> q8; DevBuf<float> qd2; DevBuf<uint32_t> qbook;   // qbook: [8][256] codebook + [8] overflow flags
+	DevBuf<unsigned long long> q8; DevBuf<float> qd2; DevBuf<unsigned short> qli; DevBuf<uint32_t> qbook;   // qbook: [8][256] codebook + [8] overflow flags
 	DevBuf<double> d_ptab; DevBuf<float> stage;
 	uint32_t qbook_host[8 * 256]; bool compact = false;
 	DevBuf<uint8_t> roll; uint32_t roll_C = 0, roll_row = 32; uint64_t roll_T = 0, roll_pitch = 0;   // Form R (32 B) or R16 (16 B) rows
@@ -199,6 +199,7 @@ int upload_ptab(apo_engine *e) {
 int compact_begin(apo_engine *e, uint32_t C, uint64_t pitch) {
 	CK(e->q8.reserve((uint64_t)(C ? C : 1) * pitch));
 	CK(e->qd2.reserve((uint64_t)(C ? C : 1) * pitch));
+	CK(e->qli.reserve((uint64_t)(C ? C : 1) * pitch));
 	CK(e->qbook.reserve(8 * 256 + 8));
 	CK(cudaMemsetAsync(e->qbook.p, 0xFF, 8 * 256 * 4, e->stream));
 	CK(cudaMemsetAsync(e->qbook.p + 8 * 256, 0, 8 * 4, e->stream));
@@ -215,7 +216,7 @@ int compact_finish(apo_engine *e, uint32_t C, uint64_t T, uint64_t pitch) {
 	CK(cudaStreamSynchronize(e->stream));
 	for (int j = 0; j < 8; j++)
 		if (host[8 * 256 + j]) {
-			e->q8.release(); e->qd2.release();
+			e->q8.release(); e->qd2.release(); e->qli.release();
 			return fail(e, APO_E_STATE, "evaluations are not categorical: coded dimension %d has more than 255 distinct values; Form D is kept", j < 2 ? j : j + 1);
 		}
 	// hash-slot codes -> dense codes ordered by value (deterministic, bank-conflict-free table reads)
@@ -236,7 +237,7 @@ int compact_finish(apo_engine *e, uint32_t C, uint64_t T, uint64_t pitch) {
 	}
 	CK(e->stage.reserve(1024));
 	CK(cudaMemcpyAsync(e->stage.p, remap, sizeof remap, cudaMemcpyHostToDevice, e->stream));
-	CK(apo::run_recode(e->q8.p, (uint64_t)C * pitch, (const uint8_t *)e->stage.p, e->stream));
+	CK(apo::run_recode(e->q8.p, e->qd2.p, e->qli.p, (uint64_t)C * pitch, (const uint8_t *)e->stage.p, e->stream));
 	CK(cudaMemcpyAsync(e->qbook.p, dense, sizeof dense, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	memcpy(e->qbook_host, dense, sizeof e->qbook_host);
@@ -303,8 +304,9 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 	const uint32_t C = raw ? e->roll_C : e->dims_C;
 	if (!raw && e->compact) {
 		if (!count) return APO_OK;
+		if (first % 8) return fail(e, APO_E_ARG, "window start must be a multiple of 8 for the compact layout");
 		apo::KqParams Q{};
-		Q.q8 = e->q8.p + first; Q.d2 = e->qd2.p + first; Q.pitch_evals = e->dims_pitch; Q.C = C; Q.T = count;
+		Q.q8 = e->q8.p + first; Q.d2 = e->qd2.p + first; Q.li = e->qli.p + first; Q.pitch_evals = e->dims_pitch; Q.C = C; Q.T = count;
 		Q.acc = e->acc.p + (uint64_t)ACC_PER_CAND * cand_offset; Q.lut = e->d_lut.p; Q.ptab = e->d_ptab.p; Q.w2 = e->W.w[2];
 		if (e->k1_used + 2 > e->k1_ev.size()) {
 			for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
@@ -438,7 +440,7 @@ extern "C" void apo_destroy(apo_engine *e) {
 	cudaSetDevice(e->device);
 	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	if (e->own_stream) cudaStreamSynchronize(e->own_stream);
-	e->q8.release(); e->qd2.release(); e->qbook.release(); e->d_ptab.release(); e->stage.release();
+	e->q8.release(); e->qd2.release(); e->qli.release(); e->qbook.release(); e->d_ptab.release(); e->stage.release();
 	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->misc.release();
 	e->result.release(); e->keys.release(); e->sel_key.release(); e->sel_idx.release();
 	e->win[0].release(); e->win[1].release(); e->batch_in.release(); e->batch_out.release(); e->batch_mask.release();
@@ -567,7 +569,7 @@ extern "C" int apo_dims_download(apo_engine *e, float *out, uint32_t c, uint64_t
 	if (e->compact) {
 		CK(e->stage.reserve((n ? n : 1) * APO_NDIM));
 		const uint64_t off = (uint64_t)c * e->dims_pitch + first;
-		CK(apo::run_decode(e->q8.p + off, e->qd2.p + off, n, e->qbook.p, e->stage.p, e->stream));
+		CK(apo::run_decode(e->q8.p + off, e->qd2.p + off, e->qli.p + off, n, e->qbook.p, e->stage.p, e->stream));
 		CK(cudaMemcpyAsync(out, e->stage.p, n * APO_NDIM * 4, cudaMemcpyDeviceToHost, e->stream));
 		CK(cudaStreamSynchronize(e->stream));
 		return APO_OK;

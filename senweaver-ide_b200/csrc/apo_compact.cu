@@ -6,8 +6,9 @@
 // token_efficiency, conversation_efficiency); only tool_success_rate (d2 = succ/total*2-1,
 // TCS:698) is a ratio.  Form Q therefore keeps, per evaluation,
 //     q8  : 8 one-byte codes (dims 0,1,3,4,5,6,7,8; 255 = dimension absent)       8 B
-//     d2  : the fp32 value of dim 2 (NaN = absent)                                 4 B
-// = 12 B instead of 36 B, plus one codebook of <= 255 fp32 bit patterns per coded dimension.
+//     d2  : the fp32 value of dim 2 (0.0 when absent)                              4 B
+//     li  : the presence mask of the evaluation as a (bank-rotated) LUT index      2 B
+// = 14 B instead of 36 B, plus one codebook of <= 255 fp32 bit patterns per coded dimension.
 // The transcoder (k_transcode) builds the codebooks with a find-or-insert hash and refuses
 // data with more than 255 distinct values in a coded dimension — the engine then simply keeps
 // Form D.  It is lossless: decoding returns the original fp32 bit patterns (absent = NaN).
@@ -89,30 +90,40 @@ cudaError_t run_transcode(const float *dims, uint64_t pitch_in, uint32_t C, uint
 // keep the product-table entries of a dimension in adjacent shared-memory banks, so a warp whose
 // lanes carry different codes reads them without bank conflicts (<= 16 values per dimension).
 __global__ void __launch_bounds__(256)
-k_recode(unsigned long long *q8, uint64_t n, const uint8_t *remap /* [8][256] */) {
+k_recode(unsigned long long *q8, float *d2, unsigned short *li, uint64_t n, const uint8_t *remap /* [8][256] */) {
 	__shared__ uint8_t s_map[8 * 256];
 	for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) s_map[i] = remap[i];
 	__syncthreads();
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
 		const unsigned long long q = q8[i];
 		unsigned long long o = 0;
+		uint32_t mask = 0;                                   // natural presence mask, bit = dimension
 #pragma unroll
-		for (int j = 0; j < 8; j++) o |= (unsigned long long)s_map[256 * j + ((uint32_t)(q >> (8 * j)) & 255u)] << (8 * j);
+		for (int j = 0; j < 8; j++) {
+			const uint32_t c = s_map[256 * j + ((uint32_t)(q >> (8 * j)) & 255u)];
+			o |= (unsigned long long)c << (8 * j);
+			mask |= (c != 255u ? 1u : 0u) << (j < 2 ? j : j + 1);
+		}
+		const float f2 = d2[i];
+		const bool p2 = (f2 == f2);
+		mask |= (p2 ? 1u : 0u) << 2;
 		q8[i] = o;
+		d2[i] = p2 ? f2 : 0.0f;                               // +0.0 * w leaves the weighted sum unchanged
+		li[i] = (unsigned short)lut_index(mask);
 	}
 }
 
-cudaError_t run_recode(unsigned long long *q8, uint64_t n, const uint8_t *remap, cudaStream_t st) {
+cudaError_t run_recode(unsigned long long *q8, float *d2, unsigned short *li, uint64_t n, const uint8_t *remap, cudaStream_t st) {
 	if (n == 0) return cudaSuccess;
 	uint64_t g = (n + 255) / 256;
 	if (g > 148ull * 32) g = 148ull * 32;
-	k_recode<<<(unsigned)g, 256, 0, st>>>(q8, n, remap);
+	k_recode<<<(unsigned)g, 256, 0, st>>>(q8, d2, li, n, remap);
 	return cudaGetLastError();
 }
 
 // Form Q -> Form D (tests, apo_dims_download)
 __global__ void __launch_bounds__(256)
-k_decode(const unsigned long long *q8, const float *d2, uint64_t n, const uint32_t *codebook, float *out) {
+k_decode(const unsigned long long *q8, const float *d2, const unsigned short *li, uint64_t n, const uint32_t *codebook, float *out) {
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const unsigned long long q = q8[i];
@@ -123,12 +134,12 @@ k_decode(const unsigned long long *q8, const float *d2, uint64_t n, const uint32
 		const uint32_t code = (uint32_t)(q >> (8 * j)) & 255u;
 		row[dim] = code == 255u ? __int_as_float(0x7fc00000) : __uint_as_float(codebook[256 * j + code]);
 	}
-	row[2] = d2[i];
+	row[2] = ((li[i] >> 6) & 1u) ? d2[i] : __int_as_float(0x7fc00000);     // rotated index: dim 2 lives in bit 6
 }
 
-cudaError_t run_decode(const unsigned long long *q8, const float *d2, uint64_t n, const uint32_t *codebook, float *out, cudaStream_t st) {
+cudaError_t run_decode(const unsigned long long *q8, const float *d2, const unsigned short *li, uint64_t n, const uint32_t *codebook, float *out, cudaStream_t st) {
 	if (n == 0) return cudaSuccess;
-	k_decode<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q8, d2, n, codebook, out);
+	k_decode<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(q8, d2, li, n, codebook, out);
 	return cudaGetLastError();
 }
 
@@ -139,8 +150,8 @@ template <int CW, int EPT, int STAGES>
 struct KqCfg {
 	static constexpr int NCONS = CW * 32;
 	static constexpr int TILE = NCONS * EPT;
-	static constexpr int Q8_BYTES = TILE * 8, D2_BYTES = TILE * 4;
-	static constexpr int STAGE_BYTES = Q8_BYTES + D2_BYTES;
+	static constexpr int Q8_BYTES = TILE * 8, D2_BYTES = TILE * 4, LI_BYTES = TILE * 2;
+	static constexpr int STAGE_BYTES = Q8_BYTES + D2_BYTES + LI_BYTES;
 	static constexpr int LUT_OFF = STAGES * STAGE_BYTES;          // double2[512]
 	static constexpr int PTAB_OFF = LUT_OFF + 512 * 16;           // double[8][256]
 	static constexpr int BAR_OFF = PTAB_OFF + 8 * 256 * 8;
@@ -150,26 +161,20 @@ struct KqCfg {
 };
 
 // One Form-Q evaluation, first half: weighted sum in push order (TCS:777-783) + LUT entry.
-__device__ __forceinline__ void evalq_ws(unsigned long long q, float d2f, const double *ptab, double w2, const double2 *lut,
-                                         double &ws_out, double2 &t_out, uint32_t &valid) {
+__device__ __forceinline__ void evalq_ws(unsigned long long q, float d2f, uint32_t idx, const double *ptab, double w2,
+                                         const double2 *lut, double &ws_out, double2 &t_out, uint32_t &valid) {
 	const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
 	double ws = ptab[0 * 256 + (lo & 255u)];                          // table 0 holds fl(0 + d0*w0)
 	ws = __dadd_rn(ws, ptab[1 * 256 + ((lo >> 8) & 255u)]);
-	const bool p2 = (d2f == d2f);
-	ws = __dadd_rn(ws, __dmul_rn((double)(p2 ? d2f : 0.0f), w2));
+	ws = __dadd_rn(ws, __dmul_rn((double)d2f, w2));                   // d2 is stored as +0.0 when absent
 	ws = __dadd_rn(ws, ptab[2 * 256 + ((lo >> 16) & 255u)]);
 	ws = __dadd_rn(ws, ptab[3 * 256 + (lo >> 24)]);
 	ws = __dadd_rn(ws, ptab[4 * 256 + (hi & 255u)]);
 	ws = __dadd_rn(ws, ptab[5 * 256 + ((hi >> 8) & 255u)]);
 	ws = __dadd_rn(ws, ptab[6 * 256 + ((hi >> 16) & 255u)]);
 	ws = __dadd_rn(ws, ptab[7 * 256 + (hi >> 24)]);
-	// presence bits: byte != 255, gathered four at a time (bits 0,8,16,24 -> a nibble)
-	const uint32_t nlo = ((__vcmpne4(lo, 0xFFFFFFFFu) & 0x01010101u) * 0x01020408u) >> 24;   // dims 0,1,3,4 -> bits 0..3
-	const uint32_t nhi = ((__vcmpne4(hi, 0xFFFFFFFFu) & 0x01010101u) * 0x01020408u) >> 24;   // dims 5,6,7,8 -> bits 0..3
-	// rotated LUT index (apo_device.cuh lut_bit): dims 5..8 -> bits 0..3, dims 0,1 -> 4,5, dim 2 -> 6, dims 3,4 -> 7,8
-	const uint32_t idx = (nhi & 15u) | ((nlo & 3u) << 4) | ((p2 ? 1u : 0u) << 6) | (((nlo >> 2) & 3u) << 7);
 	ws_out = ws;
-	t_out = lut[idx];
+	t_out = lut[idx];                                                 // presence mask -> LUT index was fixed by the transcoder
 	valid = t_out.x > 0.0 ? 1u : 0u;
 }
 
@@ -210,12 +215,13 @@ k_reward9q(const KqParams P) {
 				const uint64_t e0 = j * Cfg::TILE;
 				const uint64_t rem = P.T - e0;
 				const uint32_t n = rem < (uint64_t)Cfg::TILE ? (uint32_t)rem : (uint32_t)Cfg::TILE;
-				const uint32_t n4 = (n + 3u) & ~3u;                         // 32 B / 16 B multiples for the two bulk copies
+				const uint32_t n8 = (n + 7u) & ~7u;                         // 64 / 32 / 16 B multiples for the three bulk copies
 				meta[s].cand = (int32_t)c; meta[s].n = (int32_t)n;
-				mbar_expect_tx(&full[s], n4 * 12u);
+				mbar_expect_tx(&full[s], n8 * 14u);
 				uint8_t *st = smem + s * Cfg::STAGE_BYTES;
-				bulk_g2s(st, P.q8 + (uint64_t)c * P.pitch_evals + e0, n4 * 8u, &full[s], pol);
-				bulk_g2s(st + Cfg::Q8_BYTES, P.d2 + (uint64_t)c * P.pitch_evals + e0, n4 * 4u, &full[s], pol);
+				bulk_g2s(st, P.q8 + (uint64_t)c * P.pitch_evals + e0, n8 * 8u, &full[s], pol);
+				bulk_g2s(st + Cfg::Q8_BYTES, P.d2 + (uint64_t)c * P.pitch_evals + e0, n8 * 4u, &full[s], pol);
+				bulk_g2s(st + Cfg::Q8_BYTES + Cfg::D2_BYTES, P.li + (uint64_t)c * P.pitch_evals + e0, n8 * 2u, &full[s], pol);
 			}
 		}
 		return;
@@ -242,6 +248,7 @@ k_reward9q(const KqParams P) {
 		if (c != cur) { if (cur >= 0) flush(cur); cur = c; }
 		const unsigned long long *sq = reinterpret_cast<const unsigned long long *>(smem + s * Cfg::STAGE_BYTES);
 		const float *sd = reinterpret_cast<const float *>(smem + s * Cfg::STAGE_BYTES + Cfg::Q8_BYTES);
+		const unsigned short *sl = reinterpret_cast<const unsigned short *>(smem + s * Cfg::STAGE_BYTES + Cfg::Q8_BYTES + Cfg::D2_BYTES);
 		if (n == Cfg::TILE) {
 #pragma unroll
 			for (int g = 0; g < EPT / 4; g++) {
@@ -250,7 +257,7 @@ k_reward9q(const KqParams P) {
 				for (int k = 0; k < 4; k++) {
 					const int e = (4 * g + k) * Cfg::NCONS + tid;              // 8 B / 4 B lane stride: conflict-free
 					uint32_t ok;
-					evalq_ws(sq[e], sd[e], s_ptab, w2, s_lut, ws4[k], t4[k], ok);
+					evalq_ws(sq[e], sd[e], sl[e], s_ptab, w2, s_lut, ws4[k], t4[k], ok);
 					cnt += ok;
 				}
 				const bool generic = !RECIP && ((__double2hiint(t4[0].y) | __double2hiint(t4[1].y) |
@@ -270,7 +277,7 @@ k_reward9q(const KqParams P) {
 				const int e = k * Cfg::NCONS + tid;
 				if (e < n) {
 					double ws; double2 t; uint32_t ok;
-					evalq_ws(sq[e], sd[e], s_ptab, w2, s_lut, ws, t, ok);
+					evalq_ws(sq[e], sd[e], sl[e], s_ptab, w2, s_lut, ws, t, ok);
 					acc.add(to_fx(div_lut<RECIP>(ws, t)));
 					cnt += ok;
 				}
@@ -300,10 +307,10 @@ static cudaError_t launch_kq(const KqParams &P, int grid, bool recip, cudaStream
 
 int kq_tile_evals(int variant) {
 	switch (variant) {
-	case 1: return KqCfg<16, 8, 4>::TILE;
-	case 2: return KqCfg<24, 4, 5>::TILE;
-	case 3: return KqCfg<20, 4, 6>::TILE;
-	default: return KqCfg<20, 8, 3>::TILE;
+	case 1: return KqCfg<16, 8, 3>::TILE;
+	case 2: return KqCfg<24, 4, 4>::TILE;
+	case 3: return KqCfg<20, 4, 5>::TILE;
+	default: return KqCfg<20, 8, 2>::TILE;
 	}
 }
 
@@ -316,10 +323,10 @@ cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cuda
 	if (const char *g = getenv("APO_K1_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }
 	if ((uint64_t)grid > P.total_tiles) grid = (int)P.total_tiles;
 	switch (variant) {
-	case 1: return launch_kq<16, 8, 4>(P, grid, recip, st);
-	case 2: return launch_kq<24, 4, 5>(P, grid, recip, st);
-	case 3: return launch_kq<20, 4, 6>(P, grid, recip, st);
-	default: return launch_kq<20, 8, 3>(P, grid, recip, st);
+	case 1: return launch_kq<16, 8, 3>(P, grid, recip, st);
+	case 2: return launch_kq<24, 4, 4>(P, grid, recip, st);
+	case 3: return launch_kq<20, 4, 5>(P, grid, recip, st);
+	default: return launch_kq<20, 8, 2>(P, grid, recip, st);
 	}
 }
 

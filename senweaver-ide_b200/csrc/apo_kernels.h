@@ -53,7 +53,8 @@ struct K2Params {
 // Form Q (apo_compact.cu): 8 one-byte codes + fp32 d2 per evaluation
 struct KqParams {
 	const unsigned long long *q8;   // [C][pitch] codes, window base of candidate 0
-	const float *d2;                // [C][pitch]
+	const float *d2;                // [C][pitch]  (0.0 when absent)
+	const unsigned short *li;       // [C][pitch]  rotated presence-mask index into the LUT
 	uint64_t pitch_evals;
 	uint32_t C;
 	uint32_t tiles_per_cand;
@@ -68,8 +69,8 @@ int kq_tile_evals(int variant);
 cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cudaStream_t st);
 cudaError_t run_transcode(const float *dims, uint64_t pitch_in, uint32_t C, uint64_t T, unsigned long long *q8, float *d2,
                           uint64_t pitch_out, uint32_t *codebook, uint32_t *overflow, cudaStream_t st);
-cudaError_t run_recode(unsigned long long *q8, uint64_t n, const uint8_t *remap, cudaStream_t st);
-cudaError_t run_decode(const unsigned long long *q8, const float *d2, uint64_t n, const uint32_t *codebook, float *out, cudaStream_t st);
+cudaError_t run_recode(unsigned long long *q8, float *d2, unsigned short *li, uint64_t n, const uint8_t *remap, cudaStream_t st);
+cudaError_t run_decode(const unsigned long long *q8, const float *d2, const unsigned short *li, uint64_t n, const uint32_t *codebook, float *out, cudaStream_t st);
 
 int k1_tile_evals(int row, int variant);
 cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_count, cudaStream_t st);

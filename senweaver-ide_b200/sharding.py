@@ -19,8 +19,9 @@ def acc_words(C: int, nranks: int) -> int:
     return ACC_PER_CAND * C + CORP_FIXED + 18 * nranks
 
 
-def shard_range(T: int, nranks: int, rank: int, align: int = 4) -> tuple[int, int]:
-    """[first, last) of rank's contiguous shard; interior boundaries are multiples of `align`."""
+def shard_range(T: int, nranks: int, rank: int, align: int = 8) -> tuple[int, int]:
+    """[first, last) of rank's contiguous shard; interior boundaries are multiples of `align`
+    (8 = the window granularity of the compact layout, a multiple of the 4 the fp32 layouts need)."""
     assert 0 <= rank < nranks
     def cut(r):
         if r >= nranks:

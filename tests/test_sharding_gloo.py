@@ -93,7 +93,7 @@ def test_shard_ranges_cover_and_align():
             cuts = [sh.shard_range(Tn, world, r) for r in range(world)]
             assert cuts[0][0] == 0 and cuts[-1][1] == Tn
             for (a, b), (c, d) in zip(cuts, cuts[1:]):
-                assert b == c and b % 4 == 0
+                assert b == c and b % 8 == 0
             assert all(a <= b for a, b in cuts)
 
 

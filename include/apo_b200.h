@@ -184,7 +184,7 @@ int apo_record_unpack16(const apo_record16 *in, uint64_t n, apo_record *out);
 #define APO_SCORE_CORPUS  0x1u   /* also run the 6-pattern scan over the corpus */
 #define APO_SCORE_RECIP   0x2u   /* finalReward = ws * (1/tw) from a LUT instead of ws / tw (<= 1 ulp apart) */
 typedef struct apo_score_opts {
-	uint32_t K;          /* beam width (top-K), 0..C */
+	uint32_t K;          /* beam width (top-K), 0..min(C, 16384) */
 	uint32_t source;     /* APO_SRC_* */
 	uint32_t flags;      /* APO_SCORE_* */
 	uint32_t variant;    /* kernel variant, 0 = default (tuning / A-B only) */

@@ -58,6 +58,7 @@ bool nccl_load(std::string &err) {
 	return true;
 }
 constexpr int kNcclInt64 = 4, kNcclSum = 0;
+constexpr uint32_t kMaxK = 16384;      // the K winners are ordered by counting (O(K^2)); beam widths are tiny (APO:288: 4)
 
 template <class T>
 struct DevBuf {
@@ -391,6 +392,7 @@ int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *sco
 int check_opts(apo_engine *e, const apo_score_opts *o, uint32_t C, uint64_t T, uint64_t *first, uint64_t *count) {
 	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
 	if (o->K > C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, C);
+	if (o->K > kMaxK) return fail(e, APO_E_ARG, "K=%u exceeds the supported beam width %u", o->K, kMaxK);
 	if (o->first % 4) return fail(e, APO_E_ARG, "window start must be a multiple of 4");
 	if (o->first > T || (o->count && o->first + o->count > T)) return fail(e, APO_E_ARG, "window outside [0,%llu)", (unsigned long long)T);
 	*first = o->first;
@@ -757,6 +759,7 @@ extern "C" int apo_score_finish(apo_engine *e, const apo_score_opts *o, double *
 	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
 	if (!e->scoring) return fail(e, APO_E_STATE, "apo_score_begin has not been called");
 	if (o->K > e->score_C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, e->score_C);
+	if (o->K > kMaxK) return fail(e, APO_E_ARG, "K=%u exceeds the supported beam width %u", o->K, kMaxK);
 	CK(cudaSetDevice(e->device));
 	return finish_score(e, o, e->score_C, scores, counts, topk, report);
 }
@@ -783,6 +786,7 @@ int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows,
 	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
 	if (!rows || C == 0) return fail(e, APO_E_ARG, "input is NULL or C == 0");
 	if (o->K > C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, C);
+	if (o->K > kMaxK) return fail(e, APO_E_ARG, "K=%u exceeds the supported beam width %u", o->K, kMaxK);
 	if (o->first || o->count) return fail(e, APO_E_ARG, "windows are not supported by the host-streaming calls");
 	CK(cudaSetDevice(e->device));
 	int rc;

@@ -1,0 +1,58 @@
+"""Small end-to-end exercise of every kernel, meant to run under compute-sanitizer:
+
+    compute-sanitizer --tool memcheck  python tests/sanitize_smoke.py
+    compute-sanitizer --tool racecheck python tests/sanitize_smoke.py
+    compute-sanitizer --tool synccheck python tests/sanitize_smoke.py
+
+(also a plain script: prints OK when every result matches the oracle)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle as orc  # noqa: E402
+
+pkg = importlib.import_module("senweaver-ide_b200")
+e = pkg.Engine(0)
+C, T, seed = 5, 7001, 0x5EED00AA
+dims = orc.gen_dims(seed, 0, C, 0, T, 400, 4)
+recs = orc.gen_records(seed, orc.STREAM_CORPUS, 0, 1, 0, T, 400, 4).reshape(-1)
+roll = orc.gen_records(seed, orc.STREAM_ROLLOUT, 0, C, 0, T, 400, 4)
+exp = orc.score_dims_fx(dims)
+e.dims_upload(dims)
+e.corpus_upload(recs)
+for v in range(5):
+    r = e.score(C, 3, corpus=True, variant=v)
+    assert e.debug_partials(C) == exp
+ref = orc.report(recs)
+assert [r.report.pat[p].count for p in range(6)] == [ref.pat[p].count for p in range(6)]
+e.score(C, 2, first=1000, count=3001)
+assert e.debug_partials(C) == orc.score_dims_fx(dims[:, 1000:4001])
+e.dims_compact()
+for v in range(4):
+    e.score(C, 3, variant=v)
+    assert e.debug_partials(C) == exp
+assert np.array_equal(np.nan_to_num(e.dims_download(2, 0, T), nan=7), np.nan_to_num(dims[2], nan=7))
+e.dims_generate_compact(seed, 0, C, 0, T, 400)
+e.score(C, 1)
+assert e.debug_partials(C) == exp
+e.rollouts_upload(roll)
+e.score(C, 2, source=1)
+assert e.debug_partials(C) == orc.score_records_fx(roll)
+e.rollouts16_upload(pkg.pack16(roll))
+e.score(C, 2, source=1)
+assert e.debug_partials(C) == orc.score_records_fx(roll)
+e.score_host(dims, 2)
+assert e.debug_partials(C) == exp
+e.score_host_records(pkg.pack16(roll), 2)
+assert e.debug_partials(C) == orc.score_records_fx(roll)
+d, m, f = e.reward_batch(recs[:500])
+e.dims_generate(seed, 0, 2, 0, 300, 300)
+e.rollouts_generate(seed, 0, 2, 0, 300, 300)
+e.rollouts16_generate(seed, 0, 2, 0, 300, 300)
+e.corpus_generate(seed, 0, 300, 300)
+e.close()
+print("OK")

@@ -173,15 +173,20 @@ constexpr int CAT_D7 = 34;    // {1,0.5,0,-0.5}*w7                              
 constexpr int CAT_D8 = 39;    // {1,0.3,-0.3,-0.8}*w8                                      (5)
 constexpr int CAT_WORDS = 64;
 
+struct CatIdx { uint32_t i01, i3, i4, i5, i6, i7, i8; double d2; };   // effective slots (last slot of a group = absent)
+
 // TCS:668-783 for one record through the product table: weighted sum in push order + mask.
-__device__ __forceinline__ uint32_t record_ws_table(const apo_record &r, double w2, const double *cat, double &ws_out) {
+template <bool WANT_IDX>
+__device__ __forceinline__ uint32_t record_ws_table_t(const apo_record &r, double w2, const double *cat, double &ws_out, CatIdx &ix) {
 	const bool agent = r.mode == 2;
 	const uint32_t err = (r.flags & APO_F_ERRORS) ? 1u : 0u, ended = (r.flags & APO_F_ENDED) ? 1u : 0u;
-	double ws = cat[CAT_D01 + (r.feedback < 3 ? r.feedback : 0u) + 3u * err + 6u * ended];
+	const uint32_t i01 = (r.feedback < 3 ? r.feedback : 0u) + 3u * err + 6u * ended;
+	double ws = cat[CAT_D01 + i01];
 	const bool tool = r.toolCalls > 0;
 	const double total = (double)(tool ? r.toolCalls : 1u);
 	const double rate = div_small_int((double)r.toolSucc, total);
-	ws = __dadd_rn(ws, keep_if(tool, __dmul_rn(__dadd_rn(__dmul_rn(rate, 2.0), -1.0), w2)));
+	const double d2 = keep_if(tool, __dadd_rn(__dmul_rn(rate, 2.0), -1.0));
+	ws = __dadd_rn(ws, __dmul_rn(d2, w2));
 	const uint32_t sev = agent ? 5u : 3u, mod = agent ? 3u : 2u, mnr = agent ? 2u : 1u;
 	const uint32_t i3 = (r.toolFail >= mnr) + (r.toolFail >= mod) + (r.toolFail >= sev);
 	ws = __dadd_rn(ws, cat[CAT_D3 + (tool ? i3 : 4u)]);
@@ -206,7 +211,15 @@ __device__ __forceinline__ uint32_t record_ws_table(const apo_record &r, double 
 	const uint32_t i8 = (turns > thr8) + (turns > thr8 * 2) + (turns > thr8 * 3);
 	ws = __dadd_rn(ws, cat[CAT_D8 + (conv ? i8 : 4u)]);
 	ws_out = ws;
+	if (WANT_IDX) {
+		ix.i01 = i01; ix.i3 = tool ? i3 : 4u; ix.i4 = tool ? i4 : 4u; ix.i5 = hasdur ? i5 : 4u;
+		ix.i6 = llm ? (over < 5u ? over : 5u) : 6u; ix.i7 = tok ? i7 : 4u; ix.i8 = conv ? i8 : 4u; ix.d2 = d2;
+	}
 	return 3u | (tool ? 0x1cu : 0u) | (hasdur ? 0x20u : 0u) | (llm ? 0x40u : 0u) | (tok ? 0x80u : 0u) | (conv ? 0x100u : 0u);
+}
+__device__ __forceinline__ uint32_t record_ws_table(const apo_record &r, double w2, const double *cat, double &ws_out) {
+	CatIdx ix;
+	return record_ws_table_t<false>(r, w2, cat, ws_out, ix);
 }
 
 // TCS:777-784.  lut[mask] = sum of the present weights added in push order (host-built,

@@ -328,9 +328,6 @@ cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_cou
 
 // =================================================================== K2 detect6
 constexpr int K2_THREADS = 256;
-// lane-local u32 counters
-enum { CN_GOOD = 0, CN_BAD, CN_NONE, CN_MODE = 3 /*15*/, CN_PAT = 18 /*6*/, CN_DIM = 24 /*9*/, CN_RW = 33, CN_TOTAL = 34 };
-
 __device__ __forceinline__ void ex_insert(unsigned long long *slots, unsigned long long idx) {
 	// keep the 3 smallest indices: a value flows down the chain, every slot only decreases
 	unsigned long long v = idx;
@@ -344,19 +341,37 @@ __device__ __forceinline__ void ex_insert(unsigned long long *slots, unsigned lo
 
 __device__ void finalize_block(const FinalizeParams &F);
 
-// Lane-local sums are plain int64 (|term| <= 2^52) and are flushed every K2_CHUNK records per
-// thread, so they cannot overflow; the flush adds exact limb sums with integer atomics.
-constexpr int K2_CHUNK = 256;
+// Per-thread state of one chunk of <= K2_CHUNK records.  Seven of the nine dimensions are
+// categorical (TCS:677-761), so their per-dimension sums (APO:556-565) are kept as packed
+// occurrence counters — one 64-bit register per dimension, one small field per category — and
+// turned into exact fixed-point sums at flush time: sum = SUM_k count_k * rint(value_k * 2^52),
+// an integer product, identical to adding rint(value * 2^52) record by record.
+constexpr int K2_CHUNK = 256;      // < 2^9: no packed field (>= 9 bits wide) can overflow inside a chunk
+
+__device__ __forceinline__ void add_i128(long long *dst, __int128 v) {
+	const unsigned long long lo = (unsigned long long)v;
+	const unsigned long long l0 = lo & 0xffffffffull, l1 = lo >> 32, l2 = (unsigned long long)(long long)(v >> 64);
+	if (l0) atomicAdd((unsigned long long *)dst + 0, l0);
+	if (l1) atomicAdd((unsigned long long *)dst + 1, l1);
+	if (l2) atomicAdd((unsigned long long *)dst + 2, l2);
+}
+// field f (width bits) of a packed counter, summed over the warp
+template <int WIDTH>
+__device__ __forceinline__ uint32_t field_sum(unsigned long long pk, int f) {
+	return warp_sum_u32((uint32_t)(pk >> (WIDTH * f)) & ((1u << WIDTH) - 1u));
+}
 
 __global__ void __launch_bounds__(K2_THREADS, 2)
 k_detect6(const K2Params P) {
 	__shared__ unsigned long long s_ex[APO_NPAT * 3];
+	__shared__ double s_cat[CAT_WORDS];
 	__shared__ bool s_last;
 	const int tid = threadIdx.x, lane = tid & 31;
 	if (tid < APO_NPAT * 3) s_ex[tid] = ~0ull;
+	if (tid < CAT_WORDS) s_cat[tid] = P.lut[1024 + tid];
 	__syncthreads();
 
-	const Weights W = P.W;
+	const double w2 = P.W.w[2];
 	long long *corp = P.acc + (uint64_t)ACC_PER_CAND * P.C;
 	const uint4 *src = reinterpret_cast<const uint4 *>(P.recs);
 	const uint64_t stride = (uint64_t)gridDim.x * K2_THREADS;
@@ -366,44 +381,36 @@ k_detect6(const K2Params P) {
 	const uint64_t rounds = (per_thread + K2_CHUNK - 1) / K2_CHUNK;
 
 	for (uint64_t round = 0; round < rounds; round++) {
-		uint32_t cn[CN_TOTAL];
-#pragma unroll
-		for (int i = 0; i < CN_TOTAL; i++) cn[i] = 0;
-		long long fx[1 + APO_NDIM];
-#pragma unroll
-		for (int i = 0; i < 1 + APO_NDIM; i++) fx[i] = 0;
+		unsigned long long mTot = 0, mGood = 0, mBad = 0;        // 5 modes x 12 bits       (APO:519-525)
+		unsigned long long c01a = 0, c01b = 0;                    // (fb + 3*err) x 10 bits, endTime unset / set
+		unsigned long long c3 = 0, c4 = 0, c5 = 0, c7 = 0, c8 = 0; // 5 slots x 12 bits, slot 4 = not pushed
+		unsigned long long c6 = 0;                                // 7 slots x 9 bits, slot 6 = not pushed
+		unsigned long long pat = 0;                               // 6 patterns x 10 bits
 		unsigned long long tool[3] = {0, 0, 0};
+		long long fxR = 0, fxD2 = 0;
+		uint32_t nValid = 0;
 
 		for (int it = 0; it < K2_CHUNK && t < P.T; it++, t += stride) {
 			union { uint4 q[2]; apo_record r; } u;
 			u.q[0] = __ldg(src + 2 * t); u.q[1] = __ldg(src + 2 * t + 1);
 			const apo_record &r = u.r;
 			const bool good = r.feedback == 1, bad = r.feedback == 2;
-			cn[CN_GOOD] += good; cn[CN_BAD] += bad; cn[CN_NONE] += (!good && !bad);     // APO:513-516
-			const uint32_t m = r.mode < APO_NMODE ? r.mode : 0u;                         // APO:519-525, 627-633
-#pragma unroll
-			for (int k = 0; k < APO_NMODE; k++) {
-				const bool is = (m == (uint32_t)k);
-				cn[CN_MODE + 3 * k] += is; cn[CN_MODE + 3 * k + 1] += (is && good); cn[CN_MODE + 3 * k + 2] += (is && bad);
-			}
+			const uint32_t msh = 12u * (r.mode < APO_NMODE ? r.mode : 0u);               // APO:627-633
+			mTot += 1ull << msh; mGood += (unsigned long long)good << msh; mBad += (unsigned long long)bad << msh;
 			tool[0] += r.toolCalls; tool[1] += r.toolSucc; tool[2] += r.toolFail;       // TCS:603-605
 
 			if (r.flags & APO_F_VALID) {                                                 // APO:550, TCS:606
-				double d[APO_NDIM];
-				const uint32_t mask = reward_dims(r, d);
-				double ws = 0.0;
-#pragma unroll
-				for (int i = 0; i < APO_NDIM; i++) ws = __dadd_rn(ws, __dmul_rn(d[i], W.w[i]));
+				double ws; CatIdx ix;
+				const uint32_t mask = record_ws_table_t<true>(r, w2, s_cat, ws, ix);
 				const double2 tw = make_double2(__ldg(P.lut + mask), __ldg(P.lut + 512 + mask));
-				const bool has = tw.x > 0.0;                                             // TCS:784 totalWeight > 0
-				const double fr = div_lut<false>(ws, tw);
-				fx[0] += has ? to_fx(fr) : 0ll;
-				cn[CN_RW] += has;
-#pragma unroll
-				for (int i = 0; i < APO_NDIM; i++) {                                     // APO:556-565
-					const bool p = has && ((mask >> i) & 1u);
-					fx[1 + i] += p ? to_fx(d[i]) : 0ll;
-					cn[CN_DIM + i] += p;
+				if (tw.x > 0.0) {                                                        // TCS:784 totalWeight > 0
+					fxR += to_fx(div_lut<false>(ws, tw));
+					nValid++;
+					const unsigned long long one01 = 1ull << (10u * (ix.i01 % 6u));
+					if (ix.i01 >= 6u) c01b += one01; else c01a += one01;
+					c3 += 1ull << (12u * ix.i3); c4 += 1ull << (12u * ix.i4); c5 += 1ull << (12u * ix.i5);
+					c6 += 1ull << (9u * ix.i6); c7 += 1ull << (12u * ix.i7); c8 += 1ull << (12u * ix.i8);
+					fxD2 += to_fx(ix.d2);                                                // +0.0 when not pushed
 				}
 			}
 			if (bad) {                                                                   // APO:644-755: every predicate ANDs 'bad'
@@ -419,7 +426,7 @@ k_detect6(const K2Params P) {
 #pragma unroll
 				for (int p = 0; p < APO_NPAT; p++) {
 					if (hit[p]) {
-						cn[CN_PAT + p]++;
+						pat += 1ull << (10 * p);
 						// slice(0,3): first three in corpus order
 						if (gi < *((volatile unsigned long long *)&s_ex[3 * p + 2])) ex_insert(&s_ex[3 * p], gi);
 					}
@@ -427,29 +434,82 @@ k_detect6(const K2Params P) {
 			}
 		}
 
-		// ---- flush this chunk: warp reduce, then global integer atomics
+		// ---- flush this chunk: warp-reduce every field, lane 0 turns counts into exact sums
+		uint32_t good = 0, badn = 0, total = 0;
 #pragma unroll
-		for (int i = 0; i < CN_TOTAL; i++) {
-			const uint32_t s = warp_sum_u32(cn[i]);
-			if (lane == 0 && s) {
-				int w;
-				if (i < 3) w = CORP_TALLY + i;
-				else if (i < CN_PAT) w = CORP_MODE + (i - CN_MODE);
-				else if (i < CN_DIM) w = CORP_PAT + (i - CN_PAT);
-				else if (i < CN_RW) w = CORP_DIM + 4 * (i - CN_DIM) + 3;
-				else w = CORP_REWARD + 3;
-				atomicAdd((unsigned long long *)corp + w, (unsigned long long)s);
+		for (int m = 0; m < APO_NMODE; m++) {
+			const uint32_t a = field_sum<12>(mTot, m), g = field_sum<12>(mGood, m), b = field_sum<12>(mBad, m);
+			if (lane == 0) {
+				if (a) atomicAdd((unsigned long long *)corp + CORP_MODE + 3 * m, (unsigned long long)a);
+				if (g) atomicAdd((unsigned long long *)corp + CORP_MODE + 3 * m + 1, (unsigned long long)g);
+				if (b) atomicAdd((unsigned long long *)corp + CORP_MODE + 3 * m + 2, (unsigned long long)b);
 			}
+			total += a; good += g; badn += b;
+		}
+		if (lane == 0) {                                                                 // APO:513-516
+			if (good) atomicAdd((unsigned long long *)corp + CORP_TALLY, (unsigned long long)good);
+			if (badn) atomicAdd((unsigned long long *)corp + CORP_TALLY + 1, (unsigned long long)badn);
+			if (total - good - badn) atomicAdd((unsigned long long *)corp + CORP_TALLY + 2, (unsigned long long)(total - good - badn));
 		}
 #pragma unroll
-		for (int i = 0; i < 1 + APO_NDIM; i++) {
-			Acc128 a; a.lo = (unsigned long long)fx[i]; a.hi = fx[i] >> 63;
-			flush_acc128(a, i == 0 ? corp + CORP_REWARD : corp + CORP_DIM + 4 * (i - 1), lane);
+		for (int p = 0; p < APO_NPAT; p++) {
+			const uint32_t n = field_sum<10>(pat, p);
+			if (lane == 0 && n) atomicAdd((unsigned long long *)corp + CORP_PAT + p, (unsigned long long)n);
 		}
 #pragma unroll
 		for (int i = 0; i < 3; i++) {
 			const unsigned long long s = warp_sum_u64(tool[i]);
 			if (lane == 0 && s) atomicAdd((unsigned long long *)corp + CORP_TOOL + i, s);
+		}
+		{   // finalReward sum and count (APO:550-553)
+			Acc128 a; a.lo = (unsigned long long)fxR; a.hi = fxR >> 63;
+			flush_acc128(a, corp + CORP_REWARD, lane);
+			Acc128 b; b.lo = (unsigned long long)fxD2; b.hi = fxD2 >> 63;
+			flush_acc128(b, corp + CORP_DIM + 4 * 2, lane);
+		}
+		const uint32_t nv = warp_sum_u32(nValid);
+		// d0 / d1 from the (feedback, hasErrors, endTime) census: TCS:677-691
+		__int128 s0 = 0, s1 = 0;
+#pragma unroll
+		for (int ended = 0; ended < 2; ended++)
+#pragma unroll
+			for (int err = 0; err < 2; err++)
+#pragma unroll
+				for (int fb = 0; fb < 3; fb++) {
+					const uint32_t n = field_sum<10>(ended ? c01b : c01a, fb + 3 * err);
+					const double d0 = fb == 1 ? 1.0 : (fb == 2 ? -1.0 : 0.0);
+					const double d1 = fb == 1 ? 1.0 : (err ? -0.5 : (ended ? 0.8 : 0.5));
+					s0 += (__int128)n * to_fx(d0);
+					s1 += (__int128)n * to_fx(d1);
+				}
+		const double lv_rel[4] = {1.0, -0.2, -0.5, -1.0}, lv_cnt[4] = {1.0, 0.3, -0.3, -0.8}, lv_dur[4] = {1.0, 0.5, 0.0, -0.5};
+		__int128 s3 = 0, s4 = 0, s5 = 0, s7 = 0, s8 = 0, s6 = 0;
+		uint32_t n3 = 0, n5 = 0, n6 = 0, n7 = 0, n8 = 0;
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const uint32_t a3 = field_sum<12>(c3, k), a4 = field_sum<12>(c4, k), a5 = field_sum<12>(c5, k);
+			const uint32_t a7 = field_sum<12>(c7, k), a8 = field_sum<12>(c8, k);
+			s3 += (__int128)a3 * to_fx(lv_rel[k]); s4 += (__int128)a4 * to_fx(lv_cnt[k]); s5 += (__int128)a5 * to_fx(lv_dur[k]);
+			s7 += (__int128)a7 * to_fx(lv_dur[k]); s8 += (__int128)a8 * to_fx(lv_cnt[k]);
+			n3 += a3; n5 += a5; n7 += a7; n8 += a8;
+		}
+#pragma unroll
+		for (int k = 0; k < 6; k++) {                                                    // TCS:735: max(-1, 1 - k*0.4)
+			const uint32_t a6 = field_sum<9>(c6, k);
+			double ef = __dadd_rn(1.0, -__dmul_rn((double)k, 0.4));
+			ef = ef < -1.0 ? -1.0 : ef;
+			s6 += (__int128)a6 * to_fx(ef);
+			n6 += a6;
+		}
+		if (lane == 0) {
+			const __int128 sums[APO_NDIM] = {s0, s1, 0, s3, s4, s5, s6, s7, s8};
+			const uint32_t cnts[APO_NDIM] = {nv, nv, n3, n3, n3, n5, n6, n7, n8};            // d2,d3,d4 are pushed together (TCS:695)
+#pragma unroll
+			for (int i = 0; i < APO_NDIM; i++) {
+				if (i != 2) add_i128(corp + CORP_DIM + 4 * i, sums[i]);
+				if (cnts[i]) atomicAdd((unsigned long long *)corp + CORP_DIM + 4 * i + 3, (unsigned long long)cnts[i]);
+			}
+			if (nv) atomicAdd((unsigned long long *)corp + CORP_REWARD + 3, (unsigned long long)nv);
 		}
 	}
 	__syncthreads();

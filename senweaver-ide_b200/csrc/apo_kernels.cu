@@ -365,10 +365,12 @@ __global__ void __launch_bounds__(K2_THREADS, 2)
 k_detect6(const K2Params P) {
 	__shared__ unsigned long long s_ex[APO_NPAT * 3];
 	__shared__ double s_cat[CAT_WORDS];
+	__shared__ double2 s_lut[512];                     // {total weight, reciprocal} per (natural) presence mask
 	__shared__ bool s_last;
 	const int tid = threadIdx.x, lane = tid & 31;
 	if (tid < APO_NPAT * 3) s_ex[tid] = ~0ull;
 	if (tid < CAT_WORDS) s_cat[tid] = P.lut[1024 + tid];
+	for (int i = tid; i < 512; i += K2_THREADS) s_lut[i] = make_double2(P.lut[i], P.lut[512 + i]);
 	__syncthreads();
 
 	const double w2 = P.W.w[2];
@@ -390,9 +392,12 @@ k_detect6(const K2Params P) {
 		long long fxR = 0, fxD2 = 0;
 		uint32_t nValid = 0;
 
+		// software pipeline: the next record of this thread is in flight while the current one is scored
+		union Rec { uint4 q[2]; apo_record r; } nxt;
+		if (t < P.T) { nxt.q[0] = __ldg(src + 2 * t); nxt.q[1] = __ldg(src + 2 * t + 1); }
 		for (int it = 0; it < K2_CHUNK && t < P.T; it++, t += stride) {
-			union { uint4 q[2]; apo_record r; } u;
-			u.q[0] = __ldg(src + 2 * t); u.q[1] = __ldg(src + 2 * t + 1);
+			Rec u = nxt;
+			if (it + 1 < K2_CHUNK && t + stride < P.T) { nxt.q[0] = __ldg(src + 2 * (t + stride)); nxt.q[1] = __ldg(src + 2 * (t + stride) + 1); }
 			const apo_record &r = u.r;
 			const bool good = r.feedback == 1, bad = r.feedback == 2;
 			const uint32_t msh = 12u * (r.mode < APO_NMODE ? r.mode : 0u);               // APO:627-633
@@ -402,7 +407,7 @@ k_detect6(const K2Params P) {
 			if (r.flags & APO_F_VALID) {                                                 // APO:550, TCS:606
 				double ws; CatIdx ix;
 				const uint32_t mask = record_ws_table_t<true>(r, w2, s_cat, ws, ix);
-				const double2 tw = make_double2(__ldg(P.lut + mask), __ldg(P.lut + 512 + mask));
+				const double2 tw = s_lut[mask];
 				if (tw.x > 0.0) {                                                        // TCS:784 totalWeight > 0
 					fxR += to_fx(div_lut<false>(ws, tw));
 					nValid++;

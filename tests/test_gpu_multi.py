@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 C, T, K, SEED = 12, 400_003, 5, 0x5EED0005
 
 
-def worker(rank, world, uid_path, out_dir):
+def worker(rank, world, uid_path, out_dir, layout):
     sys.path.insert(0, ROOT)
     pkg = import_module("senweaver-ide_b200")
     torch.cuda.set_device(rank)
@@ -24,7 +24,7 @@ def worker(rank, world, uid_path, out_dir):
     uid = open(uid_path, "rb").read()
     eng.comm_init(world, rank, uid)
     first, last = pkg.sharding.shard_range(T, world, rank)
-    eng.dims_generate(SEED, 0, C, first, last - first, 300)
+    (eng.dims_generate_compact if layout == "compact" else eng.dims_generate)(SEED, 0, C, first, last - first, 300)
     eng.corpus_generate(SEED, first, last - first, 300)
     res = eng.score(C, K, corpus=True)
     sums, counts = eng.debug_partials(C)            # after the allreduce: the joined integers
@@ -36,14 +36,15 @@ def worker(rank, world, uid_path, out_dir):
     eng.close()
 
 
+@pytest.mark.parametrize("layout", ["fp32", "compact"])
 @pytest.mark.parametrize("world", [2])
-def test_sharded_score_equals_single_gpu(tmp_path, engine, orc, world):
+def test_sharded_score_equals_single_gpu(tmp_path, engine, orc, world, layout):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     pkg = import_module("senweaver-ide_b200")
     uid_path = tmp_path / "uid.bin"
     uid_path.write_bytes(pkg.Engine.comm_unique_id())
-    mp.spawn(worker, args=(world, str(uid_path), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(worker, args=(world, str(uid_path), str(tmp_path), layout), nprocs=world, join=True)
     engine.dims_generate(SEED, 0, C, 0, T, 300)
     engine.corpus_generate(SEED, 0, T, 300)
     ref = engine.score(C, K, corpus=True)

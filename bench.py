@@ -99,6 +99,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Pin this rank to the CPUs of its GPU's NUMA node before it allocates pinned host buffers
+    (first touch places them next to the GPU's PCIe root: matters for the 8-rank e2e leg)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception as ex:
+        return f"numa binding skipped: {ex}"
+    return "numa binding skipped"
+
+
 def cpu_baseline(threads: int, target_s: float = 12.0) -> dict:
     """The oracle (C port of the reference TypeScript) timed on this box's host cores on a
     bounded sample of the same workload: `C` candidates x `T` records of the same generator."""
@@ -181,6 +206,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else "single rank: no binding"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("senweaver-ide_b200")
@@ -357,7 +384,9 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        out["e2e"]["host_placement"] = numa_note
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)
             out["cpu_baseline"] = cpu_baseline(len(os.sched_getaffinity(0)))
         print(json.dumps(out))
     eng.close()

@@ -85,3 +85,21 @@ def test_duplicate_candidates_tie_break(engine, orc):
     engine.dims_upload(np.stack([row, row, row]))
     res = engine.score(3, 3)
     assert res.scores[0] == res.scores[1] == res.scores[2] and list(res.topk) == [0, 1, 2]
+
+
+def test_config3_compact_layout_is_bit_identical(engine, orc):
+    """256 x 10M: the 35.8 GB Form Q recoding must reproduce the 92 GB Form D result exactly."""
+    C, T, seed = 256, 10_000_000, 0x5EED0003
+    engine.dims_generate(seed, 0, C, 0, T, 300)
+    ref = engine.score(C, 64)
+    exp = engine.debug_partials(C)
+    engine.dims_generate_compact(seed, 0, C, 0, T, 300)
+    assert engine.dims_layout() == 2
+    res = engine.score(C, 64)
+    assert engine.debug_partials(C) == exp
+    assert np.array_equal(res.scores, ref.scores) and np.array_equal(res.topk, ref.topk)
+    # lossless: a decoded slice equals the oracle's fp32 generator output bit for bit
+    d = orc.gen_dims(seed, 200, 1, 9_000_000, 4096, 300, 8)[0]
+    got = engine.dims_download(200, 9_000_000, 4096)
+    nan = np.isnan(d)
+    assert np.array_equal(nan, np.isnan(got)) and np.array_equal(d[~nan].view(np.uint32), got[~nan].view(np.uint32))

@@ -54,3 +54,20 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "apo_oracle" not in txt, f
+
+
+def test_ts_codec_offsets_match_the_c_structs(apo):
+    """ts/traceRecordCodec.ts hard-codes the byte offsets of apo_corpus_report; pin them to the ctypes mirror."""
+    from importlib import import_module
+    eng = import_module("senweaver-ide_b200.engine")
+    R, D, P = eng.CorpusReport, eng.DimStat, eng.Pattern
+    assert ctypes.sizeof(R) == 784
+    off = {f: getattr(R, f).offset for f, _ in R._fields_}
+    assert (off["total"], off["good"], off["bad"], off["none"], off["goodRate"], off["byMode"], off["byModeGoodRate"]) == (0, 8, 16, 24, 32, 40, 160)
+    assert (off["withReward"], off["avgReward"], off["dim"], off["pat"], off["toolCalls"], off["toolSucc"], off["toolFail"], off["toolSuccessRate"]) == \
+           (200, 216, 224, 512, 752, 760, 768, 776)
+    assert (ctypes.sizeof(D), D.count.offset, D.avg.offset, D.low_flag.offset, D.low_severity.offset, D.sugg_flag.offset, D.sugg_priority.offset) == (32, 8, 16, 24, 25, 26, 27)
+    assert (ctypes.sizeof(P), P.flag.offset, P.severity.offset, P.examples.offset) == (40, 8, 9, 16)
+    src = open(os.path.join(ROOT, "ts", "traceRecordCodec.ts")).read()
+    for token in ("224 + 32 * i", "512 + 40 * p", "160 + 8 * m", "40 + 24 * m", "u64(v, 752)", "v.getFloat64(776, true)", "784"):
+        assert token in src, token

@@ -383,4 +383,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 	    : "memory");
 }
 
+__device__ __forceinline__ void bulk_g2s_nohint(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+
 }  // namespace apo

@@ -126,7 +126,19 @@ k_reward9(const K1Params P) {
 				const uint32_t bytes = ((n + 3u) & ~3u) * ROW;
 				meta[s].cand = (int32_t)c; meta[s].n = (int32_t)n;
 				mbar_expect_tx(&full[s], bytes);
-				bulk_g2s(smem + s * Cfg::STAGE_BYTES, P.base + (uint64_t)c * P.pitch_bytes + e0 * ROW, bytes, &full[s], pol);
+				uint8_t *dst = smem + s * Cfg::STAGE_BYTES;
+				const uint8_t *gsrc = P.base + (uint64_t)c * P.pitch_bytes + e0 * ROW;
+				if (P.tune == 0) bulk_g2s(dst, gsrc, bytes, &full[s], pol);
+				else {
+					const uint32_t parts = 1u << ((P.tune >> 1) & 7u);
+					uint32_t chunk = (bytes / parts + 15u) & ~15u;
+					if (chunk == 0) chunk = bytes;
+					for (uint32_t off = 0; off < bytes; off += chunk) {
+						const uint32_t nb = bytes - off < chunk ? bytes - off : chunk;
+						if (P.tune & 1u) bulk_g2s_nohint(dst + off, gsrc + off, nb, &full[s]);
+						else bulk_g2s(dst + off, gsrc + off, nb, &full[s], pol);
+					}
+				}
 			}
 		}
 		return;
@@ -298,6 +310,7 @@ cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_cou
 	if (P.total_tiles == 0) return cudaSuccess;
 	int grid = sm_count;
 	if (const char *g = getenv("APO_K1_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }   // tuning experiments only
+	if (const char *g = getenv("APO_K1_TUNE")) P.tune = (uint32_t)atoi(g);
 	if ((uint64_t)grid > P.total_tiles) grid = (int)P.total_tiles;
 	if (row == 36) {
 		switch (variant) {

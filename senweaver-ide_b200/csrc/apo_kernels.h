@@ -15,6 +15,7 @@ struct K1Params {
 	uint32_t tiles_per_cand;    // filled by run_reward9
 	uint64_t T;                 // evaluations per candidate in this launch
 	uint64_t total_tiles;       // filled by run_reward9
+	uint32_t tune;              // experiments only (APO_K1_TUNE): bit0 no L2 hint, bits 1-3 log2 of bulk copies per stage
 	long long *acc;             // accumulator vector (see apo_device.cuh)
 	const double *lut;          // [0,512) total weight per presence mask, [512,1024) its reciprocal,
 	                            // [1024,1088) categorical product table (apo_device.cuh CAT_*)

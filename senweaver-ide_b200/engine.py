@@ -111,8 +111,11 @@ def load_library() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ApoError(-2, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                           "(there is no CPU fallback)")
+        try:                                    # fresh checkout: compile the sm_100a library in-tree (nvcc needs no GPU)
+            build_library()
+        except Exception as ex:
+            raise ApoError(-2, f"{LIB_PATH} is missing and could not be built ({ex}); run "
+                               "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
     L = C.CDLL(LIB_PATH)
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     L.apo_abi_version.restype = i32

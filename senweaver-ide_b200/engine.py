@@ -99,7 +99,9 @@ def build_library(force: bool = False) -> str:
     srcs.append(os.path.join(_HERE, "..", "include", "apo_b200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
-        subprocess.check_call(["make", "-s", "-C", csrc], stdout=subprocess.DEVNULL)
+        r = subprocess.run(["make", "-s", "-C", csrc], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc build failed:\n" + r.stdout[-2000:] + r.stderr[-4000:])
     return LIB_PATH
 
 

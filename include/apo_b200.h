@@ -200,7 +200,10 @@ int apo_score(apo_engine *e, const apo_score_opts *o, double *scores, uint64_t *
  * each accumulate streams the currently loaded dims/rollouts (a chunk of candidates and/or
  * a window of records) into candidates [cand_offset, cand_offset + C_loaded); finish runs the
  * corpus scan, the cross-rank join and the top-K over all C_total.  apo_score ==
- * begin + one accumulate + finish. */
+ * begin + one accumulate + finish.  finish may be called repeatedly within one session: the
+ * candidate accumulators are exact integers that only ever grow by later accumulate calls, so
+ * new records (a window that was not scored yet) can be added as they arrive and the ranking
+ * refreshed without rescanning the old ones (incremental scoring). */
 int apo_score_begin(apo_engine *e, uint32_t C_total);
 int apo_score_accumulate(apo_engine *e, const apo_score_opts *o, uint32_t cand_offset);
 int apo_score_finish(apo_engine *e, const apo_score_opts *o, double *scores, uint64_t *counts,

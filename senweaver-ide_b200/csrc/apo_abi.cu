@@ -94,7 +94,7 @@ struct apo_engine {
 	uint32_t qbook_host[8 * 256]; bool compact = false;
 	DevBuf<uint8_t> roll; uint32_t roll_C = 0, roll_row = 32; uint64_t roll_T = 0, roll_pitch = 0;   // Form R (32 B) or R16 (16 B) rows
 
-	DevBuf<long long> acc; uint32_t last_C = 0;
+	DevBuf<long long> acc, acc_joined; uint32_t last_C = 0;   // acc_joined: allreduce output (> 1 rank); acc keeps this rank's partials
 	DevBuf<unsigned long long> misc;     // [0,18) example scratch, [18] ticket
 	DevBuf<uint8_t> result;              // scores | counts | topk | report
 	DevBuf<unsigned long long> keys, sel_key; DevBuf<int32_t> sel_idx;
@@ -291,8 +291,6 @@ apo::FinalizeParams make_fin(apo_engine *e, uint32_t C, uint32_t K, int with_cor
 // zero the accumulators, arm the example scratch and the ticket
 int begin_score(apo_engine *e, uint32_t C) {
 	CK(cudaMemsetAsync(e->acc.p, 0, acc_words(C, e->nranks) * 8, e->stream));
-	CK(cudaMemsetAsync(e->misc.p, 0xFF, 18 * 8, e->stream));
-	CK(cudaMemsetAsync(e->misc.p + 18, 0, 8, e->stream));
 	e->last_C = C; e->score_C = C; e->scoring = true; e->k1_used = 0;
 	e->timing = apo_timing{};
 	CK(cudaEventRecord(e->ev[0], e->stream));
@@ -345,6 +343,11 @@ int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *sco
 	const uint32_t K = o->K;
 	const bool with_corpus = (o->flags & APO_SCORE_CORPUS) && e->corpus_T > 0;
 	apo::FinalizeParams F = make_fin(e, C, K, with_corpus ? 1 : 0);
+	// the corpus block and the example scratch belong to this finish call only, so that a scoring session can
+	// be finished repeatedly while evaluations keep being accumulated (incremental scoring)
+	CK(cudaMemsetAsync(e->acc.p + (uint64_t)ACC_PER_CAND * C, 0, (CORP_FIXED + 18ull * e->nranks) * 8, e->stream));
+	CK(cudaMemsetAsync(e->misc.p, 0xFF, 18 * 8, e->stream));
+	CK(cudaMemsetAsync(e->misc.p + 18, 0, 8, e->stream));
 	CK(cudaEventRecord(e->ev[1], e->stream));
 	bool finalized = false;
 	if (with_corpus) {
@@ -358,9 +361,11 @@ int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *sco
 	}
 	CK(cudaEventRecord(e->ev[2], e->stream));
 	if (e->nranks > 1) {
-		const int rc = g_nccl.AllReduce(e->acc.p, e->acc.p, (size_t)acc_words(C, e->nranks), kNcclInt64, kNcclSum, e->comm, e->stream);
+		CK(e->acc_joined.reserve(acc_words(C, e->nranks)));
+		const int rc = g_nccl.AllReduce(e->acc.p, e->acc_joined.p, (size_t)acc_words(C, e->nranks), kNcclInt64, kNcclSum, e->comm, e->stream);
 		if (rc != 0) return fail(e, APO_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
 		e->timing.launches++;
+		F.acc = e->acc_joined.p;
 	}
 	CK(cudaEventRecord(e->ev[3], e->stream));
 	if (!finalized) {
@@ -381,7 +386,6 @@ int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *sco
 	float ms = 0;
 	e->timing.reward_ms = 0;
 	for (size_t i = 0; i + 1 < e->k1_used; i += 2) { cudaEventElapsedTime(&ms, e->k1_ev[i], e->k1_ev[i + 1]); e->timing.reward_ms += ms; }
-	e->scoring = false;
 	cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->timing.corpus_ms = ms;
 	cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->timing.allreduce_ms = ms;
 	cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->timing.finalize_ms = ms;
@@ -443,7 +447,7 @@ extern "C" void apo_destroy(apo_engine *e) {
 	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	if (e->own_stream) cudaStreamSynchronize(e->own_stream);
 	e->q8.release(); e->qd2.release(); e->qli.release(); e->qbook.release(); e->d_ptab.release(); e->stage.release();
-	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->misc.release();
+	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->acc_joined.release(); e->misc.release();
 	e->result.release(); e->keys.release(); e->sel_key.release(); e->sel_idx.release();
 	e->win[0].release(); e->win[1].release(); e->batch_in.release(); e->batch_out.release(); e->batch_mask.release();
 	if (e->h_result) cudaFreeHost(e->h_result);
@@ -846,7 +850,7 @@ extern "C" int apo_debug_partials(apo_engine *e, int64_t *out, uint32_t C) {
 	if (!e || !out) return fail(e, APO_E_ARG, "NULL argument");
 	if (C != e->last_C || !e->acc.p) return fail(e, APO_E_STATE, "no scoring call with C=%u to read back", C);
 	CK(cudaSetDevice(e->device));
-	CK(cudaMemcpyAsync(out, e->acc.p, 8ull * ACC_PER_CAND * C, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaMemcpyAsync(out, (e->nranks > 1 && e->acc_joined.p) ? e->acc_joined.p : e->acc.p, 8ull * ACC_PER_CAND * C, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	return APO_OK;
 }

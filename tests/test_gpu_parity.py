@@ -475,3 +475,22 @@ def test_rollouts_custom_weights_use_rebuilt_tables(engine, orc):
         assert np.array_equal(r.topk, orc.topk(orc.score_records(recs, w=w)[0], 2))
     finally:
         engine.set_weights(orc.weights())
+
+
+def test_incremental_scoring_session(engine, orc):
+    """One session, records arriving in three batches: after each batch finish() must equal a from-scratch
+    score of everything seen so far (exact integers), and the corpus report must not double count."""
+    C, T, seed = 6, 24_000, 0x5EED0009
+    dims = orc.gen_dims(seed, 0, C, 0, T, 300, 8)
+    recs = orc.gen_records(seed, orc.STREAM_CORPUS, 0, 1, 0, T, 300, 8).reshape(-1)
+    engine.dims_upload(dims)
+    engine.score_begin(C)
+    for lo, hi in [(0, 8_000), (8_000, 16_000), (16_000, 24_000)]:
+        engine.score_accumulate(0, first=lo, count=hi - lo)
+        engine.corpus_upload(recs[:hi])
+        r = engine.score_finish(C, 3, corpus=True)
+        assert engine.debug_partials(C) == orc.score_dims_fx(dims[:, :hi])
+        ref = orc.report(recs[:hi])
+        assert (r.report.total, r.report.bad, r.report.withReward) == (ref.total, ref.bad, ref.withReward)
+        assert [r.report.pat[p].count for p in range(6)] == [ref.pat[p].count for p in range(6)]
+        assert np.array_equal(r.topk, orc.topk(orc.score_dims(dims[:, :hi])[0], 3))

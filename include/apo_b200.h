@@ -138,7 +138,8 @@ int apo_corpus_generate(apo_engine *e, uint64_t seed, uint64_t t0, uint64_t T, u
 int apo_corpus_download(apo_engine *e, apo_record *out, uint64_t first, uint64_t n);
 
 /* ---- candidate x record evaluations ------------------------------------------------
- * Form D: fp32 dims[C][T][9], NaN = dimension absent, all-NaN = finalReward null.
+ * Form D: fp32 dims[C][T][9], NaN = dimension absent, all-NaN = finalReward null.  Values are
+ * expected within +-512 (the reference range is [-1,1], TCS:36): sums are exact fixed point.
  * Form R: one apo_record per (candidate, record); dims derived on device (TCS:668-763). */
 int apo_dims_upload(apo_engine *e, const float *dims, uint32_t C, uint64_t T);
 int apo_dims_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,

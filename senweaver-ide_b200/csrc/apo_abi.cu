@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <new>
@@ -298,7 +299,8 @@ int begin_score(apo_engine *e, uint32_t C) {
 }
 
 // one K1 launch over [first, first+count) of the loaded source into candidates [cand_offset, ...)
-int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_offset, uint64_t first, uint64_t count) {
+int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_offset, uint64_t first, uint64_t count,
+                       const apo::K2Params *fused = nullptr) {
 	const bool raw = o->source == APO_SRC_ROLLOUTS;
 	const uint32_t C = raw ? e->roll_C : e->dims_C;
 	if (!raw && e->compact) {
@@ -307,6 +309,7 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 		apo::KqParams Q{};
 		Q.q8 = e->q8.p + first; Q.d2 = e->qd2.p + first; Q.li = e->qli.p + first; Q.pitch_evals = e->dims_pitch; Q.C = C; Q.T = count;
 		Q.acc = e->acc.p + (uint64_t)ACC_PER_CAND * cand_offset; Q.lut = e->d_lut.p; Q.ptab = e->d_ptab.p; Q.w2 = e->W.w[2];
+		if (fused) { Q.corpus_on = 1; Q.corpus = *fused; }
 		if (e->k1_used + 2 > e->k1_ev.size()) {
 			for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
 		}
@@ -325,6 +328,7 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 	P.C = C; P.T = count; P.acc = e->acc.p + (uint64_t)ACC_PER_CAND * cand_offset;
 	P.lut = e->d_lut.p;
 	P.W = e->W;
+	if (fused) { P.corpus_on = 1; P.corpus = *fused; }
 	if (!count) return APO_OK;
 	if (e->k1_used + 2 > e->k1_ev.size()) {
 		for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
@@ -338,23 +342,36 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 }
 
 // K2 (+fused finalize) / allreduce / K3, then bring the result block home
-int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *scores, uint64_t *counts, int32_t *topk,
-                 apo_corpus_report *report) {
-	const uint32_t K = o->K;
-	const bool with_corpus = (o->flags & APO_SCORE_CORPUS) && e->corpus_T > 0;
-	apo::FinalizeParams F = make_fin(e, C, K, with_corpus ? 1 : 0);
-	// the corpus block and the example scratch belong to this finish call only, so that a scoring session can
-	// be finished repeatedly while evaluations keep being accumulated (incremental scoring)
+bool wants_corpus(const apo_engine *e, const apo_score_opts *o) { return (o->flags & APO_SCORE_CORPUS) && e->corpus_T > 0; }
+
+// the corpus block and the example scratch belong to one corpus pass only, so that a scoring session can be
+// finished repeatedly while evaluations keep being accumulated (incremental scoring)
+int arm_corpus(apo_engine *e, uint32_t C) {
 	CK(cudaMemsetAsync(e->acc.p + (uint64_t)ACC_PER_CAND * C, 0, (CORP_FIXED + 18ull * e->nranks) * 8, e->stream));
 	CK(cudaMemsetAsync(e->misc.p, 0xFF, 18 * 8, e->stream));
 	CK(cudaMemsetAsync(e->misc.p + 18, 0, 8, e->stream));
+	return APO_OK;
+}
+
+apo::K2Params make_k2(apo_engine *e, uint32_t C, const apo::FinalizeParams &F) {
+	apo::K2Params P{};
+	P.recs = e->corpus.p; P.T = e->corpus_T; P.idx_base = e->corpus_base; P.C = C; P.rank = e->rank;
+	P.acc = e->acc.p; P.ex_scratch = e->misc.p; P.ticket = (unsigned int *)(e->misc.p + 18);
+	P.lut = e->d_lut.p; P.W = e->W; P.fuse_finalize = e->nranks == 1 ? 1 : 0; P.fin = F;
+	return P;
+}
+
+// fused_corpus: the scoring kernel already ran the corpus scan (and, at one rank, the finalisation)
+int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *scores, uint64_t *counts, int32_t *topk,
+                 apo_corpus_report *report, bool fused_corpus = false) {
+	const uint32_t K = o->K;
+	const bool with_corpus = wants_corpus(e, o);
+	apo::FinalizeParams F = make_fin(e, C, K, with_corpus ? 1 : 0);
+	if (!fused_corpus) { int rc = arm_corpus(e, C); if (rc) return rc; }
 	CK(cudaEventRecord(e->ev[1], e->stream));
-	bool finalized = false;
-	if (with_corpus) {
-		apo::K2Params P{};
-		P.recs = e->corpus.p; P.T = e->corpus_T; P.idx_base = e->corpus_base; P.C = C; P.rank = e->rank;
-		P.acc = e->acc.p; P.ex_scratch = e->misc.p; P.ticket = (unsigned int *)(e->misc.p + 18);
-		P.lut = e->d_lut.p; P.W = e->W; P.fuse_finalize = e->nranks == 1 ? 1 : 0; P.fin = F;
+	bool finalized = fused_corpus && e->nranks == 1;
+	if (with_corpus && !fused_corpus) {
+		const apo::K2Params P = make_k2(e, C, F);
 		CK(apo::run_detect6(P, e->sm_count, e->stream));
 		e->timing.launches++;
 		finalized = P.fuse_finalize != 0;
@@ -777,8 +794,15 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	CK(cudaSetDevice(e->device));
 	if ((rc = ensure_scratch(e, C, o->K))) return rc;
 	if ((rc = begin_score(e, C))) return rc;
-	if ((rc = launch_k1_resident(e, o, 0, first, count))) return rc;
-	return finish_score(e, o, C, scores, counts, topk, report);
+	// one launch per call: the corpus scan (K2) rides on an extra warp of every scoring CTA and the last CTA
+	// finalises (K3) when there is a single rank
+	const bool fuse = wants_corpus(e, o) && count > 0 && getenv("APO_NO_FUSE") == nullptr;
+	if (fuse) {
+		if ((rc = arm_corpus(e, C))) return rc;
+		const apo::K2Params k2 = make_k2(e, C, make_fin(e, C, o->K, 1));
+		if ((rc = launch_k1_resident(e, o, 0, first, count, &k2))) return rc;
+	} else if ((rc = launch_k1_resident(e, o, 0, first, count))) return rc;
+	return finish_score(e, o, C, scores, counts, topk, report, fuse);
 }
 
 namespace {

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include "apo_device.cuh"
 #include "apo_kernels.h"
+#include "apo_corpus.cuh"
 
 namespace apo {
 
@@ -154,9 +155,11 @@ struct KqCfg {
 	static constexpr int STAGE_BYTES = Q8_BYTES + D2_BYTES + LI_BYTES;
 	static constexpr int LUT_OFF = STAGES * STAGE_BYTES;          // double2[512]
 	static constexpr int PTAB_OFF = LUT_OFF + 512 * 16;           // double[8][256]
-	static constexpr int BAR_OFF = PTAB_OFF + 8 * 256 * 8;
+	static constexpr int CAT_OFF = PTAB_OFF + 8 * 256 * 8;        // categorical product table of the fused corpus scan
+	static constexpr int BAR_OFF = CAT_OFF + CAT_WORDS * 8;
 	static constexpr int META_OFF = BAR_OFF + 2 * STAGES * 8;
-	static constexpr int SMEM = META_OFF + STAGES * 8;
+	static constexpr int EX_OFF = META_OFF + STAGES * 8;
+	static constexpr int SMEM = EX_OFF + 18 * 8 + 16;
 	static_assert(EPT % 4 == 0, "evaluations are processed in interleaved groups of four");
 };
 
@@ -179,7 +182,7 @@ __device__ __forceinline__ void evalq_ws(unsigned long long q, float d2f, uint32
 }
 
 template <int CW, int EPT, int STAGES, bool RECIP>
-__global__ void __launch_bounds__((CW + 1) * 32, 1)
+__global__ void __launch_bounds__((CW + 2) * 32, 1)
 k_reward9q(const KqParams P) {
 	using Cfg = KqCfg<CW, EPT, STAGES>;
 	extern __shared__ __align__(128) uint8_t smem[];
@@ -188,10 +191,14 @@ k_reward9q(const KqParams P) {
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::BAR_OFF);
 	uint64_t *empty = full + STAGES;
 	QMeta *meta = reinterpret_cast<QMeta *>(smem + Cfg::META_OFF);
+	double *s_cat = reinterpret_cast<double *>(smem + Cfg::CAT_OFF);
+	unsigned long long *s_ex = reinterpret_cast<unsigned long long *>(smem + Cfg::EX_OFF);
+	bool *s_last = reinterpret_cast<bool *>(smem + Cfg::EX_OFF + 18 * 8);
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	for (int i = tid; i < 512; i += blockDim.x) s_lut[lut_index(i)] = make_double2(P.lut[i], P.lut[512 + i]);
 	for (int i = tid; i < 8 * 256; i += blockDim.x) s_ptab[i] = P.ptab[i];
+	for (int i = tid; i < CAT_WORDS; i += blockDim.x) s_cat[i] = P.lut[1024 + i];
 	if (tid == 0) {
 		for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
 		mbar_fence_init();
@@ -224,9 +231,13 @@ k_reward9q(const KqParams P) {
 				bulk_g2s(st + Cfg::Q8_BYTES + Cfg::D2_BYTES, P.li + (uint64_t)c * P.pitch_evals + e0, n8 * 2u, &full[s], pol);
 			}
 		}
-		return;
-	}
-
+	} else if (warp == CW + 1) {
+		if (P.corpus_on) {                                        // corpus warp: K2's scan on the spare issue slots
+			if (lane < 18) s_ex[lane] = ~0ull;
+			__syncwarp();
+			corpus_scan_warp<true>(P.corpus, (uint64_t)blockIdx.x * 32, (uint64_t)gridDim.x * 32, s_ex, s_cat, s_lut, lane);
+		}
+	} else {
 	Acc128 acc; acc.zero();
 	uint32_t cnt = 0;
 	int cur = -1;
@@ -287,6 +298,8 @@ k_reward9q(const KqParams P) {
 		if (lane == 0) mbar_arrive(&empty[s]);
 	}
 	if (cur >= 0) flush(cur);
+	}
+	if (P.corpus_on) corpus_tail(P.corpus, s_ex, s_last);     // block-wide: every warp arrives here
 }
 
 template <int CW, int EPT, int STAGES>
@@ -296,11 +309,11 @@ static cudaError_t launch_kq(const KqParams &P, int grid, bool recip, cudaStream
 	if (recip) {
 		auto k = k_reward9q<CW, EPT, STAGES, true>;
 		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
-		k<<<grid, (CW + 1) * 32, Cfg::SMEM, st>>>(P);
+		k<<<grid, (CW + 2) * 32, Cfg::SMEM, st>>>(P);
 	} else {
 		auto k = k_reward9q<CW, EPT, STAGES, false>;
 		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
-		k<<<grid, (CW + 1) * 32, Cfg::SMEM, st>>>(P);
+		k<<<grid, (CW + 2) * 32, Cfg::SMEM, st>>>(P);
 	}
 	return cudaGetLastError();
 }

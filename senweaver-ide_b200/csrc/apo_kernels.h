@@ -8,20 +8,6 @@ namespace apo {
 
 struct Weights { double w[APO_NDIM]; };
 
-struct K1Params {
-	const uint8_t *base;        // first evaluation of candidate 0 inside the window
-	uint64_t pitch_bytes;       // candidate row pitch
-	uint32_t C;
-	uint32_t tiles_per_cand;    // filled by run_reward9
-	uint64_t T;                 // evaluations per candidate in this launch
-	uint64_t total_tiles;       // filled by run_reward9
-	uint32_t tune;              // experiments only (APO_K1_TUNE): bit0 no L2 hint, bits 1-3 log2 of bulk copies per stage
-	long long *acc;             // accumulator vector (see apo_device.cuh)
-	const double *lut;          // [0,512) total weight per presence mask, [512,1024) its reciprocal,
-	                            // [1024,1088) categorical product table (apo_device.cuh CAT_*)
-	Weights W;
-};
-
 struct FinalizeParams {
 	const long long *acc;
 	uint32_t C, K;
@@ -51,6 +37,23 @@ struct K2Params {
 	FinalizeParams fin;
 };
 
+struct K1Params {
+	const uint8_t *base;        // first evaluation of candidate 0 inside the window
+	uint64_t pitch_bytes;       // candidate row pitch
+	uint32_t C;
+	uint32_t tiles_per_cand;    // filled by run_reward9
+	uint64_t T;                 // evaluations per candidate in this launch
+	uint64_t total_tiles;       // filled by run_reward9
+	uint32_t tune;              // experiments only (APO_K1_TUNE): bit0 no L2 hint, bits 1-3 log2 of bulk copies per stage
+	long long *acc;             // accumulator vector (see apo_device.cuh)
+	const double *lut;          // [0,512) total weight per presence mask, [512,1024) its reciprocal,
+	                            // [1024,1088) categorical product table (apo_device.cuh CAT_*)
+	Weights W;
+	int corpus_on;              // run the corpus scan (K2) on one extra warp per CTA and the K2 tail in this launch
+	K2Params corpus;
+};
+
+
 // Form Q (apo_compact.cu): 8 one-byte codes + fp32 d2 per evaluation
 struct KqParams {
 	const unsigned long long *q8;   // [C][pitch] codes, window base of candidate 0
@@ -65,6 +68,8 @@ struct KqParams {
 	const double *lut;              // as K1Params::lut
 	const double *ptab;             // [8][256] value*weight per code (code 255 -> +0.0), table 0 = fl(0 + d0*w0)
 	double w2;
+	int corpus_on;                  // as K1Params
+	K2Params corpus;
 };
 int kq_tile_evals(int variant);
 cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cudaStream_t st);

@@ -796,7 +796,12 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	if ((rc = begin_score(e, C))) return rc;
 	// one launch per call: the corpus scan (K2) rides on an extra warp of every scoring CTA and the last CTA
 	// finalises (K3) when there is a single rank
-	const bool fuse = wants_corpus(e, o) && count > 0 && getenv("APO_NO_FUSE") == nullptr;
+	// ... when the scan can hide behind the scoring stream: one warp per SM scans ~3 records/us (measured: 10 M
+	// records in 3.35 ms on 148 SMs), the scoring kernel streams ~7.4 GB/ms (Form D / R) or ~5 GB/ms (Form Q)
+	const double k1_ms = (double)C * (double)count * (o->source == APO_SRC_ROLLOUTS ? (double)e->roll_row : (e->compact ? 14.0 : 36.0)) /
+	                     (o->source == APO_SRC_DIMS && e->compact ? 5.0e9 : 7.4e9);
+	const double scan_ms = (double)e->corpus_T * 3.35e-7 * (148.0 / (double)e->sm_count);
+	const bool fuse = wants_corpus(e, o) && count > 0 && k1_ms > 1.3 * scan_ms && getenv("APO_NO_FUSE") == nullptr;
 	if (fuse) {
 		if ((rc = arm_corpus(e, C))) return rc;
 		const apo::K2Params k2 = make_k2(e, C, make_fin(e, C, o->K, 1));

@@ -58,7 +58,7 @@ def test_sharded_score_equals_single_gpu(tmp_path, engine, orc, world, layout):
         assert z["avg"][0] == ref.report.avgReward
         for p in range(6):
             assert list(z["pat"][p]) == [ref.report.pat[p].count, *ref.report.pat[p].examples]
-        assert z["launches"][0] == 3                 # K1 (+ the corpus scan on its extra warp), ncclAllReduce, K3
+        assert z["launches"][0] in (3, 4)            # K1 (+ corpus scan when it can hide behind it, else K2), ncclAllReduce, K3
     # and the single-GPU result itself is pinned to the oracle on a window
     d = orc.gen_dims(SEED, 3, 1, 0, 50_000, 300, 8)
     engine.score(C, 1, first=0, count=50_000)

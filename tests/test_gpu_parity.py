@@ -494,3 +494,28 @@ def test_incremental_scoring_session(engine, orc):
         assert (r.report.total, r.report.bad, r.report.withReward) == (ref.total, ref.bad, ref.withReward)
         assert [r.report.pat[p].count for p in range(6)] == [ref.pat[p].count for p in range(6)]
         assert np.array_equal(r.topk, orc.topk(orc.score_dims(dims[:, :hi])[0], 3))
+
+
+def test_fused_and_standalone_corpus_paths_agree(engine, orc, monkeypatch):
+    """The corpus scan rides inside the scoring kernel when it can hide behind it (large C*T), otherwise it is
+    the stand-alone K2 launch; both must produce the identical report, for Form D, Form Q and Form R."""
+    seed, C, T, Tc = 0x5EED000B, 24, 300_000, 40_000          # 24 x 300k x 36 B = 0.26 GB: fused (scan of 40k records hides)
+    recs = orc.gen_records(seed, orc.STREAM_CORPUS, 0, 1, 0, Tc, 300, 8).reshape(-1)
+    ref = orc.report(recs)
+    engine.corpus_upload(recs)
+    for layout in ("fp32", "compact", "records"):
+        if layout == "records":
+            engine.rollouts_generate(seed, 0, C, 0, T, 300)
+            src = 1
+        else:
+            (engine.dims_generate if layout == "fp32" else engine.dims_generate_compact)(seed, 0, C, 0, T, 300)
+            src = 0
+        a = engine.score(C, 4, source=src, corpus=True)
+        assert a.timing.launches == 1, layout                   # K1 + K2 + K3 in one launch
+        monkeypatch.setenv("APO_NO_FUSE", "1")
+        b = engine.score(C, 4, source=src, corpus=True)
+        monkeypatch.delenv("APO_NO_FUSE")
+        assert b.timing.launches == 2
+        check_report(a.report, ref)
+        check_report(b.report, ref)
+        assert np.array_equal(a.scores, b.scores) and np.array_equal(a.topk, b.topk)

@@ -801,7 +801,8 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	const double k1_ms = (double)C * (double)count * (o->source == APO_SRC_ROLLOUTS ? (double)e->roll_row : (e->compact ? 14.0 : 36.0)) /
 	                     (o->source == APO_SRC_DIMS && e->compact ? 5.0e9 : 7.4e9);
 	const double scan_ms = (double)e->corpus_T * 3.35e-7 * (148.0 / (double)e->sm_count);
-	const bool fuse = wants_corpus(e, o) && count > 0 && k1_ms > 1.3 * scan_ms && getenv("APO_NO_FUSE") == nullptr;
+	const bool fuse = wants_corpus(e, o) && count > 0 && getenv("APO_NO_FUSE") == nullptr &&
+	                  (k1_ms > 1.3 * scan_ms || getenv("APO_FORCE_FUSE") != nullptr);      // env switches: tests / experiments
 	if (fuse) {
 		if ((rc = arm_corpus(e, C))) return rc;
 		const apo::K2Params k2 = make_k2(e, C, make_fin(e, C, o->K, 1));

@@ -29,6 +29,10 @@ for v in range(5):
     assert e.debug_partials(C) == exp
 ref = orc.report(recs)
 assert [r.report.pat[p].count for p in range(6)] == [ref.pat[p].count for p in range(6)]
+os.environ["APO_FORCE_FUSE"] = "1"            # the corpus scan inside the scoring launch (K1, then K1q / K1r below)
+r = e.score(C, 3, corpus=True)
+assert r.timing.launches == 1 and e.debug_partials(C) == exp
+assert [r.report.pat[p].count for p in range(6)] == [ref.pat[p].count for p in range(6)] and list(r.report.pat[0].examples) == list(ref.pat[0].examples)
 e.score(C, 2, first=1000, count=3001)
 assert e.debug_partials(C) == orc.score_dims_fx(dims[:, 1000:4001])
 e.dims_compact()
@@ -37,14 +41,15 @@ for v in range(4):
     assert e.debug_partials(C) == exp
 assert np.array_equal(np.nan_to_num(e.dims_download(2, 0, T), nan=7), np.nan_to_num(dims[2], nan=7))
 e.dims_generate_compact(seed, 0, C, 0, T, 400)
-e.score(C, 1)
-assert e.debug_partials(C) == exp
+r = e.score(C, 1, corpus=True)
+assert r.timing.launches == 1 and e.debug_partials(C) == exp and r.report.bad == ref.bad
 e.rollouts_upload(roll)
 e.score(C, 2, source=1)
 assert e.debug_partials(C) == orc.score_records_fx(roll)
 e.rollouts16_upload(pkg.pack16(roll))
-e.score(C, 2, source=1)
-assert e.debug_partials(C) == orc.score_records_fx(roll)
+r = e.score(C, 2, source=1, corpus=True)
+assert r.timing.launches == 1 and e.debug_partials(C) == orc.score_records_fx(roll) and r.report.bad == ref.bad
+os.environ.pop("APO_FORCE_FUSE")
 e.score_host(dims, 2)
 assert e.debug_partials(C) == exp
 e.score_host_records(pkg.pack16(roll), 2)

@@ -34,13 +34,13 @@ __device__ __forceinline__ uint32_t find_or_insert(uint32_t *s_slots, uint32_t *
 	uint32_t h = (bits * 2654435761u) >> 24;                 // 0..255
 	if (h == 255) h = 0;
 	for (int probe = 0; probe < 255; probe++) {
-		uint32_t cur = s_slots[h];
+		uint32_t cur = atomicOr(&s_slots[h], 0u);                // atomic read of this CTA's copy (slots only go EMPTY -> value)
 		if (cur == bits) return h;
 		if (cur == SLOT_EMPTY) {
-			// not in this CTA's copy: consult / claim the global slot
+			// not in this CTA's copy: consult / claim the global slot, then publish the global truth locally
 			cur = atomicCAS(&g_slots[h], SLOT_EMPTY, bits);
 			if (cur == SLOT_EMPTY) cur = bits;
-			s_slots[h] = cur;                                 // benign race: every writer stores the global truth
+			atomicAnd(&s_slots[h], cur);                             // EMPTY is all ones: AND installs the value, idempotent
 			if (cur == bits) return h;
 		}
 		h = h == 254 ? 0 : h + 1;

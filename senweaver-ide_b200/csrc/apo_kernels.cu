@@ -1,16 +1,17 @@
 // apo_kernels.cu — sm_100a kernels of the APO scoring engine.
 //
-//   K1  reward9        Form D (fp32 dims[C][T][9], 36 B/eval)  -> per-candidate exact partial sums
-//   K1r reward9_raw    Form R (apo_record per (c,t), 32 B/eval) -> same, dims derived on device
-//   K2  detect6        corpus records[T]: 6-pattern scan + tallies + per-dimension sums
-//                      (+ fused segmented sum / radix top-K in the last CTA at 1 rank)
-//   K3  finalize       segmented sum + radix top-K after the allreduce (> 1 rank)
-//   gen_* / reward_batch: generators and the single-trace path
+//   K1  k_reward9<36>     Form D (fp32 dims[C][T][9], 36 B/eval)  -> per-candidate exact partial sums
+//   K1r k_reward9<32|16>  Form R / R16 records per (c,t) -> same, dims derived on device (TCS:668-763)
+//   K2  corpus scan       records[T]: 6-pattern scan + tallies + per-dimension sums (apo_corpus.cuh):
+//                         one extra warp of every K1 CTA, or the stand-alone k_detect6 launch
+//   K3  finalize          segmented sum + radix top-K: last CTA of the scoring launch (1 rank), or
+//                         k_finalize after the allreduce (> 1 rank)
+//   k_gen_* / k_reward_batch: generators and the single-trace path
+//   (K1q, the Form Q kernel, lives in apo_compact.cu)
 //
-// All of them are HBM-bound integer/fp64 streaming kernels: no tensor cores on this path.
-// K1/K1r move tiles with 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) through an
-// mbarrier full/empty ring fed by a dedicated producer warp; consumers read the staged
-// tile with conflict-free LDS.128.
+// HBM-bound integer/fp64 streaming: no tensor cores on this path.  K1/K1r move tiles with 1-D
+// TMA bulk copies (cp.async.bulk -> SASS UBLKCP) through an mbarrier full/empty ring fed by a
+// dedicated producer warp; consumers read the staged tile with conflict-free LDS.128.
 #include <cstdlib>
 #include "apo_device.cuh"
 #include "apo_format.h"
@@ -37,7 +38,6 @@ struct K1Cfg {
 	static_assert(STAGE_BYTES % 16 == 0, "bulk copies are multiples of 16 bytes");
 };
 
-// One Form-D evaluation: 9 fp32 (NaN = absent) -> fixed-point finalReward.
 // One Form-D evaluation, first half: 9 fp32 (NaN = absent) -> weighted sum in push order and
 // the LUT entry {total weight, reciprocal} of its presence mask (TCS:777-783).
 __device__ __forceinline__ void eval_ws(const float (&v)[APO_NDIM], const Weights &W, const double2 *lut,

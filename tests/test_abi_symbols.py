@@ -71,3 +71,26 @@ def test_ts_codec_offsets_match_the_c_structs(apo):
     src = open(os.path.join(ROOT, "ts", "traceRecordCodec.ts")).read()
     for token in ("224 + 32 * i", "512 + 40 * p", "160 + 8 * m", "40 + 24 * m", "u64(v, 752)", "v.getFloat64(776, true)", "784"):
         assert token in src, token
+
+
+def _build_c_demo(apo, tmp_path):
+    import subprocess
+    apo.build_library()
+    exe = str(tmp_path / "score_demo")
+    lib_dir = os.path.dirname(apo.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "score_demo.c"),
+                           "-L", lib_dir, "-lapo_b200", f"-Wl,-rpath,{lib_dir}", "-lm", "-o", exe])
+    return exe
+
+
+def test_plain_c_client_links_against_the_abi(apo, tmp_path):
+    """examples/score_demo.c: pure C11, linked against libapo_b200.so; without a GPU it must fail loudly (exit 2)."""
+    import subprocess
+    import torch
+    exe = _build_c_demo(apo, tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "top-4:" in r.stdout and "K > C -> rc=-1" in r.stdout
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stdout

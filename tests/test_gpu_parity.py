@@ -519,3 +519,16 @@ def test_fused_and_standalone_corpus_paths_agree(engine, orc, monkeypatch):
         check_report(a.report, ref)
         check_report(b.report, ref)
         assert np.array_equal(a.scores, b.scores) and np.array_equal(a.topk, b.topk)
+
+
+def test_plain_c_client_runs(engine, apo, tmp_path):
+    """examples/score_demo.c (pure C11 against the .so) on the GPU: top-K sorted, error convention honoured."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "score_demo")
+    lib_dir = os.path.dirname(apo.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "score_demo.c"),
+                           "-L", lib_dir, "-lapo_b200", f"-Wl,-rpath,{lib_dir}", "-lm", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "layout=2" in r.stdout and "K > C -> rc=-1" in r.stdout

@@ -532,3 +532,28 @@ def test_plain_c_client_runs(engine, apo, tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "layout=2" in r.stdout and "K > C -> rc=-1" in r.stdout
+
+
+def test_scores_are_closer_to_the_exact_mean_than_the_sequential_sum(engine, orc):
+    """the fixed-point accumulation is at least as accurate as the reference's own
+    sequential binary64 sum.  Exact rational mean of the per-evaluation finalRewards as the yardstick."""
+    from fractions import Fraction
+    C, T = 2, 120_000
+    dims = orc.gen_dims(0x5EED000C, 0, C, 0, T, 300, 8)
+    engine.dims_upload(dims)
+    res = engine.score(C, 1)
+    seq, counts = orc.score_dims(dims)
+    w = orc.weights()
+    import ctypes
+    for c in range(C):
+        exact = Fraction(0)
+        out = ctypes.c_double()
+        for t in range(T):
+            row = np.ascontiguousarray(dims[c, t])
+            if orc.lib().orc_final_reward_f32(row.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p), ctypes.addressof(out)):
+                exact += Fraction(out.value)
+        exact /= int(counts[c])
+        err_gpu = abs(Fraction(float(res.scores[c])) - exact)
+        err_seq = abs(Fraction(float(seq[c])) - exact)
+        assert err_gpu <= err_seq + Fraction(1, 2**60), (float(err_gpu), float(err_seq))
+        assert err_gpu < Fraction(1, 2**50)

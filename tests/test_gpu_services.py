@@ -184,3 +184,66 @@ def test_beam_search_round_driver(services):
     scores = [b["score"] for b in st["beam"]]
     assert scores == sorted(scores, reverse=True) and st["historyBestScore"] >= scores[0]
     assert st["historyBestPrompt"]["content"].count("good") >= 1
+
+
+def test_storage_round_trip_and_trace_cap(engine):
+    """Persisted JSON under the reference's storage keys (TCS:216-217) reloads into an equivalent service;
+    more than MAX_TRACES traces are trimmed to the newest 1000 by startTime on save (TCS:337-345)."""
+    tcmod = import_module("senweaver-ide_b200.trace_collector")
+    store = {}
+    tc = tcmod.TraceCollectorService(engine, storageService=store)
+    drive(tc, random.Random(11), n_threads=30)
+    tc._dirty = True
+    tc._saveToStorage()
+    assert set(store) >= {"senweaver.traceCollector.data", "senweaver.traceCollector.feedbacks"}
+    tc2 = tcmod.TraceCollectorService(engine, storageService=store)
+    a, b = tc.getStats(), tc2.getStats()
+    for k in ("totalTraces", "totalSpans", "goodFeedbacks", "badFeedbacks", "totalToolCalls", "totalToolSucceeded",
+              "totalToolFailed", "toolSuccessRate", "tracesWithReward"):
+        assert a[k] == b[k], k
+    assert abs(a["avgFinalReward"] - b["avgFinalReward"]) < 1e-12
+    # cap
+    for i in range(tcmod.MAX_TRACES + 25):
+        tid = tc.startTrace(f"cap-{i}")
+        tc._traces[tid]["startTime"] = 1e12 + i
+    tc._saveToStorage()
+    assert len(tc.getAllTraces()) == tcmod.MAX_TRACES
+    assert min(t["startTime"] for t in tc.getAllTraces()) >= 1e12 + 25
+
+
+def test_span_cap_keeps_counting(engine):
+    """Past 200 spans the span object is dropped but the counters keep advancing (TCS:274-280, 505-510)."""
+    tcmod = import_module("senweaver-ide_b200.trace_collector")
+    tc = tcmod.TraceCollectorService(engine)
+    tc.startTrace("t", {"chatMode": "agent"})
+    for i in range(260):
+        tc.recordToolCall("t", i, {"toolName": "x", "toolSuccess": i % 10 != 0, "duration": 5.0})
+    tr = tc.getAllTraces()[0]
+    assert len(tr["spans"]) == tcmod.MAX_SPANS_PER_TRACE and tr["summary"]["totalToolCalls"] == 260
+    tc.endTraceForThread("t")
+    names = {d["name"]: d["value"] for d in tr["summary"]["rewardDimensions"]}
+    assert names["tool_call_efficiency"] == -0.8 and names["tool_call_reliability"] == -1.0      # agent thresholds: > 25 calls, >= 5 failures
+    assert names["tool_success_rate"] == (234 / 260) * 2 - 1
+
+
+def test_suggestion_lifecycle(services):
+    _, tc, apo = services
+    drive(tc, random.Random(5), n_threads=50)
+    rep = apo.analyzePromptEffectiveness()
+    pend = apo.getPendingSuggestions()
+    assert len(pend) == len(rep["suggestions"])
+    if pend:
+        s0 = pend[0]
+        s0["suggestedContent"] = "- always run the tests"
+        apo.applySuggestion(s0["id"])
+        assert "- always run the tests" in apo.getOptimizedRules() and apo.getStats()["appliedSuggestions"] == 1
+        apo.revertSuggestion(s0["id"])
+        assert "- always run the tests" not in apo.getOptimizedRules()
+        if len(pend) > 1:
+            apo.rejectSuggestion(pend[1]["id"])
+            assert apo.getStats()["rejectedSuggestions"] == 1
+    st = apo.getStats()
+    assert st["totalReports"] == 1 and st["currentGoodRate"] == rep["goodRate"]
+    cfg = apo.getConfig()
+    apo.setConfig({"beamWidth": 2})
+    assert apo.getConfig()["beamWidth"] == 2 and cfg["beamWidth"] == 4

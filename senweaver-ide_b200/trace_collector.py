@@ -28,6 +28,7 @@ MAX_TRACES = 1000                  # TCS:219
 MAX_SPANS_PER_TRACE = 200          # TCS:220
 TRACE_STORAGE_KEY = "senweaver.traceCollector.data"          # TCS:216
 TRACE_FEEDBACK_KEY = "senweaver.traceCollector.feedbacks"    # TCS:217
+TRACE_SCORED_KEY = "senweaver.traceCollector.scoredRecords"  # engine-side: hex Form R snapshot per scored trace
 MODE_CODE = {"normal": 1, "agent": 2, "gather": 3, "designer": 4}
 FB_CODE = {None: 0, "good": 1, "bad": 2}
 U32 = 0xFFFFFFFF
@@ -94,6 +95,11 @@ class TraceCollectorService:
             for t in json.loads(self._storage.get(TRACE_STORAGE_KEY, "[]")):
                 self._traces[t["id"]] = t
             self._feedbacks.update(json.loads(self._storage.get(TRACE_FEEDBACK_KEY, "{}")))
+            # the Form R snapshot each stored finalReward was computed from (engine-side key, not a reference key):
+            # without it a reloaded trace would be re-encoded from counters that kept moving after the reward was set
+            for tid, hx in json.loads(self._storage.get(TRACE_SCORED_KEY, "{}")).items():
+                if tid in self._traces:
+                    self._scored[tid] = np.frombuffer(bytes.fromhex(hx), dtype=RECORD_DTYPE).copy()
         except Exception as e:                      # TCS:311 warn and continue
             print("[TraceCollector] Failed to load from storage:", e)
 
@@ -104,9 +110,11 @@ class TraceCollectorService:
             if len(self._traces) > MAX_TRACES:      # keep the newest MAX_TRACES by startTime (TCS:337-345)
                 keep = sorted(self._traces.values(), key=lambda t: -(t.get("startTime") or 0))[:MAX_TRACES]
                 self._traces = {t["id"]: t for t in keep}
+                self._scored = {k: v for k, v in self._scored.items() if k in self._traces}
             if self._storage is not None:
                 self._storage[TRACE_STORAGE_KEY] = json.dumps(list(self._traces.values()))
                 self._storage[TRACE_FEEDBACK_KEY] = json.dumps(self._feedbacks)
+                self._storage[TRACE_SCORED_KEY] = json.dumps({k: v.tobytes().hex() for k, v in self._scored.items()})
             self._dirty = False
         except Exception as e:
             print("[TraceCollector] Failed to save to storage:", e)

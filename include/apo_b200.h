@@ -137,6 +137,23 @@ int apo_corpus_upload(apo_engine *e, const apo_record *recs, uint64_t T, uint64_
 int apo_corpus_generate(apo_engine *e, uint64_t seed, uint64_t t0, uint64_t T, uint32_t agent_permille);
 int apo_corpus_download(apo_engine *e, apo_record *out, uint64_t first, uint64_t n);
 
+/* ---- ingest: the reference's persisted traces -> Form R ----------
+ * json = the value TraceCollectorService._saveToStorage writes under
+ * 'senweaver.traceCollector.data' (TCS:296-359): JSON.stringify(ConversationTrace[]).  One record
+ * per trace in array order: counters from summary (TCS:94-108), ENDED from a truthy endTime
+ * (TCS:686), VALID from finalReward !== null (TCS:606), mode from metadata.chatMode (TCS:91),
+ * userMsgs/asstMsgs/FAILSPAN counted from the spans (TCS:752-753, APO:667-669).
+ * apo_records_from_json needs no engine and no GPU (format code only): returns the number of
+ * traces in the array (records beyond cap are counted, not written) or APO_E_ARG on malformed
+ * input, with the byte offset of the failure in *err_pos (may be NULL).
+ * apo_corpus_upload_json = parse + apo_corpus_upload(idx_base); *n_records (may be NULL) gets T.
+ * Note: the engine derives finalReward from the record.  A trace whose counters kept moving after
+ * its reward was set (endTraceForThread leaves the trace active, TCS:420-425) re-scores from the
+ * later counters; callers that need the stored value keep the record snapshot taken at scoring
+ * time (what the TraceCollectorService mirror does) and upload those with apo_corpus_upload. */
+int64_t apo_records_from_json(const char *json, uint64_t len, apo_record *out, uint64_t cap, uint64_t *err_pos);
+int apo_corpus_upload_json(apo_engine *e, const char *json, uint64_t len, uint64_t idx_base, uint64_t *n_records);
+
 /* ---- candidate x record evaluations ------------------------------------------------
  * Form D: fp32 dims[C][T][9], NaN = dimension absent, all-NaN = finalReward null.  Values are
  * expected within +-512 (the reference range is [-1,1], TCS:36): sums are exact fixed point.

@@ -108,6 +108,22 @@ static napi_value RewardBatch(napi_env env, napi_callback_info info) {
 	return out;
 }
 
+/* recordsFromJson(utf8:ArrayBuffer) -> ArrayBuffer of apo_record[T]
+ * utf8 = the string stored under 'senweaver.traceCollector.data' (TCS:296-359), encoded with TextEncoder.
+ * Host-side format code (apo_records_from_json); linear in the input, no GPU work. */
+static napi_value RecordsFromJson(napi_env env, napi_callback_info info) {
+	size_t argc = 1; napi_value argv[1], out;
+	napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+	void *text; size_t bytes; uint64_t pos = 0;
+	napi_get_arraybuffer_info(env, argv[0], &text, &bytes);
+	int64_t n = apo_records_from_json((const char *)text, bytes, NULL, 0, &pos);
+	if (n < 0) { napi_throw_error(env, "APO_E_ARG", "malformed trace JSON"); return NULL; }
+	void *recs;
+	napi_create_arraybuffer(env, (size_t)n * sizeof(apo_record), &recs, &out);
+	apo_records_from_json((const char *)text, bytes, (apo_record *)recs, (uint64_t)n, &pos);
+	return out;
+}
+
 /* ---- score(handle, {dims:ArrayBuffer, C, T, corpus:ArrayBuffer|null, K}) -> Promise<{scores,counts,topk,report}> ---- */
 typedef struct {
 	apo_engine *e; napi_deferred deferred; napi_async_work work; napi_ref keep_dims, keep_corpus;
@@ -172,6 +188,7 @@ NAPI_MODULE_INIT() {
 	const napi_property_descriptor props[] = {
 	    {"create", NULL, Create, NULL, NULL, NULL, napi_default, NULL},
 	    {"rewardBatch", NULL, RewardBatch, NULL, NULL, NULL, napi_default, NULL},
+	    {"recordsFromJson", NULL, RecordsFromJson, NULL, NULL, NULL, napi_default, NULL},
 	    {"score", NULL, Score, NULL, NULL, NULL, napi_default, NULL},
 	};
 	napi_define_properties(env, exports, sizeof props / sizeof props[0], props);

@@ -287,3 +287,46 @@ def dims_vector(trace: dict) -> list[float]:
     """rewardDimensions -> 9-vector in push order, NaN = absent."""
     by = {d["name"]: d["value"] for d in trace["summary"]["rewardDimensions"]}
     return [by.get(n, math.nan) for n in DIM_ORDER]
+
+
+TRICKY = ['plain', 'He said "type":"user_message" twice', 'back\\slash at end\\', 'quote at end\\"', '{"toolSuccess":false}',
+          'unicode é中\U0001F600 and \t tab \n newline', '', '[]]]{{{', '\\\\"', 'a' * 700]
+
+
+def persisted_form(trace: dict, rng, idx: int = 0) -> dict:
+    """The object JSON.stringify would see for this trace (TCS:83-109, spans TCS:30-81): ids, timestamps, message
+    previews and tool payloads added around the fields the scoring path reads.  Member order is shuffled (JSON objects
+    are unordered; a parser must not depend on it) and the free-text fields carry text that looks like structure."""
+    def text():
+        return rng.choice(TRICKY)
+    spans = []
+    for k, sp in enumerate(trace["spans"]):
+        data = dict(sp["data"])
+        if sp["type"] == "tool_call":
+            data.update(toolName=rng.choice(["read_file", "run_command", 'we"ird']), toolParams={"uri": text(), "nested": {"type": "user_message", "a": [1, {"toolSuccess": False}]}},
+                        toolResult=text())
+        else:
+            data.update(content=text(), role="user" if sp["type"] == "user_message" else "assistant")
+        full = {"id": f"s{idx}-{k}", "traceId": f"trace-{idx}", "threadId": trace["threadId"], "messageIdx": k, "type": sp["type"],
+                "timestamp": 1.7e12 + k + 0.25, "data": data}
+        if sp["type"] == "tool_call" and rng.random() < 0.7:
+            full["duration"] = rng.choice([0, 12.5, 1e3, 2.5e-3])
+        items = list(full.items())
+        rng.shuffle(items)
+        spans.append(dict(items))
+    for extra in range(rng.choice([0, 0, 1, 3])):                       # span types the scoring path ignores
+        spans.insert(rng.randint(0, len(spans)), {"id": f"x{extra}", "type": rng.choice(["llm_call", "error", "feedback", "tool_result"]), "traceId": f"trace-{idx}",
+                                                   "threadId": trace["threadId"], "messageIdx": 0, "timestamp": 1.0, "data": {"errorMessage": text(), "toolSuccess": False}})
+    out = {"id": f"trace-{idx}", "threadId": trace["threadId"], "startTime": 1.7e12 + idx, "spans": spans,
+           "summary": dict(trace["summary"], toolCallsByName={"read_file": 2, text(): 1})}
+    if trace.get("endTime"):
+        out["endTime"] = 1.7e12 + idx + 5.5
+    elif rng.random() < 0.3:
+        out["endTime"] = rng.choice([0, None])                            # falsy forms of `trace.endTime` (TCS:686)
+    if trace.get("metadata") is not None:
+        out["metadata"] = dict(trace["metadata"], modelName=text(), providerName="p")
+    elif rng.random() < 0.5:
+        out["metadata"] = rng.choice([None, {}, {"modelName": "m"}])
+    items = list(out.items())
+    rng.shuffle(items)
+    return dict(items)

@@ -14,6 +14,7 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <vector>
 
 #include "../../include/apo_b200.h"
 #include "apo_format.h"
@@ -535,6 +536,27 @@ extern "C" int apo_corpus_upload(apo_engine *e, const apo_record *recs, uint64_t
 	CK(cudaStreamSynchronize(e->stream));
 	e->corpus_T = T; e->corpus_base = idx_base;
 	return APO_OK;
+}
+
+extern "C" int apo_corpus_upload_json(apo_engine *e, const char *json, uint64_t len, uint64_t idx_base, uint64_t *n_records) {
+	if (!e) return APO_E_ARG;
+	if (!json) return fail(e, APO_E_ARG, "json is NULL");
+	std::vector<apo_record> recs;
+	uint64_t pos = 0;
+	int64_t n;
+	try {
+		recs.resize(len / 256 + 16);                      // a persisted trace is never shorter than ~300 bytes
+		n = apo_records_from_json(json, len, recs.data(), recs.size(), &pos);
+		if (n >= 0 && uint64_t(n) > recs.size()) {
+			recs.resize(size_t(n));
+			n = apo_records_from_json(json, len, recs.data(), recs.size(), &pos);
+		}
+	} catch (const std::bad_alloc &) {
+		return fail(e, APO_E_NOMEM, "host allocation for %llu bytes of JSON failed", (unsigned long long)len);
+	}
+	if (n < 0) return fail(e, APO_E_ARG, "malformed trace JSON at byte %llu", (unsigned long long)pos);
+	if (n_records) *n_records = uint64_t(n);
+	return apo_corpus_upload(e, recs.data(), uint64_t(n), idx_base);
 }
 
 extern "C" int apo_corpus_generate(apo_engine *e, uint64_t seed, uint64_t t0, uint64_t T, uint32_t agent_permille) {

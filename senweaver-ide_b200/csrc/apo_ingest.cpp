@@ -1,0 +1,251 @@
+// Ingest: the reference's persisted trace array -> Form R records.
+//
+// Input is what TraceCollectorService._saveToStorage writes under the storage key
+// 'senweaver.traceCollector.data' (TCS:296-359): JSON.stringify(ConversationTrace[]), each trace
+// {id, threadId, startTime, endTime?, spans:[TraceSpan], metadata?:{chatMode?..}, summary:{..}}
+// (TCS:83-109, span TCS:30-81).  Output is one apo_record per trace, in array order (= corpus order,
+// the order the pattern examples of APO:635-773 are reported in).
+//
+// Host-side format code only: one pass, no allocation per token, no DOM.  The scoring itself never
+// runs here — the records go to apo_corpus_upload / apo_rollouts_upload.
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/apo_b200.h"
+
+namespace {
+
+struct Cur {
+	const char *p, *end, *base;
+	bool ok = true;
+	void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
+	bool eat(char c) { ws(); if (p < end && *p == c) { ++p; return true; } return false; }
+	bool peek(char c) { ws(); return p < end && *p == c; }
+	void bad() { ok = false; }
+};
+
+// A JSON string; returns a view of the raw (still escaped) bytes.  Keys and the enum-like values this
+// parser compares against contain no escapes in what JSON.stringify emits, so raw comparison is exact.
+struct Str { const char *s; size_t n; bool is(const char *lit) const { return n == strlen(lit) && memcmp(s, lit, n) == 0; } };
+
+bool parse_string(Cur &c, Str &out) {
+	c.ws();
+	if (c.p >= c.end || *c.p != '"') { c.bad(); return false; }
+	const char *s = ++c.p;
+	while (c.p < c.end) {
+		const char *q = static_cast<const char *>(memchr(c.p, '"', size_t(c.end - c.p)));
+		if (!q) break;
+		// count the backslashes directly before the quote: an odd run escapes it
+		size_t bs = 0;
+		for (const char *b = q; b > s && b[-1] == '\\'; --b) ++bs;
+		c.p = q + 1;
+		if ((bs & 1) == 0) { out = {s, size_t(q - s)}; return true; }
+	}
+	c.bad();
+	return false;
+}
+
+enum Kind { K_NULL, K_TRUE, K_FALSE, K_NUM, K_STR, K_OBJ, K_ARR };
+struct Val { Kind k; double num; Str str; };
+
+bool skip_value(Cur &c, int depth);
+
+// Parses a scalar fully; for containers stops just before '{' / '['.
+bool parse_head(Cur &c, Val &v) {
+	c.ws();
+	if (c.p >= c.end) { c.bad(); return false; }
+	char ch = *c.p;
+	if (ch == '{') { v.k = K_OBJ; return true; }
+	if (ch == '[') { v.k = K_ARR; return true; }
+	if (ch == '"') { v.k = K_STR; return parse_string(c, v.str); }
+	auto lit = [&](const char *w, Kind k) {
+		size_t n = strlen(w);
+		if (size_t(c.end - c.p) >= n && memcmp(c.p, w, n) == 0) { c.p += n; v.k = k; return true; }
+		c.bad();
+		return false;
+	};
+	if (ch == 't') return lit("true", K_TRUE);
+	if (ch == 'f') return lit("false", K_FALSE);
+	if (ch == 'n') return lit("null", K_NULL);
+	if (ch == '-' || (ch >= '0' && ch <= '9')) {
+		char buf[64];
+		size_t n = 0;
+		const char *q = c.p;
+		while (q < c.end && n < sizeof buf - 1 && (*q == '-' || *q == '+' || *q == '.' || *q == 'e' || *q == 'E' || (*q >= '0' && *q <= '9'))) buf[n++] = *q++;
+		buf[n] = 0;
+		char *e = nullptr;
+		v.num = strtod(buf, &e);
+		if (e == buf) { c.bad(); return false; }
+		c.p += (e - buf);
+		v.k = K_NUM;
+		return true;
+	}
+	c.bad();
+	return false;
+}
+
+bool skip_container(Cur &c, int depth) {
+	if (depth > 256) { c.bad(); return false; }
+	if (c.eat('{')) {
+		if (c.eat('}')) return true;
+		do {
+			Str k;
+			if (!parse_string(c, k) || !c.eat(':') || !skip_value(c, depth + 1)) { c.bad(); return false; }
+		} while (c.eat(','));
+		if (!c.eat('}')) { c.bad(); return false; }
+		return true;
+	}
+	if (c.eat('[')) {
+		if (c.eat(']')) return true;
+		do { if (!skip_value(c, depth + 1)) return false; } while (c.eat(','));
+		if (!c.eat(']')) { c.bad(); return false; }
+		return true;
+	}
+	c.bad();
+	return false;
+}
+
+bool skip_value(Cur &c, int depth) {
+	Val v;
+	if (!parse_head(c, v)) return false;
+	return (v.k == K_OBJ || v.k == K_ARR) ? skip_container(c, depth) : true;
+}
+
+// Calls fn(key, cursor-at-value) for every member of the object at the cursor; fn must consume the value.
+template <class F> bool each_member(Cur &c, F fn) {
+	if (!c.eat('{')) { c.bad(); return false; }
+	if (c.eat('}')) return true;
+	do {
+		Str k;
+		if (!parse_string(c, k) || !c.eat(':')) { c.bad(); return false; }
+		if (!fn(k) || !c.ok) return false;
+	} while (c.eat(','));
+	if (!c.eat('}')) { c.bad(); return false; }
+	return true;
+}
+
+bool truthy(const Val &v) {          // JS truthiness of a parsed scalar (containers are always truthy)
+	switch (v.k) {
+	case K_NULL: case K_FALSE: return false;
+	case K_NUM: return v.num != 0.0 && v.num == v.num;
+	case K_STR: return v.str.n != 0;
+	default: return true;
+	}
+}
+
+uint32_t to_u32(const Val &v) {      // counters are non-negative integers held in JS doubles
+	if (v.k != K_NUM || !(v.num > 0.0)) return 0;
+	return v.num >= 4294967295.0 ? 0xFFFFFFFFu : uint32_t(v.num);
+}
+
+struct SpanInfo { int type = 0; bool tool_failed = false; };   // type: 1 user_message, 2 assistant_message, 3 tool_call
+
+bool parse_span(Cur &c, SpanInfo &si) {
+	return each_member(c, [&](const Str &k) {
+		Val v;
+		if (k.is("type")) {
+			if (!parse_head(c, v)) return false;
+			if (v.k == K_STR) si.type = v.str.is("user_message") ? 1 : v.str.is("assistant_message") ? 2 : v.str.is("tool_call") ? 3 : 0;
+			else if (v.k == K_OBJ || v.k == K_ARR) return skip_container(c, 2);
+			return true;
+		}
+		if (k.is("data") && c.peek('{')) {
+			return each_member(c, [&](const Str &dk) {
+				Val dv;
+				if (!parse_head(c, dv)) return false;
+				if (dv.k == K_OBJ || dv.k == K_ARR) return skip_container(c, 3);
+				if (dk.is("toolSuccess") && dv.k == K_FALSE) si.tool_failed = true;   // === false, APO:668
+				return true;
+			});
+		}
+		return skip_value(c, 2);
+	});
+}
+
+bool parse_trace(Cur &c, apo_record &r) {
+	memset(&r, 0, sizeof r);
+	uint32_t user = 0, asst = 0;
+	bool failspan = false, ended = false, valid = false, errors = false;
+	bool ok = each_member(c, [&](const Str &k) {
+		Val v;
+		if (k.is("endTime")) {
+			if (!parse_head(c, v)) return false;
+			if (v.k == K_OBJ || v.k == K_ARR) { ended = true; return skip_container(c, 1); }
+			ended = truthy(v);                                                   // `trace.endTime && ...` TCS:686
+			return true;
+		}
+		if (k.is("spans") && c.peek('[')) {
+			c.eat('[');
+			if (c.eat(']')) return true;
+			do {
+				SpanInfo si;
+				if (c.peek('{')) { if (!parse_span(c, si)) return false; }
+				else if (!skip_value(c, 1)) return false;
+				if (si.type == 1) ++user;
+				else if (si.type == 2) ++asst;
+				else if (si.type == 3 && si.tool_failed) failspan = true;
+			} while (c.eat(','));
+			if (!c.eat(']')) { c.bad(); return false; }
+			return true;
+		}
+		if (k.is("metadata") && c.peek('{')) {
+			return each_member(c, [&](const Str &mk) {
+				Val mv;
+				if (!parse_head(c, mv)) return false;
+				if (mv.k == K_OBJ || mv.k == K_ARR) return skip_container(c, 2);
+				if (mk.is("chatMode") && mv.k == K_STR)                           // TCS:91, APO:627-633
+					r.mode = mv.str.is("normal") ? 1 : mv.str.is("agent") ? 2 : mv.str.is("gather") ? 3 : mv.str.is("designer") ? 4 : 0;
+				return true;
+			});
+		}
+		if (k.is("summary") && c.peek('{')) {
+			return each_member(c, [&](const Str &sk) {
+				Val sv;
+				if (!parse_head(c, sv)) return false;
+				if (sv.k == K_OBJ || sv.k == K_ARR) return skip_container(c, 2);   // toolCallsByName, rewardDimensions
+				if (sk.is("totalLLMCalls")) r.llmCalls = to_u32(sv);
+				else if (sk.is("totalToolCalls")) r.toolCalls = to_u32(sv);
+				else if (sk.is("totalTokens")) r.tokens = to_u32(sv);
+				else if (sk.is("toolCallsSucceeded")) r.toolSucc = to_u32(sv);
+				else if (sk.is("toolCallsFailed")) r.toolFail = to_u32(sv);
+				else if (sk.is("totalToolDurationMs")) r.toolDurMs = sv.k == K_NUM ? float(sv.num) : 0.f;
+				else if (sk.is("userFeedback")) r.feedback = sv.k == K_STR ? (sv.str.is("good") ? 1 : sv.str.is("bad") ? 2 : 0) : 0;
+				else if (sk.is("hasErrors")) errors = truthy(sv);
+				else if (sk.is("finalReward")) valid = sv.k == K_NUM;               // !== null, TCS:606 / APO:550
+				return true;
+			});
+		}
+		return skip_value(c, 1);
+	});
+	if (!ok) return false;
+	r.userMsgs = uint16_t(user > 65535u ? 65535u : user);
+	r.asstMsgs = uint16_t(asst > 65535u ? 65535u : asst);
+	r.flags = uint8_t((errors ? APO_F_ERRORS : 0) | (ended ? APO_F_ENDED : 0) | (valid ? APO_F_VALID : 0) | (failspan ? APO_F_FAILSPAN : 0));
+	return true;
+}
+
+}  // namespace
+
+extern "C" int64_t apo_records_from_json(const char *json, uint64_t len, apo_record *out, uint64_t cap, uint64_t *err_pos) {
+	if (err_pos) *err_pos = 0;
+	if (!json || (cap && !out)) return APO_E_ARG;
+	Cur c{json, json + len, json};
+	int64_t n = 0;
+	auto fail = [&]() -> int64_t { if (err_pos) *err_pos = uint64_t(c.p - c.base); return APO_E_ARG; };
+	if (!c.eat('[')) return fail();
+	if (!c.eat(']')) {
+		do {
+			apo_record r;
+			if (!c.peek('{')) { c.bad(); return fail(); }
+			if (!parse_trace(c, r) || !c.ok) return fail();
+			if (uint64_t(n) < cap) out[n] = r;
+			++n;
+		} while (c.eat(','));
+		if (!c.eat(']')) return fail();
+	}
+	c.ws();
+	if (c.p != c.end) return fail();
+	return n;
+}

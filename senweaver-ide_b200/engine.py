@@ -83,7 +83,7 @@ class ApoError(RuntimeError):
 ABI_SYMBOLS = (
     "apo_abi_version", "apo_create", "apo_destroy", "apo_last_error", "apo_set_stream", "apo_set_weights",
     "apo_get_weights", "apo_reward_batch", "apo_reward_one", "apo_corpus_upload", "apo_corpus_generate",
-    "apo_corpus_download", "apo_dims_upload", "apo_dims_generate", "apo_dims_download", "apo_dims_attach",
+    "apo_corpus_download", "apo_records_from_json", "apo_corpus_upload_json", "apo_dims_upload", "apo_dims_generate", "apo_dims_download", "apo_dims_attach",
     "apo_dims_compact", "apo_dims_generate_compact", "apo_dims_upload_compact", "apo_dims_layout",
     "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_rollouts16_upload",
     "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_score",
@@ -95,7 +95,7 @@ ABI_SYMBOLS = (
 def build_library(force: bool = False) -> str:
     """Compile csrc/ for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     csrc = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(csrc, f) for f in ("apo_kernels.cu", "apo_abi.cu", "apo_kernels.h", "apo_device.cuh")]
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h", ".cpp")) or f == "Makefile"]
     srcs.append(os.path.join(_HERE, "..", "include", "apo_b200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
@@ -163,14 +163,32 @@ def load_library() -> C.CDLL:
     L.apo_comm_destroy.argtypes = [vp]
     for name in ABI_SYMBOLS:
         f = getattr(L, name)
-        if name not in ("apo_destroy", "apo_last_error"):
+        if name not in ("apo_destroy", "apo_last_error", "apo_records_from_json"):
             f.restype = i32
+    L.apo_records_from_json.argtypes = [C.c_char_p, u64, vp, u64, C.POINTER(u64)]
+    L.apo_records_from_json.restype = C.c_int64
+    L.apo_corpus_upload_json.argtypes = [vp, C.c_char_p, u64, u64, C.POINTER(u64)]
     _lib = L
     return L
 
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def records_from_json(text: str | bytes) -> np.ndarray:
+    """apo_records_from_json: the reference's persisted trace array (TCS:296-359) -> Form R.  Host-side
+    format code of the C library; needs no GPU.  Raises ValueError with the byte offset on malformed input."""
+    L = load_library()
+    raw = text.encode() if isinstance(text, str) else text
+    pos = C.c_uint64(0)
+    n = L.apo_records_from_json(raw, len(raw), None, 0, C.byref(pos))
+    if n < 0:
+        raise ValueError(f"malformed trace JSON at byte {pos.value}")
+    out = np.zeros(n, RECORD_DTYPE)
+    if n:
+        L.apo_records_from_json(raw, len(raw), _p(out), n, C.byref(pos))
+    return out
 
 
 class ScoreResult:
@@ -235,6 +253,13 @@ class Engine:
     def corpus_upload(self, recs: np.ndarray, idx_base: int = 0):
         recs = np.ascontiguousarray(recs, RECORD_DTYPE).reshape(-1)
         self._ck(self._L.apo_corpus_upload(self._h, _p(recs), recs.shape[0], idx_base))
+
+    def corpus_upload_json(self, text: str | bytes, idx_base: int = 0) -> int:
+        """Persisted `senweaver.traceCollector.data` JSON -> Form R -> device corpus; returns T."""
+        raw = text.encode() if isinstance(text, str) else text
+        n = C.c_uint64(0)
+        self._ck(self._L.apo_corpus_upload_json(self._h, raw, len(raw), idx_base, C.byref(n)))
+        return n.value
 
     def corpus_generate(self, seed: int, t0: int, T: int, agent_permille: int = 300):
         self._ck(self._L.apo_corpus_generate(self._h, seed, t0, T, agent_permille))

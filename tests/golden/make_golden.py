@@ -79,6 +79,18 @@ def main():
          "dims_c5_t1000": oracle.gen_dims(0x5EED0003, 5, 1, 1000, 64, 300, 1).tobytes().hex()}
     with open(os.path.join(HERE, "generator_case.json"), "w") as f:
         json.dump(g, f, indent=0)
+    # ingest fixture: a persisted trace array (shape of TCS:296-359's JSON) and the Form R bytes it must encode to
+    rng = random.Random(0x1265)
+    persisted = []
+    for i in range(24):
+        t = ts.make_trace(*random_tuple(rng))
+        if i % 5:
+            ts.compute_reward_signals(t)
+        persisted.append(ts.persisted_form(t, rng, i))
+    fixture = {"json": json.dumps(persisted, separators=(",", ":"), ensure_ascii=False),
+               "records_hex": b"".join(ts.encode_record(t) for t in persisted).hex()}
+    with open(os.path.join(HERE, "persisted_traces.json"), "w") as f:
+        json.dump(fixture, f)
 
 
 if __name__ == "__main__":

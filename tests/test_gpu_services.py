@@ -247,3 +247,31 @@ def test_suggestion_lifecycle(services):
     cfg = apo.getConfig()
     apo.setConfig({"beamWidth": 2})
     assert apo.getConfig()["beamWidth"] == 2 and cfg["beamWidth"] == 4
+
+
+def test_persisted_json_ingest_feeds_the_corpus_scan(engine, orc):
+    """Storage JSON written by the collector -> apo_corpus_upload_json -> device corpus: same records as the
+    Python encoder, and the report over them equals the oracle's report of those records."""
+    tcmod = import_module("senweaver-ide_b200.trace_collector")
+    store = {}
+    tc = tcmod.TraceCollectorService(engine, storageService=store)
+    drive(tc, random.Random(21), n_threads=120)
+    tc._dirty = True
+    tc._saveToStorage()
+    text = store["senweaver.traceCollector.data"]
+    n = engine.corpus_upload_json(text)
+    traces = tc.getAllTraces()
+    assert n == len(traces)
+    want = tc.corpus_records(traces)                        # live counters, valid = finalReward !== null
+    got = engine.corpus_download(0, n)
+    assert got.tobytes() == want.tobytes()
+    engine.dims_upload(np.full((1, 4, 9), np.nan, np.float32))
+    rep = engine.score(1, 0, corpus=True).report
+    ref = orc.report(want)
+    assert (rep.total, rep.good, rep.bad, rep.none, rep.withReward) == (ref.total, ref.good, ref.bad, ref.none, ref.withReward)
+    assert rep.avgReward == pytest.approx(ref.avgReward, rel=1e-12)
+    for p in range(6):
+        assert (rep.pat[p].count, rep.pat[p].flag, list(rep.pat[p].examples)) == (ref.pat[p].count, ref.pat[p].flag, list(ref.pat[p].examples))
+    with pytest.raises(import_module("senweaver-ide_b200").ApoError) as ei:
+        engine.corpus_upload_json(text[:-5])
+    assert "malformed trace JSON at byte" in str(ei.value)

@@ -17,6 +17,7 @@ import { ApoScoreBlocks, IApoScoringService } from '../common/apoScoringService.
 interface ApoAddon {
 	create(device: number): unknown;
 	rewardBatch(handle: unknown, records: ArrayBuffer): { dims: ArrayBuffer; masks: ArrayBuffer; finals: ArrayBuffer };
+	recordsFromJson(utf8: ArrayBuffer): ArrayBuffer;
 	score(handle: unknown, dims: ArrayBuffer, C: number, T: number, corpus: ArrayBuffer | null, K: number):
 		Promise<{ scores: ArrayBuffer; counts: ArrayBuffer; topk: ArrayBuffer; report: ArrayBuffer }>;
 }
@@ -57,6 +58,12 @@ export class ApoScoringMainService implements IApoScoringService {
 		if (!this._addon) { throw new Error('apo_b200 addon not loaded'); }
 		const r = this._addon.rewardBatch(this._handle, ab(records));
 		return { dims: VSBuffer.wrap(new Uint8Array(r.dims)), masks: VSBuffer.wrap(new Uint8Array(r.masks)), finals: VSBuffer.wrap(new Uint8Array(r.finals)) };
+	}
+
+	async recordsFromJson(persisted: string): Promise<VSBuffer> {
+		await this._ready;
+		if (!this._addon) { throw new Error('apo_b200 addon not loaded'); }
+		return VSBuffer.wrap(new Uint8Array(this._addon.recordsFromJson(ab(VSBuffer.fromString(persisted)))));
 	}
 
 	async score(dims: VSBuffer, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks> {

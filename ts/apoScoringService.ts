@@ -32,6 +32,9 @@ export interface IApoScoringService {
 	isAvailable(): Promise<boolean>;
 	/** TraceCollectorService._computeRewardSignals for n packed records (apo_reward_batch). */
 	rewardBatch(records: VSBuffer): Promise<{ dims: VSBuffer; masks: VSBuffer; finals: VSBuffer }>;
+	/** The string stored under 'senweaver.traceCollector.data' -> packed Form R records (apo_records_from_json):
+	 *  lets a stored corpus reach the engine without materialising ConversationTrace objects. */
+	recordsFromJson(persisted: string): Promise<VSBuffer>;
 	/** Corpus report (APOService._buildReport numeric content) + candidate scores / top-K.
 	 *  dims: float32[C][T][9] with NaN = dimension absent (pass C = 1, T = 4 of NaN for report-only calls). */
 	score(dims: VSBuffer, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks>;
@@ -50,6 +53,7 @@ export class ApoScoringService implements IApoScoringService {
 
 	isAvailable(): Promise<boolean> { return this._proxy.isAvailable(); }
 	rewardBatch(records: VSBuffer) { return this._proxy.rewardBatch(records); }
+	recordsFromJson(persisted: string) { return this._proxy.recordsFromJson(persisted); }
 	score(dims: VSBuffer, C: number, T: number, corpus: VSBuffer | undefined, K: number) { return this._proxy.score(dims, C, T, corpus, K); }
 }
 

@@ -108,9 +108,20 @@ bool skip_container(Cur &c, int depth) {
 }
 
 bool skip_value(Cur &c, int depth) {
+	c.ws();
+	if (c.p < c.end) {
+		const char ch = *c.p;
+		if (ch == '"') { Str s; return parse_string(c, s); }
+		if (ch == '{' || ch == '[') return skip_container(c, depth);
+		if (ch == '-' || (ch >= '0' && ch <= '9')) {          // a skipped number needs its extent, not its value
+			const char *q = c.p + 1;
+			while (q < c.end && ((*q >= '0' && *q <= '9') || *q == '.' || *q == 'e' || *q == 'E' || *q == '+' || *q == '-')) ++q;
+			c.p = q;
+			return true;
+		}
+	}
 	Val v;
-	if (!parse_head(c, v)) return false;
-	return (v.k == K_OBJ || v.k == K_ARR) ? skip_container(c, depth) : true;
+	return parse_head(c, v);                                  // true / false / null, or an error
 }
 
 // Calls fn(key, cursor-at-value) for every member of the object at the cursor; fn must consume the value.

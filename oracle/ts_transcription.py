@@ -330,3 +330,33 @@ def persisted_form(trace: dict, rng, idx: int = 0) -> dict:
     items = list(out.items())
     rng.shuffle(items)
     return dict(items)
+
+
+def upload_summaries(new_traces: list[dict]) -> dict:
+    """TCS:805-845 + 860-873: rewardSummary and toolCallSummary of uploadToServer, statement by statement."""
+    with_reward = [t for t in new_traces if t["summary"]["finalReward"] is not None]
+    avg = None
+    if with_reward:
+        acc = 0
+        for t in with_reward:
+            acc = acc + (t["summary"]["finalReward"] or 0)
+        avg = acc / len(with_reward)
+    succ = fail = dur = 0
+    by_name: dict = {}
+    for t in new_traces:
+        succ += t["summary"]["toolCallsSucceeded"]
+        fail += t["summary"]["toolCallsFailed"]
+        dur += t["summary"]["totalToolDurationMs"]
+        for name, st in t["summary"]["toolCallsByName"].items():
+            g = by_name.setdefault(name, {"total": 0, "succeeded": 0, "failed": 0})
+            g["total"] += st["total"]; g["succeeded"] += st["succeeded"]; g["failed"] += st["failed"]
+    agg: dict = {}
+    for t in with_reward:
+        for d in t["summary"]["rewardDimensions"]:
+            a = agg.setdefault(d["name"], {"sum": 0, "count": 0})
+            a["sum"] += d["value"]; a["count"] += 1
+    return {"rewardSummary": {"totalTracesWithReward": len(with_reward), "avgFinalReward": avg,
+                              "rewardDimensionAvg": {k: (v["sum"] / v["count"] if v["count"] > 0 else 0) for k, v in agg.items()}},
+            "toolCallSummary": {"totalToolCalls": succ + fail, "totalSucceeded": succ, "totalFailed": fail,
+                                "successRate": succ / (succ + fail) if succ + fail > 0 else None,
+                                "totalDurationMs": dur, "byToolName": by_name}}

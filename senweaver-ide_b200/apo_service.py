@@ -23,6 +23,7 @@ import uuid
 import numpy as np
 
 from .engine import DIM_NAMES, MODE_NAMES, SRC_DIMS, SRC_ROLLOUTS, Engine
+from .jsfmt import js_substring, js_to_fixed
 from .trace_collector import TraceCollectorService
 
 APO_STORAGE_KEY, APO_CONFIG_KEY, APO_SEGMENTS_KEY = "senweaver.apo.data", "senweaver.apo.config", "senweaver.apo.segments"
@@ -314,8 +315,7 @@ class APOService:
             if self._request is None:
                 print("[APO] Server optimization request failed: no request service")
                 return []
-            reply = self._request(f"{self._apoApiUrl}/optimize", {"version": "2.0.0", "report": self._reports[-1],
-                                  "beamConfig": {k: self._config[k] for k in ("beamWidth", "branchFactor", "beamRounds")}}) or {}
+            reply = self._request(f"{self._apoApiUrl}/optimize", self.buildOptimizePayload()) or {}
             sugg = reply.get("suggestions") or []
             for s in sugg:
                 s["id"] = s.get("id") or str(uuid.uuid4())
@@ -330,6 +330,59 @@ class APOService:
 
     def requestTextualGradient(self):
         return None                                                           # LLM critique lives on the backend (APO:1268-1343)
+
+    # ---- candidate-generation hooks: the two prompts of the textual-gradient loop ----------
+    NO_RULES = "(No optimized prompt rules currently active)"
+
+    @staticmethod
+    def _experiment_block(i, r):
+        """One '--- Experiment i ---' block, field for field and digit for digit as APO:926-941
+        (toFixed(3) reward, toFixed(0) percent and milliseconds, toFixed(2) dims, 200-unit message previews)."""
+        status = {"succeeded": "\u2705 Succeeded", "failed": "\u274c Failed"}.get(r["status"], "\u2753 Unknown")
+        reward = "N/A" if r["finalReward"] is None else js_to_fixed(r["finalReward"], 3)
+        msgs = "\n    ".join(f"[{m['role']}] {js_substring(m['content'], 0, 200)}" for m in r["messages"])
+        tc = r["toolCallStats"]
+        if tc["totalCalls"] > 0:
+            rate = "N/A" if tc["successRate"] is None else js_to_fixed(tc["successRate"] * 100, 0) + "%"
+            tool = (f"Tool Calls: {tc['totalCalls']} ({tc['succeeded']} succeeded, {tc['failed']} failed, rate: {rate}, "
+                    f"duration: {js_to_fixed(tc['totalDurationMs'], 0)}ms)")
+        else:
+            tool = "Tool Calls: none"
+        dims = ("Reward Dims: " + ", ".join(f"{d['name']}={js_to_fixed(d['value'], 2)}" for d in r["rewardDimensions"])) if r["rewardDimensions"] else ""
+        llm = f"LLM Calls: {r['llmStats']['totalCalls']}, Tokens: {r['llmStats']['totalTokens']}"
+        return (f"--- Experiment {i + 1} ---\nStatus: {status}\nFinal Reward: {reward}\nChat Mode: {r['chatMode']}\n{tool}\n{llm}\n{dims}\n"
+                f"Messages:\n    {msgs}")
+
+    def _buildTextualGradientPrompt(self, currentPromptRules, rolloutResults):
+        """APO:918-962 ("textual gradient": critique the current rules from sample runs).  The section layout and
+        the experiment blocks follow the reference; the instruction prose is this build's own wording."""
+        rules = "\n".join(currentPromptRules) if currentPromptRules else self.NO_RULES
+        experiments = "\n\n".join(self._experiment_block(i, r) for i, r in enumerate(rolloutResults))
+        return ("You are an expert prompt engineer improving the system prompt of a coding-IDE assistant.\n\n"
+                f"## Current Prompt Rules\n{rules}\n\n## Sample Runs with Current Prompt\n{experiments}\n\n"
+                "## Your Task\nWrite a short critique: name the specific causes of the failures above and what would raise the reward "
+                "next time.\nAnswer with a bullet list of concrete, testable changes (format, constraints, ordering, definitions), looking at:\n"
+                "1. Structure: missing goals, contradictions, absent stop conditions\n"
+                "2. Instruction quality: vague verbs, no hierarchy, overlapping scope\n"
+                "3. Control and behaviour: tool limits, handling of uncertainty, verbosity\n"
+                "4. Input/output specification: missing defaults, inconsistent formats\n"
+                "5. Scope and safety: scope creep, unsafe actions, error handling\n\n"
+                "Be direct. Fewer than 350 words.")
+
+    def _buildApplyEditPrompt(self, currentPromptRules, critique):
+        """APO:966-988 ("apply edit": rewrite the rules under the critique); reply format `- rule` per line, which is
+        what _applyBeamBestPrompt splits on (APO:1226-1229)."""
+        rules = "\n".join(currentPromptRules) if currentPromptRules else self.NO_RULES
+        return ("Revise the prompt rules below, treating the critique as both constraint and guide.\n\n"
+                "## Revision Rules\n"
+                "1. Rewrite or restructure the prompt where the critique calls for it.\n"
+                "2. State any requested output format, structure or word limit explicitly.\n"
+                "3. Put the mechanism first: what to do, then how.\n"
+                "4. Stay close to the original in tone, length and structure.\n"
+                "5. Concentrate on the single most important issue raised.\n\n"
+                f"## Current Prompt Rules\n{rules}\n\n## Critique\n{critique}\n\n"
+                "Return only the improved prompt rules, without explanations or headers.\n"
+                'Each rule goes on its own line and starts with "- ".')
 
     # ---- wire formats after the path (SURVEY 8f rank 2) ---------------------------------------------------
     def _convertTracesToRolloutResults(self, traces):
@@ -383,7 +436,9 @@ class APOService:
                     e = by.setdefault(name, {"total": 0, "succeeded": 0, "failed": 0})
                     for k in e:
                         e[k] += st[k]
-            succ, fail = int(rep.toolSucc), int(rep.toolFail)
+            self._engine.corpus_upload(self._tc.corpus_records(recent))           # tool totals read the live counters (APO:1081-1084)
+            live = self._engine.score(1, 0, corpus=True).report
+            succ, fail = int(live.toolSucc), int(live.toolFail)
             tool_summary = {"totalCalls": succ + fail, "totalSucceeded": succ, "totalFailed": fail,
                             "successRate": succ / (succ + fail) if succ + fail > 0 else None,
                             "totalDurationMs": sum(r["toolCallStats"]["totalDurationMs"] for r in rollouts), "byToolName": by}
@@ -394,6 +449,7 @@ class APOService:
                 "rolloutResults": rollouts[:20],
                 "currentSegments": [{"id": s["id"], "category": s["category"], "content": s["content"][:1000],
                                      "isOptimized": s["isOptimized"], "version": s["version"]} for s in self.getActiveSegments()],
+                "textualGradientPrompt": self._buildTextualGradientPrompt(self.getOptimizedRules(), rollouts[: self._config["gradientBatchSize"]]),
                 "beamConfig": {k: self._config[k] for k in ("beamWidth", "branchFactor", "beamRounds")},
                 "beamState": None if st is None else {"currentRound": st["currentRound"], "historyBestScore": st["historyBestScore"],
                                                       "beamSize": len(st["beam"])},

@@ -28,6 +28,8 @@ MAX_TRACES = 1000                  # TCS:219
 MAX_SPANS_PER_TRACE = 200          # TCS:220
 TRACE_STORAGE_KEY = "senweaver.traceCollector.data"          # TCS:216
 TRACE_FEEDBACK_KEY = "senweaver.traceCollector.feedbacks"    # TCS:217
+UPLOADED_IDS_KEY = "senweaver.traceCollector.uploadedIds"     # TCS:795
+UPLOAD_CONFIG_KEY = "senweaver.traceCollector.uploadConfig"   # TCS:317
 TRACE_SCORED_KEY = "senweaver.traceCollector.scoredRecords"  # engine-side: hex Form R snapshot per scored trace
 MODE_CODE = {"normal": 1, "agent": 2, "gather": 3, "designer": 4}
 FB_CODE = {None: 0, "good": 1, "bad": 2}
@@ -75,6 +77,8 @@ class TraceCollectorService:
         self._autoUploadConfig = {"enabled": False, "intervalMs": 300000}              # TCS:792
         self._uploadedIds: set[str] = set()
         self._loadFromStorage()
+        self._loadUploadConfig()
+        self._loadUploadedIds()
 
     # ---- events
     def onDidChangeState(self, listener):
@@ -306,30 +310,96 @@ class TraceCollectorService:
         self._saveToStorage()
         self._fire()
 
-    # ---- backend upload (TCS:797-898): payload assembly only; HTTP goes through the injected request service
+    # ---- backend upload (TCS:797-898): payload assembly; HTTP goes through the injected request service
     def uploadToServer(self):
         try:
-            new = [t for t in self._traces.values() if t["id"] not in self._uploadedIds]
+            new = [t for t in self._traces.values() if t["id"] not in self._uploadedIds]     # incremental (TCS:800)
             if not new:
                 return {"success": True, "message": "No new traces to upload", "uploadedCount": 0}
+            payload = self.buildUploadPayload(new)
             if self._request is None:
-                return {"success": False, "message": "no request service configured", "uploadedCount": 0}
-            self._engine.corpus_upload(self.corpus_records(new, scored=True))
-            self._engine.dims_upload(np.full((1, 4, 9), np.nan, np.float32))
-            rep = self._engine.score(1, 0, corpus=True).report
-            payload = {"version": "2.0.0", "traces": new, "rewardSummary": {
-                "totalWithReward": int(rep.withReward), "avgFinalReward": None if rep.withReward == 0 else float(rep.avgReward),
-                "rewardDimensionAvg": {DIM_NAMES[i]: float(rep.dim[i].avg) for i in range(9) if rep.dim[i].count}}}
-            ok = self._request(self._traceApiUrl, payload)
-            if ok:
-                self._uploadedIds.update(t["id"] for t in new)
-            return {"success": bool(ok), "message": "uploaded" if ok else "upload failed", "uploadedCount": len(new) if ok else 0}
-        except Exception as e:                          # TCS:894-898
+                raise RuntimeError("no request service configured")
+            resp = self._request(self._traceApiUrl, payload)
+            status = resp.get("statusCode") if isinstance(resp, dict) else (resp if isinstance(resp, int) and not isinstance(resp, bool) else (200 if resp else 500))
+            if status and status >= 400:                                                     # TCS:881-883
+                return {"success": False, "message": f"Server returned {status}", "uploadedCount": 0}
+            self._uploadedIds.update(t["id"] for t in new)
+            self._saveUploadedIds()
+            return {"success": True, "message": "Upload successful", "uploadedCount": len(new)}
+        except Exception as e:                          # TCS:892-896
             print("[TraceCollector] Upload failed:", e)
-            return {"success": False, "message": str(e), "uploadedCount": 0}
+            return {"success": False, "message": f"Upload failed: {e}", "uploadedCount": 0}
 
-    def setAutoUploadConfig(self, config):
-        self._autoUploadConfig = {"enabled": bool(config.get("enabled")), "intervalMs": config.get("intervalMs") or self._autoUploadConfig["intervalMs"]}
+    def buildUploadPayload(self, new):
+        """The v2.0.0 body of TCS:846-873.  rewardSummary and the tool totals are reductions of the same records the
+        scoring path reads and run on the engine (reward from the records the rewards were computed from, tool totals
+        from the live counters, TCS:813-818); the string-keyed byToolName table and the duration total stay on the host."""
+        nan_dims = np.full((1, 4, 9), np.nan, np.float32)
+        self._engine.corpus_upload(self.corpus_records(new))
+        self._engine.dims_upload(nan_dims)
+        live = self._engine.score(1, 0, corpus=True).report
+        self._engine.corpus_upload(self.corpus_records(new, scored=True))
+        rep = self._engine.score(1, 0, corpus=True).report
+        by_name, duration = {}, 0
+        for t in new:
+            duration += t["summary"]["totalToolDurationMs"]
+            for name, st in t["summary"]["toolCallsByName"].items():
+                g = by_name.setdefault(name, {"total": 0, "succeeded": 0, "failed": 0})
+                for k in g:
+                    g[k] += st[k]
+        threads = {t["threadId"] for t in new}
+        succ, fail = int(live.toolSucc), int(live.toolFail)
+        return {
+            "version": "2.0.0",
+            "uploadTime": time.strftime("%Y-%m-%dT%H:%M:%S.000Z", time.gmtime()),
+            "traces": new,
+            "feedbacks": {k: v for k, v in self._feedbacks.items() if k.split(":")[0] in threads},
+            "rewardSummary": {
+                "totalTracesWithReward": int(rep.withReward),
+                "avgFinalReward": None if rep.withReward == 0 else float(rep.avgReward),
+                "rewardDimensionAvg": {DIM_NAMES[i]: float(rep.dim[i].avg) for i in range(9) if rep.dim[i].count},
+            },
+            "toolCallSummary": {
+                "totalToolCalls": succ + fail, "totalSucceeded": succ, "totalFailed": fail,
+                "successRate": succ / (succ + fail) if succ + fail > 0 else None,
+                "totalDurationMs": duration, "byToolName": by_name,
+            },
+        }
+
+    def _loadUploadedIds(self):                          # TCS:939-947
+        try:
+            js = self._storage.get(UPLOADED_IDS_KEY) if self._storage else None
+            if js:
+                self._uploadedIds = set(json.loads(js))
+        except Exception:
+            pass
+
+    def _saveUploadedIds(self):                          # TCS:949-961: only ids that still exist
+        try:
+            self._uploadedIds = {i for i in self._uploadedIds if i in self._traces}
+            if self._storage is not None:
+                self._storage[UPLOADED_IDS_KEY] = json.dumps(sorted(self._uploadedIds))
+        except Exception:
+            pass
+
+    def _loadUploadConfig(self):                         # TCS:314-330
+        try:
+            js = self._storage.get(UPLOAD_CONFIG_KEY) if self._storage else None
+            if js:
+                cfg = json.loads(js)
+                iv = cfg.get("intervalMs")
+                self._autoUploadConfig = {"enabled": bool(cfg.get("enabled")), "intervalMs": 300000 if iv is None else iv}
+        except Exception:
+            pass
+
+    def setAutoUploadConfig(self, config):               # TCS:900-933 (the interval timer itself belongs to the host application)
+        iv = config.get("intervalMs")
+        self._autoUploadConfig = {"enabled": bool(config.get("enabled")), "intervalMs": 300000 if iv is None else iv}
+        try:
+            if self._storage is not None:
+                self._storage[UPLOAD_CONFIG_KEY] = json.dumps(self._autoUploadConfig)
+        except Exception:
+            pass
 
     def getAutoUploadConfig(self):
         return {**self._autoUploadConfig, "traceApiUrl": self._traceApiUrl}

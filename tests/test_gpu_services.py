@@ -1,6 +1,7 @@
 """TraceCollectorService / APOService mirrors driven the way the reference's callers drive them
 (CTS:1120-1738, 2745-2746; SidebarChat.tsx:4378), checked against the pure-Python transcription
 of the reference source (oracle/ts_transcription.py).  -m gpu: every reduction runs on the B200."""
+import json
 import math
 import random
 from importlib import import_module
@@ -275,3 +276,57 @@ def test_persisted_json_ingest_feeds_the_corpus_scan(engine, orc):
     with pytest.raises(import_module("senweaver-ide_b200").ApoError) as ei:
         engine.corpus_upload_json(text[:-5])
     assert "malformed trace JSON at byte" in str(ei.value)
+
+
+def test_upload_payload_matches_transcription(engine):
+    """uploadToServer (TCS:797-898): incremental selection, v2.0.0 body with rewardSummary / toolCallSummary from the
+    engine, uploaded ids persisted under the reference's key, HTTP status handling and messages."""
+    tcmod = import_module("senweaver-ide_b200.trace_collector")
+    sent, store = [], {}
+
+    def request(url, payload):
+        sent.append((url, payload))
+        return {"statusCode": 200}
+    tc = tcmod.TraceCollectorService(engine, storageService=store, productService=None, requestService=request)
+    assert tc.uploadToServer() == {"success": True, "message": "No new traces to upload", "uploadedCount": 0}
+    drive(tc, random.Random(33), n_threads=80)
+    res = tc.uploadToServer()
+    assert res == {"success": True, "message": "Upload successful", "uploadedCount": 80}
+    url, pay = sent[-1]
+    assert url == "https://ide-api.senweaver.com/api/traces" and pay["version"] == "2.0.0" and len(pay["traces"]) == 80
+    ref = ts.upload_summaries(pay["traces"])
+    assert pay["toolCallSummary"] == ref["toolCallSummary"]
+    rs, rr = pay["rewardSummary"], ref["rewardSummary"]
+    assert rs["totalTracesWithReward"] == rr["totalTracesWithReward"] and set(rs["rewardDimensionAvg"]) == set(rr["rewardDimensionAvg"])
+    assert rs["avgFinalReward"] == pytest.approx(rr["avgFinalReward"], rel=1e-12)
+    for k, v in rr["rewardDimensionAvg"].items():
+        assert rs["rewardDimensionAvg"][k] == pytest.approx(v, rel=1e-12, abs=1e-15)
+    threads = {t["threadId"] for t in pay["traces"]}
+    assert all(k.split(":")[0] in threads for k in pay["feedbacks"]) and len(pay["feedbacks"]) > 0
+    assert sorted(json.loads(store["senweaver.traceCollector.uploadedIds"])) == sorted(t["id"] for t in pay["traces"])
+    # nothing new -> nothing sent; a new trace -> only that one; a 5xx leaves it pending
+    assert tc.uploadToServer()["uploadedCount"] == 0 and len(sent) == 1
+    tc.startTrace("later")
+    tc._request = lambda url, payload: {"statusCode": 503}
+    assert tc.uploadToServer() == {"success": False, "message": "Server returned 503", "uploadedCount": 0}
+    tc._request = request
+    assert tc.uploadToServer()["uploadedCount"] == 1 and len(sent[-1][1]["traces"]) == 1
+    tc._request = lambda url, payload: (_ for _ in ()).throw(OSError("offline"))
+    tc.startTrace("later2")
+    assert tc.uploadToServer() == {"success": False, "message": "Upload failed: offline", "uploadedCount": 0}
+    # upload config persists under the reference's key
+    tc.setAutoUploadConfig({"enabled": True, "intervalMs": 1000})
+    tc2 = tcmod.TraceCollectorService(engine, storageService=store)
+    assert tc2.getAutoUploadConfig() == {"enabled": True, "intervalMs": 1000, "traceApiUrl": "https://ide-api.senweaver.com/api/traces"}
+    assert tc2.uploadToServer()["message"].startswith("Upload failed")      # no request service: one pending trace, reported as a failure
+
+
+def test_optimize_payload_carries_the_gradient_prompt(services):
+    _, tc, apo = services
+    drive(tc, random.Random(8), n_threads=60)
+    pay = apo.buildOptimizePayload()
+    assert pay["textualGradientPrompt"].count("--- Experiment ") == min(apo.getConfig()["gradientBatchSize"], len(pay["rolloutResults"]))
+    assert "## Current Prompt Rules\n(No optimized prompt rules currently active)" in pay["textualGradientPrompt"]
+    live_s = sum(r["toolCallStats"]["succeeded"] for r in apo._convertTracesToRolloutResults(
+        sorted([t for t in tc.getAllTraces() if t["summary"]["userFeedback"] is not None], key=lambda t: -t["startTime"])[:16]))
+    assert pay["toolCallSummary"]["totalSucceeded"] == live_s

@@ -318,7 +318,8 @@ def test_upload_payload_matches_transcription(engine):
     tc.setAutoUploadConfig({"enabled": True, "intervalMs": 1000})
     tc2 = tcmod.TraceCollectorService(engine, storageService=store)
     assert tc2.getAutoUploadConfig() == {"enabled": True, "intervalMs": 1000, "traceApiUrl": "https://ide-api.senweaver.com/api/traces"}
-    assert tc2.uploadToServer()["message"].startswith("Upload failed")      # no request service: one pending trace, reported as a failure
+    tc2.startTrace("fresh")
+    assert tc2.uploadToServer()["message"].startswith("Upload failed")      # no request service: reported as a failure, trace stays pending
 
 
 def test_optimize_payload_carries_the_gradient_prompt(services):

@@ -27,7 +27,8 @@ from .jsfmt import js_substring, js_to_fixed
 from .trace_collector import TraceCollectorService
 
 APO_STORAGE_KEY, APO_CONFIG_KEY, APO_SEGMENTS_KEY = "senweaver.apo.data", "senweaver.apo.config", "senweaver.apo.segments"
-MAX_REPORTS, MAX_SUGGESTIONS = 50, 200                                   # APO:276-277
+APO_BEAM_KEY, APO_GRADIENTS_KEY = "senweaver.apo.beamState", "senweaver.apo.gradients"   # APO:360,364
+MAX_REPORTS, MAX_SUGGESTIONS, MAX_GRADIENTS = 50, 200, 50                # APO:276-277, 405
 DEFAULT_APO_CONFIG = {                                                   # APO:279-292
     "enabled": True, "autoAnalyzeEnabled": True, "autoAnalyzeIntervalMs": 3600000, "minTracesForAnalysis": 20,
     "minFeedbacksForAnalysis": 10, "autoApplySuggestions": False, "uploadOptimizationsToServer": True,
@@ -57,6 +58,21 @@ def _first_preview(trace, type_):
     return ""
 
 
+def _js_constant(name):
+    return {"Infinity": math.inf, "-Infinity": -math.inf, "NaN": math.nan}[name]
+
+
+def _finite_or_none(obj):
+    """What JSON.stringify does to non-finite numbers (they become null), applied recursively."""
+    if isinstance(obj, float) and not math.isfinite(obj):
+        return None
+    if isinstance(obj, dict):
+        return {k: _finite_or_none(v) for k, v in obj.items()}
+    if isinstance(obj, list):
+        return [_finite_or_none(v) for v in obj]
+    return obj
+
+
 class APOService:
     def __init__(self, engine: Engine, traceCollectorService: TraceCollectorService, storageService=None,
                  productService=None, requestService=None):
@@ -69,6 +85,7 @@ class APOService:
         self._dirty = False
         api = (getattr(productService, "senweaverApiConfig", None) or {}).get("apiBaseUrl") if productService else None
         self._apoApiUrl = f"{api or 'https://ide-api.senweaver.com'}/api/apo"          # APO:328-329
+        self._loadFromStorage()
 
     # ---- events
     def onDidChangeState(self, fn):
@@ -88,8 +105,13 @@ class APOService:
     def analyzePromptEffectiveness(self):
         report = self._buildReport(self._tc.getAllTraces())
         self._reports.append(report)
-        self._reports = self._reports[-MAX_REPORTS:]
         self._dirty = True
+        self._saveToStorage()
+        if self._config["uploadOptimizationsToServer"] and self._request is not None:
+            try:                                                               # APO:1345-1356, silent on failure
+                self._request(f"{self._apoApiUrl}/report", {"version": "1.0.0", "report": report})
+            except Exception:
+                pass
         self._fire(self._stateListeners)
         return report
 
@@ -149,7 +171,7 @@ class APOService:
                 d = rew.dim[i]
                 if d.count and d.low_flag:
                     patterns.append({"id": str(uuid.uuid4()),
-                                     "description": f"{name} dimension reward signal consistently low (avg: {d.avg:.3f})",
+                                     "description": f"{name} dimension reward signal consistently low (avg: {js_to_fixed(d.avg, 3)})",
                                      "frequency": int(d.count), "severity": SEVERITY[d.low_severity],
                                      "relatedCategory": DIM_CATEGORY.get(name, "core_behavior"), "examples": []})
 
@@ -181,7 +203,7 @@ class APOService:
             return f"LLM calls: {s['totalLLMCalls']}"
         if p == 4:
             return f"Conversation turns: {sum(1 for sp in t['spans'] if sp['type'] == 'user_message')}"
-        return f"Tool duration: {s['totalToolDurationMs'] / 1000:.1f}s"
+        return f"Tool duration: {js_to_fixed(s['totalToolDurationMs'] / 1000, 1)}s"
 
     def _generateLocalSuggestions(self, goodRate, patterns, byMode, avgReward, rew):
         """APO:775-862: thresholds from the engine's flags, text on the host."""
@@ -192,15 +214,15 @@ class APOService:
                         "description": desc, "reasoning": why, "estimatedImpact": impact, "status": "pending"})
 
         if 0 < goodRate < 0.5:                                               # APO:785
-            extra = f" (avg reward: {avgReward:.3f})" if avgReward is not None else ""
-            add("core_behavior", "high", f"Overall approval rate is only {goodRate * 100:.1f}%{extra}; the prompt needs a broad revision",
+            extra = f" (avg reward: {js_to_fixed(avgReward, 3)})" if avgReward is not None else ""
+            add("core_behavior", "high", f"Overall approval rate is only {js_to_fixed(goodRate * 100, 1)}%{extra}; the prompt needs a broad revision",
                 "An approval rate under 50% points at a systemic prompt problem", "approval rate +10-20%")
         if rew is not None:
             for i, name in enumerate(DIM_NAMES):                             # APO:800-827
                 d = rew.dim[i]
                 if d.count and d.sugg_flag:
                     add(DIM_CATEGORY.get(name, "core_behavior"), SEVERITY[d.sugg_priority],
-                        f"{name} dimension performing poorly (avg: {d.avg:.3f}, n={d.count})",
+                        f"{name} dimension performing poorly (avg: {js_to_fixed(d.avg, 3)}, n={d.count})",
                         f"The {name} reward dimension is negative on average", f"{name} reward +0.2-0.5")
         for p in patterns:                                                   # APO:830-843
             if p["severity"] == "high":
@@ -209,7 +231,7 @@ class APOService:
         for mode, st in byMode.items():                                      # APO:846-859
             if st["total"] >= 5 and st["goodRate"] < 0.3:
                 o = {"id": str(uuid.uuid4()), "targetCategory": "mode_specific", "type": "modify", "priority": "medium",
-                     "description": f"{mode} mode approval rate is only {st['goodRate'] * 100:.1f}%",
+                     "description": f"{mode} mode approval rate is only {js_to_fixed(st['goodRate'] * 100, 1)}%",
                      "reasoning": "This mode is well below the average approval rate", "estimatedImpact": f"better {mode} mode approval",
                      "status": "pending"}
                 out.append(o)
@@ -277,11 +299,14 @@ class APOService:
             st["beam"] = bu["beam"]
         if bu.get("round") is not None:
             st["currentRound"] = bu["round"]
-        if bu.get("bestPrompt") and bu.get("bestScore") is not None and bu["bestScore"] > st["historyBestScore"]:   # APO:1159
+        # a beam state reloaded before its first score carries null here (JSON.stringify(-Infinity)); `x > null` compares with 0 in JS
+        incumbent = 0 if st["historyBestScore"] is None else st["historyBestScore"]
+        if bu.get("bestPrompt") and bu.get("bestScore") is not None and bu["bestScore"] > incumbent:                # strict, APO:1159
             st["historyBestPrompt"], st["historyBestScore"] = bu["bestPrompt"], bu["bestScore"]
             self._applyBeamBestPrompt(bu["bestPrompt"])
         st["lastUpdatedAt"] = now
         self._dirty = True
+        self._saveToStorage()
         self._fire(self._stateListeners)
 
     def _applyBeamBestPrompt(self, best):
@@ -329,7 +354,44 @@ class APOService:
             return []
 
     def requestTextualGradient(self):
-        return None                                                           # LLM critique lives on the backend (APO:1268-1343)
+        """APO:1268-1343: POST {apo}/gradient with both prompts and the gradientBatchSize most recent rated rollouts;
+        the reply's critique becomes a TextualGradient, its editedPrompt (if any) a pending high-priority suggestion."""
+        try:
+            recent = sorted([t for t in self._tc.getAllTraces() if t["summary"]["userFeedback"] is not None],
+                            key=lambda t: -t["startTime"])[: self._config["gradientBatchSize"]]
+            if len(recent) < 2:
+                return None
+            rollouts = self._convertTracesToRolloutResults(recent)
+            rules = self.getOptimizedRules()
+            payload = {"version": "2.0.0", "action": "textual_gradient",
+                       "textualGradientPrompt": self._buildTextualGradientPrompt(rules, rollouts),
+                       "applyEditPrompt": self._buildApplyEditPrompt(rules, "{{critique_placeholder}}"),
+                       "rolloutResults": rollouts, "currentRules": rules}
+            if self._request is None:
+                raise RuntimeError("no request service")
+            reply = self._request(f"{self._apoApiUrl}/gradient", payload)
+            if not isinstance(reply, dict) or (reply.get("statusCode") or 0) >= 400 or not reply.get("critique"):
+                return None
+            acc = 0
+            for r in rollouts:
+                acc = acc + (r["finalReward"] or 0)
+            best = (self._beamState or {}).get("historyBestPrompt") or {}
+            tg = {"id": str(uuid.uuid4()), "promptVersion": best.get("version") or "v0", "critique": reply["critique"],
+                  "rolloutSummary": f"Based on {len(rollouts)} rollouts, avg reward: {js_to_fixed(acc / len(rollouts), 3)}",
+                  "createdAt": time.time() * 1000.0}
+            self._textualGradients.append(tg)
+            if reply.get("editedPrompt"):
+                sug = {"id": str(uuid.uuid4()), "targetCategory": "core_behavior", "type": "modify", "priority": "high",
+                       "description": f"Textual Gradient: {js_substring(tg['critique'], 0, 100)}...", "suggestedContent": reply["editedPrompt"],
+                       "reasoning": tg["critique"], "estimatedImpact": "Prompt optimization based on Textual Gradient",
+                       "status": "pending", "promptVersion": tg["promptVersion"]}
+                self._suggestions.append(sug)
+                self._fire(self._suggestionListeners, [sug])
+            self._touched()
+            return tg
+        except Exception as e:
+            print("[APO] Textual gradient request failed:", e)
+            return None
 
     # ---- candidate-generation hooks (SURVEY 8f rank 3): the two prompts of the textual-gradient loop ----------
     NO_RULES = "(No optimized prompt rules currently active)"
@@ -461,8 +523,8 @@ class APOService:
         return [s for s in self._segments if s["isActive"]]
 
     def getOptimizedPromptForCategory(self, category):
-        segs = [s["content"] for s in self._segments if s["isActive"] and s["isOptimized"] and s["category"] == category]
-        return "\n".join(segs) if segs else None
+        seg = next((s for s in self._segments if s["isActive"] and s["isOptimized"] and s["category"] == category), None)
+        return (seg["content"] or None) if seg else None                       # first match only (APO:1364-1367)
 
     def getOptimizedRules(self):
         return [s["content"] for s in self._segments if s["isActive"] and s["isOptimized"]]
@@ -470,30 +532,64 @@ class APOService:
     def _find(self, sid):
         return next((s for s in self._suggestions if s["id"] == sid), None)
 
+    def _touched(self):
+        self._dirty = True
+        self._saveToStorage()
+        self._fire(self._stateListeners)
+
     def applySuggestion(self, suggestionId):
+        """APO:1375-1411: 'modify' rewrites the targeted (or first active same-category) segment and keeps the
+        original for revert; 'add' appends a new optimized segment; anything else only changes status."""
         s = self._find(suggestionId)
         if not s or s["status"] != "pending":
             return
+        now = time.time() * 1000.0
+        s["status"], s["appliedAt"] = "applied", now
         if s.get("suggestedContent"):
-            now = time.time() * 1000.0
-            self._segments.append({"id": str(uuid.uuid4()), "category": s["targetCategory"], "content": s["suggestedContent"],
-                                   "isActive": True, "isOptimized": True, "version": 1, "createdAt": now, "updatedAt": now,
-                                   "fromSuggestion": s["id"]})
-        s["status"], s["appliedAt"] = "applied", time.time() * 1000.0
-        self._fire(self._stateListeners)
+            if s.get("targetSegmentId"):
+                seg = next((g for g in self._segments if g["id"] == s["targetSegmentId"]), None)
+            else:
+                seg = next((g for g in self._segments if g["category"] == s["targetCategory"] and g["isActive"]), None)
+            if seg is not None and s.get("type") == "modify":
+                seg["originalContent"] = seg.get("originalContent") or seg["content"]
+                seg["content"], seg["isOptimized"] = s["suggestedContent"], True
+                seg["version"] += 1
+                seg["updatedAt"] = now
+            elif s.get("type") == "add":
+                self._segments.append({"id": str(uuid.uuid4()), "category": s["targetCategory"], "content": s["suggestedContent"],
+                                       "isActive": True, "isOptimized": True, "version": 1, "createdAt": now, "updatedAt": now})
+        self._touched()
 
     def rejectSuggestion(self, suggestionId):
         s = self._find(suggestionId)
-        if s and s["status"] == "pending":
-            s["status"] = "rejected"
-            self._fire(self._stateListeners)
+        if not s or s["status"] != "pending":
+            return
+        s["status"] = "rejected"
+        self._touched()
 
     def revertSuggestion(self, suggestionId):
+        """APO:1423-1458: restore the segment's original content (by id, else by category for 'modify'), or remove the
+        segment an 'add' created (matched by category + content)."""
         s = self._find(suggestionId)
-        if s and s["status"] == "applied":
-            self._segments = [g for g in self._segments if g.get("fromSuggestion") != s["id"]]
-            s["status"] = "reverted"
-            self._fire(self._stateListeners)
+        if not s or s["status"] != "applied":
+            return
+
+        def restore(seg):
+            if seg is not None and seg.get("originalContent"):
+                seg["content"] = seg["originalContent"]
+                seg.pop("originalContent", None)
+                seg["isOptimized"] = False
+                seg["version"] += 1
+                seg["updatedAt"] = time.time() * 1000.0
+        if s.get("targetSegmentId"):
+            restore(next((g for g in self._segments if g["id"] == s["targetSegmentId"]), None))
+        elif s.get("type") == "modify":
+            restore(next((g for g in self._segments if g["category"] == s["targetCategory"] and g["isActive"] and g["isOptimized"]), None))
+        elif s.get("type") == "add":
+            self._segments = [g for g in self._segments
+                              if not (g["category"] == s["targetCategory"] and g["isOptimized"] and g["content"] == s.get("suggestedContent"))]
+        s["status"] = "reverted"
+        self._touched()
 
     # ---- rule injection (SURVEY 8f rank 4): the consumer of getOptimizedRules in the system-prompt builder
     def packOptimizedRules(self, maxChars: int = 2000):
@@ -534,7 +630,7 @@ class APOService:
                 "activeSegments": len(self.getActiveSegments()),
                 "optimizedSegments": sum(1 for s in self._segments if s["isActive"] and s["isOptimized"]),
                 "lastAnalysisTime": last["generatedAt"] if last else None, "currentGoodRate": last["goodRate"] if last else None,
-                "beamSearchActive": st is not None and st["currentRound"] < st["totalRounds"],
+                "beamSearchActive": st is not None,                                  # APO:1502
                 "beamCurrentRound": st["currentRound"] if st else None,
                 "beamBestScore": st["historyBestScore"] if st and st["historyBestScore"] != -math.inf else None,
                 "totalTextualGradients": len(self._textualGradients),
@@ -543,15 +639,83 @@ class APOService:
     def getConfig(self):
         return dict(self._config)
 
-    def setConfig(self, config):
+    def setConfig(self, config):                                               # APO:1514-1526 (timers belong to the host application)
         self._config.update(config)
-        self._dirty = True
+        self._saveConfig()
+        self._fire(self._stateListeners)
 
     def getBeamState(self):
         return copy.deepcopy(self._beamState)
 
-    def getTextualGradients(self, limit=None):
-        return self._textualGradients[-(limit or 10):]
+    def getTextualGradients(self, limit=None):                                 # newest first (APO:1534-1537)
+        g = sorted(self._textualGradients, key=lambda t: -t["createdAt"])
+        return g[:limit] if limit else g
+
+    # ---- persistence (APO:336-413): same keys, same caps
+    def _loadFromStorage(self):
+        st = self._storage
+        if not st:
+            return
+        try:
+            if st.get(APO_CONFIG_KEY):
+                self._config = {**DEFAULT_APO_CONFIG, **json.loads(st[APO_CONFIG_KEY])}
+            if st.get(APO_STORAGE_KEY):
+                data = json.loads(st[APO_STORAGE_KEY])
+                self._reports, self._suggestions = data.get("reports") or [], data.get("suggestions") or []
+            if st.get(APO_SEGMENTS_KEY):
+                self._segments = json.loads(st[APO_SEGMENTS_KEY])
+            if st.get(APO_BEAM_KEY):
+                self._beamState = json.loads(st[APO_BEAM_KEY], parse_constant=_js_constant)
+            if st.get(APO_GRADIENTS_KEY):
+                self._textualGradients = json.loads(st[APO_GRADIENTS_KEY])
+        except Exception as e:
+            print("[APO] Failed to load from storage:", e)
+
+    def _saveToStorage(self):
+        if not self._dirty:
+            return
+        try:
+            self._reports = self._reports[-MAX_REPORTS:]
+            self._suggestions = self._suggestions[-MAX_SUGGESTIONS:]
+            if self._storage is not None:
+                self._storage[APO_STORAGE_KEY] = json.dumps({"reports": self._reports, "suggestions": self._suggestions})
+                self._storage[APO_SEGMENTS_KEY] = json.dumps(self._segments)
+                if self._beamState:
+                    # JSON.stringify(-Infinity) is null: a never-scored beam reloads with historyBestScore null (APO:388-392)
+                    self._storage[APO_BEAM_KEY] = json.dumps(_finite_or_none(self._beamState))
+                if self._textualGradients:
+                    self._textualGradients = self._textualGradients[-MAX_GRADIENTS:]
+                    self._storage[APO_GRADIENTS_KEY] = json.dumps(self._textualGradients)
+            self._dirty = False
+        except Exception as e:
+            print("[APO] Failed to save to storage:", e)
+
+    def _saveConfig(self):
+        try:
+            if self._storage is not None:
+                self._storage[APO_CONFIG_KEY] = json.dumps(self._config)
+        except Exception:
+            pass
+
+    def dispose(self):                                                         # APO:1539-1542
+        self._saveToStorage()
+
+    # ---- periodic analysis (APO:453-475): the host application's timer calls this
+    def _tryAutoAnalyze(self, now_ms=None):
+        c = self._config
+        if not c["enabled"] or not c["autoAnalyzeEnabled"]:
+            return None
+        stats = self._tc.getStats()
+        if stats["totalTraces"] < c["minTracesForAnalysis"] or stats["totalFeedbacks"] < c["minFeedbacksForAnalysis"]:
+            return None
+        now_ms = time.time() * 1000.0 if now_ms is None else now_ms
+        last = self.getLatestReport()
+        if last and now_ms - last["generatedAt"] < c["autoAnalyzeIntervalMs"]:
+            return None
+        report = self.analyzePromptEffectiveness()
+        if report["goodRate"] < 0.7 and c["uploadOptimizationsToServer"] and stats["totalFeedbacks"] >= 15:
+            self.requestTextualGradient()
+        return report
 
     def exportState(self):
         return json.dumps({"reports": self._reports, "suggestions": self._suggestions, "segments": self._segments,

@@ -235,7 +235,7 @@ def test_suggestion_lifecycle(services):
     assert len(pend) == len(rep["suggestions"])
     if pend:
         s0 = pend[0]
-        s0["suggestedContent"] = "- always run the tests"
+        s0["suggestedContent"], s0["type"] = "- always run the tests", "add"
         apo.applySuggestion(s0["id"])
         assert "- always run the tests" in apo.getOptimizedRules() and apo.getStats()["appliedSuggestions"] == 1
         apo.revertSuggestion(s0["id"])
@@ -331,3 +331,59 @@ def test_optimize_payload_carries_the_gradient_prompt(services):
     live_s = sum(r["toolCallStats"]["succeeded"] for r in apo._convertTracesToRolloutResults(
         sorted([t for t in tc.getAllTraces() if t["summary"]["userFeedback"] is not None], key=lambda t: -t["startTime"])[:16]))
     assert pay["toolCallSummary"]["totalSucceeded"] == live_s
+
+
+def test_apo_state_persists_and_gradient_flow(engine):
+    """APO storage keys (APO:273-275,360,364), suggestion modify/revert against an existing segment (APO:1375-1458), the
+    textual-gradient request (APO:1268-1343) and the auto-analyze gate (APO:453-475)."""
+    pkg = import_module("senweaver-ide_b200")
+    tcmod, apomod = import_module("senweaver-ide_b200.trace_collector"), import_module("senweaver-ide_b200.apo_service")
+    store, sent = {}, []
+
+    def request(url, payload):
+        sent.append((url, payload))
+        if url.endswith("/gradient"):
+            return {"statusCode": 200, "critique": "Rules lack a stop condition. " * 8, "editedPrompt": "- stop after two failed tool calls"}
+        return {"statusCode": 200}
+    tc = tcmod.TraceCollectorService(engine, storageService=store)
+    apo = apomod.APOService(engine, tc, storageService=store, requestService=request)
+    assert apo._tryAutoAnalyze() is None                               # too few traces
+    drive(tc, random.Random(77), n_threads=60)
+    rep = apo._tryAutoAnalyze()
+    assert rep is not None and sent[0][0].endswith("/api/apo/report") and sent[0][1]["version"] == "1.0.0"
+    assert apo._tryAutoAnalyze() is None                               # interval not elapsed
+    grads = apo.getTextualGradients()
+    if rep["goodRate"] < 0.7:
+        assert len(grads) == 1 and grads[0]["promptVersion"] == "v0" and grads[0]["rolloutSummary"].startswith("Based on 4 rollouts, avg reward: ")
+        url, pay = [x for x in sent if x[0].endswith("/gradient")][0]
+        assert pay["action"] == "textual_gradient" and len(pay["rolloutResults"]) == 4 and "{{critique_placeholder}}" in pay["applyEditPrompt"]
+    else:
+        apo.requestTextualGradient()
+    sug = [s for s in apo.getPendingSuggestions() if s["description"].startswith("Textual Gradient: ")][0]
+    assert sug["description"].endswith("...") and len(sug["description"]) == len("Textual Gradient: ") + 103
+    # modify with no segment of that category: status only (APO:1388-1406); then against an existing segment
+    apo.applySuggestion(sug["id"])
+    assert apo.getOptimizedRules() == [] and apo.getStats()["appliedSuggestions"] == 1
+    apo._segments.append({"id": "seg-1", "category": "core_behavior", "content": "be brief", "isActive": True, "isOptimized": False,
+                          "version": 1, "createdAt": 0, "updatedAt": 0})
+    s2 = dict(sug, id="s2", status="pending")
+    apo._suggestions.append(s2)
+    apo.applySuggestion("s2")
+    assert apo.getOptimizedRules() == ["- stop after two failed tool calls"] and apo._segments[0]["originalContent"] == "be brief"
+    assert apo.getOptimizedPromptForCategory("core_behavior") == "- stop after two failed tool calls"
+    apo.revertSuggestion("s2")
+    assert apo.getOptimizedRules() == [] and apo._segments[0]["content"] == "be brief" and apo._segments[0]["version"] == 3
+    # beam state + everything else survives a restart; -Infinity is stored as null and compares like 0 afterwards
+    apo._applyBeamUpdate({"beam": [{"version": "v1", "content": "- a", "score": -0.2}], "round": 1})
+    apo.setConfig({"beamWidth": 8})
+    apo.dispose()
+    assert {"senweaver.apo.data", "senweaver.apo.config", "senweaver.apo.segments", "senweaver.apo.beamState", "senweaver.apo.gradients"} <= set(store)
+    apo2 = apomod.APOService(engine, tc, storageService=store)
+    assert apo2.getConfig()["beamWidth"] == 8 and apo2.getStats()["totalReports"] == apo.getStats()["totalReports"]
+    assert apo2.getBeamState()["historyBestScore"] is None and apo2.getStats()["beamSearchActive"] is True
+    assert len(apo2.getTextualGradients()) == len(apo.getTextualGradients())
+    apo2._applyBeamUpdate({"bestPrompt": {"version": "v2", "content": "- b", "score": -0.1}, "bestScore": -0.1, "round": 2})
+    assert apo2.getBeamState()["historyBestPrompt"] is None             # -0.1 > null is false in JS
+    apo2._applyBeamUpdate({"bestPrompt": {"version": "v3", "content": "- c", "score": 0.1}, "bestScore": 0.1, "round": 3})
+    assert apo2.getBeamState()["historyBestPrompt"]["version"] == "v3" and "c" in " ".join(apo2.getOptimizedRules())
+    assert pkg is not None

@@ -92,7 +92,7 @@ struct apo_engine {
 	DevBuf<float> dims; const float *dims_ptr = nullptr; uint32_t dims_C = 0; uint64_t dims_T = 0, dims_pitch = 0;
 	// Form Q (compact) copy of the evaluations: replaces dims/dims_ptr when `compact` is set
 	DevBuf<unsigned long long> q8; DevBuf<float> qd2; DevBuf<unsigned short> qli; DevBuf<uint32_t> qbook;   // qbook: [8][256] codebook + [8] overflow flags
-	DevBuf<double> d_ptab; DevBuf<float> stage;
+	DevBuf<double> d_ptab, d_pair; DevBuf<float> stage, d_cbf; uint32_t q_n0 = 0, q_n1 = 0; bool q_pair_ok = false;
 	uint32_t qbook_host[8 * 256]; bool compact = false;
 	DevBuf<uint8_t> roll; uint32_t roll_C = 0, roll_row = 32; uint64_t roll_T = 0, roll_pitch = 0;   // Form R (32 B) or R16 (16 B) rows
 
@@ -195,6 +195,30 @@ int upload_ptab(apo_engine *e) {
 		}
 	CK(e->d_ptab.reserve(8 * 256));
 	CK(cudaMemcpyAsync(e->d_ptab.p, tab.data(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream));
+	// tables of the mixed-lookup variants: fp32 values per code, and the exact two-term prefix of dimensions 0 and 1
+	std::vector<float> cbf(8 * 256, 0.0f);
+	uint32_t used[8] = {0};
+	for (int j = 0; j < 8; j++)
+		for (int c = 0; c < 255; c++) {
+			const uint32_t bits = e->qbook_host[256 * j + c];
+			if (bits == 0xFFFFFFFFu) continue;
+			memcpy(&cbf[256 * j + c], &bits, 4);
+			used[j] = (uint32_t)c + 1;                                // dense codes: 0 .. used-1
+		}
+	e->q_n0 = used[0]; e->q_n1 = used[1];
+	e->q_pair_ok = (uint64_t)(used[0] + 1) * (used[1] + 1) <= (uint64_t)apo::KQ_PAIR_MAX;
+	std::vector<double> pair(apo::KQ_PAIR_MAX, 0.0);
+	if (e->q_pair_ok)
+		for (uint32_t a = 0; a <= used[0]; a++)
+			for (uint32_t b = 0; b <= used[1]; b++) {
+				volatile double s = tab[a < used[0] ? a : 255];           // fl(0 + d0*w0), +0.0 when absent
+				s = s + tab[256 + (b < used[1] ? b : 255)];               // + d1*w1 (TCS:781, second push)
+				pair[a * (used[1] + 1) + b] = s;
+			}
+	CK(e->d_cbf.reserve(8 * 256));
+	CK(e->d_pair.reserve(apo::KQ_PAIR_MAX));
+	CK(cudaMemcpyAsync(e->d_cbf.p, cbf.data(), 8 * 256 * 4, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaMemcpyAsync(e->d_pair.p, pair.data(), apo::KQ_PAIR_MAX * 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	return APO_OK;
 }
@@ -310,12 +334,19 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 		apo::KqParams Q{};
 		Q.q8 = e->q8.p + first; Q.d2 = e->qd2.p + first; Q.li = e->qli.p + first; Q.pitch_evals = e->dims_pitch; Q.C = C; Q.T = count;
 		Q.acc = e->acc.p + (uint64_t)ACC_PER_CAND * cand_offset; Q.lut = e->d_lut.p; Q.ptab = e->d_ptab.p; Q.w2 = e->W.w[2];
+		Q.pair = e->d_pair.p; Q.cbf = e->d_cbf.p; Q.n0 = e->q_n0; Q.n1 = e->q_n1;
+		{
+			static const int dim_of[8] = {0, 1, 3, 4, 5, 6, 7, 8};
+			for (int j = 0; j < 8; j++) Q.wq[j] = e->W.w[dim_of[j]];
+		}
+		int qvariant = (int)o->variant;
+		if (qvariant >= 4 && !e->q_pair_ok) qvariant = 0;           // prefix table would not fit: plain product tables
 		if (fused) { Q.corpus_on = 1; Q.corpus = *fused; }
 		if (e->k1_used + 2 > e->k1_ev.size()) {
 			for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
 		}
 		CK(cudaEventRecord(e->k1_ev[e->k1_used], e->stream));
-		CK(apo::run_reward9q(Q, (int)o->variant, (o->flags & APO_SCORE_RECIP) != 0, e->sm_count, e->stream));
+		CK(apo::run_reward9q(Q, qvariant, (o->flags & APO_SCORE_RECIP) != 0, e->sm_count, e->stream));
 		CK(cudaEventRecord(e->k1_ev[e->k1_used + 1], e->stream));
 		e->k1_used += 2;
 		e->timing.launches++;
@@ -464,7 +495,7 @@ extern "C" void apo_destroy(apo_engine *e) {
 	cudaSetDevice(e->device);
 	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	if (e->own_stream) cudaStreamSynchronize(e->own_stream);
-	e->q8.release(); e->qd2.release(); e->qli.release(); e->qbook.release(); e->d_ptab.release(); e->stage.release();
+	e->q8.release(); e->qd2.release(); e->qli.release(); e->qbook.release(); e->d_ptab.release(); e->d_pair.release(); e->d_cbf.release(); e->stage.release();
 	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->acc_joined.release(); e->misc.release();
 	e->result.release(); e->keys.release(); e->sel_key.release(); e->sel_idx.release();
 	e->win[0].release(); e->win[1].release(); e->batch_in.release(); e->batch_out.release(); e->batch_mask.release();

@@ -155,7 +155,9 @@ struct KqCfg {
 	static constexpr int STAGE_BYTES = Q8_BYTES + D2_BYTES + LI_BYTES;
 	static constexpr int LUT_OFF = STAGES * STAGE_BYTES;          // double2[512]
 	static constexpr int PTAB_OFF = LUT_OFF + 512 * 16;           // double[8][256]
-	static constexpr int CAT_OFF = PTAB_OFF + 8 * 256 * 8;        // categorical product table of the fused corpus scan
+	static constexpr int CBF_OFF = PTAB_OFF + 8 * 256 * 8;        // float[8][256] code -> value (mixed-lookup variants)
+	static constexpr int PAIR_OFF = CBF_OFF + 8 * 256 * 4;        // double[KQ_PAIR_MAX] exact prefix fl(fl(0 + d0*w0) + d1*w1)
+	static constexpr int CAT_OFF = PAIR_OFF + KQ_PAIR_MAX * 8;    // categorical product table of the fused corpus scan
 	static constexpr int BAR_OFF = CAT_OFF + CAT_WORDS * 8;
 	static constexpr int META_OFF = BAR_OFF + 2 * STAGES * 8;
 	static constexpr int EX_OFF = META_OFF + STAGES * 8;
@@ -181,7 +183,30 @@ __device__ __forceinline__ void evalq_ws(unsigned long long q, float d2f, uint32
 	valid = t_out.x > 0.0 ? 1u : 0u;
 }
 
-template <int CW, int EPT, int STAGES, bool RECIP>
+// Mixed-lookup form of the same evaluation.  The 8-byte product reads of evalq_ws cost two shared-memory
+// wavefronts each and that pipe is what bounds K1q; here dimensions 0 and 1 share one read of the exact
+// prefix table, and NF of the other six read the 4-byte value (one wavefront) and form value*weight with
+// the same F2F + DMUL the Form D kernel issues.  Every operation and its order are those of eval_ws.
+template <int NF>
+__device__ __forceinline__ void evalq_ws_mixed(unsigned long long q, float d2f, uint32_t idx, const double *ptab, const float *cbf,
+                                               const double *pair, uint32_t n0, uint32_t n1, const double (&wq)[8], double w2,
+                                               const double2 *lut, double &ws_out, double2 &t_out, uint32_t &valid) {
+	const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
+	const uint32_t c0 = min(lo & 255u, n0), c1 = min((lo >> 8) & 255u, n1);      // 255 (absent) -> last row / column
+	double ws = pair[c0 * (n1 + 1u) + c1];
+	ws = __dadd_rn(ws, __dmul_rn((double)d2f, w2));
+#pragma unroll
+	for (int j = 2; j < 8; j++) {
+		const uint32_t code = j < 4 ? ((lo >> (8 * j)) & 255u) : ((hi >> (8 * (j - 4))) & 255u);
+		if (j - 2 < NF) ws = __dadd_rn(ws, __dmul_rn((double)cbf[j * 256 + code], wq[j]));
+		else ws = __dadd_rn(ws, ptab[j * 256 + code]);
+	}
+	ws_out = ws;
+	t_out = lut[idx];
+	valid = t_out.x > 0.0 ? 1u : 0u;
+}
+
+template <int CW, int EPT, int STAGES, bool RECIP, int NF = -1>
 __global__ void __launch_bounds__((CW + 2) * 32, 1)
 k_reward9q(const KqParams P) {
 	using Cfg = KqCfg<CW, EPT, STAGES>;
@@ -192,12 +217,18 @@ k_reward9q(const KqParams P) {
 	uint64_t *empty = full + STAGES;
 	QMeta *meta = reinterpret_cast<QMeta *>(smem + Cfg::META_OFF);
 	double *s_cat = reinterpret_cast<double *>(smem + Cfg::CAT_OFF);
+	float *s_cbf = reinterpret_cast<float *>(smem + Cfg::CBF_OFF);
+	double *s_pair = reinterpret_cast<double *>(smem + Cfg::PAIR_OFF);
 	unsigned long long *s_ex = reinterpret_cast<unsigned long long *>(smem + Cfg::EX_OFF);
 	bool *s_last = reinterpret_cast<bool *>(smem + Cfg::EX_OFF + 18 * 8);
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	for (int i = tid; i < 512; i += blockDim.x) s_lut[lut_index(i)] = make_double2(P.lut[i], P.lut[512 + i]);
 	for (int i = tid; i < 8 * 256; i += blockDim.x) s_ptab[i] = P.ptab[i];
+	if (NF >= 0) {
+		for (int i = tid; i < 8 * 256; i += blockDim.x) s_cbf[i] = P.cbf[i];
+		for (int i = tid; i < (int)((P.n0 + 1u) * (P.n1 + 1u)); i += blockDim.x) s_pair[i] = P.pair[i];
+	}
 	for (int i = tid; i < CAT_WORDS; i += blockDim.x) s_cat[i] = P.lut[1024 + i];
 	if (tid == 0) {
 		for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
@@ -242,6 +273,14 @@ k_reward9q(const KqParams P) {
 	uint32_t cnt = 0;
 	int cur = -1;
 	const double w2 = P.w2;
+	double wq[8];
+#pragma unroll
+	for (int j = 0; j < 8; j++) wq[j] = P.wq[j];
+	const uint32_t n0 = P.n0, n1 = P.n1;
+	auto evalq = [&](unsigned long long q, float d2f, uint32_t idx, double &ws, double2 &t, uint32_t &ok) {
+		if (NF >= 0) evalq_ws_mixed<(NF >= 0 ? NF : 0)>(q, d2f, idx, s_ptab, s_cbf, s_pair, n0, n1, wq, w2, s_lut, ws, t, ok);
+		else evalq_ws(q, d2f, idx, s_ptab, w2, s_lut, ws, t, ok);
+	};
 	auto flush = [&](int c) {
 		long long *dst = P.acc + (uint64_t)ACC_PER_CAND * c;
 		flush_acc128(acc, dst, lane);
@@ -268,7 +307,7 @@ k_reward9q(const KqParams P) {
 				for (int k = 0; k < 4; k++) {
 					const int e = (4 * g + k) * Cfg::NCONS + tid;              // 8 B / 4 B lane stride: conflict-free
 					uint32_t ok;
-					evalq_ws(sq[e], sd[e], sl[e], s_ptab, w2, s_lut, ws4[k], t4[k], ok);
+					evalq(sq[e], sd[e], sl[e], ws4[k], t4[k], ok);
 					cnt += ok;
 				}
 				const bool generic = !RECIP && ((__double2hiint(t4[0].y) | __double2hiint(t4[1].y) |
@@ -288,7 +327,7 @@ k_reward9q(const KqParams P) {
 				const int e = k * Cfg::NCONS + tid;
 				if (e < n) {
 					double ws; double2 t; uint32_t ok;
-					evalq_ws(sq[e], sd[e], sl[e], s_ptab, w2, s_lut, ws, t, ok);
+					evalq(sq[e], sd[e], sl[e], ws, t, ok);
 					acc.add(to_fx(div_lut<RECIP>(ws, t)));
 					cnt += ok;
 				}
@@ -302,16 +341,16 @@ k_reward9q(const KqParams P) {
 	if (P.corpus_on) corpus_tail(P.corpus, s_ex, s_last);     // block-wide: every warp arrives here
 }
 
-template <int CW, int EPT, int STAGES>
+template <int CW, int EPT, int STAGES, int NF = -1>
 static cudaError_t launch_kq(const KqParams &P, int grid, bool recip, cudaStream_t st) {
 	using Cfg = KqCfg<CW, EPT, STAGES>;
 	cudaError_t err;
 	if (recip) {
-		auto k = k_reward9q<CW, EPT, STAGES, true>;
+		auto k = k_reward9q<CW, EPT, STAGES, true, NF>;
 		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
 		k<<<grid, (CW + 2) * 32, Cfg::SMEM, st>>>(P);
 	} else {
-		auto k = k_reward9q<CW, EPT, STAGES, false>;
+		auto k = k_reward9q<CW, EPT, STAGES, false, NF>;
 		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
 		k<<<grid, (CW + 2) * 32, Cfg::SMEM, st>>>(P);
 	}
@@ -323,7 +362,9 @@ int kq_tile_evals(int variant) {
 	case 1: return KqCfg<16, 8, 3>::TILE;
 	case 2: return KqCfg<24, 4, 4>::TILE;
 	case 3: return KqCfg<20, 4, 5>::TILE;
-	default: return KqCfg<20, 8, 2>::TILE;
+	case 7: return KqCfg<16, 8, 3>::TILE;
+	case 8: return KqCfg<24, 4, 4>::TILE;
+	default: return KqCfg<20, 8, 2>::TILE;                       // 0 and the mixed-lookup variants 4, 5, 6
 	}
 }
 
@@ -339,6 +380,11 @@ cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cuda
 	case 1: return launch_kq<16, 8, 3>(P, grid, recip, st);
 	case 2: return launch_kq<24, 4, 4>(P, grid, recip, st);
 	case 3: return launch_kq<20, 4, 5>(P, grid, recip, st);
+	case 4: return launch_kq<20, 8, 2, 4>(P, grid, recip, st);   // prefix table + 4 fp32 dimensions
+	case 5: return launch_kq<20, 8, 2, 5>(P, grid, recip, st);
+	case 6: return launch_kq<20, 8, 2, 6>(P, grid, recip, st);
+	case 7: return launch_kq<16, 8, 3, 5>(P, grid, recip, st);
+	case 8: return launch_kq<24, 4, 4, 5>(P, grid, recip, st);
 	default: return launch_kq<20, 8, 2>(P, grid, recip, st);
 	}
 }

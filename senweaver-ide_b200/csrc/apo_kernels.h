@@ -68,9 +68,16 @@ struct KqParams {
 	const double *lut;              // as K1Params::lut
 	const double *ptab;             // [8][256] value*weight per code (code 255 -> +0.0), table 0 = fl(0 + d0*w0)
 	double w2;
+	// mixed-lookup variants (>= 4): table 0+1 fused into one exact prefix table, the first NF of the
+	// six remaining coded dimensions read the fp32 value and multiply on the fp64 pipe instead
+	const double *pair;             // [(n0+1)][(n1+1)] fl(fl(0 + d0*w0) + d1*w1); last row / column = absent
+	const float *cbf;               // [8][256] code -> fp32 value (unused / absent -> 0.0f)
+	uint32_t n0, n1;                // used codes of dimensions 0 and 1
+	double wq[8];                   // weight of coded dimension j (push order 0,1,3..8)
 	int corpus_on;                  // as K1Params
 	K2Params corpus;
 };
+constexpr int KQ_PAIR_MAX = 1024;   // entries of the prefix table that fit its shared-memory slot
 int kq_tile_evals(int variant);
 cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cudaStream_t st);
 cudaError_t run_transcode(const float *dims, uint64_t pitch_in, uint32_t C, uint64_t T, unsigned long long *q8, float *d2,

@@ -14,7 +14,7 @@ def same_bits(a, b):
 
 
 @pytest.mark.parametrize("C,T", [(4, 1000), (3, 1), (7, 5121), (16, 40_003), (2, 5120)])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_compact_matches_fp32_and_oracle(engine, orc, C, T, variant):
     dims = orc.gen_dims(0x5EED0010 + C, 3, C, 100, T, 400, 8)
     engine.dims_upload(dims)
@@ -61,13 +61,15 @@ def test_compact_all_presence_masks_and_custom_weights(engine, orc):
     dims[3] = np.nan
     w = np.array([0.3, 0.1, 0.05, 0.05, 0.1, 0.1, 0.1, 0.1, 0.1])          # total weight with an all-ones significand
     try:
-        for weights in (orc.weights(), w):
+        wz = np.array([0.0, 0.4, 0.05, 0.0, 0.1, 0.1, 0.15, 0.1, 0.1])        # zero weights: all-null masks exist
+        for weights in (orc.weights(), w, wz):
             engine.set_weights(weights)
             engine.dims_upload(dims)
             engine.dims_compact()
-            r = engine.score(C, C)
-            assert engine.debug_partials(C) == orc.score_dims_fx(dims, w=weights)
-            assert np.array_equal(r.topk, orc.topk(orc.score_dims(dims, w=weights)[0], C))
+            for variant in (0, 4, 6):                                       # product tables / prefix table + fp32 lookups
+                r = engine.score(C, C, variant=variant)
+                assert engine.debug_partials(C) == orc.score_dims_fx(dims, w=weights), variant
+                assert np.array_equal(r.topk, orc.topk(orc.score_dims(dims, w=weights)[0], C))
         # changing the weights after compaction rebuilds the product tables
         engine.set_weights(orc.weights())
         engine.score(C, 1)
@@ -107,3 +109,29 @@ def test_compact_full_size_config2(engine, orc):
     res = engine.score(C, 16)
     assert engine.debug_partials(C) == exp
     assert np.array_equal(res.scores, ref.scores) and np.array_equal(res.topk, ref.topk)
+
+
+def test_mixed_lookup_falls_back_when_the_prefix_table_is_too_large(engine, orc):
+    """40 x 40 distinct (d0, d1) values exceed the 1024-entry prefix table: variants >= 4 must still be exact."""
+    rng = np.random.default_rng(23)
+    C, T = 3, 30_000
+    lv = np.linspace(-1, 1, 40).astype(np.float32)
+    dims = np.full((C, T, 9), np.nan, np.float32)
+    dims[:, :, 0] = lv[rng.integers(0, 40, (C, T))]
+    dims[:, :, 1] = lv[rng.integers(0, 40, (C, T))]
+    dims[:, :, 6] = lv[rng.integers(0, 5, (C, T))]
+    dims[rng.random(dims.shape) < 0.1] = np.nan
+    engine.dims_upload(dims)
+    engine.dims_compact()
+    exp = orc.score_dims_fx(dims)
+    for variant in (0, 5):
+        engine.score(C, 1, variant=variant)
+        assert engine.debug_partials(C) == exp
+    # 31 x 31 (+ absent) just fits
+    dims[:, :, 0] = lv[rng.integers(0, 31, (C, T))]
+    dims[:, :, 1] = lv[rng.integers(0, 31, (C, T))]
+    dims[rng.random(dims.shape) < 0.1] = np.nan
+    engine.dims_upload(dims)
+    engine.dims_compact()
+    engine.score(C, 1, variant=5)
+    assert engine.debug_partials(C) == orc.score_dims_fx(dims)

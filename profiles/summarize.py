@@ -15,6 +15,8 @@ KEYS = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__registers_per_thread", "launch__grid_size",
     "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem", "sm__cycles_elapsed.avg", "lts__t_sector_hit_rate.pct",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
 ]
 
 

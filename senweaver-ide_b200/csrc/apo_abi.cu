@@ -340,7 +340,7 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 			for (int j = 0; j < 8; j++) Q.wq[j] = e->W.w[dim_of[j]];
 		}
 		int qvariant = (int)o->variant;
-		if (qvariant >= 4 && !e->q_pair_ok) qvariant = 0;           // prefix table would not fit: plain product tables
+		if ((qvariant == 0 || qvariant >= 5) && !e->q_pair_ok) qvariant = 4;   // prefix table would not fit: product tables only
 		if (fused) { Q.corpus_on = 1; Q.corpus = *fused; }
 		if (e->k1_used + 2 > e->k1_ev.size()) {
 			for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }

@@ -165,19 +165,27 @@ struct KqCfg {
 	static_assert(EPT % 4 == 0, "evaluations are processed in interleaved groups of four");
 };
 
+// byte j of a 32-bit word as one PRMT (the shift + mask form costs two ALU slots per table index)
+template <int J>
+__device__ __forceinline__ uint32_t byte_of(uint32_t w) {
+	uint32_t r;
+	asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "n"(0x4440 | J));
+	return r;
+}
+
 // One Form-Q evaluation, first half: weighted sum in push order (TCS:777-783) + LUT entry.
 __device__ __forceinline__ void evalq_ws(unsigned long long q, float d2f, uint32_t idx, const double *ptab, double w2,
                                          const double2 *lut, double &ws_out, double2 &t_out, uint32_t &valid) {
 	const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
-	double ws = ptab[0 * 256 + (lo & 255u)];                          // table 0 holds fl(0 + d0*w0)
-	ws = __dadd_rn(ws, ptab[1 * 256 + ((lo >> 8) & 255u)]);
+	double ws = ptab[0 * 256 + byte_of<0>(lo)];                       // table 0 holds fl(0 + d0*w0)
+	ws = __dadd_rn(ws, ptab[1 * 256 + byte_of<1>(lo)]);
 	ws = __dadd_rn(ws, __dmul_rn((double)d2f, w2));                   // d2 is stored as +0.0 when absent
-	ws = __dadd_rn(ws, ptab[2 * 256 + ((lo >> 16) & 255u)]);
-	ws = __dadd_rn(ws, ptab[3 * 256 + (lo >> 24)]);
-	ws = __dadd_rn(ws, ptab[4 * 256 + (hi & 255u)]);
-	ws = __dadd_rn(ws, ptab[5 * 256 + ((hi >> 8) & 255u)]);
-	ws = __dadd_rn(ws, ptab[6 * 256 + ((hi >> 16) & 255u)]);
-	ws = __dadd_rn(ws, ptab[7 * 256 + (hi >> 24)]);
+	ws = __dadd_rn(ws, ptab[2 * 256 + byte_of<2>(lo)]);
+	ws = __dadd_rn(ws, ptab[3 * 256 + byte_of<3>(lo)]);
+	ws = __dadd_rn(ws, ptab[4 * 256 + byte_of<0>(hi)]);
+	ws = __dadd_rn(ws, ptab[5 * 256 + byte_of<1>(hi)]);
+	ws = __dadd_rn(ws, ptab[6 * 256 + byte_of<2>(hi)]);
+	ws = __dadd_rn(ws, ptab[7 * 256 + byte_of<3>(hi)]);
 	ws_out = ws;
 	t_out = lut[idx];                                                 // presence mask -> LUT index was fixed by the transcoder
 	valid = t_out.x > 0.0 ? 1u : 0u;
@@ -192,12 +200,13 @@ __device__ __forceinline__ void evalq_ws_mixed(unsigned long long q, float d2f, 
                                                const double *pair, uint32_t n0, uint32_t n1, const double (&wq)[8], double w2,
                                                const double2 *lut, double &ws_out, double2 &t_out, uint32_t &valid) {
 	const uint32_t lo = (uint32_t)q, hi = (uint32_t)(q >> 32);
-	const uint32_t c0 = min(lo & 255u, n0), c1 = min((lo >> 8) & 255u, n1);      // 255 (absent) -> last row / column
+	const uint32_t c0 = min(byte_of<0>(lo), n0), c1 = min(byte_of<1>(lo), n1);   // 255 (absent) -> last row / column
 	double ws = pair[c0 * (n1 + 1u) + c1];
 	ws = __dadd_rn(ws, __dmul_rn((double)d2f, w2));
 #pragma unroll
 	for (int j = 2; j < 8; j++) {
-		const uint32_t code = j < 4 ? ((lo >> (8 * j)) & 255u) : ((hi >> (8 * (j - 4))) & 255u);
+		const uint32_t code = j == 2 ? byte_of<2>(lo) : j == 3 ? byte_of<3>(lo) : j == 4 ? byte_of<0>(hi) : j == 5 ? byte_of<1>(hi)
+		                      : j == 6 ? byte_of<2>(hi) : byte_of<3>(hi);
 		if (j - 2 < NF) ws = __dadd_rn(ws, __dmul_rn((double)cbf[j * 256 + code], wq[j]));
 		else ws = __dadd_rn(ws, ptab[j * 256 + code]);
 	}
@@ -362,9 +371,7 @@ int kq_tile_evals(int variant) {
 	case 1: return KqCfg<16, 8, 3>::TILE;
 	case 2: return KqCfg<24, 4, 4>::TILE;
 	case 3: return KqCfg<20, 4, 5>::TILE;
-	case 7: return KqCfg<16, 8, 3>::TILE;
-	case 8: return KqCfg<24, 4, 4>::TILE;
-	default: return KqCfg<20, 8, 2>::TILE;                       // 0 and the mixed-lookup variants 4, 5, 6
+	default: return KqCfg<20, 8, 2>::TILE;                       // 0 (mixed lookup, default), 4 (product tables only), 5, 6
 	}
 }
 
@@ -380,12 +387,10 @@ cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cuda
 	case 1: return launch_kq<16, 8, 3>(P, grid, recip, st);
 	case 2: return launch_kq<24, 4, 4>(P, grid, recip, st);
 	case 3: return launch_kq<20, 4, 5>(P, grid, recip, st);
-	case 4: return launch_kq<20, 8, 2, 4>(P, grid, recip, st);   // prefix table + 4 fp32 dimensions
-	case 5: return launch_kq<20, 8, 2, 5>(P, grid, recip, st);
-	case 6: return launch_kq<20, 8, 2, 6>(P, grid, recip, st);
-	case 7: return launch_kq<16, 8, 3, 5>(P, grid, recip, st);
-	case 8: return launch_kq<24, 4, 4, 5>(P, grid, recip, st);
-	default: return launch_kq<20, 8, 2>(P, grid, recip, st);
+	case 4: return launch_kq<20, 8, 2>(P, grid, recip, st);      // product tables only (also the fallback of 0)
+	case 5: return launch_kq<20, 8, 2, 4>(P, grid, recip, st);   // prefix table + 4 fp32 dimensions
+	case 6: return launch_kq<20, 8, 2, 6>(P, grid, recip, st);   // prefix table + all 6 through fp32
+	default: return launch_kq<20, 8, 2, 3>(P, grid, recip, st);  // prefix table + 3 fp32 dimensions: the measured optimum
 	}
 }
 

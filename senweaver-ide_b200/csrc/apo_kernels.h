@@ -68,7 +68,7 @@ struct KqParams {
 	const double *lut;              // as K1Params::lut
 	const double *ptab;             // [8][256] value*weight per code (code 255 -> +0.0), table 0 = fl(0 + d0*w0)
 	double w2;
-	// mixed-lookup variants (>= 4): table 0+1 fused into one exact prefix table, the first NF of the
+	// mixed-lookup variants (0, 5, 6): table 0+1 fused into one exact prefix table, the first NF of the
 	// six remaining coded dimensions read the fp32 value and multiply on the fp64 pipe instead
 	const double *pair;             // [(n0+1)][(n1+1)] fl(fl(0 + d0*w0) + d1*w1); last row / column = absent
 	const float *cbf;               // [8][256] code -> fp32 value (unused / absent -> 0.0f)

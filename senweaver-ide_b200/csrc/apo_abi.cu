@@ -85,7 +85,7 @@ struct apo_engine {
 	cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
 	std::string err;
 	apo::Weights W;
-	double lut_tw[512], lut_rc[512], lut_cat[64];
+	double lut_tw[512], lut_rc[512], lut_cat[apo::CAT_WORDS];
 	DevBuf<double> d_lut;          // [0,512) total weight, [512,1024) reciprocal, [1024,1088) categorical products
 
 	DevBuf<apo_record> corpus; uint64_t corpus_T = 0, corpus_base = 0;
@@ -143,7 +143,7 @@ void build_luts(apo_engine *e) {
 	// multiplications the reference performs at TCS:781, tabulated once per weight vector
 	const double *w = e->W.w;
 	double *c = e->lut_cat;
-	for (int i = 0; i < 64; i++) c[i] = 0.0;
+	for (int i = 0; i < apo::CAT_WORDS; i++) c[i] = 0.0;
 	for (int ended = 0; ended < 2; ended++)
 		for (int err = 0; err < 2; err++)
 			for (int fb = 0; fb < 3; fb++) {
@@ -169,11 +169,27 @@ void build_luts(apo_engine *e) {
 		if (ef < -1) ef = -1;
 		c[27 + k] = ef * w[6];
 	}
+	// direct tables of K1r: [agent][min(counter, cap)] -> the level product above (bit copies)
+	using namespace apo;
+	for (int ag = 0; ag < 2; ag++) {
+		const uint32_t sev = ag ? 5u : 3u, mod = ag ? 3u : 2u, mnr = ag ? 2u : 1u;                       // TCS:702-704
+		for (uint32_t f = 0; f <= 5; f++) c[DIR_D3 + ag * 7 + f] = c[CAT_D3 + (f >= mnr) + (f >= mod) + (f >= sev)];
+		c[DIR_D3 + ag * 7 + 6] = 0.0;
+		const uint32_t cexc = ag ? 8u : 3u, cgood = ag ? 15u : 6u, cfair = ag ? 25u : 10u;               // TCS:711-713
+		c[DIR_D4 + ag * 27] = 0.0;
+		for (uint32_t n = 1; n <= 26; n++) c[DIR_D4 + ag * 27 + n] = c[CAT_D4 + (n > cexc) + (n > cgood) + (n > cfair)];
+		const uint32_t thr6 = ag ? 3u : 1u;                                                               // TCS:734
+		c[DIR_D6 + ag * 10] = 0.0;
+		for (uint32_t n = 1; n <= 9; n++) { const uint32_t over = n > thr6 ? n - thr6 : 0u; c[DIR_D6 + ag * 10 + n] = c[CAT_D6 + (over < 5u ? over : 5u)]; }
+		const uint32_t thr8 = ag ? 3u : 2u;                                                               // TCS:756
+		c[DIR_D8 + ag * 11] = 0.0;
+		for (uint32_t n = 1; n <= 10; n++) c[DIR_D8 + ag * 11 + n] = c[CAT_D8 + (n > thr8) + (n > 2 * thr8) + (n > 3 * thr8)];
+	}
 }
 
 int upload_luts(apo_engine *e) {
-	CK(e->d_lut.reserve(1024 + 64));
-	CK(cudaMemcpyAsync(e->d_lut.p + 1024, e->lut_cat, 64 * 8, cudaMemcpyHostToDevice, e->stream));
+	CK(e->d_lut.reserve(1024 + apo::CAT_WORDS));
+	CK(cudaMemcpyAsync(e->d_lut.p + 1024, e->lut_cat, apo::CAT_WORDS * 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaMemcpyAsync(e->d_lut.p, e->lut_tw, 512 * 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaMemcpyAsync(e->d_lut.p + 512, e->lut_rc, 512 * 8, cudaMemcpyHostToDevice, e->stream));
 	CK(cudaStreamSynchronize(e->stream));

@@ -70,7 +70,7 @@ __device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const
 __device__ __forceinline__ void record_ws(const apo_record &r, const Weights &W, const double2 *lut,
                                           double &ws_out, double2 &t_out) {
 	const double *cat = reinterpret_cast<const double *>(lut + 512);
-	const uint32_t mask = record_ws_table(r, W.w[2], cat, ws_out);
+	const uint32_t mask = record_ws_direct(r, W.w[2], cat, ws_out);
 	t_out = lut[lut_index(mask)];
 }
 

@@ -77,6 +77,23 @@ struct KqParams {
 	int corpus_on;                  // as K1Params
 	K2Params corpus;
 };
+// ---- categorical product table layout (built by apo_abi.cu build_luts, read by the kernels)
+constexpr int CAT_D01 = 0;    // [fb + 3*err + 6*ended] -> fl(fl(0 + d0*w0) + d1*w1)      (12)
+constexpr int CAT_D3 = 12;    // thresholds met 0..3 -> {1,-0.2,-0.5,-1}*w3, [4] = 0       (5)
+constexpr int CAT_D4 = 17;    // {1,0.3,-0.3,-0.8}*w4                                      (5)
+constexpr int CAT_D5 = 22;    // {1,0.5,0,-0.5}*w5                                         (5)
+constexpr int CAT_D6 = 27;    // k = clamp(llm - thr, 0, 5) -> max(-1, 1 - k*0.4)*w6, [6] = 0 (7)
+constexpr int CAT_D7 = 34;    // {1,0.5,0,-0.5}*w7                                         (5)
+constexpr int CAT_D8 = 39;    // {1,0.3,-0.3,-0.8}*w8                                      (5)
+// Direct tables for K1r: four dimensions depend on one small counter and the mode only, so the
+// product is read straight from [agent][min(counter, cap)] — no threshold selects, no compares.
+// Entries are copies of the level products above (same bits); slot "absent" holds +0.0.
+constexpr int DIR_D3 = 64;    // [2][7]  min(toolFail, 5); slot 6 = no tool calls                 (TCS:701-708)
+constexpr int DIR_D4 = 78;    // [2][27] min(toolCalls, 26); 0 = absent                            (TCS:711-718)
+constexpr int DIR_D6 = 132;   // [2][10] min(llmCalls, 9); 0 = absent                              (TCS:733-737)
+constexpr int DIR_D8 = 152;   // [2][11] min(turns, 10); 0 = absent                                (TCS:752-762)
+constexpr int CAT_WORDS = 176;
+
 constexpr int KQ_PAIR_MAX = 1024;   // entries of the prefix table that fit its shared-memory slot
 int kq_tile_evals(int variant);
 cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cudaStream_t st);

@@ -36,7 +36,7 @@ assert [r.report.pat[p].count for p in range(6)] == [ref.pat[p].count for p in r
 e.score(C, 2, first=1000, count=3001)
 assert e.debug_partials(C) == orc.score_dims_fx(dims[:, 1000:4001])
 e.dims_compact()
-for v in range(4):
+for v in range(7):                           # 0 mixed lookup (default), 1-3 tile shapes, 4 product tables only, 5-6 more fp32 lookups
     e.score(C, 3, variant=v)
     assert e.debug_partials(C) == exp
 assert np.array_equal(np.nan_to_num(e.dims_download(2, 0, T), nan=7), np.nan_to_num(dims[2], nan=7))

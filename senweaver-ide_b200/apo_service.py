@@ -83,6 +83,7 @@ class APOService:
         self._beamState, self._textualGradients = None, []
         self._stateListeners, self._suggestionListeners = [], []
         self._dirty = False
+        self._lastRolloutCount = 0
         api = (getattr(productService, "senweaverApiConfig", None) or {}).get("apiBaseUrl") if productService else None
         self._apoApiUrl = f"{api or 'https://ide-api.senweaver.com'}/api/apo"          # APO:328-329
         self._loadFromStorage()
@@ -288,7 +289,7 @@ class APOService:
             self._beamState["versionCounter"] = counter
         return self.getBeamState()
 
-    def _applyBeamUpdate(self, bu):
+    def _applyBeamUpdate(self, bu, notify=True):
         now = time.time() * 1000.0
         if self._beamState is None:                                          # APO:1141-1152
             self._beamState = {"currentRound": 0, "totalRounds": self._config["beamRounds"], "beam": [],
@@ -306,8 +307,9 @@ class APOService:
             self._applyBeamBestPrompt(bu["bestPrompt"])
         st["lastUpdatedAt"] = now
         self._dirty = True
-        self._saveToStorage()
-        self._fire(self._stateListeners)
+        if notify:
+            self._saveToStorage()
+            self._fire(self._stateListeners)
 
     def _applyBeamBestPrompt(self, best):
         """APO:1219-1264: '- ' lines become individual optimized segments; otherwise replace/add one."""
@@ -332,22 +334,51 @@ class APOService:
                 self._segments.append(new_seg(text))
 
     def requestOptimizationFromServer(self):
-        """APO:992-1215.  Needs the closed backend; without a request service it returns [] like any
-        failed request in the reference.  A reply's beamUpdate goes through the same update rule."""
+        """APO:992-1215: POST {apo}/optimize with the v2.0.0 payload; the reply's suggestions join the local list as
+        pending, its beamUpdate goes through the strict-greater adoption rule, its textualGradient is stored (and its
+        editedPrompt becomes one more pending suggestion).  Any failure: warn and return [] (APO:1211-1214)."""
         try:
             if not self._reports:
                 self.analyzePromptEffectiveness()
-            if self._request is None:
-                print("[APO] Server optimization request failed: no request service")
+            if not self._reports:
                 return []
-            reply = self._request(f"{self._apoApiUrl}/optimize", self.buildOptimizePayload()) or {}
-            sugg = reply.get("suggestions") or []
+            payload = self.buildOptimizePayload()
+            if self._request is None:
+                raise RuntimeError("no request service")
+            reply = self._request(f"{self._apoApiUrl}/optimize", payload)
+            if not isinstance(reply, dict):
+                reply = {}
+            if (reply.get("statusCode") or 0) >= 400:
+                print("[APO] Server optimization request failed:", reply["statusCode"])
+                return []
+            sugg = list(reply.get("suggestions") or [])
             for s in sugg:
                 s["id"] = s.get("id") or str(uuid.uuid4())
                 s["status"] = "pending"
                 self._suggestions.append(s)
             if reply.get("beamUpdate"):
-                self._applyBeamUpdate(reply["beamUpdate"])
+                self._applyBeamUpdate(reply["beamUpdate"], notify=False)
+            tgr = reply.get("textualGradient") or {}
+            if tgr.get("critique"):
+                best = (self._beamState or {}).get("historyBestPrompt") or {}
+                tg = {"id": str(uuid.uuid4()), "promptVersion": best.get("version") or "v0", "critique": tgr["critique"],
+                      "rolloutSummary": f"Based on {self._lastRolloutCount} rollouts",
+                      "createdAt": time.time() * 1000.0}
+                self._textualGradients.append(tg)
+                self._textualGradients = self._textualGradients[-MAX_GRADIENTS:]
+                if tgr.get("editedPrompt"):
+                    edit = {"id": str(uuid.uuid4()), "targetCategory": "core_behavior", "type": "modify", "priority": "high",
+                            "description": f"Textual Gradient optimization: {js_substring(tg['critique'], 0, 100)}...",
+                            "suggestedContent": tgr["editedPrompt"], "reasoning": tg["critique"],
+                            "estimatedImpact": "Prompt optimization based on Textual Gradient", "status": "pending",
+                            "promptVersion": tg["promptVersion"]}
+                    sugg.append(edit)
+                    self._suggestions.append(edit)
+            self._dirty = True
+            self._saveToStorage()
+            if sugg:
+                self._fire(self._suggestionListeners, sugg)
+            self._fire(self._stateListeners)
             return sugg
         except Exception as e:
             print("[APO] Server optimization request failed:", e)
@@ -483,6 +514,7 @@ class APOService:
         recent = sorted([t for t in self._tc.getAllTraces() if t["summary"]["userFeedback"] is not None],
                         key=lambda t: -t["startTime"])[: self._config["gradientBatchSize"] * 4]
         rollouts = self._convertTracesToRolloutResults(recent)
+        self._lastRolloutCount = len(rollouts)                                 # rolloutResults.length before the slice(0, 20)
         reward_summary = {"totalWithReward": 0, "avgFinalReward": None, "rewardDimensionAvg": {}}
         tool_summary = {"totalCalls": 0, "totalSucceeded": 0, "totalFailed": 0, "successRate": None, "totalDurationMs": 0, "byToolName": {}}
         if recent:

@@ -387,3 +387,41 @@ def test_apo_state_persists_and_gradient_flow(engine):
     apo2._applyBeamUpdate({"bestPrompt": {"version": "v3", "content": "- c", "score": 0.1}, "bestScore": 0.1, "round": 3})
     assert apo2.getBeamState()["historyBestPrompt"]["version"] == "v3" and "c" in " ".join(apo2.getOptimizedRules())
     assert pkg is not None
+
+
+def test_server_optimization_reply_is_merged(engine):
+    """requestOptimizationFromServer (APO:992-1215): payload sent to {apo}/optimize, reply suggestions become pending,
+    beamUpdate follows the strict-greater rule, textualGradient is stored with its edit suggestion; HTTP >= 400 -> []."""
+    tcmod, apomod = import_module("senweaver-ide_b200.trace_collector"), import_module("senweaver-ide_b200.apo_service")
+    sent, fired = [], []
+    reply = {"statusCode": 200,
+             "suggestions": [{"targetCategory": "tool_usage", "type": "add", "priority": "medium", "description": "d", "suggestedContent": "- check tool output",
+                              "reasoning": "r", "estimatedImpact": "i"}],
+             "beamUpdate": {"beam": [{"version": "v1", "content": "- x\n- y", "score": 0.4}], "bestPrompt": {"version": "v1", "content": "- x\n- y", "score": 0.4},
+                            "bestScore": 0.4, "round": 1},
+             "textualGradient": {"critique": "c" * 150, "editedPrompt": "- z"}}
+
+    def request(url, payload):
+        sent.append((url, payload))
+        return reply if url.endswith("/optimize") else {"statusCode": 200}
+    tc = tcmod.TraceCollectorService(engine)
+    apo = apomod.APOService(engine, tc, requestService=request)
+    apo.onDidGenerateSuggestions(lambda s: fired.append(s))
+    drive(tc, random.Random(4), n_threads=40)
+    out = apo.requestOptimizationFromServer()
+    url, pay = [x for x in sent if x[0].endswith("/optimize")][0]
+    assert url == "https://ide-api.senweaver.com/api/apo/optimize" and pay["version"] == "2.0.0" and "textualGradientPrompt" in pay
+    assert len(out) == 2 and all(s["status"] == "pending" and s["id"] for s in out) and fired == [out]
+    assert out[1]["description"] == "Textual Gradient optimization: " + "c" * 100 + "..." and out[1]["promptVersion"] == "v1"
+    st = apo.getBeamState()
+    assert st["currentRound"] == 1 and st["historyBestScore"] == 0.4 and apo.getOptimizedRules() == ["x", "y"]
+    g = apo.getTextualGradients()
+    n_rated = min(16, sum(1 for t in tc.getAllTraces() if t["summary"]["userFeedback"] is not None))
+    assert len(g) == 1 and g[0]["rolloutSummary"] == f"Based on {n_rated} rollouts"
+    # an equal score does not replace the incumbent; an HTTP error yields [] and changes nothing
+    reply["beamUpdate"] = {"bestPrompt": {"version": "v2", "content": "- q", "score": 0.4}, "bestScore": 0.4, "round": 2}
+    reply["suggestions"], reply["textualGradient"] = [], None
+    assert apo.requestOptimizationFromServer() == [] and apo.getBeamState()["historyBestPrompt"]["version"] == "v1"
+    reply["statusCode"] = 500
+    before = apo.getStats()
+    assert apo.requestOptimizationFromServer() == [] and apo.getStats()["totalSuggestions"] == before["totalSuggestions"]

@@ -411,7 +411,7 @@ def test_server_optimization_reply_is_merged(engine):
     out = apo.requestOptimizationFromServer()
     url, pay = [x for x in sent if x[0].endswith("/optimize")][0]
     assert url == "https://ide-api.senweaver.com/api/apo/optimize" and pay["version"] == "2.0.0" and "textualGradientPrompt" in pay
-    assert len(out) == 2 and all(s["status"] == "pending" and s["id"] for s in out) and fired == [out]
+    assert len(out) == 2 and all(s["status"] == "pending" and s["id"] for s in out) and fired[-1] == out
     assert out[1]["description"] == "Textual Gradient optimization: " + "c" * 100 + "..." and out[1]["promptVersion"] == "v1"
     st = apo.getBeamState()
     assert st["currentRound"] == 1 and st["historyBestScore"] == 0.4 and apo.getOptimizedRules() == ["x", "y"]

@@ -557,3 +557,41 @@ def test_scores_are_closer_to_the_exact_mean_than_the_sequential_sum(engine, orc
         err_seq = abs(Fraction(float(seq[c])) - exact)
         assert err_gpu <= err_seq + Fraction(1, 2**60), (float(err_gpu), float(err_seq))
         assert err_gpu < Fraction(1, 2**50)
+
+
+def test_rollout_records_at_every_threshold_boundary(engine, orc):
+    """K1r reads four dimensions from [mode][counter] tables, tokens from a (tokens-1)/1000 bucket table and the
+    tool_success_rate quotient from tabulated reciprocals when a warp's records all have < 64 tool calls: sweep every
+    counter across its thresholds +-1 (both threshold sets), the 63/64 switch, saturated and degenerate records."""
+    rng = np.random.default_rng(99)
+    C, T = 4, 24_000
+    tokens = np.array([0, 1, 999, 1000, 1001, 1999, 2000, 2001, 4999, 5000, 5001, 9999, 10000, 10001, 14999, 15000, 15001, 29999, 30000, 30001,
+                       31000, 31001, 65535, 10**6, 2**32 - 1], np.uint32)
+    calls = np.array([0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 15, 16, 25, 26, 27, 62, 63, 64, 65, 100, 1000, 65535, 2**32 - 1], np.uint32)
+    recs = np.zeros((C, T), orc.RECORD_DTYPE)
+    recs["feedback"] = rng.integers(0, 3, (C, T))
+    recs["flags"] = rng.integers(0, 4, (C, T)) | 8 | (rng.integers(0, 2, (C, T)) << 4)
+    recs["flags"][rng.random((C, T)) < 0.03] &= ~np.uint8(8)                        # a few never-scored records
+    recs["mode"] = rng.integers(0, 5, (C, T))
+    recs["userMsgs"] = rng.integers(0, 12, (C, T))
+    recs["asstMsgs"] = rng.integers(0, 12, (C, T))
+    recs["toolCalls"] = calls[rng.integers(0, len(calls), (C, T))]
+    recs["toolCalls"][0, :8000] = rng.integers(0, 64, 8000)                         # whole warps below 64: the tabulated-reciprocal path
+    fail = (rng.random((C, T)) * (np.minimum(recs["toolCalls"], 8) + 1)).astype(np.uint32)
+    recs["toolFail"] = np.minimum(fail, recs["toolCalls"])
+    recs["toolSucc"] = recs["toolCalls"] - recs["toolFail"]
+    odd = rng.random((C, T)) < 0.02                                                 # malformed: succ + fail != total
+    recs["toolSucc"][odd] = rng.integers(0, 200, odd.sum())
+    recs["llmCalls"] = rng.integers(0, 12, (C, T))
+    recs["tokens"] = tokens[rng.integers(0, len(tokens), (C, T))]
+    per = np.array([0, 1, 999.5, 1000, 1000.0001, 2999, 3000, 3001, 9999, 10000, 10001, 1e7], np.float64)
+    recs["toolDurMs"] = (per[rng.integers(0, len(per), (C, T))] * np.maximum(recs["toolCalls"], 1)).astype(np.float32)
+    engine.rollouts_upload(recs)
+    engine.score(C, 2, source=1)
+    assert engine.debug_partials(C) == orc.score_records_fx(recs)
+    # the same records through the single-trace path (reward_dims) agree with the oracle per record
+    flat = recs[1, :4000]
+    dims, masks, finals = engine.reward_batch(flat)
+    for i in range(0, 4000, 7):
+        d, m = orc.reward_dims(flat[i])
+        assert m == masks[i] and np.array_equal(np.nan_to_num(d, nan=9.0), np.nan_to_num(dims[i], nan=9.0))

@@ -184,12 +184,7 @@ void build_luts(apo_engine *e) {
 		const uint32_t thr8 = ag ? 3u : 2u;                                                               // TCS:756
 		c[DIR_D8 + ag * 11] = 0.0;
 		for (uint32_t n = 1; n <= 10; n++) c[DIR_D8 + ag * 11 + n] = c[CAT_D8 + (n > thr8) + (n > 2 * thr8) + (n > 3 * thr8)];
-		// tokens > 1000k  <=>  (tokens-1)/1000 >= k for tokens >= 1: bucket b = min((tokens-1)/1000, 30)
-		const uint32_t texc = ag ? 5u : 2u, tgood = ag ? 15u : 5u, tfair = ag ? 30u : 10u;               // TCS:741-743, in thousands
-		for (uint32_t b = 0; b <= 30; b++) c[DIR_D7 + ag * 32 + b] = c[CAT_D7 + (b >= texc) + (b >= tgood) + (b >= tfair)];
-		c[DIR_D7 + ag * 32 + 31] = 0.0;
 	}
-	for (int n = 1; n < 64; n++) { volatile double one = 1.0, d = (double)n; c[RCP_TAB + n] = one / d; }
 }
 
 int upload_luts(apo_engine *e) {

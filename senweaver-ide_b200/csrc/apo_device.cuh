@@ -216,27 +216,15 @@ __device__ __forceinline__ uint32_t record_ws_table(const apo_record &r, double 
 }
 
 // Same weighted sum through the direct tables (K1r's inner loop): identical table values added in the
-// same push order, about a third fewer instructions than the threshold form above.
-// RCPTAB: every record of the calling warp's group has < 64 tool calls, so succ/total takes the tabulated
-// reciprocal RN(1/total) + the Markstein correction (correctly rounded: an integer < 64 never has an
-// all-ones significand) instead of the seed + two Newton steps of div_small_int.  Same quotient bits.
-template <bool RCPTAB>
+// same push order, about a quarter fewer instructions than the threshold form above.
 __device__ __forceinline__ uint32_t record_ws_direct(const apo_record &r, double w2, const double *cat, double &ws_out) {
 	const uint32_t ag = r.mode == 2 ? 1u : 0u;
 	const uint32_t err = (r.flags & APO_F_ERRORS) ? 1u : 0u, ended = (r.flags & APO_F_ENDED) ? 1u : 0u;
 	const uint32_t i01 = (r.feedback < 3 ? r.feedback : 0u) + 3u * err + 6u * ended;
 	double ws = cat[CAT_D01 + i01];
 	const bool tool = r.toolCalls > 0;
-	const uint32_t tc1 = tool ? r.toolCalls : 1u;
-	const double total = (double)tc1, succ = (double)r.toolSucc;
-	double rate;
-	if (RCPTAB) {
-		const double y = cat[RCP_TAB + tc1];
-		const double q = __dmul_rn(succ, y);
-		rate = __fma_rn(__fma_rn(-total, q, succ), y, q);
-	} else {
-		rate = div_small_int(succ, total);
-	}
+	const double total = (double)(tool ? r.toolCalls : 1u);
+	const double rate = div_small_int((double)r.toolSucc, total);
 	const double d2 = keep_if(tool, __dadd_rn(__dmul_rn(rate, 2.0), -1.0));
 	ws = __dadd_rn(ws, __dmul_rn(d2, w2));
 	ws = __dadd_rn(ws, cat[DIR_D3 + ag * 7u + (tool ? min(r.toolFail, 5u) : 6u)]);
@@ -247,8 +235,9 @@ __device__ __forceinline__ uint32_t record_ws_direct(const apo_record &r, double
 	ws = __dadd_rn(ws, cat[CAT_D5 + (hasdur ? i5 : 4u)]);
 	ws = __dadd_rn(ws, cat[DIR_D6 + ag * 10u + min(r.llmCalls, 9u)]);
 	const bool tok = r.tokens > 0;
-	const uint32_t bucket = min(__umulhi(r.tokens - 1u, 0x10624DD3u) >> 6, 30u);      // (tokens-1)/1000, exact for all u32
-	ws = __dadd_rn(ws, cat[DIR_D7 + ag * 32u + (tok ? bucket : 31u)]);
+	const uint32_t texc = ag ? 5000u : 2000u, tgood = ag ? 15000u : 5000u, tfair = ag ? 30000u : 10000u;
+	const uint32_t i7 = (r.tokens > texc) + (r.tokens > tgood) + (r.tokens > tfair);
+	ws = __dadd_rn(ws, cat[CAT_D7 + (tok ? i7 : 4u)]);
 	const uint32_t turns = r.userMsgs < r.asstMsgs ? r.userMsgs : r.asstMsgs;
 	ws = __dadd_rn(ws, cat[DIR_D8 + ag * 11u + min(turns, 10u)]);
 	ws_out = ws;

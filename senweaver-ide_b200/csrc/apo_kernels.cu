@@ -67,11 +67,10 @@ __device__ __forceinline__ long long eval_dims(const float (&v)[APO_NDIM], const
 
 // One Form-R evaluation, first half (TCS:668-783): record -> weighted sum + LUT entry.  The
 // categorical product table sits right behind the 512-entry LUT in shared memory.
-template <bool RCPTAB = false>
 __device__ __forceinline__ void record_ws(const apo_record &r, const Weights &W, const double2 *lut,
                                           double &ws_out, double2 &t_out) {
 	const double *cat = reinterpret_cast<const double *>(lut + 512);
-	const uint32_t mask = record_ws_direct<RCPTAB>(r, W.w[2], cat, ws_out);
+	const uint32_t mask = record_ws_direct(r, W.w[2], cat, ws_out);
 	t_out = lut[lut_index(mask)];
 }
 
@@ -246,21 +245,11 @@ k_reward9(const K1Params P) {
 			};
 			if (n == Cfg::TILE) {
 				double ws4[Cfg::EPT]; double2 t4[Cfg::EPT]; uint32_t ok4[Cfg::EPT];
-				apo_record r4[Cfg::EPT];
-				uint32_t calls = 0;
-#pragma unroll
-				for (int k = 0; k < Cfg::EPT; k++) { r4[k] = load_record(k * Cfg::NCONS + tid); calls |= r4[k].toolCalls; }
-				// one warp-uniform choice per group: tabulated reciprocals when every record has < 64 tool calls
-				if (!__any_sync(0xffffffffu, calls >= 64u)) {
-#pragma unroll
-					for (int k = 0; k < Cfg::EPT; k++) record_ws<true>(r4[k], W, s_lut, ws4[k], t4[k]);
-				} else {
-#pragma unroll
-					for (int k = 0; k < Cfg::EPT; k++) record_ws<false>(r4[k], W, s_lut, ws4[k], t4[k]);
-				}
 #pragma unroll
 				for (int k = 0; k < Cfg::EPT; k++) {
-					ok4[k] = ((r4[k].flags & APO_F_VALID) && t4[k].x > 0.0) ? 1u : 0u;
+					const apo_record r = load_record(k * Cfg::NCONS + tid);
+					record_ws(r, W, s_lut, ws4[k], t4[k]);
+					ok4[k] = ((r.flags & APO_F_VALID) && t4[k].x > 0.0) ? 1u : 0u;
 					cnt += ok4[k];
 				}
 				const bool generic = !RECIP && ((__double2hiint(t4[0].y) | __double2hiint(t4[1].y) |
@@ -373,7 +362,7 @@ k_detect6(const K2Params P) {
 	__shared__ bool s_last;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if (tid < APO_NPAT * 3) s_ex[tid] = ~0ull;
-	for (int i = tid; i < CAT_WORDS; i += blockDim.x) s_cat[i] = P.lut[1024 + i];
+	if (tid < CAT_WORDS) s_cat[tid] = P.lut[1024 + tid];
 	for (int i = tid; i < 512; i += K2_THREADS) s_lut[i] = make_double2(P.lut[i], P.lut[512 + i]);
 	__syncthreads();
 	const uint64_t nwarps = (uint64_t)gridDim.x * (K2_THREADS / 32);

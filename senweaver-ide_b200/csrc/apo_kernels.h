@@ -92,9 +92,7 @@ constexpr int DIR_D3 = 64;    // [2][7]  min(toolFail, 5); slot 6 = no tool call
 constexpr int DIR_D4 = 78;    // [2][27] min(toolCalls, 26); 0 = absent                            (TCS:711-718)
 constexpr int DIR_D6 = 132;   // [2][10] min(llmCalls, 9); 0 = absent                              (TCS:733-737)
 constexpr int DIR_D8 = 152;   // [2][11] min(turns, 10); 0 = absent                                (TCS:752-762)
-constexpr int DIR_D7 = 176;   // [2][32] tokens: bucket min((tokens-1)/1000, 30), 31 = absent; every threshold is a multiple of 1000 (TCS:740-748)
-constexpr int RCP_TAB = 240;  // [64] RN(1/n) for n = 1..63 ([0] unused): tool_success_rate quotients with < 64 tool calls (TCS:697)
-constexpr int CAT_WORDS = 304;
+constexpr int CAT_WORDS = 176;
 
 constexpr int KQ_PAIR_MAX = 1024;   // entries of the prefix table that fit its shared-memory slot
 int kq_tile_evals(int variant);

@@ -36,6 +36,8 @@ struct K1Cfg {
 	static constexpr int EX_OFF = META_OFF + STAGES * 8;          // 18 example slots + the last-CTA flag of the fused corpus scan
 	static constexpr int SMEM = EX_OFF + 18 * 8 + 16;
 	static_assert(STAGE_BYTES % 16 == 0, "bulk copies are multiples of 16 bytes");
+	// 227 KB per CTA minus the kernel's static shared memory (1408 B, ptxas -v): the 24-warp Form D tile sits 48 B under the limit
+	static_assert(SMEM <= 232448 - 1408, "tile + tables exceed the shared memory of one CTA");
 };
 
 // One Form-D evaluation, first half: 9 fp32 (NaN = absent) -> weighted sum in push order and

@@ -89,3 +89,70 @@ def test_ingest_throughput_is_reported(pkg):
     dt = time.perf_counter() - t0
     assert recs.shape[0] == 6000
     print(f"ingest: {len(text) / 1e6:.1f} MB in {dt * 1e3:.1f} ms = {len(text) / dt / 1e6:.0f} MB/s, {recs.shape[0] / dt / 1e3:.0f} k traces/s")
+
+
+def test_ingest_never_crashes_on_mutated_input(pkg):
+    """Byte-level mutations of a valid document: the parser returns a count or rejects with a position, nothing else."""
+    traces, persisted = corpus(5, 12)
+    good = json.dumps(persisted, separators=(",", ":")).encode()
+    rng = random.Random(1234)
+    rejected = 0
+    for _ in range(1500):
+        b = bytearray(good)
+        for _ in range(rng.randint(1, 4)):
+            op, pos = rng.randint(0, 3), rng.randrange(len(b))
+            if op == 0:
+                b[pos] = rng.randrange(256)
+            elif op == 1:
+                del b[pos:pos + rng.randint(1, 40)]
+            elif op == 2:
+                b[pos:pos] = bytes(rng.choice(b'{}[]",:\\0-9etn ') for _ in range(rng.randint(1, 6)))
+            else:
+                b = b[:pos]
+            if not b:
+                b = bytearray(b" ")
+        try:
+            recs = pkg.records_from_json(bytes(b))
+            assert recs.shape[0] <= 12 + 6
+        except ValueError as e:
+            rejected += 1
+            assert "malformed trace JSON at byte" in str(e)
+    assert rejected > 500
+
+
+def test_ingest_agrees_with_a_general_json_parser_on_random_documents(pkg):
+    """Random nested JSON around the fields that matter: whatever json.loads makes of the document, encode_trace of
+    that equals the native record (member order, nesting depth, odd value types in ignored positions)."""
+    enc = import_module("senweaver-ide_b200.trace_collector").encode_trace
+    rng = random.Random(77)
+
+    def junk(depth=0):
+        k = rng.randint(0, 7 if depth < 4 else 4)
+        if k == 0:
+            return None
+        if k == 1:
+            return rng.choice([True, False])
+        if k == 2:
+            return rng.choice([0, -1, 3.5, 1e-7, 1.5e300, 12345678901234567890, -0.0])
+        if k in (3, 4):
+            return rng.choice(ts.TRICKY)
+        if k == 5:
+            return [junk(depth + 1) for _ in range(rng.randint(0, 4))]
+        return {rng.choice(["type", "data", "toolSuccess", "summary", "spans", "x", "endTime", 'q"k']): junk(depth + 1) for _ in range(rng.randint(0, 4))}
+
+    docs = []
+    for i in range(300):
+        t = ts.make_trace(*random_tuple(rng))
+        if rng.random() < 0.7:
+            ts.compute_reward_signals(t)
+        p = ts.persisted_form(t, rng, i)
+        p["extra"] = junk()
+        for sp in p["spans"]:
+            if rng.random() < 0.3:
+                sp["data"]["payload"] = junk()
+        p["summary"]["toolCallsByName"] = {"a": junk(), "type": "user_message"}
+        docs.append(p)
+    text = json.dumps(docs)
+    recs = pkg.records_from_json(text)
+    want = b"".join(enc(t).tobytes() for t in json.loads(text))
+    assert recs.tobytes() == want

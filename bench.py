@@ -139,7 +139,14 @@ def cpu_baseline(threads: int, target_s: float = 12.0) -> dict:
     for _ in range(reps):
         s, n = oracle.score_dims(dims, nthreads=threads)
     dt = (time.perf_counter() - t0) / reps
-    return {"value": Cn * T / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    # the parity oracle itself: one thread, exact reference order (SURVEY 8d "CPU baseline" (i)); ~3 s
+    t0 = time.perf_counter()
+    one = 0
+    while time.perf_counter() - t0 < 3.0:
+        oracle.score_dims(dims[:8], nthreads=1)
+        one += 1
+    dt1 = (time.perf_counter() - t0) / one
+    return {"value": Cn * T / dt, "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": 8 * T / dt1,
             "sample": f"{Cn} candidates x {T} records of the configs[2] generator (seed {SEED:#x}), {reps} passes, "
                       f"oracle/apo_oracle.c orc_score_dims_mt; the reference TypeScript cannot run here (no JS runtime)"}
 

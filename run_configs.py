@@ -80,7 +80,18 @@ def main():
             eng.dims_upload(f32)
             eng.corpus_upload(recs[0])
             r = eng.score(C, 2, corpus=True)
-            emit({"config": 1, "C": C, "T": T, "wall_ms": (time.perf_counter() - t0) * 1e3, "topk": r.topk.tolist(),
+            wall = (time.perf_counter() - t0) * 1e3
+            # call latencies at the reference's real sizes (<= 1000 traces, TCS:219): host wall clock, 200 calls each
+            lat = {}
+            for name, fn in (("reward_one_us", lambda: eng.reward_batch(recs[0, :1])),
+                             ("report_1000_traces_us", lambda: eng.score(C, 0, corpus=True, count=4)),
+                             ("score_4x1000_top2_with_report_us", lambda: eng.score(C, 2, corpus=True))):
+                fn()
+                t1 = time.perf_counter()
+                for _ in range(200):
+                    fn()
+                lat[name] = (time.perf_counter() - t1) / 200 * 1e6
+            emit({"config": 1, "C": C, "T": T, "wall_ms": wall, "call_latency": lat, "topk": r.topk.tolist(),
                   "scores": r.scores.tolist(), "note": "plumbing: Form R -> apo_reward_batch -> Form D -> apo_score (GPU path; Node.js itself is unavailable here)"})
         elif cfg in (2, 3):
             C, T = (64, 1_000_000) if cfg == 2 else (256, 10_000_000)

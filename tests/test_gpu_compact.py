@@ -1,4 +1,4 @@
-"""Form Q — the compact resident layout (12 B per evaluation) and its kernel K1q (-m gpu).
+"""Form Q — the compact resident layout (14 B per evaluation) and its kernel K1q (-m gpu).
 Lossless: decoding returns the original fp32 bit patterns, and the integer partial sums equal
 those of the fp32 kernel and of the oracle with no tolerance."""
 import numpy as np

@@ -65,3 +65,43 @@ def test_sharded_score_equals_single_gpu(tmp_path, engine, orc, world, layout):
     s, n = engine.debug_partials(C)
     es, en = orc.score_dims_fx(d)
     assert s[3] == es[0] and n[3] == en[0]
+
+
+def test_single_process_two_handles_on_threads(engine, orc):
+    """The Electron main process is ONE process: two handles (one per GPU) driven by two threads of the same process
+    must join through the library's communicator exactly like two ranks in two processes."""
+    import threading
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    pkg = import_module("senweaver-ide_b200")
+    uid = pkg.Engine.comm_unique_id()
+    world, out, errs = 2, {}, []
+
+    def run(rank):
+        try:
+            eng = pkg.Engine(rank)
+            eng.comm_init(world, rank, uid)
+            first, last = pkg.sharding.shard_range(T, world, rank)
+            eng.dims_generate(SEED, 0, C, first, last - first, 300)
+            eng.corpus_generate(SEED, first, last - first, 300)
+            res = eng.score(C, K, corpus=True)
+            out[rank] = (res.scores.copy(), res.topk.copy(), eng.debug_partials(C), res.report.bad, [res.report.pat[p].count for p in range(6)])
+            eng.close()
+        except Exception as e:                      # surfaced below: a failing thread must not hang the other in NCCL silently
+            errs.append((rank, repr(e)))
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not errs, errs
+    assert all(not t.is_alive() for t in th)
+    engine.dims_generate(SEED, 0, C, 0, T, 300)
+    engine.corpus_generate(SEED, 0, T, 300)
+    ref = engine.score(C, K, corpus=True)
+    rp = engine.debug_partials(C)
+    for r in range(world):
+        s, tk, parts, bad, pats = out[r]
+        assert np.array_equal(s, ref.scores) and np.array_equal(tk, ref.topk) and parts == rp
+        assert bad == ref.report.bad and pats == [ref.report.pat[p].count for p in range(6)]

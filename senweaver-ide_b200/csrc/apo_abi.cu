@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <string>
 #include <utility>
+#include <thread>
 #include <vector>
 #include <vector>
 
@@ -102,6 +103,7 @@ struct apo_engine {
 	DevBuf<unsigned long long> keys, sel_key; DevBuf<int32_t> sel_idx;
 	uint8_t *h_result = nullptr; uint64_t h_result_cap = 0;
 	DevBuf<uint8_t> win[2]; cudaEvent_t win_free[2] = {nullptr, nullptr}, win_ready[2] = {nullptr, nullptr};
+	uint8_t *h_stage[2] = {nullptr, nullptr}; uint64_t h_stage_cap = 0; cudaEvent_t stage_done[2] = {nullptr, nullptr};   // pinned staging of pageable callers
 	DevBuf<apo_record> batch_in; DevBuf<double> batch_out; DevBuf<uint32_t> batch_mask;
 
 	void *comm = nullptr; int nranks = 1, rank = 0;
@@ -498,6 +500,7 @@ extern "C" int apo_create(int device, apo_engine **out) {
 	for (int i = 0; i < 2; i++) {
 		if ((c = cudaEventCreateWithFlags(&e->win_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", c);
 		if ((c = cudaEventCreateWithFlags(&e->win_ready[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", c);
+		if ((c = cudaEventCreateWithFlags(&e->stage_done[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", c);
 	}
 	memcpy(e->W.w, kDefaultWeights, sizeof kDefaultWeights);
 	build_luts(e);
@@ -519,6 +522,7 @@ extern "C" void apo_destroy(apo_engine *e) {
 	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
 	for (auto &ev : e->k1_ev) cudaEventDestroy(ev);
 	for (int i = 0; i < 2; i++) { if (e->win_free[i]) cudaEventDestroy(e->win_free[i]); if (e->win_ready[i]) cudaEventDestroy(e->win_ready[i]); }
+	for (int i = 0; i < 2; i++) { if (e->stage_done[i]) cudaEventDestroy(e->stage_done[i]); if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]); }
 	if (e->own_stream) cudaStreamDestroy(e->own_stream);
 	if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
 	delete e;
@@ -881,6 +885,31 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 }
 
 namespace {
+// true when the driver does not know the pointer: ordinary pageable host memory (malloc, JS ArrayBuffer, numpy)
+bool is_pageable(const void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+	return a.type == cudaMemoryTypeUnregistered;
+}
+
+// rows x width bytes, strided -> strided, split over a few host threads (a single memcpy stream does not fill PCIe 5)
+void parallel_rows_copy(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t width, uint32_t rows) {
+	unsigned nt = std::thread::hardware_concurrency();
+	if (const char *v = getenv("APO_HOST_THREADS")) { const int x = atoi(v); if (x > 0) nt = (unsigned)x; }
+	nt = nt ? (nt > 8 ? 8 : nt) : 4;
+	const size_t total = width * rows;
+	if (nt == 1 || total < (8u << 20)) { for (uint32_t r = 0; r < rows; r++) memcpy(dst + r * dpitch, src + r * spitch, width); return; }
+	// split every row into nt column slices: works for C = 1 as well as for many short rows
+	auto work = [&](unsigned k) {
+		const size_t lo = width * k / nt, hi = width * (k + 1) / nt;
+		for (uint32_t r = 0; r < rows; r++) memcpy(dst + r * dpitch + lo, src + r * spitch + lo, hi - lo);
+	};
+	std::vector<std::thread> th;
+	for (unsigned k = 1; k < nt; k++) th.emplace_back(work, k);
+	work(0);
+	for (auto &t : th) t.join();
+}
+
 // Streams host rows [C][T] (row bytes 36 = Form D, 32 = Form R, 16 = Form R16) through two device
 // windows: the H2D copy of chunk i+1 (copy stream) overlaps K1 on chunk i (compute stream).
 int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows, uint32_t row, uint32_t C, uint64_t T,
@@ -901,14 +930,32 @@ int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows,
 	if (Tc < (uint64_t)tile) Tc = tile;
 	if (Tc > round_up(T ? T : 1, tile)) Tc = round_up(T ? T : 1, tile);
 	for (int i = 0; i < 2; i++) CK(e->win[i].reserve((uint64_t)C * Tc * row));
+	// pageable callers (malloc / ArrayBuffer / numpy): the driver would stage such copies through one small internal
+	// buffer on the calling thread; instead gather each chunk into pinned memory with a few host threads while the
+	// previous chunk is on the wire.  Pinned or registered callers (apo_host_alloc) are read in place.
+	const bool staged = T > 0 && is_pageable(rows) && getenv("APO_NO_STAGING") == nullptr;
+	if (staged && e->h_stage_cap < (uint64_t)C * Tc * row) {
+		for (int i = 0; i < 2; i++) { if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]); e->h_stage[i] = nullptr; }
+		e->h_stage_cap = 0;
+		for (int i = 0; i < 2; i++) CK(cudaMallocHost((void **)&e->h_stage[i], (uint64_t)C * Tc * row));
+		e->h_stage_cap = (uint64_t)C * Tc * row;
+	}
 	if ((rc = begin_score(e, C))) return rc;
 	const bool recip = (o->flags & APO_SCORE_RECIP) != 0;
 	int nchunk = 0;
 	for (uint64_t t0 = 0; t0 < T; t0 += Tc, nchunk++) {
 		const int b = nchunk & 1;
 		const uint64_t n = T - t0 < Tc ? T - t0 : Tc;
+		const uint8_t *src = rows + t0 * row;
+		size_t spitch = T * row;
+		if (staged) {
+			if (nchunk >= 2) CK(cudaEventSynchronize(e->stage_done[b]));      // the copy that read this staging buffer has finished
+			parallel_rows_copy(e->h_stage[b], Tc * row, src, spitch, n * row, C);
+			src = e->h_stage[b]; spitch = Tc * row;
+		}
 		if (nchunk >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->win_free[b], 0));
-		CK(cudaMemcpy2DAsync(e->win[b].p, Tc * row, rows + t0 * row, T * row, n * row, C, cudaMemcpyHostToDevice, e->copy_stream));
+		CK(cudaMemcpy2DAsync(e->win[b].p, Tc * row, src, spitch, n * row, C, cudaMemcpyHostToDevice, e->copy_stream));
+		if (staged) CK(cudaEventRecord(e->stage_done[b], e->copy_stream));
 		CK(cudaEventRecord(e->win_ready[b], e->copy_stream));
 		CK(cudaStreamWaitEvent(e->stream, e->win_ready[b], 0));
 		apo::K1Params P{};
@@ -927,6 +974,19 @@ int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows,
 	return finish_score(e, o, C, scores, counts, topk, report);
 }
 }  // namespace
+
+extern "C" int apo_host_alloc(uint64_t bytes, void **out) {
+	if (!out) return APO_E_ARG;
+	*out = nullptr;
+	const cudaError_t c = cudaMallocHost(out, bytes ? bytes : 1);
+	if (c != cudaSuccess) { cudaGetLastError(); return fail(nullptr, c == cudaErrorMemoryAllocation ? APO_E_NOMEM : APO_E_CUDA, "cudaMallocHost(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(c)); }
+	return APO_OK;
+}
+
+extern "C" int apo_host_free(void *p) {
+	if (!p) return APO_OK;
+	return cudaFreeHost(p) == cudaSuccess ? APO_OK : APO_E_CUDA;
+}
 
 extern "C" int apo_score_host(apo_engine *e, const apo_score_opts *o, const float *dims, uint32_t C, uint64_t T,
                               double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {

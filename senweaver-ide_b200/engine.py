@@ -87,7 +87,7 @@ ABI_SYMBOLS = (
     "apo_dims_compact", "apo_dims_generate_compact", "apo_dims_upload_compact", "apo_dims_layout",
     "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_rollouts16_upload",
     "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_score",
-    "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records",
+    "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records", "apo_host_alloc", "apo_host_free",
     "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy",
 )
 
@@ -165,6 +165,8 @@ def load_library() -> C.CDLL:
         f = getattr(L, name)
         if name not in ("apo_destroy", "apo_last_error", "apo_records_from_json"):
             f.restype = i32
+    L.apo_host_alloc.argtypes = [u64, C.POINTER(vp)]
+    L.apo_host_free.argtypes = [vp]
     L.apo_records_from_json.argtypes = [C.c_char_p, u64, vp, u64, C.POINTER(u64)]
     L.apo_records_from_json.restype = C.c_int64
     L.apo_corpus_upload_json.argtypes = [vp, C.c_char_p, u64, u64, C.POINTER(u64)]
@@ -174,6 +176,33 @@ def load_library() -> C.CDLL:
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _Pinned:
+    """Owner of one apo_host_alloc block.  numpy arrays made from it (array interface) hold it as their base,
+    so the block is released when the last view goes away."""
+
+    def __init__(self, nbytes):
+        self._L, self.ptr, self.nbytes = load_library(), C.c_void_p(), int(nbytes)
+        rc = self._L.apo_host_alloc(self.nbytes, C.byref(self.ptr))
+        if rc != 0:
+            raise ApoError(rc, (self._L.apo_last_error(None) or b"").decode())
+
+    @property
+    def __array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr.value, False), "version": 3}
+
+    def __del__(self):
+        if getattr(self, "ptr", None) is not None and self.ptr.value:
+            self._L.apo_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def host_empty(shape, dtype) -> np.ndarray:
+    """Page-locked host array (apo_host_alloc): the streaming calls read it in place at PCIe line rate."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    return np.asarray(_Pinned(n)).view(dt).reshape(shape)
 
 
 def records_from_json(text: str | bytes) -> np.ndarray:

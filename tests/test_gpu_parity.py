@@ -595,3 +595,21 @@ def test_rollout_records_at_every_threshold_boundary(engine, orc):
     for i in range(0, 4000, 7):
         d, m = orc.reward_dims(flat[i])
         assert m == masks[i] and np.array_equal(np.nan_to_num(d, nan=9.0), np.nan_to_num(dims[i], nan=9.0))
+
+
+def test_host_streaming_pageable_and_pinned_inputs_agree(engine, orc, apo):
+    """apo_score_host reads page-locked memory (apo_host_alloc) in place and gathers pageable memory through its pinned
+    staging buffers on host threads; both must give the resident result (several chunks, ragged last chunk, C = 1)."""
+    for C, T in ((5, 2_100_001), (1, 300_007)):
+        dims = orc.gen_dims(0x5EED0077, 1, C, 0, T, 300, 8)
+        exp = orc.score_dims_fx(dims)
+        engine.score_host(dims, 1)                                        # pageable numpy
+        assert engine.debug_partials(C) == exp
+        pinned = apo.host_empty(dims.shape, np.float32)
+        pinned[:] = dims
+        engine.score_host(pinned, 1)
+        assert engine.debug_partials(C) == exp
+        del pinned
+    recs = orc.gen_records(0x5EED0078, orc.STREAM_ROLLOUT, 0, 3, 0, 700_001, 300, 8)
+    engine.score_host_records(recs, 2)                                    # 32-byte rows, pageable
+    assert engine.debug_partials(3) == orc.score_records_fx(recs)

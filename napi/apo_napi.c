@@ -50,6 +50,7 @@ napi_status napi_get_value_uint32(napi_env, napi_value, uint32_t *);
 napi_status napi_get_value_double(napi_env, napi_value, double *);
 napi_status napi_get_arraybuffer_info(napi_env, napi_value, void **, size_t *);
 napi_status napi_create_arraybuffer(napi_env, size_t, void **, napi_value *);
+napi_status napi_create_external_arraybuffer(napi_env, void *, size_t, napi_finalize, void *, napi_value *);
 napi_status napi_create_object(napi_env, napi_value *);
 napi_status napi_create_double(napi_env, double, napi_value *);
 napi_status napi_create_int32(napi_env, int32_t, napi_value *);
@@ -105,6 +106,20 @@ static napi_value RewardBatch(napi_env env, napi_callback_info info) {
 	}
 	napi_create_object(env, &out);
 	napi_set_named_property(env, out, "dims", vd); napi_set_named_property(env, out, "masks", vm); napi_set_named_property(env, out, "finals", vf);
+	return out;
+}
+
+/* allocPinned(bytes:number) -> ArrayBuffer over page-locked memory (apo_host_alloc).  Typed arrays built on it
+ * (the dims / record buffers handed to score) are read in place by the streaming calls at PCIe line rate; ordinary
+ * ArrayBuffers work too, through the library's staging path, at about half that. */
+static void pinned_finalize(napi_env env, void *data, void *hint) { (void)env; (void)hint; apo_host_free(data); }
+
+static napi_value AllocPinned(napi_env env, napi_callback_info info) {
+	size_t argc = 1; napi_value argv[1], out; double bytes = 0; void *p = NULL;
+	napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+	napi_get_value_double(env, argv[0], &bytes);
+	if (bytes < 0 || apo_host_alloc((uint64_t)bytes, &p) != APO_OK) { napi_throw_error(env, "APO_E_NOMEM", apo_last_error(NULL)); return NULL; }
+	napi_create_external_arraybuffer(env, p, (size_t)bytes, pinned_finalize, NULL, &out);
 	return out;
 }
 
@@ -188,6 +203,7 @@ NAPI_MODULE_INIT() {
 	const napi_property_descriptor props[] = {
 	    {"create", NULL, Create, NULL, NULL, NULL, napi_default, NULL},
 	    {"rewardBatch", NULL, RewardBatch, NULL, NULL, NULL, napi_default, NULL},
+	    {"allocPinned", NULL, AllocPinned, NULL, NULL, NULL, napi_default, NULL},
 	    {"recordsFromJson", NULL, RecordsFromJson, NULL, NULL, NULL, napi_default, NULL},
 	    {"score", NULL, Score, NULL, NULL, NULL, napi_default, NULL},
 	};

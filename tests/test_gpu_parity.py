@@ -600,7 +600,7 @@ def test_rollout_records_at_every_threshold_boundary(engine, orc):
 def test_host_streaming_pageable_and_pinned_inputs_agree(engine, orc, apo):
     """apo_score_host reads page-locked memory (apo_host_alloc) in place and gathers pageable memory through its pinned
     staging buffers on host threads; both must give the resident result (several chunks, ragged last chunk, C = 1)."""
-    for C, T in ((5, 2_100_001), (1, 300_007)):
+    for C, T in ((5, 4_700_001), (1, 300_007)):          # 846 MB = 4 windows of 256 MB: staging buffers are reused
         dims = orc.gen_dims(0x5EED0077, 1, C, 0, T, 300, 8)
         exp = orc.score_dims_fx(dims)
         engine.score_host(dims, 1)                                        # pageable numpy

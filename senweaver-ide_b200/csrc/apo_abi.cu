@@ -876,12 +876,15 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	const double scan_ms = (double)e->corpus_T * 3.35e-7 * (148.0 / (double)e->sm_count);
 	const bool fuse = wants_corpus(e, o) && count > 0 && getenv("APO_NO_FUSE") == nullptr &&
 	                  (k1_ms > 1.3 * scan_ms || getenv("APO_FORCE_FUSE") != nullptr);      // env switches: tests / experiments
-	if (fuse) {
+	// without a corpus request the same tail still saves the K3 launch at one rank: an empty scan, then the last CTA finalises
+	const bool tail_only = !wants_corpus(e, o) && e->nranks == 1 && count > 0 && getenv("APO_NO_FUSE") == nullptr;
+	if (fuse || tail_only) {
 		if ((rc = arm_corpus(e, C))) return rc;
-		const apo::K2Params k2 = make_k2(e, C, make_fin(e, C, o->K, 1));
+		apo::K2Params k2 = make_k2(e, C, make_fin(e, C, o->K, fuse ? 1 : 0));
+		if (tail_only) { k2.T = 0; k2.recs = nullptr; }
 		if ((rc = launch_k1_resident(e, o, 0, first, count, &k2))) return rc;
 	} else if ((rc = launch_k1_resident(e, o, 0, first, count))) return rc;
-	return finish_score(e, o, C, scores, counts, topk, report, fuse);
+	return finish_score(e, o, C, scores, counts, topk, report, fuse || tail_only);
 }
 
 namespace {

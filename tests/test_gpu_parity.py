@@ -519,6 +519,8 @@ def test_fused_and_standalone_corpus_paths_agree(engine, orc, monkeypatch):
         check_report(a.report, ref)
         check_report(b.report, ref)
         assert np.array_equal(a.scores, b.scores) and np.array_equal(a.topk, b.topk)
+        c = engine.score(C, 4, source=src)                      # no corpus request: still one launch (empty scan + last-CTA finalise)
+        assert c.timing.launches == 1 and np.array_equal(c.scores, a.scores) and np.array_equal(c.topk, a.topk)
 
 
 def test_plain_c_client_runs(engine, apo, tmp_path):

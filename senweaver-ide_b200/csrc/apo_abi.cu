@@ -292,6 +292,67 @@ int compact_finish(apo_engine *e, uint32_t C, uint64_t T, uint64_t pitch) {
 	return APO_OK;
 }
 
+// true when the driver does not know the pointer: ordinary pageable host memory (malloc, JS ArrayBuffer, numpy)
+bool is_pageable(const void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+	return a.type == cudaMemoryTypeUnregistered;
+}
+
+// rows x width bytes, strided -> strided, split over a few host threads (a single memcpy stream does not fill PCIe 5)
+void parallel_rows_copy(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t width, uint32_t rows) {
+	unsigned nt = std::thread::hardware_concurrency();
+	if (const char *v = getenv("APO_HOST_THREADS")) { const int x = atoi(v); if (x > 0) nt = (unsigned)x; }
+	else nt = nt ? (nt > 16 ? 16 : nt) : 4;        // default: at most 16 (measured: 4 / 8 / 16 / 32 threads -> 15 / 22-29 / 30 / 25 GB/s); APO_HOST_THREADS overrides
+	if (nt > 64) nt = 64;
+	const size_t total = width * rows;
+	if (nt == 1 || total < (8u << 20)) { for (uint32_t r = 0; r < rows; r++) memcpy(dst + r * dpitch, src + r * spitch, width); return; }
+	// split every row into nt column slices: works for C = 1 as well as for many short rows
+	auto work = [&](unsigned k) {
+		const size_t lo = width * k / nt, hi = width * (k + 1) / nt;
+		for (uint32_t r = 0; r < rows; r++) memcpy(dst + r * dpitch + lo, src + r * spitch + lo, hi - lo);
+	};
+	std::vector<std::thread> th;
+	for (unsigned k = 1; k < nt; k++) th.emplace_back(work, k);
+	work(0);
+	for (auto &t : th) t.join();
+}
+
+// two page-locked staging buffers of at least `bytes` each (kept for the life of the handle)
+int ensure_stage(apo_engine *e, uint64_t bytes) {
+	if (e->h_stage_cap >= bytes) return APO_OK;
+	for (int i = 0; i < 2; i++) { if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]); e->h_stage[i] = nullptr; }
+	e->h_stage_cap = 0;
+	for (int i = 0; i < 2; i++) CK(cudaMallocHost((void **)&e->h_stage[i], bytes));
+	e->h_stage_cap = bytes;
+	return APO_OK;
+}
+
+// rows x width bytes host -> device on `st` (asynchronous for page-locked sources; a pageable source is fully consumed
+// when this returns).  Large pageable sources go through the staging buffers in column slices of all rows.
+int h2d_rows(apo_engine *e, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, uint32_t rows, cudaStream_t st) {
+	const uint64_t total = (uint64_t)width * rows;
+	if (total < (64ull << 20) || !is_pageable(src) || getenv("APO_NO_STAGING") != nullptr) {
+		CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, st));
+		return APO_OK;
+	}
+	const uint64_t cap = 256ull << 20;
+	int rc = ensure_stage(e, cap);
+	if (rc) return rc;
+	size_t W = (size_t)(cap / rows) & ~(size_t)255;            // slice width per row, 256-byte granular
+	if (W == 0) W = 256;
+	int k = 0;
+	for (size_t w0 = 0; w0 < width; w0 += W, k++) {
+		const int b = k & 1;
+		const size_t w = width - w0 < W ? width - w0 : W;
+		if (k >= 2) CK(cudaEventSynchronize(e->stage_done[b]));
+		parallel_rows_copy(e->h_stage[b], W, (const uint8_t *)src + w0, spitch, w, rows);
+		CK(cudaMemcpy2DAsync((uint8_t *)dst + w0, dpitch, e->h_stage[b], W, w, rows, cudaMemcpyHostToDevice, st));
+		CK(cudaEventRecord(e->stage_done[b], st));
+	}
+	return APO_OK;
+}
+
 struct ResultLayout { uint64_t off_scores, off_counts, off_topk, off_report, bytes; };
 ResultLayout result_layout(uint32_t C, uint32_t K) {
 	ResultLayout L;
@@ -583,7 +644,7 @@ extern "C" int apo_corpus_upload(apo_engine *e, const apo_record *recs, uint64_t
 	if (T && !recs) return fail(e, APO_E_ARG, "recs is NULL");
 	CK(cudaSetDevice(e->device));
 	CK(e->corpus.reserve(T ? T : 1));
-	if (T) CK(cudaMemcpyAsync(e->corpus.p, recs, T * sizeof(apo_record), cudaMemcpyHostToDevice, e->stream));
+	if (T) { const int rc = h2d_rows(e, e->corpus.p, T * sizeof(apo_record), recs, T * sizeof(apo_record), T * sizeof(apo_record), 1, e->stream); if (rc) return rc; }
 	CK(cudaStreamSynchronize(e->stream));
 	e->corpus_T = T; e->corpus_base = idx_base;
 	return APO_OK;
@@ -639,7 +700,7 @@ extern "C" int apo_dims_upload(apo_engine *e, const float *dims, uint32_t C, uin
 	if (C && T) {
 		// pad evaluations of every row are all-NaN = finalReward null
 		if (pitch != T) CK(cudaMemsetAsync(e->dims.p, 0xFF, (uint64_t)C * pitch * APO_NDIM * 4, e->stream));
-		CK(cudaMemcpy2DAsync(e->dims.p, pitch * APO_NDIM * 4, dims, T * APO_NDIM * 4, T * APO_NDIM * 4, C, cudaMemcpyHostToDevice, e->stream));
+		{ const int rc = h2d_rows(e, e->dims.p, pitch * APO_NDIM * 4, dims, T * APO_NDIM * 4, T * APO_NDIM * 4, C, e->stream); if (rc) return rc; }
 	}
 	CK(cudaStreamSynchronize(e->stream));
 	e->dims_ptr = e->dims.p; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch; e->compact = false;
@@ -742,8 +803,8 @@ extern "C" int apo_dims_upload_compact(apo_engine *e, const float *dims, uint32_
 	if (!e) return APO_E_ARG;
 	if (C && T && !dims) return fail(e, APO_E_ARG, "dims is NULL");
 	return compact_stream(e, C, T, [&](uint32_t cb, uint32_t cn, float *stage, uint64_t pitch) -> int {
-		CK(cudaMemcpy2DAsync(stage, pitch * APO_NDIM * 4, dims + (uint64_t)cb * T * APO_NDIM, T * APO_NDIM * 4, T * APO_NDIM * 4, cn,
-		                     cudaMemcpyHostToDevice, e->stream));
+		const int rc = h2d_rows(e, stage, pitch * APO_NDIM * 4, dims + (uint64_t)cb * T * APO_NDIM, T * APO_NDIM * 4, T * APO_NDIM * 4, cn, e->stream);
+		if (rc) return rc;
 		CK(cudaStreamSynchronize(e->stream));              // the host chunk may be reused by the caller after return
 		return APO_OK;
 	});
@@ -758,7 +819,7 @@ int rollouts_upload_rows(apo_engine *e, const void *recs, uint32_t row, uint32_t
 	CK(e->roll.reserve((uint64_t)(C ? C : 1) * pitch * row));
 	if (C && T) {
 		if (pitch != T) CK(cudaMemsetAsync(e->roll.p, 0, (uint64_t)C * pitch * row, e->stream));   // VALID clear
-		CK(cudaMemcpy2DAsync(e->roll.p, pitch * row, recs, T * row, T * row, C, cudaMemcpyHostToDevice, e->stream));
+		{ const int rc = h2d_rows(e, e->roll.p, pitch * row, recs, T * row, T * row, C, e->stream); if (rc) return rc; }
 	}
 	CK(cudaStreamSynchronize(e->stream));
 	e->roll_C = C; e->roll_T = T; e->roll_pitch = pitch; e->roll_row = row;
@@ -888,32 +949,6 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 }
 
 namespace {
-// true when the driver does not know the pointer: ordinary pageable host memory (malloc, JS ArrayBuffer, numpy)
-bool is_pageable(const void *p) {
-	cudaPointerAttributes a;
-	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
-	return a.type == cudaMemoryTypeUnregistered;
-}
-
-// rows x width bytes, strided -> strided, split over a few host threads (a single memcpy stream does not fill PCIe 5)
-void parallel_rows_copy(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t width, uint32_t rows) {
-	unsigned nt = std::thread::hardware_concurrency();
-	if (const char *v = getenv("APO_HOST_THREADS")) { const int x = atoi(v); if (x > 0) nt = (unsigned)x; }
-	else nt = nt ? (nt > 16 ? 16 : nt) : 4;        // default: at most 16 (measured: 4 / 8 / 16 / 32 threads -> 15 / 22-29 / 30 / 25 GB/s); APO_HOST_THREADS overrides
-	if (nt > 64) nt = 64;
-	const size_t total = width * rows;
-	if (nt == 1 || total < (8u << 20)) { for (uint32_t r = 0; r < rows; r++) memcpy(dst + r * dpitch, src + r * spitch, width); return; }
-	// split every row into nt column slices: works for C = 1 as well as for many short rows
-	auto work = [&](unsigned k) {
-		const size_t lo = width * k / nt, hi = width * (k + 1) / nt;
-		for (uint32_t r = 0; r < rows; r++) memcpy(dst + r * dpitch + lo, src + r * spitch + lo, hi - lo);
-	};
-	std::vector<std::thread> th;
-	for (unsigned k = 1; k < nt; k++) th.emplace_back(work, k);
-	work(0);
-	for (auto &t : th) t.join();
-}
-
 // Streams host rows [C][T] (row bytes 36 = Form D, 32 = Form R, 16 = Form R16) through two device
 // windows: the H2D copy of chunk i+1 (copy stream) overlaps K1 on chunk i (compute stream).
 int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows, uint32_t row, uint32_t C, uint64_t T,
@@ -938,12 +973,7 @@ int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows,
 	// buffer on the calling thread; instead gather each chunk into pinned memory with a few host threads while the
 	// previous chunk is on the wire.  Pinned or registered callers (apo_host_alloc) are read in place.
 	const bool staged = T > 0 && is_pageable(rows) && getenv("APO_NO_STAGING") == nullptr;
-	if (staged && e->h_stage_cap < (uint64_t)C * Tc * row) {
-		for (int i = 0; i < 2; i++) { if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]); e->h_stage[i] = nullptr; }
-		e->h_stage_cap = 0;
-		for (int i = 0; i < 2; i++) CK(cudaMallocHost((void **)&e->h_stage[i], (uint64_t)C * Tc * row));
-		e->h_stage_cap = (uint64_t)C * Tc * row;
-	}
+	if (staged && (rc = ensure_stage(e, (uint64_t)C * Tc * row))) return rc;
 	if ((rc = begin_score(e, C))) return rc;
 	const bool recip = (o->flags & APO_SCORE_RECIP) != 0;
 	int nchunk = 0;

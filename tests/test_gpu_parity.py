@@ -615,3 +615,27 @@ def test_host_streaming_pageable_and_pinned_inputs_agree(engine, orc, apo):
     recs = orc.gen_records(0x5EED0078, orc.STREAM_ROLLOUT, 0, 3, 0, 700_001, 300, 8)
     engine.score_host_records(recs, 2)                                    # 32-byte rows, pageable
     assert engine.debug_partials(3) == orc.score_records_fx(recs)
+
+
+def test_large_pageable_uploads_go_through_staging(engine, orc, monkeypatch):
+    """apo_dims_upload / apo_rollouts_upload / apo_corpus_upload of >= 64 MB pageable arrays are gathered through the pinned
+    staging buffers in column slices (three slices for the 605 MB case); the resident bytes must be exactly the input."""
+    C, T = 4, 4_200_001
+    dims = orc.gen_dims(0x5EED0079, 0, C, 0, T, 300, 8)
+    engine.dims_upload(dims)
+    for c, (a, n) in ((0, (0, 5000)), (3, (T - 7001, 7001)), (2, (2_000_000, 4096))):
+        assert engine.dims_download(c, a, n).tobytes() == dims[c, a:a + n].tobytes()
+    engine.score(C, 1)
+    staged = engine.debug_partials(C)
+    monkeypatch.setenv("APO_NO_STAGING", "1")
+    engine.dims_upload(dims)
+    engine.score(C, 1)
+    monkeypatch.delenv("APO_NO_STAGING")
+    assert engine.debug_partials(C) == staged == orc.score_dims_fx(dims)
+    recs = orc.gen_records(0x5EED007A, orc.STREAM_ROLLOUT, 0, 3, 0, 700_001, 300, 8)          # 67 MB
+    engine.rollouts_upload(recs)
+    assert engine.rollouts_download(2, 699_000, 1001).tobytes() == recs[2, 699_000:].tobytes()
+    corpus = orc.gen_records(0x5EED007B, orc.STREAM_CORPUS, 0, 1, 0, 2_100_003, 300, 8).reshape(-1)   # 67 MB
+    engine.corpus_upload(corpus)
+    assert engine.corpus_download(2_100_000, 3).tobytes() == corpus[2_100_000:].tobytes()
+    assert engine.corpus_download(0, 4096).tobytes() == corpus[:4096].tobytes()

@@ -235,7 +235,7 @@ int apo_score_host(apo_engine *e, const apo_score_opts *o, const float *dims, ui
 int apo_score_host_records(apo_engine *e, const apo_score_opts *o, const void *recs, uint32_t row_bytes,
                            uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
                            apo_corpus_report *report);
-/* Host buffers for the streaming calls.  Any host pointer is accepted: pageable memory (malloc, a JS
+/* Host buffers for the streaming calls and the uploads.  Any host pointer is accepted: pageable memory (malloc, a JS
  * ArrayBuffer, numpy) is gathered chunk by chunk into pinned staging buffers by a few host threads while
  * the previous chunk is on the wire; memory from apo_host_alloc (page-locked) is read in place and
  * reaches PCIe line rate — the binding can hand such memory to JS as an external ArrayBuffer

@@ -313,8 +313,12 @@ void parallel_rows_copy(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t 
 		for (uint32_t r = 0; r < rows; r++) memcpy(dst + r * dpitch + lo, src + r * spitch + lo, hi - lo);
 	};
 	std::vector<std::thread> th;
-	for (unsigned k = 1; k < nt; k++) th.emplace_back(work, k);
+	unsigned started = 1;
+	try {
+		for (unsigned k = 1; k < nt; k++, started++) th.emplace_back(work, k);
+	} catch (...) {}                                   // thread limit reached: the slices not handed out are copied here
 	work(0);
+	for (unsigned k = started; k < nt; k++) work(k);
 	for (auto &t : th) t.join();
 }
 

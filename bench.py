@@ -176,6 +176,15 @@ def run_reference(args):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     v = Cn * T / dt
+    # the same step when the caller holds trace records (the reference's own representation) instead of dims:
+    # TCS:668-763 per evaluation + the mean — the CPU side of the e2e_records16 leg of the GPU arm
+    roll = oracle.gen_records(SEED, oracle.STREAM_ROLLOUT, 0, Cn, 0, T, 300, threads)
+    oracle.score_records(roll, nthreads=threads)
+    t0 = time.perf_counter()
+    nrec = max(2, args.steps // 2)
+    for _ in range(nrec):
+        oracle.score_records(roll, nthreads=threads)
+    v_rec = Cn * T / ((time.perf_counter() - t0) / nrec)
     sample = f"{Cn} candidates x {T} records + {T}-record corpus per step (bounded sample of 256 x 10M), C oracle port, {threads} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -184,6 +193,7 @@ def run_reference(args):
         "config": {"workload": "configs[2] 256-beam x 10M-span finalReward + detect6 + top-K (bounded CPU sample)", "C": Cn, "T": T},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "from_records": {"value": v_rec, "unit": UNIT, "note": "same sample as per-(candidate, record) trace records: dims derived per evaluation on the CPU"},
     }))
 
 

@@ -5,12 +5,17 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        # the reference arm: CPU oracle, all host threads
 
-A "step" is one pass of the hot path over the resident workload:
-K1 reward9 (Form D, 36 B/eval) -> K2 detect6 over the corpus (+ fused segmented sum and
-radix top-K at one rank; ncclAllReduce + K3 at N > 1) -> result block to the host.
-Workload at N=1: BASELINE configs[2] = 256 candidates x 10 M records (92.16 GB resident) + the
-10 M-record corpus; weak scaling: every rank holds 256 x 10 M, the global record axis is
-N x 10 M, sharded with no data-path collective except the one allreduce of the partials.
+A "step" is one pass of the hot path over the resident workload — ONE kernel launch per rank:
+K1 reward9 (Form D, 36 B/eval) with the K2 detect6 corpus scan on its spare warp; the last CTA
+joins the shards' int64 partial vectors over NVLink peer memory (N > 1) and runs K3 (segmented
+sum + radix top-K); the result block lands in the caller's page-locked buffer.
+
+Workload: BASELINE configs[2] = 256 candidates x 10 M records (92.16 GB) + the 10 M-record corpus.
+N > 1, default `--scaling strong`: the SAME 256 x 10 M is sharded over the record axis (T_global
+fixed, T_per_gpu = T_global / N; SURVEY 8d config 3 "T-sharded for 2/4/8") — `value` is that;
+the weak-scaling number (256 x 10 M per GPU) is measured in the same run and reported beside it
+under "weak_scaling".  Every measured number carries a parity block checked against the CPU oracle
+outside the timed region; a mismatch makes the run exit non-zero.
 """
 from __future__ import annotations
 
@@ -34,16 +39,16 @@ SEED = 0x5EED0003
 
 
 def read_traffic(C, T):
-    """DRAM bytes of one K1 launch from the committed ncu capture (profiles/traffic.json); None when the
-    benchmarked configuration is not the profiled one."""
+    """DRAM bytes of one fused K1 launch from the committed ncu capture (profiles/traffic.json) and the capture's name;
+    (None, None) when the benchmarked launch is not the profiled one (other shape, or a changed kernel)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)["k_reward9"]
         if (t["C"], t["T"]) == (C, T):
-            return t["dram_bytes_read"] + t["dram_bytes_write"]
+            return t["dram_bytes_read"] + t["dram_bytes_write"], t.get("source", "profiles/traffic.json")
     except Exception:
         pass
-    return None
+    return None, None
 
 
 def read_peak():
@@ -124,77 +129,282 @@ def bind_to_gpu_numa_node(local: int) -> str:
     return "numa binding skipped"
 
 
-def cpu_baseline(threads: int, target_s: float = 12.0) -> dict:
-    """The oracle (C port of the reference TypeScript) timed on this box's host cores on a
-    bounded sample of the same workload: `C` candidates x `T` records of the same generator."""
-    import oracle
-    oracle.build()
-    Cn, T = 32, 200_000
-    dims = oracle.gen_dims(SEED, 0, Cn, 0, T, 300, threads)
-    t0 = time.perf_counter()
-    oracle.score_dims(dims, nthreads=threads)
-    dt = time.perf_counter() - t0
-    reps = max(1, min(200, int(target_s / max(dt, 1e-3))))
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        s, n = oracle.score_dims(dims, nthreads=threads)
-    dt = (time.perf_counter() - t0) / reps
-    # the parity oracle itself: one thread, exact reference order (SURVEY 8d "CPU baseline" (i)); ~3 s
-    t0 = time.perf_counter()
-    one = 0
-    while time.perf_counter() - t0 < 3.0:
-        oracle.score_dims(dims[:8], nthreads=1)
-        one += 1
-    dt1 = (time.perf_counter() - t0) / one
-    return {"value": Cn * T / dt, "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": 8 * T / dt1,
-            "sample": f"{Cn} candidates x {T} records of the configs[2] generator (seed {SEED:#x}), {reps} passes, "
-                      f"oracle/apo_oracle.c orc_score_dims_mt; the reference TypeScript cannot run here (no JS runtime)"}
+def host_cpu_budget() -> dict:
+    """What the box really gives this process: affinity mask and the cgroup CPU quota (a quota below the mask
+    bounds every multi-threaded CPU number of this run)."""
+    out = {"affinity_cpus": len(os.sched_getaffinity(0))}
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        out["cgroup_cpu_max"] = "unlimited" if q == "max" else round(int(q) / int(p), 2)
+    except Exception:
+        out["cgroup_cpu_max"] = "unknown"
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample_shape(C: int):
+    """Bounded sample of configs[2] at its true candidate : record ratio: C x Ts Form D + a Ts-record corpus, sized to
+    a quarter of the free host memory (256 x 1 M = 9.2 GB when it fits)."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 16 << 30
+    Ts = int(min(1_000_000, (avail // 4) // (C * 36 + 32)))
+    return C, max(Ts // 1000 * 1000, 10_000)
+
+
+class CpuArm:
+    """The reference's CPU implementation of the step = the oracle port (the reference is TypeScript; no JS runtime
+    exists here or on the GPU box): orc_score_dims_mt + orc_topk + orc_report_build_mt on all host threads."""
+
+    def __init__(self, C: int):
+        import oracle
+        oracle.build()
+        self.orc = oracle
+        self.threads = len(os.sched_getaffinity(0))
+        self.C, self.T = cpu_sample_shape(C)
+        t0 = time.perf_counter()
+        self.dims = oracle.gen_dims(SEED, 0, self.C, 0, self.T, 300, self.threads)
+        self.recs = oracle.gen_records(SEED, oracle.STREAM_CORPUS, 0, 1, 0, self.T, 300, self.threads).reshape(-1)
+        self.gen_s = time.perf_counter() - t0
+
+    def step(self):
+        s, n = self.orc.score_dims(self.dims, nthreads=self.threads)
+        self.orc.topk(s, self.C // 4)
+        self.orc.report(self.recs, nthreads=self.threads)
+
+    def time_steps(self, steps: int, warmup: int):
+        for _ in range(warmup):
+            self.step()
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            self.step()
+            ts.append(time.perf_counter() - t0)
+        return ts
+
+    def single_thread_rate(self, seconds: float = 3.0) -> float:
+        """The parity oracle itself: one thread, exact reference order (SURVEY 8d "CPU baseline" (i))."""
+        sub = self.dims[:2]
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds:
+            self.orc.score_dims(sub, nthreads=0)
+            n += 1
+        return 2 * self.T * n / (time.perf_counter() - t0)
+
+    def describe(self, ts) -> dict:
+        med = float(np.median(ts))
+        return {"value": self.C * self.T / med, "unit": UNIT, "cores": self.threads, "kind": "port",
+                "sample": f"{self.C} candidates x {self.T} records Form D ({self.C * self.T * 36 / 1e9:.2f} GB) + {self.T}-record corpus per step "
+                          f"(configs[2] generator, seed {SEED:#x}, true candidate:record ratio), {len(ts)} timed steps after warm-up; "
+                          f"oracle/apo_oracle.c on a persistent pinned thread pool (orc_score_dims_mt + orc_topk + orc_report_build_mt); "
+                          f"the reference TypeScript cannot run here (no JS runtime)",
+                "ms_per_step_median": med * 1e3, "ms_per_step_min": min(ts) * 1e3, "ms_per_step_max": max(ts) * 1e3,
+                "spread": (max(ts) - min(ts)) / med, "host_GBps": (self.C * self.T * 36 + self.T * 32) / med / 1e9,
+                "host": host_cpu_budget()}
+
+
+def cpu_baseline(C: int, target_s: float = 12.0) -> dict:
+    arm = CpuArm(C)
+    one = arm.time_steps(1, 1)[0]
+    steps = max(5, min(200, int(target_s / max(one, 1e-3))))
+    d = arm.describe(arm.time_steps(steps, 1))
+    d["single_thread_value"] = arm.single_thread_rate()
+    d["speedup_vs_single_thread"] = d["value"] / d["single_thread_value"]
+    return d
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path = the oracle port
-    (the reference is TypeScript and no JS runtime exists here), all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, on a bounded sample of
+    the GPU arm's config (same metric / unit).  Rank 0 alone runs and prints."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import oracle
-    oracle.build()
-    threads = len(os.sched_getaffinity(0))
-    Cn, T = 32, 200_000                       # bounded sample of configs[2] (256 x 10 M)
-    dims = oracle.gen_dims(SEED, 0, Cn, 0, T, 300, threads)
-    recs = oracle.gen_records(SEED, oracle.STREAM_CORPUS, 0, 1, 0, T, 300, threads).reshape(-1)
-
-    def step():
-        s, n = oracle.score_dims(dims, nthreads=threads)
-        oracle.topk(s, Cn // 4)
-        oracle.report(recs)
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    v = Cn * T / dt
+    arm = CpuArm(args.candidates)
+    ts = arm.time_steps(args.steps, args.warmup)
+    d = arm.describe(ts)
+    dt = float(np.mean(ts))
+    v = arm.C * arm.T / dt
+    d["value"] = v
     # the same step when the caller holds trace records (the reference's own representation) instead of dims:
-    # TCS:668-763 per evaluation + the mean — the CPU side of the e2e_records16 leg of the GPU arm
-    roll = oracle.gen_records(SEED, oracle.STREAM_ROLLOUT, 0, Cn, 0, T, 300, threads)
-    oracle.score_records(roll, nthreads=threads)
+    # TCS:668-763 per evaluation + the mean — the CPU side of the e2e_records16 leg of the GPU arm (32-candidate slice)
+    Cr = min(32, arm.C)
+    roll = arm.orc.gen_records(SEED, arm.orc.STREAM_ROLLOUT, 0, Cr, 0, arm.T, 300, arm.threads)
+    arm.orc.score_records(roll, nthreads=arm.threads)
     t0 = time.perf_counter()
     nrec = max(2, args.steps // 2)
     for _ in range(nrec):
-        oracle.score_records(roll, nthreads=threads)
-    v_rec = Cn * T / ((time.perf_counter() - t0) / nrec)
-    sample = f"{Cn} candidates x {T} records + {T}-record corpus per step (bounded sample of 256 x 10M), C oracle port, {threads} threads"
+        arm.orc.score_records(roll, nthreads=arm.threads)
+    v_rec = Cr * arm.T / ((time.perf_counter() - t0) / nrec)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[2] 256-beam x 10M-span finalReward + detect6 + top-K (bounded CPU sample)", "C": Cn, "T": T},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling if args.gpus > 1 else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"configs[2] {args.candidates}-beam x 10M-span finalReward + detect6 + top-K "
+                               f"(bounded CPU sample: {arm.C} x {arm.T} + {arm.T}-record corpus per step)", "C": arm.C, "T": arm.T},
+        "cpu_baseline": d,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "from_records": {"value": v_rec, "unit": UNIT, "note": "same sample as per-(candidate, record) trace records: dims derived per evaluation on the CPU"},
+        "from_records": {"value": v_rec, "unit": UNIT, "note": f"{Cr} x {arm.T} per-(candidate, record) trace records: dims derived per evaluation on the CPU"},
     }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class Harness:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.all_cpus = os.sched_getaffinity(0)
+        self.numa_note = bind_to_gpu_numa_node(self.local) if self.world > 1 else "single rank: no binding"
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.pkg = importlib.import_module("senweaver-ide_b200")
+        self.stream = torch.cuda.current_stream()
+
+    def engine(self):
+        eng = self.pkg.Engine(self.local)
+        if self.world > 1:
+            box = [self.pkg.Engine.comm_unique_id() if self.rank == 0 else None]
+            self.dist.broadcast_object_list(box, src=0)
+            eng.comm_init(self.world, self.rank, box[0])
+        return eng
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, steps: int, warmup: int, sampler=None):
+        """W warm-up calls, then exactly `steps` calls between barrier + synchronize, CUDA events on the launching
+        stream, max over ranks.  Returns (ms per step, list of per-step results)."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.3)
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        res = []
+        w0 = time.perf_counter()
+        ev0.record(self.stream)
+        for _ in range(steps):
+            res.append(fn())
+        ev1.record(self.stream)
+        self.barrier()
+        w1 = time.perf_counter()
+        ms = self.max_over_ranks(ev0.elapsed_time(ev1) / steps)
+        return ms, res, (w0, w1)
+
+
+def check_parity(H: Harness, eng, C: int, K: int, shards, last, layout_name: str, budget_s: float) -> dict:
+    """Oracle parity of the measured configuration, outside the timed region:
+      * full record axis: exact integer sums of the oracle (orc_score_generated_fx, the generator restated in C) for the
+        candidates on both sides of the top-K boundary, the best one and a spread of others — as many as `budget_s` allows,
+        all C when it fits; compared with the joined int64 partials with NO tolerance;
+      * spot windows on every rank's shard (3 windows x 3 candidates per shard), exact;
+      * scores == correctly rounded quotient of the exact sums, top-K == (score desc, index asc) order of them;
+      * the whole corpus report (tallies, byMode, pattern counts / flags / severities / first-3 examples, per-dimension
+        counts exactly; averages within 1e-5 relative) against orc_report_generated over all T_global records."""
+    pkg, rank, world = H.pkg, H.rank, H.world
+    sh = pkg.sharding
+    out = {"layout": layout_name}
+    tA = time.perf_counter()
+    Tg = shards[-1][1]                                                     # shards: [first, last) of every rank, rank order
+    Tmin = min(b - a for a, b in shards)
+    sums, counts = eng.debug_partials(C)                                  # joined integers of the last timed step
+    # windows: every rank scores the same relative window of its own shard; the join adds them up
+    tail = max(0, (Tmin - 1000) // 8 * 8)
+    rel = [(0, min(2048, Tmin)), ((Tmin // 2) // 8 * 8, min(2048, Tmin - (Tmin // 2) // 8 * 8)), (tail, Tmin - tail)]
+    wcands = sorted({0, C // 2, C - 1})
+    win_parts = []
+    for first, count in rel:
+        eng.score(C, 1, first=first, count=count)
+        win_parts.append(eng.debug_partials(C))
+    ok = True
+    if rank == 0:
+        import oracle
+        oracle.build()
+        nthreads = len(H.all_cpus)
+        os.sched_setaffinity(0, H.all_cpus)
+        exp_scores = sh.scores_from_partials(sums, counts)
+        out["scores_from_exact_sums"] = bool(np.array_equal(exp_scores, last.scores))
+        order = sh.topk_indices(exp_scores, C)
+        out["topk_consistent"] = bool(np.array_equal(order[:K], last.topk))
+        # candidates to verify on the full record axis, most important first
+        prio = [int(order[0]), int(order[K - 1])] + ([int(order[K])] if K < C else []) + [int(order[-1])]
+        prio += [int(x) for x in order[max(0, K - 3):K + 3]]
+        prio += [int(x) for x in np.linspace(0, C - 1, 8).astype(int)]
+        prio += [int(x) for x in order]
+        seen, cl = set(), []
+        for c in prio:
+            if c not in seen:
+                seen.add(c); cl.append(c)
+        checked, exact, tB = 0, True, time.perf_counter()
+        batch = 4
+        while checked < len(cl):
+            part = cl[checked:checked + batch]
+            es, en = oracle.score_generated_fx(SEED, part, 0, Tg, 300, nthreads=nthreads)
+            for c, s_, n_ in zip(part, es, en):
+                if sums[c] != s_ or counts[c] != n_:
+                    exact = False
+            checked += len(part)
+            el = time.perf_counter() - tB
+            if checked >= 8 and el * (checked + batch) / checked > budget_s:
+                break
+            batch = min(64, batch * 2)
+        out["full_axis_candidates_checked"] = checked
+        out["full_axis_candidates_of"] = C
+        out["full_axis_seconds"] = round(time.perf_counter() - tB, 2)
+        out["partials_exact"] = exact
+        # top-K vs the CPU reference: exact when every candidate was recomputed, else boundary-verified
+        out["topk_match"] = bool(exact and out["topk_consistent"] and out["scores_from_exact_sums"])
+        out["topk_check"] = "all candidates recomputed by the oracle" if checked == C else \
+            "top-K boundary candidates (K-th, K+1-th and neighbours), best and worst recomputed by the oracle; order of the rest follows from the exact GPU sums"
+        wins_ok, nwin = True, 0
+        for (first, count), (ws, wn) in zip(rel, win_parts):
+            for c in wcands:
+                es = en = 0
+                for r in range(world):
+                    a, b = oracle.score_generated_fx(SEED, [c], shards[r][0] + first, count, 300, nthreads=1)
+                    es += a[0]; en += b[0]
+                nwin += world
+                if ws[c] != es or wn[c] != en:
+                    wins_ok = False
+        out["windows"] = nwin
+        out["windows_exact"] = wins_ok
+        tC = time.perf_counter()
+        ref = oracle.report_generated(SEED, 0, Tg, 0, 300, nthreads=nthreads)
+        rep = last.report
+        rep_ok = (rep.total, rep.good, rep.bad, rep.none, rep.withReward, rep.toolCalls, rep.toolSucc, rep.toolFail) == \
+                 (ref.total, ref.good, ref.bad, ref.none, ref.withReward, ref.toolCalls, ref.toolSucc, ref.toolFail)
+        for m in range(5):
+            rep_ok &= list(rep.byMode[m]) == list(ref.byMode[m])
+        for p in range(6):
+            rep_ok &= (rep.pat[p].count, rep.pat[p].flag, rep.pat[p].severity, list(rep.pat[p].examples)) == \
+                      (ref.pat[p].count, ref.pat[p].flag, ref.pat[p].severity, list(ref.pat[p].examples))
+        rel_ok = abs(rep.avgReward - ref.avgReward) <= 1e-5 * max(abs(ref.avgReward), 1e-6)
+        for i in range(9):
+            rep_ok &= rep.dim[i].count == ref.dim[i].count and rep.dim[i].low_flag == ref.dim[i].low_flag and rep.dim[i].sugg_flag == ref.dim[i].sugg_flag
+            rel_ok &= abs(rep.dim[i].avg - ref.dim[i].avg) <= 1e-5 * max(abs(ref.dim[i].avg), 1e-6)
+        out["report_exact"] = bool(rep_ok)
+        out["report_means_within_1e-5"] = bool(rel_ok)
+        out["report_records"] = Tg
+        out["report_seconds"] = round(time.perf_counter() - tC, 2)
+        ok = bool(out["topk_match"] and wins_ok and rep_ok and rel_ok)
+    out["ok"] = ok
+    out["seconds"] = round(time.perf_counter() - tA, 2)
+    return out
 
 
 def main():
@@ -203,213 +413,210 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the 256 x 10M workload sharded over the ranks (default), weak = 256 x 10M per GPU")
     ap.add_argument("--candidates", type=int, default=256)
-    ap.add_argument("--records", type=int, default=10_000_000, help="records per GPU")
+    ap.add_argument("--records", type=int, default=10_000_000, help="records of the workload (strong: in total; weak: per GPU)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--recip", type=int, default=0)
     ap.add_argument("--e2e-candidates", type=int, default=64)
     ap.add_argument("--e2e-records", type=int, default=1_000_000)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the weak-scaling, compact-layout and e2e legs")
+    ap.add_argument("--parity-budget", type=float, default=20.0, help="seconds of oracle time for the full-axis parity check")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    all_cpus = os.sched_getaffinity(0)
-    numa_note = bind_to_gpu_numa_node(local) if world > 1 else "single rank: no binding"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    pkg = importlib.import_module("senweaver-ide_b200")
-    eng = pkg.Engine(local)
-    if world > 1:
-        box = [pkg.Engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        eng.comm_init(world, rank, box[0])
+    H = Harness(args)
+    torch, dist, pkg, rank, world, local = H.torch, H.dist, H.pkg, H.rank, H.world, H.local
+    sh = pkg.sharding
+    C, K = args.candidates, max(1, args.candidates // 4)
+    strong = args.scaling == "strong" or world == 1
+    Tg = args.records if strong else args.records * world
 
-    C, T, K = args.candidates, args.records, max(1, args.candidates // 4)
-    free, total = torch.cuda.mem_get_info()
-    need = C * ((T + 31) // 32 * 32) * 36 + T * 32 + (3 << 30)
+    def fit(T):
+        free, _ = torch.cuda.mem_get_info()
+        need = C * ((T + 31) // 32 * 32) * 36 + T * 32 + (3 << 30)
+        if need > free:
+            return int((free - (4 << 30)) // (C * 36 + 32)) // 1024 * 1024, f"records per GPU reduced to fit {free >> 30} GiB free"
+        return T, ""
+
+    first, last_ = sh.shard_range(Tg, world, rank)
+    T = last_ - first
     note = ""
-    if need > free:
-        T = int((free - (4 << 30)) // (C * 36 + 32)) // 1024 * 1024
-        note = f"records per GPU reduced to {T} to fit {free >> 30} GiB free"
-    t0 = rank * T
-    eng.dims_generate(SEED, 0, C, t0, T, 300)
-    eng.corpus_generate(SEED, t0, T, 300)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        eng.score(C, K, corpus=True, variant=args.variant, recip=bool(args.recip))
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k1_ms, k2_ms, ar_ms, launches = [], [], [], 0
-    w0 = time.perf_counter()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        r = eng.score(C, K, corpus=True, variant=args.variant, recip=bool(args.recip))
-        k1_ms.append(r.timing.reward_ms); k2_ms.append(r.timing.corpus_ms); ar_ms.append(r.timing.allreduce_ms + r.timing.finalize_ms)
-        launches += r.timing.launches
-    ev1.record(stream)
-    barrier()
-    w1 = time.perf_counter()
-    ms = ev0.elapsed_time(ev1) / args.steps
-    tms = torch.tensor([ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
+    if world == 1:
+        T, note = fit(T)
+        Tg = T
+    eng = H.engine()
+    eng.dims_generate(SEED, 0, C, first, T, 300)
+    eng.corpus_generate(SEED, first, T, 300)
+    eng.set_stream(H.stream.cuda_stream)
+    step = lambda: eng.score(C, K, corpus=True, variant=args.variant, recip=bool(args.recip))
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, res, (w0, w1) = H.timed(step, args.steps, args.warmup, sampler)
     clocks = sampler.stop(w0, w1) if rank == 0 else None
+    r = res[-1]
+    k1 = float(np.mean([x.timing.reward_ms for x in res]))
+    launches = int(sum(x.timing.launches for x in res))
+    join_wait = float(np.mean([x.timing.join_wait_ms for x in res]))
+    join_red = float(np.mean([x.timing.join_reduce_ms for x in res]))
+    nccl_ms = float(np.mean([x.timing.allreduce_ms + x.timing.finalize_ms for x in res]))
+    k2_ms = float(np.mean([x.timing.corpus_ms for x in res]))
+    join_mode = eng.comm_join_mode()
+    Tmax = int(H.max_over_ranks(float(T)))
+    shards = [sh.shard_range(Tg, world, q) for q in range(world)] if world > 1 else [(0, T)]
+    parity = check_parity(H, eng, C, K, shards, r, "Form D", args.parity_budget)
+    H.barrier()
 
-    # ---- the same workload held in the compact resident layout (Form Q, 14 B/eval, lossless; csrc/apo_compact.cu):
-    # transcoded once at load, scored by K1q.  Reported beside the fp32 numbers, not instead of them.
-    compact = None
-    try:
-        engq = pkg.Engine(local)
-        if world > 1:
-            box = [pkg.Engine.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(box, src=0)
-            engq.comm_init(world, rank, box[0])
-        engq.dims_generate_compact(SEED, 0, C, t0, T, 300)
-        engq.corpus_generate(SEED, t0, T, 300)
-        engq.set_stream(stream.cuda_stream)
-        for _ in range(args.warmup):
-            rq = engq.score(C, K, corpus=True)
-        same = bool(np.array_equal(rq.scores, r.scores) and np.array_equal(rq.topk, r.topk))
-        barrier()
-        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kq_ms = []
-        q0.record(stream)
-        for _ in range(args.steps):
-            rq = engq.score(C, K, corpus=True)
-            kq_ms.append(rq.timing.reward_ms)
-        q1.record(stream)
-        barrier()
-        qms = torch.tensor([q0.elapsed_time(q1) / args.steps], device="cuda")
-        if world > 1:
-            dist.all_reduce(qms, op=dist.ReduceOp.MAX)
-        qms = float(qms.item())
-        kq = float(np.mean(kq_ms))
-        compact = {"value": C * T * world / (qms * 1e-3), "unit": UNIT, "ms_per_step": qms, "bytes_per_eval": 14,
-                   "k1q_ms": kq, "k1q_GBps": 14.0 * C * T / (kq * 1e-3) / 1e9, "identical_to_fp32_layout": same,
-                   "layout": "Form Q: 8 one-byte codebook indices + fp32 tool_success_rate + 2-byte presence index per evaluation, "
-                             "lossless recoding of the same Form D tensor done once at load (apo_dims_generate_compact)"}
-        engq.close()
-    except Exception as ex:                         # the compact path is optional: never take the primary numbers down with it
-        compact = {"error": str(ex)}
+    secondary = {}
+    if not args.no_secondary:
+        # ---- weak scaling beside the strong number (N > 1): 256 x 10M per GPU, the record axis is N x 10M
+        if world > 1 and strong:
+            Tw = args.records
+            eng.dims_generate(SEED, 0, C, rank * Tw, Tw, 300)
+            eng.corpus_generate(SEED, rank * Tw, Tw, 300)
+            wms, wres, _ = H.timed(step, args.steps, args.warmup)
+            wpar = check_parity(H, eng, C, K, [(q * Tw, (q + 1) * Tw) for q in range(world)], wres[-1], "Form D, weak", min(args.parity_budget, 10.0))
+            secondary["weak_scaling"] = {"value": C * Tw * world / (wms * 1e-3), "unit": UNIT, "ms_per_step": wms, "T_per_gpu": Tw,
+                                         "T_global": Tw * world, "k1_ms": float(np.mean([x.timing.reward_ms for x in wres])), "parity": wpar}
+            H.barrier()
+        # ---- the same workload in the compact resident layout (Form Q, 14 B/eval, lossless; csrc/apo_compact.cu)
+        try:
+            eng.dims_generate_compact(SEED, 0, C, first, T, 300)
+            eng.corpus_generate(SEED, first, T, 300)
+            qms, qres, _ = H.timed(lambda: eng.score(C, K, corpus=True), args.steps, args.warmup)
+            rq = qres[-1]
+            same = bool(np.array_equal(rq.scores, r.scores) and np.array_equal(rq.topk, r.topk))
+            qsums = eng.debug_partials(C)
+            kq = float(np.mean([x.timing.reward_ms for x in qres]))
+            secondary["compact_layout"] = {
+                "value": C * Tg / (qms * 1e-3), "unit": UNIT, "ms_per_step": qms, "bytes_per_eval": 14, "k1q_ms": kq,
+                "k1q_GBps": 14.0 * C * Tmax / (kq * 1e-3) / 1e9, "identical_to_fp32_layout": same,
+                "parity": {"ok": bool(same and parity["ok"]), "note": "scores and top-K bit-identical to the oracle-checked Form D run of the same evaluations"},
+                "layout": "Form Q: 8 one-byte codebook indices + fp32 tool_success_rate + 2-byte presence index per evaluation, "
+                          "lossless recoding of the same Form D tensor done once at load (apo_dims_generate_compact)"}
+            del qsums
+        except Exception as ex:                     # the compact path is optional: never take the primary numbers down with it
+            secondary["compact_layout"] = {"error": str(ex)}
+        H.barrier()
 
     # ---- end to end through the C ABI with HOST buffers (pinned), H2D inside the timed region
-    Ce, Te = min(args.e2e_candidates, C), min(args.e2e_records, T)
-    eng.set_stream(0)
-    eng2 = pkg.Engine(local)                                # separate handle: keeps the resident workload intact
-    eng2.dims_generate(SEED, 0, Ce, t0, Te, 300)            # device generator == oracle generator, bit for bit
-    host = torch.empty((Ce, Te, 9), dtype=torch.float32, pin_memory=True)
-    hnp = host.numpy()
-    for c in range(Ce):
-        hnp[c] = eng2.dims_download(c, 0, Te)
-    eng2.corpus_generate(SEED, t0, Te, 300)
-    hrec_t = torch.empty((Te * 32,), dtype=torch.uint8, pin_memory=True)
-    hrec = hrec_t.numpy().view(pkg.RECORD_DTYPE)
-    hrec[:] = eng2.corpus_download(0, Te)
-    Ke = max(1, Ce // 4)
+    e2e, e2e16 = None, None
+    if not args.no_secondary:
+        Ce, Te = min(args.e2e_candidates, C), min(args.e2e_records, T)
+        eng.set_stream(0)
+        eng2 = pkg.Engine(local)                                # separate handle, single rank: each rank scores its own host buffers
+        t0e = first
+        eng2.dims_generate(SEED, 0, Ce, t0e, Te, 300)           # device generator == oracle generator, bit for bit
+        host = torch.empty((Ce, Te, 9), dtype=torch.float32, pin_memory=True)
+        hnp = host.numpy()
+        for c in range(Ce):
+            hnp[c] = eng2.dims_download(c, 0, Te)
+        eng2.corpus_generate(SEED, t0e, Te, 300)
+        hrec_t = torch.empty((Te * 32,), dtype=torch.uint8, pin_memory=True)
+        hrec = hrec_t.numpy().view(pkg.RECORD_DTYPE)
+        hrec[:] = eng2.corpus_download(0, Te)
+        Ke = max(1, Ce // 4)
 
-    def e2e_step():
-        eng2.corpus_upload(hrec, idx_base=t0)
-        return eng2.score_host(hnp, Ke, corpus=True, variant=args.variant, recip=bool(args.recip))
+        def e2e_step():
+            eng2.corpus_upload(hrec, idx_base=t0e)
+            return eng2.score_host(hnp, Ke, corpus=True, variant=args.variant, recip=bool(args.recip))
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        re = e2e_step()
-    torch.cuda.synchronize()
-    e_ms = (time.perf_counter() - e0) * 1e3 / args.e2e_steps
-    ems = torch.tensor([e_ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    e_ms = float(ems.item())
-    d2h = 16 * Ce + 4 * Ke + 1024
+        def wall(fn, n):
+            for _ in range(2):
+                fn()
+            H.barrier()
+            a = time.perf_counter()
+            for _ in range(n):
+                out = fn()
+            torch.cuda.synchronize()
+            return H.max_over_ranks((time.perf_counter() - a) * 1e3 / n), out
 
-    # ---- the same call with the evaluations as packed trace records (Form R16, 16 B/eval): dims are
-    # derived on the device (TCS:668-763), 2.25x fewer bytes cross PCIe.  Reported beside the Form D number.
-    eng2.rollouts16_generate(SEED, 0, Ce, t0, Te, 300)
-    host16_t = torch.empty((Ce * Te * 16,), dtype=torch.uint8, pin_memory=True)
-    host16 = host16_t.numpy().view(pkg.RECORD16_DTYPE).reshape(Ce, Te)
-    for c in range(Ce):
-        host16[c] = eng2.rollouts16_download(c, 0, Te)
+        e_ms, re_ = wall(e2e_step, args.e2e_steps)
+        d2h = 16 * Ce + 4 * Ke + 1024
+        e2e_sums = eng2.debug_partials(Ce)
+        # ---- the same call with the evaluations as packed trace records (Form R16, 16 B/eval): dims derived on the device
+        eng2.rollouts16_generate(SEED, 0, Ce, t0e, Te, 300)
+        host16_t = torch.empty((Ce * Te * 16,), dtype=torch.uint8, pin_memory=True)
+        host16 = host16_t.numpy().view(pkg.RECORD16_DTYPE).reshape(Ce, Te)
+        for c in range(Ce):
+            host16[c] = eng2.rollouts16_download(c, 0, Te)
 
-    def e2e16_step():
-        eng2.corpus_upload(hrec, idx_base=t0)
-        return eng2.score_host_records(host16, Ke, corpus=True, variant=args.variant, recip=bool(args.recip))
+        def e2e16_step():
+            eng2.corpus_upload(hrec, idx_base=t0e)
+            return eng2.score_host_records(host16, Ke, corpus=True, variant=args.variant, recip=bool(args.recip))
 
-    for _ in range(2):
-        e2e16_step()
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e16_step()
-    torch.cuda.synchronize()
-    e16_ms = (time.perf_counter() - e0) * 1e3 / args.e2e_steps
-    ems = torch.tensor([e16_ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    e16_ms = float(ems.item())
-    eng2.close()
+        e16_ms, _ = wall(e2e16_step, args.e2e_steps)
+        e16_sums = eng2.debug_partials(Ce)
+        eng2.close()
+        # parity of the e2e legs: a few whole candidates of this rank's host buffers against the oracle
+        e2e_ok = True
+        if rank == 0:
+            import oracle
+            cl = sorted({0, Ce // 2, Ce - 1})
+            es, en = oracle.score_generated_fx(SEED, cl, t0e, Te, 300, nthreads=len(H.all_cpus))
+            e2e_ok = all(e2e_sums[0][c] == s_ and e2e_sums[1][c] == n_ for c, s_, n_ in zip(cl, es, en))
+            e16_ok = True
+            for c in cl[:2]:                                    # Form R16: dims are derived from the records (TCS:668-763) on both sides
+                roll = oracle.gen_records(SEED, oracle.STREAM_ROLLOUT, c, 1, t0e, Te, 300, 8)
+                rs, rn = oracle.score_records_fx(roll)
+                e16_ok &= (e16_sums[0][c], e16_sums[1][c]) == (rs[0], rn[0])
+                del roll
+            e2e = {"value": Ce * Te * world / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 36 + Te * 32,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "host_placement": H.numa_note,
+                   "parity": {"partials_exact": bool(e2e_ok), "candidates": cl},
+                   "workload": f"{Ce} x {Te} Form D + {Te}-record corpus from pinned host memory per rank via apo_corpus_upload + apo_score_host"}
+            e2e16 = {"value": Ce * Te * world / (e16_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 16 + Te * 32,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": e16_ms, "parity": {"partials_exact": bool(e16_ok), "candidates": cl[:2]},
+                     "workload": f"{Ce} x {Te} packed trace records (Form R16, 16 B/eval) + corpus from pinned host memory per rank via apo_score_host_records"}
 
+    rc = 0
     if rank == 0:
         peak, peak_src = read_peak()
-        k1 = float(np.mean(k1_ms))
-        fused = launches == args.steps * (1 if world == 1 else 3)            # the corpus scan rode inside the scoring launch
-        alg_bytes = 36.0 * C * T + (32.0 * T if fused else 0.0)                # 36*C*T + 32*T = 92.48 GB at configs[2]
+        one_launch = launches == args.steps
+        fused = one_launch or (world > 1 and join_mode == 1 and launches == 3 * args.steps)       # the corpus scan rode inside the scoring launch
+        alg_bytes = 36.0 * C * Tmax + (32.0 * Tmax if fused else 0.0)             # 36*C*T + 32*T = 92.48 GB at configs[2]
         achieved = alg_bytes / (k1 * 1e-3) / 1e9
+        traffic, traffic_src = read_traffic(C, Tmax)
         out = {
-            "metric": METRIC, "value": C * T * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"configs[2]: {C}-beam x {T}-record Form D (36 B/eval) resident per GPU + {T}-record corpus; "
-                                   f"K1 reward9 -> K2 detect6 + segmented sum + radix top-K (K={K})",
-                       "C": C, "T_per_gpu": T, "T_global": T * world, "K": K, "parallelism": f"record-axis shards x{world}",
+            "metric": METRIC, "value": C * Tg / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[2]: {C}-beam x {Tg}-record Form D (36 B/eval) + {Tg}-record corpus, record axis sharded x{world} "
+                                   f"({Tmax} records resident per GPU); one launch per rank: K1 reward9 + K2 detect6 scan + "
+                                   f"{'peer-memory join + ' if join_mode == 2 else ''}segmented sum + radix top-K (K={K})",
+                       "C": C, "T_per_gpu": Tmax, "T_global": Tg, "K": K, "parallelism": f"record-axis shards x{world}",
+                       "join": {0: "single rank", 1: "ncclAllReduce + k_finalize", 2: "NVLink peer-memory join inside the scoring launch"}[join_mode],
                        "l2": "inputs (>= 2.3 GB per step) exceed the 126 MB L2; no flush needed", "variant": args.variant,
                        "recip": args.recip, "note": note},
-            "roofline": {"bound": "hbm", "kernel": "k_reward9 (K1, with the K2 corpus scan on its extra warp)" if fused else "k_reward9 (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": read_traffic(C, T), "peak_source": peak_src,
-                         "alg_bytes_per_launch": alg_bytes, "k1_ms": k1, "k2_ms": float(np.mean(k2_ms)),
-                         "join_ms": float(np.mean(ar_ms))},
-            "e2e": {"value": Ce * Te * world / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 36 + Te * 32,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e_ms,
-                    "workload": f"{Ce} x {Te} Form D + {Te}-record corpus from pinned host memory per rank via apo_corpus_upload + apo_score_host"},
-            "e2e_records16": {"value": Ce * Te * world / (e16_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 16 + Te * 32,
-                              "d2h_bytes_per_step": d2h, "ms_per_step": e16_ms,
-                              "workload": f"{Ce} x {Te} packed trace records (Form R16, 16 B/eval) + corpus from pinned host memory per rank via apo_score_host_records"},
-            "compact_layout": compact,
+            "parity": parity,
+            "roofline": {"bound": "hbm", "kernel": "k_reward9 (K1, with the K2 corpus scan on its extra warp and the join + K3 tail)" if fused else "k_reward9 (K1)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "alg_bytes_per_launch": alg_bytes, "k1_ms": k1, "k2_ms": k2_ms,
+                         "join_wait_ms": join_wait, "join_reduce_ms": join_red, "join_ms": join_wait + join_red + nccl_ms},
+            "e2e": e2e, "e2e_records16": e2e16,
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        out["e2e"]["host_placement"] = numa_note
+        out.update(secondary)
         if world == 1 and not args.no_cpu_baseline:
-            os.sched_setaffinity(0, all_cpus)
-            out["cpu_baseline"] = cpu_baseline(len(os.sched_getaffinity(0)))
+            os.sched_setaffinity(0, H.all_cpus)
+            out["cpu_baseline"] = cpu_baseline(C)
+        ok = parity["ok"] and all(v.get("parity", {}).get("ok", True) for v in secondary.values() if isinstance(v, dict))
+        if e2e is not None:
+            ok = ok and e2e["parity"]["partials_exact"] and e2e16["parity"]["partials_exact"]
+        out["parity_ok"] = bool(ok)
         print(json.dumps(out))
+        rc = 0 if ok else 1
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+    sys.exit(rc)
 
 
 if __name__ == "__main__":

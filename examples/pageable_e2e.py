@@ -9,9 +9,8 @@ eng.dims_generate(0x5EED0002, 0, C, 0, T, 300)
 host = np.stack([eng.dims_download(c, 0, T) for c in range(C)])          # pageable numpy
 pin = pkg.host_empty((C, T, 9), np.float32)
 pin[:] = host
-for name, buf, env in (("pageable, driver staging (APO_NO_STAGING=1)", host, "1"), ("pageable, library staging", host, None), ("pinned (apo_host_alloc)", pin, None)):
-    if env: os.environ["APO_NO_STAGING"] = env
-    else: os.environ.pop("APO_NO_STAGING", None)
+for name, buf, env in (("pageable, driver staging (APO_TUNE_NO_STAGING)", host, "1"), ("pageable, library staging", host, None), ("pinned (apo_host_alloc)", pin, None)):
+    eng.set_tuning(pkg.TUNE_NO_STAGING if env else 0)
     eng.score_host(buf, 16)
     t0 = time.perf_counter()
     for _ in range(5):

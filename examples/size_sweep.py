@@ -15,10 +15,11 @@ for C, T in [(4, 1000), (16, 10_000), (64, 10_000), (64, 100_000), (256, 100_000
     eng.dims_generate(0x5EED0042, 0, C, 0, T, 300)
     K = max(1, C // 4)
     eng.score(C, K)
-    reps = 50 if C * T < 10**8 else 10
+    reps = 200 if C * T < 10**8 else 10
     t0 = time.perf_counter()
     for _ in range(reps):
         r = eng.score(C, K)
     wall = (time.perf_counter() - t0) / reps
-    print(json.dumps({"C": C, "T": T, "bytes": 36 * C * T, "wall_us_per_call": wall * 1e6, "device_ms": r.timing.total_ms,
+    rt = eng.score(C, K, timing=True)                 # per-stage CUDA events on request (a small call does not record them by default)
+    print(json.dumps({"C": C, "T": T, "bytes": 36 * C * T, "wall_us_per_call": wall * 1e6, "device_ms": rt.timing.total_ms,
                       "evals_per_s_wall": C * T / wall, "GBps_wall": 36 * C * T / wall / 1e9, "launches": r.timing.launches}), flush=True)

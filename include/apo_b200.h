@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define APO_ABI_VERSION 1
+#define APO_ABI_VERSION 2
 #define APO_NDIM  9   /* reward dimensions, push order of TCS:679..762 */
 #define APO_NPAT  6   /* problem patterns, APO:643-770 */
 #define APO_NMODE 5   /* 0 no metadata ('unknown', APO:632), 1 normal, 2 agent, 3 gather, 4 designer */
@@ -105,7 +105,12 @@ typedef struct apo_timing {       /* device time of the stages of the last apo_s
 	float total_ms;               /* first launch -> last kernel end          */
 	uint32_t launches;            /* kernels launched by the call             */
 	uint32_t pad;
+	float join_wait_ms;           /* peer-memory join: publish -> every rank arrived (includes rank skew), device timer */
+	float join_reduce_ms;         /* peer-memory join: NVLink reads + sum of the peers' partial vectors                 */
 } apo_timing;
+/* The *_ms stage fields come from CUDA events, which are recorded only for calls that stream >= 64 MB or set
+ * APO_SCORE_TIMING (a small call is launch-bound and every event costs it ~1 us); launches and the join_* fields
+ * (device-side timer) are always filled. */
 
 typedef struct apo_engine apo_engine;
 
@@ -121,6 +126,13 @@ const char *apo_last_error(const apo_engine *e);
 int  apo_set_stream(apo_engine *e, uint64_t cuda_stream);
 /* Replace the TCS:766-776 weights (default = reference values). */
 int  apo_set_weights(apo_engine *e, const double w[APO_NDIM]);
+/* Experiment / test switches of one handle (initial value: the environment variables APO_NO_FUSE, APO_FORCE_FUSE,
+ * APO_NO_STAGING, APO_JOIN_NCCL read once at apo_create).  Results are identical for every setting. */
+#define APO_TUNE_NO_FUSE     0x1u  /* corpus scan / finalisation as stand-alone launches                         */
+#define APO_TUNE_FORCE_FUSE  0x2u  /* corpus scan inside the scoring launch even when it cannot hide behind it   */
+#define APO_TUNE_NO_STAGING  0x4u  /* pageable host buffers straight to cudaMemcpy (no threaded pinned staging)  */
+#define APO_TUNE_NCCL_JOIN   0x8u  /* join shards with ncclAllReduce + k_finalize instead of the peer-memory join */
+int  apo_set_tuning(apo_engine *e, uint32_t flags);
 int  apo_get_weights(const apo_engine *e, double w[APO_NDIM]);
 
 /* ---- single-trace path: TraceCollectorService._computeRewardSignals (TCS:668-788) --
@@ -201,6 +213,7 @@ int apo_record_unpack16(const apo_record16 *in, uint64_t n, apo_record *out);
 #define APO_SRC_ROLLOUTS  1u
 #define APO_SCORE_CORPUS  0x1u   /* also run the 6-pattern scan over the corpus */
 #define APO_SCORE_RECIP   0x2u   /* finalReward = ws * (1/tw) from a LUT instead of ws / tw (<= 1 ulp apart) */
+#define APO_SCORE_TIMING  0x4u   /* record the per-stage CUDA events of apo_timing also for a small call */
 typedef struct apo_score_opts {
 	uint32_t K;          /* beam width (top-K), 0..min(C, 16384) */
 	uint32_t source;     /* APO_SRC_* */
@@ -249,12 +262,20 @@ int apo_last_timing(const apo_engine *e, apo_timing *out);
  * shard or rank count. */
 int apo_debug_partials(apo_engine *e, int64_t *out, uint32_t C);
 
-/* ---- multi-GPU: the record axis is sharded across ranks (one process per GPU); one
- * ncclAllReduce(sum,int64) of the packed partial vector joins the shards. */
+/* ---- multi-GPU: the record axis is sharded across ranks (one process per GPU, or one handle per GPU inside one
+ * process); the packed int64 partial vectors of the shards are joined INSIDE the scoring launch: the finalising CTA
+ * of every rank publishes its vector in a peer-mapped block, signals the other ranks and sums their vectors with
+ * NVLink loads (csrc/apo_corpus.cuh peer_join), so a sharded apo_score is still one kernel launch.  NCCL bootstraps
+ * the exchange of the peer handles and remains the fallback (ncclAllReduce(sum,int64) + a finalise launch) when
+ * peer memory is unavailable (ranks on different boxes, IPC disabled) or APO_TUNE_NCCL_JOIN is set.  Every joined
+ * call (apo_score, apo_score_finish, apo_score_host*) must be made by all ranks in the same order; a rank that never
+ * arrives makes the others fail with APO_E_NCCL after 20 s instead of hanging. */
 #define APO_UNIQUE_ID_BYTES 128
 int apo_comm_unique_id(uint8_t out[APO_UNIQUE_ID_BYTES]);
 int apo_comm_init(apo_engine *e, int nranks, int rank, const uint8_t id[APO_UNIQUE_ID_BYTES]);
 int apo_comm_destroy(apo_engine *e);
+/* 0 = single rank, 1 = ncclAllReduce join, 2 = peer-memory join inside the scoring launch */
+int apo_comm_join_mode(const apo_engine *e);
 
 #ifdef __cplusplus
 }

@@ -82,12 +82,15 @@ def lib() -> C.CDLL:
         L.orc_unpack16.restype = None
         L.orc_topk.argtypes = [dp, u32, u32, vp]
         L.orc_report_build.argtypes = [vp, u64, u64, dp, C.POINTER(Report)]
+        L.orc_report_build_mt.argtypes = [vp, u64, u64, dp, C.POINTER(Report), i32]
+        L.orc_report_generated.argtypes = [u64, u64, u64, u64, u32, dp, C.POINTER(Report), i32]
+        L.orc_score_generated_fx.argtypes = [u64, vp, u32, u64, u64, u32, dp, vp, vp, vp, i32]
         L.orc_gen_record.argtypes = [u64, u32, u32, u64, u32, vp]
         L.orc_gen_dims_row.argtypes = [u64, u32, u64, u32, vp]
         L.orc_gen_dims.argtypes = [u64, u32, u32, u64, u64, u64, u32, vp, i32]
         L.orc_gen_records.argtypes = [u64, u32, u32, u32, u64, u64, u64, u32, vp, i32]
         for f in (L.orc_score_dims_fx, L.orc_score_records_fx, L.orc_score_dims, L.orc_score_records, L.orc_score_dims_mt, L.orc_score_records_mt, L.orc_topk,
-                  L.orc_report_build, L.orc_gen_record, L.orc_gen_dims_row, L.orc_gen_dims, L.orc_gen_records):
+                  L.orc_report_build, L.orc_report_build_mt, L.orc_report_generated, L.orc_score_generated_fx, L.orc_gen_record, L.orc_gen_dims_row, L.orc_gen_dims, L.orc_gen_records):
             f.restype = None
         _lib = L
     return _lib
@@ -191,12 +194,36 @@ def topk(scores: np.ndarray, K: int) -> np.ndarray:
     return out
 
 
-def report(recs: np.ndarray, idx_base: int = 0, w=None) -> Report:
+def report(recs: np.ndarray, idx_base: int = 0, w=None, nthreads: int = 0) -> Report:
+    """nthreads == 0: single thread in exact reference order (the parity oracle); > 0: per-slice partials on the
+    thread pool (same integers and examples, binary64 sums merged per slice)."""
     recs = np.ascontiguousarray(recs, RECORD_DTYPE).reshape(-1)
     w = weights() if w is None else np.ascontiguousarray(w, np.float64)
     r = Report()
-    lib().orc_report_build(_p(recs), recs.shape[0], idx_base, _p(w), C.byref(r))
+    if nthreads > 0:
+        lib().orc_report_build_mt(_p(recs), recs.shape[0], idx_base, _p(w), C.byref(r), nthreads)
+    else:
+        lib().orc_report_build(_p(recs), recs.shape[0], idx_base, _p(w), C.byref(r))
     return r
+
+
+def report_generated(seed: int, t0: int, T: int, idx_base: int | None = None, agent_permille: int = 300, w=None,
+                     nthreads: int = 8) -> Report:
+    """Report over records [t0, t0+T) of the generator's corpus stream, generated on the fly (never materialised)."""
+    w = weights() if w is None else np.ascontiguousarray(w, np.float64)
+    r = Report()
+    lib().orc_report_generated(seed, t0, T, t0 if idx_base is None else idx_base, agent_permille, _p(w), C.byref(r), nthreads)
+    return r
+
+
+def score_generated_fx(seed: int, cands, t0: int, T: int, agent_permille: int = 300, w=None, nthreads: int = 8):
+    """Exact integer sums / counts (as score_dims_fx) of the listed candidates over generated Form D evaluations."""
+    cands = np.ascontiguousarray(cands, np.uint32)
+    w = weights() if w is None else np.ascontiguousarray(w, np.float64)
+    n = cands.shape[0]
+    lo = np.empty(n, np.uint64); hi = np.empty(n, np.int64); cnt = np.empty(n, np.uint64)
+    lib().orc_score_generated_fx(seed, _p(cands), n, t0, T, agent_permille, _p(w), _p(lo), _p(hi), _p(cnt), nthreads)
+    return [(int(h) << 64) + int(l) for l, h in zip(lo, hi)], [int(x) for x in cnt]
 
 
 def gen_records(seed: int, stream: int, c0: int, Cn: int, t0: int, T: int, agent_permille: int = 300,

@@ -9,8 +9,10 @@
  * TCS = src/vs/workbench/contrib/senweaver/common/traceCollectorService.ts
  * APO = src/vs/workbench/contrib/senweaver/common/apoService.ts
  */
+#define _GNU_SOURCE
 #include "apo_oracle.h"
 #include <math.h>
+#include <sched.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -231,21 +233,95 @@ void orc_score_records_fx(const orc_record *recs, uint32_t C, uint64_t T, uint64
 	}
 }
 
+/* ---- persistent thread pool (timing legs of bench.py and the bench-side parity checks) ----
+ * Workers are created once and parked on a condition variable; a run hands every participant
+ * (tid, nthreads) and items are claimed through an atomic counter, so a busy or slow core does not
+ * hold the others back.  Workers are pinned to the CPUs of the process's affinity mask (set ORC_PIN=0
+ * to leave them floating): pages first touched by the multi-threaded generators stay local to the
+ * thread that later reads them. */
+typedef void (*pool_fn)(void *arg, int tid, int nthreads);
+static struct {
+	pthread_mutex_t mu, run_mu;
+	pthread_cond_t go, done;
+	pthread_t *th;
+	int nworkers;              /* threads created so far (tids 1..nworkers) */
+	uint64_t gen;
+	int active, pending;
+	pool_fn fn; void *arg;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, 0, NULL, NULL};
+
+static void *pool_worker(void *p)
+{
+	const int tid = (int)(intptr_t)p;
+	uint64_t seen = 0;
+	pthread_mutex_lock(&g_pool.mu);
+	for (;;) {
+		while (g_pool.gen == seen) pthread_cond_wait(&g_pool.go, &g_pool.mu);
+		seen = g_pool.gen;
+		if (tid >= g_pool.active) continue;
+		pool_fn fn = g_pool.fn; void *arg = g_pool.arg; const int n = g_pool.active;
+		pthread_mutex_unlock(&g_pool.mu);
+		fn(arg, tid, n);
+		pthread_mutex_lock(&g_pool.mu);
+		if (--g_pool.pending == 0) pthread_cond_signal(&g_pool.done);
+	}
+	return NULL;
+}
+
+static void pool_run(pool_fn fn, void *arg, int nthreads)
+{
+	if (nthreads <= 1) { fn(arg, 0, 1); return; }
+	pthread_mutex_lock(&g_pool.run_mu);                       /* one run at a time */
+	pthread_mutex_lock(&g_pool.mu);
+	if (g_pool.nworkers < nthreads - 1) {
+		cpu_set_t allowed; int ncpu = 0, cpus[1024];
+		const char *pin = getenv("ORC_PIN");
+		const int do_pin = !(pin && pin[0] == '0');
+		if (do_pin && sched_getaffinity(0, sizeof allowed, &allowed) == 0)
+			for (int c = 0; c < CPU_SETSIZE && ncpu < 1024; c++) if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
+		g_pool.th = (pthread_t *)realloc(g_pool.th, sizeof(pthread_t) * (size_t)(nthreads - 1));
+		while (g_pool.nworkers < nthreads - 1) {
+			const int tid = g_pool.nworkers + 1;
+			if (pthread_create(&g_pool.th[tid - 1], NULL, pool_worker, (void *)(intptr_t)tid) != 0) break;
+			if (ncpu > 0) {
+				cpu_set_t one; CPU_ZERO(&one); CPU_SET(cpus[tid % ncpu], &one);
+				pthread_setaffinity_np(g_pool.th[tid - 1], sizeof one, &one);
+			}
+			g_pool.nworkers++;
+		}
+		if (nthreads - 1 > g_pool.nworkers) nthreads = g_pool.nworkers + 1;   /* thread limit reached: run narrower */
+	}
+	g_pool.fn = fn; g_pool.arg = arg; g_pool.active = nthreads; g_pool.pending = nthreads - 1;
+	g_pool.gen++;
+	pthread_cond_broadcast(&g_pool.go);
+	pthread_mutex_unlock(&g_pool.mu);
+	fn(arg, 0, nthreads);
+	pthread_mutex_lock(&g_pool.mu);
+	while (g_pool.pending > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+	pthread_mutex_unlock(&g_pool.mu);
+	pthread_mutex_unlock(&g_pool.run_mu);
+}
+
 /* ---- multi-threaded baseline: (candidate, T-slice) work items, merged in slice order ---- */
 typedef struct {
 	const float *dims; const orc_record *recs;
 	uint32_t C; uint64_t T, pitch; const double *w;
 	int nslice; double *psum; uint64_t *pcnt;
-	int tid, nthreads;
+	uint64_t next;                     /* atomic item counter */
 } mt_job;
 
-static void *mt_worker(void *arg)
+static void mt_worker(void *arg, int tid, int nthreads)
 {
+	(void)tid; (void)nthreads;
 	mt_job *j = (mt_job *)arg;
 	const uint64_t nitems = (uint64_t)j->C * (uint64_t)j->nslice;
-	for (uint64_t it = (uint64_t)j->tid; it < nitems; it += (uint64_t)j->nthreads) {
-		const uint32_t c = (uint32_t)(it / (uint64_t)j->nslice);
-		const int s = (int)(it % (uint64_t)j->nslice);
+	for (;;) {
+		/* slice-major claim order: neighbouring claims are the same T-slice of consecutive candidates */
+		const uint64_t k = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+		if (k >= nitems) break;
+		const int s = (int)(k / j->C);
+		const uint32_t c = (uint32_t)(k % j->C);
+		const uint64_t it = (uint64_t)c * (uint64_t)j->nslice + (uint64_t)s;
 		const uint64_t t0 = j->T * (uint64_t)s / (uint64_t)j->nslice;
 		const uint64_t t1 = j->T * (uint64_t)(s + 1) / (uint64_t)j->nslice;
 		if (j->dims)
@@ -253,7 +329,6 @@ static void *mt_worker(void *arg)
 		else
 			score_recs_range(j->recs + (uint64_t)c * j->pitch, t0, t1, j->w, &j->psum[it], &j->pcnt[it]);
 	}
-	return NULL;
 }
 
 static void score_mt(const float *dims, const orc_record *recs, uint32_t C, uint64_t T, uint64_t pitch,
@@ -264,20 +339,15 @@ static void score_mt(const float *dims, const orc_record *recs, uint32_t C, uint
 	const uint64_t nitems = (uint64_t)C * (uint64_t)nslice;
 	double *psum = (double *)calloc(nitems ? nitems : 1, sizeof(double));
 	uint64_t *pcnt = (uint64_t *)calloc(nitems ? nitems : 1, sizeof(uint64_t));
-	pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
-	mt_job *jobs = (mt_job *)malloc(sizeof(mt_job) * (size_t)nthreads);
-	for (int i = 0; i < nthreads; i++) {
-		jobs[i] = (mt_job){dims, recs, C, T, pitch, w, nslice, psum, pcnt, i, nthreads};
-		pthread_create(&th[i], NULL, mt_worker, &jobs[i]);
-	}
-	for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+	mt_job job = {dims, recs, C, T, pitch, w, nslice, psum, pcnt, 0};
+	pool_run(mt_worker, &job, nthreads);
 	for (uint32_t c = 0; c < C; c++) {
 		double s = 0; uint64_t n = 0;
 		for (int k = 0; k < nslice; k++) { s += psum[(uint64_t)c * nslice + k]; n += pcnt[(uint64_t)c * nslice + k]; }
 		counts[c] = n;
 		scores[c] = n > 0 ? s / (double)n : -INFINITY;
 	}
-	free(psum); free(pcnt); free(th); free(jobs);
+	free(psum); free(pcnt);
 }
 
 void orc_score_dims_mt(const float *dims, uint32_t C, uint64_t T, uint64_t pitch_evals,
@@ -312,14 +382,12 @@ static void pat_hit(orc_pattern *p, uint64_t idx)
 	p->count++;
 }
 
-void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
-                      const double w[ORC_NDIM], orc_report *out)
+/* Everything _buildReport / _analyzePatterns / getStats accumulate over the records [0,T): tallies, byMode,
+ * tool totals (APO:509-538, TCS:602-610), the sequential reward / per-dimension sums (APO:550-568) and the six
+ * 'bad'-gated predicates with their first three matches (APO:635-773).  `out` must be zeroed with examples = -1. */
+static void report_accumulate(const orc_record *recs, uint64_t T, uint64_t idx_base, const double w[ORC_NDIM], orc_report *out)
 {
-	memset(out, 0, sizeof(*out));
-	for (int p = 0; p < ORC_NPAT; p++) for (int k = 0; k < 3; k++) out->pat[p].examples[k] = -1;
-	out->total = T;
-
-	/* pass 1, APO:509-538 + TCS:602-610 */
+	out->total += T;
 	for (uint64_t t = 0; t < T; t++) {
 		const orc_record *r = &recs[t];
 		if (r->feedback == 1) out->good++;
@@ -333,16 +401,6 @@ void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
 		out->toolSucc += r->toolSucc;
 		out->toolFail += r->toolFail;
 	}
-	for (int m = 0; m < ORC_NMODE; m++) {                     /* APO:541-544 */
-		const uint64_t tot = out->byMode[m][1] + out->byMode[m][2];
-		out->byModeGoodRate[m] = tot > 0 ? (double)out->byMode[m][1] / (double)tot : 0;
-	}
-	{
-		const uint64_t tot = out->good + out->bad;              /* APO:546-547 */
-		out->goodRate = tot > 0 ? (double)out->good / (double)tot : 0;
-	}
-	out->toolSuccessRate = out->toolCalls > 0 ? (double)out->toolSucc / (double)out->toolCalls : NAN; /* TCS:624 */
-
 	/* APO:550-568: sequential sums over traces with non-null finalReward */
 	for (uint64_t t = 0; t < T; t++) {
 		const orc_record *r = &recs[t];
@@ -358,6 +416,39 @@ void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
 			out->dim[i].count++;
 		}
 	}
+	/* APO:635-773.  Every predicate ANDs userFeedback==='bad', so with no bad trace nothing matches — which is
+	 * exactly the APO:641 early-out (no bad examples -> no patterns at all). */
+	for (uint64_t t = 0; t < T; t++) {
+		const orc_record *r = &recs[t];
+		if (r->feedback != 2) continue;
+		const uint64_t gi = idx_base + t;
+		if (r->flags & ORC_F_ERRORS) pat_hit(&out->pat[0], gi);          /* P1 APO:644 */
+		if (r->flags & ORC_F_FAILSPAN) pat_hit(&out->pat[1], gi);        /* P2 APO:666-670 */
+		if (r->tokens > 10000) pat_hit(&out->pat[2], gi);                /* P3 APO:692-694 */
+		if (r->llmCalls > 2) pat_hit(&out->pat[3], gi);                  /* P4 APO:712-714 */
+		if (r->userMsgs >= 4) pat_hit(&out->pat[4], gi);                 /* P5 APO:732-735 */
+		if ((double)r->toolDurMs > 15000) pat_hit(&out->pat[5], gi);     /* P6 APO:753-755 */
+	}
+}
+
+static void report_init(orc_report *out)
+{
+	memset(out, 0, sizeof(*out));
+	for (int p = 0; p < ORC_NPAT; p++) for (int k = 0; k < 3; k++) out->pat[p].examples[k] = -1;
+}
+
+/* rates, averages, rule flags and severities from the accumulated totals */
+static void report_finish(orc_report *out)
+{
+	for (int m = 0; m < ORC_NMODE; m++) {                     /* APO:541-544 */
+		const uint64_t tot = out->byMode[m][1] + out->byMode[m][2];
+		out->byModeGoodRate[m] = tot > 0 ? (double)out->byMode[m][1] / (double)tot : 0;
+	}
+	{
+		const uint64_t tot = out->good + out->bad;              /* APO:546-547 */
+		out->goodRate = tot > 0 ? (double)out->good / (double)tot : 0;
+	}
+	out->toolSuccessRate = out->toolCalls > 0 ? (double)out->toolSucc / (double)out->toolCalls : NAN; /* TCS:624 */
 	out->avgReward = out->withReward > 0 ? out->rewardSum / (double)out->withReward : NAN;
 	for (int i = 0; i < ORC_NDIM; i++) {
 		orc_dimstat *ds = &out->dim[i];
@@ -367,20 +458,7 @@ void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
 		ds->sugg_flag = (ds->count > 0 && ds->avg < 0 && ds->count >= 3);    /* APO:802 */
 		ds->sugg_priority = ds->avg < -0.5 ? 2 : 1;                          /* APO:819 */
 	}
-
-	/* APO:635-773.  APO:641: no bad examples -> no patterns at all. */
-	if (out->bad == 0) return;
-	for (uint64_t t = 0; t < T; t++) {
-		const orc_record *r = &recs[t];
-		if (r->feedback != 2) continue;                       /* every predicate ANDs userFeedback==='bad' */
-		const uint64_t gi = idx_base + t;
-		if (r->flags & ORC_F_ERRORS) pat_hit(&out->pat[0], gi);          /* P1 APO:644 */
-		if (r->flags & ORC_F_FAILSPAN) pat_hit(&out->pat[1], gi);        /* P2 APO:666-670 */
-		if (r->tokens > 10000) pat_hit(&out->pat[2], gi);                /* P3 APO:692-694 */
-		if (r->llmCalls > 2) pat_hit(&out->pat[3], gi);                  /* P4 APO:712-714 */
-		if (r->userMsgs >= 4) pat_hit(&out->pat[4], gi);                 /* P5 APO:732-735 */
-		if ((double)r->toolDurMs > 15000) pat_hit(&out->pat[5], gi);     /* P6 APO:753-755 */
-	}
+	if (out->bad == 0) return;                                 /* APO:641 */
 	/* thresholds and severities: APO:645,650 / 671,676 / 695,700 / 715,720 / 736,741 / 756,761 */
 	static const uint64_t minc[ORC_NPAT] = {2, 2, 3, 2, 2, 2};
 	for (int p = 0; p < ORC_NPAT; p++) {
@@ -394,6 +472,142 @@ void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
 		default: pp->severity = 1; break;
 		}
 	}
+}
+
+/* single thread, exact reference order: the parity oracle */
+void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
+                      const double w[ORC_NDIM], orc_report *out)
+{
+	report_init(out);
+	report_accumulate(recs, T, idx_base, w, out);
+	report_finish(out);
+}
+
+/* merge partial `b` (a later, disjoint index range) into `a`: integers add, binary64 sums add in slice order,
+ * the first three examples are taken in index order */
+static void report_merge(orc_report *a, const orc_report *b)
+{
+	a->total += b->total; a->good += b->good; a->bad += b->bad; a->none += b->none;
+	for (int m = 0; m < ORC_NMODE; m++) for (int k = 0; k < 3; k++) a->byMode[m][k] += b->byMode[m][k];
+	a->toolCalls += b->toolCalls; a->toolSucc += b->toolSucc; a->toolFail += b->toolFail;
+	a->withReward += b->withReward; a->rewardSum += b->rewardSum;
+	for (int i = 0; i < ORC_NDIM; i++) { a->dim[i].sum += b->dim[i].sum; a->dim[i].count += b->dim[i].count; }
+	for (int p = 0; p < ORC_NPAT; p++) {
+		uint64_t have = a->pat[p].count < 3 ? a->pat[p].count : 3;
+		const uint64_t from = b->pat[p].count < 3 ? b->pat[p].count : 3;
+		for (uint64_t k = 0; k < from && have < 3; k++) a->pat[p].examples[have++] = b->pat[p].examples[k];
+		a->pat[p].count += b->pat[p].count;
+	}
+}
+
+typedef struct {
+	const orc_record *recs;            /* NULL: generate records [t0, t0+T) of the corpus stream on the fly */
+	uint64_t seed, t0; uint32_t agent_permille;
+	uint64_t T, idx_base; const double *w;
+	orc_report *parts;                 /* one per slice */
+	int nslice; uint64_t next;
+} rep_job;
+
+static void rep_worker(void *arg, int tid, int nthreads)
+{
+	(void)tid; (void)nthreads;
+	rep_job *j = (rep_job *)arg;
+	enum { CHUNK = 4096 };
+	orc_record *buf = j->recs ? NULL : (orc_record *)malloc(sizeof(orc_record) * CHUNK);
+	for (;;) {
+		const uint64_t s = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+		if (s >= (uint64_t)j->nslice) break;
+		const uint64_t a = j->T * s / (uint64_t)j->nslice, b = j->T * (s + 1) / (uint64_t)j->nslice;
+		orc_report *part = &j->parts[s];
+		report_init(part);
+		if (j->recs) report_accumulate(j->recs + a, b - a, j->idx_base + a, j->w, part);
+		else
+			for (uint64_t t = a; t < b; t += CHUNK) {
+				const uint64_t n = b - t < CHUNK ? b - t : CHUNK;
+				for (uint64_t k = 0; k < n; k++) orc_gen_record(j->seed, ORC_STREAM_CORPUS, 0, j->t0 + t + k, j->agent_permille, &buf[k]);
+				report_accumulate(buf, n, j->idx_base + t, j->w, part);
+			}
+	}
+	free(buf);
+}
+
+static void report_mt(rep_job *j, orc_report *out, int nthreads)
+{
+	if (nthreads < 1) nthreads = 1;
+	j->nslice = nthreads * 4; j->next = 0;
+	j->parts = (orc_report *)malloc(sizeof(orc_report) * (size_t)j->nslice);
+	pool_run(rep_worker, j, nthreads);
+	report_init(out);
+	for (int s = 0; s < j->nslice; s++) report_merge(out, &j->parts[s]);
+	report_finish(out);
+	free(j->parts);
+}
+
+/* all host threads: per-slice partials merged in slice order (integers and examples identical to the
+ * single-thread report; the binary64 sums differ from the sequential ones in the last bits) */
+void orc_report_build_mt(const orc_record *recs, uint64_t T, uint64_t idx_base,
+                         const double w[ORC_NDIM], orc_report *out, int nthreads)
+{
+	rep_job j = {recs, 0, 0, 0, T, idx_base, w, NULL, 0, 0};
+	report_mt(&j, out, nthreads);
+}
+
+/* the same over records [t0, t0+T) of the generator's corpus stream, generated chunk by chunk (never
+ * materialised): bench.py checks the GPU's corpus report of the full benchmark corpus against it */
+void orc_report_generated(uint64_t seed, uint64_t t0, uint64_t T, uint64_t idx_base, uint32_t agent_permille,
+                          const double w[ORC_NDIM], orc_report *out, int nthreads)
+{
+	rep_job j = {NULL, seed, t0, agent_permille, T, idx_base, w, NULL, 0, 0};
+	report_mt(&j, out, nthreads);
+}
+
+/* ---- exact per-candidate sums over generated Form D evaluations (never materialised) ----
+ * For each listed candidate: sum over t in [t0, t0+T) of llrint(finalReward * 2^52), finalReward computed from the
+ * fp32-rounded dims exactly as orc_score_dims_fx does on a materialised tensor.  Integer partials per (candidate,
+ * slice) item: any thread count gives the same integers. */
+typedef struct {
+	uint64_t seed; const uint32_t *cands; uint32_t ncand; uint64_t t0, T; uint32_t agent_permille; const double *w;
+	__int128 *psum; uint64_t *pcnt; int nslice; uint64_t next;
+} genfx_job;
+
+static void genfx_worker(void *arg, int tid, int nthreads)
+{
+	(void)tid; (void)nthreads;
+	genfx_job *j = (genfx_job *)arg;
+	const uint64_t nitems = (uint64_t)j->ncand * (uint64_t)j->nslice;
+	for (;;) {
+		const uint64_t it = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+		if (it >= nitems) break;
+		const uint32_t ci = (uint32_t)(it / (uint64_t)j->nslice);
+		const uint64_t s = it % (uint64_t)j->nslice;
+		const uint64_t a = j->T * s / (uint64_t)j->nslice, b = j->T * (s + 1) / (uint64_t)j->nslice;
+		__int128 acc = 0; uint64_t n = 0;
+		for (uint64_t t = a; t < b; t++) {
+			float row[ORC_NDIM]; double fr;
+			orc_gen_dims_row(j->seed, j->cands[ci], j->t0 + t, j->agent_permille, row);
+			if (orc_final_reward_f32(row, j->w, &fr)) { acc += (__int128)llrint(fr * 4503599627370496.0); n++; }
+		}
+		j->psum[it] = acc; j->pcnt[it] = n;
+	}
+}
+
+void orc_score_generated_fx(uint64_t seed, const uint32_t *cands, uint32_t ncand, uint64_t t0, uint64_t T,
+                            uint32_t agent_permille, const double w[ORC_NDIM], uint64_t *lo, int64_t *hi,
+                            uint64_t *counts, int nthreads)
+{
+	if (nthreads < 1) nthreads = 1;
+	genfx_job j = {seed, cands, ncand, t0, T, agent_permille, w, NULL, NULL, 0, 0};
+	j.nslice = (int)((uint64_t)nthreads * 4 / (ncand ? ncand : 1)) + 1;
+	const uint64_t nitems = (uint64_t)ncand * (uint64_t)j.nslice;
+	j.psum = (__int128 *)calloc(nitems ? nitems : 1, sizeof(__int128));
+	j.pcnt = (uint64_t *)calloc(nitems ? nitems : 1, sizeof(uint64_t));
+	pool_run(genfx_worker, &j, nthreads);
+	for (uint32_t c = 0; c < ncand; c++) {
+		__int128 acc = 0; uint64_t n = 0;
+		for (int s = 0; s < j.nslice; s++) { acc += j.psum[(uint64_t)c * j.nslice + s]; n += j.pcnt[(uint64_t)c * j.nslice + s]; }
+		lo[c] = (uint64_t)acc; hi[c] = (int64_t)(acc >> 64); counts[c] = n;
+	}
+	free(j.psum); free(j.pcnt);
 }
 
 /* ---------------------------------------------------------------- Form R16 -> Form R */
@@ -509,15 +723,17 @@ void orc_gen_dims_row(uint64_t seed, uint32_t c, uint64_t t, uint32_t agent_perm
 
 typedef struct {
 	uint64_t seed; uint32_t stream, c0, C; uint64_t t0, T, pitch; uint32_t ap;
-	float *dims; orc_record *recs; int tid, nthreads;
+	float *dims; orc_record *recs;
 } gen_job;
 
-static void *gen_worker(void *arg)
+/* thread k fills the k-th T-slice of every candidate: with pinned workers the pages it first touches are the
+ * ones the same thread reads back in score_mt's slice k */
+static void gen_worker(void *arg, int tid, int nthreads)
 {
 	gen_job *j = (gen_job *)arg;
 	for (uint32_t c = 0; c < j->C; c++) {
-		const uint64_t a = j->T * (uint64_t)j->tid / (uint64_t)j->nthreads;
-		const uint64_t b = j->T * (uint64_t)(j->tid + 1) / (uint64_t)j->nthreads;
+		const uint64_t a = j->T * (uint64_t)tid / (uint64_t)nthreads;
+		const uint64_t b = j->T * (uint64_t)(tid + 1) / (uint64_t)nthreads;
 		for (uint64_t t = a; t < b; t++) {
 			if (j->dims)
 				orc_gen_dims_row(j->seed, j->c0 + c, j->t0 + t, j->ap, j->dims + ((uint64_t)c * j->pitch + t) * ORC_NDIM);
@@ -525,32 +741,24 @@ static void *gen_worker(void *arg)
 				orc_gen_record(j->seed, j->stream, j->c0 + c, j->t0 + t, j->ap, j->recs + (uint64_t)c * j->pitch + t);
 		}
 	}
-	return NULL;
 }
 
 static void gen_mt(gen_job proto, int nthreads)
 {
 	if (nthreads < 1) nthreads = 1;
-	pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
-	gen_job *jobs = (gen_job *)malloc(sizeof(gen_job) * (size_t)nthreads);
-	for (int i = 0; i < nthreads; i++) {
-		jobs[i] = proto; jobs[i].tid = i; jobs[i].nthreads = nthreads;
-		pthread_create(&th[i], NULL, gen_worker, &jobs[i]);
-	}
-	for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
-	free(th); free(jobs);
+	pool_run(gen_worker, &proto, nthreads);
 }
 
 void orc_gen_dims(uint64_t seed, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T, uint64_t pitch_evals,
                   uint32_t agent_permille, float *out, int nthreads)
 {
-	gen_job p = {seed, ORC_STREAM_ROLLOUT, c0, C, t0, T, pitch_evals, agent_permille, out, NULL, 0, 1};
+	gen_job p = {seed, ORC_STREAM_ROLLOUT, c0, C, t0, T, pitch_evals, agent_permille, out, NULL};
 	gen_mt(p, nthreads);
 }
 
 void orc_gen_records(uint64_t seed, uint32_t stream, uint32_t c0, uint32_t C, uint64_t t0, uint64_t T,
                      uint64_t pitch, uint32_t agent_permille, orc_record *out, int nthreads)
 {
-	gen_job p = {seed, stream, c0, C, t0, T, pitch, agent_permille, NULL, out, 0, 1};
+	gen_job p = {seed, stream, c0, C, t0, T, pitch, agent_permille, NULL, out};
 	gen_mt(p, nthreads);
 }

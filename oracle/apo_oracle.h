@@ -129,6 +129,19 @@ typedef struct {
  * indices (global index of records[0]). */
 void orc_report_build(const orc_record *recs, uint64_t T, uint64_t idx_base,
                       const double w[ORC_NDIM], orc_report *out);
+/* The same on all host threads (persistent pool): integers and first-3 examples identical to
+ * orc_report_build, binary64 sums merged per slice (last bits differ from the sequential sums).
+ * orc_report_generated walks records [t0, t0+T) of the generator's corpus stream without
+ * materialising them. */
+void orc_report_build_mt(const orc_record *recs, uint64_t T, uint64_t idx_base,
+                         const double w[ORC_NDIM], orc_report *out, int nthreads);
+void orc_report_generated(uint64_t seed, uint64_t t0, uint64_t T, uint64_t idx_base, uint32_t agent_permille,
+                          const double w[ORC_NDIM], orc_report *out, int nthreads);
+/* Exact integer sums (as orc_score_dims_fx) for the listed candidates over generated Form D
+ * evaluations t0 .. t0+T-1, never materialised; any thread count gives the same integers. */
+void orc_score_generated_fx(uint64_t seed, const uint32_t *cands, uint32_t ncand, uint64_t t0, uint64_t T,
+                            uint32_t agent_permille, const double w[ORC_NDIM], uint64_t *lo, int64_t *hi,
+                            uint64_t *counts, int nthreads);
 
 /* Form R16 (include/apo_b200.h apo_record16): independent restatement of the 16-byte unpacking. */
 typedef struct {

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <new>
 #include <algorithm>
 #include <string>
@@ -38,6 +39,7 @@ struct NcclApi {
 	int (*GetUniqueId)(NcclId *) = nullptr;
 	int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
 	int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+	int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
 	int (*CommDestroy)(void *) = nullptr;
 	const char *(*GetErrorString)(int) = nullptr;
 };
@@ -53,6 +55,7 @@ bool nccl_load(std::string &err) {
 	g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.h, "ncclGetUniqueId");
 	g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.h, "ncclCommInitRank");
 	g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.h, "ncclAllReduce");
+	g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.h, "ncclAllGather");
 	g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.h, "ncclCommDestroy");
 	g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.h, "ncclGetErrorString");
 	if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
@@ -60,7 +63,7 @@ bool nccl_load(std::string &err) {
 	}
 	return true;
 }
-constexpr int kNcclInt64 = 4, kNcclSum = 0;
+constexpr int kNcclInt64 = 4, kNcclInt8 = 0, kNcclSum = 0, kNcclMin = 3;
 constexpr uint32_t kMaxK = 16384;      // the K winners are ordered by counting (O(K^2)); beam widths are tiny (APO:288: 4)
 
 template <class T>
@@ -97,8 +100,10 @@ struct apo_engine {
 	uint32_t qbook_host[8 * 256]; bool compact = false;
 	DevBuf<uint8_t> roll; uint32_t roll_C = 0, roll_row = 32; uint64_t roll_T = 0, roll_pitch = 0;   // Form R (32 B) or R16 (16 B) rows
 
-	DevBuf<long long> acc, acc_joined; uint32_t last_C = 0;   // acc_joined: allreduce output (> 1 rank); acc keeps this rank's partials
-	DevBuf<unsigned long long> misc;     // [0,18) example scratch, [18] ticket
+	// acc: [acc_words(C, nranks)] partial vector | [18] example scratch (inverted indices) | [1] ticket — one allocation, so one
+	// memset arms a scoring call.  acc_joined: the joined vector (> 1 rank); acc keeps this rank's partials.
+	DevBuf<long long> acc, acc_joined; uint32_t last_C = 0;
+	DevBuf<unsigned long long> misc;     // NCCL warm-up / status scratch
 	DevBuf<uint8_t> result;              // scores | counts | topk | report
 	DevBuf<unsigned long long> keys, sel_key; DevBuf<int32_t> sel_idx;
 	uint8_t *h_result = nullptr; uint64_t h_result_cap = 0;
@@ -107,6 +112,15 @@ struct apo_engine {
 	DevBuf<apo_record> batch_in; DevBuf<double> batch_out; DevBuf<uint32_t> batch_mask;
 
 	void *comm = nullptr; int nranks = 1, rank = 0;
+	// peer-memory join (csrc/apo_corpus.cuh peer_join): this rank's block and the peer-mapped views of the others
+	uint8_t *peer_block = nullptr; uint64_t peer_slot_words = 0; bool peer_ok = false;
+	void *peer_base[apo::PEER_MAX] = {nullptr}; bool peer_ipc[apo::PEER_MAX] = {false};
+	unsigned long long join_epoch = 0;
+	bool env_no_fuse = false, env_force_fuse = false, env_no_staging = false, env_nccl_join = false;   // apo_set_tuning
+	double stream_bytes_per_ms = 7.4e9, stream_q_bytes_per_ms = 5.0e9, scan_ms_per_record = 3.35e-7;   // fuse heuristic, derived from the device at apo_create
+	size_t mem_pitch_max = 0;
+	uint8_t *zc_host = nullptr; uint64_t zc_cap = 0;   // zero-copy block of the single-trace path
+	bool timing_on = true;
 	cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	std::vector<cudaEvent_t> k1_ev;      // start/stop pairs of the K1 launches of the current scoring call
 	size_t k1_used = 0;
@@ -302,7 +316,8 @@ bool is_pageable(const void *p) {
 // rows x width bytes, strided -> strided, split over a few host threads (a single memcpy stream does not fill PCIe 5)
 void parallel_rows_copy(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t width, uint32_t rows) {
 	unsigned nt = std::thread::hardware_concurrency();
-	if (const char *v = getenv("APO_HOST_THREADS")) { const int x = atoi(v); if (x > 0) nt = (unsigned)x; }
+	static const int env_threads = [] { const char *v = getenv("APO_HOST_THREADS"); return v ? atoi(v) : 0; }();   // read once per process
+	if (env_threads > 0) nt = (unsigned)env_threads;
 	else nt = nt ? (nt > 16 ? 16 : nt) : 4;        // default: at most 16 (measured: 4 / 8 / 16 / 32 threads -> 15 / 22-29 / 30 / 25 GB/s); APO_HOST_THREADS overrides
 	if (nt > 64) nt = 64;
 	const size_t total = width * rows;
@@ -332,14 +347,27 @@ int ensure_stage(apo_engine *e, uint64_t bytes) {
 	return APO_OK;
 }
 
+// cudaMemcpy2DAsync rejects pitches above cudaDeviceProp::memPitch (2 GiB - 1 on B200): rows of a host tensor whose
+// record axis is longer than that (T * row bytes > 2 GiB, the "larger than device memory" case of the streaming calls)
+// are copied one by one instead.
+int copy_rows_h2d(apo_engine *e, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, uint32_t rows, cudaStream_t st) {
+	if (rows == 0 || width == 0) return APO_OK;
+	if (rows == 1) { CK(cudaMemcpyAsync(dst, src, width, cudaMemcpyHostToDevice, st)); return APO_OK; }
+	if (e->mem_pitch_max == 0 || (dpitch <= e->mem_pitch_max && spitch <= e->mem_pitch_max)) {
+		CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, st));
+		return APO_OK;
+	}
+	for (uint32_t r = 0; r < rows; r++)
+		CK(cudaMemcpyAsync((uint8_t *)dst + (size_t)r * dpitch, (const uint8_t *)src + (size_t)r * spitch, width, cudaMemcpyHostToDevice, st));
+	return APO_OK;
+}
+
 // rows x width bytes host -> device on `st` (asynchronous for page-locked sources; a pageable source is fully consumed
 // when this returns).  Large pageable sources go through the staging buffers in column slices of all rows.
 int h2d_rows(apo_engine *e, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, uint32_t rows, cudaStream_t st) {
 	const uint64_t total = (uint64_t)width * rows;
-	if (total < (64ull << 20) || !is_pageable(src) || getenv("APO_NO_STAGING") != nullptr) {
-		CK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, st));
-		return APO_OK;
-	}
+	if (total < (64ull << 20) || !is_pageable(src) || e->env_no_staging)
+		return copy_rows_h2d(e, dst, dpitch, src, spitch, width, rows, st);
 	const uint64_t cap = 256ull << 20;
 	int rc = ensure_stage(e, cap);
 	if (rc) return rc;
@@ -351,31 +379,36 @@ int h2d_rows(apo_engine *e, void *dst, size_t dpitch, const void *src, size_t sp
 		const size_t w = width - w0 < W ? width - w0 : W;
 		if (k >= 2) CK(cudaEventSynchronize(e->stage_done[b]));
 		parallel_rows_copy(e->h_stage[b], W, (const uint8_t *)src + w0, spitch, w, rows);
-		CK(cudaMemcpy2DAsync((uint8_t *)dst + w0, dpitch, e->h_stage[b], W, w, rows, cudaMemcpyHostToDevice, st));
+		{ const int rc2 = copy_rows_h2d(e, (uint8_t *)dst + w0, dpitch, e->h_stage[b], W, w, rows, st); if (rc2) return rc2; }
 		CK(cudaEventRecord(e->stage_done[b], st));
 	}
 	return APO_OK;
 }
 
-struct ResultLayout { uint64_t off_scores, off_counts, off_topk, off_report, bytes; };
+struct ResultLayout { uint64_t off_scores, off_counts, off_topk, off_report, off_meta, bytes; };
 ResultLayout result_layout(uint32_t C, uint32_t K) {
 	ResultLayout L;
 	L.off_scores = 0;
 	L.off_counts = L.off_scores + 8ull * C;
 	L.off_topk = L.off_counts + 8ull * C;
 	L.off_report = round_up(L.off_topk + 4ull * K, 16);
-	L.bytes = L.off_report + sizeof(apo_corpus_report);
+	L.off_meta = round_up(L.off_report + sizeof(apo_corpus_report), 16);
+	L.bytes = L.off_meta + sizeof(apo::ResultMeta);
 	return L;
 }
+static_assert(sizeof(apo::ResultMeta) == 16, "result block stays a multiple of 16 bytes");
+constexpr uint64_t kHostOutMax = 64ull << 10;      // result blocks up to this size are written to the caller's page-locked buffer by the kernel itself
+constexpr uint64_t kTimingMinBytes = 64ull << 20;  // per-stage CUDA events are recorded for calls streaming at least this much (or on request)
+constexpr uint64_t ARM_WORDS = 19;                  // 18 example slots + ticket, right behind the partial vector
 
 int ensure_scratch(apo_engine *e, uint32_t C, uint32_t K) {
-	CK(e->acc.reserve(acc_words(C, e->nranks)));
-	CK(e->misc.reserve(32));
+	CK(e->acc.reserve(acc_words(C, e->nranks) + ARM_WORDS));
 	const ResultLayout L = result_layout(C, K);
 	CK(e->result.reserve(L.bytes));
 	CK(e->keys.reserve(C ? C : 1));
 	CK(e->sel_key.reserve(K ? K : 1));
 	CK(e->sel_idx.reserve(K ? K : 1));
+	if (e->nranks > 1) CK(e->acc_joined.reserve(acc_words(C, e->nranks)));
 	if (e->h_result_cap < L.bytes) {
 		if (e->h_result) cudaFreeHost(e->h_result);
 		e->h_result = nullptr; e->h_result_cap = 0;
@@ -385,24 +418,58 @@ int ensure_scratch(apo_engine *e, uint32_t C, uint32_t K) {
 	return APO_OK;
 }
 
+// the peer-memory join is used when the block exists on every rank and the partial vector fits its slots
+bool peer_join_active(const apo_engine *e, uint32_t C) {
+	return e->nranks > 1 && e->peer_ok && !e->env_nccl_join && acc_words(C, e->nranks) <= e->peer_slot_words;
+}
+
+// layout of one rank's peer block: [PEER_MAX] arrival flags | [PEER_MAX] done-reading flags (128 B) | slot 0 | slot 1
+constexpr uint64_t kPeerHeader = 2 * apo::PEER_MAX * 8;
+inline unsigned long long *peer_flags(void *base) { return (unsigned long long *)base; }
+inline long long *peer_slot(void *base, uint64_t slot_words, int parity) { return (long long *)((uint8_t *)base + kPeerHeader) + (uint64_t)parity * slot_words; }
+
 apo::FinalizeParams make_fin(apo_engine *e, uint32_t C, uint32_t K, int with_corpus) {
 	const ResultLayout L = result_layout(C, K);
-	apo::FinalizeParams F;
+	apo::FinalizeParams F{};
 	F.acc = e->acc.p; F.C = C; F.K = K; F.nranks = e->nranks; F.with_corpus = with_corpus;
 	F.scores = (double *)(e->result.p + L.off_scores);
 	F.counts = (uint64_t *)(e->result.p + L.off_counts);
 	F.keys = e->keys.p; F.sel_key = e->sel_key.p; F.sel_idx = e->sel_idx.p;
 	F.topk = (int32_t *)(e->result.p + L.off_topk);
 	F.report = (apo_corpus_report *)(e->result.p + L.off_report);
+	F.result_base = e->result.p; F.result_bytes = (uint32_t)L.bytes; F.meta_off = (uint32_t)L.off_meta;
+	F.host_out = L.bytes <= kHostOutMax ? e->h_result : nullptr;
+	F.join.nranks = 1;
+	if (peer_join_active(e, C)) {
+		apo::JoinParams &J = F.join;
+		J.nranks = e->nranks; J.rank = e->rank; J.words = (uint32_t)acc_words(C, e->nranks); J.epoch = e->join_epoch;
+		for (int r = 0; r < e->nranks; r++) {
+			J.slot[r] = peer_slot(e->peer_base[r], e->peer_slot_words, (int)(e->join_epoch & 1ull));
+			J.flag[r] = peer_flags(e->peer_base[r]);
+		}
+		J.joined = e->acc_joined.p;
+	}
 	return F;
 }
 
-// zero the accumulators, arm the example scratch and the ticket
-int begin_score(apo_engine *e, uint32_t C) {
-	CK(cudaMemsetAsync(e->acc.p, 0, acc_words(C, e->nranks) * 8, e->stream));
+// zero the candidate accumulators of a scoring session
+int begin_score(apo_engine *e, uint32_t C, bool whole = false) {
+	// whole: also the corpus block, the example scratch and the ticket (one-shot calls: a single memset arms everything)
+	const uint64_t words = whole ? acc_words(C, e->nranks) + ARM_WORDS : (uint64_t)ACC_PER_CAND * C;
+	CK(cudaMemsetAsync(e->acc.p, 0, words * 8, e->stream));
 	e->last_C = C; e->score_C = C; e->scoring = true; e->k1_used = 0;
 	e->timing = apo_timing{};
-	CK(cudaEventRecord(e->ev[0], e->stream));
+	if (e->timing_on) CK(cudaEventRecord(e->ev[0], e->stream));
+	return APO_OK;
+}
+
+int record_k1_event(apo_engine *e, int which) {
+	if (!e->timing_on) return APO_OK;
+	if (which == 0 && e->k1_used + 2 > e->k1_ev.size()) {
+		for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
+	}
+	CK(cudaEventRecord(e->k1_ev[e->k1_used + which], e->stream));
+	if (which == 1) e->k1_used += 2;
 	return APO_OK;
 }
 
@@ -411,6 +478,7 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
                        const apo::K2Params *fused = nullptr) {
 	const bool raw = o->source == APO_SRC_ROLLOUTS;
 	const uint32_t C = raw ? e->roll_C : e->dims_C;
+	int rc;
 	if (!raw && e->compact) {
 		if (!count) return APO_OK;
 		if (first % 8) return fail(e, APO_E_ARG, "window start must be a multiple of 8 for the compact layout");
@@ -425,13 +493,9 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 		int qvariant = (int)o->variant;
 		if ((qvariant == 0 || qvariant >= 5) && !e->q_pair_ok) qvariant = 4;   // prefix table would not fit: product tables only
 		if (fused) { Q.corpus_on = 1; Q.corpus = *fused; }
-		if (e->k1_used + 2 > e->k1_ev.size()) {
-			for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
-		}
-		CK(cudaEventRecord(e->k1_ev[e->k1_used], e->stream));
+		if ((rc = record_k1_event(e, 0))) return rc;
 		CK(apo::run_reward9q(Q, qvariant, (o->flags & APO_SCORE_RECIP) != 0, e->sm_count, e->stream));
-		CK(cudaEventRecord(e->k1_ev[e->k1_used + 1], e->stream));
-		e->k1_used += 2;
+		if ((rc = record_k1_event(e, 1))) return rc;
 		e->timing.launches++;
 		return APO_OK;
 	}
@@ -445,13 +509,9 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 	P.W = e->W;
 	if (fused) { P.corpus_on = 1; P.corpus = *fused; }
 	if (!count) return APO_OK;
-	if (e->k1_used + 2 > e->k1_ev.size()) {
-		for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
-	}
-	CK(cudaEventRecord(e->k1_ev[e->k1_used], e->stream));
+	if ((rc = record_k1_event(e, 0))) return rc;
 	CK(apo::run_reward9(P, row, (int)o->variant, (o->flags & APO_SCORE_RECIP) != 0, e->sm_count, e->stream));
-	CK(cudaEventRecord(e->k1_ev[e->k1_used + 1], e->stream));
-	e->k1_used += 2;
+	if ((rc = record_k1_event(e, 1))) return rc;
 	e->timing.launches++;
 	return APO_OK;
 }
@@ -459,55 +519,61 @@ int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_off
 // K2 (+fused finalize) / allreduce / K3, then bring the result block home
 bool wants_corpus(const apo_engine *e, const apo_score_opts *o) { return (o->flags & APO_SCORE_CORPUS) && e->corpus_T > 0; }
 
-// the corpus block and the example scratch belong to one corpus pass only, so that a scoring session can be
-// finished repeatedly while evaluations keep being accumulated (incremental scoring)
+// the corpus block, the example scratch and the ticket belong to one corpus pass only, so that a scoring session can be
+// finished repeatedly while evaluations keep being accumulated (incremental scoring); they sit behind the candidate
+// accumulators in one allocation: one memset
 int arm_corpus(apo_engine *e, uint32_t C) {
-	CK(cudaMemsetAsync(e->acc.p + (uint64_t)ACC_PER_CAND * C, 0, (CORP_FIXED + 18ull * e->nranks) * 8, e->stream));
-	CK(cudaMemsetAsync(e->misc.p, 0xFF, 18 * 8, e->stream));
-	CK(cudaMemsetAsync(e->misc.p + 18, 0, 8, e->stream));
+	CK(cudaMemsetAsync(e->acc.p + (uint64_t)ACC_PER_CAND * C, 0, (CORP_FIXED + 18ull * e->nranks + ARM_WORDS) * 8, e->stream));
 	return APO_OK;
 }
 
 apo::K2Params make_k2(apo_engine *e, uint32_t C, const apo::FinalizeParams &F) {
 	apo::K2Params P{};
+	unsigned long long *arm = (unsigned long long *)(e->acc.p + acc_words(C, e->nranks));
 	P.recs = e->corpus.p; P.T = e->corpus_T; P.idx_base = e->corpus_base; P.C = C; P.rank = e->rank;
-	P.acc = e->acc.p; P.ex_scratch = e->misc.p; P.ticket = (unsigned int *)(e->misc.p + 18);
-	P.lut = e->d_lut.p; P.W = e->W; P.fuse_finalize = e->nranks == 1 ? 1 : 0; P.fin = F;
+	P.acc = e->acc.p; P.ex_scratch = arm; P.ticket = (unsigned int *)(arm + 18);
+	P.lut = e->d_lut.p; P.W = e->W; P.fuse_finalize = (e->nranks == 1 || F.join.nranks > 1) ? 1 : 0; P.fin = F;
 	return P;
 }
 
-// fused_corpus: the scoring kernel already ran the corpus scan (and, at one rank, the finalisation)
+// fused_corpus: the scoring kernel already ran the corpus scan and the finalisation
 int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *scores, uint64_t *counts, int32_t *topk,
                  apo_corpus_report *report, bool fused_corpus = false) {
 	const uint32_t K = o->K;
 	const bool with_corpus = wants_corpus(e, o);
+	const bool tm = e->timing_on;
 	apo::FinalizeParams F = make_fin(e, C, K, with_corpus ? 1 : 0);
+	const bool peer = F.join.nranks > 1;
 	if (!fused_corpus) { int rc = arm_corpus(e, C); if (rc) return rc; }
-	CK(cudaEventRecord(e->ev[1], e->stream));
-	bool finalized = fused_corpus && e->nranks == 1;
+	if (tm) CK(cudaEventRecord(e->ev[1], e->stream));
+	bool finalized = fused_corpus && (e->nranks == 1 || peer);
 	if (with_corpus && !fused_corpus) {
 		const apo::K2Params P = make_k2(e, C, F);
 		CK(apo::run_detect6(P, e->sm_count, e->stream));
 		e->timing.launches++;
 		finalized = P.fuse_finalize != 0;
 	}
-	CK(cudaEventRecord(e->ev[2], e->stream));
-	if (e->nranks > 1) {
-		CK(e->acc_joined.reserve(acc_words(C, e->nranks)));
+	if (tm) CK(cudaEventRecord(e->ev[2], e->stream));
+	if (e->nranks > 1 && !peer) {
 		const int rc = g_nccl.AllReduce(e->acc.p, e->acc_joined.p, (size_t)acc_words(C, e->nranks), kNcclInt64, kNcclSum, e->comm, e->stream);
 		if (rc != 0) return fail(e, APO_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
 		e->timing.launches++;
 		F.acc = e->acc_joined.p;
 	}
-	CK(cudaEventRecord(e->ev[3], e->stream));
+	if (tm) CK(cudaEventRecord(e->ev[3], e->stream));
 	if (!finalized) {
 		CK(apo::run_finalize(F, e->stream));
 		e->timing.launches++;
 	}
-	CK(cudaEventRecord(e->ev[4], e->stream));
+	if (tm) CK(cudaEventRecord(e->ev[4], e->stream));
 	const ResultLayout L = result_layout(C, K);
-	CK(cudaMemcpyAsync(e->h_result, e->result.p, L.bytes, cudaMemcpyDeviceToHost, e->stream));
+	if (!F.host_out) CK(cudaMemcpyAsync(e->h_result, e->result.p, L.bytes, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
+	apo::ResultMeta meta;
+	memcpy(&meta, e->h_result + L.off_meta, sizeof meta);
+	if (meta.status != 0)
+		return fail(e, APO_E_NCCL, "peer-memory join timed out after %.0f ms: a rank did not reach the join of call %llu", meta.join_wait_us * 1e-3,
+		            (unsigned long long)e->join_epoch);
 	if (scores) memcpy(scores, e->h_result + L.off_scores, 8ull * C);
 	if (counts) memcpy(counts, e->h_result + L.off_counts, 8ull * C);
 	if (topk && K) memcpy(topk, e->h_result + L.off_topk, 4ull * (K < C ? K : C));
@@ -515,14 +581,23 @@ int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *sco
 		if (with_corpus) memcpy(report, e->h_result + L.off_report, sizeof(apo_corpus_report));
 		else memset(report, 0, sizeof(apo_corpus_report));
 	}
-	float ms = 0;
-	e->timing.reward_ms = 0;
-	for (size_t i = 0; i + 1 < e->k1_used; i += 2) { cudaEventElapsedTime(&ms, e->k1_ev[i], e->k1_ev[i + 1]); e->timing.reward_ms += ms; }
-	cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->timing.corpus_ms = ms;
-	cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->timing.allreduce_ms = ms;
-	cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->timing.finalize_ms = ms;
-	cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]); e->timing.total_ms = ms;
+	e->timing.join_wait_ms = meta.join_wait_us * 1e-3f;
+	e->timing.join_reduce_ms = meta.join_reduce_us * 1e-3f;
+	if (tm) {
+		float ms = 0;
+		e->timing.reward_ms = 0;
+		for (size_t i = 0; i + 1 < e->k1_used; i += 2) { cudaEventElapsedTime(&ms, e->k1_ev[i], e->k1_ev[i + 1]); e->timing.reward_ms += ms; }
+		cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->timing.corpus_ms = ms;
+		cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->timing.allreduce_ms = ms;
+		cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->timing.finalize_ms = ms;
+		cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]); e->timing.total_ms = ms;
+	}
 	return APO_OK;
+}
+
+// per-stage CUDA events cost ~1 us each on the host: record them for calls that stream enough for it not to matter, or on request
+void choose_timing(apo_engine *e, const apo_score_opts *o, uint64_t bytes) {
+	e->timing_on = (o->flags & APO_SCORE_TIMING) != 0 || bytes >= kTimingMinBytes;
 }
 
 int check_opts(apo_engine *e, const apo_score_opts *o, uint32_t C, uint64_t T, uint64_t *first, uint64_t *count) {
@@ -536,6 +611,97 @@ int check_opts(apo_engine *e, const apo_score_opts *o, uint32_t C, uint64_t T, u
 	return APO_OK;
 }
 
+}  // namespace
+
+namespace {
+struct PeerInfo {                        // exchanged with ncclAllGather at apo_comm_init, 128 bytes per rank
+	cudaIpcMemHandle_t handle;           // 64 B
+	uint64_t pid, ptr, host_hash;
+	int32_t device, ok;
+	uint8_t pad[128 - 64 - 24 - 8];
+};
+static_assert(sizeof(PeerInfo) == 128, "PeerInfo is exchanged as 128 raw bytes");
+
+void peer_teardown(apo_engine *e) {
+	if (e->peer_ok && e->peer_block && e->join_epoch > 0) {
+		// peers read this block with NVLink loads inside their own launches: wait (bounded) until every peer has signalled
+		// that it finished reading the last joined call before the memory goes away
+		unsigned long long done[apo::PEER_MAX];
+		for (int spin = 0; spin < 2000; spin++) {
+			if (cudaMemcpy(done, e->peer_block + apo::PEER_MAX * 8, sizeof done, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); break; }
+			bool all = true;
+			for (int r = 0; r < e->nranks; r++) if (r != e->rank && done[r] < e->join_epoch) all = false;
+			if (all) break;
+			usleep(1000);
+		}
+	}
+	for (int r = 0; r < apo::PEER_MAX; r++) {
+		if (e->peer_base[r] && e->peer_ipc[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
+		e->peer_base[r] = nullptr; e->peer_ipc[r] = false;
+	}
+	if (e->peer_block) cudaFree(e->peer_block);
+	e->peer_block = nullptr; e->peer_ok = false; e->peer_slot_words = 0;
+}
+
+// Allocate this rank's block, exchange handles, map the peers.  Any failure leaves peer_ok false on EVERY rank (the
+// outcome is agreed with one ncclAllReduce(min)) and the join falls back to ncclAllReduce + k_finalize.
+int peer_setup(apo_engine *e) {
+	peer_teardown(e);
+	if (e->nranks > apo::PEER_MAX || !g_nccl.AllGather) return APO_OK;
+	const uint64_t slot_words = acc_words(16384, e->nranks);          // candidates up to the top-K limit fit a slot (~0.5 MB)
+	const uint64_t bytes = kPeerHeader + 2 * slot_words * 8;
+	PeerInfo mine{};
+	mine.ok = 1;
+	if (cudaMalloc((void **)&e->peer_block, bytes) != cudaSuccess) { cudaGetLastError(); e->peer_block = nullptr; mine.ok = 0; }
+	if (mine.ok && cudaMemsetAsync(e->peer_block, 0, bytes, e->stream) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+	if (mine.ok && cudaIpcGetMemHandle(&mine.handle, e->peer_block) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+	mine.pid = (uint64_t)getpid(); mine.ptr = (uint64_t)(uintptr_t)e->peer_block; mine.device = e->device;
+	{
+		char host[256] = {0};
+		gethostname(host, sizeof host - 1);
+		uint64_t h = 1469598103934665603ull;
+		for (const char *c = host; *c; c++) h = (h ^ (uint8_t)*c) * 1099511628211ull;
+		mine.host_hash = h;
+	}
+	DevBuf<uint8_t> xch;
+	CK(xch.reserve(128ull * (e->nranks + 1)));
+	std::vector<PeerInfo> all(e->nranks);
+	CK(cudaMemcpyAsync(xch.p, &mine, 128, cudaMemcpyHostToDevice, e->stream));
+	int rc = g_nccl.AllGather(xch.p, xch.p + 128, 128, kNcclInt8, e->comm, e->stream);
+	if (rc != 0) { xch.release(); return fail(e, APO_E_NCCL, "ncclAllGather (peer handles): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); }
+	CK(cudaMemcpyAsync(all.data(), xch.p + 128, 128ull * e->nranks, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	long long ok = mine.ok;
+	for (int r = 0; r < e->nranks && ok; r++) {
+		const PeerInfo &pi = all[r];
+		if (!pi.ok || pi.host_hash != mine.host_hash) { ok = 0; break; }           // peer memory needs one NVLink domain: same box
+		if (r == e->rank) { e->peer_base[r] = e->peer_block; continue; }
+		if (pi.pid == mine.pid) {
+			// another handle of this process (one Electron main process driving several GPUs): plain peer access
+			int can = 0;
+			if (cudaDeviceCanAccessPeer(&can, e->device, pi.device) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+			const cudaError_t pe = cudaDeviceEnablePeerAccess(pi.device, 0);
+			if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = 0; break; }
+			cudaGetLastError();
+			e->peer_base[r] = (void *)(uintptr_t)pi.ptr;
+		} else {
+			void *p = nullptr;
+			if (cudaIpcOpenMemHandle(&p, pi.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+			e->peer_base[r] = p; e->peer_ipc[r] = true;
+		}
+	}
+	// agree on the outcome (also the barrier that orders every rank's zero-fill before the first join)
+	long long *flag = (long long *)xch.p;
+	CK(cudaMemcpyAsync(flag, &ok, 8, cudaMemcpyHostToDevice, e->stream));
+	rc = g_nccl.AllReduce(flag, flag, 1, kNcclInt64, kNcclMin, e->comm, e->stream);
+	if (rc != 0) { xch.release(); return fail(e, APO_E_NCCL, "ncclAllReduce (peer agreement): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); }
+	CK(cudaMemcpyAsync(&ok, flag, 8, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	xch.release();
+	if (!ok) { peer_teardown(e); return APO_OK; }
+	e->peer_ok = true; e->peer_slot_words = slot_words; e->join_epoch = 0;
+	return APO_OK;
+}
 }  // namespace
 
 // =============================================================================== lifecycle
@@ -558,6 +724,29 @@ extern "C" int apo_create(int device, apo_engine **out) {
 	if ((c = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", c);
 	if (prop.major != 10) { fail(nullptr, APO_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); apo_destroy(e); return APO_E_CUDA; }
 	e->sm_count = prop.multiProcessorCount;
+	e->mem_pitch_max = prop.memPitch;
+	{
+		// fuse heuristic (apo_score): the corpus scan rides on one warp per SM and must hide behind the evaluation stream.
+		// Stream rate = 0.9 x the pin bandwidth of this device (measured on B200: 7.4 of 8.19 TB/s for Form D / R; the compact
+		// layout is SM-bound at 0.61 x); scan rate = kScanRecordsPerSmCycle records per SM clock on that one warp
+		// (measured: 10 M records in 3.35 ms on 148 SMs at 1.965 GHz).
+		int mem_khz = 0, bus_bits = 0, sm_khz = 0;
+		cudaDeviceGetAttribute(&mem_khz, cudaDevAttrMemoryClockRate, device);
+		cudaDeviceGetAttribute(&bus_bits, cudaDevAttrGlobalMemoryBusWidth, device);
+		cudaDeviceGetAttribute(&sm_khz, cudaDevAttrClockRate, device);
+		constexpr double kStreamFracOfPin = 0.90, kCompactFracOfPin = 0.61, kScanRecordsPerSmCycle = 1.0264e-2;
+		if (mem_khz > 0 && bus_bits > 0) {
+			const double pin_bytes_per_ms = 2.0 * (double)mem_khz * (double)bus_bits / 8.0;     // kHz x bytes = bytes per ms
+			e->stream_bytes_per_ms = kStreamFracOfPin * pin_bytes_per_ms;
+			e->stream_q_bytes_per_ms = kCompactFracOfPin * pin_bytes_per_ms;
+		}
+		if (sm_khz > 0) e->scan_ms_per_record = 1.0 / (kScanRecordsPerSmCycle * (double)e->sm_count * (double)sm_khz);
+	}
+	// experiment / test switches: the environment gives the initial value once per handle (never read per call), apo_set_tuning changes them
+	e->env_no_fuse = getenv("APO_NO_FUSE") != nullptr;
+	e->env_force_fuse = getenv("APO_FORCE_FUSE") != nullptr;
+	e->env_no_staging = getenv("APO_NO_STAGING") != nullptr;
+	e->env_nccl_join = getenv("APO_JOIN_NCCL") != nullptr;
 	if ((c = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", c);
 	if ((c = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", c);
 	e->stream = e->own_stream;
@@ -577,8 +766,10 @@ extern "C" int apo_create(int device, apo_engine **out) {
 extern "C" void apo_destroy(apo_engine *e) {
 	if (!e) return;
 	cudaSetDevice(e->device);
-	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+	peer_teardown(e);
+	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+	if (e->zc_host) cudaFreeHost(e->zc_host);
 	e->q8.release(); e->qd2.release(); e->qli.release(); e->qbook.release(); e->d_ptab.release(); e->d_pair.release(); e->d_cbf.release(); e->stage.release();
 	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->acc_joined.release(); e->misc.release();
 	e->result.release(); e->keys.release(); e->sel_key.release(); e->sel_idx.release();
@@ -598,6 +789,14 @@ extern "C" const char *apo_last_error(const apo_engine *e) { return e ? e->err.c
 extern "C" int apo_set_stream(apo_engine *e, uint64_t cuda_stream) {
 	if (!e) return APO_E_ARG;
 	e->stream = cuda_stream ? (cudaStream_t)(uintptr_t)cuda_stream : e->own_stream;
+	return APO_OK;
+}
+
+extern "C" int apo_set_tuning(apo_engine *e, uint32_t flags) {
+	if (!e) return APO_E_ARG;
+	if (flags & ~(APO_TUNE_NO_FUSE | APO_TUNE_FORCE_FUSE | APO_TUNE_NO_STAGING | APO_TUNE_NCCL_JOIN)) return fail(e, APO_E_ARG, "unknown tuning flag %#x", flags);
+	e->env_no_fuse = (flags & APO_TUNE_NO_FUSE) != 0; e->env_force_fuse = (flags & APO_TUNE_FORCE_FUSE) != 0;
+	e->env_no_staging = (flags & APO_TUNE_NO_STAGING) != 0; e->env_nccl_join = (flags & APO_TUNE_NCCL_JOIN) != 0;
 	return APO_OK;
 }
 
@@ -626,6 +825,24 @@ extern "C" int apo_reward_batch(apo_engine *e, const apo_record *recs, uint64_t 
 	if (n == 0) return APO_OK;
 	if (!recs) return fail(e, APO_E_ARG, "recs is NULL");
 	CK(cudaSetDevice(e->device));
+	constexpr uint64_t kZeroCopyMax = 1024;      // records: the IDE scores one trace at a time (TCS:408-418, 547)
+	if (n <= kZeroCopyMax) {
+		// single-trace path: one launch, no copies — the kernel reads the records from and writes the results to one
+		// page-locked, device-mapped block (PCIe round trips of a few hundred bytes beat four cudaMemcpyAsync calls)
+		const uint64_t per = sizeof(apo_record) + APO_NDIM * 8 + 8 + 4;
+		if (!e->zc_host) { CK(cudaMallocHost((void **)&e->zc_host, kZeroCopyMax * per)); e->zc_cap = kZeroCopyMax * per; }
+		apo_record *zin = (apo_record *)e->zc_host;
+		double *zdims = (double *)(e->zc_host + kZeroCopyMax * sizeof(apo_record));
+		double *zfin = zdims + kZeroCopyMax * APO_NDIM;
+		uint32_t *zmask = (uint32_t *)(zfin + kZeroCopyMax);
+		memcpy(zin, recs, n * sizeof(apo_record));
+		CK(apo::run_reward_batch(zin, n, e->W, e->d_lut.p, zdims, zmask, zfin, e->stream));
+		CK(cudaStreamSynchronize(e->stream));
+		if (dims) memcpy(dims, zdims, n * APO_NDIM * 8);
+		if (masks) memcpy(masks, zmask, n * 4);
+		if (finals) memcpy(finals, zfin, n * 8);
+		return APO_OK;
+	}
 	CK(e->batch_in.reserve(n));
 	CK(e->batch_out.reserve(n * (APO_NDIM + 1)));
 	CK(e->batch_mask.reserve(n));
@@ -895,6 +1112,7 @@ extern "C" int apo_score_begin(apo_engine *e, uint32_t C_total) {
 	CK(cudaSetDevice(e->device));
 	int rc = ensure_scratch(e, C_total, C_total);
 	if (rc) return rc;
+	e->timing_on = true;
 	return begin_score(e, C_total);
 }
 
@@ -920,6 +1138,7 @@ extern "C" int apo_score_finish(apo_engine *e, const apo_score_opts *o, double *
 	if (o->K > e->score_C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, e->score_C);
 	if (o->K > kMaxK) return fail(e, APO_E_ARG, "K=%u exceeds the supported beam width %u", o->K, kMaxK);
 	CK(cudaSetDevice(e->device));
+	if (peer_join_active(e, e->score_C)) e->join_epoch++;
 	return finish_score(e, o, e->score_C, scores, counts, topk, report);
 }
 
@@ -931,32 +1150,36 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	if ((rc = check_opts(e, o, C, T, &first, &count))) return rc;
 	CK(cudaSetDevice(e->device));
 	if ((rc = ensure_scratch(e, C, o->K))) return rc;
-	if ((rc = begin_score(e, C))) return rc;
-	// one launch per call: the corpus scan (K2) rides on an extra warp of every scoring CTA and the last CTA
-	// finalises (K3) when there is a single rank
-	// ... when the scan can hide behind the scoring stream: one warp per SM scans ~3 records/us (measured: 10 M
-	// records in 3.35 ms on 148 SMs), the scoring kernel streams ~7.4 GB/ms (Form D / R) or ~5 GB/ms (Form Q)
-	const double k1_ms = (double)C * (double)count * (o->source == APO_SRC_ROLLOUTS ? (double)e->roll_row : (e->compact ? 14.0 : 36.0)) /
-	                     (o->source == APO_SRC_DIMS && e->compact ? 5.0e9 : 7.4e9);
-	const double scan_ms = (double)e->corpus_T * 3.35e-7 * (148.0 / (double)e->sm_count);
-	const bool fuse = wants_corpus(e, o) && count > 0 && getenv("APO_NO_FUSE") == nullptr &&
-	                  (k1_ms > 1.3 * scan_ms || getenv("APO_FORCE_FUSE") != nullptr);      // env switches: tests / experiments
-	// without a corpus request the same tail still saves the K3 launch at one rank: an empty scan, then the last CTA finalises
-	const bool tail_only = !wants_corpus(e, o) && e->nranks == 1 && count > 0 && getenv("APO_NO_FUSE") == nullptr;
+	const double row_bytes = o->source == APO_SRC_ROLLOUTS ? (double)e->roll_row : (e->compact ? 14.0 : 36.0);
+	const double stream_bytes = (double)C * (double)count * row_bytes;
+	choose_timing(e, o, (uint64_t)stream_bytes);
+	if (peer_join_active(e, C)) e->join_epoch++;          // counts joined calls only: consecutive joins alternate between the two export slots
+	// One launch per call: the corpus scan (K2) rides on an extra warp of every scoring CTA and the last CTA finalises (K3,
+	// after the peer-memory join when the record axis is sharded) ... when the scan can hide behind the evaluation stream.
+	// Both rates are derived from the device at apo_create.
+	const double k1_ms = stream_bytes / (o->source == APO_SRC_DIMS && e->compact ? e->stream_q_bytes_per_ms : e->stream_bytes_per_ms);
+	const double scan_ms = (double)e->corpus_T * e->scan_ms_per_record;
+	const bool one_launch = e->nranks == 1 || peer_join_active(e, C);
+	const bool fuse = wants_corpus(e, o) && count > 0 && !e->env_no_fuse && (k1_ms > 1.3 * scan_ms || e->env_force_fuse);
+	// without a corpus request the same tail still saves the K3 launch: an empty scan, then the last CTA finalises
+	const bool tail_only = !wants_corpus(e, o) && one_launch && count > 0 && !e->env_no_fuse;
 	if (fuse || tail_only) {
-		if ((rc = arm_corpus(e, C))) return rc;
+		if ((rc = begin_score(e, C, true))) return rc;
 		apo::K2Params k2 = make_k2(e, C, make_fin(e, C, o->K, fuse ? 1 : 0));
 		if (tail_only) { k2.T = 0; k2.recs = nullptr; }
 		if ((rc = launch_k1_resident(e, o, 0, first, count, &k2))) return rc;
-	} else if ((rc = launch_k1_resident(e, o, 0, first, count))) return rc;
+	} else {
+		if ((rc = begin_score(e, C))) return rc;
+		if ((rc = launch_k1_resident(e, o, 0, first, count))) return rc;
+	}
 	return finish_score(e, o, C, scores, counts, topk, report, fuse || tail_only);
 }
 
 namespace {
 // Streams host rows [C][T] (row bytes 36 = Form D, 32 = Form R, 16 = Form R16) through two device
 // windows: the H2D copy of chunk i+1 (copy stream) overlaps K1 on chunk i (compute stream).
-int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows, uint32_t row, uint32_t C, uint64_t T,
-                    double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+int score_host_rows_impl(apo_engine *e, const apo_score_opts *o, const uint8_t *rows, uint32_t row, uint32_t C, uint64_t T,
+                         double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
 	if (!e) return APO_E_ARG;
 	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
 	if (!rows || C == 0) return fail(e, APO_E_ARG, "input is NULL or C == 0");
@@ -976,8 +1199,10 @@ int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows,
 	// pageable callers (malloc / ArrayBuffer / numpy): the driver would stage such copies through one small internal
 	// buffer on the calling thread; instead gather each chunk into pinned memory with a few host threads while the
 	// previous chunk is on the wire.  Pinned or registered callers (apo_host_alloc) are read in place.
-	const bool staged = T > 0 && is_pageable(rows) && getenv("APO_NO_STAGING") == nullptr;
+	const bool staged = T > 0 && is_pageable(rows) && !e->env_no_staging;
 	if (staged && (rc = ensure_stage(e, (uint64_t)C * Tc * row))) return rc;
+	choose_timing(e, o, (uint64_t)C * T * row);
+	if (peer_join_active(e, C)) e->join_epoch++;
 	if ((rc = begin_score(e, C))) return rc;
 	const bool recip = (o->flags & APO_SCORE_RECIP) != 0;
 	int nchunk = 0;
@@ -992,24 +1217,31 @@ int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows,
 			src = e->h_stage[b]; spitch = Tc * row;
 		}
 		if (nchunk >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->win_free[b], 0));
-		CK(cudaMemcpy2DAsync(e->win[b].p, Tc * row, src, spitch, n * row, C, cudaMemcpyHostToDevice, e->copy_stream));
+		if ((rc = copy_rows_h2d(e, e->win[b].p, Tc * row, src, spitch, n * row, C, e->copy_stream))) { cudaStreamSynchronize(e->copy_stream); return rc; }
 		if (staged) CK(cudaEventRecord(e->stage_done[b], e->copy_stream));
 		CK(cudaEventRecord(e->win_ready[b], e->copy_stream));
 		CK(cudaStreamWaitEvent(e->stream, e->win_ready[b], 0));
 		apo::K1Params P{};
 		P.base = e->win[b].p; P.pitch_bytes = Tc * row; P.C = C; P.T = n; P.acc = e->acc.p;
 		P.lut = e->d_lut.p; P.W = e->W;
-		if (e->k1_used + 2 > e->k1_ev.size()) {
-			for (int i = 0; i < 2; i++) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->k1_ev.push_back(ev); }
-		}
-		CK(cudaEventRecord(e->k1_ev[e->k1_used], e->stream));
+		if ((rc = record_k1_event(e, 0))) return rc;
 		CK(apo::run_reward9(P, (int)row, (int)o->variant, recip, e->sm_count, e->stream));
-		CK(cudaEventRecord(e->k1_ev[e->k1_used + 1], e->stream));
-		e->k1_used += 2;
+		if ((rc = record_k1_event(e, 1))) return rc;
 		e->timing.launches++;
 		CK(cudaEventRecord(e->win_free[b], e->stream));
 	}
 	return finish_score(e, o, C, scores, counts, topk, report);
+}
+
+int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows, uint32_t row, uint32_t C, uint64_t T,
+                    double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+	const int rc = score_host_rows_impl(e, o, rows, row, C, T, scores, counts, topk, report);
+	if (rc && e) {
+		// a failure in the middle of the chunk loop: nothing may still be reading the caller's memory when we return
+		cudaStreamSynchronize(e->copy_stream);
+		cudaStreamSynchronize(e->stream);
+	}
+	return rc;
 }
 }  // namespace
 
@@ -1068,6 +1300,7 @@ extern "C" int apo_comm_init(apo_engine *e, int nranks, int rank, const uint8_t 
 	if (!e || !id) return fail(e, APO_E_ARG, "NULL argument");
 	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(e, APO_E_ARG, "bad rank %d of %d", rank, nranks);
 	CK(cudaSetDevice(e->device));
+	peer_teardown(e);
 	if (e->comm) { g_nccl.CommDestroy(e->comm); e->comm = nullptr; }
 	e->nranks = 1; e->rank = 0;
 	if (nranks == 1) return APO_OK;
@@ -1084,11 +1317,20 @@ extern "C" int apo_comm_init(apo_engine *e, int nranks, int rank, const uint8_t 
 	const int wrc = g_nccl.AllReduce(e->misc.p + 24, e->misc.p + 24, 1, kNcclInt64, kNcclSum, e->comm, e->stream);
 	if (wrc != 0) return fail(e, APO_E_NCCL, "ncclAllReduce (warm-up): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(wrc) : "error");
 	CK(cudaStreamSynchronize(e->stream));
-	return APO_OK;
+	// the join itself runs over NVLink peer memory inside the scoring launch; NCCL stays as the bootstrap and the fallback
+	return peer_setup(e);
+}
+
+extern "C" int apo_comm_join_mode(const apo_engine *e) {
+	if (!e || e->nranks <= 1) return 0;
+	return (e->peer_ok && !e->env_nccl_join) ? 2 : 1;
 }
 
 extern "C" int apo_comm_destroy(apo_engine *e) {
 	if (!e) return APO_E_ARG;
+	cudaSetDevice(e->device);
+	if (e->own_stream) cudaStreamSynchronize(e->stream);
+	peer_teardown(e);
 	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	e->comm = nullptr; e->nranks = 1; e->rank = 0;
 	return APO_OK;

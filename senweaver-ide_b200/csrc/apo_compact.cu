@@ -273,7 +273,7 @@ k_reward9q(const KqParams P) {
 		}
 	} else if (warp == CW + 1) {
 		if (P.corpus_on) {                                        // corpus warp: K2's scan on the spare issue slots
-			if (lane < 18) s_ex[lane] = ~0ull;
+			if (lane < 18) s_ex[lane] = 0ull;
 			__syncwarp();
 			corpus_scan_warp<true>(P.corpus, (uint64_t)blockIdx.x * 32, (uint64_t)gridDim.x * 32, s_ex, s_cat, s_lut, lane);
 		}

@@ -8,14 +8,16 @@
 
 namespace apo {
 
-__device__ __forceinline__ void ex_insert(unsigned long long *slots, unsigned long long idx) {
-	// keep the 3 smallest indices: a value flows down the chain, every slot only decreases
-	unsigned long long v = idx;
+// First-three-examples slots hold INVERTED record indices (key = ~index, 0 = empty), so that zero-filled memory is
+// an armed slot set (one memset arms accumulators, slots and ticket).  Smallest index == largest key.
+__device__ __forceinline__ void ex_insert(unsigned long long *slots, unsigned long long key) {
+	// keep the 3 largest keys: a key flows down the chain, every slot only increases
+	unsigned long long v = key;
 #pragma unroll
 	for (int k = 0; k < 3; k++) {
-		const unsigned long long old = atomicMin(&slots[k], v);
-		if (old == ~0ull) return;                   // slot was empty: nothing displaced
-		v = old > v ? old : v;
+		const unsigned long long old = atomicMax(&slots[k], v);
+		if (old == 0ull) return;                    // slot was empty: nothing displaced
+		v = old < v ? old : v;
 	}
 }
 
@@ -43,7 +45,7 @@ __device__ __forceinline__ uint32_t field_sum(unsigned long long pk, int f) {
 
 // One warp's share of the corpus: records t = first + lane, first + lane + stride, ...  All 32 lanes stay
 // in the loop together (full-warp collectives in the flush).  s_ex: 18 shared-memory slots (first three
-// matches of each pattern, ~0 = empty) shared by the caller's warps; s_cat / s_lut: the categorical
+// matches of each pattern as inverted indices, 0 = empty) shared by the caller's warps; s_cat / s_lut: the categorical
 // product table and the {total weight, reciprocal} LUT (ROT: LUT stored at the bank-rotated index).
 template <bool ROT>
 __device__ __forceinline__ void corpus_scan_warp(const K2Params &P, uint64_t first, uint64_t stride, unsigned long long *s_ex,
@@ -92,7 +94,7 @@ __device__ __forceinline__ void corpus_scan_warp(const K2Params &P, uint64_t fir
 				}
 			}
 			if (bad) {                                                                   // APO:644-755: every predicate ANDs 'bad'
-				const unsigned long long gi = P.idx_base + t;
+				const unsigned long long gk = ~(P.idx_base + t);                         // inverted index (see ex_insert)
 				const bool hit[APO_NPAT] = {
 				    (r.flags & APO_F_ERRORS) != 0,       // P1 APO:644
 				    (r.flags & APO_F_FAILSPAN) != 0,     // P2 APO:666-670
@@ -106,7 +108,7 @@ __device__ __forceinline__ void corpus_scan_warp(const K2Params &P, uint64_t fir
 					if (hit[p]) {
 						pat += 1ull << (10 * p);
 						// slice(0,3): first three in corpus order
-						if (gi < *((volatile unsigned long long *)&s_ex[3 * p + 2])) ex_insert(&s_ex[3 * p], gi);
+						if (gk > *((volatile unsigned long long *)&s_ex[3 * p + 2])) ex_insert(&s_ex[3 * p], gk);
 					}
 				}
 			}
@@ -193,9 +195,10 @@ __device__ __forceinline__ void corpus_scan_warp(const K2Params &P, uint64_t fir
 }
 
 // After every scanning warp of the CTA has flushed: push the CTA's first-three examples to the global
-// scratch, take a ticket, and let the last CTA publish this rank's examples and (at one rank) finalise.
+// scratch, take a ticket, and let the last CTA publish this rank's examples and finalise (segmented sum +
+// top-K; at > 1 rank after the peer-memory join of the partial vectors).
 // Must be called by every thread of the CTA (it synchronises the block).
-static __device__ void finalize_block(const FinalizeParams &F);
+static __device__ void finalize_and_publish(const FinalizeParams &F);
 
 __device__ __forceinline__ void corpus_tail(const K2Params &P, const unsigned long long *s_ex, bool *s_last) {
 	const int tid = threadIdx.x;
@@ -205,7 +208,7 @@ __device__ __forceinline__ void corpus_tail(const K2Params &P, const unsigned lo
 #pragma unroll
 		for (int k = 0; k < 3; k++) {
 			const unsigned long long v = s_ex[3 * tid + k];
-			if (v != ~0ull && v < P.ex_scratch[3 * tid + 2]) ex_insert(&P.ex_scratch[3 * tid], v);
+			if (v != 0ull && v > P.ex_scratch[3 * tid + 2]) ex_insert(&P.ex_scratch[3 * tid], v);
 		}
 	}
 	__threadfence();
@@ -219,12 +222,12 @@ __device__ __forceinline__ void corpus_tail(const K2Params &P, const unsigned lo
 	__threadfence();
 	if (tid < APO_NPAT * 3) {
 		const unsigned long long v = *((volatile unsigned long long *)&P.ex_scratch[tid]);
-		corp[CORP_EX + 18 * P.rank + tid] = v == ~0ull ? 0ll : (long long)(v + 1);
+		corp[CORP_EX + 18 * P.rank + tid] = v == 0ull ? 0ll : (long long)(~v + 1);     // index + 1, 0 = none
 	}
 	if (tid == 0) { corp[CORP_NREC] = (long long)P.T; *P.ticket = 0; }
 	__threadfence();
 	__syncthreads();
-	if (P.fuse_finalize) finalize_block(P.fin);
+	if (P.fuse_finalize) finalize_and_publish(P.fin);
 }
 
 __device__ __forceinline__ unsigned long long score_key(double s) {
@@ -232,38 +235,53 @@ __device__ __forceinline__ unsigned long long score_key(double s) {
 	return (b >> 63) ? ~b : (b | 0x8000000000000000ull);     // ascending order-preserving map
 }
 
+// APO:498-625 / TCS:596-626 from the joined corpus block.  Block-wide: thread 0 the tallies, threads 1..9 one
+// dimension each, threads 10..15 one pattern each (a single thread walking all of it costs ~10 us of serial latency).
 static __device__ void build_report(const FinalizeParams &F, const long long *corp_g) {
 	apo_corpus_report &R = *F.report;
-	// L2 loads: the partials were produced by other CTAs' atomics (or by the allreduce)
-	long long corp[CORP_FIXED];
-	for (int i = 0; i < CORP_FIXED; i++) corp[i] = __ldcg(corp_g + i);
-	R.total = (uint64_t)corp[CORP_NREC];
-	R.good = (uint64_t)corp[CORP_TALLY]; R.bad = (uint64_t)corp[CORP_TALLY + 1]; R.none = (uint64_t)corp[CORP_TALLY + 2];
-	const uint64_t twf = R.good + R.bad;
-	R.goodRate = twf > 0 ? __ddiv_rn((double)R.good, (double)twf) : 0.0;                     // APO:546-547
-	for (int m = 0; m < APO_NMODE; m++) {
-		for (int k = 0; k < 3; k++) R.byMode[m][k] = (uint64_t)corp[CORP_MODE + 3 * m + k];
-		const uint64_t tot = R.byMode[m][1] + R.byMode[m][2];
-		R.byModeGoodRate[m] = tot > 0 ? __ddiv_rn((double)R.byMode[m][1], (double)tot) : 0.0; // APO:541-544
-	}
-	R.withReward = (uint64_t)corp[CORP_REWARD + 3];
-	R.rewardSum = limbs_to_double(corp + CORP_REWARD);
-	R.avgReward = R.withReward > 0 ? __ddiv_rn(R.rewardSum, (double)R.withReward) : __longlong_as_double(0x7ff8000000000000ll);
-	for (int i = 0; i < APO_NDIM; i++) {
-		apo_dimstat &D = R.dim[i];
-		D.sum = limbs_to_double(corp + CORP_DIM + 4 * i);
-		D.count = (uint64_t)corp[CORP_DIM + 4 * i + 3];
+	const int tid = threadIdx.x;
+	if (tid == 0) {
+		R.total = (uint64_t)__ldcg(corp_g + CORP_NREC);
+		const uint64_t good = (uint64_t)__ldcg(corp_g + CORP_TALLY), bad = (uint64_t)__ldcg(corp_g + CORP_TALLY + 1);
+		R.good = good; R.bad = bad; R.none = (uint64_t)__ldcg(corp_g + CORP_TALLY + 2);
+		const uint64_t twf = good + bad;
+		R.goodRate = twf > 0 ? __ddiv_rn((double)good, (double)twf) : 0.0;                       // APO:546-547
+		for (int m = 0; m < APO_NMODE; m++) {
+			uint64_t v[3];
+			for (int k = 0; k < 3; k++) { v[k] = (uint64_t)__ldcg(corp_g + CORP_MODE + 3 * m + k); R.byMode[m][k] = v[k]; }
+			const uint64_t tot = v[1] + v[2];
+			R.byModeGoodRate[m] = tot > 0 ? __ddiv_rn((double)v[1], (double)tot) : 0.0;         // APO:541-544
+		}
+		long long l[4];
+		for (int q = 0; q < 4; q++) l[q] = __ldcg(corp_g + CORP_REWARD + q);
+		const uint64_t nrew = (uint64_t)l[3];
+		const double rsum = limbs_to_double(l);
+		R.withReward = nrew; R.rewardSum = rsum;
+		R.avgReward = nrew > 0 ? __ddiv_rn(rsum, (double)nrew) : __longlong_as_double(0x7ff8000000000000ll);
+		const uint64_t tc = (uint64_t)__ldcg(corp_g + CORP_TOOL), ts = (uint64_t)__ldcg(corp_g + CORP_TOOL + 1);
+		R.toolCalls = tc; R.toolSucc = ts; R.toolFail = (uint64_t)__ldcg(corp_g + CORP_TOOL + 2);
+		R.toolSuccessRate = tc > 0 ? __ddiv_rn((double)ts, (double)tc)                          // TCS:624
+		                           : __longlong_as_double(0x7ff8000000000000ll);
+	} else if (tid <= APO_NDIM) {
+		const int i = tid - 1;
+		apo_dimstat D;
+		long long l[4];
+		for (int q = 0; q < 4; q++) l[q] = __ldcg(corp_g + CORP_DIM + 4 * i + q);
+		D.sum = limbs_to_double(l);
+		D.count = (uint64_t)l[3];
 		D.avg = D.count > 0 ? __ddiv_rn(D.sum, (double)D.count) : 0.0;                       // APO:567
 		D.low_flag = (D.count >= 5 && D.avg < -0.3) ? 1 : 0;                                 // APO:575
 		D.low_severity = D.avg < -0.5 ? 2 : 1;                                               // APO:591
 		D.sugg_flag = (D.count >= 3 && D.avg < 0.0) ? 1 : 0;                                 // APO:802
 		D.sugg_priority = D.avg < -0.5 ? 2 : 1;                                              // APO:819
 		for (int k = 0; k < 4; k++) D.pad[k] = 0;
-	}
-	const uint64_t minc[APO_NPAT] = {2, 2, 3, 2, 2, 2};                                      // APO:645,671,695,715,736,756
-	for (int p = 0; p < APO_NPAT; p++) {
-		apo_pattern &Q = R.pat[p];
-		Q.count = R.bad == 0 ? 0 : (uint64_t)corp[CORP_PAT + p];                             // APO:641
+		R.dim[i] = D;
+	} else if (tid <= APO_NDIM + APO_NPAT) {
+		const int p = tid - 1 - APO_NDIM;
+		const uint64_t minc[APO_NPAT] = {2, 2, 3, 2, 2, 2};                                      // APO:645,671,695,715,736,756
+		const uint64_t bad = (uint64_t)__ldcg(corp_g + CORP_TALLY + 1);
+		apo_pattern Q;
+		Q.count = bad == 0 ? 0 : (uint64_t)__ldcg(corp_g + CORP_PAT + p);                       // APO:641
 		Q.flag = Q.count >= minc[p] ? 1 : 0;
 		uint8_t sev = 1;
 		if (p == 0 || p == 1) sev = Q.count >= 5 ? 2 : 1;                                    // APO:650,676
@@ -274,15 +292,13 @@ static __device__ void build_report(const FinalizeParams &F, const long long *co
 		// first three in corpus order: ranks hold disjoint ascending index ranges
 		int got = 0;
 		for (int k = 0; k < 3; k++) Q.examples[k] = -1;
-		for (int r = 0; r < F.nranks && got < 3; r++)
-			for (int k = 0; k < 3 && got < 3; k++) {
-				const long long v = __ldcg(corp_g + CORP_EX + 18 * r + 3 * p + k);
-				if (v > 0) Q.examples[got++] = v - 1;
-			}
+		for (int r = 0; r < F.nranks && got < 3; r++) {
+			long long v[3];
+			for (int k = 0; k < 3; k++) v[k] = __ldcg(corp_g + CORP_EX + 18 * r + 3 * p + k);
+			for (int k = 0; k < 3 && got < 3; k++) if (v[k] > 0) Q.examples[got++] = v[k] - 1;
+		}
+		R.pat[p] = Q;
 	}
-	R.toolCalls = (uint64_t)corp[CORP_TOOL]; R.toolSucc = (uint64_t)corp[CORP_TOOL + 1]; R.toolFail = (uint64_t)corp[CORP_TOOL + 2];
-	R.toolSuccessRate = R.toolCalls > 0 ? __ddiv_rn((double)R.toolSucc, (double)R.toolCalls)  // TCS:624
-	                                    : __longlong_as_double(0x7ff8000000000000ll);
 }
 
 // Block-wide; every thread of the calling block must enter.  Works for any blockDim.x
@@ -306,7 +322,7 @@ static __device__ __noinline__ void finalize_block(const FinalizeParams &F) {
 		F.counts[c] = n;
 		F.keys[c] = score_key(s);
 	}
-	if (tid == 0 && F.with_corpus) build_report(F, acc + (uint64_t)ACC_PER_CAND * C);
+	if (F.with_corpus) build_report(F, acc + (uint64_t)ACC_PER_CAND * C);
 	__syncthreads();
 	const uint32_t K = F.K < C ? F.K : C;
 	if (K == 0) return;
@@ -325,15 +341,30 @@ static __device__ __noinline__ void finalize_block(const FinalizeParams &F) {
 			if ((k & maskhi) == prefix) atomicAdd(&s_hist[(k >> shift) & 255], 1u);
 		}
 		__syncthreads();
-		if (tid == 0) {
-			unsigned int need = s_need;
-			int d = 255;
-			for (; d > 0; d--) {
-				if (s_hist[d] >= need) break;
-				need -= s_hist[d];
+		if (warp == 0) {
+			// the digit d whose suffix count first reaches `need`, scanning 255 -> 0: lane l owns bins [8l, 8l+8)
+			unsigned int h[8], tot = 0;
+#pragma unroll
+			for (int j = 0; j < 8; j++) { h[j] = s_hist[8 * lane + j]; tot += h[j]; }
+			unsigned int suf = tot;                                   // sum over lanes >= this one
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const unsigned int v = __shfl_down_sync(0xffffffffu, suf, o);
+				if (lane + o < 32) suf += v;
 			}
-			s_need = need;
-			s_prefix = prefix | ((unsigned long long)d << shift);
+			const unsigned int need = s_need, above = suf - tot;
+			const bool here = above < need && need <= suf;
+			const unsigned int any = __ballot_sync(0xffffffffu, here);
+			if (here || (any == 0u && lane == 0)) {                   // (any == 0 cannot happen: need <= #keys under the prefix)
+				unsigned int rem = need - (here ? above : 0u);
+				int j = 7;
+				for (; j > 0; j--) {
+					if (h[j] >= rem) break;
+					rem -= h[j];
+				}
+				s_need = rem;
+				s_prefix = prefix | ((unsigned long long)(8 * lane + j) << shift);
+			}
 		}
 		__syncthreads();
 	}
@@ -379,5 +410,83 @@ static __device__ __noinline__ void finalize_block(const FinalizeParams &F) {
 	}
 }
 
+// ---------------------------------------------------------------- cross-rank join over peer memory
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ long long ld_relaxed_sys(const long long *p) {
+	long long v;
+	asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;   // a rank that never arrives: report, do not hang
+
+// Block-wide.  Returns false when a peer did not arrive within PEER_TIMEOUT_NS.
+static __device__ bool peer_join(const JoinParams &J, const long long *acc_local, ResultMeta *meta) {
+	__shared__ int s_ok;
+	const int tid = threadIdx.x, nth = blockDim.x;
+	long long *mine = J.slot[J.rank];
+	if (tid == 0) s_ok = 1;
+	const unsigned long long t0 = globaltimer_ns();
+	// 1. publish this rank's partials (they were produced by other CTAs' atomics: read them from L2)
+	for (uint32_t i = tid; i < J.words; i += nth) mine[i] = __ldcg(acc_local + i);
+	__threadfence_system();
+	__syncthreads();
+	// 2. raise this rank's flag in every rank's block (remote stores), 3. wait for every rank's flag in ours (local loads)
+	if (tid < J.nranks) {
+		st_release_sys(J.flag[tid] + J.rank, J.epoch);
+		const unsigned long long *f = J.flag[J.rank] + tid;
+		while (ld_acquire_sys(f) < J.epoch) {
+			if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { s_ok = 0; break; }
+			__nanosleep(64);
+		}
+	}
+	__syncthreads();
+	const unsigned long long t1 = globaltimer_ns();
+	if (!s_ok) { if (tid == 0) { meta->status = 1u; meta->join_wait_us = (float)((t1 - t0) * 1e-3); meta->join_reduce_us = 0.f; } return false; }
+	// 4. sum the slots of all ranks (NVLink peer loads; integers: any order gives the same bits)
+	for (uint32_t i = tid; i < J.words; i += nth) {
+		long long s = 0;
+		for (int r = 0; r < J.nranks; r++) s += ld_relaxed_sys(J.slot[r] + i);
+		J.joined[i] = s;
+	}
+	__threadfence();
+	__syncthreads();
+	// tell every peer that this rank no longer reads its slot (only consulted when a peer tears its block down)
+	if (tid < J.nranks) st_release_sys(J.flag[tid] + PEER_MAX + J.rank, J.epoch);
+	if (tid == 0) { meta->status = 0u; meta->join_wait_us = (float)((t1 - t0) * 1e-3); meta->join_reduce_us = (float)((globaltimer_ns() - t1) * 1e-3); }
+	return true;
+}
+
+// join (> 1 rank) -> segmented sum + report + top-K -> result block written to the caller's page-locked buffer.
+static __device__ void finalize_and_publish(const FinalizeParams &F0) {
+	FinalizeParams F = F0;
+	ResultMeta *meta = reinterpret_cast<ResultMeta *>(F.result_base + F.meta_off);
+	bool ok = true;
+	if (F.join.nranks > 1) {
+		ok = peer_join(F.join, F.acc, meta);
+		F.acc = F.join.joined;
+	} else if (threadIdx.x == 0) { meta->status = 0u; meta->pad = 0u; meta->join_wait_us = 0.f; meta->join_reduce_us = 0.f; }
+	if (ok) finalize_block(F);
+	if (F.host_out) {
+		__threadfence();
+		__syncthreads();
+		const uint4 *src = reinterpret_cast<const uint4 *>(F.result_base);
+		uint4 *dst = reinterpret_cast<uint4 *>(F.host_out);
+		for (uint32_t i = threadIdx.x; i < F.result_bytes / 16; i += blockDim.x) dst[i] = __ldcg(src + i);
+		__threadfence_system();
+	}
+}
 
 }  // namespace apo

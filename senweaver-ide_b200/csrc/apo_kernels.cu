@@ -150,7 +150,7 @@ k_reward9(const K1Params P) {
 	} else if (warp == CW + 1) {
 		// ------------------------------------------------ corpus warp: K2's scan rides on the spare issue slots
 		if (P.corpus_on) {
-			if (lane < 18) s_ex[lane] = ~0ull;
+			if (lane < 18) s_ex[lane] = 0ull;
 			__syncwarp();
 			corpus_scan_warp<true>(P.corpus, (uint64_t)blockIdx.x * 32, (uint64_t)gridDim.x * 32, s_ex,
 			                       reinterpret_cast<const double *>(s_lut + 512), s_lut, lane);
@@ -363,7 +363,7 @@ k_detect6(const K2Params P) {
 	__shared__ double2 s_lut[512];                     // {total weight, reciprocal} per (natural) presence mask
 	__shared__ bool s_last;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if (tid < APO_NPAT * 3) s_ex[tid] = ~0ull;
+	if (tid < APO_NPAT * 3) s_ex[tid] = 0ull;
 	if (tid < CAT_WORDS) s_cat[tid] = P.lut[1024 + tid];
 	for (int i = tid; i < 512; i += K2_THREADS) s_lut[i] = make_double2(P.lut[i], P.lut[512 + i]);
 	__syncthreads();
@@ -380,7 +380,7 @@ cudaError_t run_detect6(const K2Params &P, int sm_count, cudaStream_t st) {
 	return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(1024) k_finalize(const FinalizeParams F) { finalize_block(F); }
+__global__ void __launch_bounds__(1024) k_finalize(const FinalizeParams F) { finalize_and_publish(F); }
 
 cudaError_t run_finalize(const FinalizeParams &F, cudaStream_t st) {
 	k_finalize<<<1, 1024, 0, st>>>(F);

@@ -8,11 +8,32 @@ namespace apo {
 
 struct Weights { double w[APO_NDIM]; };
 
+// Cross-rank join of the packed int64 partial vector over NVLink peer memory (one process per GPU).
+// Every rank owns one peer-mapped block: two export slots (epoch parity) and one arrival flag per source rank.
+// The CTA that finalises a scoring call publishes this rank's partials into its own slot, raises its flag in
+// every peer's block, waits for all flags of the epoch in its OWN block (local polling), then sums the peers'
+// slots with direct NVLink loads.  Integer sums: the result is the same on every rank and for every rank count.
+constexpr int PEER_MAX = 8;
+struct JoinParams {
+	int nranks, rank;                       // nranks <= 1: no join
+	uint32_t words;                         // int64 words exchanged (acc_words(C, nranks))
+	uint32_t pad;
+	unsigned long long epoch;               // > 0, identical on every rank for the same call
+	long long *slot[PEER_MAX];              // export slot of rank r for this epoch's parity (peer-mapped address)
+	unsigned long long *flag[PEER_MAX];     // arrival flags inside rank r's block: flag[r][source rank]
+	long long *joined;                      // local: the summed vector
+};
+
 struct FinalizeParams {
 	const long long *acc;
 	uint32_t C, K;
 	int nranks;
 	int with_corpus;
+	JoinParams join;
+	uint8_t *result_base;       // device result block (scores | counts | topk | report | meta)
+	uint8_t *host_out;          // page-locked, device-mapped copy of the block written by the finalising CTA; NULL = the host copies
+	uint32_t result_bytes;
+	uint32_t meta_off;          // ResultMeta inside the block
 	double *scores;             // [C]
 	uint64_t *counts;           // [C]
 	unsigned long long *keys;   // [C] scratch
@@ -20,6 +41,13 @@ struct FinalizeParams {
 	int32_t *sel_idx;           // [K] scratch
 	int32_t *topk;              // [K]
 	apo_corpus_report *report;
+};
+
+struct ResultMeta {             // tail of the result block
+	uint32_t status;            // 0 ok, 1 = peer join timed out (a rank never arrived)
+	uint32_t pad;
+	float join_wait_us;         // publish -> all ranks arrived (includes the skew between ranks)
+	float join_reduce_us;       // reading and summing the peers' slots
 };
 
 struct K2Params {

@@ -18,7 +18,8 @@ LIB_PATH = os.path.join(_HERE, "libapo_b200.so")
 
 NDIM, NPAT, NMODE = 9, 6, 5
 SRC_DIMS, SRC_ROLLOUTS = 0, 1
-SCORE_CORPUS, SCORE_RECIP = 0x1, 0x2
+SCORE_CORPUS, SCORE_RECIP, SCORE_TIMING = 0x1, 0x2, 0x4
+TUNE_NO_FUSE, TUNE_FORCE_FUSE, TUNE_NO_STAGING, TUNE_NCCL_JOIN = 0x1, 0x2, 0x4, 0x8
 F_ERRORS, F_ENDED, F_VALID, F_FAILSPAN = 0x01, 0x02, 0x08, 0x10
 UNIQUE_ID_BYTES = 128
 
@@ -65,7 +66,8 @@ class CorpusReport(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("reward_ms", C.c_float), ("corpus_ms", C.c_float), ("allreduce_ms", C.c_float),
-                ("finalize_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("pad", C.c_uint32)]
+                ("finalize_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("pad", C.c_uint32),
+                ("join_wait_ms", C.c_float), ("join_reduce_ms", C.c_float)]
 
 
 class ScoreOpts(C.Structure):
@@ -81,14 +83,14 @@ class ApoError(RuntimeError):
 
 # every symbol include/apo_b200.h declares (tests/test_abi_symbols.py checks the .so against this list)
 ABI_SYMBOLS = (
-    "apo_abi_version", "apo_create", "apo_destroy", "apo_last_error", "apo_set_stream", "apo_set_weights",
+    "apo_abi_version", "apo_create", "apo_destroy", "apo_last_error", "apo_set_stream", "apo_set_weights", "apo_set_tuning",
     "apo_get_weights", "apo_reward_batch", "apo_reward_one", "apo_corpus_upload", "apo_corpus_generate",
     "apo_corpus_download", "apo_records_from_json", "apo_corpus_upload_json", "apo_dims_upload", "apo_dims_generate", "apo_dims_download", "apo_dims_attach",
     "apo_dims_compact", "apo_dims_generate_compact", "apo_dims_upload_compact", "apo_dims_layout",
     "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_rollouts16_upload",
     "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_score",
     "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records", "apo_host_alloc", "apo_host_free",
-    "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy",
+    "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy", "apo_comm_join_mode",
 )
 
 
@@ -128,6 +130,7 @@ def load_library() -> C.CDLL:
     L.apo_last_error.restype = C.c_char_p
     L.apo_set_stream.argtypes = [vp, u64]
     L.apo_set_weights.argtypes = [vp, vp]
+    L.apo_set_tuning.argtypes = [vp, u32]
     L.apo_get_weights.argtypes = [vp, vp]
     L.apo_reward_batch.argtypes = [vp, vp, u64, vp, vp, vp]
     L.apo_reward_one.argtypes = [vp, vp, vp, vp, vp]
@@ -161,6 +164,7 @@ def load_library() -> C.CDLL:
     L.apo_comm_unique_id.argtypes = [vp]
     L.apo_comm_init.argtypes = [vp, i32, i32, vp]
     L.apo_comm_destroy.argtypes = [vp]
+    L.apo_comm_join_mode.argtypes = [vp]
     for name in ABI_SYMBOLS:
         f = getattr(L, name)
         if name not in ("apo_destroy", "apo_last_error", "apo_records_from_json"):
@@ -257,6 +261,10 @@ class Engine:
 
     def set_stream(self, cuda_stream: int):
         self._ck(self._L.apo_set_stream(self._h, cuda_stream))
+
+    def set_tuning(self, flags: int):
+        """TUNE_* switches (experiments / tests); results are identical for every setting."""
+        self._ck(self._L.apo_set_tuning(self._h, flags))
 
     def set_weights(self, w):
         w = np.ascontiguousarray(w, np.float64)
@@ -373,12 +381,13 @@ class Engine:
         return ScoreResult(scores, counts, topk, rep, self.last_timing())
 
     # -- scoring
-    def _opts(self, K, source, corpus, recip, variant, first, count) -> ScoreOpts:
-        return ScoreOpts(K, source, (SCORE_CORPUS if corpus else 0) | (SCORE_RECIP if recip else 0), variant, first, count)
+    def _opts(self, K, source, corpus, recip, variant, first, count, timing=False) -> ScoreOpts:
+        return ScoreOpts(K, source, (SCORE_CORPUS if corpus else 0) | (SCORE_RECIP if recip else 0) | (SCORE_TIMING if timing else 0),
+                         variant, first, count)
 
     def score(self, Cn: int, K: int, source: int = SRC_DIMS, corpus: bool = False, recip: bool = False,
-              variant: int = 0, first: int = 0, count: int = 0) -> ScoreResult:
-        o = self._opts(K, source, corpus, recip, variant, first, count)
+              variant: int = 0, first: int = 0, count: int = 0, timing: bool = False) -> ScoreResult:
+        o = self._opts(K, source, corpus, recip, variant, first, count, timing)
         scores = np.empty(Cn, np.float64)
         counts = np.empty(Cn, np.uint64)
         topk = np.empty(K, np.int32)
@@ -448,6 +457,10 @@ class Engine:
 
     def comm_destroy(self):
         self._ck(self._L.apo_comm_destroy(self._h))
+
+    def comm_join_mode(self) -> int:
+        """0 single rank, 1 ncclAllReduce join, 2 peer-memory join inside the scoring launch."""
+        return int(self._L.apo_comm_join_mode(self._h))
 
 
 def pack16(recs: np.ndarray) -> np.ndarray:

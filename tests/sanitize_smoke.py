@@ -29,7 +29,7 @@ for v in range(5):
     assert e.debug_partials(C) == exp
 ref = orc.report(recs)
 assert [r.report.pat[p].count for p in range(6)] == [ref.pat[p].count for p in range(6)]
-os.environ["APO_FORCE_FUSE"] = "1"            # the corpus scan inside the scoring launch (K1, then K1q / K1r below)
+e.set_tuning(pkg.TUNE_FORCE_FUSE)             # the corpus scan inside the scoring launch (K1, then K1q / K1r below)
 r = e.score(C, 3, corpus=True)
 assert r.timing.launches == 1 and e.debug_partials(C) == exp
 assert [r.report.pat[p].count for p in range(6)] == [ref.pat[p].count for p in range(6)] and list(r.report.pat[0].examples) == list(ref.pat[0].examples)
@@ -49,7 +49,7 @@ assert e.debug_partials(C) == orc.score_records_fx(roll)
 e.rollouts16_upload(pkg.pack16(roll))
 r = e.score(C, 2, source=1, corpus=True)
 assert r.timing.launches == 1 and e.debug_partials(C) == orc.score_records_fx(roll) and r.report.bad == ref.bad
-os.environ.pop("APO_FORCE_FUSE")
+e.set_tuning(0)
 e.score_host(dims, 2)
 assert e.debug_partials(C) == exp
 e.score_host_records(pkg.pack16(roll), 2)

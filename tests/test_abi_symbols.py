@@ -24,7 +24,7 @@ def test_library_exports_every_symbol(apo):
     lib = ctypes.CDLL(apo.LIB_PATH)
     for s in header_symbols():
         assert hasattr(lib, s), s
-    assert lib.apo_abi_version() == 1
+    assert lib.apo_abi_version() == 2
 
 
 def test_struct_sizes_match_header(apo):
@@ -33,7 +33,7 @@ def test_struct_sizes_match_header(apo):
     assert ctypes.sizeof(eng.Pattern) == 40
     assert ctypes.sizeof(eng.DimStat) == 32
     assert ctypes.sizeof(eng.ScoreOpts) == 32
-    assert ctypes.sizeof(eng.Timing) == 28
+    assert ctypes.sizeof(eng.Timing) == 36
     assert eng.RECORD_DTYPE.itemsize == 32
 
 

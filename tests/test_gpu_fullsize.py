@@ -103,3 +103,72 @@ def test_config3_compact_layout_is_bit_identical(engine, orc):
     got = engine.dims_download(200, 9_000_000, 4096)
     nan = np.isnan(d)
     assert np.array_equal(nan, np.isnan(got)) and np.array_equal(d[~nan].view(np.uint32), got[~nan].view(np.uint32))
+
+
+@pytest.mark.parametrize("name,agent_permille", [("all-normal", 0), ("all-agent", 1024), ("mixed", 512)])
+def test_config4_128x5M_records_thresholds(engine, orc, apo, name, agent_permille):
+    """BASELINE configs[3]: 128 x 5 M per-(candidate, record) trace records (Form R, 20.5 GB), dims derived on the device with
+    the normal / agent threshold sets (TCS:702-704, 711-713, 734, 741-743, 756) — all-normal, all-agent and a 50/50 mix.
+    Oracle spot windows (exact integers), exact additivity over a 3-way split, variant determinism, top-K from the sums."""
+    C, T, K, seed = 128, 5_000_000, 32, 0x5EED0004
+    engine.rollouts_generate(seed, 0, C, 0, T, agent_permille)
+    res = engine.score(C, K, source=apo.SRC_ROLLOUTS)
+    total, tcount = engine.debug_partials(C)
+    res1 = engine.score(C, K, source=apo.SRC_ROLLOUTS, variant=1)
+    assert engine.debug_partials(C) == (total, tcount) and np.array_equal(res1.topk, res.topk)
+    for first, count, cands in [(0, 4096, [0, 127]), (2_500_000, 2048, [64]), (4_999_000, 1000, [5, 101])]:
+        engine.score(C, 1, source=apo.SRC_ROLLOUTS, first=first, count=count)
+        s, n = engine.debug_partials(C)
+        for c in cands:
+            recs = orc.gen_records(seed, orc.STREAM_ROLLOUT, c, 1, first, count, agent_permille, 8)
+            es, en = orc.score_records_fx(recs)
+            assert s[c] == es[0] and n[c] == en[0], (name, first, c)
+            modes = set(int(m) for m in np.unique(recs["mode"]))
+            if agent_permille == 0:
+                assert 2 not in modes
+            elif agent_permille == 1024:
+                assert modes == {2}
+            else:
+                assert 2 in modes and len(modes) > 1
+    a, b = (T // 3) // 4 * 4, (2 * T // 3) // 4 * 4
+    acc, cnt = [0] * C, [0] * C
+    for first, count in [(0, a), (a, b - a), (b, T - b)]:
+        engine.score(C, 1, source=apo.SRC_ROLLOUTS, first=first, count=count)
+        s, n = engine.debug_partials(C)
+        acc = [x + y for x, y in zip(acc, s)]
+        cnt = [x + y for x, y in zip(cnt, n)]
+    assert acc == total and cnt == tcount
+    exp_scores = apo.sharding.scores_from_partials(total, tcount)
+    assert np.array_equal(exp_scores, res.scores)
+    assert np.array_equal(apo.sharding.topk_indices(exp_scores, K), res.topk)
+
+
+def test_near_tie_topk_order_is_defined_by_the_exact_sums(engine, orc, apo):
+    """Two candidates whose exact means differ by less than 1e-15 (top-K is unpinned by the reference; the
+    reference's own sequential binary64 mean drifts by ~1e-14 at this size, so it cannot resolve such a gap).  The engine's
+    order is defined as: score = the exact rational mean rounded once to binary64 (sum -> binary64, / count), descending,
+    ties -> lower index.  Candidate 1 is candidate 0 with ONE evaluation's tool_success_rate raised by one fp32 ulp."""
+    from fractions import Fraction
+    T = 400_000
+    base = orc.gen_dims(0x5EED0C0D, 3, 1, 0, T, 300, 8)[0]
+    t_star = int(np.flatnonzero(~np.isnan(base[:, 2]) & (np.abs(base[:, 2]) < 0.9))[0])
+    bumped = base.copy()
+    bumped[t_star, 2] = np.nextafter(base[t_star, 2], np.float32(2.0))
+    dims = np.stack([base, bumped, base])                     # 2 == 0 exactly (tie), 1 is a hair better
+    engine.dims_upload(dims)
+    res = engine.score(3, 3)
+    sums, counts = engine.debug_partials(3)
+    assert (sums, counts) == orc.score_dims_fx(dims)          # the integers are the oracle's, exactly
+    assert sums[1] > sums[0] == sums[2] and counts[0] == counts[1]
+    gap = Fraction(sums[1] - sums[0], 1 << 52) / counts[0]
+    assert 0 < gap < Fraction(1, 10**15)
+    exp = apo.sharding.scores_from_partials(sums, counts)
+    assert np.array_equal(res.scores, exp)
+    assert list(res.topk) == list(apo.sharding.topk_indices(exp, 3))
+    if exp[1] > exp[0]:
+        assert list(res.topk) == [1, 0, 2]                    # the gap survives the rounding to binary64: the better candidate wins
+    else:
+        assert exp[1] == exp[0] and list(res.topk) == [0, 1, 2]   # it does not: a binary64 tie, lower index first
+    # the sequential binary64 oracle (the reference's arithmetic) agrees to 1e-11 but need not resolve the gap
+    seq, _ = orc.score_dims(dims)
+    assert np.all(np.abs(seq - exp) <= 1e-11)

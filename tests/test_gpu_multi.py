@@ -23,21 +23,25 @@ def worker(rank, world, uid_path, out_dir, layout):
     eng = pkg.Engine(rank)
     uid = open(uid_path, "rb").read()
     eng.comm_init(world, rank, uid)
+    if layout.endswith("nccl-join"):
+        eng.set_tuning(pkg.TUNE_NCCL_JOIN)          # the fallback join: ncclAllReduce + k_finalize
+    mode = eng.comm_join_mode()
     first, last = pkg.sharding.shard_range(T, world, rank)
     (eng.dims_generate_compact if layout == "compact" else eng.dims_generate)(SEED, 0, C, first, last - first, 300)
     eng.corpus_generate(SEED, first, last - first, 300)
-    res = eng.score(C, K, corpus=True)
-    sums, counts = eng.debug_partials(C)            # after the allreduce: the joined integers
+    for _ in range(3):                              # consecutive joined calls alternate between the two export slots
+        res = eng.score(C, K, corpus=True)
+    sums, counts = eng.debug_partials(C)            # after the join: the summed integers
     rep = res.report
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), scores=res.scores, counts=res.counts, topk=res.topk,
              sums=np.array([str(s) for s in sums]), pat=np.array([[rep.pat[p].count, *rep.pat[p].examples] for p in range(6)]),
              tallies=np.array([rep.total, rep.good, rep.bad, rep.none, rep.withReward]), avg=np.array([rep.avgReward]),
-             launches=np.array([res.timing.launches]))
+             launches=np.array([res.timing.launches]), mode=np.array([mode]))
     eng.close()
 
 
-@pytest.mark.parametrize("layout", ["fp32", "compact"])
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("layout", ["fp32", "compact", "fp32-nccl-join"])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_score_equals_single_gpu(tmp_path, engine, orc, world, layout):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -58,7 +62,10 @@ def test_sharded_score_equals_single_gpu(tmp_path, engine, orc, world, layout):
         assert z["avg"][0] == ref.report.avgReward
         for p in range(6):
             assert list(z["pat"][p]) == [ref.report.pat[p].count, *ref.report.pat[p].examples]
-        assert z["launches"][0] in (3, 4)            # K1 (+ corpus scan when it can hide behind it, else K2), ncclAllReduce, K3
+        if layout.endswith("nccl-join"):
+            assert z["mode"][0] == 1 and z["launches"][0] in (3, 4)   # K1 (+ corpus scan when it can hide behind it, else K2), ncclAllReduce, K3
+        else:
+            assert z["mode"][0] == 2 and z["launches"][0] in (1, 2)   # peer-memory join inside the scoring launch (or inside K2's tail)
     # and the single-GPU result itself is pinned to the oracle on a window
     d = orc.gen_dims(SEED, 3, 1, 0, 50_000, 300, 8)
     engine.score(C, 1, first=0, count=50_000)
@@ -105,3 +112,51 @@ def test_single_process_two_handles_on_threads(engine, orc):
         s, tk, parts, bad, pats = out[r]
         assert np.array_equal(s, ref.scores) and np.array_equal(tk, ref.topk) and parts == rp
         assert bad == ref.report.bad and pats == [ref.report.pat[p].count for p in range(6)]
+
+
+def chunked_worker(rank, world, uid_path, out_dir):
+    """BASELINE configs[4] in miniature: C_total candidates in candidate-chunks that are regenerated between passes
+    (score_begin / accumulate / finish), the record axis sharded over the ranks and joined once in finish."""
+    sys.path.insert(0, ROOT)
+    pkg = import_module("senweaver-ide_b200")
+    torch.cuda.set_device(rank)
+    eng = pkg.Engine(rank)
+    eng.comm_init(world, rank, open(uid_path, "rb").read())
+    Ct, Cc, Tg = 40, 8, 600_000
+    first, last = pkg.sharding.shard_range(Tg, world, rank)
+    eng.corpus_generate(SEED, first, last - first, 300)
+    eng.score_begin(Ct)
+    for c0 in range(0, Ct, Cc):
+        eng.dims_generate(SEED, c0, Cc, first, last - first, 300)
+        half = ((last - first) // 2) // 8 * 8
+        eng.score_accumulate(c0, count=half)                 # and each chunk in two record windows
+        eng.score_accumulate(c0, first=half)
+    res = eng.score_finish(Ct, 10, corpus=True)
+    res2 = eng.score_finish(Ct, 10, corpus=True)             # repeatable finish: a second join of the same partials
+    sums, counts = eng.debug_partials(Ct)
+    assert np.array_equal(res.scores, res2.scores) and np.array_equal(res.topk, res2.topk) and res.report.bad == res2.report.bad
+    np.savez(os.path.join(out_dir, f"c{rank}.npz"), scores=res.scores, topk=res.topk, sums=np.array([str(s) for s in sums]),
+             counts=np.array(counts), bad=np.array([res.report.bad]), pat=np.array([res.report.pat[p].count for p in range(6)]))
+    eng.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_config5_shape_chunked_sharded_session(tmp_path, engine, orc, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    pkg = import_module("senweaver-ide_b200")
+    uid_path = tmp_path / "uid.bin"
+    uid_path.write_bytes(pkg.Engine.comm_unique_id())
+    mp.spawn(chunked_worker, args=(world, str(uid_path), str(tmp_path)), nprocs=world, join=True)
+    Ct, Tg = 40, 600_000
+    engine.dims_generate(SEED, 0, Ct, 0, Tg, 300)
+    engine.corpus_generate(SEED, 0, Tg, 300)
+    ref = engine.score(Ct, 10, corpus=True)
+    rsums, rcounts = engine.debug_partials(Ct)
+    es, en = orc.score_generated_fx(SEED, [0, 17, 39], 0, Tg, 300, nthreads=8)    # and the single-GPU call against the oracle
+    assert [rsums[c] for c in (0, 17, 39)] == es and [rcounts[c] for c in (0, 17, 39)] == en
+    for r in range(world):
+        z = np.load(tmp_path / f"c{r}.npz")
+        assert [int(s) for s in z["sums"]] == rsums and list(z["counts"]) == rcounts
+        assert np.array_equal(z["scores"], ref.scores) and np.array_equal(z["topk"], ref.topk)
+        assert z["bad"][0] == ref.report.bad and list(z["pat"]) == [ref.report.pat[p].count for p in range(6)]

@@ -496,7 +496,7 @@ def test_incremental_scoring_session(engine, orc):
         assert np.array_equal(r.topk, orc.topk(orc.score_dims(dims[:, :hi])[0], 3))
 
 
-def test_fused_and_standalone_corpus_paths_agree(engine, orc, monkeypatch):
+def test_fused_and_standalone_corpus_paths_agree(engine, orc, apo):
     """The corpus scan rides inside the scoring kernel when it can hide behind it (large C*T), otherwise it is
     the stand-alone K2 launch; both must produce the identical report, for Form D, Form Q and Form R."""
     seed, C, T, Tc = 0x5EED000B, 24, 300_000, 40_000          # 24 x 300k x 36 B = 0.26 GB: fused (scan of 40k records hides)
@@ -512,9 +512,9 @@ def test_fused_and_standalone_corpus_paths_agree(engine, orc, monkeypatch):
             src = 0
         a = engine.score(C, 4, source=src, corpus=True)
         assert a.timing.launches == 1, layout                   # K1 + K2 + K3 in one launch
-        monkeypatch.setenv("APO_NO_FUSE", "1")
+        engine.set_tuning(apo.TUNE_NO_FUSE)
         b = engine.score(C, 4, source=src, corpus=True)
-        monkeypatch.delenv("APO_NO_FUSE")
+        engine.set_tuning(0)
         assert b.timing.launches == 2
         check_report(a.report, ref)
         check_report(b.report, ref)
@@ -617,7 +617,7 @@ def test_host_streaming_pageable_and_pinned_inputs_agree(engine, orc, apo):
     assert engine.debug_partials(3) == orc.score_records_fx(recs)
 
 
-def test_large_pageable_uploads_go_through_staging(engine, orc, monkeypatch):
+def test_large_pageable_uploads_go_through_staging(engine, orc, apo):
     """apo_dims_upload / apo_rollouts_upload / apo_corpus_upload of >= 64 MB pageable arrays are gathered through the pinned
     staging buffers in column slices (three slices for the 605 MB case); the resident bytes must be exactly the input."""
     C, T = 4, 4_200_001
@@ -627,10 +627,10 @@ def test_large_pageable_uploads_go_through_staging(engine, orc, monkeypatch):
         assert engine.dims_download(c, a, n).tobytes() == dims[c, a:a + n].tobytes()
     engine.score(C, 1)
     staged = engine.debug_partials(C)
-    monkeypatch.setenv("APO_NO_STAGING", "1")
+    engine.set_tuning(apo.TUNE_NO_STAGING)
     engine.dims_upload(dims)
     engine.score(C, 1)
-    monkeypatch.delenv("APO_NO_STAGING")
+    engine.set_tuning(0)
     assert engine.debug_partials(C) == staged == orc.score_dims_fx(dims)
     recs = orc.gen_records(0x5EED007A, orc.STREAM_ROLLOUT, 0, 3, 0, 700_001, 300, 8)          # 67 MB
     engine.rollouts_upload(recs)

@@ -131,7 +131,7 @@ def bind_to_gpu_numa_node(local: int) -> str:
 
 def host_cpu_budget() -> dict:
     """What the box really gives this process: affinity mask and the cgroup CPU quota (a quota below the mask
-    bounds every multi-threaded CPU number of this run)."""
+    bounds every multi-threaded CPU number of this run: the measurement pod grants 16 CPUs of its 128)."""
     out = {"affinity_cpus": len(os.sched_getaffinity(0))}
     try:
         q, p = open("/sys/fs/cgroup/cpu.max").read().split()
@@ -139,6 +139,16 @@ def host_cpu_budget() -> dict:
     except Exception:
         out["cgroup_cpu_max"] = "unknown"
     return out
+
+
+def usable_threads(affinity=None) -> int:
+    """Host threads worth starting: the affinity mask capped by the cgroup CPU quota (more threads than quota only
+    buys throttling: 128 threads under a 16-CPU quota ran 2x slower than 16)."""
+    n = len(affinity if affinity is not None else os.sched_getaffinity(0))
+    q = host_cpu_budget()["cgroup_cpu_max"]
+    if isinstance(q, float) and q >= 1:
+        n = min(n, int(q + 0.5))
+    return max(1, n)
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -162,7 +172,7 @@ class CpuArm:
         import oracle
         oracle.build()
         self.orc = oracle
-        self.threads = len(os.sched_getaffinity(0))
+        self.threads = usable_threads()
         self.C, self.T = cpu_sample_shape(C)
         t0 = time.perf_counter()
         self.dims = oracle.gen_dims(SEED, 0, self.C, 0, self.T, 300, self.threads)
@@ -335,7 +345,7 @@ def check_parity(H: Harness, eng, C: int, K: int, shards, last, layout_name: str
     if rank == 0:
         import oracle
         oracle.build()
-        nthreads = len(H.all_cpus)
+        nthreads = usable_threads(H.all_cpus)
         os.sched_setaffinity(0, H.all_cpus)
         exp_scores = sh.scores_from_partials(sums, counts)
         out["scores_from_exact_sums"] = bool(np.array_equal(exp_scores, last.scores))
@@ -360,8 +370,8 @@ def check_parity(H: Harness, eng, C: int, K: int, shards, last, layout_name: str
                     exact = False
             checked += len(part)
             el = time.perf_counter() - tB
-            if checked >= 8 and el * (checked + batch) / checked > budget_s:
-                break
+            if checked >= 8 and el * len(cl) / checked > 1.5 * budget_s and el * (checked + batch) / checked > budget_s:
+                break                                             # all C do not fit the budget (the boundary candidates came first)
             batch = min(64, batch * 2)
         out["full_axis_candidates_checked"] = checked
         out["full_axis_candidates_of"] = C
@@ -424,7 +434,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the weak-scaling, compact-layout and e2e legs")
-    ap.add_argument("--parity-budget", type=float, default=20.0, help="seconds of oracle time for the full-axis parity check")
+    ap.add_argument("--parity-budget", type=float, default=25.0, help="seconds of oracle time for the full-axis parity check")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -558,7 +568,7 @@ def main():
         if rank == 0:
             import oracle
             cl = sorted({0, Ce // 2, Ce - 1})
-            es, en = oracle.score_generated_fx(SEED, cl, t0e, Te, 300, nthreads=len(H.all_cpus))
+            es, en = oracle.score_generated_fx(SEED, cl, t0e, Te, 300, nthreads=usable_threads(H.all_cpus))
             e2e_ok = all(e2e_sums[0][c] == s_ and e2e_sums[1][c] == n_ for c, s_, n_ in zip(cl, es, en))
             e16_ok = True
             for c in cl[:2]:                                    # Form R16: dims are derived from the records (TCS:668-763) on both sides

@@ -1,26 +1,44 @@
 /*
- * apo_napi.c — thin N-API addon over the C ABI of include/apo_b200.h.
+ * apo_napi.c — N-API addon over the C ABI of include/apo_b200.h (marshalling only; the job structs, their
+ * validation and the per-handle FIFO live in apo_jobs.c so that they are testable without Node).
  *
- * Loaded by the IDE's *main process* (the renderer cannot load native modules:
- * eslint.config.js:94 — `common` imports nothing platform specific), behind a named IPC
- * channel exactly like the reference's metrics service
+ * Loaded by the IDE's *main process* (the renderer cannot load native modules: eslint.config.js:94 — `common`
+ * imports nothing platform specific), behind a named IPC channel exactly like the reference's metrics service
  * (common/metricsService.ts:25-50 + electron-main/metricsMainService.ts:35, registered in
- * src/vs/code/electron-main/app.ts:1124,1259-1260).  See INTEGRATION.md.
+ * src/vs/code/electron-main/app.ts:1124,1259-1260).  See INTEGRATION.md and ts/.
  *
- * N-API is a stable C ABI (Electron 34 -> Node 20.18 -> N-API v9).  node_api.h is not
- * present in this build image, so the handful of prototypes used are declared below when the
- * real header is absent; `gcc -fsyntax-only -I../include apo_napi.c` is the check run here,
- * the real build is `node-gyp` / `cmake-js` with the genuine header.
+ * Rules every exported function follows:
+ *   - never throws: failures come back as null (create) or a rejected Promise whose Error carries the library's
+ *     message (reference convention TCS:438, APO:1211-1214);
+ *   - everything that touches the GPU is async work on the libuv pool resolving a Promise ("anything transmitted
+ *     over a channel must be async", metricsService.ts:47): the Electron main loop never blocks, not even for the
+ *     ~15 us single-trace call;
+ *   - one in-flight call per handle: jobs of a handle run strictly in submission order (ticket FIFO, apo_jobs.h);
+ *   - ownership: every ArrayBuffer a job reads and the handle itself stay napi_ref'd until the job completed, so
+ *     neither the data nor the engine can be collected under a running job; nothing is retained afterwards;
+ *   - every shape that arrives over IPC (C, T, K, rowBytes, byte lengths) is validated against the real buffer
+ *     lengths with overflow-safe arithmetic before a pointer is dereferenced (apo_job_validate).
  *
- * Heavy calls (score) run on the libuv pool via napi_create_async_work and resolve a
- * Promise: "anything transmitted over a channel must be async" (metricsService.ts:47), and
- * the Electron main loop must never block.  Typed arrays cross the IPC channel as raw bytes
- * (base/parts/ipc/common/ipc.ts:274-283).
+ * JS surface:
+ *   create(device) -> handle | null        lastCreateError() -> string
+ *   dimsUpload(h, dims:ArrayBuffer f32[C][T][9], C, T, compact:boolean)      -> Promise<void>     uploaded once ...
+ *   rolloutsUpload(h, recs:ArrayBuffer, rowBytes 32|16, C, T)               -> Promise<void>
+ *   corpusUpload(h, recs:ArrayBuffer apo_record[T], idxBase)                -> Promise<void>
+ *   corpusUploadJson(h, utf8:ArrayBuffer, idxBase)                          -> Promise<number>   (records)
+ *   scoreResident(h, {C, K, source, corpus, first, count})                  -> Promise<blocks>   ... scored many times
+ *   score(h, dims, C, T, corpus|null, K)                                    -> Promise<blocks>   host streaming, Form D
+ *   scoreHostRecords(h, recs, rowBytes, C, T, corpus|null, K)               -> Promise<blocks>   host streaming, trace records
+ *   rewardBatch(h, recs:ArrayBuffer apo_record[n])                          -> Promise<{dims,masks,finals}>
+ *   commUniqueId() -> ArrayBuffer(128) | null     commInit(h, nranks, rank, id) -> Promise<void>
+ *   recordsFromJson(utf8) -> ArrayBuffer | null   allocPinned(bytes) -> ArrayBuffer | null      (host-only helpers)
+ *   blocks = {scores:ArrayBuffer f64[C], counts:ArrayBuffer u64[C], topk:ArrayBuffer i32[K], report:ArrayBuffer}
  */
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "apo_b200.h"
+#include "apo_jobs.h"
 
 #if defined(__has_include)
 #if __has_include(<node_api.h>)
@@ -29,183 +47,383 @@
 #endif
 #endif
 #ifndef APO_HAVE_NODE_API
-/* ---- minimal N-API v9 declarations (subset used here) ---- */
-typedef struct napi_env__ *napi_env;
-typedef struct napi_value__ *napi_value;
-typedef struct napi_callback_info__ *napi_callback_info;
-typedef struct napi_deferred__ *napi_deferred;
-typedef struct napi_async_work__ *napi_async_work;
-typedef struct napi_ref__ *napi_ref;
-typedef enum { napi_ok = 0 } napi_status;
-typedef napi_value (*napi_callback)(napi_env, napi_callback_info);
-typedef void (*napi_finalize)(napi_env, void *, void *);
-typedef void (*napi_async_execute_callback)(napi_env, void *);
-typedef void (*napi_async_complete_callback)(napi_env, napi_status, void *);
-typedef enum { napi_default = 0 } napi_property_attributes;
-typedef struct { const char *utf8name; napi_value name; napi_callback method, getter, setter; napi_value value;
-                 napi_property_attributes attributes; void *data; } napi_property_descriptor;
-napi_status napi_get_cb_info(napi_env, napi_callback_info, size_t *, napi_value *, napi_value *, void **);
-napi_status napi_get_value_int32(napi_env, napi_value, int32_t *);
-napi_status napi_get_value_uint32(napi_env, napi_value, uint32_t *);
-napi_status napi_get_value_double(napi_env, napi_value, double *);
-napi_status napi_get_arraybuffer_info(napi_env, napi_value, void **, size_t *);
-napi_status napi_create_arraybuffer(napi_env, size_t, void **, napi_value *);
-napi_status napi_create_external_arraybuffer(napi_env, void *, size_t, napi_finalize, void *, napi_value *);
-napi_status napi_create_object(napi_env, napi_value *);
-napi_status napi_create_double(napi_env, double, napi_value *);
-napi_status napi_create_int32(napi_env, int32_t, napi_value *);
-napi_status napi_create_string_utf8(napi_env, const char *, size_t, napi_value *);
-napi_status napi_set_named_property(napi_env, napi_value, const char *, napi_value);
-napi_status napi_create_external(napi_env, void *, napi_finalize, void *, napi_value *);
-napi_status napi_get_value_external(napi_env, napi_value, void **);
-napi_status napi_create_promise(napi_env, napi_deferred *, napi_value *);
-napi_status napi_resolve_deferred(napi_env, napi_deferred, napi_value);
-napi_status napi_reject_deferred(napi_env, napi_deferred, napi_value);
-napi_status napi_create_async_work(napi_env, napi_value, napi_value, napi_async_execute_callback,
-                                   napi_async_complete_callback, void *, napi_async_work *);
-napi_status napi_queue_async_work(napi_env, napi_async_work);
-napi_status napi_delete_async_work(napi_env, napi_async_work);
-napi_status napi_create_reference(napi_env, napi_value, uint32_t, napi_ref *);
-napi_status napi_delete_reference(napi_env, napi_ref);
-napi_status napi_define_properties(napi_env, napi_value, size_t, const napi_property_descriptor *);
-napi_status napi_create_error(napi_env, napi_value, napi_value, napi_value *);
-napi_status napi_throw_error(napi_env, const char *, const char *);
-#define NAPI_AUTO_LENGTH ((size_t)-1)
-#define NAPI_MODULE_INIT() napi_value napi_register_module_v1(napi_env env, napi_value exports)
+#include "node_api_stub.h"
 #endif
 
-static void engine_finalize(napi_env env, void *data, void *hint) { (void)env; (void)hint; apo_destroy((apo_engine *)data); }
+static char g_create_error[256];
 
-static apo_engine *get_engine(napi_env env, napi_value v) { void *p = NULL; napi_get_value_external(env, v, &p); return (apo_engine *)p; }
+/* ------------------------------------------------------------------------------------------ helpers */
+static void serial_finalize(napi_env env, void *data, void *hint) { (void)env; (void)hint; apo_serial_destroy((apo_serial *)data); }
 
-/* create(device:number) -> external handle */
-static napi_value Create(napi_env env, napi_callback_info info) {
-	size_t argc = 1; napi_value argv[1]; int32_t dev = 0;
-	napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
-	if (argc > 0) napi_get_value_int32(env, argv[0], &dev);
-	apo_engine *e = NULL;
-	if (apo_create(dev, &e) != APO_OK) { napi_throw_error(env, "APO_E_CUDA", apo_last_error(NULL)); return NULL; }
-	napi_value out; napi_create_external(env, e, engine_finalize, NULL, &out);
-	return out;
+static apo_serial *get_serial(napi_env env, napi_value v)
+{
+	napi_valuetype t;
+	void *p = NULL;
+	if (napi_typeof(env, v, &t) != napi_ok || t != napi_external) return NULL;
+	if (napi_get_value_external(env, v, &p) != napi_ok) return NULL;
+	return (apo_serial *)p;
 }
 
-/* rewardBatch(handle, records:ArrayBuffer) -> {dims:ArrayBuffer(f64 n*9), masks:ArrayBuffer(u32 n), finals:ArrayBuffer(f64 n)}
- * = TraceCollectorService._computeRewardSignals for n traces (TCS:668-788). Small and latency bound: synchronous. */
-static napi_value RewardBatch(napi_env env, napi_callback_info info) {
-	size_t argc = 2; napi_value argv[2];
-	napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
-	apo_engine *e = get_engine(env, argv[0]);
-	void *recs; size_t bytes; napi_get_arraybuffer_info(env, argv[1], &recs, &bytes);
-	const uint64_t n = bytes / sizeof(apo_record);
-	void *dims, *masks, *finals; napi_value vd, vm, vf, out;
-	napi_create_arraybuffer(env, n * APO_NDIM * 8, &dims, &vd);
-	napi_create_arraybuffer(env, n * 4, &masks, &vm);
-	napi_create_arraybuffer(env, n * 8, &finals, &vf);
-	if (apo_reward_batch(e, (const apo_record *)recs, n, (double *)dims, (uint32_t *)masks, (double *)finals) != APO_OK) {
-		napi_throw_error(env, "APO", apo_last_error(e)); return NULL;
-	}
-	napi_create_object(env, &out);
-	napi_set_named_property(env, out, "dims", vd); napi_set_named_property(env, out, "masks", vm); napi_set_named_property(env, out, "finals", vf);
-	return out;
+static int get_buffer(napi_env env, napi_value v, const void **p, uint64_t *bytes)
+{
+	bool is = false;
+	void *data = NULL; size_t n = 0;
+	if (napi_is_arraybuffer(env, v, &is) != napi_ok || !is) return 0;
+	if (napi_get_arraybuffer_info(env, v, &data, &n) != napi_ok) return 0;
+	*p = data; *bytes = (uint64_t)n;
+	return 1;
 }
 
-/* allocPinned(bytes:number) -> ArrayBuffer over page-locked memory (apo_host_alloc).  Typed arrays built on it
- * (the dims / record buffers handed to score) are read in place by the streaming calls at PCIe line rate; ordinary
- * ArrayBuffers work too, through the library's staging path, at about half that. */
-static void pinned_finalize(napi_env env, void *data, void *hint) { (void)env; (void)hint; apo_host_free(data); }
-
-static napi_value AllocPinned(napi_env env, napi_callback_info info) {
-	size_t argc = 1; napi_value argv[1], out; double bytes = 0; void *p = NULL;
-	napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
-	napi_get_value_double(env, argv[0], &bytes);
-	if (bytes < 0 || apo_host_alloc((uint64_t)bytes, &p) != APO_OK) { napi_throw_error(env, "APO_E_NOMEM", apo_last_error(NULL)); return NULL; }
-	napi_create_external_arraybuffer(env, p, (size_t)bytes, pinned_finalize, NULL, &out);
-	return out;
+static int get_u32(napi_env env, napi_value v, uint32_t *out)
+{
+	napi_valuetype t; double d = 0;
+	if (napi_typeof(env, v, &t) != napi_ok || t != napi_number) return 0;
+	if (napi_get_value_double(env, v, &d) != napi_ok || !(d >= 0) || d > 4294967295.0 || d != (double)(uint32_t)d) return 0;
+	*out = (uint32_t)d;
+	return 1;
 }
 
-/* recordsFromJson(utf8:ArrayBuffer) -> ArrayBuffer of apo_record[T]
- * utf8 = the string stored under 'senweaver.traceCollector.data' (TCS:296-359), encoded with TextEncoder.
- * Host-side format code (apo_records_from_json); linear in the input, no GPU work. */
-static napi_value RecordsFromJson(napi_env env, napi_callback_info info) {
-	size_t argc = 1; napi_value argv[1], out;
-	napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
-	void *text; size_t bytes; uint64_t pos = 0;
-	napi_get_arraybuffer_info(env, argv[0], &text, &bytes);
-	int64_t n = apo_records_from_json((const char *)text, bytes, NULL, 0, &pos);
-	if (n < 0) { napi_throw_error(env, "APO_E_ARG", "malformed trace JSON"); return NULL; }
-	void *recs;
-	napi_create_arraybuffer(env, (size_t)n * sizeof(apo_record), &recs, &out);
-	apo_records_from_json((const char *)text, bytes, (apo_record *)recs, (uint64_t)n, &pos);
-	return out;
+static int get_u64(napi_env env, napi_value v, uint64_t *out)        /* JS numbers: exact integers up to 2^53 */
+{
+	napi_valuetype t; double d = 0;
+	if (napi_typeof(env, v, &t) != napi_ok || t != napi_number) return 0;
+	if (napi_get_value_double(env, v, &d) != napi_ok || !(d >= 0) || d > 9007199254740992.0 || d != (double)(uint64_t)d) return 0;
+	*out = (uint64_t)d;
+	return 1;
 }
 
-/* ---- score(handle, {dims:ArrayBuffer, C, T, corpus:ArrayBuffer|null, K}) -> Promise<{scores,counts,topk,report}> ---- */
+static int is_nullish(napi_env env, napi_value v)
+{
+	napi_valuetype t;
+	return napi_typeof(env, v, &t) != napi_ok || t == napi_null || t == napi_undefined;
+}
+
+static napi_value copy_out(napi_env env, const void *src, size_t bytes)
+{
+	void *p = NULL; napi_value v = NULL;
+	if (napi_create_arraybuffer(env, bytes, &p, &v) != napi_ok) return NULL;
+	if (bytes) memcpy(p, src, bytes);
+	return v;
+}
+
+/* ------------------------------------------------------------------------------------------ async plumbing */
 typedef struct {
-	apo_engine *e; napi_deferred deferred; napi_async_work work; napi_ref keep_dims, keep_corpus;
-	const float *dims; const apo_record *corpus; uint32_t C, K; uint64_t T, Tc;
-	double *scores; uint64_t *counts; int32_t *topk; apo_corpus_report report; int rc;
-} score_job;
+	apo_serial *s;
+	apo_job job;
+	napi_deferred deferred;
+	napi_async_work work;
+	napi_ref keep[3];            /* handle, data buffer, corpus buffer */
+	int nkeep;
+} call_t;
 
-static void score_execute(napi_env env, void *data) {
+static void call_execute(napi_env env, void *data)
+{
 	(void)env;
-	score_job *j = (score_job *)data;
-	apo_score_opts o; memset(&o, 0, sizeof o);
-	o.K = j->K; o.source = APO_SRC_DIMS; o.flags = j->corpus ? APO_SCORE_CORPUS : 0;
-	j->rc = APO_OK;
-	if (j->corpus) j->rc = apo_corpus_upload(j->e, j->corpus, j->Tc, 0);
-	if (j->rc == APO_OK) j->rc = apo_score_host(j->e, &o, j->dims, j->C, j->T, j->scores, j->counts, j->topk, &j->report);
+	call_t *c = (call_t *)data;
+	apo_job_run(c->s, &c->job);                     /* waits for its turn on the handle (FIFO), then runs */
 }
 
-static void score_complete(napi_env env, napi_status st, void *data) {
+static napi_value blocks_of(napi_env env, const apo_job *j)
+{
+	napi_value out = NULL, v;
+	const uint32_t C = j->C, K = j->K < j->C ? j->K : j->C;
+	napi_create_object(env, &out);
+	if ((v = copy_out(env, j->scores, 8u * (size_t)C))) napi_set_named_property(env, out, "scores", v);
+	if ((v = copy_out(env, j->counts, 8u * (size_t)C))) napi_set_named_property(env, out, "counts", v);
+	if ((v = copy_out(env, j->topk, 4u * (size_t)K))) napi_set_named_property(env, out, "topk", v);
+	if ((v = copy_out(env, &j->report, sizeof j->report))) napi_set_named_property(env, out, "report", v);
+	return out;
+}
+
+static void call_complete(napi_env env, napi_status st, void *data)
+{
 	(void)st;
-	score_job *j = (score_job *)data;
+	call_t *c = (call_t *)data;
+	apo_job *j = &c->job;
 	if (j->rc != APO_OK) {
-		napi_value msg, err; napi_create_string_utf8(env, apo_last_error(j->e), NAPI_AUTO_LENGTH, &msg);
-		napi_create_error(env, NULL, msg, &err); napi_reject_deferred(env, j->deferred, err);
+		napi_value msg, err;
+		napi_create_string_utf8(env, j->err[0] ? j->err : "apo_b200 call failed", NAPI_AUTO_LENGTH, &msg);
+		napi_create_error(env, NULL, msg, &err);
+		napi_reject_deferred(env, c->deferred, err);
 	} else {
-		napi_value out, v; void *p;
-		napi_create_object(env, &out);
-		napi_create_arraybuffer(env, 8u * j->C, &p, &v); memcpy(p, j->scores, 8u * j->C); napi_set_named_property(env, out, "scores", v);
-		napi_create_arraybuffer(env, 8u * j->C, &p, &v); memcpy(p, j->counts, 8u * j->C); napi_set_named_property(env, out, "counts", v);
-		napi_create_arraybuffer(env, 4u * j->K, &p, &v); memcpy(p, j->topk, 4u * j->K); napi_set_named_property(env, out, "topk", v);
-		napi_create_arraybuffer(env, sizeof j->report, &p, &v); memcpy(p, &j->report, sizeof j->report); napi_set_named_property(env, out, "report", v);
-		napi_resolve_deferred(env, j->deferred, out);
+		napi_value out = NULL, v;
+		switch (j->kind) {
+		case APO_JOB_SCORE_RESIDENT: case APO_JOB_SCORE_HOST: case APO_JOB_SCORE_HOST_RECORDS:
+			out = blocks_of(env, j);
+			break;
+		case APO_JOB_REWARD_BATCH:
+			napi_create_object(env, &out);
+			if ((v = copy_out(env, j->dims_out, 8u * APO_NDIM * (size_t)j->n_out))) napi_set_named_property(env, out, "dims", v);
+			if ((v = copy_out(env, j->masks_out, 4u * (size_t)j->n_out))) napi_set_named_property(env, out, "masks", v);
+			if ((v = copy_out(env, j->finals_out, 8u * (size_t)j->n_out))) napi_set_named_property(env, out, "finals", v);
+			break;
+		case APO_JOB_CORPUS_UPLOAD_JSON:
+			napi_create_double(env, (double)j->n_out, &out);
+			break;
+		default:
+			napi_get_null(env, &out);
+		}
+		napi_resolve_deferred(env, c->deferred, out);
 	}
-	napi_delete_reference(env, j->keep_dims);
-	if (j->keep_corpus) napi_delete_reference(env, j->keep_corpus);
-	napi_delete_async_work(env, j->work);
-	free(j->scores); free(j->counts); free(j->topk); free(j);
+	for (int i = 0; i < c->nkeep; i++) napi_delete_reference(env, c->keep[i]);
+	napi_delete_async_work(env, c->work);
+	apo_job_release(j);
+	free(c);
 }
 
-static napi_value Score(napi_env env, napi_callback_info info) {
-	size_t argc = 6; napi_value argv[6], promise, name;
-	napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
-	score_job *j = (score_job *)calloc(1, sizeof *j);
-	j->e = get_engine(env, argv[0]);
-	void *p; size_t bytes; double Td = 0;
-	napi_get_arraybuffer_info(env, argv[1], &p, &bytes); j->dims = (const float *)p;
-	napi_get_value_uint32(env, argv[2], &j->C);
-	napi_get_value_double(env, argv[3], &Td); j->T = (uint64_t)Td;
-	if (argc > 4 && napi_get_arraybuffer_info(env, argv[4], &p, &bytes) == napi_ok && bytes) { j->corpus = (const apo_record *)p; j->Tc = bytes / sizeof(apo_record); }
-	napi_get_value_uint32(env, argv[5], &j->K);
-	j->scores = (double *)malloc(8u * (j->C ? j->C : 1)); j->counts = (uint64_t *)malloc(8u * (j->C ? j->C : 1)); j->topk = (int32_t *)malloc(4u * (j->K ? j->K : 1));
-	/* the ArrayBuffers stay referenced until the worker is done (ownership rule of INTEGRATION.md) */
-	napi_create_reference(env, argv[1], 1, &j->keep_dims);
-	if (j->corpus) napi_create_reference(env, argv[4], 1, &j->keep_corpus);
-	napi_create_promise(env, &j->deferred, &promise);
-	napi_create_string_utf8(env, "apo_score", NAPI_AUTO_LENGTH, &name);
-	napi_create_async_work(env, NULL, name, score_execute, score_complete, j, &j->work);
-	napi_queue_async_work(env, j->work);
+/* Validates, takes the handle's ticket and queues the job.  A job that fails validation is still queued (it rejects in
+ * its turn): tickets stay dense and the Promise order seen by JS matches the submission order. */
+static napi_value submit(napi_env env, call_t *c, napi_value handle, napi_value buf, napi_value corpus, const char *name)
+{
+	napi_value promise = NULL, rname;
+	napi_create_promise(env, &c->deferred, &promise);
+	if (apo_job_validate(&c->job) == APO_OK) apo_job_prepare(&c->job);
+	c->job.ticket = apo_serial_ticket(c->s);
+	napi_create_reference(env, handle, 1, &c->keep[c->nkeep++]);            /* the engine cannot be finalized under the job */
+	if (buf) napi_create_reference(env, buf, 1, &c->keep[c->nkeep++]);
+	if (corpus) napi_create_reference(env, corpus, 1, &c->keep[c->nkeep++]);
+	napi_create_string_utf8(env, name, NAPI_AUTO_LENGTH, &rname);
+	napi_create_async_work(env, NULL, rname, call_execute, call_complete, c, &c->work);
+	napi_queue_async_work(env, c->work);
 	return promise;
 }
 
-NAPI_MODULE_INIT() {
+/* a Promise rejected on the spot: the handle itself is unusable, so there is no FIFO to take a turn in */
+static napi_value reject_now(napi_env env, const char *why)
+{
+	napi_deferred d; napi_value promise = NULL, msg, err;
+	napi_create_promise(env, &d, &promise);
+	napi_create_string_utf8(env, why, NAPI_AUTO_LENGTH, &msg);
+	napi_create_error(env, NULL, msg, &err);
+	napi_reject_deferred(env, d, err);
+	return promise;
+}
+
+static call_t *new_call(napi_env env, napi_value handle, apo_job_kind kind)
+{
+	apo_serial *s = get_serial(env, handle);
+	if (!s) return NULL;
+	call_t *c = (call_t *)calloc(1, sizeof *c);
+	if (!c) return NULL;
+	c->s = s; c->job.kind = kind;
+	return c;
+}
+
+static void arg_error(call_t *c, const char *msg) { c->job.rc = APO_E_ARG; snprintf(c->job.err, sizeof c->job.err, "%s", msg); }
+
+#define ARGS(n)                                                    \
+	size_t argc = (n); napi_value argv[(n)];                       \
+	for (size_t i_ = 0; i_ < (n); i_++) argv[i_] = NULL;           \
+	napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+
+/* ------------------------------------------------------------------------------------------ exported functions */
+/* create(device:number) -> external handle, or null (lastCreateError() tells why): never throws */
+static napi_value Create(napi_env env, napi_callback_info info)
+{
+	ARGS(1)
+	int32_t dev = 0;
+	napi_value out = NULL;
+	if (argc > 0 && argv[0]) napi_get_value_int32(env, argv[0], &dev);
+	apo_serial *s = apo_serial_create(dev, g_create_error, sizeof g_create_error);
+	if (!s) { napi_get_null(env, &out); return out; }
+	if (napi_create_external(env, s, serial_finalize, NULL, &out) != napi_ok) { apo_serial_destroy(s); napi_get_null(env, &out); }
+	return out;
+}
+
+static napi_value LastCreateError(napi_env env, napi_callback_info info)
+{
+	(void)info;
+	napi_value out = NULL;
+	napi_create_string_utf8(env, g_create_error, NAPI_AUTO_LENGTH, &out);
+	return out;
+}
+
+/* dimsUpload(h, dims, C, T, compact) */
+static napi_value DimsUpload(napi_env env, napi_callback_info info)
+{
+	ARGS(5)
+	call_t *c = argc >= 1 ? new_call(env, argv[0], APO_JOB_DIMS_UPLOAD) : NULL;
+	if (!c) return reject_now(env, "dimsUpload: invalid handle");
+	bool compact = false;
+	if (argc < 4 || !get_buffer(env, argv[1], &c->job.buf, &c->job.buf_bytes) || !get_u32(env, argv[2], &c->job.C) || !get_u64(env, argv[3], &c->job.T))
+		arg_error(c, "dimsUpload(handle, dims:ArrayBuffer, C:uint32, T:uint53, compact?:boolean)");
+	if (argc >= 5 && argv[4] && !is_nullish(env, argv[4])) napi_get_value_bool(env, argv[4], &compact);
+	c->job.compact = compact ? 1 : 0;
+	return submit(env, c, argv[0], c->job.buf ? argv[1] : NULL, NULL, "apo_dims_upload");
+}
+
+/* rolloutsUpload(h, recs, rowBytes, C, T) */
+static napi_value RolloutsUpload(napi_env env, napi_callback_info info)
+{
+	ARGS(5)
+	call_t *c = argc >= 1 ? new_call(env, argv[0], APO_JOB_ROLLOUTS_UPLOAD) : NULL;
+	if (!c) return reject_now(env, "rolloutsUpload: invalid handle");
+	if (argc < 5 || !get_buffer(env, argv[1], &c->job.buf, &c->job.buf_bytes) || !get_u32(env, argv[2], &c->job.row_bytes) ||
+	    !get_u32(env, argv[3], &c->job.C) || !get_u64(env, argv[4], &c->job.T))
+		arg_error(c, "rolloutsUpload(handle, recs:ArrayBuffer, rowBytes:32|16, C:uint32, T:uint53)");
+	return submit(env, c, argv[0], c->job.buf ? argv[1] : NULL, NULL, "apo_rollouts_upload");
+}
+
+/* corpusUpload(h, recs, idxBase) */
+static napi_value CorpusUpload(napi_env env, napi_callback_info info)
+{
+	ARGS(3)
+	call_t *c = argc >= 1 ? new_call(env, argv[0], APO_JOB_CORPUS_UPLOAD) : NULL;
+	if (!c) return reject_now(env, "corpusUpload: invalid handle");
+	if (argc < 2 || !get_buffer(env, argv[1], &c->job.buf, &c->job.buf_bytes)) arg_error(c, "corpusUpload(handle, recs:ArrayBuffer, idxBase?:uint53)");
+	if (argc >= 3 && argv[2] && !is_nullish(env, argv[2]) && !get_u64(env, argv[2], &c->job.idx_base)) arg_error(c, "corpusUpload: idxBase must be a non-negative integer");
+	return submit(env, c, argv[0], c->job.buf ? argv[1] : NULL, NULL, "apo_corpus_upload");
+}
+
+/* corpusUploadJson(h, utf8, idxBase) -> Promise<number of records> */
+static napi_value CorpusUploadJson(napi_env env, napi_callback_info info)
+{
+	ARGS(3)
+	call_t *c = argc >= 1 ? new_call(env, argv[0], APO_JOB_CORPUS_UPLOAD_JSON) : NULL;
+	if (!c) return reject_now(env, "corpusUploadJson: invalid handle");
+	if (argc < 2 || !get_buffer(env, argv[1], &c->job.buf, &c->job.buf_bytes)) arg_error(c, "corpusUploadJson(handle, utf8:ArrayBuffer, idxBase?:uint53)");
+	if (argc >= 3 && argv[2] && !is_nullish(env, argv[2]) && !get_u64(env, argv[2], &c->job.idx_base)) arg_error(c, "corpusUploadJson: idxBase must be a non-negative integer");
+	return submit(env, c, argv[0], c->job.buf ? argv[1] : NULL, NULL, "apo_corpus_upload_json");
+}
+
+static int opt_u32(napi_env env, napi_value obj, const char *key, uint32_t *out)
+{
+	bool has = false; napi_value v;
+	if (napi_has_named_property(env, obj, key, &has) != napi_ok || !has) return 1;
+	if (napi_get_named_property(env, obj, key, &v) != napi_ok || is_nullish(env, v)) return 1;
+	return get_u32(env, v, out);
+}
+static int opt_u64(napi_env env, napi_value obj, const char *key, uint64_t *out)
+{
+	bool has = false; napi_value v;
+	if (napi_has_named_property(env, obj, key, &has) != napi_ok || !has) return 1;
+	if (napi_get_named_property(env, obj, key, &v) != napi_ok || is_nullish(env, v)) return 1;
+	return get_u64(env, v, out);
+}
+
+/* scoreResident(h, {C, K, source?, corpus?, first?, count?}): scores what dimsUpload / rolloutsUpload / corpusUpload left
+ * resident — "uploaded once, scored many times" (SURVEY 8b ownership row); nothing crosses PCIe but the result block. */
+static napi_value ScoreResident(napi_env env, napi_callback_info info)
+{
+	ARGS(2)
+	call_t *c = argc >= 1 ? new_call(env, argv[0], APO_JOB_SCORE_RESIDENT) : NULL;
+	if (!c) return reject_now(env, "scoreResident: invalid handle");
+	napi_valuetype t;
+	uint32_t corpus = 0;
+	if (argc < 2 || napi_typeof(env, argv[1], &t) != napi_ok || t != napi_object ||
+	    !opt_u32(env, argv[1], "C", &c->job.C) || !opt_u32(env, argv[1], "K", &c->job.K) || !opt_u32(env, argv[1], "source", &c->job.source) ||
+	    !opt_u32(env, argv[1], "corpus", &corpus) || !opt_u64(env, argv[1], "first", &c->job.first) || !opt_u64(env, argv[1], "count", &c->job.count))
+		arg_error(c, "scoreResident(handle, {C:uint32, K:uint32, source?:0|1, corpus?:0|1, first?:uint53, count?:uint53})");
+	if (c->job.C == 0) arg_error(c, "scoreResident: C (the number of uploaded candidates) is required");
+	if (c->job.K > c->job.C) arg_error(c, "scoreResident: K exceeds C");
+	c->job.flags = corpus ? APO_SCORE_CORPUS : 0;
+	return submit(env, c, argv[0], NULL, NULL, "apo_score");
+}
+
+static napi_value score_host_common(napi_env env, napi_callback_info info, apo_job_kind kind)
+{
+	const int rec = kind == APO_JOB_SCORE_HOST_RECORDS;
+	ARGS(7)
+	call_t *c = argc >= 1 ? new_call(env, argv[0], kind) : NULL;
+	if (!c) return reject_now(env, "score: invalid handle");
+	const size_t base = rec ? 3 : 2;              /* index of C */
+	const size_t need = base + 4;                 /* ..., C, T, corpus, K */
+	int ok = argc >= need && get_buffer(env, argv[1], &c->job.buf, &c->job.buf_bytes);
+	if (ok && rec) ok = get_u32(env, argv[2], &c->job.row_bytes);
+	if (ok) ok = get_u32(env, argv[base], &c->job.C) && get_u64(env, argv[base + 1], &c->job.T) && get_u32(env, argv[base + 3], &c->job.K);
+	napi_value corpus = NULL;
+	if (ok && !is_nullish(env, argv[base + 2])) {
+		ok = get_buffer(env, argv[base + 2], &c->job.corpus, &c->job.corpus_bytes);
+		corpus = ok ? argv[base + 2] : NULL;
+	}
+	if (!ok) arg_error(c, rec ? "scoreHostRecords(handle, recs:ArrayBuffer, rowBytes:32|16, C:uint32, T:uint53, corpus:ArrayBuffer|null, K:uint32)"
+	                          : "score(handle, dims:ArrayBuffer, C:uint32, T:uint53, corpus:ArrayBuffer|null, K:uint32)");
+	return submit(env, c, argv[0], c->job.buf ? argv[1] : NULL, corpus, rec ? "apo_score_host_records" : "apo_score_host");
+}
+static napi_value Score(napi_env env, napi_callback_info info) { return score_host_common(env, info, APO_JOB_SCORE_HOST); }
+static napi_value ScoreHostRecords(napi_env env, napi_callback_info info) { return score_host_common(env, info, APO_JOB_SCORE_HOST_RECORDS); }
+
+/* rewardBatch(h, recs) -> Promise<{dims, masks, finals}> = TraceCollectorService._computeRewardSignals for n traces
+ * (TCS:668-788).  Async like everything else; the TS service micro-batches the single-trace calls of one tick. */
+static napi_value RewardBatch(napi_env env, napi_callback_info info)
+{
+	ARGS(2)
+	call_t *c = argc >= 1 ? new_call(env, argv[0], APO_JOB_REWARD_BATCH) : NULL;
+	if (!c) return reject_now(env, "rewardBatch: invalid handle");
+	if (argc < 2 || !get_buffer(env, argv[1], &c->job.buf, &c->job.buf_bytes)) arg_error(c, "rewardBatch(handle, records:ArrayBuffer)");
+	return submit(env, c, argv[0], c->job.buf ? argv[1] : NULL, NULL, "apo_reward_batch");
+}
+
+/* commUniqueId() -> ArrayBuffer(128) | null;  commInit(h, nranks, rank, id) -> Promise<void> */
+static napi_value CommUniqueId(napi_env env, napi_callback_info info)
+{
+	(void)info;
+	uint8_t id[APO_UNIQUE_ID_BYTES];
+	napi_value out = NULL;
+	if (apo_comm_unique_id(id) != APO_OK) { napi_get_null(env, &out); return out; }
+	out = copy_out(env, id, sizeof id);
+	if (!out) napi_get_null(env, &out);
+	return out;
+}
+
+static napi_value CommInit(napi_env env, napi_callback_info info)
+{
+	ARGS(4)
+	call_t *c = argc >= 1 ? new_call(env, argv[0], APO_JOB_COMM_INIT) : NULL;
+	if (!c) return reject_now(env, "commInit: invalid handle");
+	const void *id = NULL; uint64_t idb = 0; int32_t nr = 0, rk = 0;
+	if (argc < 4 || napi_get_value_int32(env, argv[1], &nr) != napi_ok || napi_get_value_int32(env, argv[2], &rk) != napi_ok ||
+	    !get_buffer(env, argv[3], &id, &idb) || idb != APO_UNIQUE_ID_BYTES)
+		arg_error(c, "commInit(handle, nranks:int, rank:int, id:ArrayBuffer(128))");
+	else { c->job.nranks = nr; c->job.rank = rk; memcpy(c->job.comm_id, id, APO_UNIQUE_ID_BYTES); }
+	return submit(env, c, argv[0], NULL, NULL, "apo_comm_init");
+}
+
+/* allocPinned(bytes) -> ArrayBuffer over page-locked memory (apo_host_alloc) | null.  Typed arrays built on it are read in
+ * place by the streaming calls at PCIe line rate; ordinary ArrayBuffers work too (threaded pinned staging, about half). */
+static void pinned_finalize(napi_env env, void *data, void *hint) { (void)env; (void)hint; apo_host_free(data); }
+
+static napi_value AllocPinned(napi_env env, napi_callback_info info)
+{
+	ARGS(1)
+	napi_value out = NULL; uint64_t bytes = 0; void *p = NULL;
+	if (argc < 1 || !get_u64(env, argv[0], &bytes) || apo_host_alloc(bytes, &p) != APO_OK) { napi_get_null(env, &out); return out; }
+	if (napi_create_external_arraybuffer(env, p, (size_t)bytes, pinned_finalize, NULL, &out) != napi_ok) { apo_host_free(p); napi_get_null(env, &out); }
+	return out;
+}
+
+/* recordsFromJson(utf8:ArrayBuffer) -> ArrayBuffer of apo_record[T] | null (malformed).  utf8 = the string stored under
+ * 'senweaver.traceCollector.data' (TCS:296-359).  Host-side format code, linear in the input, no GPU work. */
+static napi_value RecordsFromJson(napi_env env, napi_callback_info info)
+{
+	ARGS(1)
+	napi_value out = NULL;
+	const void *text = NULL; uint64_t bytes = 0, pos = 0;
+	if (argc < 1 || !get_buffer(env, argv[0], &text, &bytes)) { napi_get_null(env, &out); return out; }
+	const int64_t n = apo_records_from_json((const char *)text, bytes, NULL, 0, &pos);
+	void *recs = NULL;
+	if (n < 0 || napi_create_arraybuffer(env, (size_t)n * sizeof(apo_record), &recs, &out) != napi_ok) { napi_get_null(env, &out); return out; }
+	if (n) apo_records_from_json((const char *)text, bytes, (apo_record *)recs, (uint64_t)n, &pos);
+	return out;
+}
+
+NAPI_MODULE_INIT()
+{
 	const napi_property_descriptor props[] = {
 	    {"create", NULL, Create, NULL, NULL, NULL, napi_default, NULL},
+	    {"lastCreateError", NULL, LastCreateError, NULL, NULL, NULL, napi_default, NULL},
+	    {"dimsUpload", NULL, DimsUpload, NULL, NULL, NULL, napi_default, NULL},
+	    {"rolloutsUpload", NULL, RolloutsUpload, NULL, NULL, NULL, napi_default, NULL},
+	    {"corpusUpload", NULL, CorpusUpload, NULL, NULL, NULL, napi_default, NULL},
+	    {"corpusUploadJson", NULL, CorpusUploadJson, NULL, NULL, NULL, napi_default, NULL},
+	    {"scoreResident", NULL, ScoreResident, NULL, NULL, NULL, napi_default, NULL},
+	    {"score", NULL, Score, NULL, NULL, NULL, napi_default, NULL},
+	    {"scoreHostRecords", NULL, ScoreHostRecords, NULL, NULL, NULL, napi_default, NULL},
 	    {"rewardBatch", NULL, RewardBatch, NULL, NULL, NULL, napi_default, NULL},
+	    {"commUniqueId", NULL, CommUniqueId, NULL, NULL, NULL, napi_default, NULL},
+	    {"commInit", NULL, CommInit, NULL, NULL, NULL, napi_default, NULL},
 	    {"allocPinned", NULL, AllocPinned, NULL, NULL, NULL, napi_default, NULL},
 	    {"recordsFromJson", NULL, RecordsFromJson, NULL, NULL, NULL, napi_default, NULL},
-	    {"score", NULL, Score, NULL, NULL, NULL, napi_default, NULL},
 	};
 	napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
 	return exports;

@@ -102,7 +102,9 @@ struct apo_engine {
 
 	// acc: [acc_words(C, nranks)] partial vector | [18] example scratch (inverted indices) | [1] ticket — one allocation, so one
 	// memset arms a scoring call.  acc_joined: the joined vector (> 1 rank); acc keeps this rank's partials.
-	DevBuf<long long> acc, acc_joined; uint32_t last_C = 0;
+	DevBuf<long long> acc, acc_joined, acc_snapshot; uint32_t last_C = 0;
+	uint64_t acc_clean_words = 0;        // > 0: the first acc_clean_words of acc are known to be zero (left so by the last one-shot call)
+	const long long *partials_src = nullptr;   // where apo_debug_partials finds the candidate partials of the last call
 	DevBuf<unsigned long long> misc;     // NCCL warm-up / status scratch
 	DevBuf<uint8_t> result;              // scores | counts | topk | report
 	DevBuf<unsigned long long> keys, sel_key; DevBuf<int32_t> sel_idx;
@@ -402,7 +404,9 @@ constexpr uint64_t kTimingMinBytes = 64ull << 20;  // per-stage CUDA events are 
 constexpr uint64_t ARM_WORDS = 19;                  // 18 example slots + ticket, right behind the partial vector
 
 int ensure_scratch(apo_engine *e, uint32_t C, uint32_t K) {
+	if (acc_words(C, e->nranks) + ARM_WORDS > e->acc.cap) e->acc_clean_words = 0;      // a fresh allocation is not zeroed
 	CK(e->acc.reserve(acc_words(C, e->nranks) + ARM_WORDS));
+	CK(e->acc_snapshot.reserve((uint64_t)ACC_PER_CAND * (C ? C : 1)));
 	const ResultLayout L = result_layout(C, K);
 	CK(e->result.reserve(L.bytes));
 	CK(e->keys.reserve(C ? C : 1));
@@ -454,9 +458,12 @@ apo::FinalizeParams make_fin(apo_engine *e, uint32_t C, uint32_t K, int with_cor
 
 // zero the candidate accumulators of a scoring session
 int begin_score(apo_engine *e, uint32_t C, bool whole = false) {
-	// whole: also the corpus block, the example scratch and the ticket (one-shot calls: a single memset arms everything)
+	// whole: also the corpus block, the example scratch and the ticket (one-shot calls: a single memset arms everything —
+	// and none at all when the previous one-shot call left the block zeroed, see FinalizeParams::clean_ptr)
 	const uint64_t words = whole ? acc_words(C, e->nranks) + ARM_WORDS : (uint64_t)ACC_PER_CAND * C;
-	CK(cudaMemsetAsync(e->acc.p, 0, words * 8, e->stream));
+	if (!(whole && e->acc_clean_words >= words)) CK(cudaMemsetAsync(e->acc.p, 0, words * 8, e->stream));
+	e->acc_clean_words = 0;                         // from here on the block is in use
+	e->partials_src = e->nranks > 1 ? e->acc_joined.p : e->acc.p;
 	e->last_C = C; e->score_C = C; e->scoring = true; e->k1_used = 0;
 	e->timing = apo_timing{};
 	if (e->timing_on) CK(cudaEventRecord(e->ev[0], e->stream));
@@ -771,7 +778,7 @@ extern "C" void apo_destroy(apo_engine *e) {
 	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	if (e->zc_host) cudaFreeHost(e->zc_host);
 	e->q8.release(); e->qd2.release(); e->qli.release(); e->qbook.release(); e->d_ptab.release(); e->d_pair.release(); e->d_cbf.release(); e->stage.release();
-	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->acc_joined.release(); e->misc.release();
+	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->acc_joined.release(); e->acc_snapshot.release(); e->misc.release();
 	e->result.release(); e->keys.release(); e->sel_key.release(); e->sel_idx.release();
 	e->win[0].release(); e->win[1].release(); e->batch_in.release(); e->batch_out.release(); e->batch_mask.release();
 	if (e->h_result) cudaFreeHost(e->h_result);
@@ -1165,9 +1172,18 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	const bool tail_only = !wants_corpus(e, o) && one_launch && count > 0 && !e->env_no_fuse;
 	if (fuse || tail_only) {
 		if ((rc = begin_score(e, C, true))) return rc;
-		apo::K2Params k2 = make_k2(e, C, make_fin(e, C, o->K, fuse ? 1 : 0));
+		apo::FinalizeParams F = make_fin(e, C, o->K, fuse ? 1 : 0);
+		const bool self_clean = one_launch;          // the finalising CTA is in this launch: it can leave the block zeroed
+		if (self_clean) { F.clean_ptr = e->acc.p; F.clean_words = (uint32_t)(acc_words(C, e->nranks) + ARM_WORDS); F.snapshot = e->acc_snapshot.p; }
+		apo::K2Params k2 = make_k2(e, C, F);
 		if (tail_only) { k2.T = 0; k2.recs = nullptr; }
 		if ((rc = launch_k1_resident(e, o, 0, first, count, &k2))) return rc;
+		rc = finish_score(e, o, C, scores, counts, topk, report, true);
+		if (rc == APO_OK && self_clean) {
+			e->acc_clean_words = F.clean_words;
+			if (e->nranks == 1) e->partials_src = e->acc_snapshot.p;
+		}
+		return rc;
 	} else {
 		if ((rc = begin_score(e, C))) return rc;
 		if ((rc = launch_k1_resident(e, o, 0, first, count))) return rc;
@@ -1279,7 +1295,7 @@ extern "C" int apo_debug_partials(apo_engine *e, int64_t *out, uint32_t C) {
 	if (!e || !out) return fail(e, APO_E_ARG, "NULL argument");
 	if (C != e->last_C || !e->acc.p) return fail(e, APO_E_STATE, "no scoring call with C=%u to read back", C);
 	CK(cudaSetDevice(e->device));
-	CK(cudaMemcpyAsync(out, (e->nranks > 1 && e->acc_joined.p) ? e->acc_joined.p : e->acc.p, 8ull * ACC_PER_CAND * C, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaMemcpyAsync(out, e->partials_src ? e->partials_src : e->acc.p, 8ull * ACC_PER_CAND * C, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	return APO_OK;
 }
@@ -1310,7 +1326,7 @@ extern "C" int apo_comm_init(apo_engine *e, int nranks, int rank, const uint8_t 
 	void *comm = nullptr;
 	const int rc = g_nccl.CommInitRank(&comm, nranks, nid, rank);
 	if (rc != 0) return fail(e, APO_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
-	e->comm = comm; e->nranks = nranks; e->rank = rank;
+	e->comm = comm; e->nranks = nranks; e->rank = rank; e->acc_clean_words = 0; e->partials_src = nullptr;
 	// one tiny allreduce now so that the first scoring call does not pay NCCL's lazy connection setup (~1 s)
 	CK(e->misc.reserve(32));
 	CK(cudaMemsetAsync(e->misc.p + 24, 0, 8, e->stream));

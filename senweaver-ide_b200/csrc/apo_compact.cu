@@ -356,11 +356,11 @@ static cudaError_t launch_kq(const KqParams &P, int grid, bool recip, cudaStream
 	cudaError_t err;
 	if (recip) {
 		auto k = k_reward9q<CW, EPT, STAGES, true, NF>;
-		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
+		if ((err = allow_big_smem(k, Cfg::SMEM)) != cudaSuccess) return err;
 		k<<<grid, (CW + 2) * 32, Cfg::SMEM, st>>>(P);
 	} else {
 		auto k = k_reward9q<CW, EPT, STAGES, false, NF>;
-		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
+		if ((err = allow_big_smem(k, Cfg::SMEM)) != cudaSuccess) return err;
 		k<<<grid, (CW + 2) * 32, Cfg::SMEM, st>>>(P);
 	}
 	return cudaGetLastError();
@@ -381,7 +381,7 @@ cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cuda
 	P.total_tiles = (uint64_t)P.tiles_per_cand * P.C;
 	if (P.total_tiles == 0) return cudaSuccess;
 	int grid = sm_count;
-	if (const char *g = getenv("APO_K1_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }
+	{ static const int env_grid = [] { const char *g = getenv("APO_K1_GRID"); return g ? atoi(g) : 0; }(); if (env_grid > 0 && env_grid < grid) grid = env_grid; }
 	if ((uint64_t)grid > P.total_tiles) grid = (int)P.total_tiles;
 	switch (variant) {
 	case 1: return launch_kq<16, 8, 3>(P, grid, recip, st);

@@ -487,6 +487,14 @@ static __device__ void finalize_and_publish(const FinalizeParams &F0) {
 		for (uint32_t i = threadIdx.x; i < F.result_bytes / 16; i += blockDim.x) dst[i] = __ldcg(src + i);
 		__threadfence_system();
 	}
+	if (F0.clean_ptr) {
+		// every other CTA has flushed and left (ticket), the join has read this rank's vector: keep the candidate partials
+		// for apo_debug_partials and hand the next call a zeroed accumulator block
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < (uint32_t)ACC_PER_CAND * F.C; i += blockDim.x) F0.snapshot[i] = __ldcg(F0.acc + i);
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < F0.clean_words; i += blockDim.x) F0.clean_ptr[i] = 0ll;
+	}
 }
 
 }  // namespace apo

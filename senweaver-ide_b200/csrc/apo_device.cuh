@@ -370,6 +370,31 @@ __device__ __forceinline__ apo_record gen_record(unsigned long long key, uint32_
 	return o;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device): the driver call costs a few microseconds,
+// which a 4 x 1000 call would pay on every launch.  Keyed by the kernel's address (instantiations share pointer types).
+inline cudaError_t allow_big_smem_impl(const void *kernel, int bytes) {
+	struct Entry { const void *k; int dev; };
+	static Entry table[256];
+	static int n = 0;
+	static volatile int lock = 0;
+	int dev = 0;
+	cudaGetDevice(&dev);
+	while (__sync_lock_test_and_set(&lock, 1)) {}
+	bool known = false;
+	for (int i = 0; i < n; i++) if (table[i].k == kernel && table[i].dev == dev) { known = true; break; }
+	__sync_lock_release(&lock);
+	if (known) return cudaSuccess;
+	const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (err == cudaSuccess) {
+		while (__sync_lock_test_and_set(&lock, 1)) {}
+		if (n < 256) { table[n].k = kernel; table[n].dev = dev; n++; }
+		__sync_lock_release(&lock);
+	}
+	return err;
+}
+template <class K>
+inline cudaError_t allow_big_smem(K kernel, int bytes) { return allow_big_smem_impl(reinterpret_cast<const void *>(kernel), bytes); }
+
 // ---------------------------------------------------------------- mbarrier / bulk-copy PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

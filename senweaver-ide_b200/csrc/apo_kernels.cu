@@ -293,11 +293,11 @@ static cudaError_t launch_k1(const K1Params &P, int grid, bool recip, cudaStream
 	cudaError_t err;
 	if (recip) {
 		auto k = k_reward9<ROW, CW, STAGES, true>;
-		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
+		if ((err = allow_big_smem(k, Cfg::SMEM)) != cudaSuccess) return err;
 		k<<<grid, (CW + 2) * 32, Cfg::SMEM, st>>>(P);
 	} else {
 		auto k = k_reward9<ROW, CW, STAGES, false>;
-		if ((err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return err;
+		if ((err = allow_big_smem(k, Cfg::SMEM)) != cudaSuccess) return err;
 		k<<<grid, (CW + 2) * 32, Cfg::SMEM, st>>>(P);
 	}
 	return cudaGetLastError();
@@ -323,8 +323,8 @@ cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_cou
 	P.total_tiles = (uint64_t)P.tiles_per_cand * P.C;
 	if (P.total_tiles == 0) return cudaSuccess;
 	int grid = sm_count;
-	if (const char *g = getenv("APO_K1_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }   // tuning experiments only
-	if (const char *g = getenv("APO_K1_TUNE")) P.tune = (uint32_t)atoi(g);
+	{ static const int env_grid = [] { const char *g = getenv("APO_K1_GRID"); return g ? atoi(g) : 0; }(); if (env_grid > 0 && env_grid < grid) grid = env_grid; }   // tuning experiments only, read once
+	{ static const int env_tune = [] { const char *g = getenv("APO_K1_TUNE"); return g ? atoi(g) : 0; }(); if (env_tune) P.tune = (uint32_t)env_tune; }
 	if ((uint64_t)grid > P.total_tiles) grid = (int)P.total_tiles;
 	if (row == 36) {
 		switch (variant) {

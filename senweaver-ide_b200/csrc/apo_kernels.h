@@ -34,6 +34,11 @@ struct FinalizeParams {
 	uint8_t *host_out;          // page-locked, device-mapped copy of the block written by the finalising CTA; NULL = the host copies
 	uint32_t result_bytes;
 	uint32_t meta_off;          // ResultMeta inside the block
+	// self-cleaning (one-shot calls): after the result is out, the finalising CTA keeps a copy of this rank's candidate
+	// partials (apo_debug_partials) and zeroes the whole accumulator block, so the NEXT call needs no memset: one launch per call
+	long long *clean_ptr;       // NULL = leave the accumulators alone (sessions)
+	uint32_t clean_words;
+	long long *snapshot;        // [4*C] copy of the candidate partials taken before cleaning
 	double *scores;             // [C]
 	uint64_t *counts;           // [C]
 	unsigned long long *keys;   // [C] scratch

@@ -151,7 +151,8 @@ def test_near_tie_topk_order_is_defined_by_the_exact_sums(engine, orc, apo):
     from fractions import Fraction
     T = 400_000
     base = orc.gen_dims(0x5EED0C0D, 3, 1, 0, T, 300, 8)[0]
-    t_star = int(np.flatnonzero(~np.isnan(base[:, 2]) & (np.abs(base[:, 2]) < 0.9))[0])
+    t_star = int(np.flatnonzero(~np.isnan(base[:, 2]))[0])
+    base[t_star, 2] = np.float32(1e-3)                        # a small value: one fp32 ulp is 1.2e-10, the mean moves by ~5e-17
     bumped = base.copy()
     bumped[t_star, 2] = np.nextafter(base[t_star, 2], np.float32(2.0))
     dims = np.stack([base, bumped, base])                     # 2 == 0 exactly (tie), 1 is a hair better

@@ -10,6 +10,8 @@ import { VSBuffer } from '../../../../base/common/buffer.js';
 import type { ConversationTrace } from './traceCollectorService.js';
 
 export const APO_RECORD_BYTES = 32;
+/** A 1 x 4 block of all-absent evaluations (36 floats of NaN): the dims argument of a report-only scoring call. */
+export const EMPTY_DIMS: VSBuffer = VSBuffer.wrap(new Uint8Array(new Float32Array(36).fill(NaN).buffer));
 const F_ERRORS = 0x01, F_ENDED = 0x02, F_VALID = 0x08, F_FAILSPAN = 0x10;
 const MODE_CODE: Record<string, number> = { normal: 1, agent: 2, gather: 3, designer: 4 };   // anything else -> 0 ('unknown')
 const U32_MAX = 0xFFFFFFFF;

@@ -514,13 +514,86 @@ def main():
             secondary["compact_layout"] = {"error": str(ex)}
         H.barrier()
 
-    # ---- end to end through the C ABI with HOST buffers (pinned), H2D inside the timed region
-    e2e, e2e16 = None, None
+    # ---- end to end through the C ABI with HOST buffers (page-locked), H2D inside the timed region.
+    # Headline: the configs[2] workload itself (this rank's shard: C x T) held in host memory in the compact wire format
+    # (Form Q planes, 14 B/eval) -> apo_corpus_upload + apo_score_host_compact per step.  Beside it, at 64 x 1M: the same call
+    # on fp32 Form D (36 B/eval) and on packed trace records (Form R16, 16 B/eval, dims derived on the device).
+    e2e, e2e_d, e2e16 = None, None, None
     if not args.no_secondary:
-        Ce, Te = min(args.e2e_candidates, C), min(args.e2e_records, T)
-        eng.set_stream(0)
-        eng2 = pkg.Engine(local)                                # separate handle, single rank: each rank scores its own host buffers
+        eng.close()                                             # the resident 92 GB are no longer needed
+        eng = None
+        eng2 = pkg.Engine(local)                                # single-rank handle: each rank streams its own host buffers
         t0e = first
+
+        def wall(fn, n, warm=2):
+            for _ in range(warm):
+                fn()
+            H.barrier()
+            a = time.perf_counter()
+            for _ in range(n):
+                out = fn()
+            torch.cuda.synchronize()
+            return H.max_over_ranks((time.perf_counter() - a) * 1e3 / n), out
+
+        def cand_check(sums_counts, cl, Tn):
+            import oracle
+            es, en = oracle.score_generated_fx(SEED, cl, t0e, Tn, 300, nthreads=usable_threads(H.all_cpus))
+            return all(sums_counts[0][c] == s_ and sums_counts[1][c] == n_ for c, s_, n_ in zip(cl, es, en))
+
+        # -- compact wire format at the full shard, bounded by host memory (3 x the planes must fit the cgroup / free RAM)
+        Cq, Tq, mem_note = C, T, ""
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+            try:
+                lim = open("/sys/fs/cgroup/memory.max").read().strip()
+                cur = int(open("/sys/fs/cgroup/memory.current").read().strip())
+                if lim != "max":
+                    avail = min(avail, int(lim) - cur)
+            except Exception:
+                pass
+        except Exception:
+            avail = 32 << 30
+        avail = int(H.max_over_ranks(-float(avail)) * -1) // max(1, world)      # the tightest rank, shared by the ranks of the box
+        if Cq * Tq * 14 * 3 > avail:
+            Tq = max(1_000_000, int(avail // (Cq * 14 * 3)) // 1_000_000 * 1_000_000)
+            Tq = min(Tq, T)
+            mem_note = f"records per rank reduced to {Tq}: three times the {Cq} x {T} compact planes exceed the {avail >> 30} GiB of host memory this rank may lock"
+        tA = time.perf_counter()
+        eng2.dims_generate_compact(SEED, 0, Cq, t0e, Tq, 300)
+        book = eng2.dims_codebook()
+        q8h, d2h_, lih = pkg.host_empty((Cq, Tq), np.uint64), pkg.host_empty((Cq, Tq), np.float32), pkg.host_empty((Cq, Tq), np.uint16)
+        for c in range(Cq):
+            eng2.dims_compact_download(c, 0, Tq, out=(q8h[c], d2h_[c], lih[c]))
+        eng2.corpus_generate(SEED, t0e, Tq, 300)
+        hrecq = pkg.host_empty((Tq,), pkg.RECORD_DTYPE)
+        hrecq[:] = eng2.corpus_download(0, Tq)
+        eng2.close()
+        eng2 = pkg.Engine(local)                                # nothing resident: the timed call brings everything over PCIe
+        setup_s = time.perf_counter() - tA
+        Kq = max(1, Cq // 4)
+
+        def e2eq_step():
+            eng2.corpus_upload(hrecq, idx_base=t0e)
+            return eng2.score_host_compact(q8h, d2h_, lih, book, Kq, corpus=True)
+
+        q_ms, rq2 = wall(e2eq_step, max(2, min(args.e2e_steps, 3)) if Cq * Tq > 10**9 else args.e2e_steps, warm=1 if Cq * Tq > 10**9 else 2)
+        q_sums = eng2.debug_partials(Cq)
+        d2h = 16 * Cq + 4 * Kq + 1024
+        if rank == 0:
+            cl = sorted({0, Cq // 2, Cq - 1})
+            okq = cand_check(q_sums, cl, Tq)
+            same_as_resident = bool(Tq == T and np.array_equal(rq2.topk, r.topk) and (world > 1 or np.array_equal(rq2.scores, r.scores)))
+            e2e = {"value": Cq * Tq * world / (q_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Cq * Tq * 14 + Tq * 32,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": q_ms, "h2d_GBps": (Cq * Tq * 14 + Tq * 32) / (q_ms * 1e-3) / 1e9,
+                   "host_placement": H.numa_note, "setup_s_excluded": round(setup_s, 1), "note": mem_note,
+                   "parity": {"partials_exact": bool(okq), "candidates": cl, "same_topk_as_resident_run": same_as_resident if world == 1 else None},
+                   "workload": f"configs[2] shard {Cq} x {Tq} in the compact wire format (Form Q planes, 14 B/eval: lossless recoding of the Form D tensor) + "
+                               f"{Tq}-record corpus, from page-locked host memory per rank via apo_corpus_upload + apo_score_host_compact"}
+        del q8h, d2h_, lih, hrecq
+
+        # -- 64 x 1M: fp32 Form D and packed trace records
+        Ce, Te = min(args.e2e_candidates, C), min(args.e2e_records, T)
         eng2.dims_generate(SEED, 0, Ce, t0e, Te, 300)           # device generator == oracle generator, bit for bit
         host = torch.empty((Ce, Te, 9), dtype=torch.float32, pin_memory=True)
         hnp = host.numpy()
@@ -536,20 +609,8 @@ def main():
             eng2.corpus_upload(hrec, idx_base=t0e)
             return eng2.score_host(hnp, Ke, corpus=True, variant=args.variant, recip=bool(args.recip))
 
-        def wall(fn, n):
-            for _ in range(2):
-                fn()
-            H.barrier()
-            a = time.perf_counter()
-            for _ in range(n):
-                out = fn()
-            torch.cuda.synchronize()
-            return H.max_over_ranks((time.perf_counter() - a) * 1e3 / n), out
-
         e_ms, re_ = wall(e2e_step, args.e2e_steps)
-        d2h = 16 * Ce + 4 * Ke + 1024
         e2e_sums = eng2.debug_partials(Ce)
-        # ---- the same call with the evaluations as packed trace records (Form R16, 16 B/eval): dims derived on the device
         eng2.rollouts16_generate(SEED, 0, Ce, t0e, Te, 300)
         host16_t = torch.empty((Ce * Te * 16,), dtype=torch.uint8, pin_memory=True)
         host16 = host16_t.numpy().view(pkg.RECORD16_DTYPE).reshape(Ce, Te)
@@ -563,23 +624,20 @@ def main():
         e16_ms, _ = wall(e2e16_step, args.e2e_steps)
         e16_sums = eng2.debug_partials(Ce)
         eng2.close()
-        # parity of the e2e legs: a few whole candidates of this rank's host buffers against the oracle
-        e2e_ok = True
         if rank == 0:
             import oracle
             cl = sorted({0, Ce // 2, Ce - 1})
-            es, en = oracle.score_generated_fx(SEED, cl, t0e, Te, 300, nthreads=usable_threads(H.all_cpus))
-            e2e_ok = all(e2e_sums[0][c] == s_ and e2e_sums[1][c] == n_ for c, s_, n_ in zip(cl, es, en))
+            e2e_ok = cand_check(e2e_sums, cl, Te)
             e16_ok = True
             for c in cl[:2]:                                    # Form R16: dims are derived from the records (TCS:668-763) on both sides
                 roll = oracle.gen_records(SEED, oracle.STREAM_ROLLOUT, c, 1, t0e, Te, 300, 8)
                 rs, rn = oracle.score_records_fx(roll)
                 e16_ok &= (e16_sums[0][c], e16_sums[1][c]) == (rs[0], rn[0])
                 del roll
-            e2e = {"value": Ce * Te * world / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 36 + Te * 32,
-                   "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "host_placement": H.numa_note,
-                   "parity": {"partials_exact": bool(e2e_ok), "candidates": cl},
-                   "workload": f"{Ce} x {Te} Form D + {Te}-record corpus from pinned host memory per rank via apo_corpus_upload + apo_score_host"}
+            d2h = 16 * Ce + 4 * Ke + 1024
+            e2e_d = {"value": Ce * Te * world / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 36 + Te * 32,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "parity": {"partials_exact": bool(e2e_ok), "candidates": cl},
+                     "workload": f"{Ce} x {Te} fp32 Form D (36 B/eval) + {Te}-record corpus from pinned host memory per rank via apo_corpus_upload + apo_score_host"}
             e2e16 = {"value": Ce * Te * world / (e16_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 16 + Te * 32,
                      "d2h_bytes_per_step": d2h, "ms_per_step": e16_ms, "parity": {"partials_exact": bool(e16_ok), "candidates": cl[:2]},
                      "workload": f"{Ce} x {Te} packed trace records (Form R16, 16 B/eval) + corpus from pinned host memory per rank via apo_score_host_records"}
@@ -609,7 +667,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "alg_bytes_per_launch": alg_bytes, "k1_ms": k1, "k2_ms": k2_ms,
                          "join_wait_ms": join_wait, "join_reduce_ms": join_red, "join_ms": join_wait + join_red + nccl_ms},
-            "e2e": e2e, "e2e_records16": e2e16,
+            "e2e": e2e, "e2e_form_d": e2e_d, "e2e_records16": e2e16,
             "gpu_launches": launches,
             "clocks": clocks,
         }
@@ -619,11 +677,12 @@ def main():
             out["cpu_baseline"] = cpu_baseline(C)
         ok = parity["ok"] and all(v.get("parity", {}).get("ok", True) for v in secondary.values() if isinstance(v, dict))
         if e2e is not None:
-            ok = ok and e2e["parity"]["partials_exact"] and e2e16["parity"]["partials_exact"]
+            ok = ok and e2e["parity"]["partials_exact"] and e2e_d["parity"]["partials_exact"] and e2e16["parity"]["partials_exact"]
         out["parity_ok"] = bool(ok)
         print(json.dumps(out))
         rc = 0 if ok else 1
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
     sys.exit(rc)

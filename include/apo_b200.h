@@ -248,6 +248,19 @@ int apo_score_host(apo_engine *e, const apo_score_opts *o, const float *dims, ui
 int apo_score_host_records(apo_engine *e, const apo_score_opts *o, const void *recs, uint32_t row_bytes,
                            uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
                            apo_corpus_report *report);
+/* Form Q as a wire format — the same call for callers that hold the evaluations in the compact layout in host memory:
+ * three planes [C][T] (q8: 8 one-byte codes per evaluation, d2: fp32 tool_success_rate, li: 2-byte presence index = 14 B
+ * per evaluation instead of 36) + the codebook (8 x 256 fp32 bit patterns, 0xFFFFFFFF = unused) that assigns the codes.
+ * apo_compact_encode_host builds them from Form D on the host (two passes on nthreads threads; APO_E_STATE when a coded
+ * dimension has more than 255 distinct values); apo_dims_compact_download / apo_dims_codebook export a resident Form Q
+ * tensor.  Results are bit-identical to scoring the Form D tensor. */
+int apo_compact_encode_host(const float *dims, uint32_t C, uint64_t T, uint64_t *q8, float *d2, uint16_t *li,
+                            uint32_t *codebook /* [8*256] */, int nthreads);
+int apo_dims_compact_download(apo_engine *e, uint64_t *q8, float *d2, uint16_t *li, uint32_t c, uint64_t first, uint64_t n);
+int apo_dims_codebook(apo_engine *e, uint32_t *codebook /* [8*256] */);
+int apo_score_host_compact(apo_engine *e, const apo_score_opts *o, const uint64_t *q8, const float *d2, const uint16_t *li,
+                           const uint32_t *codebook, uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
+                           apo_corpus_report *report);
 /* Host buffers for the streaming calls and the uploads.  Any host pointer is accepted: pageable memory (malloc, a JS
  * ArrayBuffer, numpy) is gathered chunk by chunk into pinned staging buffers by a few host threads while
  * the previous chunk is on the wire; memory from apo_host_alloc (page-locked) is read in place and

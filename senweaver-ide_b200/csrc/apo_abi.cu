@@ -1261,6 +1261,108 @@ int score_host_rows(apo_engine *e, const apo_score_opts *o, const uint8_t *rows,
 }
 }  // namespace
 
+// =============================================================================== Form Q in host memory (compact wire format)
+extern "C" int apo_dims_codebook(apo_engine *e, uint32_t *codebook) {
+	if (!e || !codebook) return fail(e, APO_E_ARG, "NULL argument");
+	if (!e->compact) return fail(e, APO_E_STATE, "no compact (Form Q) evaluations loaded");
+	memcpy(codebook, e->qbook_host, sizeof e->qbook_host);
+	return APO_OK;
+}
+
+extern "C" int apo_dims_compact_download(apo_engine *e, uint64_t *q8, float *d2, uint16_t *li, uint32_t c, uint64_t first, uint64_t n) {
+	if (!e || !q8 || !d2 || !li) return fail(e, APO_E_ARG, "NULL argument");
+	if (!e->compact) return fail(e, APO_E_STATE, "no compact (Form Q) evaluations loaded");
+	if (c >= e->dims_C || first + n > e->dims_T) return fail(e, APO_E_ARG, "range outside the evaluations");
+	CK(cudaSetDevice(e->device));
+	const uint64_t off = (uint64_t)c * e->dims_pitch + first;
+	CK(cudaMemcpyAsync(q8, e->q8.p + off, n * 8, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaMemcpyAsync(d2, e->qd2.p + off, n * 4, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaMemcpyAsync(li, e->qli.p + off, n * 2, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	return APO_OK;
+}
+
+namespace {
+// Streams the three Form Q planes [C][T] (8 + 4 + 2 bytes per evaluation) through two device windows, H2D of chunk i+1
+// overlapped with K1q on chunk i — the host-streaming call for callers that hold the compact wire format (14 B / evaluation
+// over PCIe instead of 36).
+int score_host_compact_impl(apo_engine *e, const apo_score_opts *o, const uint64_t *q8, const float *d2, const uint16_t *li,
+                            const uint32_t *codebook, uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
+                            apo_corpus_report *report) {
+	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
+	if (!q8 || !d2 || !li || !codebook || C == 0) return fail(e, APO_E_ARG, "input is NULL or C == 0");
+	if (o->K > C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, C);
+	if (o->K > kMaxK) return fail(e, APO_E_ARG, "K=%u exceeds the supported beam width %u", o->K, kMaxK);
+	if (o->first || o->count) return fail(e, APO_E_ARG, "windows are not supported by the host-streaming calls");
+	CK(cudaSetDevice(e->device));
+	int rc;
+	if ((rc = ensure_scratch(e, C, o->K))) return rc;
+	// the lookup tables of K1q follow the codebook of THIS call; a resident Form Q tensor keeps its own and gets it back below
+	uint32_t saved[8 * 256];
+	const bool had_resident = e->compact;
+	const bool same_book = memcmp(e->qbook_host, codebook, sizeof e->qbook_host) == 0 && e->d_ptab.p != nullptr;
+	if (had_resident) memcpy(saved, e->qbook_host, sizeof saved);
+	if (!same_book) {
+		memcpy(e->qbook_host, codebook, sizeof e->qbook_host);
+		if ((rc = upload_ptab(e))) return rc;
+	}
+	const int qv = e->q_pair_ok ? 0 : 4;
+	const int tile = apo::kq_tile_evals(qv);
+	uint64_t Tc = (256ull << 20) / ((uint64_t)C * 14);
+	Tc = Tc / tile * tile;
+	if (Tc < (uint64_t)tile) Tc = tile;
+	if (Tc > round_up(T ? T : 1, tile)) Tc = round_up(T ? T : 1, tile);
+	for (int i = 0; i < 2; i++) CK(e->win[i].reserve((uint64_t)C * Tc * 14));
+	choose_timing(e, o, (uint64_t)C * T * 14);
+	if (peer_join_active(e, C)) e->join_epoch++;
+	if ((rc = begin_score(e, C))) return rc;
+	int nchunk = 0;
+	for (uint64_t t0 = 0; t0 < T; t0 += Tc, nchunk++) {
+		const int b = nchunk & 1;
+		const uint64_t n = T - t0 < Tc ? T - t0 : Tc;
+		uint8_t *w = e->win[b].p;
+		unsigned long long *wq = (unsigned long long *)w;
+		float *wd = (float *)(w + (uint64_t)C * Tc * 8);
+		unsigned short *wl = (unsigned short *)(w + (uint64_t)C * Tc * 12);
+		if (nchunk >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->win_free[b], 0));
+		if ((rc = copy_rows_h2d(e, wq, Tc * 8, q8 + t0, T * 8, n * 8, C, e->copy_stream))) return rc;
+		if ((rc = copy_rows_h2d(e, wd, Tc * 4, d2 + t0, T * 4, n * 4, C, e->copy_stream))) return rc;
+		if ((rc = copy_rows_h2d(e, wl, Tc * 2, li + t0, T * 2, n * 2, C, e->copy_stream))) return rc;
+		CK(cudaEventRecord(e->win_ready[b], e->copy_stream));
+		CK(cudaStreamWaitEvent(e->stream, e->win_ready[b], 0));
+		apo::KqParams Q{};
+		Q.q8 = wq; Q.d2 = wd; Q.li = wl; Q.pitch_evals = Tc; Q.C = C; Q.T = n;
+		Q.acc = e->acc.p; Q.lut = e->d_lut.p; Q.ptab = e->d_ptab.p; Q.w2 = e->W.w[2];
+		Q.pair = e->d_pair.p; Q.cbf = e->d_cbf.p; Q.n0 = e->q_n0; Q.n1 = e->q_n1;
+		{
+			static const int dim_of[8] = {0, 1, 3, 4, 5, 6, 7, 8};
+			for (int j = 0; j < 8; j++) Q.wq[j] = e->W.w[dim_of[j]];
+		}
+		if ((rc = record_k1_event(e, 0))) return rc;
+		CK(apo::run_reward9q(Q, qv, (o->flags & APO_SCORE_RECIP) != 0, e->sm_count, e->stream));
+		if ((rc = record_k1_event(e, 1))) return rc;
+		e->timing.launches++;
+		CK(cudaEventRecord(e->win_free[b], e->stream));
+	}
+	rc = finish_score(e, o, C, scores, counts, topk, report);
+	if (had_resident && !same_book) {
+		memcpy(e->qbook_host, saved, sizeof saved);
+		const int rc2 = upload_ptab(e);
+		if (rc == APO_OK) rc = rc2;
+	}
+	return rc;
+}
+}  // namespace
+
+extern "C" int apo_score_host_compact(apo_engine *e, const apo_score_opts *o, const uint64_t *q8, const float *d2, const uint16_t *li,
+                                      const uint32_t *codebook, uint32_t C, uint64_t T, double *scores, uint64_t *counts,
+                                      int32_t *topk, apo_corpus_report *report) {
+	if (!e) return APO_E_ARG;
+	const int rc = score_host_compact_impl(e, o, q8, d2, li, codebook, C, T, scores, counts, topk, report);
+	if (rc) { cudaStreamSynchronize(e->copy_stream); cudaStreamSynchronize(e->stream); }
+	return rc;
+}
+
 extern "C" int apo_host_alloc(uint64_t bytes, void **out) {
 	if (!out) return APO_E_ARG;
 	*out = nullptr;

@@ -260,3 +260,96 @@ extern "C" int64_t apo_records_from_json(const char *json, uint64_t len, apo_rec
 	if (c.p != c.end) return fail();
 	return n;
 }
+
+// =================================================================== Form D -> Form Q on the host (wire format)
+// The CPU twin of k_transcode + k_recode (apo_compact.cu): per coded dimension (0,1,3,4,5,6,7,8) the distinct fp32 bit
+// patterns, ordered by value (-0.0 before +0.0), become dense one-byte codes (255 = absent); d2 keeps its fp32 value
+// (+0.0 when absent); li = the presence mask rotated like apo::lut_index.  Same planes, same codebook, bit for bit, as the
+// device transcoder produces for the same tensor (tests/test_gpu_compact.py).  Two passes on `nthreads` host threads.
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+namespace {
+inline uint32_t fbits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
+inline int dim_of(int j) { return j < 2 ? j : j + 1; }
+
+struct DistinctSet {
+	uint32_t v[256]; int n = 0; bool overflow = false;
+	inline void add(uint32_t b) {
+		for (int i = 0; i < n; i++) if (v[i] == b) return;
+		if (n == 255) { overflow = true; return; }
+		v[n++] = b;
+	}
+};
+
+template <class F>
+void run_threads(int nthreads, F fn) {
+	if (nthreads <= 1) { fn(0, 1); return; }
+	std::vector<std::thread> th;
+	for (int k = 1; k < nthreads; k++) th.emplace_back(fn, k, nthreads);
+	fn(0, nthreads);
+	for (auto &t : th) t.join();
+}
+}  // namespace
+
+extern "C" int apo_compact_encode_host(const float *dims, uint32_t C, uint64_t T, uint64_t *q8, float *d2, uint16_t *li,
+                                       uint32_t *codebook, int nthreads) {
+	if ((C && T && (!dims || !q8 || !d2 || !li)) || !codebook) return APO_E_ARG;
+	if (nthreads < 1) nthreads = 1;
+	if (nthreads > 256) nthreads = 256;
+	const uint64_t N = (uint64_t)C * T;
+	// ---- pass 1: distinct values per coded dimension
+	std::vector<DistinctSet> sets((size_t)nthreads * 8);
+	run_threads(nthreads, [&](int k, int n) {
+		DistinctSet *mine = &sets[(size_t)k * 8];
+		const uint64_t a = N * (uint64_t)k / (uint64_t)n, b = N * (uint64_t)(k + 1) / (uint64_t)n;
+		for (uint64_t i = a; i < b; i++) {
+			const float *row = dims + i * APO_NDIM;
+			for (int j = 0; j < 8; j++) { const float f = row[dim_of(j)]; if (f == f) mine[j].add(fbits(f)); }
+		}
+	});
+	std::vector<uint32_t> dense[8];
+	for (int j = 0; j < 8; j++) {
+		DistinctSet all;
+		for (int k = 0; k < nthreads; k++) {
+			const DistinctSet &s = sets[(size_t)k * 8 + j];
+			if (s.overflow) all.overflow = true;
+			for (int i = 0; i < s.n; i++) all.add(s.v[i]);
+		}
+		if (all.overflow) return APO_E_STATE;              // not categorical: more than 255 distinct values (Form D must be kept)
+		dense[j].assign(all.v, all.v + all.n);
+		std::sort(dense[j].begin(), dense[j].end(), [](uint32_t x, uint32_t y) {
+			float fx, fy; memcpy(&fx, &x, 4); memcpy(&fy, &y, 4);
+			if (fx != fy) return fx < fy;
+			return x > y;                                    // -0.0 (sign bit set) before +0.0
+		});
+		for (int c = 0; c < 256; c++) codebook[256 * j + c] = c < (int)dense[j].size() ? dense[j][c] : 0xFFFFFFFFu;
+	}
+	// ---- pass 2: encode
+	run_threads(nthreads, [&](int k, int n) {
+		const uint64_t a = N * (uint64_t)k / (uint64_t)n, b = N * (uint64_t)(k + 1) / (uint64_t)n;
+		for (uint64_t i = a; i < b; i++) {
+			const float *row = dims + i * APO_NDIM;
+			uint64_t q = 0; uint32_t mask = 0;
+			for (int j = 0; j < 8; j++) {
+				const float f = row[dim_of(j)];
+				uint32_t code = 255u;
+				if (f == f) {
+					const uint32_t bits = fbits(f);
+					const std::vector<uint32_t> &dv = dense[j];
+					for (uint32_t c = 0; c < dv.size(); c++) if (dv[c] == bits) { code = c; break; }
+					mask |= 1u << dim_of(j);
+				}
+				q |= (uint64_t)code << (8 * j);
+			}
+			const float f2 = row[2];
+			const bool p2 = (f2 == f2);
+			mask |= (p2 ? 1u : 0u) << 2;
+			q8[i] = q;
+			d2[i] = p2 ? f2 : 0.0f;
+			li[i] = (uint16_t)(((mask >> 5) | (mask << 4)) & 511u);      // apo::lut_index: dims 5..8 in the low bits
+		}
+	});
+	return APO_OK;
+}

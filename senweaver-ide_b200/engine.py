@@ -89,7 +89,8 @@ ABI_SYMBOLS = (
     "apo_dims_compact", "apo_dims_generate_compact", "apo_dims_upload_compact", "apo_dims_layout",
     "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_rollouts16_upload",
     "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_score",
-    "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records", "apo_host_alloc", "apo_host_free",
+    "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records", "apo_score_host_compact", "apo_compact_encode_host",
+    "apo_dims_compact_download", "apo_dims_codebook", "apo_host_alloc", "apo_host_free",
     "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy", "apo_comm_join_mode",
 )
 
@@ -159,6 +160,10 @@ def load_library() -> C.CDLL:
     L.apo_score_accumulate.argtypes = [vp, C.POINTER(ScoreOpts), u32]
     L.apo_score_finish.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp]
     L.apo_score_host.argtypes = [vp, C.POINTER(ScoreOpts), vp, u32, u64, vp, vp, vp, vp]
+    L.apo_score_host_compact.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp, u32, u64, vp, vp, vp, vp]
+    L.apo_compact_encode_host.argtypes = [vp, u32, u64, vp, vp, vp, vp, i32]
+    L.apo_dims_compact_download.argtypes = [vp, vp, vp, vp, u32, u64, u64]
+    L.apo_dims_codebook.argtypes = [vp, vp]
     L.apo_last_timing.argtypes = [vp, C.POINTER(Timing)]
     L.apo_debug_partials.argtypes = [vp, vp, u32]
     L.apo_comm_unique_id.argtypes = [vp]
@@ -428,6 +433,34 @@ class Engine:
                                         C.byref(rep) if rep is not None else None))
         return ScoreResult(scores, counts, topk, rep, self.last_timing())
 
+    # -- Form Q in host memory (compact wire format)
+    def dims_codebook(self) -> np.ndarray:
+        out = np.empty(8 * 256, np.uint32)
+        self._ck(self._L.apo_dims_codebook(self._h, _p(out)))
+        return out
+
+    def dims_compact_download(self, c: int, first: int, n: int, out=None):
+        """(q8 u64[n], d2 f32[n], li u16[n]) of candidate c; pass out=(q8, d2, li) views to fill existing (pinned) buffers."""
+        q8, d2, li = out if out is not None else (np.empty(n, np.uint64), np.empty(n, np.float32), np.empty(n, np.uint16))
+        self._ck(self._L.apo_dims_compact_download(self._h, _p(q8), _p(d2), _p(li), c, first, n))
+        return q8, d2, li
+
+    def score_host_compact(self, q8: np.ndarray, d2: np.ndarray, li: np.ndarray, codebook: np.ndarray, K: int, corpus: bool = False,
+                           recip: bool = False) -> ScoreResult:
+        """q8 uint64 [C][T], d2 float32 [C][T], li uint16 [C][T] in (preferably pinned) host memory + the uint32[2048] codebook."""
+        assert q8.dtype == np.uint64 and d2.dtype == np.float32 and li.dtype == np.uint16 and q8.shape == d2.shape == li.shape and q8.ndim == 2
+        assert q8.flags.c_contiguous and d2.flags.c_contiguous and li.flags.c_contiguous
+        codebook = np.ascontiguousarray(codebook, np.uint32)
+        Cn, T = q8.shape
+        o = self._opts(K, SRC_DIMS, corpus, recip, 0, 0, 0)
+        scores = np.empty(Cn, np.float64)
+        counts = np.empty(Cn, np.uint64)
+        topk = np.empty(K, np.int32)
+        rep = CorpusReport() if corpus else None
+        self._ck(self._L.apo_score_host_compact(self._h, C.byref(o), _p(q8), _p(d2), _p(li), _p(codebook), Cn, T, _p(scores), _p(counts),
+                                                _p(topk), C.byref(rep) if rep is not None else None))
+        return ScoreResult(scores, counts, topk, rep, self.last_timing())
+
     def last_timing(self) -> Timing:
         t = Timing()
         self._ck(self._L.apo_last_timing(self._h, C.byref(t)))
@@ -461,6 +494,21 @@ class Engine:
     def comm_join_mode(self) -> int:
         """0 single rank, 1 ncclAllReduce join, 2 peer-memory join inside the scoring launch."""
         return int(self._L.apo_comm_join_mode(self._h))
+
+
+def compact_encode_host(dims: np.ndarray, nthreads: int = 8):
+    """Form D float32 [C][T][9] -> (q8, d2, li, codebook): the compact wire format, built on the host (apo_compact_encode_host).
+    Raises ApoError(APO_E_STATE) when the data is not categorical."""
+    L = load_library()
+    dims = np.ascontiguousarray(dims, np.float32)
+    Cn, T, nd = dims.shape
+    assert nd == NDIM
+    q8, d2, li = np.empty((Cn, T), np.uint64), np.empty((Cn, T), np.float32), np.empty((Cn, T), np.uint16)
+    book = np.empty(8 * 256, np.uint32)
+    rc = L.apo_compact_encode_host(_p(dims), Cn, T, _p(q8), _p(d2), _p(li), _p(book), nthreads)
+    if rc != 0:
+        raise ApoError(rc, "evaluations are not categorical: a coded dimension has more than 255 distinct values" if rc == -3 else "bad argument")
+    return q8, d2, li, book
 
 
 def pack16(recs: np.ndarray) -> np.ndarray:

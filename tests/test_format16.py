@@ -58,3 +58,30 @@ def test_generator_records_roundtrip(apo, orc):
     exp["tokens"] = np.minimum(recs["tokens"], 65535)                # the only saturating field the generator reaches
     assert np.array_equal(back, exp)
     assert orc.score_records_fx(back) == orc.score_records_fx(recs)  # and it does not change a single evaluation
+
+
+def test_compact_host_encoder_is_lossless(apo, orc):
+    """apo_compact_encode_host (host-format code, no GPU): decoding the three planes with the codebook gives back the fp32 bit
+    patterns of Form D, codes are dense and ordered by value, absent = 255 / +0.0 / cleared mask bit."""
+    import numpy as np
+    dims = orc.gen_dims(0x5EED00C8, 2, 5, 100, 20_011, 400, 4)
+    q8, d2, li, book = apo.compact_encode_host(dims, nthreads=3)
+    book = book.reshape(8, 256)
+    dim_of = [0, 1, 3, 4, 5, 6, 7, 8]
+    for j, dim in enumerate(dim_of):
+        used = book[j][book[j] != 0xFFFFFFFF]
+        vals = used.view(np.float32)
+        assert np.all(np.diff(vals) >= 0) and len(set(used.tolist())) == len(used)           # dense, ordered by value
+        code = ((q8 >> np.uint64(8 * j)) & np.uint64(255)).astype(np.int64)
+        absent = np.isnan(dims[:, :, dim])
+        assert np.array_equal(code == 255, absent)
+        dec = book[j][np.where(absent, 0, code)]
+        assert np.array_equal(dec[~absent], dims[:, :, dim][~absent].view(np.uint32))
+    a2 = np.isnan(dims[:, :, 2])
+    assert np.array_equal(d2[~a2].view(np.uint32), dims[:, :, 2][~a2].view(np.uint32)) and np.all(d2[a2] == 0)
+    mask = np.zeros(dims.shape[:2], np.uint32)
+    for i in range(9):
+        mask |= (~np.isnan(dims[:, :, i])).astype(np.uint32) << i
+    assert np.array_equal(li, (((mask >> 5) | (mask << 4)) & 511).astype(np.uint16))
+    one = apo.compact_encode_host(dims, nthreads=1)
+    assert all(np.array_equal(x, y) for x, y in zip(one, (q8, d2, li, book.reshape(-1))))      # thread count does not matter

@@ -135,3 +135,43 @@ def test_mixed_lookup_falls_back_when_the_prefix_table_is_too_large(engine, orc)
     engine.dims_compact()
     engine.score(C, 1, variant=5)
     assert engine.debug_partials(C) == orc.score_dims_fx(dims)
+
+
+def test_host_compact_wire_format_streams_to_the_same_integers(engine, orc, apo):
+    """Form Q as a PCIe wire format (14 B / evaluation): apo_score_host_compact over host planes must give the integers of the
+    Form D tensor; the host encoder (apo_compact_encode_host) must emit exactly the planes and the codebook of the device
+    transcoder; a resident Form Q tensor with another codebook keeps working after the streaming call."""
+    seed, C, T = 0x5EED00C7, 9, 150_001
+    dims = orc.gen_dims(seed, 0, C, 0, T, 300, 8)
+    exp = orc.score_dims_fx(dims)
+    q8, d2, li, book = apo.compact_encode_host(dims, nthreads=4)
+    engine.dims_upload_compact(dims)
+    assert np.array_equal(engine.dims_codebook(), book)
+    for c in (0, 4, 8):
+        a, b, l = engine.dims_compact_download(c, 0, T)
+        assert np.array_equal(a, q8[c]) and np.array_equal(b.view(np.uint32), d2[c].view(np.uint32)) and np.array_equal(l, li[c])
+    res = engine.score(C, 3)
+    assert engine.debug_partials(C) == exp
+    # another tensor stays resident (different candidate qualities -> usually another codebook order) while we stream this one
+    other = orc.gen_dims(seed + 1, 40, 3, 0, 40_000, 900, 8)
+    engine.dims_upload_compact(other)
+    exp_other = orc.score_dims_fx(other)
+    recs = orc.gen_records(seed, orc.STREAM_CORPUS, 0, 1, 0, 30_000, 300, 8).reshape(-1)
+    engine.corpus_upload(recs)
+    for host in ("pageable", "pinned"):
+        planes = (q8, d2, li)
+        if host == "pinned":
+            planes = tuple(apo.host_empty(p.shape, p.dtype) for p in (q8, d2, li))
+            for dst, src in zip(planes, (q8, d2, li)):
+                dst[:] = src
+        r = engine.score_host_compact(*planes, book, 3, corpus=True)
+        assert engine.debug_partials(C) == exp
+        assert np.array_equal(r.scores, res.scores) and np.array_equal(r.topk, res.topk)
+        assert r.report.bad == orc.report(recs).bad
+    engine.score(3, 1)                                   # the resident tensor's lookup tables were restored
+    assert engine.debug_partials(3) == exp_other
+    # not categorical -> the encoder refuses (Form D must be kept)
+    noisy = dims.copy()
+    noisy[0, :300, 3] = np.linspace(-1, 1, 300, dtype=np.float32)
+    with pytest.raises(apo.ApoError):
+        apo.compact_encode_host(noisy)

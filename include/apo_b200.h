@@ -42,12 +42,21 @@ typedef struct apo_record {
 	uint8_t  feedback;   /* 0 null, 1 'good', 2 'bad' */
 	uint8_t  flags;      /* APO_F_* */
 	uint8_t  mode;       /* chat mode code, see APO_NMODE */
-	uint8_t  pad;
+	uint8_t  durClass;   /* APO_DC_*: what the path asks of totalToolDurationMs, decided in binary64 by the encoder; 0 = derive from toolDurMs */
 	uint16_t userMsgs;   /* # user_message spans */
 	uint16_t asstMsgs;   /* # assistant_message spans */
 	uint32_t toolCalls, toolSucc, toolFail, llmCalls, tokens;
-	float    toolDurMs;
+	float    toolDurMs;  /* totalToolDurationMs rounded to binary32 (the value itself is only read when durClass is 0) */
 } apo_record;
+/* The reference compares totalToolDurationMs (a JS double: fractional performance.now() deltas) with 0 and 15000 and its
+ * per-call average with 1000 / 3000 / 10000 in binary64 (TCS:721-728, APO:754).  A binary32 copy can land on the other side of
+ * a threshold, so encoders that hold the double (the TypeScript codec, the JSON ingest, apo_duration_class) store the four
+ * comparison results here; records without them (durClass == 0: synthetic generators, hand-built records) are scored from
+ * toolDurMs, which is exact whenever the duration is representable in binary32. */
+#define APO_DC_SET     0x80u  /* the bits below are valid                                           */
+#define APO_DC_LEVEL   0x03u  /* how many of avg > 1000, avg > 3000, avg > 10000 hold (TCS:724-727) */
+#define APO_DC_POS     0x04u  /* totalToolDurationMs > 0 (TCS:721)                                  */
+#define APO_DC_SLOW    0x08u  /* totalToolDurationMs > 15000 (APO:754)                              */
 #define APO_F_ERRORS   0x01u  /* summary.hasErrors                                   */
 #define APO_F_ENDED    0x02u  /* endTime set                                         */
 #define APO_F_VALID    0x08u  /* summary.finalReward !== null (TCS:606, APO:550)     */
@@ -64,7 +73,7 @@ typedef struct apo_record16 {
 	uint16_t hdr;        /* bits 0-1 feedback, 2 hasErrors, 3 ended, 4 valid, 5 failspan, 6-8 mode */
 	uint8_t  userMsgs, asstMsgs;
 	uint16_t toolCalls, toolFail;
-	uint8_t  llmCalls, pad;
+	uint8_t  llmCalls, durClass;
 	uint16_t tokens;
 	float    toolDurMs;
 } apo_record16;
@@ -202,6 +211,8 @@ int apo_rollouts16_generate(apo_engine *e, uint64_t seed, uint32_t c0, uint32_t 
 int apo_rollouts16_download(apo_engine *e, apo_record16 *out, uint32_t c, uint64_t first, uint64_t n);
 /* Host-side format helpers (no device work).  pack returns APO_E_ARG and the index of the first
  * unrepresentable record in *bad (may be NULL). */
+/* durClass of a trace from the binary64 duration and the call count, exactly as TCS:721-728 / APO:754 compare them. */
+uint8_t apo_duration_class(double totalToolDurationMs, uint32_t totalToolCalls);
 int apo_record_pack16(const apo_record *in, uint64_t n, apo_record16 *out, uint64_t *bad);
 int apo_record_unpack16(const apo_record16 *in, uint64_t n, apo_record *out);
 

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY — importable from tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py; never from the product package.
-PARITY UNPINNED (see apo_oracle.h).
+Parity pinned by tests/golden/ref_*.json (reference method texts executed by oracle/ts_harness; see apo_oracle.h).
 """
 from __future__ import annotations
 
@@ -19,7 +19,7 @@ NDIM, NPAT, NMODE = 9, 6, 5
 STREAM_CORPUS, STREAM_ROLLOUT = 1, 2
 
 RECORD_DTYPE = np.dtype([
-    ("feedback", "u1"), ("flags", "u1"), ("mode", "u1"), ("pad", "u1"),
+    ("feedback", "u1"), ("flags", "u1"), ("mode", "u1"), ("durClass", "u1"),
     ("userMsgs", "<u2"), ("asstMsgs", "<u2"),
     ("toolCalls", "<u4"), ("toolSucc", "<u4"), ("toolFail", "<u4"),
     ("llmCalls", "<u4"), ("tokens", "<u4"), ("toolDurMs", "<f4"),
@@ -27,7 +27,7 @@ RECORD_DTYPE = np.dtype([
 assert RECORD_DTYPE.itemsize == 32
 RECORD16_DTYPE = np.dtype([
     ("hdr", "<u2"), ("userMsgs", "u1"), ("asstMsgs", "u1"), ("toolCalls", "<u2"), ("toolFail", "<u2"),
-    ("llmCalls", "u1"), ("pad", "u1"), ("tokens", "<u2"), ("toolDurMs", "<f4"),
+    ("llmCalls", "u1"), ("durClass", "u1"), ("tokens", "<u2"), ("toolDurMs", "<f4"),
 ])
 assert RECORD16_DTYPE.itemsize == 16
 

@@ -1,7 +1,8 @@
 /*
  * apo_oracle.c — CPU ORACLE (test infrastructure only; see apo_oracle.h header).
  *
- * PARITY UNPINNED (no reference tests / golden vectors / runnable reference exist).
+ * PARITY PINNED by tests/golden/ref_*.json: outputs of the reference's own method texts executed by
+ * oracle/ts_harness (see apo_oracle.h); tests/test_reference_pin.py compares this file with them bit for bit.
  * Plain C, IEEE-754 binary64 throughout (JS `number`), compiled with
  * -ffp-contract=off so no multiply-add is fused: every `a*b + c` below rounds twice,
  * exactly like the TypeScript it restates.
@@ -78,14 +79,21 @@ uint32_t orc_reward_dims(const orc_record *r, double dims[ORC_NDIM])
 		dims[4] = cnt;
 		mask |= 1u << 4;
 
-		/* TCS:721-729 */
+		/* TCS:721-729.  The record carries totalToolDurationMs as binary32 plus, when the encoder held the JS double, the
+		 * results of the binary64 comparisons (durClass); without them the comparisons are made here on the binary32 value. */
 		const double dur = (double)r->toolDurMs;
-		if (dur > 0) {
-			const double avg = dur / total;
+		const int set = (r->durClass & 0x80) != 0;
+		if (set ? (r->durClass & 0x04) != 0 : dur > 0) {
 			double ds = 1.0;
-			if (avg > 10000) ds = -0.5;
-			else if (avg > 3000) ds = 0.0;
-			else if (avg > 1000) ds = 0.5;
+			if (set) {
+				const unsigned lv = r->durClass & 3u;
+				ds = lv == 3 ? -0.5 : (lv == 2 ? 0.0 : (lv == 1 ? 0.5 : 1.0));
+			} else {
+				const double avg = dur / total;
+				if (avg > 10000) ds = -0.5;
+				else if (avg > 3000) ds = 0.0;
+				else if (avg > 1000) ds = 0.5;
+			}
 			dims[5] = ds;
 			mask |= 1u << 5;
 		}
@@ -427,7 +435,7 @@ static void report_accumulate(const orc_record *recs, uint64_t T, uint64_t idx_b
 		if (r->tokens > 10000) pat_hit(&out->pat[2], gi);                /* P3 APO:692-694 */
 		if (r->llmCalls > 2) pat_hit(&out->pat[3], gi);                  /* P4 APO:712-714 */
 		if (r->userMsgs >= 4) pat_hit(&out->pat[4], gi);                 /* P5 APO:732-735 */
-		if ((double)r->toolDurMs > 15000) pat_hit(&out->pat[5], gi);     /* P6 APO:753-755 */
+		if ((r->durClass & 0x80) ? (r->durClass & 0x08) != 0 : (double)r->toolDurMs > 15000) pat_hit(&out->pat[5], gi);   /* P6 APO:753-755 */
 	}
 }
 
@@ -623,7 +631,7 @@ void orc_unpack16(const orc_record16 *in, uint64_t n, orc_record *out)
 		r->mode = (uint8_t)((p->hdr >> 6) & 7);
 		r->userMsgs = p->userMsgs; r->asstMsgs = p->asstMsgs;
 		r->toolCalls = p->toolCalls; r->toolFail = p->toolFail; r->toolSucc = (uint32_t)p->toolCalls - p->toolFail;
-		r->llmCalls = p->llmCalls; r->tokens = p->tokens; r->toolDurMs = p->toolDurMs;
+		r->llmCalls = p->llmCalls; r->tokens = p->tokens; r->toolDurMs = p->toolDurMs; r->durClass = p->durClass;
 	}
 }
 
@@ -699,7 +707,7 @@ void orc_gen_record(uint64_t seed, uint32_t stream, uint32_t c, uint64_t t,
 	out->flags = (uint8_t)((hasErrors ? ORC_F_ERRORS : 0) | (ended ? ORC_F_ENDED : 0) |
 	                       ((ended || feedback) ? ORC_F_VALID : 0) | (toolFail > 0 ? ORC_F_FAILSPAN : 0));
 	out->mode = mode;
-	out->pad = 0;
+	out->durClass = 0;
 	out->userMsgs = (uint16_t)userMsgs;
 	const uint32_t asst = llm + ((((h4 >> 46) & 15) == 0) ? 1u : 0u);   /* 1/16: an assistant span without an llm_call record */
 	out->asstMsgs = (uint16_t)(asst < 65535 ? asst : 65535);

@@ -5,10 +5,14 @@
  * may include, link or call this.  Only tests/, __graft_entry__.smoke() and the
  * cpu_baseline / --impl reference legs of bench.py use it, as the checker.
  *
- * PARITY UNPINNED: the reference (TypeScript, VS Code fork) ships no tests, golden
- * vectors or fixtures for this path and cannot be executed in this environment (no JS
- * runtime).  This file is a plain-C binary64 restatement of the reference *source text*;
- * it is cross-checked against an independent pure-Python transcription
+ * PARITY PIN: the reference (TypeScript, VS Code fork) ships no tests, golden vectors or fixtures
+ * for this path and no JS runtime exists in this environment, so its OWN method texts (`_computeRewardSignals`,
+ * `getStats`, `_buildReport`, `_analyzePatterns`, `_generateLocalSuggestions`) are executed unmodified by the in-repo
+ * interpreter oracle/ts_harness/minijs.py (run_reference.py; run_reference.mjs does the same under Node): the outputs
+ * are the fixtures tests/golden/ref_*.json, and tests/test_reference_pin.py holds this file to them bit for bit
+ * (409 traces, 11 corpora).  The beam top-K alone stays defined by SURVEY 8c: the reference performs it on a closed
+ * backend.  This file is a plain-C binary64 restatement of the reference *source text*,
+ * also cross-checked against an independent pure-Python transcription
  * (oracle/ts_transcription.py) and the hand-derived known-answer vectors K1..K7.
  *
  * Citations: TCS = src/vs/workbench/contrib/senweaver/common/traceCollectorService.ts
@@ -35,7 +39,8 @@ typedef struct {
 	                        bit3 finalReward!==null (TCS:106, "valid"),
 	                        bit4 any tool_call span with toolSuccess===false (APO:667-669) */
 	uint8_t  mode;       /* 0 no metadata.chatMode, 1 'normal', 2 'agent', 3 'gather', 4 'designer' */
-	uint8_t  pad;
+	uint8_t  durClass;   /* 0x80 set | 0x03 level | 0x04 duration > 0 | 0x08 duration > 15000: the binary64 comparisons of
+	                        TCS:721-728 / APO:754 made by the encoder; 0 = derive them from toolDurMs */
 	uint16_t userMsgs;   /* # spans of type user_message      (TCS:752, APO:733) */
 	uint16_t asstMsgs;   /* # spans of type assistant_message (TCS:753)          */
 	uint32_t toolCalls;  /* totalToolCalls      (TCS:96)  */
@@ -145,7 +150,7 @@ void orc_score_generated_fx(uint64_t seed, const uint32_t *cands, uint32_t ncand
 
 /* Form R16 (include/apo_b200.h apo_record16): independent restatement of the 16-byte unpacking. */
 typedef struct {
-	uint16_t hdr; uint8_t userMsgs, asstMsgs; uint16_t toolCalls, toolFail; uint8_t llmCalls, pad; uint16_t tokens; float toolDurMs;
+	uint16_t hdr; uint8_t userMsgs, asstMsgs; uint16_t toolCalls, toolFail; uint8_t llmCalls, durClass; uint16_t tokens; float toolDurMs;
 } orc_record16;
 void orc_unpack16(const orc_record16 *in, uint64_t n, orc_record *out);
 

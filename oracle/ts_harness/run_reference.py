@@ -228,6 +228,10 @@ def golden_inputs():
             edge.append((None, True, True, 0, 0, 0, 0, 1, tok, 1, 1, mode))
         for turns in range(0, 11):
             edge.append(("bad", False, True, 0, 0, 0, 0, 1, 0, turns, turns + 1, mode))
+        # durations a binary32 copy would put on the other side of a threshold (the record's durClass carries the binary64 answer)
+        for dur, calls in ((1000.00001, 1), (3000.0000001, 1), (10000.0000001, 1), (15000.0000001, 1), (15000.0004, 2), (6000.0000002, 2),
+                           (29999.9999999, 3), (30000.000000001, 3), (1e-9, 4), (16777217.0, 1), (2999.99999999, 1)):
+            edge.append(("bad", False, True, calls, calls, 0, dur, 2, 1500, 2, 2, mode))
     tuples += [("e%03d" % i, t) for i, t in enumerate(edge)]
     return tuples
 

@@ -1,8 +1,8 @@
 """Pure-Python transcription of the reference's TypeScript hot path.
 
-TEST INFRASTRUCTURE ONLY (see oracle/apo_oracle.h).  PARITY UNPINNED: the reference has
-no tests or golden vectors for this path and cannot be executed here; this file restates
-the source text statement by statement on the reference's own object shapes
+TEST INFRASTRUCTURE ONLY (see oracle/apo_oracle.h).  Pinned by tests/golden/ref_*.json: the outputs of the
+reference's own method texts executed by oracle/ts_harness (tests/test_reference_pin.py compares this file with them
+bit for bit).  This file restates the source text statement by statement on the reference's own object shapes
 (ConversationTrace with `summary`, `spans`, `metadata`).  Python floats are IEEE-754
 binary64, the same arithmetic as a JS `number`, and Python never fuses multiply-add.
 
@@ -251,6 +251,21 @@ RECORD_STRUCT = struct.Struct("<BBBBHHIIIIIf")
 assert RECORD_STRUCT.size == 32
 
 
+def duration_class(dur, total_tool_calls) -> int:
+    """apo_record.durClass: the binary64 comparisons TCS:721-728 / APO:754 make on totalToolDurationMs, decided here because
+    the record only carries a binary32 copy of the value."""
+    dur = float(dur)
+    dc = 0x80
+    if dur > 0:
+        dc |= 0x04
+    if dur > 15000:
+        dc |= 0x08
+    if total_tool_calls > 0 and dur > 0:
+        avg = dur / total_tool_calls
+        dc |= (avg > 1000) + (avg > 3000) + (avg > 10000)
+    return dc
+
+
 def encode_record(trace: dict) -> bytes:
     """ConversationTrace -> 32-byte Form R (layout: oracle/apo_oracle.h orc_record)."""
     s = trace["summary"]
@@ -262,7 +277,8 @@ def encode_record(trace: dict) -> bytes:
     flags = ((1 if s["hasErrors"] else 0) | (2 if trace.get("endTime") else 0) |
              (8 if s["finalReward"] is not None else 0) | (16 if failspan else 0))
     sat32 = lambda v: int(min(max(v, 0), 0xFFFFFFFF))
-    return RECORD_STRUCT.pack(FB_CODE[s["userFeedback"]], flags, mode, 0, min(user, 65535), min(asst, 65535),
+    return RECORD_STRUCT.pack(FB_CODE[s["userFeedback"]], flags, mode, duration_class(s["totalToolDurationMs"], s["totalToolCalls"]),
+                              min(user, 65535), min(asst, 65535),
                               sat32(s["totalToolCalls"]), sat32(s["toolCallsSucceeded"]), sat32(s["toolCallsFailed"]),
                               sat32(s["totalLLMCalls"]), sat32(s["totalTokens"]), float(s["totalToolDurationMs"]))
 

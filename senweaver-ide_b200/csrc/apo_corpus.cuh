@@ -101,7 +101,7 @@ __device__ __forceinline__ void corpus_scan_warp(const K2Params &P, uint64_t fir
 				    r.tokens > 10000u,                   // P3 APO:693
 				    r.llmCalls > 2u,                     // P4 APO:713
 				    r.userMsgs >= 4u,                    // P5 APO:733-734
-				    (double)r.toolDurMs > 15000.0,       // P6 APO:754
+				    (r.durClass & APO_DC_SET) ? (r.durClass & APO_DC_SLOW) != 0 : (double)r.toolDurMs > 15000.0,   // P6 APO:754
 				};
 #pragma unroll
 				for (int p = 0; p < APO_NPAT; p++) {

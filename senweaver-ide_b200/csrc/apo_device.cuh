@@ -107,6 +107,21 @@ __device__ __forceinline__ double keep_if(bool p, double x) {
 	return __longlong_as_double(__double_as_longlong(x) & (p ? -1ll : 0ll));
 }
 
+// What the path asks of totalToolDurationMs (TCS:721-728, APO:754): taken from the record's durClass when the encoder decided
+// it in binary64 (APO_DC_SET), else derived from the binary32 copy.  `avg > thr` is evaluated as `dur > thr * total` (exact
+// product).
+struct DurClass { uint32_t level; bool pos, slow; };
+__device__ __forceinline__ DurClass dur_class(const apo_record &r, double dur, double total) {
+	const uint32_t dcb = r.durClass;
+	const bool set = (dcb & APO_DC_SET) != 0;
+	const uint32_t lv = (dur > __dmul_rn(1000.0, total)) + (dur > __dmul_rn(3000.0, total)) + (dur > __dmul_rn(10000.0, total));
+	DurClass d;
+	d.level = set ? (dcb & APO_DC_LEVEL) : lv;
+	d.pos = set ? (dcb & APO_DC_POS) != 0 : dur > 0.0;
+	d.slow = set ? (dcb & APO_DC_SLOW) != 0 : dur > 15000.0;
+	return d;
+}
+
 // dims[i] is the pushed value where bit i of the returned mask is set and +0.0 elsewhere.
 // Written select-style (no data-dependent branches) so that independent evaluations of one
 // thread interleave and warps do not diverge; every conditional push of the reference becomes a
@@ -134,8 +149,9 @@ __device__ __forceinline__ uint32_t reward_dims(const apo_record &r, double dims
 	// TCS:721-728.  avg = dur / total; `avg > thr`  <=>  dur > thr * total (exact product): a quotient of
 	// an fp32 value by an integer <= 2^32 cannot lie in (thr, thr + ulp/2].
 	const double dur = (double)r.toolDurMs;
-	const bool hasdur = tool && dur > 0.0;
-	const double ds = dur > __dmul_rn(10000.0, total) ? -0.5 : (dur > __dmul_rn(3000.0, total) ? 0.0 : (dur > __dmul_rn(1000.0, total) ? 0.5 : 1.0));
+	const DurClass dc = dur_class(r, dur, total);
+	const bool hasdur = tool && dc.pos;
+	const double ds = dc.level == 3u ? -0.5 : (dc.level == 2u ? 0.0 : (dc.level == 1u ? 0.5 : 1.0));
 	dims[5] = keep_if(hasdur, ds);
 
 	const bool llm = r.llmCalls > 0;                                  // TCS:733-736
@@ -187,8 +203,9 @@ __device__ __forceinline__ uint32_t record_ws_table_t(const apo_record &r, doubl
 	const uint32_t i4 = (r.toolCalls > cexc) + (r.toolCalls > cgood) + (r.toolCalls > cfair);
 	ws = __dadd_rn(ws, cat[CAT_D4 + (tool ? i4 : 4u)]);
 	const double dur = (double)r.toolDurMs;
-	const bool hasdur = tool && dur > 0.0;
-	const uint32_t i5 = (dur > __dmul_rn(1000.0, total)) + (dur > __dmul_rn(3000.0, total)) + (dur > __dmul_rn(10000.0, total));
+	const DurClass dc = dur_class(r, dur, total);
+	const bool hasdur = tool && dc.pos;
+	const uint32_t i5 = dc.level;
 	ws = __dadd_rn(ws, cat[CAT_D5 + (hasdur ? i5 : 4u)]);
 	const bool llm = r.llmCalls > 0;
 	const uint32_t thr6 = agent ? 3u : 1u;
@@ -230,8 +247,9 @@ __device__ __forceinline__ uint32_t record_ws_direct(const apo_record &r, double
 	ws = __dadd_rn(ws, cat[DIR_D3 + ag * 7u + (tool ? min(r.toolFail, 5u) : 6u)]);
 	ws = __dadd_rn(ws, cat[DIR_D4 + ag * 27u + min(r.toolCalls, 26u)]);
 	const double dur = (double)r.toolDurMs;
-	const bool hasdur = tool && dur > 0.0;
-	const uint32_t i5 = (dur > __dmul_rn(1000.0, total)) + (dur > __dmul_rn(3000.0, total)) + (dur > __dmul_rn(10000.0, total));
+	const DurClass dc = dur_class(r, dur, total);
+	const bool hasdur = tool && dc.pos;
+	const uint32_t i5 = dc.level;
 	ws = __dadd_rn(ws, cat[CAT_D5 + (hasdur ? i5 : 4u)]);
 	ws = __dadd_rn(ws, cat[DIR_D6 + ag * 10u + min(r.llmCalls, 9u)]);
 	const bool tok = r.tokens > 0;
@@ -361,7 +379,7 @@ __device__ __forceinline__ apo_record gen_record(unsigned long long key, uint32_
 	o.flags = (uint8_t)((err ? APO_F_ERRORS : 0u) | (ended ? APO_F_ENDED : 0u) |
 	                    ((ended || feedback) ? APO_F_VALID : 0u) | (fail > 0 ? APO_F_FAILSPAN : 0u));
 	o.mode = (uint8_t)mode;
-	o.pad = 0;
+	o.durClass = 0;                       // generator durations are integers < 2^24: exact in binary32
 	o.userMsgs = (uint16_t)user;
 	const uint32_t asst = llm + ((((h4 >> 46) & 15) == 0) ? 1u : 0u);
 	o.asstMsgs = (uint16_t)(asst < 65535u ? asst : 65535u);

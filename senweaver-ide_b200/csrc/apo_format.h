@@ -26,7 +26,7 @@ APO_HD apo_record16 pack16(const apo_record &r) {
 	p.toolCalls = (uint16_t)r.toolCalls;
 	p.toolFail = (uint16_t)r.toolFail;
 	p.llmCalls = (uint8_t)(r.llmCalls < 255u ? r.llmCalls : 255u);
-	p.pad = 0;
+	p.durClass = r.durClass;
 	p.tokens = (uint16_t)(r.tokens < 65535u ? r.tokens : 65535u);
 	p.toolDurMs = r.toolDurMs;
 	return p;
@@ -39,7 +39,7 @@ APO_HD apo_record unpack16(const apo_record16 &p) {
 	r.flags = (uint8_t)(((h & 4u) ? APO_F_ERRORS : 0u) | ((h & 8u) ? APO_F_ENDED : 0u) | ((h & 16u) ? APO_F_VALID : 0u) |
 	                    ((h & 32u) ? APO_F_FAILSPAN : 0u));
 	r.mode = (uint8_t)((h >> 6) & 7u);
-	r.pad = 0;
+	r.durClass = p.durClass;
 	r.userMsgs = p.userMsgs;
 	r.asstMsgs = p.asstMsgs;
 	r.toolCalls = p.toolCalls;

@@ -178,6 +178,7 @@ bool parse_span(Cur &c, SpanInfo &si) {
 bool parse_trace(Cur &c, apo_record &r) {
 	memset(&r, 0, sizeof r);
 	uint32_t user = 0, asst = 0;
+	double dur64 = 0.0;
 	bool failspan = false, ended = false, valid = false, errors = false;
 	bool ok = each_member(c, [&](const Str &k) {
 		Val v;
@@ -221,7 +222,7 @@ bool parse_trace(Cur &c, apo_record &r) {
 				else if (sk.is("totalTokens")) r.tokens = to_u32(sv);
 				else if (sk.is("toolCallsSucceeded")) r.toolSucc = to_u32(sv);
 				else if (sk.is("toolCallsFailed")) r.toolFail = to_u32(sv);
-				else if (sk.is("totalToolDurationMs")) r.toolDurMs = sv.k == K_NUM ? float(sv.num) : 0.f;
+				else if (sk.is("totalToolDurationMs")) { dur64 = sv.k == K_NUM ? sv.num : 0.0; r.toolDurMs = float(dur64); }
 				else if (sk.is("userFeedback")) r.feedback = sv.k == K_STR ? (sv.str.is("good") ? 1 : sv.str.is("bad") ? 2 : 0) : 0;
 				else if (sk.is("hasErrors")) errors = truthy(sv);
 				else if (sk.is("finalReward")) valid = sv.k == K_NUM;               // !== null, TCS:606 / APO:550
@@ -231,6 +232,7 @@ bool parse_trace(Cur &c, apo_record &r) {
 		return skip_value(c, 1);
 	});
 	if (!ok) return false;
+	r.durClass = apo_duration_class(dur64, r.toolCalls);     // the comparisons of TCS:721-728 / APO:754 on the stored double
 	r.userMsgs = uint16_t(user > 65535u ? 65535u : user);
 	r.asstMsgs = uint16_t(asst > 65535u ? 65535u : asst);
 	r.flags = uint8_t((errors ? APO_F_ERRORS : 0) | (ended ? APO_F_ENDED : 0) | (valid ? APO_F_VALID : 0) | (failspan ? APO_F_FAILSPAN : 0));
@@ -238,6 +240,17 @@ bool parse_trace(Cur &c, apo_record &r) {
 }
 
 }  // namespace
+
+extern "C" uint8_t apo_duration_class(double dur, uint32_t totalToolCalls) {
+	uint8_t dc = APO_DC_SET;
+	if (dur > 0) dc |= APO_DC_POS;                           // TCS:721 (NaN compares false, as in JS)
+	if (dur > 15000) dc |= APO_DC_SLOW;                      // APO:754
+	if (totalToolCalls > 0 && dur > 0) {
+		const double avg = dur / (double)totalToolCalls;     // TCS:722
+		dc |= uint8_t((avg > 1000) + (avg > 3000) + (avg > 10000));
+	}
+	return dc;
+}
 
 extern "C" int64_t apo_records_from_json(const char *json, uint64_t len, apo_record *out, uint64_t cap, uint64_t *err_pos) {
 	if (err_pos) *err_pos = 0;

@@ -31,7 +31,7 @@ DIM_NAMES = (
 MODE_NAMES = ("unknown", "normal", "agent", "gather", "designer")
 
 RECORD_DTYPE = np.dtype([
-    ("feedback", "u1"), ("flags", "u1"), ("mode", "u1"), ("pad", "u1"),
+    ("feedback", "u1"), ("flags", "u1"), ("mode", "u1"), ("durClass", "u1"),
     ("userMsgs", "<u2"), ("asstMsgs", "<u2"),
     ("toolCalls", "<u4"), ("toolSucc", "<u4"), ("toolFail", "<u4"),
     ("llmCalls", "<u4"), ("tokens", "<u4"), ("toolDurMs", "<f4"),
@@ -39,7 +39,7 @@ RECORD_DTYPE = np.dtype([
 assert RECORD_DTYPE.itemsize == 32
 RECORD16_DTYPE = np.dtype([
     ("hdr", "<u2"), ("userMsgs", "u1"), ("asstMsgs", "u1"), ("toolCalls", "<u2"), ("toolFail", "<u2"),
-    ("llmCalls", "u1"), ("pad", "u1"), ("tokens", "<u2"), ("toolDurMs", "<f4"),
+    ("llmCalls", "u1"), ("durClass", "u1"), ("tokens", "<u2"), ("toolDurMs", "<f4"),
 ])
 assert RECORD16_DTYPE.itemsize == 16
 
@@ -88,7 +88,7 @@ ABI_SYMBOLS = (
     "apo_corpus_download", "apo_records_from_json", "apo_corpus_upload_json", "apo_dims_upload", "apo_dims_generate", "apo_dims_download", "apo_dims_attach",
     "apo_dims_compact", "apo_dims_generate_compact", "apo_dims_upload_compact", "apo_dims_layout",
     "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_rollouts16_upload",
-    "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_score",
+    "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_duration_class", "apo_score",
     "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records", "apo_score_host_compact", "apo_compact_encode_host",
     "apo_dims_compact_download", "apo_dims_codebook", "apo_host_alloc", "apo_host_free",
     "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy", "apo_comm_join_mode",
@@ -172,8 +172,10 @@ def load_library() -> C.CDLL:
     L.apo_comm_join_mode.argtypes = [vp]
     for name in ABI_SYMBOLS:
         f = getattr(L, name)
-        if name not in ("apo_destroy", "apo_last_error", "apo_records_from_json"):
+        if name not in ("apo_destroy", "apo_last_error", "apo_records_from_json", "apo_duration_class"):
             f.restype = i32
+    L.apo_duration_class.argtypes = [C.c_double, u32]
+    L.apo_duration_class.restype = C.c_uint8
     L.apo_host_alloc.argtypes = [u64, C.POINTER(vp)]
     L.apo_host_free.argtypes = [vp]
     L.apo_records_from_json.argtypes = [C.c_char_p, u64, vp, u64, C.POINTER(u64)]

@@ -36,6 +36,20 @@ FB_CODE = {None: 0, "good": 1, "bad": 2}
 U32 = 0xFFFFFFFF
 
 
+def duration_class(dur: float, total_tool_calls: int) -> int:
+    """apo_record.durClass (include/apo_b200.h APO_DC_*): the comparisons TCS:721-728 / APO:754 make on the binary64
+    totalToolDurationMs, stored because the record keeps only a binary32 copy of the value (apo_duration_class in C)."""
+    dc = 0x80
+    if dur > 0:
+        dc |= 0x04
+    if dur > 15000:
+        dc |= 0x08
+    if total_tool_calls > 0 and dur > 0:
+        avg = dur / total_tool_calls
+        dc |= (avg > 1000) + (avg > 3000) + (avg > 10000)
+    return dc
+
+
 def encode_trace(trace: dict, valid: bool | None = None) -> np.ndarray:
     """ConversationTrace -> Form R (include/apo_b200.h apo_record): the fields the scoring
     path reads (TCS:94-108, :87, :91) plus the span-derived counts of TCS:752-753, APO:667-669."""
@@ -59,6 +73,7 @@ def encode_trace(trace: dict, valid: bool | None = None) -> np.ndarray:
     rec["llmCalls"] = min(int(s["totalLLMCalls"]), U32)
     rec["tokens"] = min(int(s["totalTokens"]), U32)
     rec["toolDurMs"] = float(s["totalToolDurationMs"])
+    rec["durClass"] = duration_class(float(s["totalToolDurationMs"]), int(s["totalToolCalls"]))
     return rec
 
 

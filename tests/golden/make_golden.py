@@ -1,9 +1,10 @@
 """Generates tests/golden/*.json.
 
-PARITY UNPINNED: the reference has no golden vectors for this path and cannot run here;
-these fixtures are produced by the independent pure-Python transcription of the reference
-source (oracle/ts_transcription.py) — KATs K1..K7 of SURVEY.md 8c plus a seeded random
-set — and by the C oracle's generator.  Floats are stored as hex strings (bit-exact).
+These four fixtures (reward_cases, report_case, generator_case, persisted_traces) are produced by the independent
+pure-Python transcription of the reference source (oracle/ts_transcription.py) — KATs K1..K7 of SURVEY.md 8c plus a seeded
+random set — and by the C oracle's generator.  Floats are stored as hex strings (bit-exact).  The fixtures that PIN parity
+are the ref_*.json files next to them: outputs of the reference's own method texts (oracle/ts_harness/run_reference.py),
+which reproduce every value in reward_cases.json (tests/test_reference_pin.py).
 
     python tests/golden/make_golden.py
 """

@@ -66,10 +66,16 @@ def test_ingest_edge_cases(pkg):
     assert pkg.records_from_json("[]").shape[0] == 0
     assert pkg.records_from_json("  [ ]\n").shape[0] == 0
     r = pkg.records_from_json('[{}]')                                  # a trace with nothing in it: zero record, not valid
-    assert r.shape[0] == 1 and r.tobytes() == bytes(32)
+    assert r.shape[0] == 1 and r["durClass"][0] == 0x80               # ... whose duration class says "0 ms: nothing holds"
+    z = r.copy(); z["durClass"] = 0
+    assert z.tobytes() == bytes(32)
     r = pkg.records_from_json('[{"summary":{"totalTokens":1e12,"totalLLMCalls":-3,"totalToolDurationMs":1234.5678,"finalReward":0,"hasErrors":true},"endTime":1}]')
     assert r["tokens"][0] == 0xFFFFFFFF and r["llmCalls"][0] == 0 and r["toolDurMs"][0] == np.float32(1234.5678)
     assert r["flags"][0] == 0x01 | 0x02 | 0x08
+    assert r["durClass"][0] == 0x80 | 0x04                            # duration > 0, but no tool calls: no average to classify
+    r = pkg.records_from_json('[{"summary":{"totalToolCalls":1,"totalToolDurationMs":3000.0000001}},{"summary":{"totalToolCalls":2,"totalToolDurationMs":30000.5}}]')
+    assert r["toolDurMs"][0] == np.float32(3000.0) and r["durClass"][0] == 0x80 | 0x04 | 2      # the double is > 3000, its float32 copy is not
+    assert r["durClass"][1] == 0x80 | 0x04 | 0x08 | 3
     # 300 spans: counts come from the spans actually stored (the reference caps at 200 before persisting, TCS:274-280)
     spans = [{"type": "user_message", "data": {}}] * 70000
     r = pkg.records_from_json(json.dumps([{"spans": spans}]))

@@ -33,7 +33,14 @@ export function encodeTraceRecord(trace: ConversationTrace, view: DataView, offs
 	view.setUint8(offset + 0, s.userFeedback === 'good' ? 1 : s.userFeedback === 'bad' ? 2 : 0);
 	view.setUint8(offset + 1, (s.hasErrors ? F_ERRORS : 0) | (trace.endTime ? F_ENDED : 0) | (valid ? F_VALID : 0) | (failSpan ? F_FAILSPAN : 0));
 	view.setUint8(offset + 2, mode);
-	view.setUint8(offset + 3, 0);
+	// durClass (APO_DC_*): the comparisons TCS:721-728 / APO:754 make on the double, decided here — the record keeps a float32 copy
+	const dur = s.totalToolDurationMs;
+	let dc = 0x80 | (dur > 0 ? 0x04 : 0) | (dur > 15000 ? 0x08 : 0);
+	if (s.totalToolCalls > 0 && dur > 0) {
+		const avg = dur / s.totalToolCalls;
+		dc |= (avg > 1000 ? 1 : 0) + (avg > 3000 ? 1 : 0) + (avg > 10000 ? 1 : 0);
+	}
+	view.setUint8(offset + 3, dc);
 	view.setUint16(offset + 4, Math.min(user, 0xFFFF), true);
 	view.setUint16(offset + 6, Math.min(asst, 0xFFFF), true);
 	view.setUint32(offset + 8, Math.min(s.totalToolCalls, U32_MAX), true);

@@ -515,10 +515,11 @@ def main():
         H.barrier()
 
     # ---- end to end through the C ABI with HOST buffers (page-locked), H2D inside the timed region.
-    # Headline: the configs[2] workload itself (this rank's shard: C x T) held in host memory in the compact wire format
-    # (Form Q planes, 14 B/eval) -> apo_corpus_upload + apo_score_host_compact per step.  Beside it, at 64 x 1M: the same call
-    # on fp32 Form D (36 B/eval) and on packed trace records (Form R16, 16 B/eval, dims derived on the device).
-    e2e, e2e_d, e2e16 = None, None, None
+    # Headline: the configs[2] workload itself (this rank's shard: C x T) held in host memory in the packed wire format
+    # (Form P, 6 B/eval: lossless for categorical reward dimensions) -> apo_corpus_upload + apo_score_host_packed per step.
+    # Beside it, at 64 x 1M: the same call on Form Q planes (14 B/eval), on fp32 Form D (36 B/eval) and on packed trace
+    # records (Form R16, 16 B/eval, dims derived on the device).
+    e2e, e2e_d, e2e16, e2e_q = None, None, None, None
     if not args.no_secondary:
         eng.close()                                             # the resident 92 GB are no longer needed
         eng = None
@@ -555,16 +556,16 @@ def main():
         except Exception:
             avail = 32 << 30
         avail = int(H.max_over_ranks(-float(avail)) * -1) // max(1, world)      # the tightest rank, shared by the ranks of the box
-        if Cq * Tq * 14 * 3 > avail:
-            Tq = max(1_000_000, int(avail // (Cq * 14 * 3)) // 1_000_000 * 1_000_000)
+        if Cq * Tq * 6 * 3 > avail:
+            Tq = max(1_000_000, int(avail // (Cq * 6 * 3)) // 1_000_000 * 1_000_000)
             Tq = min(Tq, T)
-            mem_note = f"records per rank reduced to {Tq}: three times the {Cq} x {T} compact planes exceed the {avail >> 30} GiB of host memory this rank may lock"
+            mem_note = f"records per rank reduced to {Tq}: three times the {Cq} x {T} packed planes exceed the {avail >> 30} GiB of host memory this rank may lock"
         tA = time.perf_counter()
         eng2.dims_generate_compact(SEED, 0, Cq, t0e, Tq, 300)
-        book = eng2.dims_codebook()
-        q8h, d2h_, lih = pkg.host_empty((Cq, Tq), np.uint64), pkg.host_empty((Cq, Tq), np.float32), pkg.host_empty((Cq, Tq), np.uint16)
+        book, d2book = eng2.dims_codebook(), eng2.dims_d2book()
+        pch, pdh = pkg.host_empty((Cq, Tq), np.uint32), pkg.host_empty((Cq, Tq), np.uint16)
         for c in range(Cq):
-            eng2.dims_compact_download(c, 0, Tq, out=(q8h[c], d2h_[c], lih[c]))
+            eng2.dims_packed_download(c, 0, Tq, out=(pch[c], pdh[c]))
         eng2.corpus_generate(SEED, t0e, Tq, 300)
         hrecq = pkg.host_empty((Tq,), pkg.RECORD_DTYPE)
         hrecq[:] = eng2.corpus_download(0, Tq)
@@ -575,7 +576,7 @@ def main():
 
         def e2eq_step():
             eng2.corpus_upload(hrecq, idx_base=t0e)
-            return eng2.score_host_compact(q8h, d2h_, lih, book, Kq, corpus=True)
+            return eng2.score_host_packed(pch, pdh, book, d2book, Kq, corpus=True)
 
         q_ms, rq2 = wall(e2eq_step, max(2, min(args.e2e_steps, 3)) if Cq * Tq > 10**9 else args.e2e_steps, warm=1 if Cq * Tq > 10**9 else 2)
         q_sums = eng2.debug_partials(Cq)
@@ -584,13 +585,13 @@ def main():
             cl = sorted({0, Cq // 2, Cq - 1})
             okq = cand_check(q_sums, cl, Tq)
             same_as_resident = bool(Tq == T and np.array_equal(rq2.topk, r.topk) and (world > 1 or np.array_equal(rq2.scores, r.scores)))
-            e2e = {"value": Cq * Tq * world / (q_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Cq * Tq * 14 + Tq * 32,
-                   "d2h_bytes_per_step": d2h, "ms_per_step": q_ms, "h2d_GBps": (Cq * Tq * 14 + Tq * 32) / (q_ms * 1e-3) / 1e9,
+            e2e = {"value": Cq * Tq * world / (q_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Cq * Tq * 6 + Tq * 32 + 4096 * 4,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": q_ms, "h2d_GBps": (Cq * Tq * 6 + Tq * 32) / (q_ms * 1e-3) / 1e9,
                    "host_placement": H.numa_note, "setup_s_excluded": round(setup_s, 1), "note": mem_note,
                    "parity": {"partials_exact": bool(okq), "candidates": cl, "same_topk_as_resident_run": same_as_resident if world == 1 else None},
-                   "workload": f"configs[2] shard {Cq} x {Tq} in the compact wire format (Form Q planes, 14 B/eval: lossless recoding of the Form D tensor) + "
-                               f"{Tq}-record corpus, from page-locked host memory per rank via apo_corpus_upload + apo_score_host_compact"}
-        del q8h, d2h_, lih, hrecq
+                   "workload": f"configs[2] shard {Cq} x {Tq} in the packed wire format (Form P, 6 B/eval: eight 4-bit codes + a 12-bit tool_success_rate index, "
+                               f"lossless recoding of the Form D tensor) + {Tq}-record corpus, from page-locked host memory per rank via apo_corpus_upload + apo_score_host_packed"}
+        del pch, pdh, hrecq
 
         # -- 64 x 1M: fp32 Form D and packed trace records
         Ce, Te = min(args.e2e_candidates, C), min(args.e2e_records, T)
@@ -611,6 +612,18 @@ def main():
 
         e_ms, re_ = wall(e2e_step, args.e2e_steps)
         e2e_sums = eng2.debug_partials(Ce)
+        q8s, d2s, lis, books = pkg.compact_encode_host(hnp, nthreads=usable_threads(H.all_cpus))   # the CPU encoder, on this rank's 64 x 1M
+        q8p, d2p, lip = (pkg.host_empty(x.shape, x.dtype) for x in (q8s, d2s, lis))
+        q8p[:], d2p[:], lip[:] = q8s, d2s, lis
+        del q8s, d2s, lis
+
+        def e2eq14_step():
+            eng2.corpus_upload(hrec, idx_base=t0e)
+            return eng2.score_host_compact(q8p, d2p, lip, books, Ke, corpus=True)
+
+        q14_ms, _ = wall(e2eq14_step, args.e2e_steps)
+        q14_same = eng2.debug_partials(Ce) == e2e_sums
+        del q8p, d2p, lip
         eng2.rollouts16_generate(SEED, 0, Ce, t0e, Te, 300)
         host16_t = torch.empty((Ce * Te * 16,), dtype=torch.uint8, pin_memory=True)
         host16 = host16_t.numpy().view(pkg.RECORD16_DTYPE).reshape(Ce, Te)
@@ -638,6 +651,9 @@ def main():
             e2e_d = {"value": Ce * Te * world / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 36 + Te * 32,
                      "d2h_bytes_per_step": d2h, "ms_per_step": e_ms, "parity": {"partials_exact": bool(e2e_ok), "candidates": cl},
                      "workload": f"{Ce} x {Te} fp32 Form D (36 B/eval) + {Te}-record corpus from pinned host memory per rank via apo_corpus_upload + apo_score_host"}
+            e2e_q = {"value": Ce * Te * world / (q14_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 14 + Te * 32, "d2h_bytes_per_step": d2h,
+                     "ms_per_step": q14_ms, "parity": {"partials_exact": bool(q14_same and e2e_ok), "note": "integers identical to the oracle-checked Form D leg"},
+                     "workload": f"{Ce} x {Te} Form Q planes (14 B/eval, encoded on the host by apo_compact_encode_host) + corpus via apo_score_host_compact"}
             e2e16 = {"value": Ce * Te * world / (e16_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Ce * Te * 16 + Te * 32,
                      "d2h_bytes_per_step": d2h, "ms_per_step": e16_ms, "parity": {"partials_exact": bool(e16_ok), "candidates": cl[:2]},
                      "workload": f"{Ce} x {Te} packed trace records (Form R16, 16 B/eval) + corpus from pinned host memory per rank via apo_score_host_records"}
@@ -667,7 +683,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "alg_bytes_per_launch": alg_bytes, "k1_ms": k1, "k2_ms": k2_ms,
                          "join_wait_ms": join_wait, "join_reduce_ms": join_red, "join_ms": join_wait + join_red + nccl_ms},
-            "e2e": e2e, "e2e_form_d": e2e_d, "e2e_records16": e2e16,
+            "e2e": e2e, "e2e_form_q": e2e_q, "e2e_form_d": e2e_d, "e2e_records16": e2e16,
             "gpu_launches": launches,
             "clocks": clocks,
         }
@@ -677,7 +693,7 @@ def main():
             out["cpu_baseline"] = cpu_baseline(C)
         ok = parity["ok"] and all(v.get("parity", {}).get("ok", True) for v in secondary.values() if isinstance(v, dict))
         if e2e is not None:
-            ok = ok and e2e["parity"]["partials_exact"] and e2e_d["parity"]["partials_exact"] and e2e16["parity"]["partials_exact"]
+            ok = ok and all(x["parity"]["partials_exact"] for x in (e2e, e2e_q, e2e_d, e2e16))
         out["parity_ok"] = bool(ok)
         print(json.dumps(out))
         rc = 0 if ok else 1

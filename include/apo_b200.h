@@ -272,6 +272,20 @@ int apo_dims_codebook(apo_engine *e, uint32_t *codebook /* [8*256] */);
 int apo_score_host_compact(apo_engine *e, const apo_score_opts *o, const uint64_t *q8, const float *d2, const uint16_t *li,
                            const uint32_t *codebook, uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
                            apo_corpus_report *report);
+/* Form P — the tightest lossless wire format (6 B per evaluation): pc = eight 4-bit codes in a uint32 (dimension order
+ * 0,1,3,4,5,6,7,8; 15 = absent), pd = 12-bit index of the tool_success_rate value into d2book (4095 = absent), both [C][T].
+ * Needs <= 15 distinct values per coded dimension and <= 4095 distinct tool_success_rate values (APO_E_STATE otherwise:
+ * fall back to Form Q / Form D); dims produced by TCS:668-763 always qualify.  The device expands every window to Form Q
+ * (k_unpack_p) right behind its H2D copy and scores it with K1q: same integers, 2.3x fewer PCIe bytes than Form Q. */
+int apo_packed_encode_host(const float *dims, uint32_t C, uint64_t T, uint32_t *pc, uint16_t *pd,
+                           uint32_t *codebook /* [8*256] */, uint32_t *d2book /* [4096] fp32 bit patterns */, int nthreads);
+/* Export of a resident Form Q tensor in Form P (rows of candidate c) and the tool_success_rate table that goes with it
+ * (the codebook is apo_dims_codebook's). */
+int apo_dims_packed_download(apo_engine *e, uint32_t *pc, uint16_t *pd, uint32_t c, uint64_t first, uint64_t n);
+int apo_dims_d2book(apo_engine *e, uint32_t *d2book /* [4096] */);
+int apo_score_host_packed(apo_engine *e, const apo_score_opts *o, const uint32_t *pc, const uint16_t *pd, const uint32_t *codebook,
+                          const uint32_t *d2book, uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
+                          apo_corpus_report *report);
 /* Host buffers for the streaming calls and the uploads.  Any host pointer is accepted: pageable memory (malloc, a JS
  * ArrayBuffer, numpy) is gathered chunk by chunk into pinned staging buffers by a few host threads while
  * the previous chunk is on the wire; memory from apo_host_alloc (page-locked) is read in place and

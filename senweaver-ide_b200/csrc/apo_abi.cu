@@ -96,8 +96,9 @@ struct apo_engine {
 	DevBuf<float> dims; const float *dims_ptr = nullptr; uint32_t dims_C = 0; uint64_t dims_T = 0, dims_pitch = 0;
 	// Form Q (compact) copy of the evaluations: replaces dims/dims_ptr when `compact` is set
 	DevBuf<unsigned long long> q8; DevBuf<float> qd2; DevBuf<unsigned short> qli; DevBuf<uint32_t> qbook;   // qbook: [8][256] codebook + [8] overflow flags
-	DevBuf<double> d_ptab, d_pair; DevBuf<float> stage, d_cbf; uint32_t q_n0 = 0, q_n1 = 0; bool q_pair_ok = false;
+	DevBuf<double> d_ptab, d_pair; DevBuf<float> stage, d_cbf, d_d2book, d_d2stream; uint32_t q_n0 = 0, q_n1 = 0; bool q_pair_ok = false;
 	uint32_t qbook_host[8 * 256]; bool compact = false;
+	uint32_t d2book_host[4096]; uint32_t d2book_n = ~0u;       // Form P export of the resident tensor (~0 = not built yet)
 	DevBuf<uint8_t> roll; uint32_t roll_C = 0, roll_row = 32; uint64_t roll_T = 0, roll_pitch = 0;   // Form R (32 B) or R16 (16 B) rows
 
 	// acc: [acc_words(C, nranks)] partial vector | [18] example scratch (inverted indices) | [1] ticket — one allocation, so one
@@ -305,6 +306,7 @@ int compact_finish(apo_engine *e, uint32_t C, uint64_t T, uint64_t pitch) {
 	int rc = upload_ptab(e);
 	if (rc) return rc;
 	e->compact = true; e->dims_C = C; e->dims_T = T; e->dims_pitch = pitch; e->dims_ptr = nullptr;
+	e->d2book_n = ~0u;
 	return APO_OK;
 }
 
@@ -777,7 +779,7 @@ extern "C" void apo_destroy(apo_engine *e) {
 	peer_teardown(e);
 	if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
 	if (e->zc_host) cudaFreeHost(e->zc_host);
-	e->q8.release(); e->qd2.release(); e->qli.release(); e->qbook.release(); e->d_ptab.release(); e->d_pair.release(); e->d_cbf.release(); e->stage.release();
+	e->q8.release(); e->qd2.release(); e->qli.release(); e->qbook.release(); e->d_ptab.release(); e->d_pair.release(); e->d_cbf.release(); e->d_d2book.release(); e->d_d2stream.release(); e->stage.release();
 	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->acc_joined.release(); e->acc_snapshot.release(); e->misc.release();
 	e->result.release(); e->keys.release(); e->sel_key.release(); e->sel_idx.release();
 	e->win[0].release(); e->win[1].release(); e->batch_in.release(); e->batch_out.release(); e->batch_mask.release();
@@ -1283,14 +1285,82 @@ extern "C" int apo_dims_compact_download(apo_engine *e, uint64_t *q8, float *d2,
 }
 
 namespace {
+// d2book of the resident Form Q tensor: distinct tool_success_rate values ordered by value (built once per loaded tensor)
+int ensure_d2book(apo_engine *e) {
+	if (e->d2book_n != ~0u) return APO_OK;
+	DevBuf<uint32_t> table;
+	CK(table.reserve(16384 + 1));
+	CK(cudaMemsetAsync(table.p, 0xFF, 16384 * 4, e->stream));
+	CK(cudaMemsetAsync(table.p + 16384, 0, 4, e->stream));
+	// pad evaluations carry a cleared presence bit, so the whole pitched planes can be scanned
+	CK(apo::run_collect_d2(e->qd2.p, e->qli.p, (uint64_t)e->dims_C * e->dims_pitch, table.p, table.p + 16384, e->stream));
+	std::vector<uint32_t> host(16384 + 1);
+	CK(cudaMemcpyAsync(host.data(), table.p, host.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	table.release();
+	if (host[16384] > 4095) return fail(e, APO_E_STATE, "tool_success_rate takes %u distinct values: more than the 4095 Form P can index", host[16384]);
+	std::vector<uint32_t> vals;
+	for (int i = 0; i < 16384; i++) if (host[i] != 0xFFFFFFFFu) vals.push_back(host[i]);
+	std::sort(vals.begin(), vals.end(), [](uint32_t x, uint32_t y) {
+		float fx, fy; memcpy(&fx, &x, 4); memcpy(&fy, &y, 4);
+		if (fx != fy) return fx < fy;
+		return x > y;
+	});
+	for (size_t c = 0; c < 4096; c++) e->d2book_host[c] = c < vals.size() ? vals[c] : 0xFFFFFFFFu;
+	CK(e->d_d2book.reserve(4096));
+	CK(cudaMemcpyAsync(e->d_d2book.p, e->d2book_host, 4096 * 4, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	e->d2book_n = (uint32_t)vals.size();
+	return APO_OK;
+}
+}  // namespace
+
+extern "C" int apo_dims_d2book(apo_engine *e, uint32_t *d2book) {
+	if (!e || !d2book) return fail(e, APO_E_ARG, "NULL argument");
+	if (!e->compact) return fail(e, APO_E_STATE, "no compact (Form Q) evaluations loaded");
+	CK(cudaSetDevice(e->device));
+	const int rc = ensure_d2book(e);
+	if (rc) return rc;
+	memcpy(d2book, e->d2book_host, sizeof e->d2book_host);
+	return APO_OK;
+}
+
+extern "C" int apo_dims_packed_download(apo_engine *e, uint32_t *pc, uint16_t *pd, uint32_t c, uint64_t first, uint64_t n) {
+	if (!e || !pc || !pd) return fail(e, APO_E_ARG, "NULL argument");
+	if (!e->compact) return fail(e, APO_E_STATE, "no compact (Form Q) evaluations loaded");
+	if (c >= e->dims_C || first + n > e->dims_T) return fail(e, APO_E_ARG, "range outside the evaluations");
+	CK(cudaSetDevice(e->device));
+	int rc = ensure_d2book(e);
+	if (rc) return rc;
+	if (n == 0) return APO_OK;
+	CK(e->stage.reserve((n * 6 + 3) / 4 + 16));
+	uint32_t *dpc = (uint32_t *)e->stage.p;
+	unsigned short *dpd = (unsigned short *)(dpc + n);
+	uint32_t *bad = (uint32_t *)(e->stage.p + (n * 6 + 3) / 4 + 8);
+	CK(cudaMemsetAsync(bad, 0, 4, e->stream));
+	const uint64_t off = (uint64_t)c * e->dims_pitch + first;
+	CK(apo::run_pack_p(e->q8.p + off, e->qd2.p + off, e->qli.p + off, n, (const uint32_t *)e->d_d2book.p, e->d2book_n, dpc, dpd, bad, e->stream));
+	uint32_t hbad = 0;
+	CK(cudaMemcpyAsync(pc, dpc, n * 4, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaMemcpyAsync(pd, dpd, n * 2, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	if (hbad) return fail(e, APO_E_STATE, "a coded dimension takes more than 15 distinct values: not representable in Form P");
+	return APO_OK;
+}
+
+namespace {
 // Streams the three Form Q planes [C][T] (8 + 4 + 2 bytes per evaluation) through two device windows, H2D of chunk i+1
 // overlapped with K1q on chunk i — the host-streaming call for callers that hold the compact wire format (14 B / evaluation
 // over PCIe instead of 36).
+// Form P (pc / pd / d2book non-NULL): 6 B per evaluation cross PCIe and k_unpack_p expands each window to Form Q on the device.
 int score_host_compact_impl(apo_engine *e, const apo_score_opts *o, const uint64_t *q8, const float *d2, const uint16_t *li,
+                            const uint32_t *pc, const uint16_t *pd, const uint32_t *d2book,
                             const uint32_t *codebook, uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
                             apo_corpus_report *report) {
+	const bool packed = pc != nullptr;
 	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
-	if (!q8 || !d2 || !li || !codebook || C == 0) return fail(e, APO_E_ARG, "input is NULL or C == 0");
+	if (!codebook || C == 0 || (packed ? (!pd || !d2book) : (!q8 || !d2 || !li))) return fail(e, APO_E_ARG, "input is NULL or C == 0");
 	if (o->K > C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, C);
 	if (o->K > kMaxK) return fail(e, APO_E_ARG, "K=%u exceeds the supported beam width %u", o->K, kMaxK);
 	if (o->first || o->count) return fail(e, APO_E_ARG, "windows are not supported by the host-streaming calls");
@@ -1308,12 +1378,17 @@ int score_host_compact_impl(apo_engine *e, const apo_score_opts *o, const uint64
 	}
 	const int qv = e->q_pair_ok ? 0 : 4;
 	const int tile = apo::kq_tile_evals(qv);
-	uint64_t Tc = (256ull << 20) / ((uint64_t)C * 14);
+	const uint64_t wire = packed ? 6 : 14;
+	uint64_t Tc = (256ull << 20) / ((uint64_t)C * wire);
 	Tc = Tc / tile * tile;
 	if (Tc < (uint64_t)tile) Tc = tile;
 	if (Tc > round_up(T ? T : 1, tile)) Tc = round_up(T ? T : 1, tile);
-	for (int i = 0; i < 2; i++) CK(e->win[i].reserve((uint64_t)C * Tc * 14));
-	choose_timing(e, o, (uint64_t)C * T * 14);
+	for (int i = 0; i < 2; i++) CK(e->win[i].reserve((uint64_t)C * Tc * (packed ? 20 : 14)));
+	if (packed) {
+		CK(e->d_d2stream.reserve(4096));
+		CK(cudaMemcpyAsync(e->d_d2stream.p, d2book, 4096 * 4, cudaMemcpyHostToDevice, e->stream));   // bit patterns: unused slots are NaNs nobody reads
+	}
+	choose_timing(e, o, (uint64_t)C * T * wire);
 	if (peer_join_active(e, C)) e->join_epoch++;
 	if ((rc = begin_score(e, C))) return rc;
 	int nchunk = 0;
@@ -1324,12 +1399,23 @@ int score_host_compact_impl(apo_engine *e, const apo_score_opts *o, const uint64
 		unsigned long long *wq = (unsigned long long *)w;
 		float *wd = (float *)(w + (uint64_t)C * Tc * 8);
 		unsigned short *wl = (unsigned short *)(w + (uint64_t)C * Tc * 12);
+		uint32_t *wpc = (uint32_t *)(w + (uint64_t)C * Tc * 14);
+		unsigned short *wpd = (unsigned short *)(w + (uint64_t)C * Tc * 18);
 		if (nchunk >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->win_free[b], 0));
-		if ((rc = copy_rows_h2d(e, wq, Tc * 8, q8 + t0, T * 8, n * 8, C, e->copy_stream))) return rc;
-		if ((rc = copy_rows_h2d(e, wd, Tc * 4, d2 + t0, T * 4, n * 4, C, e->copy_stream))) return rc;
-		if ((rc = copy_rows_h2d(e, wl, Tc * 2, li + t0, T * 2, n * 2, C, e->copy_stream))) return rc;
+		if (packed) {
+			if ((rc = copy_rows_h2d(e, wpc, Tc * 4, pc + t0, T * 4, n * 4, C, e->copy_stream))) return rc;
+			if ((rc = copy_rows_h2d(e, wpd, Tc * 2, pd + t0, T * 2, n * 2, C, e->copy_stream))) return rc;
+		} else {
+			if ((rc = copy_rows_h2d(e, wq, Tc * 8, q8 + t0, T * 8, n * 8, C, e->copy_stream))) return rc;
+			if ((rc = copy_rows_h2d(e, wd, Tc * 4, d2 + t0, T * 4, n * 4, C, e->copy_stream))) return rc;
+			if ((rc = copy_rows_h2d(e, wl, Tc * 2, li + t0, T * 2, n * 2, C, e->copy_stream))) return rc;
+		}
 		CK(cudaEventRecord(e->win_ready[b], e->copy_stream));
 		CK(cudaStreamWaitEvent(e->stream, e->win_ready[b], 0));
+		if (packed) {
+			CK(apo::run_unpack_p(wpc, wpd, Tc, C, n, e->d_d2stream.p, wq, wd, wl, Tc, e->stream));
+			e->timing.launches++;
+		}
 		apo::KqParams Q{};
 		Q.q8 = wq; Q.d2 = wd; Q.li = wl; Q.pitch_evals = Tc; Q.C = C; Q.T = n;
 		Q.acc = e->acc.p; Q.lut = e->d_lut.p; Q.ptab = e->d_ptab.p; Q.w2 = e->W.w[2];
@@ -1358,7 +1444,17 @@ extern "C" int apo_score_host_compact(apo_engine *e, const apo_score_opts *o, co
                                       const uint32_t *codebook, uint32_t C, uint64_t T, double *scores, uint64_t *counts,
                                       int32_t *topk, apo_corpus_report *report) {
 	if (!e) return APO_E_ARG;
-	const int rc = score_host_compact_impl(e, o, q8, d2, li, codebook, C, T, scores, counts, topk, report);
+	const int rc = score_host_compact_impl(e, o, q8, d2, li, nullptr, nullptr, nullptr, codebook, C, T, scores, counts, topk, report);
+	if (rc) { cudaStreamSynchronize(e->copy_stream); cudaStreamSynchronize(e->stream); }
+	return rc;
+}
+
+extern "C" int apo_score_host_packed(apo_engine *e, const apo_score_opts *o, const uint32_t *pc, const uint16_t *pd, const uint32_t *codebook,
+                                     const uint32_t *d2book, uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
+                                     apo_corpus_report *report) {
+	if (!e) return APO_E_ARG;
+	if (!pc) return fail(e, APO_E_ARG, "input is NULL");
+	const int rc = score_host_compact_impl(e, o, nullptr, nullptr, nullptr, pc, pd, d2book, codebook, C, T, scores, counts, topk, report);
 	if (rc) { cudaStreamSynchronize(e->copy_stream); cudaStreamSynchronize(e->stream); }
 	return rc;
 }

@@ -122,6 +122,120 @@ cudaError_t run_recode(unsigned long long *q8, float *d2, unsigned short *li, ui
 	return cudaGetLastError();
 }
 
+// Form P -> Form Q on the device.  Form P is the tightest lossless wire format of the same evaluations for PCIe
+// (6 B instead of 14 B / 36 B): the eight coded dimensions as 4-bit codes in one uint32 (15 = absent; needs <= 15 distinct
+// values per dimension, true for dims produced by TCS:668-763) and tool_success_rate as a 12-bit index into a per-tensor
+// fp32 table (4095 = absent; <= 4095 distinct ratios).  Expansion runs at HBM speed right behind the H2D copy of a window.
+__global__ void __launch_bounds__(256)
+k_unpack_p(const uint32_t *pc, const unsigned short *pd, uint64_t pitch_in, uint32_t C, uint64_t T, const float *d2book,
+           unsigned long long *q8, float *d2, unsigned short *li, uint64_t pitch_out) {
+	__shared__ float s_d2[4096];
+	for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_d2[i] = d2book[i];
+	__syncthreads();
+	const uint32_t c = blockIdx.y;
+	if (c >= C) return;
+	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x) {
+		const uint32_t w = pc[(uint64_t)c * pitch_in + t];
+		const uint32_t k2 = pd[(uint64_t)c * pitch_in + t] & 4095u;
+		unsigned long long q = 0;
+		uint32_t mask = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const uint32_t nib = (w >> (4 * j)) & 15u;
+			const uint32_t code = nib == 15u ? 255u : nib;
+			q |= (unsigned long long)code << (8 * j);
+			mask |= (nib != 15u ? 1u : 0u) << (j < 2 ? j : j + 1);
+		}
+		const bool p2 = k2 != 4095u;
+		mask |= (p2 ? 1u : 0u) << 2;
+		const uint64_t o = (uint64_t)c * pitch_out + t;
+		q8[o] = q;
+		d2[o] = p2 ? s_d2[k2] : 0.0f;
+		li[o] = (unsigned short)lut_index(mask);
+	}
+}
+
+cudaError_t run_unpack_p(const uint32_t *pc, const unsigned short *pd, uint64_t pitch_in, uint32_t C, uint64_t T, const float *d2book,
+                         unsigned long long *q8, float *d2, unsigned short *li, uint64_t pitch_out, cudaStream_t st) {
+	if (C == 0 || T == 0) return cudaSuccess;
+	uint64_t gx = (T + 255) / 256;
+	if (gx > 148ull * 8) gx = 148ull * 8;
+	for (uint32_t cb = 0; cb < C; cb += 32768) {
+		const uint32_t cn = C - cb < 32768 ? C - cb : 32768;
+		k_unpack_p<<<dim3((unsigned)gx, cn), 256, 0, st>>>(pc + (uint64_t)cb * pitch_in, pd + (uint64_t)cb * pitch_in, pitch_in, cn, T, d2book,
+		                                                 q8 + (uint64_t)cb * pitch_out, d2 + (uint64_t)cb * pitch_out, li + (uint64_t)cb * pitch_out, pitch_out);
+	}
+	return cudaGetLastError();
+}
+
+// Form Q -> Form P (export of a resident tensor in the 6-byte wire format).  k_collect_d2 gathers the distinct
+// tool_success_rate bit patterns into a 16384-slot open-addressing set; the host sorts them into the d2book; k_pack_p then
+// writes the nibble word and the 12-bit index (binary search in the sorted book) per evaluation.
+__global__ void __launch_bounds__(256)
+k_collect_d2(const float *d2, const unsigned short *li, uint64_t n, uint32_t *table /* [16384], 0xFFFFFFFF = free */, uint32_t *count) {
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		if (!((li[i] >> 6) & 1u)) continue;                       // rotated index: dimension 2 lives in bit 6
+		const uint32_t bits = __float_as_uint(d2[i]);
+		uint32_t h = (bits * 2654435761u) >> 18;
+		for (int probe = 0; probe < 16384; probe++) {
+			const uint32_t cur = atomicCAS(&table[h], SLOT_EMPTY, bits);
+			if (cur == bits) break;
+			if (cur == SLOT_EMPTY) { atomicAdd(count, 1u); break; }
+			h = (h + 1) & 16383u;
+		}
+	}
+}
+
+__device__ __forceinline__ bool d2_less(uint32_t x, uint32_t y) {     // by value, -0.0 before +0.0 (the host's sort order)
+	const float fx = __uint_as_float(x), fy = __uint_as_float(y);
+	return fx != fy ? fx < fy : x > y;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_p(const unsigned long long *q8, const float *d2, const unsigned short *li, uint64_t n, const uint32_t *d2book, uint32_t nbook,
+         uint32_t *pc, unsigned short *pd, uint32_t *bad) {
+	__shared__ uint32_t s_book[4096];
+	for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_book[i] = d2book[i];
+	__syncthreads();
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		const unsigned long long q = q8[i];
+		uint32_t w = 0;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			const uint32_t code = (uint32_t)(q >> (8 * j)) & 255u;
+			if (code != 255u && code > 14u) *bad = 1u;                // more than 15 distinct values: not representable
+			w |= (code == 255u ? 15u : (code & 15u)) << (4 * j);
+		}
+		uint32_t k2 = 4095u;
+		if ((li[i] >> 6) & 1u) {
+			const uint32_t bits = __float_as_uint(d2[i]);
+			uint32_t lo = 0, hi = nbook;                              // first entry not less than bits
+			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (d2_less(s_book[mid], bits)) lo = mid + 1; else hi = mid; }
+			k2 = lo;
+			if (lo >= nbook || s_book[lo] != bits) *bad = 1u;
+		}
+		pc[i] = w;
+		pd[i] = (unsigned short)k2;
+	}
+}
+
+cudaError_t run_collect_d2(const float *d2, const unsigned short *li, uint64_t n, uint32_t *table, uint32_t *count, cudaStream_t st) {
+	if (n == 0) return cudaSuccess;
+	uint64_t g = (n + 255) / 256;
+	if (g > 148ull * 16) g = 148ull * 16;
+	k_collect_d2<<<(unsigned)g, 256, 0, st>>>(d2, li, n, table, count);
+	return cudaGetLastError();
+}
+
+cudaError_t run_pack_p(const unsigned long long *q8, const float *d2, const unsigned short *li, uint64_t n, const uint32_t *d2book, uint32_t nbook,
+                       uint32_t *pc, unsigned short *pd, uint32_t *bad, cudaStream_t st) {
+	if (n == 0) return cudaSuccess;
+	uint64_t g = (n + 255) / 256;
+	if (g > 148ull * 8) g = 148ull * 8;
+	k_pack_p<<<(unsigned)g, 256, 0, st>>>(q8, d2, li, n, d2book, nbook, pc, pd, bad);
+	return cudaGetLastError();
+}
+
 // Form Q -> Form D (tests, apo_dims_download)
 __global__ void __launch_bounds__(256)
 k_decode(const unsigned long long *q8, const float *d2, const unsigned short *li, uint64_t n, const uint32_t *codebook, float *out) {

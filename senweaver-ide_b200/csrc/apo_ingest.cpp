@@ -366,3 +366,90 @@ extern "C" int apo_compact_encode_host(const float *dims, uint32_t C, uint64_t T
 	});
 	return APO_OK;
 }
+
+// Form D -> Form P on the host (6 B / evaluation: a uint32 of eight 4-bit codes + a 12-bit tool_success_rate index, stored as
+// uint16): the PCIe wire format of apo_score_host_packed.  codebook as apo_compact_encode_host (<= 15 codes used per
+// dimension), d2book[4096] = the distinct fp32 values of dimension 2 ordered by value (unused = 0xFFFFFFFF).
+// APO_E_STATE when a coded dimension has more than 15 distinct values or dimension 2 more than 4095.
+extern "C" int apo_packed_encode_host(const float *dims, uint32_t C, uint64_t T, uint32_t *pc, uint16_t *pd,
+                                      uint32_t *codebook, uint32_t *d2book, int nthreads) {
+	if ((C && T && (!dims || !pc || !pd)) || !codebook || !d2book) return APO_E_ARG;
+	if (nthreads < 1) nthreads = 1;
+	if (nthreads > 256) nthreads = 256;
+	const uint64_t N = (uint64_t)C * T;
+	// ---- pass 1: distinct values (coded dimensions: tiny sets; dimension 2: a sorted vector per thread)
+	std::vector<DistinctSet> sets((size_t)nthreads * 8);
+	std::vector<std::vector<uint32_t>> d2sets((size_t)nthreads);
+	std::vector<int> too_many((size_t)nthreads, 0);
+	run_threads(nthreads, [&](int k, int n) {
+		DistinctSet *mine = &sets[(size_t)k * 8];
+		std::vector<uint32_t> &seen = d2sets[(size_t)k];
+		// open addressing over the bit patterns: dimension 2 has a few hundred distinct ratios at most
+		std::vector<uint32_t> table(16384, 0xFFFFFFFFu);
+		const uint64_t a = N * (uint64_t)k / (uint64_t)n, b = N * (uint64_t)(k + 1) / (uint64_t)n;
+		for (uint64_t i = a; i < b; i++) {
+			const float *row = dims + i * APO_NDIM;
+			for (int j = 0; j < 8; j++) { const float f = row[dim_of(j)]; if (f == f) mine[j].add(fbits(f)); }
+			const float f2 = row[2];
+			if (f2 == f2 && !too_many[(size_t)k]) {
+				const uint32_t bits = fbits(f2);
+				uint32_t h = (bits * 2654435761u) >> 18;
+				for (;;) {
+					if (table[h] == bits) break;
+					if (table[h] == 0xFFFFFFFFu) { table[h] = bits; seen.push_back(bits); if (seen.size() > 4095) too_many[(size_t)k] = 1; break; }
+					h = (h + 1) & 16383u;
+				}
+			}
+		}
+	});
+	std::vector<uint32_t> dense[8], d2all;
+	auto by_value = [](uint32_t x, uint32_t y) {
+		float fx, fy; memcpy(&fx, &x, 4); memcpy(&fy, &y, 4);
+		if (fx != fy) return fx < fy;
+		return x > y;
+	};
+	for (int j = 0; j < 8; j++) {
+		DistinctSet all;
+		for (int k = 0; k < nthreads; k++) {
+			const DistinctSet &st = sets[(size_t)k * 8 + j];
+			if (st.overflow) all.overflow = true;
+			for (int i = 0; i < st.n; i++) all.add(st.v[i]);
+		}
+		if (all.overflow || all.n > 15) return APO_E_STATE;
+		dense[j].assign(all.v, all.v + all.n);
+		std::sort(dense[j].begin(), dense[j].end(), by_value);
+		for (int c = 0; c < 256; c++) codebook[256 * j + c] = c < (int)dense[j].size() ? dense[j][c] : 0xFFFFFFFFu;
+	}
+	for (int k = 0; k < nthreads; k++) {
+		if (too_many[(size_t)k]) return APO_E_STATE;
+		d2all.insert(d2all.end(), d2sets[(size_t)k].begin(), d2sets[(size_t)k].end());
+	}
+	std::sort(d2all.begin(), d2all.end(), by_value);
+	d2all.erase(std::unique(d2all.begin(), d2all.end()), d2all.end());
+	if (d2all.size() > 4095) return APO_E_STATE;
+	for (size_t c = 0; c < 4096; c++) d2book[c] = c < d2all.size() ? d2all[c] : 0xFFFFFFFFu;
+	// ---- pass 2: encode
+	run_threads(nthreads, [&](int k, int n) {
+		const uint64_t a = N * (uint64_t)k / (uint64_t)n, b = N * (uint64_t)(k + 1) / (uint64_t)n;
+		for (uint64_t i = a; i < b; i++) {
+			const float *row = dims + i * APO_NDIM;
+			uint32_t w = 0;
+			for (int j = 0; j < 8; j++) {
+				const float f = row[dim_of(j)];
+				uint32_t code = 15u;
+				if (f == f) {
+					const uint32_t bits = fbits(f);
+					const std::vector<uint32_t> &dv = dense[j];
+					for (uint32_t c = 0; c < dv.size(); c++) if (dv[c] == bits) { code = c; break; }
+				}
+				w |= code << (4 * j);
+			}
+			const float f2 = row[2];
+			uint16_t k2 = 4095;
+			if (f2 == f2) k2 = (uint16_t)(std::lower_bound(d2all.begin(), d2all.end(), fbits(f2), by_value) - d2all.begin());
+			pc[i] = w;
+			pd[i] = k2;
+		}
+	});
+	return APO_OK;
+}

@@ -133,6 +133,11 @@ cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cuda
 cudaError_t run_transcode(const float *dims, uint64_t pitch_in, uint32_t C, uint64_t T, unsigned long long *q8, float *d2,
                           uint64_t pitch_out, uint32_t *codebook, uint32_t *overflow, cudaStream_t st);
 cudaError_t run_recode(unsigned long long *q8, float *d2, unsigned short *li, uint64_t n, const uint8_t *remap, cudaStream_t st);
+cudaError_t run_unpack_p(const uint32_t *pc, const unsigned short *pd, uint64_t pitch_in, uint32_t C, uint64_t T, const float *d2book,
+                         unsigned long long *q8, float *d2, unsigned short *li, uint64_t pitch_out, cudaStream_t st);
+cudaError_t run_collect_d2(const float *d2, const unsigned short *li, uint64_t n, uint32_t *table, uint32_t *count, cudaStream_t st);
+cudaError_t run_pack_p(const unsigned long long *q8, const float *d2, const unsigned short *li, uint64_t n, const uint32_t *d2book, uint32_t nbook,
+                       uint32_t *pc, unsigned short *pd, uint32_t *bad, cudaStream_t st);
 cudaError_t run_decode(const unsigned long long *q8, const float *d2, const unsigned short *li, uint64_t n, const uint32_t *codebook, float *out, cudaStream_t st);
 
 int k1_tile_evals(int row, int variant);

@@ -90,7 +90,7 @@ ABI_SYMBOLS = (
     "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_rollouts16_upload",
     "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_duration_class", "apo_score",
     "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records", "apo_score_host_compact", "apo_compact_encode_host",
-    "apo_dims_compact_download", "apo_dims_codebook", "apo_host_alloc", "apo_host_free",
+    "apo_dims_compact_download", "apo_dims_codebook", "apo_packed_encode_host", "apo_score_host_packed", "apo_dims_packed_download", "apo_dims_d2book", "apo_host_alloc", "apo_host_free",
     "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy", "apo_comm_join_mode",
 )
 
@@ -162,6 +162,10 @@ def load_library() -> C.CDLL:
     L.apo_score_host.argtypes = [vp, C.POINTER(ScoreOpts), vp, u32, u64, vp, vp, vp, vp]
     L.apo_score_host_compact.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp, u32, u64, vp, vp, vp, vp]
     L.apo_compact_encode_host.argtypes = [vp, u32, u64, vp, vp, vp, vp, i32]
+    L.apo_packed_encode_host.argtypes = [vp, u32, u64, vp, vp, vp, vp, i32]
+    L.apo_dims_packed_download.argtypes = [vp, vp, vp, u32, u64, u64]
+    L.apo_dims_d2book.argtypes = [vp, vp]
+    L.apo_score_host_packed.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp, u32, u64, vp, vp, vp, vp]
     L.apo_dims_compact_download.argtypes = [vp, vp, vp, vp, u32, u64, u64]
     L.apo_dims_codebook.argtypes = [vp, vp]
     L.apo_last_timing.argtypes = [vp, C.POINTER(Timing)]
@@ -463,6 +467,33 @@ class Engine:
                                                 _p(topk), C.byref(rep) if rep is not None else None))
         return ScoreResult(scores, counts, topk, rep, self.last_timing())
 
+    def dims_d2book(self) -> np.ndarray:
+        out = np.empty(4096, np.uint32)
+        self._ck(self._L.apo_dims_d2book(self._h, _p(out)))
+        return out
+
+    def dims_packed_download(self, c: int, first: int, n: int, out=None):
+        """(pc u32[n], pd u16[n]) of candidate c of the resident compact tensor, in the 6-byte wire format."""
+        pc, pd = out if out is not None else (np.empty(n, np.uint32), np.empty(n, np.uint16))
+        self._ck(self._L.apo_dims_packed_download(self._h, _p(pc), _p(pd), c, first, n))
+        return pc, pd
+
+    def score_host_packed(self, pc: np.ndarray, pd: np.ndarray, codebook: np.ndarray, d2book: np.ndarray, K: int, corpus: bool = False,
+                          recip: bool = False) -> ScoreResult:
+        """Form P: pc uint32 [C][T] (eight 4-bit codes), pd uint16 [C][T] (tool_success_rate index) + the two codebooks."""
+        assert pc.dtype == np.uint32 and pd.dtype == np.uint16 and pc.shape == pd.shape and pc.ndim == 2 and pc.flags.c_contiguous and pd.flags.c_contiguous
+        codebook, d2book = np.ascontiguousarray(codebook, np.uint32), np.ascontiguousarray(d2book, np.uint32)
+        assert codebook.size == 2048 and d2book.size == 4096
+        Cn, T = pc.shape
+        o = self._opts(K, SRC_DIMS, corpus, recip, 0, 0, 0)
+        scores = np.empty(Cn, np.float64)
+        counts = np.empty(Cn, np.uint64)
+        topk = np.empty(K, np.int32)
+        rep = CorpusReport() if corpus else None
+        self._ck(self._L.apo_score_host_packed(self._h, C.byref(o), _p(pc), _p(pd), _p(codebook), _p(d2book), Cn, T, _p(scores), _p(counts),
+                                               _p(topk), C.byref(rep) if rep is not None else None))
+        return ScoreResult(scores, counts, topk, rep, self.last_timing())
+
     def last_timing(self) -> Timing:
         t = Timing()
         self._ck(self._L.apo_last_timing(self._h, C.byref(t)))
@@ -511,6 +542,21 @@ def compact_encode_host(dims: np.ndarray, nthreads: int = 8):
     if rc != 0:
         raise ApoError(rc, "evaluations are not categorical: a coded dimension has more than 255 distinct values" if rc == -3 else "bad argument")
     return q8, d2, li, book
+
+
+def packed_encode_host(dims: np.ndarray, nthreads: int = 8, out=None):
+    """Form D float32 [C][T][9] -> (pc, pd, codebook, d2book): the 6-byte wire format (apo_packed_encode_host).  out=(pc, pd)
+    fills existing (pinned) buffers.  Raises ApoError(APO_E_STATE) when the data does not fit 4-bit / 12-bit codes."""
+    L = load_library()
+    dims = np.ascontiguousarray(dims, np.float32)
+    Cn, T, nd = dims.shape
+    assert nd == NDIM
+    pc, pd = out if out is not None else (np.empty((Cn, T), np.uint32), np.empty((Cn, T), np.uint16))
+    book, d2book = np.empty(8 * 256, np.uint32), np.empty(4096, np.uint32)
+    rc = L.apo_packed_encode_host(_p(dims), Cn, T, _p(pc), _p(pd), _p(book), _p(d2book), nthreads)
+    if rc != 0:
+        raise ApoError(rc, "evaluations do not fit the 4-bit / 12-bit codes of Form P" if rc == -3 else "bad argument")
+    return pc, pd, book, d2book
 
 
 def pack16(recs: np.ndarray) -> np.ndarray:

@@ -85,3 +85,24 @@ def test_compact_host_encoder_is_lossless(apo, orc):
     assert np.array_equal(li, (((mask >> 5) | (mask << 4)) & 511).astype(np.uint16))
     one = apo.compact_encode_host(dims, nthreads=1)
     assert all(np.array_equal(x, y) for x, y in zip(one, (q8, d2, li, book.reshape(-1))))      # thread count does not matter
+
+
+def test_packed_host_encoder_is_lossless(apo, orc):
+    """apo_packed_encode_host (host-format code, no GPU): nibble j of pc indexes codebook[j], pd indexes d2book; decoding
+    returns the fp32 bit patterns of Form D; 15 / 4095 mean absent; any thread count gives the same bytes."""
+    import numpy as np
+    dims = orc.gen_dims(0x5EED00CA, 1, 4, 50, 30_011, 350, 4)
+    pc, pd, book, d2book = apo.packed_encode_host(dims, nthreads=3)
+    book = book.reshape(8, 256)
+    for j, dim in enumerate([0, 1, 3, 4, 5, 6, 7, 8]):
+        code = ((pc >> np.uint32(4 * j)) & np.uint32(15)).astype(np.int64)
+        absent = np.isnan(dims[:, :, dim])
+        assert np.array_equal(code == 15, absent)
+        assert np.array_equal(book[j][np.where(absent, 0, code)][~absent], dims[:, :, dim][~absent].view(np.uint32))
+    a2 = np.isnan(dims[:, :, 2])
+    assert np.array_equal(pd == 4095, a2)
+    assert np.array_equal(d2book[np.where(a2, 0, pd.astype(np.int64))][~a2], dims[:, :, 2][~a2].view(np.uint32))
+    used = d2book[d2book != 0xFFFFFFFF].view(np.float32)
+    assert np.all(np.diff(used) >= 0) and len(used) < 4095
+    one = apo.packed_encode_host(dims, nthreads=1)
+    assert all(np.array_equal(x, y) for x, y in zip(one, (pc, pd, book.reshape(-1), d2book)))

@@ -175,3 +175,46 @@ def test_host_compact_wire_format_streams_to_the_same_integers(engine, orc, apo)
     noisy[0, :300, 3] = np.linspace(-1, 1, 300, dtype=np.float32)
     with pytest.raises(apo.ApoError):
         apo.compact_encode_host(noisy)
+
+
+def test_packed_wire_format_six_bytes_per_evaluation(engine, orc, apo):
+    """Form P (6 B / evaluation): the host encoder and the device export of a resident tensor agree bit for bit, streaming it
+    (apo_score_host_packed: H2D -> k_unpack_p -> K1q) gives the integers of the Form D tensor, and data that does not fit the
+    4-bit / 12-bit codes is refused."""
+    seed, C, T = 0x5EED00C9, 7, 120_007
+    dims = orc.gen_dims(seed, 3, C, 1000, T, 400, 8)
+    exp = orc.score_dims_fx(dims)
+    pc, pd, book, d2book = apo.packed_encode_host(dims, nthreads=4)
+    engine.dims_upload_compact(dims)
+    assert np.array_equal(engine.dims_codebook(), book) and np.array_equal(engine.dims_d2book(), d2book)
+    for c in (0, 3, 6):
+        a, b = engine.dims_packed_download(c, 0, T)
+        assert np.array_equal(a, pc[c]) and np.array_equal(b, pd[c])
+    a, b = engine.dims_packed_download(2, 5000, 4097)                     # a window
+    assert np.array_equal(a, pc[2, 5000:9097]) and np.array_equal(b, pd[2, 5000:9097])
+    recs = orc.gen_records(seed, orc.STREAM_CORPUS, 0, 1, 0, 20_000, 300, 8).reshape(-1)
+    engine.corpus_upload(recs)
+    ref = engine.score(C, 3)
+    r = engine.score_host_packed(pc, pd, book, d2book, 3, corpus=True)
+    assert engine.debug_partials(C) == exp
+    assert np.array_equal(r.scores, ref.scores) and np.array_equal(r.topk, ref.topk) and r.report.bad == orc.report(recs).bad
+    assert r.timing.launches >= 3                                          # unpack + K1q per window, then the corpus scan / finalize
+    ppc, ppd = apo.host_empty(pc.shape, np.uint32), apo.host_empty(pd.shape, np.uint16)
+    ppc[:], ppd[:] = pc, pd
+    engine.score_host_packed(ppc, ppd, book, d2book, 3)
+    assert engine.debug_partials(C) == exp
+    engine.score(C, 1)                                                     # the resident tensor is untouched by the streaming calls
+    assert engine.debug_partials(C) == exp
+    # 16 distinct values in a coded dimension: Form Q still works, Form P refuses (encoder and export)
+    wide = dims.copy()
+    wide[0, :16, 4] = np.arange(16, dtype=np.float32) / 32
+    with pytest.raises(apo.ApoError):
+        apo.packed_encode_host(wide)
+    engine.dims_upload_compact(wide)
+    with pytest.raises(apo.ApoError):
+        engine.dims_packed_download(0, 0, 100)
+    # more than 4095 distinct tool_success_rate values
+    many = dims.copy()
+    many[1, :5000, 2] = np.linspace(-1, 1, 5000, dtype=np.float32)
+    with pytest.raises(apo.ApoError):
+        apo.packed_encode_host(many)

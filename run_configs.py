@@ -130,14 +130,32 @@ def main():
                 gen_s += time.perf_counter() - g0
                 eng.score_accumulate(c0)
                 passes += 1
+            # every rank has finished its passes before the join is timed: the skew of the per-pass generation (seconds) is not the join's
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             r = eng.score_finish(C, 256)
             k1 = r.timing.reward_ms
             gbs = 36.0 * C * T / (k1 * 1e-3) / 1e9
-            join = r.timing.allreduce_ms + r.timing.finalize_ms + r.timing.corpus_ms
+            join = r.timing.allreduce_ms + r.timing.finalize_ms + r.timing.corpus_ms       # finalize_ms = peer-memory join + K3 in one launch (or NCCL + K3)
+            # parity: three whole candidates over the full 100 M-record axis against the oracle's exact integer sums (joined over all ranks
+            # on the engine side), and the ranking must follow from the exact sums
+            sums, counts = eng.debug_partials(C)
+            exact = None
+            if rank == 0:
+                import oracle
+                oracle.build()
+                cl = [0, C // 2 - 1, C - 1]
+                es, en = oracle.score_generated_fx(seed, cl, 0, Tg, 300, nthreads=min(16, len(os.sched_getaffinity(0))))
+                exact = all(sums[c] == a and counts[c] == b for c, a, b in zip(cl, es, en))
+            exp_scores = pkg.sharding.scores_from_partials(sums, counts)
+            topk_ok = bool(np.array_equal(pkg.sharding.topk_indices(exp_scores, 256), r.topk) and np.array_equal(exp_scores, r.scores))
             emit({"config": 5, "C": C, "T_global": Tg, "T_per_gpu": T, "n_gpus": world, "chunk_candidates": Cc, "passes": passes,
-                  "k1_ms_sum": k1, "join_ms": join, "evals_per_s_kernels": C * Tg / ((k1 + join) * 1e-3),
+                  "k1_ms_sum": k1, "join_ms": join, "join_wait_ms": r.timing.join_wait_ms, "join_reduce_ms": r.timing.join_reduce_ms,
+                  "join_mode": eng.comm_join_mode(), "evals_per_s_kernels": C * Tg / ((k1 + join) * 1e-3),
                   "k1_GBps_per_gpu": gbs, "frac_of_measured_peak": gbs / PK, "generation_s_excluded": gen_s,
-                  "topk_head": r.topk[:4].tolist(), "counts_ok": bool((r.counts > 0).all())})
+                  "topk_head": r.topk[:4].tolist(), "counts_ok": bool((r.counts > 0).all()),
+                  "parity": {"partials_exact_full_axis": exact, "candidates": [0, C // 2 - 1, C - 1], "topk_follows_from_exact_sums": topk_ok}})
     eng.close()
     if world > 1:
         dist.destroy_process_group()

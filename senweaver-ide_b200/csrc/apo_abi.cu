@@ -1169,7 +1169,13 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	const double k1_ms = stream_bytes / (o->source == APO_SRC_DIMS && e->compact ? e->stream_q_bytes_per_ms : e->stream_bytes_per_ms);
 	const double scan_ms = (double)e->corpus_T * e->scan_ms_per_record;
 	const bool one_launch = e->nranks == 1 || peer_join_active(e, C);
-	const bool fuse = wants_corpus(e, o) && count > 0 && !e->env_no_fuse && (k1_ms > 1.3 * scan_ms || e->env_force_fuse);
+	// ... or when it is tiny anyway (the IDE's real corpora, <= 1000 traces): at most 16 records per lane of the corpus warps,
+	// a few microseconds, against a second launch
+	const int tile_evals = (o->source == APO_SRC_DIMS && e->compact) ? apo::kq_tile_evals((int)o->variant) : apo::k1_tile_evals((int)row_bytes, (int)o->variant);
+	const uint64_t tiles = (uint64_t)C * ((count + (uint64_t)tile_evals - 1) / (uint64_t)tile_evals);
+	const uint64_t ctas = tiles < (uint64_t)e->sm_count ? tiles : (uint64_t)e->sm_count;
+	const bool small_scan = e->corpus_T <= 16ull * 32ull * ctas;
+	const bool fuse = wants_corpus(e, o) && count > 0 && !e->env_no_fuse && (k1_ms > 1.3 * scan_ms || small_scan || e->env_force_fuse);
 	// without a corpus request the same tail still saves the K3 launch: an empty scan, then the last CTA finalises
 	const bool tail_only = !wants_corpus(e, o) && one_launch && count > 0 && !e->env_no_fuse;
 	if (fuse || tail_only) {

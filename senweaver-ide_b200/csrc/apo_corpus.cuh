@@ -43,6 +43,147 @@ __device__ __forceinline__ uint32_t field_sum(unsigned long long pk, int f) {
 }
 
 
+// Per-thread accumulators of the corpus scan between two flushes (<= K2_CHUNK records).
+struct ScanAcc {
+	unsigned long long mTot, mGood, mBad;                    // 5 modes x 12 bits       (APO:519-525)
+	unsigned long long c01a, c01b;                            // (fb + 3*err) x 10 bits, endTime unset / set
+	unsigned long long c3, c4, c5, c7, c8;                    // 5 slots x 12 bits, slot 4 = not pushed
+	unsigned long long c6;                                    // 7 slots x 9 bits, slot 6 = not pushed
+	unsigned long long pat;                                   // 6 patterns x 10 bits
+	unsigned long long tool[3];
+	long long fxR, fxD2;
+	uint32_t nValid;
+	__device__ __forceinline__ void zero() {
+		mTot = mGood = mBad = c01a = c01b = c3 = c4 = c5 = c7 = c8 = c6 = pat = 0ull;
+		tool[0] = tool[1] = tool[2] = 0ull; fxR = fxD2 = 0ll; nValid = 0u;
+	}
+};
+
+// One record of the corpus: tallies, the weighted reward and the per-dimension census, the six 'bad'-gated predicates
+// (APO:509-538, 550-565, 644-755).  gi = global index of the record.  ROT: LUT stored at the bank-rotated index.
+template <bool ROT>
+__device__ __forceinline__ void scan_record(ScanAcc &A, const apo_record &r, unsigned long long gi, unsigned long long *s_ex,
+                                            const double *s_cat, const double2 *s_lut, double w2) {
+	const bool good = r.feedback == 1, bad = r.feedback == 2;
+	const uint32_t msh = 12u * (r.mode < APO_NMODE ? r.mode : 0u);               // APO:627-633
+	A.mTot += 1ull << msh; A.mGood += (unsigned long long)good << msh; A.mBad += (unsigned long long)bad << msh;
+	A.tool[0] += r.toolCalls; A.tool[1] += r.toolSucc; A.tool[2] += r.toolFail;  // TCS:603-605
+
+	if (r.flags & APO_F_VALID) {                                                 // APO:550, TCS:606
+		double ws; CatIdx ix;
+		const uint32_t mask = record_ws_table_t<true>(r, w2, s_cat, ws, ix);
+		const double2 tw = s_lut[ROT ? lut_index(mask) : mask];
+		if (tw.x > 0.0) {                                                        // TCS:784 totalWeight > 0
+			A.fxR += to_fx(div_lut<false>(ws, tw));
+			A.nValid++;
+			const unsigned long long one01 = 1ull << (10u * (ix.i01 % 6u));
+			if (ix.i01 >= 6u) A.c01b += one01; else A.c01a += one01;
+			A.c3 += 1ull << (12u * ix.i3); A.c4 += 1ull << (12u * ix.i4); A.c5 += 1ull << (12u * ix.i5);
+			A.c6 += 1ull << (9u * ix.i6); A.c7 += 1ull << (12u * ix.i7); A.c8 += 1ull << (12u * ix.i8);
+			A.fxD2 += to_fx(ix.d2);                                              // +0.0 when not pushed
+		}
+	}
+	if (bad) {                                                                   // APO:644-755: every predicate ANDs 'bad'
+		const unsigned long long gk = ~gi;                                       // inverted index (see ex_insert)
+		const bool hit[APO_NPAT] = {
+		    (r.flags & APO_F_ERRORS) != 0,       // P1 APO:644
+		    (r.flags & APO_F_FAILSPAN) != 0,     // P2 APO:666-670
+		    r.tokens > 10000u,                   // P3 APO:693
+		    r.llmCalls > 2u,                     // P4 APO:713
+		    r.userMsgs >= 4u,                    // P5 APO:733-734
+		    (r.durClass & APO_DC_SET) ? (r.durClass & APO_DC_SLOW) != 0 : (double)r.toolDurMs > 15000.0,   // P6 APO:754
+		};
+#pragma unroll
+		for (int p = 0; p < APO_NPAT; p++) {
+			if (hit[p]) {
+				A.pat += 1ull << (10 * p);
+				// slice(0,3): first three in corpus order
+				if (gk > *((volatile unsigned long long *)&s_ex[3 * p + 2])) ex_insert(&s_ex[3 * p], gk);
+			}
+		}
+	}
+}
+
+// Flush one chunk: warp-reduce every field, lane 0 turns counts into exact sums.  Full-warp collective.
+__device__ __forceinline__ void scan_flush(const ScanAcc &A, long long *corp, int lane) {
+	uint32_t good = 0, badn = 0, total = 0;
+#pragma unroll
+	for (int m = 0; m < APO_NMODE; m++) {
+		const uint32_t a = field_sum<12>(A.mTot, m), g = field_sum<12>(A.mGood, m), b = field_sum<12>(A.mBad, m);
+		if (lane == 0) {
+			if (a) atomicAdd((unsigned long long *)corp + CORP_MODE + 3 * m, (unsigned long long)a);
+			if (g) atomicAdd((unsigned long long *)corp + CORP_MODE + 3 * m + 1, (unsigned long long)g);
+			if (b) atomicAdd((unsigned long long *)corp + CORP_MODE + 3 * m + 2, (unsigned long long)b);
+		}
+		total += a; good += g; badn += b;
+	}
+	if (lane == 0) {                                                                 // APO:513-516
+		if (good) atomicAdd((unsigned long long *)corp + CORP_TALLY, (unsigned long long)good);
+		if (badn) atomicAdd((unsigned long long *)corp + CORP_TALLY + 1, (unsigned long long)badn);
+		if (total - good - badn) atomicAdd((unsigned long long *)corp + CORP_TALLY + 2, (unsigned long long)(total - good - badn));
+	}
+#pragma unroll
+	for (int p = 0; p < APO_NPAT; p++) {
+		const uint32_t n = field_sum<10>(A.pat, p);
+		if (lane == 0 && n) atomicAdd((unsigned long long *)corp + CORP_PAT + p, (unsigned long long)n);
+	}
+#pragma unroll
+	for (int i = 0; i < 3; i++) {
+		const unsigned long long s = warp_sum_u64(A.tool[i]);
+		if (lane == 0 && s) atomicAdd((unsigned long long *)corp + CORP_TOOL + i, s);
+	}
+	{   // finalReward sum and count (APO:550-553)
+		Acc128 a; a.lo = (unsigned long long)A.fxR; a.hi = A.fxR >> 63;
+		flush_acc128(a, corp + CORP_REWARD, lane);
+		Acc128 b; b.lo = (unsigned long long)A.fxD2; b.hi = A.fxD2 >> 63;
+		flush_acc128(b, corp + CORP_DIM + 4 * 2, lane);
+	}
+	const uint32_t nv = warp_sum_u32(A.nValid);
+	// d0 / d1 from the (feedback, hasErrors, endTime) census: TCS:677-691
+	__int128 s0 = 0, s1 = 0;
+#pragma unroll
+	for (int ended = 0; ended < 2; ended++)
+#pragma unroll
+		for (int err = 0; err < 2; err++)
+#pragma unroll
+			for (int fb = 0; fb < 3; fb++) {
+				const uint32_t n = field_sum<10>(ended ? A.c01b : A.c01a, fb + 3 * err);
+				const double d0 = fb == 1 ? 1.0 : (fb == 2 ? -1.0 : 0.0);
+				const double d1 = fb == 1 ? 1.0 : (err ? -0.5 : (ended ? 0.8 : 0.5));
+				s0 += (__int128)n * to_fx(d0);
+				s1 += (__int128)n * to_fx(d1);
+			}
+	const double lv_rel[4] = {1.0, -0.2, -0.5, -1.0}, lv_cnt[4] = {1.0, 0.3, -0.3, -0.8}, lv_dur[4] = {1.0, 0.5, 0.0, -0.5};
+	__int128 s3 = 0, s4 = 0, s5 = 0, s7 = 0, s8 = 0, s6 = 0;
+	uint32_t n3 = 0, n5 = 0, n6 = 0, n7 = 0, n8 = 0;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const uint32_t a3 = field_sum<12>(A.c3, k), a4 = field_sum<12>(A.c4, k), a5 = field_sum<12>(A.c5, k);
+		const uint32_t a7 = field_sum<12>(A.c7, k), a8 = field_sum<12>(A.c8, k);
+		s3 += (__int128)a3 * to_fx(lv_rel[k]); s4 += (__int128)a4 * to_fx(lv_cnt[k]); s5 += (__int128)a5 * to_fx(lv_dur[k]);
+		s7 += (__int128)a7 * to_fx(lv_dur[k]); s8 += (__int128)a8 * to_fx(lv_cnt[k]);
+		n3 += a3; n5 += a5; n7 += a7; n8 += a8;
+	}
+#pragma unroll
+	for (int k = 0; k < 6; k++) {                                                    // TCS:735: max(-1, 1 - k*0.4)
+		const uint32_t a6 = field_sum<9>(A.c6, k);
+		double ef = __dadd_rn(1.0, -__dmul_rn((double)k, 0.4));
+		ef = ef < -1.0 ? -1.0 : ef;
+		s6 += (__int128)a6 * to_fx(ef);
+		n6 += a6;
+	}
+	if (lane == 0) {
+		const __int128 sums[APO_NDIM] = {s0, s1, 0, s3, s4, s5, s6, s7, s8};
+		const uint32_t cnts[APO_NDIM] = {nv, nv, n3, n3, n3, n5, n6, n7, n8};            // d2,d3,d4 are pushed together (TCS:695)
+#pragma unroll
+		for (int i = 0; i < APO_NDIM; i++) {
+			if (i != 2) add_i128(corp + CORP_DIM + 4 * i, sums[i]);
+			if (cnts[i]) atomicAdd((unsigned long long *)corp + CORP_DIM + 4 * i + 3, (unsigned long long)cnts[i]);
+		}
+		if (nv) atomicAdd((unsigned long long *)corp + CORP_REWARD + 3, (unsigned long long)nv);
+	}
+}
+
 // One warp's share of the corpus: records t = first + lane, first + lane + stride, ...  All 32 lanes stay
 // in the loop together (full-warp collectives in the flush).  s_ex: 18 shared-memory slots (first three
 // matches of each pattern as inverted indices, 0 = empty) shared by the caller's warps; s_cat / s_lut: the categorical
@@ -58,139 +199,16 @@ __device__ __forceinline__ void corpus_scan_warp(const K2Params &P, uint64_t fir
 	const uint64_t rounds = (per_lane + K2_CHUNK - 1) / K2_CHUNK;
 
 	for (uint64_t round = 0; round < rounds; round++) {
-		unsigned long long mTot = 0, mGood = 0, mBad = 0;        // 5 modes x 12 bits       (APO:519-525)
-		unsigned long long c01a = 0, c01b = 0;                    // (fb + 3*err) x 10 bits, endTime unset / set
-		unsigned long long c3 = 0, c4 = 0, c5 = 0, c7 = 0, c8 = 0; // 5 slots x 12 bits, slot 4 = not pushed
-		unsigned long long c6 = 0;                                // 7 slots x 9 bits, slot 6 = not pushed
-		unsigned long long pat = 0;                               // 6 patterns x 10 bits
-		unsigned long long tool[3] = {0, 0, 0};
-		long long fxR = 0, fxD2 = 0;
-		uint32_t nValid = 0;
-
+		ScanAcc A; A.zero();
 		// software pipeline: the next record of this thread is in flight while the current one is scored
 		union Rec { uint4 q[2]; apo_record r; } nxt;
 		if (t < P.T) { nxt.q[0] = __ldg(src + 2 * t); nxt.q[1] = __ldg(src + 2 * t + 1); }
 		for (int it = 0; it < K2_CHUNK && t < P.T; it++, t += stride) {
 			Rec u = nxt;
 			if (it + 1 < K2_CHUNK && t + stride < P.T) { nxt.q[0] = __ldg(src + 2 * (t + stride)); nxt.q[1] = __ldg(src + 2 * (t + stride) + 1); }
-			const apo_record &r = u.r;
-			const bool good = r.feedback == 1, bad = r.feedback == 2;
-			const uint32_t msh = 12u * (r.mode < APO_NMODE ? r.mode : 0u);               // APO:627-633
-			mTot += 1ull << msh; mGood += (unsigned long long)good << msh; mBad += (unsigned long long)bad << msh;
-			tool[0] += r.toolCalls; tool[1] += r.toolSucc; tool[2] += r.toolFail;       // TCS:603-605
-
-			if (r.flags & APO_F_VALID) {                                                 // APO:550, TCS:606
-				double ws; CatIdx ix;
-				const uint32_t mask = record_ws_table_t<true>(r, w2, s_cat, ws, ix);
-				const double2 tw = s_lut[ROT ? lut_index(mask) : mask];
-				if (tw.x > 0.0) {                                                        // TCS:784 totalWeight > 0
-					fxR += to_fx(div_lut<false>(ws, tw));
-					nValid++;
-					const unsigned long long one01 = 1ull << (10u * (ix.i01 % 6u));
-					if (ix.i01 >= 6u) c01b += one01; else c01a += one01;
-					c3 += 1ull << (12u * ix.i3); c4 += 1ull << (12u * ix.i4); c5 += 1ull << (12u * ix.i5);
-					c6 += 1ull << (9u * ix.i6); c7 += 1ull << (12u * ix.i7); c8 += 1ull << (12u * ix.i8);
-					fxD2 += to_fx(ix.d2);                                                // +0.0 when not pushed
-				}
-			}
-			if (bad) {                                                                   // APO:644-755: every predicate ANDs 'bad'
-				const unsigned long long gk = ~(P.idx_base + t);                         // inverted index (see ex_insert)
-				const bool hit[APO_NPAT] = {
-				    (r.flags & APO_F_ERRORS) != 0,       // P1 APO:644
-				    (r.flags & APO_F_FAILSPAN) != 0,     // P2 APO:666-670
-				    r.tokens > 10000u,                   // P3 APO:693
-				    r.llmCalls > 2u,                     // P4 APO:713
-				    r.userMsgs >= 4u,                    // P5 APO:733-734
-				    (r.durClass & APO_DC_SET) ? (r.durClass & APO_DC_SLOW) != 0 : (double)r.toolDurMs > 15000.0,   // P6 APO:754
-				};
-#pragma unroll
-				for (int p = 0; p < APO_NPAT; p++) {
-					if (hit[p]) {
-						pat += 1ull << (10 * p);
-						// slice(0,3): first three in corpus order
-						if (gk > *((volatile unsigned long long *)&s_ex[3 * p + 2])) ex_insert(&s_ex[3 * p], gk);
-					}
-				}
-			}
+			scan_record<ROT>(A, u.r, P.idx_base + t, s_ex, s_cat, s_lut, w2);
 		}
-
-		// ---- flush this chunk: warp-reduce every field, lane 0 turns counts into exact sums
-		uint32_t good = 0, badn = 0, total = 0;
-#pragma unroll
-		for (int m = 0; m < APO_NMODE; m++) {
-			const uint32_t a = field_sum<12>(mTot, m), g = field_sum<12>(mGood, m), b = field_sum<12>(mBad, m);
-			if (lane == 0) {
-				if (a) atomicAdd((unsigned long long *)corp + CORP_MODE + 3 * m, (unsigned long long)a);
-				if (g) atomicAdd((unsigned long long *)corp + CORP_MODE + 3 * m + 1, (unsigned long long)g);
-				if (b) atomicAdd((unsigned long long *)corp + CORP_MODE + 3 * m + 2, (unsigned long long)b);
-			}
-			total += a; good += g; badn += b;
-		}
-		if (lane == 0) {                                                                 // APO:513-516
-			if (good) atomicAdd((unsigned long long *)corp + CORP_TALLY, (unsigned long long)good);
-			if (badn) atomicAdd((unsigned long long *)corp + CORP_TALLY + 1, (unsigned long long)badn);
-			if (total - good - badn) atomicAdd((unsigned long long *)corp + CORP_TALLY + 2, (unsigned long long)(total - good - badn));
-		}
-#pragma unroll
-		for (int p = 0; p < APO_NPAT; p++) {
-			const uint32_t n = field_sum<10>(pat, p);
-			if (lane == 0 && n) atomicAdd((unsigned long long *)corp + CORP_PAT + p, (unsigned long long)n);
-		}
-#pragma unroll
-		for (int i = 0; i < 3; i++) {
-			const unsigned long long s = warp_sum_u64(tool[i]);
-			if (lane == 0 && s) atomicAdd((unsigned long long *)corp + CORP_TOOL + i, s);
-		}
-		{   // finalReward sum and count (APO:550-553)
-			Acc128 a; a.lo = (unsigned long long)fxR; a.hi = fxR >> 63;
-			flush_acc128(a, corp + CORP_REWARD, lane);
-			Acc128 b; b.lo = (unsigned long long)fxD2; b.hi = fxD2 >> 63;
-			flush_acc128(b, corp + CORP_DIM + 4 * 2, lane);
-		}
-		const uint32_t nv = warp_sum_u32(nValid);
-		// d0 / d1 from the (feedback, hasErrors, endTime) census: TCS:677-691
-		__int128 s0 = 0, s1 = 0;
-#pragma unroll
-		for (int ended = 0; ended < 2; ended++)
-#pragma unroll
-			for (int err = 0; err < 2; err++)
-#pragma unroll
-				for (int fb = 0; fb < 3; fb++) {
-					const uint32_t n = field_sum<10>(ended ? c01b : c01a, fb + 3 * err);
-					const double d0 = fb == 1 ? 1.0 : (fb == 2 ? -1.0 : 0.0);
-					const double d1 = fb == 1 ? 1.0 : (err ? -0.5 : (ended ? 0.8 : 0.5));
-					s0 += (__int128)n * to_fx(d0);
-					s1 += (__int128)n * to_fx(d1);
-				}
-		const double lv_rel[4] = {1.0, -0.2, -0.5, -1.0}, lv_cnt[4] = {1.0, 0.3, -0.3, -0.8}, lv_dur[4] = {1.0, 0.5, 0.0, -0.5};
-		__int128 s3 = 0, s4 = 0, s5 = 0, s7 = 0, s8 = 0, s6 = 0;
-		uint32_t n3 = 0, n5 = 0, n6 = 0, n7 = 0, n8 = 0;
-#pragma unroll
-		for (int k = 0; k < 4; k++) {
-			const uint32_t a3 = field_sum<12>(c3, k), a4 = field_sum<12>(c4, k), a5 = field_sum<12>(c5, k);
-			const uint32_t a7 = field_sum<12>(c7, k), a8 = field_sum<12>(c8, k);
-			s3 += (__int128)a3 * to_fx(lv_rel[k]); s4 += (__int128)a4 * to_fx(lv_cnt[k]); s5 += (__int128)a5 * to_fx(lv_dur[k]);
-			s7 += (__int128)a7 * to_fx(lv_dur[k]); s8 += (__int128)a8 * to_fx(lv_cnt[k]);
-			n3 += a3; n5 += a5; n7 += a7; n8 += a8;
-		}
-#pragma unroll
-		for (int k = 0; k < 6; k++) {                                                    // TCS:735: max(-1, 1 - k*0.4)
-			const uint32_t a6 = field_sum<9>(c6, k);
-			double ef = __dadd_rn(1.0, -__dmul_rn((double)k, 0.4));
-			ef = ef < -1.0 ? -1.0 : ef;
-			s6 += (__int128)a6 * to_fx(ef);
-			n6 += a6;
-		}
-		if (lane == 0) {
-			const __int128 sums[APO_NDIM] = {s0, s1, 0, s3, s4, s5, s6, s7, s8};
-			const uint32_t cnts[APO_NDIM] = {nv, nv, n3, n3, n3, n5, n6, n7, n8};            // d2,d3,d4 are pushed together (TCS:695)
-#pragma unroll
-			for (int i = 0; i < APO_NDIM; i++) {
-				if (i != 2) add_i128(corp + CORP_DIM + 4 * i, sums[i]);
-				if (cnts[i]) atomicAdd((unsigned long long *)corp + CORP_DIM + 4 * i + 3, (unsigned long long)cnts[i]);
-			}
-			if (nv) atomicAdd((unsigned long long *)corp + CORP_REWARD + 3, (unsigned long long)nv);
-		}
+		scan_flush(A, corp, lane);
 	}
 }
 
@@ -201,6 +219,9 @@ __device__ __forceinline__ void corpus_scan_warp(const K2Params &P, uint64_t fir
 static __device__ void finalize_and_publish(const FinalizeParams &F);
 
 __device__ __forceinline__ void corpus_tail(const K2Params &P, const unsigned long long *s_ex, bool *s_last) {
+	// Fences: one thread fences AFTER a block barrier instead of every thread fencing before it — the barrier makes the
+	// block's earlier writes (the warps' atomics) visible to that thread and the fence is cumulative, which is the pattern
+	// of a grid-wide barrier; 704 MEMBARs per CTA were most of a small call's device time.
 	const int tid = threadIdx.x;
 	long long *corp = P.acc + (uint64_t)ACC_PER_CAND * P.C;
 	__syncthreads();
@@ -211,22 +232,21 @@ __device__ __forceinline__ void corpus_tail(const K2Params &P, const unsigned lo
 			if (v != 0ull && v > P.ex_scratch[3 * tid + 2]) ex_insert(&P.ex_scratch[3 * tid], v);
 		}
 	}
-	__threadfence();
 	__syncthreads();
 	if (tid == 0) {
+		__threadfence();
 		const unsigned int ticket = atomicAdd(P.ticket, 1u);
 		*s_last = (ticket == gridDim.x - 1);
+		if (*s_last) __threadfence();                             // acquire side: the other CTAs' flushes are visible from here on
 	}
 	__syncthreads();
 	if (!*s_last) return;
-	__threadfence();
 	if (tid < APO_NPAT * 3) {
 		const unsigned long long v = *((volatile unsigned long long *)&P.ex_scratch[tid]);
 		corp[CORP_EX + 18 * P.rank + tid] = v == 0ull ? 0ll : (long long)(~v + 1);     // index + 1, 0 = none
 	}
 	if (tid == 0) { corp[CORP_NREC] = (long long)P.T; *P.ticket = 0; }
-	__threadfence();
-	__syncthreads();
+	__syncthreads();                                              // block-scope visibility is all the finalising CTA needs (it reads through L2)
 	if (P.fuse_finalize) finalize_and_publish(P.fin);
 }
 
@@ -441,10 +461,11 @@ static __device__ bool peer_join(const JoinParams &J, const long long *acc_local
 	const unsigned long long t0 = globaltimer_ns();
 	// 1. publish this rank's partials (they were produced by other CTAs' atomics: read them from L2)
 	for (uint32_t i = tid; i < J.words; i += nth) mine[i] = __ldcg(acc_local + i);
-	__threadfence_system();
 	__syncthreads();
-	// 2. raise this rank's flag in every rank's block (remote stores), 3. wait for every rank's flag in ours (local loads)
+	// 2. raise this rank's flag in every rank's block (remote stores), 3. wait for every rank's flag in ours (local loads).
+	//    The signalling threads fence at system scope after the barrier (cumulative over the block's slot writes).
 	if (tid < J.nranks) {
+		__threadfence_system();
 		st_release_sys(J.flag[tid] + J.rank, J.epoch);
 		const unsigned long long *f = J.flag[J.rank] + tid;
 		while (ld_acquire_sys(f) < J.epoch) {
@@ -461,7 +482,6 @@ static __device__ bool peer_join(const JoinParams &J, const long long *acc_local
 		for (int r = 0; r < J.nranks; r++) s += ld_relaxed_sys(J.slot[r] + i);
 		J.joined[i] = s;
 	}
-	__threadfence();
 	__syncthreads();
 	// tell every peer that this rank no longer reads its slot (only consulted when a peer tears its block down)
 	if (tid < J.nranks) st_release_sys(J.flag[tid] + PEER_MAX + J.rank, J.epoch);
@@ -480,12 +500,11 @@ static __device__ void finalize_and_publish(const FinalizeParams &F0) {
 	} else if (threadIdx.x == 0) { meta->status = 0u; meta->pad = 0u; meta->join_wait_us = 0.f; meta->join_reduce_us = 0.f; }
 	if (ok) finalize_block(F);
 	if (F.host_out) {
-		__threadfence();
 		__syncthreads();
+		// the end of the kernel makes these stores visible to the host that synchronises on the stream: no system fence here
 		const uint4 *src = reinterpret_cast<const uint4 *>(F.result_base);
 		uint4 *dst = reinterpret_cast<uint4 *>(F.host_out);
 		for (uint32_t i = threadIdx.x; i < F.result_bytes / 16; i += blockDim.x) dst[i] = __ldcg(src + i);
-		__threadfence_system();
 	}
 	if (F0.clean_ptr) {
 		// every other CTA has flushed and left (ticket), the join has read this rank's vector: keep the candidate partials

@@ -372,7 +372,113 @@ k_detect6(const K2Params P) {
 	corpus_tail(P, s_ex, &s_last);
 }
 
+// The stand-alone corpus scan as a streaming kernel (what sessions, host streaming and small calls pay when the scan cannot
+// ride inside a scoring launch): one persistent CTA per SM, a producer warp moving 64 KB record tiles with 1-D TMA bulk
+// copies through a 3-stage mbarrier ring, 16 consumer warps scoring 4 records per thread per tile out of shared memory —
+// the grid-stride form above keeps one 32-byte record per thread in flight (16 KB per SM, a third of what the HBM latency x
+// bandwidth product needs) and stalls on every load.
+template <int CW, int RPT, int STAGES>
+struct K2Cfg {
+	static constexpr int NCONS = CW * 32;
+	static constexpr int TILE = NCONS * RPT;                 // records per tile
+	static constexpr int STAGE_BYTES = TILE * 32;
+	static constexpr int LUT_OFF = STAGES * STAGE_BYTES;     // double2[512]
+	static constexpr int CAT_OFF = LUT_OFF + 512 * 16;
+	static constexpr int BAR_OFF = CAT_OFF + CAT_WORDS * 8;
+	static constexpr int META_OFF = BAR_OFF + 2 * STAGES * 8;
+	static constexpr int EX_OFF = META_OFF + STAGES * 8;
+	static constexpr int SMEM = EX_OFF + 18 * 8 + 16;
+	static_assert(SMEM <= 232448 - 1408, "tiles + tables exceed the shared memory of one CTA");
+};
+
+template <int CW, int RPT, int STAGES>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
+k_detect6_tiles(const K2Params P, uint64_t total_tiles) {
+	using Cfg = K2Cfg<CW, RPT, STAGES>;
+	extern __shared__ __align__(128) uint8_t smem[];
+	double2 *s_lut = reinterpret_cast<double2 *>(smem + Cfg::LUT_OFF);
+	double *s_cat = reinterpret_cast<double *>(smem + Cfg::CAT_OFF);
+	uint64_t *full = reinterpret_cast<uint64_t *>(smem + Cfg::BAR_OFF);
+	uint64_t *empty = full + STAGES;
+	StageMeta *meta = reinterpret_cast<StageMeta *>(smem + Cfg::META_OFF);
+	unsigned long long *s_ex = reinterpret_cast<unsigned long long *>(smem + Cfg::EX_OFF);
+	bool *s_last = reinterpret_cast<bool *>(smem + Cfg::EX_OFF + 18 * 8);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	for (int i = tid; i < 512; i += blockDim.x) s_lut[i] = make_double2(P.lut[i], P.lut[512 + i]);
+	for (int i = tid; i < CAT_WORDS; i += blockDim.x) s_cat[i] = P.lut[1024 + i];
+	if (tid < 18) s_ex[tid] = 0ull;
+	if (tid == 0) {
+		for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CW); }
+		mbar_fence_init();
+	}
+	__syncthreads();
+	const uint64_t lo = total_tiles * blockIdx.x / gridDim.x;
+	const uint64_t hi = total_tiles * (blockIdx.x + 1ull) / gridDim.x;
+
+	if (warp == CW) {
+		if (lane == 0) {
+			const uint64_t pol = policy_evict_first();
+			uint32_t it = 0;
+			for (uint64_t tile = lo; tile <= hi; ++tile, ++it) {
+				const int s = it % STAGES;
+				const uint32_t ph = (it / STAGES) & 1u;
+				mbar_wait(&empty[s], ph ^ 1u);
+				if (tile == hi) { meta[s].cand = -1; meta[s].n = 0; mbar_arrive(&full[s]); break; }
+				const uint64_t e0 = tile * Cfg::TILE;
+				const uint64_t rem = P.T - e0;
+				const uint32_t n = rem < (uint64_t)Cfg::TILE ? (uint32_t)rem : (uint32_t)Cfg::TILE;
+				meta[s].cand = 0; meta[s].n = (int32_t)n;
+				mbar_expect_tx(&full[s], n * 32u);
+				bulk_g2s(smem + s * Cfg::STAGE_BYTES, reinterpret_cast<const uint8_t *>(P.recs) + e0 * 32, n * 32u, &full[s], pol);
+			}
+		}
+	} else {
+		const double w2 = P.W.w[2];
+		long long *corp = P.acc + (uint64_t)ACC_PER_CAND * P.C;
+		ScanAcc A; A.zero();
+		int since = 0;                                            // tiles since the last flush: RPT records per thread each
+		uint64_t tile = lo;
+		for (uint32_t it = 0;; ++it, ++tile) {
+			const int s = it % STAGES;
+			const uint32_t ph = (it / STAGES) & 1u;
+			mbar_wait(&full[s], ph);
+			const int n = meta[s].n;
+			if (n == 0) break;
+			const uint8_t *st = smem + s * Cfg::STAGE_BYTES;
+			const unsigned long long g0 = P.idx_base + tile * Cfg::TILE;
+#pragma unroll
+			for (int k = 0; k < RPT; k++) {
+				const int e = k * Cfg::NCONS + tid;
+				if (e < n) {
+					const uint4 *src = reinterpret_cast<const uint4 *>(st + (size_t)e * 32);
+					union { uint4 q[2]; apo_record r; } u;
+					u.q[0] = src[0]; u.q[1] = src[1];
+					scan_record<false>(A, u.r, g0 + (unsigned long long)e, s_ex, s_cat, s_lut, w2);
+				}
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty[s]);
+			if (++since == K2_CHUNK / RPT) { scan_flush(A, corp, lane); A.zero(); since = 0; }
+		}
+		if (since) scan_flush(A, corp, lane);
+	}
+	corpus_tail(P, s_ex, s_last);                                 // block-wide: every warp arrives here
+}
+
 cudaError_t run_detect6(const K2Params &P, int sm_count, cudaStream_t st) {
+	using Cfg = K2Cfg<16, 4, 3>;
+	const uint64_t tiles = (P.T + Cfg::TILE - 1) / Cfg::TILE;
+	static const int env_old = [] { const char *g = getenv("APO_K2_GRIDSTRIDE"); return g ? atoi(g) : 0; }();   // A/B against the grid-stride form
+	if (tiles >= 4 && !env_old) {
+		auto k = k_detect6_tiles<16, 4, 3>;
+		cudaError_t err = allow_big_smem(k, Cfg::SMEM);
+		if (err != cudaSuccess) return err;
+		int grid = sm_count;
+		if ((uint64_t)grid > tiles) grid = (int)tiles;
+		k<<<grid, 17 * 32, Cfg::SMEM, st>>>(P, tiles);
+		return cudaGetLastError();
+	}
+	// a handful of records (the IDE's real corpora: <= 1000 traces): the light grid-stride kernel, no 200 KB of shared memory to set up
 	uint64_t want = (P.T + K2_THREADS - 1) / K2_THREADS;
 	int grid = sm_count * 2;            // two resident CTAs per SM (launch bounds), one wave
 	if ((uint64_t)grid > want) grid = (int)(want ? want : 1);

@@ -10,8 +10,8 @@
 #include <string.h>
 #include "apo_jobs.h"
 
-#define C 6
-#define T 20000
+#define NC 6
+#define NT 20000
 #define NW 6
 static apo_serial *S;
 static apo_job jobs[64];
@@ -30,8 +30,8 @@ static void *worker(void *p)
 
 static float *make_dims(unsigned seed)
 {
-	float *d = (float *)malloc(sizeof(float) * C * T * 9);
-	for (size_t i = 0; i < (size_t)C * T * 9; i++) {
+	float *d = (float *)malloc(sizeof(float) * NC * NT * 9);
+	for (size_t i = 0; i < (size_t)NC * NT * 9; i++) {
 		seed = seed * 1664525u + 1013904223u;
 		const unsigned r = seed >> 24;
 		d[i] = (r & 7) == 0 ? NAN : (float)((int)(r % 5) - 2) * 0.5f;
@@ -57,16 +57,16 @@ static void build_sequence(float *X, float *Y, apo_record *recs)
 {
 	njobs = 0;
 	apo_job *j;
-	j = push(APO_JOB_DIMS_UPLOAD); j->buf = X; j->buf_bytes = sizeof(float) * C * T * 9; j->C = C; j->T = T; seal(j);          /* 0 A */
-	j = push(APO_JOB_SCORE_RESIDENT); j->C = C; j->K = 3; seal(j);                                                             /* 1 A: scores X */
-	j = push(APO_JOB_DIMS_UPLOAD); j->buf = Y; j->buf_bytes = sizeof(float) * C * T * 9; j->C = C; j->T = T; j->compact = 0; seal(j); /* 2 B */
-	j = push(APO_JOB_SCORE_RESIDENT); j->C = C; j->K = 3; seal(j);                                                             /* 3 A again: must see Y */
-	j = push(APO_JOB_SCORE_RESIDENT); j->C = C; j->K = C; j->first = 4000; j->count = 8000; seal(j);                          /* 4 B: window of Y */
+	j = push(APO_JOB_DIMS_UPLOAD); j->buf = X; j->buf_bytes = sizeof(float) * NC * NT * 9; j->C = NC; j->T = NT; seal(j);          /* 0 A */
+	j = push(APO_JOB_SCORE_RESIDENT); j->C = NC; j->K = 3; seal(j);                                                             /* 1 A: scores X */
+	j = push(APO_JOB_DIMS_UPLOAD); j->buf = Y; j->buf_bytes = sizeof(float) * NC * NT * 9; j->C = NC; j->T = NT; j->compact = 0; seal(j); /* 2 B */
+	j = push(APO_JOB_SCORE_RESIDENT); j->C = NC; j->K = 3; seal(j);                                                             /* 3 A again: must see Y */
+	j = push(APO_JOB_SCORE_RESIDENT); j->C = NC; j->K = NC; j->first = 4000; j->count = 8000; seal(j);                          /* 4 B: window of Y */
 	j = push(APO_JOB_REWARD_BATCH); j->buf = recs; j->buf_bytes = sizeof(apo_record) * 64; seal(j);                           /* 5 */
-	j = push(APO_JOB_SCORE_HOST); j->buf = X; j->buf_bytes = sizeof(float) * C * T * 9; j->C = C; j->T = T; j->K = 2;
+	j = push(APO_JOB_SCORE_HOST); j->buf = X; j->buf_bytes = sizeof(float) * NC * NT * 9; j->C = NC; j->T = NT; j->K = 2;
 	j->corpus = recs; j->corpus_bytes = sizeof(apo_record) * 64; seal(j);                                                      /* 6 host streaming + corpus */
-	j = push(APO_JOB_SCORE_HOST); j->buf = X; j->buf_bytes = 100; j->C = C; j->T = T; j->K = 2; seal(j);                       /* 7 invalid: rejected in its turn */
-	j = push(APO_JOB_SCORE_RESIDENT); j->C = C; j->K = 1; seal(j);                                                             /* 8 still Y resident */
+	j = push(APO_JOB_SCORE_HOST); j->buf = X; j->buf_bytes = 100; j->C = NC; j->T = NT; j->K = 2; seal(j);                       /* 7 invalid: rejected in its turn */
+	j = push(APO_JOB_SCORE_RESIDENT); j->C = NC; j->K = 1; seal(j);                                                             /* 8 still Y resident */
 }
 
 int main(void)
@@ -101,7 +101,7 @@ int main(void)
 			const apo_job *a = &truth[i], *b = &jobs[i];
 			if (a->rc != b->rc) { printf("FAIL round %d job %d: rc %d vs %d (%s)\n", round, i, b->rc, a->rc, b->err); fails++; continue; }
 			if (a->rc != APO_OK) continue;
-			if (a->scores && (memcmp(a->scores, b->scores, 8 * C) || memcmp(a->counts, b->counts, 8 * C) || memcmp(a->topk, b->topk, 4 * (a->K < C ? a->K : C)))) {
+			if (a->scores && (memcmp(a->scores, b->scores, 8 * NC) || memcmp(a->counts, b->counts, 8 * NC) || memcmp(a->topk, b->topk, 4 * (a->K < NC ? a->K : NC)))) {
 				printf("FAIL round %d job %d: scores / counts / top-K differ from the sequential run\n", round, i); fails++;
 			}
 			if (a->kind == APO_JOB_SCORE_HOST && memcmp(&a->report, &b->report, sizeof a->report)) { printf("FAIL round %d job %d: report differs\n", round, i); fails++; }
@@ -109,8 +109,8 @@ int main(void)
 		}
 		if (round == 0) {
 			if (truth[7].rc != APO_E_ARG) { printf("FAIL: undersized buffer accepted\n"); fails++; }
-			if (!memcmp(truth[1].scores, truth[3].scores, 8 * C)) { printf("FAIL: job 3 did not see tensor Y\n"); fails++; }
-			if (memcmp(truth[3].scores, truth[8].scores, 8 * C)) { printf("FAIL: resident tensor changed under the host-streaming call\n"); fails++; }
+			if (!memcmp(truth[1].scores, truth[3].scores, 8 * NC)) { printf("FAIL: job 3 did not see tensor Y\n"); fails++; }
+			if (memcmp(truth[3].scores, truth[8].scores, 8 * NC)) { printf("FAIL: resident tensor changed under the host-streaming call\n"); fails++; }
 		}
 		for (int i = 0; i < n; i++) apo_job_release(&jobs[i]);
 		apo_serial_destroy(S);

@@ -33,8 +33,9 @@ int main(void)
 	for (int i = 0; i < 50; i++) apo_score(e, &o, scores, counts, topk, &rep);
 	t0 = now_us(); for (int i = 0; i < REPS; i++) apo_score(e, &o, scores, counts, topk, &rep); c = (now_us() - t0) / REPS;
 	apo_timing tm; apo_last_timing(e, &tm);
-	printf("{\"reward_one_us\": %.2f, \"report_1000_traces_us\": %.2f, \"score_4x1000_top2_with_report_us\": %.2f, \"launches_per_score\": %u, \"reps\": %d, \"final\": %.17g, \"top\": [%d, %d]}\n",
-	       a, b, c, tm.launches, REPS, fin, topk[0], topk[1]);
+	printf("{\"reward_one_us\": %.2f, \"report_1000_traces_us\": %.2f, \"score_4x1000_top2_with_report_us\": %.2f, \"launches_per_score\": %u, \"tail_finalize_us\": %.2f, "
+	       "\"tail_publish_us\": %.2f, \"reps\": %d, \"final\": %.17g, \"top\": [%d, %d]}\n",
+	       a, b, c, tm.launches, tm.tail_finalize_ms * 1e3, tm.tail_publish_ms * 1e3, REPS, fin, topk[0], topk[1]);
 	apo_destroy(e);
 	return 0;
 }

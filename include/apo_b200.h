@@ -116,6 +116,8 @@ typedef struct apo_timing {       /* device time of the stages of the last apo_s
 	uint32_t pad;
 	float join_wait_ms;           /* peer-memory join: publish -> every rank arrived (includes rank skew), device timer */
 	float join_reduce_ms;         /* peer-memory join: NVLink reads + sum of the peers' partial vectors                 */
+	float tail_finalize_ms;       /* K3 in the finalising CTA: segmented sum + report + radix top-K (device timer)      */
+	float tail_publish_ms;        /* result block written to the caller's page-locked buffer + accumulators re-armed    */
 } apo_timing;
 /* The *_ms stage fields come from CUDA events, which are recorded only for calls that stream >= 64 MB or set
  * APO_SCORE_TIMING (a small call is launch-bound and every event costs it ~1 us); launches and the join_* fields

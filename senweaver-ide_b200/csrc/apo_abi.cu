@@ -400,7 +400,7 @@ ResultLayout result_layout(uint32_t C, uint32_t K) {
 	L.bytes = L.off_meta + sizeof(apo::ResultMeta);
 	return L;
 }
-static_assert(sizeof(apo::ResultMeta) == 16, "result block stays a multiple of 16 bytes");
+static_assert(sizeof(apo::ResultMeta) == 32, "result block stays a multiple of 16 bytes");
 constexpr uint64_t kHostOutMax = 64ull << 10;      // result blocks up to this size are written to the caller's page-locked buffer by the kernel itself
 constexpr uint64_t kTimingMinBytes = 64ull << 20;  // per-stage CUDA events are recorded for calls streaming at least this much (or on request)
 constexpr uint64_t ARM_WORDS = 19;                  // 18 example slots + ticket, right behind the partial vector
@@ -592,6 +592,8 @@ int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *sco
 	}
 	e->timing.join_wait_ms = meta.join_wait_us * 1e-3f;
 	e->timing.join_reduce_ms = meta.join_reduce_us * 1e-3f;
+	e->timing.tail_finalize_ms = meta.finalize_us * 1e-3f;
+	e->timing.tail_publish_ms = meta.publish_us * 1e-3f;
 	if (tm) {
 		float ms = 0;
 		e->timing.reward_ms = 0;

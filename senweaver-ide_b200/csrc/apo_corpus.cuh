@@ -498,7 +498,11 @@ static __device__ void finalize_and_publish(const FinalizeParams &F0) {
 		ok = peer_join(F.join, F.acc, meta);
 		F.acc = F.join.joined;
 	} else if (threadIdx.x == 0) { meta->status = 0u; meta->pad = 0u; meta->join_wait_us = 0.f; meta->join_reduce_us = 0.f; }
+	const unsigned long long tf0 = globaltimer_ns();
 	if (ok) finalize_block(F);
+	__syncthreads();
+	const unsigned long long tf1 = globaltimer_ns();
+	if (threadIdx.x == 0) { meta->finalize_us = (float)((tf1 - tf0) * 1e-3); meta->publish_us = 0.f; meta->entered_us = 0.f; meta->pad2 = 0u; }
 	if (F.host_out) {
 		__syncthreads();
 		// the end of the kernel makes these stores visible to the host that synchronises on the stream: no system fence here
@@ -513,6 +517,10 @@ static __device__ void finalize_and_publish(const FinalizeParams &F0) {
 		for (uint32_t i = threadIdx.x; i < (uint32_t)ACC_PER_CAND * F.C; i += blockDim.x) F0.snapshot[i] = __ldcg(F0.acc + i);
 		__syncthreads();
 		for (uint32_t i = threadIdx.x; i < F0.clean_words; i += blockDim.x) F0.clean_ptr[i] = 0ll;
+	}
+	if (F.host_out && threadIdx.x == 0) {
+		// the timer of this last step lands in the host copy only (the device block was already copied out)
+		reinterpret_cast<ResultMeta *>(F.host_out + F.meta_off)->publish_us = (float)((globaltimer_ns() - tf1) * 1e-3);
 	}
 }
 

@@ -53,6 +53,10 @@ struct ResultMeta {             // tail of the result block
 	uint32_t pad;
 	float join_wait_us;         // publish -> all ranks arrived (includes the skew between ranks)
 	float join_reduce_us;       // reading and summing the peers' slots
+	float finalize_us;          // segmented sum + report + radix top-K (device timer, finalising CTA)
+	float publish_us;           // result block -> caller's buffer, accumulators re-armed
+	float entered_us;           // kernel start of the finalising CTA -> it entered the tail (its share of the scoring / scanning work)
+	uint32_t pad2;
 };
 
 struct K2Params {

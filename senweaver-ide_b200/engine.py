@@ -67,7 +67,7 @@ class CorpusReport(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("reward_ms", C.c_float), ("corpus_ms", C.c_float), ("allreduce_ms", C.c_float),
                 ("finalize_ms", C.c_float), ("total_ms", C.c_float), ("launches", C.c_uint32), ("pad", C.c_uint32),
-                ("join_wait_ms", C.c_float), ("join_reduce_ms", C.c_float)]
+                ("join_wait_ms", C.c_float), ("join_reduce_ms", C.c_float), ("tail_finalize_ms", C.c_float), ("tail_publish_ms", C.c_float)]
 
 
 class ScoreOpts(C.Structure):

@@ -33,7 +33,7 @@ def test_struct_sizes_match_header(apo):
     assert ctypes.sizeof(eng.Pattern) == 40
     assert ctypes.sizeof(eng.DimStat) == 32
     assert ctypes.sizeof(eng.ScoreOpts) == 32
-    assert ctypes.sizeof(eng.Timing) == 36
+    assert ctypes.sizeof(eng.Timing) == 44
     assert eng.RECORD_DTYPE.itemsize == 32
 
 

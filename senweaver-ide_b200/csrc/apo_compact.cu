@@ -461,7 +461,7 @@ k_reward9q(const KqParams P) {
 	}
 	if (cur >= 0) flush(cur);
 	}
-	if (P.corpus_on) corpus_tail(P.corpus, s_ex, s_last);     // block-wide: every warp arrives here
+	if (P.corpus_on) corpus_tail(P.corpus, s_ex, s_last, reinterpret_cast<unsigned long long *>(smem), 2048u);     // block-wide; stage 0 is free: scratch
 }
 
 template <int CW, int EPT, int STAGES, int NF = -1>
@@ -497,6 +497,11 @@ cudaError_t run_reward9q(KqParams P, int variant, bool recip, int sm_count, cuda
 	int grid = sm_count;
 	{ static const int env_grid = [] { const char *g = getenv("APO_K1_GRID"); return g ? atoi(g) : 0; }(); if (env_grid > 0 && env_grid < grid) grid = env_grid; }
 	if ((uint64_t)grid > P.total_tiles) grid = (int)P.total_tiles;
+	if (P.corpus_on && P.corpus.T) {
+		const uint64_t want = (P.corpus.T + 63) / 64;
+		const int more = (int)(want < (uint64_t)sm_count ? want : (uint64_t)sm_count);
+		if (more > grid) grid = more;
+	}
 	switch (variant) {
 	case 1: return launch_kq<16, 8, 3>(P, grid, recip, st);
 	case 2: return launch_kq<24, 4, 4>(P, grid, recip, st);

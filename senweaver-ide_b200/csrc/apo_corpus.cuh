@@ -216,9 +216,12 @@ __device__ __forceinline__ void corpus_scan_warp(const K2Params &P, uint64_t fir
 // scratch, take a ticket, and let the last CTA publish this rank's examples and finalise (segmented sum +
 // top-K; at > 1 rank after the peer-memory join of the partial vectors).
 // Must be called by every thread of the CTA (it synchronises the block).
-static __device__ void finalize_and_publish(const FinalizeParams &F);
+static __device__ void finalize_and_publish(const FinalizeParams &F, unsigned long long *s_scratch, uint32_t scratch_keys);
 
-__device__ __forceinline__ void corpus_tail(const K2Params &P, const unsigned long long *s_ex, bool *s_last) {
+// s_scratch / scratch_keys: shared memory the caller no longer needs at this point (a free stage buffer, the LUT of the
+// grid-stride kernel), lent to the finalisation for its small-C top-K.
+__device__ __forceinline__ void corpus_tail(const K2Params &P, const unsigned long long *s_ex, bool *s_last,
+                                            unsigned long long *s_scratch = nullptr, uint32_t scratch_keys = 0) {
 	// Fences: one thread fences AFTER a block barrier instead of every thread fencing before it — the barrier makes the
 	// block's earlier writes (the warps' atomics) visible to that thread and the fence is cumulative, which is the pattern
 	// of a grid-wide barrier; 704 MEMBARs per CTA were most of a small call's device time.
@@ -247,7 +250,7 @@ __device__ __forceinline__ void corpus_tail(const K2Params &P, const unsigned lo
 	}
 	if (tid == 0) { corp[CORP_NREC] = (long long)P.T; *P.ticket = 0; }
 	__syncthreads();                                              // block-scope visibility is all the finalising CTA needs (it reads through L2)
-	if (P.fuse_finalize) finalize_and_publish(P.fin);
+	if (P.fuse_finalize) finalize_and_publish(P.fin, s_scratch, scratch_keys);
 }
 
 __device__ __forceinline__ unsigned long long score_key(double s) {
@@ -323,7 +326,7 @@ static __device__ void build_report(const FinalizeParams &F, const long long *co
 
 // Block-wide; every thread of the calling block must enter.  Works for any blockDim.x
 // that is a multiple of 32 (<= 1024).
-static __device__ __noinline__ void finalize_block(const FinalizeParams &F) {
+static __device__ __noinline__ void finalize_block(const FinalizeParams &F, unsigned long long *s_scratch, uint32_t scratch_keys) {
 	__shared__ unsigned int s_hist[256];
 	__shared__ unsigned long long s_prefix;
 	__shared__ unsigned int s_need, s_base_gt, s_base_eq, s_warp_gt[32], s_warp_eq[32];
@@ -341,11 +344,28 @@ static __device__ __noinline__ void finalize_block(const FinalizeParams &F) {
 		F.scores[c] = s;
 		F.counts[c] = n;
 		F.keys[c] = score_key(s);
+		if (C <= scratch_keys) s_scratch[c] = score_key(s);
 	}
 	if (F.with_corpus) build_report(F, acc + (uint64_t)ACC_PER_CAND * C);
 	__syncthreads();
 	const uint32_t K = F.K < C ? F.K : C;
 	if (K == 0) return;
+
+	// Small beams (the reference's are 4 wide, APO:288): rank every candidate by counting over the keys held in shared memory —
+	// position = #{better score, or equal score and lower index} — and let the first K write themselves out.  One barrier
+	// instead of the eight histogram passes of the radix select below (12 us of a 4 x 1000 call).
+	if (C <= scratch_keys) {
+		for (uint32_t i = tid; i < C; i += nth) {
+			const unsigned long long ki = s_scratch[i];
+			uint32_t rank = 0;
+			for (uint32_t j = 0; j < C; j++) {
+				const unsigned long long kj = s_scratch[j];
+				rank += (kj > ki || (kj == ki && j < i)) ? 1u : 0u;
+			}
+			if (rank < K) F.topk[rank] = (int32_t)i;
+		}
+		return;
+	}
 
 	// 2. radix select (8-bit digits, MSB first): key of the K-th best candidate
 	if (tid == 0) { s_prefix = 0; s_need = K; }
@@ -490,7 +510,7 @@ static __device__ bool peer_join(const JoinParams &J, const long long *acc_local
 }
 
 // join (> 1 rank) -> segmented sum + report + top-K -> result block written to the caller's page-locked buffer.
-static __device__ void finalize_and_publish(const FinalizeParams &F0) {
+static __device__ void finalize_and_publish(const FinalizeParams &F0, unsigned long long *s_scratch, uint32_t scratch_keys) {
 	FinalizeParams F = F0;
 	ResultMeta *meta = reinterpret_cast<ResultMeta *>(F.result_base + F.meta_off);
 	bool ok = true;
@@ -499,7 +519,7 @@ static __device__ void finalize_and_publish(const FinalizeParams &F0) {
 		F.acc = F.join.joined;
 	} else if (threadIdx.x == 0) { meta->status = 0u; meta->pad = 0u; meta->join_wait_us = 0.f; meta->join_reduce_us = 0.f; }
 	const unsigned long long tf0 = globaltimer_ns();
-	if (ok) finalize_block(F);
+	if (ok) finalize_block(F, s_scratch, scratch_keys);
 	__syncthreads();
 	const unsigned long long tf1 = globaltimer_ns();
 	if (threadIdx.x == 0) { meta->finalize_us = (float)((tf1 - tf0) * 1e-3); meta->publish_us = 0.f; meta->entered_us = 0.f; meta->pad2 = 0u; }

@@ -284,7 +284,8 @@ k_reward9(const K1Params P) {
 	}
 	if (cur >= 0) flush(cur);
 	}
-	if (P.corpus_on) corpus_tail(P.corpus, s_ex, s_last);     // block-wide: every warp arrives here
+	// block-wide: every warp arrives here; the stage buffers are free by now (every tile was consumed) and serve as scratch
+	if (P.corpus_on) corpus_tail(P.corpus, s_ex, s_last, reinterpret_cast<unsigned long long *>(smem), 2048u);
 }
 
 template <int ROW, int CW, int STAGES>
@@ -326,6 +327,12 @@ cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_cou
 	{ static const int env_grid = [] { const char *g = getenv("APO_K1_GRID"); return g ? atoi(g) : 0; }(); if (env_grid > 0 && env_grid < grid) grid = env_grid; }   // tuning experiments only, read once
 	{ static const int env_tune = [] { const char *g = getenv("APO_K1_TUNE"); return g ? atoi(g) : 0; }(); if (env_tune) P.tune = (uint32_t)env_tune; }
 	if ((uint64_t)grid > P.total_tiles) grid = (int)P.total_tiles;
+	if (P.corpus_on && P.corpus.T) {
+		// a tiny evaluation set with a corpus to scan: CTAs without tiles still lend their corpus warp (<= 2 records per lane)
+		const uint64_t want = (P.corpus.T + 63) / 64;
+		const int more = (int)(want < (uint64_t)sm_count ? want : (uint64_t)sm_count);
+		if (more > grid) grid = more;
+	}
 	if (row == 36) {
 		switch (variant) {
 		case 1: return launch_k1<36, 16, 3>(P, grid, recip, st);
@@ -369,7 +376,7 @@ k_detect6(const K2Params P) {
 	__syncthreads();
 	const uint64_t nwarps = (uint64_t)gridDim.x * (K2_THREADS / 32);
 	corpus_scan_warp<false>(P, ((uint64_t)blockIdx.x * (K2_THREADS / 32) + warp) * 32, nwarps * 32, s_ex, s_cat, s_lut, lane);
-	corpus_tail(P, s_ex, &s_last);
+	corpus_tail(P, s_ex, &s_last, reinterpret_cast<unsigned long long *>(s_lut), 1024u);     // the LUT (8 KB) is done with: scratch of the tail
 }
 
 // The stand-alone corpus scan as a streaming kernel (what sessions, host streaming and small calls pay when the scan cannot
@@ -462,7 +469,7 @@ k_detect6_tiles(const K2Params P, uint64_t total_tiles) {
 		}
 		if (since) scan_flush(A, corp, lane);
 	}
-	corpus_tail(P, s_ex, s_last);                                 // block-wide: every warp arrives here
+	corpus_tail(P, s_ex, s_last, reinterpret_cast<unsigned long long *>(smem), 2048u);     // block-wide: every warp arrives here
 }
 
 cudaError_t run_detect6(const K2Params &P, int sm_count, cudaStream_t st) {
@@ -486,7 +493,10 @@ cudaError_t run_detect6(const K2Params &P, int sm_count, cudaStream_t st) {
 	return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(1024) k_finalize(const FinalizeParams F) { finalize_and_publish(F); }
+__global__ void __launch_bounds__(1024) k_finalize(const FinalizeParams F) {
+	__shared__ unsigned long long s_keys[1024];
+	finalize_and_publish(F, s_keys, 1024u);
+}
 
 cudaError_t run_finalize(const FinalizeParams &F, cudaStream_t st) {
 	k_finalize<<<1, 1024, 0, st>>>(F);

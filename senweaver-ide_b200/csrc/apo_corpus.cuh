@@ -466,7 +466,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 __device__ __forceinline__ long long ld_relaxed_sys(const long long *p) {
 	long long v;
-	asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p));      // no memory clobber: independent loads may be in flight together
 	return v;
 }
 
@@ -483,10 +483,9 @@ static __device__ bool peer_join(const JoinParams &J, const long long *acc_local
 	for (uint32_t i = tid; i < J.words; i += nth) mine[i] = __ldcg(acc_local + i);
 	__syncthreads();
 	// 2. raise this rank's flag in every rank's block (remote stores), 3. wait for every rank's flag in ours (local loads).
-	//    The signalling threads fence at system scope after the barrier (cumulative over the block's slot writes).
+	//    The signalling threads release at system scope after the barrier (cumulative over the block's slot writes).
 	if (tid < J.nranks) {
-		__threadfence_system();
-		st_release_sys(J.flag[tid] + J.rank, J.epoch);
+		st_release_sys(J.flag[tid] + J.rank, J.epoch);            // release at system scope: fence + store (SASS: MEMBAR.ALL.SYS; STG.STRONG.SYS)
 		const unsigned long long *f = J.flag[J.rank] + tid;
 		while (ld_acquire_sys(f) < J.epoch) {
 			if (globaltimer_ns() - t0 > PEER_TIMEOUT_NS) { s_ok = 0; break; }
@@ -497,14 +496,20 @@ static __device__ bool peer_join(const JoinParams &J, const long long *acc_local
 	const unsigned long long t1 = globaltimer_ns();
 	if (!s_ok) { if (tid == 0) { meta->status = 1u; meta->join_wait_us = (float)((t1 - t0) * 1e-3); meta->join_reduce_us = 0.f; } return false; }
 	// 4. sum the slots of all ranks (NVLink peer loads; integers: any order gives the same bits)
+	//    All loads of a word are issued before the first add: eight NVLink round trips in flight per thread, not one after the other.
 	for (uint32_t i = tid; i < J.words; i += nth) {
+		long long v[PEER_MAX];
+#pragma unroll
+		for (int r = 0; r < PEER_MAX; r++) v[r] = r < J.nranks ? ld_relaxed_sys(J.slot[r] + i) : 0ll;
 		long long s = 0;
-		for (int r = 0; r < J.nranks; r++) s += ld_relaxed_sys(J.slot[r] + i);
+#pragma unroll
+		for (int r = 0; r < PEER_MAX; r++) s += v[r];
 		J.joined[i] = s;
 	}
 	__syncthreads();
 	// tell every peer that this rank no longer reads its slot (only consulted when a peer tears its block down)
-	if (tid < J.nranks) st_release_sys(J.flag[tid] + PEER_MAX + J.rank, J.epoch);
+	// (a relaxed store: the loads above have returned their values — they fed the stores to `joined` before the barrier)
+	if (tid < J.nranks) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(J.flag[tid] + PEER_MAX + J.rank), "l"(J.epoch) : "memory");
 	if (tid == 0) { meta->status = 0u; meta->join_wait_us = (float)((t1 - t0) * 1e-3); meta->join_reduce_us = (float)((globaltimer_ns() - t1) * 1e-3); }
 	return true;
 }

@@ -403,9 +403,13 @@ class Engine:
         counts = np.empty(Cn, np.uint64)
         topk = np.empty(K, np.int32)
         rep = CorpusReport() if corpus else None
-        self._ck(self._L.apo_score(self._h, C.byref(o), _p(scores), _p(counts), _p(topk),
-                                   C.byref(rep) if rep is not None else None))
-        return ScoreResult(scores, counts, topk, rep, self.last_timing())
+        t = Timing()
+        L = self._L
+        rc = L.apo_score(self._h, C.byref(o), scores.ctypes.data, counts.ctypes.data, topk.ctypes.data, C.byref(rep) if rep is not None else None)
+        if rc != 0:
+            self._ck(rc)
+        L.apo_last_timing(self._h, C.byref(t))
+        return ScoreResult(scores, counts, topk, rep, t)
 
     # chunked form: begin / accumulate (per candidate chunk or record window) / finish
     def score_begin(self, C_total: int):

@@ -129,9 +129,8 @@ cudaError_t run_recode(unsigned long long *q8, float *d2, unsigned short *li, ui
 __global__ void __launch_bounds__(256)
 k_unpack_p(const uint32_t *pc, const unsigned short *pd, uint64_t pitch_in, uint32_t C, uint64_t T, const float *d2book,
            unsigned long long *q8, float *d2, unsigned short *li, uint64_t pitch_out) {
-	__shared__ float s_d2[4096];
-	for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_d2[i] = d2book[i];
-	__syncthreads();
+	// d2book is read through the read-only path: a tensor uses a few hundred of its 4096 entries, which stay in L1
+	// (staging the 16 KB table in shared memory per block cost more than the block's own 256 evaluations)
 	const uint32_t c = blockIdx.y;
 	if (c >= C) return;
 	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (uint64_t)gridDim.x * blockDim.x) {
@@ -150,7 +149,7 @@ k_unpack_p(const uint32_t *pc, const unsigned short *pd, uint64_t pitch_in, uint
 		mask |= (p2 ? 1u : 0u) << 2;
 		const uint64_t o = (uint64_t)c * pitch_out + t;
 		q8[o] = q;
-		d2[o] = p2 ? s_d2[k2] : 0.0f;
+		d2[o] = p2 ? __ldg(d2book + k2) : 0.0f;
 		li[o] = (unsigned short)lut_index(mask);
 	}
 }
@@ -158,7 +157,7 @@ k_unpack_p(const uint32_t *pc, const unsigned short *pd, uint64_t pitch_in, uint
 cudaError_t run_unpack_p(const uint32_t *pc, const unsigned short *pd, uint64_t pitch_in, uint32_t C, uint64_t T, const float *d2book,
                          unsigned long long *q8, float *d2, unsigned short *li, uint64_t pitch_out, cudaStream_t st) {
 	if (C == 0 || T == 0) return cudaSuccess;
-	uint64_t gx = (T + 255) / 256;
+	uint64_t gx = (T + 1023) / 1024;                              // four evaluations per thread and row
 	if (gx > 148ull * 8) gx = 148ull * 8;
 	for (uint32_t cb = 0; cb < C; cb += 32768) {
 		const uint32_t cn = C - cb < 32768 ? C - cb : 32768;
@@ -178,9 +177,14 @@ k_collect_d2(const float *d2, const unsigned short *li, uint64_t n, uint32_t *ta
 		const uint32_t bits = __float_as_uint(d2[i]);
 		uint32_t h = (bits * 2654435761u) >> 18;
 		for (int probe = 0; probe < 16384; probe++) {
-			const uint32_t cur = atomicCAS(&table[h], SLOT_EMPTY, bits);
+			// look first: after the first few thousand evaluations every value is already there, and a plain (L1/L2) read of a
+			// slot that only ever goes EMPTY -> value costs nothing next to 2.5 G contended atomics on a few hundred addresses
+			uint32_t cur = *((volatile uint32_t *)&table[h]);
+			if (cur == SLOT_EMPTY) {
+				cur = atomicCAS(&table[h], SLOT_EMPTY, bits);
+				if (cur == SLOT_EMPTY) { atomicAdd(count, 1u); break; }
+			}
 			if (cur == bits) break;
-			if (cur == SLOT_EMPTY) { atomicAdd(count, 1u); break; }
 			h = (h + 1) & 16383u;
 		}
 	}

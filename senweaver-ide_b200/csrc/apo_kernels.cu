@@ -472,18 +472,26 @@ k_detect6_tiles(const K2Params P, uint64_t total_tiles) {
 	corpus_tail(P, s_ex, s_last, reinterpret_cast<unsigned long long *>(smem), 2048u);     // block-wide: every warp arrives here
 }
 
-cudaError_t run_detect6(const K2Params &P, int sm_count, cudaStream_t st) {
-	using Cfg = K2Cfg<16, 4, 3>;
+template <int CW, int RPT, int STAGES>
+static cudaError_t launch_k2_tiles(const K2Params &P, int sm_count, cudaStream_t st) {
+	using Cfg = K2Cfg<CW, RPT, STAGES>;
 	const uint64_t tiles = (P.T + Cfg::TILE - 1) / Cfg::TILE;
+	auto k = k_detect6_tiles<CW, RPT, STAGES>;
+	cudaError_t err = allow_big_smem(k, Cfg::SMEM);
+	if (err != cudaSuccess) return err;
+	int grid = sm_count;
+	if ((uint64_t)grid > tiles) grid = (int)tiles;
+	k<<<grid, (CW + 1) * 32, Cfg::SMEM, st>>>(P, tiles);
+	return cudaGetLastError();
+}
+
+cudaError_t run_detect6(const K2Params &P, int sm_count, cudaStream_t st) {
 	static const int env_old = [] { const char *g = getenv("APO_K2_GRIDSTRIDE"); return g ? atoi(g) : 0; }();   // A/B against the grid-stride form
-	if (tiles >= 4 && !env_old) {
-		auto k = k_detect6_tiles<16, 4, 3>;
-		cudaError_t err = allow_big_smem(k, Cfg::SMEM);
-		if (err != cudaSuccess) return err;
-		int grid = sm_count;
-		if ((uint64_t)grid > tiles) grid = (int)tiles;
-		k<<<grid, 17 * 32, Cfg::SMEM, st>>>(P, tiles);
-		return cudaGetLastError();
+	static const int env_cw = [] { const char *g = getenv("APO_K2_CW"); return g ? atoi(g) : 0; }();            // A/B: consumer warps per CTA
+	if (P.T >= 4 * 2048 && !env_old) {
+		if (env_cw == 16) return launch_k2_tiles<16, 4, 3>(P, sm_count, st);
+		if (env_cw == 20) return launch_k2_tiles<20, 2, 4>(P, sm_count, st);
+		return launch_k2_tiles<24, 2, 4>(P, sm_count, st);
 	}
 	// a handful of records (the IDE's real corpora: <= 1000 traces): the light grid-stride kernel, no 200 KB of shared memory to set up
 	uint64_t want = (P.T + K2_THREADS - 1) / K2_THREADS;

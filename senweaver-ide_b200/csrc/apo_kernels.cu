@@ -489,9 +489,9 @@ cudaError_t run_detect6(const K2Params &P, int sm_count, cudaStream_t st) {
 	static const int env_old = [] { const char *g = getenv("APO_K2_GRIDSTRIDE"); return g ? atoi(g) : 0; }();   // A/B against the grid-stride form
 	static const int env_cw = [] { const char *g = getenv("APO_K2_CW"); return g ? atoi(g) : 0; }();            // A/B: consumer warps per CTA
 	if (P.T >= 4 * 2048 && !env_old) {
-		if (env_cw == 16) return launch_k2_tiles<16, 4, 3>(P, sm_count, st);
+		if (env_cw == 24) return launch_k2_tiles<24, 2, 4>(P, sm_count, st);
 		if (env_cw == 20) return launch_k2_tiles<20, 2, 4>(P, sm_count, st);
-		return launch_k2_tiles<24, 2, 4>(P, sm_count, st);
+		return launch_k2_tiles<16, 4, 3>(P, sm_count, st);      // measured: 16 warps x 4 records 0.225 ms / 10 M records, 20 x 2: 0.252, 24 x 2: 0.306 (register spills)
 	}
 	// a handful of records (the IDE's real corpora: <= 1000 traces): the light grid-stride kernel, no 200 KB of shared memory to set up
 	uint64_t want = (P.T + K2_THREADS - 1) / K2_THREADS;

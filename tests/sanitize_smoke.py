@@ -55,6 +55,33 @@ assert e.debug_partials(C) == exp
 e.score_host_records(pkg.pack16(roll), 2)
 assert e.debug_partials(C) == orc.score_records_fx(roll)
 d, m, f = e.reward_batch(recs[:500])
+d1, m1, f1 = e.reward_batch(recs[:3])                 # zero-copy single-trace path (kernel reads / writes page-locked host memory)
+assert np.array_equal(f1, f[:3], equal_nan=True)
+# round-2 kernels: stand-alone corpus scan as TMA tiles (>= 8192 records), the packed / compact wire formats, their export
+big = orc.gen_records(seed, orc.STREAM_CORPUS, 0, 1, 0, 20_000, 300, 4).reshape(-1)
+e.corpus_upload(big)
+e.dims_upload(dims)
+e.score_begin(C)
+e.score_accumulate(0)
+r = e.score_finish(C, 3, corpus=True)                 # k_detect6_tiles + fused K3
+refb = orc.report(big)
+assert r.report.bad == refb.bad and [r.report.pat[p].count for p in range(6)] == [refb.pat[p].count for p in range(6)]
+assert list(r.report.pat[2].examples) == list(refb.pat[2].examples)
+pc, pd, book, d2book = pkg.packed_encode_host(dims, nthreads=2)
+e.score_host_packed(pc, pd, book, d2book, 2, corpus=True)         # k_unpack_p + K1q
+assert e.debug_partials(C) == exp
+q8, d2, li, book2 = pkg.compact_encode_host(dims, nthreads=2)
+e.score_host_compact(q8, d2, li, book2, 2)
+assert e.debug_partials(C) == exp
+e.dims_upload_compact(dims)
+a, b = e.dims_packed_download(1, 0, T)                            # k_collect_d2 + k_pack_p
+assert np.array_equal(a, pc[1]) and np.array_equal(b, pd[1])
+for Cn in (3, 1500, 3000):                                        # counting top-K (<= 2048 keys in shared memory) and the radix select
+    e.dims_generate(seed, 0, Cn, 0, 64, 300)
+    r = e.score(Cn, min(Cn, 40))
+    sc = r.scores
+    order = sorted(range(Cn), key=lambda c: (-sc[c], c))[:min(Cn, 40)]
+    assert list(r.topk) == order
 e.dims_generate(seed, 0, 2, 0, 300, 300)
 e.rollouts_generate(seed, 0, 2, 0, 300, 300)
 e.rollouts16_generate(seed, 0, 2, 0, 300, 300)

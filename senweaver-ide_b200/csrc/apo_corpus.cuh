@@ -395,6 +395,7 @@ static __device__ __noinline__ void finalize_block(const FinalizeParams &F, unsi
 			const unsigned int need = s_need, above = suf - tot;
 			const bool here = above < need && need <= suf;
 			const unsigned int any = __ballot_sync(0xffffffffu, here);
+			__syncwarp();                                             // every lane has read s_need before one of them rewrites it
 			if (here || (any == 0u && lane == 0)) {                   // (any == 0 cannot happen: need <= #keys under the prefix)
 				unsigned int rem = need - (here ? above : 0u);
 				int j = 7;

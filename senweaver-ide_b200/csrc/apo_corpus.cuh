@@ -493,6 +493,12 @@ static __device__ bool peer_join(const JoinParams &J, const long long *acc_local
 			__nanosleep(64);
 		}
 	}
+	// while those threads wait (tens of microseconds of launch skew between the ranks), a second warp touches every peer's slot:
+	// the first access to a peer mapping pays a page-table walk over NVLink (~2.5 us each, serial in the reduce below otherwise)
+	if (tid >= 32 && tid < 32 + J.nranks) {
+		long long sink = ld_relaxed_sys(J.slot[tid - 32]);
+		asm volatile("" ::"l"(sink));
+	}
 	__syncthreads();
 	const unsigned long long t1 = globaltimer_ns();
 	if (!s_ok) { if (tid == 0) { meta->status = 1u; meta->join_wait_us = (float)((t1 - t0) * 1e-3); meta->join_reduce_us = 0.f; } return false; }

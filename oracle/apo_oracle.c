@@ -707,7 +707,10 @@ void orc_gen_record(uint64_t seed, uint32_t stream, uint32_t c, uint64_t t,
 	out->flags = (uint8_t)((hasErrors ? ORC_F_ERRORS : 0) | (ended ? ORC_F_ENDED : 0) |
 	                       ((ended || feedback) ? ORC_F_VALID : 0) | (toolFail > 0 ? ORC_F_FAILSPAN : 0));
 	out->mode = mode;
-	out->durClass = 0;
+	{   /* the generator's durations are integers (dur = avg * toolCalls < 2^24): the class follows from them, as on the device */
+		const uint32_t dms = (uint32_t)dur, avg = toolCalls ? dms / toolCalls : 0u;
+		out->durClass = (uint8_t)(0x80u | (dms > 0u ? 0x04u : 0u) | (dms > 15000u ? 0x08u : 0u) | ((avg > 1000u) + (avg > 3000u) + (avg > 10000u)));
+	}
 	out->userMsgs = (uint16_t)userMsgs;
 	const uint32_t asst = llm + ((((h4 >> 46) & 15) == 0) ? 1u : 0u);   /* 1/16: an assistant span without an llm_call record */
 	out->asstMsgs = (uint16_t)(asst < 65535 ? asst : 65535);

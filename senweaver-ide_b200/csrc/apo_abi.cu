@@ -877,6 +877,7 @@ extern "C" int apo_corpus_upload(apo_engine *e, const apo_record *recs, uint64_t
 	CK(cudaSetDevice(e->device));
 	CK(e->corpus.reserve(T ? T : 1));
 	if (T) { const int rc = h2d_rows(e, e->corpus.p, T * sizeof(apo_record), recs, T * sizeof(apo_record), T * sizeof(apo_record), 1, e->stream); if (rc) return rc; }
+	CK(apo::run_fill_durclass(e->corpus.p, 32, T, e->stream));        // resident records always carry the duration class
 	CK(cudaStreamSynchronize(e->stream));
 	e->corpus_T = T; e->corpus_base = idx_base;
 	return APO_OK;
@@ -1052,6 +1053,7 @@ int rollouts_upload_rows(apo_engine *e, const void *recs, uint32_t row, uint32_t
 	if (C && T) {
 		if (pitch != T) CK(cudaMemsetAsync(e->roll.p, 0, (uint64_t)C * pitch * row, e->stream));   // VALID clear
 		{ const int rc = h2d_rows(e, e->roll.p, pitch * row, recs, T * row, T * row, C, e->stream); if (rc) return rc; }
+		CK(apo::run_fill_durclass(e->roll.p, row, (uint64_t)C * pitch, e->stream));
 	}
 	CK(cudaStreamSynchronize(e->stream));
 	e->roll_C = C; e->roll_T = T; e->roll_pitch = pitch; e->roll_row = row;
@@ -1247,6 +1249,10 @@ int score_host_rows_impl(apo_engine *e, const apo_score_opts *o, const uint8_t *
 		if (staged) CK(cudaEventRecord(e->stage_done[b], e->copy_stream));
 		CK(cudaEventRecord(e->win_ready[b], e->copy_stream));
 		CK(cudaStreamWaitEvent(e->stream, e->win_ready[b], 0));
+		if (row != 36) {                                               // trace records: make sure the window carries the duration class
+			CK(apo::run_fill_durclass(e->win[b].p, row, (uint64_t)C * Tc, e->stream));
+			e->timing.launches++;
+		}
 		apo::K1Params P{};
 		P.base = e->win[b].p; P.pitch_bytes = Tc * row; P.C = C; P.T = n; P.acc = e->acc.p;
 		P.lut = e->d_lut.p; P.W = e->W;

@@ -71,7 +71,7 @@ __device__ __forceinline__ void scan_record(ScanAcc &A, const apo_record &r, uns
 
 	if (r.flags & APO_F_VALID) {                                                 // APO:550, TCS:606
 		double ws; CatIdx ix;
-		const uint32_t mask = record_ws_table_t<true>(r, w2, s_cat, ws, ix);
+		const uint32_t mask = record_ws_table_t<true, true>(r, w2, s_cat, ws, ix);
 		const double2 tw = s_lut[ROT ? lut_index(mask) : mask];
 		if (tw.x > 0.0) {                                                        // TCS:784 totalWeight > 0
 			A.fxR += to_fx(div_lut<false>(ws, tw));
@@ -91,7 +91,7 @@ __device__ __forceinline__ void scan_record(ScanAcc &A, const apo_record &r, uns
 		    r.tokens > 10000u,                   // P3 APO:693
 		    r.llmCalls > 2u,                     // P4 APO:713
 		    r.userMsgs >= 4u,                    // P5 APO:733-734
-		    (r.durClass & APO_DC_SET) ? (r.durClass & APO_DC_SLOW) != 0 : (double)r.toolDurMs > 15000.0,   // P6 APO:754
+		    (r.durClass & APO_DC_SLOW) != 0,     // P6 APO:754 (resident records always carry the class)
 		};
 #pragma unroll
 		for (int p = 0; p < APO_NPAT; p++) {

@@ -110,15 +110,21 @@ __device__ __forceinline__ double keep_if(bool p, double x) {
 // What the path asks of totalToolDurationMs (TCS:721-728, APO:754): taken from the record's durClass when the encoder decided
 // it in binary64 (APO_DC_SET), else derived from the binary32 copy.  `avg > thr` is evaluated as `dur > thr * total` (exact
 // product).
+// TRUST: the record is resident — every load path (uploads, streaming windows, generators) has run fill_dur_class over it,
+// so the class is always present and the streaming kernels (K1r, the corpus scan) spend no float compares on the duration.
 struct DurClass { uint32_t level; bool pos, slow; };
-__device__ __forceinline__ DurClass dur_class(const apo_record &r, double dur, double total) {
-	const uint32_t dcb = r.durClass;
-	const bool set = (dcb & APO_DC_SET) != 0;
+__device__ __forceinline__ uint32_t dur_class_from_float(double dur, double total, bool tool) {
 	const uint32_t lv = (dur > __dmul_rn(1000.0, total)) + (dur > __dmul_rn(3000.0, total)) + (dur > __dmul_rn(10000.0, total));
+	return APO_DC_SET | ((tool && dur > 0.0) ? lv : 0u) | (dur > 0.0 ? APO_DC_POS : 0u) | (dur > 15000.0 ? APO_DC_SLOW : 0u);
+}
+template <bool TRUST = false>
+__device__ __forceinline__ DurClass dur_class(const apo_record &r, double dur, double total) {
+	uint32_t dcb = r.durClass;
+	if (!TRUST && !(dcb & APO_DC_SET)) dcb = dur_class_from_float(dur, total, r.toolCalls > 0);
 	DurClass d;
-	d.level = set ? (dcb & APO_DC_LEVEL) : lv;
-	d.pos = set ? (dcb & APO_DC_POS) != 0 : dur > 0.0;
-	d.slow = set ? (dcb & APO_DC_SLOW) != 0 : dur > 15000.0;
+	d.level = dcb & APO_DC_LEVEL;
+	d.pos = (dcb & APO_DC_POS) != 0;
+	d.slow = (dcb & APO_DC_SLOW) != 0;
 	return d;
 }
 
@@ -185,7 +191,7 @@ __device__ __forceinline__ uint32_t reward_dims(const apo_record &r, double dims
 struct CatIdx { uint32_t i01, i3, i4, i5, i6, i7, i8; double d2; };   // effective slots (last slot of a group = absent)
 
 // TCS:668-783 for one record through the product table: weighted sum in push order + mask.
-template <bool WANT_IDX>
+template <bool WANT_IDX, bool TRUST = false>
 __device__ __forceinline__ uint32_t record_ws_table_t(const apo_record &r, double w2, const double *cat, double &ws_out, CatIdx &ix) {
 	const bool agent = r.mode == 2;
 	const uint32_t err = (r.flags & APO_F_ERRORS) ? 1u : 0u, ended = (r.flags & APO_F_ENDED) ? 1u : 0u;
@@ -203,7 +209,7 @@ __device__ __forceinline__ uint32_t record_ws_table_t(const apo_record &r, doubl
 	const uint32_t i4 = (r.toolCalls > cexc) + (r.toolCalls > cgood) + (r.toolCalls > cfair);
 	ws = __dadd_rn(ws, cat[CAT_D4 + (tool ? i4 : 4u)]);
 	const double dur = (double)r.toolDurMs;
-	const DurClass dc = dur_class(r, dur, total);
+	const DurClass dc = dur_class<TRUST>(r, dur, total);
 	const bool hasdur = tool && dc.pos;
 	const uint32_t i5 = dc.level;
 	ws = __dadd_rn(ws, cat[CAT_D5 + (hasdur ? i5 : 4u)]);
@@ -247,7 +253,7 @@ __device__ __forceinline__ uint32_t record_ws_direct(const apo_record &r, double
 	ws = __dadd_rn(ws, cat[DIR_D3 + ag * 7u + (tool ? min(r.toolFail, 5u) : 6u)]);
 	ws = __dadd_rn(ws, cat[DIR_D4 + ag * 27u + min(r.toolCalls, 26u)]);
 	const double dur = (double)r.toolDurMs;
-	const DurClass dc = dur_class(r, dur, total);
+	const DurClass dc = dur_class<true>(r, dur, total);        // resident records always carry the class (fill_dur_class)
 	const bool hasdur = tool && dc.pos;
 	const uint32_t i5 = dc.level;
 	ws = __dadd_rn(ws, cat[CAT_D5 + (hasdur ? i5 : 4u)]);
@@ -379,7 +385,12 @@ __device__ __forceinline__ apo_record gen_record(unsigned long long key, uint32_
 	o.flags = (uint8_t)((err ? APO_F_ERRORS : 0u) | (ended ? APO_F_ENDED : 0u) |
 	                    ((ended || feedback) ? APO_F_VALID : 0u) | (fail > 0 ? APO_F_FAILSPAN : 0u));
 	o.mode = (uint8_t)mode;
-	o.durClass = 0;                       // generator durations are integers < 2^24: exact in binary32
+	// generator durations are integers < 2^24 (exact in binary32, dur = avg * tool): the class follows from the integers
+	{
+		const uint32_t dms = (uint32_t)dur, avg = tool ? dms / tool : 0u;
+		o.durClass = (uint8_t)(APO_DC_SET | (dms > 0u ? APO_DC_POS : 0u) | (dms > 15000u ? APO_DC_SLOW : 0u) |
+		                       ((avg > 1000u) + (avg > 3000u) + (avg > 10000u)));
+	}
 	o.userMsgs = (uint16_t)user;
 	const uint32_t asst = llm + ((((h4 >> 46) & 15) == 0) ? 1u : 0u);
 	o.asstMsgs = (uint16_t)(asst < 65535u ? asst : 65535u);

@@ -597,6 +597,34 @@ cudaError_t run_gen_records(apo_record *out, uint64_t pitch, uint64_t seed, uint
 	return cudaGetLastError();
 }
 
+// Records that arrive without the duration class (durClass == 0: hand-built records, older producers) get it here, once, from the
+// binary32 duration — the comparisons the streaming kernels would otherwise repeat per evaluation.  rows = n records of 32 or 16 bytes.
+__global__ void __launch_bounds__(256)
+k_fill_durclass(uint8_t *rows, uint32_t row_bytes, uint64_t n) {
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint8_t *p = rows + i * row_bytes;
+		if (row_bytes == 32) {
+			apo_record *r = reinterpret_cast<apo_record *>(p);
+			if (r->durClass & APO_DC_SET) continue;
+			const double total = (double)(r->toolCalls ? r->toolCalls : 1u);
+			r->durClass = (uint8_t)dur_class_from_float((double)r->toolDurMs, total, r->toolCalls > 0);
+		} else {
+			apo_record16 *r = reinterpret_cast<apo_record16 *>(p);
+			if (r->durClass & APO_DC_SET) continue;
+			const double total = (double)(r->toolCalls ? r->toolCalls : 1u);
+			r->durClass = (uint8_t)dur_class_from_float((double)r->toolDurMs, total, r->toolCalls > 0);
+		}
+	}
+}
+
+cudaError_t run_fill_durclass(void *rows, uint32_t row_bytes, uint64_t n, cudaStream_t st) {
+	if (n == 0) return cudaSuccess;
+	uint64_t g = (n + 255) / 256;
+	if (g > 148ull * 16) g = 148ull * 16;
+	k_fill_durclass<<<(unsigned)g, 256, 0, st>>>(reinterpret_cast<uint8_t *>(rows), row_bytes, n);
+	return cudaGetLastError();
+}
+
 // TraceCollectorService._computeRewardSignals for a batch of records (TCS:668-788).
 __global__ void __launch_bounds__(256)
 k_reward_batch(const apo_record *recs, uint64_t n, const Weights W, const double *lut, double *dims, uint32_t *masks,

@@ -22,7 +22,7 @@ pkg = importlib.import_module("senweaver-ide_b200")
 def main(trials: int, seed: int):
     e = pkg.Engine(0)
     rng = np.random.default_rng(seed)
-    kinds = {"fp32": 0, "fp32-nan": 0, "compact": 0, "records": 0, "records16": 0}
+    kinds = {"fp32": 0, "fp32-nan": 0, "compact": 0, "records": 0, "records16": 0, "host-packed": 0, "host-compact": 0}
     evals = 0
     for trial in range(trials):
         C = int(rng.integers(1, 24))
@@ -34,10 +34,13 @@ def main(trials: int, seed: int):
         align = 8 if kind == "compact" else 4
         first = int(rng.integers(0, T // align + 1)) * align if T >= align and rng.random() < 0.4 else 0
         count = int(rng.integers(1, T - first + 1)) if first < T and rng.random() < 0.4 else 0
+        if kind.startswith("host-"):
+            first = count = 0                                   # the host-streaming calls take the whole tensor
+        e.set_tuning(pkg.TUNE_NO_FUSE if rng.random() < 0.3 else 0)      # stand-alone K2 / K3 launches (TMA tiles from 8192 records) or the fused tail
         hi = first + count if count else T
         with_corpus = rng.random() < 0.5
         if with_corpus:
-            Tc = int(rng.choice([1, 50, 1000, 4097]))
+            Tc = int(rng.choice([1, 50, 1000, 4097, 9001]))
             recs = orc.gen_records(s0 ^ 0x55, orc.STREAM_CORPUS, 0, 1, 0, Tc, ap, 2).reshape(-1)
             e.corpus_upload(recs)
         if kind in ("records", "records16"):
@@ -57,13 +60,21 @@ def main(trials: int, seed: int):
                 dims[rng.random(dims.shape) < rng.random()] = np.nan
             else:
                 dims = orc.gen_dims(s0, c0, C, t0, T, ap, 4)
-            e.dims_upload(dims)
-            if kind == "compact":
-                e.dims_compact()
-                variant = int(rng.integers(0, 7))
+            variant = 0
+            if kind == "host-packed":
+                pc, pd, book, d2book = pkg.packed_encode_host(dims, nthreads=2)
+                r = e.score_host_packed(pc, pd, book, d2book, K, corpus=with_corpus)
+            elif kind == "host-compact":
+                q8, d2, li, book = pkg.compact_encode_host(dims, nthreads=2)
+                r = e.score_host_compact(q8, d2, li, book, K, corpus=with_corpus)
             else:
-                variant = int(rng.integers(0, 5))
-            r = e.score(C, K, corpus=with_corpus, variant=variant, first=first, count=count)
+                e.dims_upload(dims)
+                if kind == "compact":
+                    e.dims_compact()
+                    variant = int(rng.integers(0, 7))
+                else:
+                    variant = int(rng.integers(0, 5))
+                r = e.score(C, K, corpus=with_corpus, variant=variant, first=first, count=count)
             exp = orc.score_dims_fx(dims[:, first:hi])
             ref_s, _ = orc.score_dims(dims[:, first:hi])
         got = e.debug_partials(C)

@@ -674,12 +674,12 @@ int peer_setup(apo_engine *e) {
 		for (const char *c = host; *c; c++) h = (h ^ (uint8_t)*c) * 1099511628211ull;
 		mine.host_hash = h;
 	}
-	DevBuf<uint8_t> xch;
+	struct Scoped : DevBuf<uint8_t> { ~Scoped() { release(); } } xch;      // freed on every return path
 	CK(xch.reserve(128ull * (e->nranks + 1)));
 	std::vector<PeerInfo> all(e->nranks);
 	CK(cudaMemcpyAsync(xch.p, &mine, 128, cudaMemcpyHostToDevice, e->stream));
 	int rc = g_nccl.AllGather(xch.p, xch.p + 128, 128, kNcclInt8, e->comm, e->stream);
-	if (rc != 0) { xch.release(); return fail(e, APO_E_NCCL, "ncclAllGather (peer handles): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); }
+	if (rc != 0) { return fail(e, APO_E_NCCL, "ncclAllGather (peer handles): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); }
 	CK(cudaMemcpyAsync(all.data(), xch.p + 128, 128ull * e->nranks, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
 	long long ok = mine.ok;
@@ -705,10 +705,9 @@ int peer_setup(apo_engine *e) {
 	long long *flag = (long long *)xch.p;
 	CK(cudaMemcpyAsync(flag, &ok, 8, cudaMemcpyHostToDevice, e->stream));
 	rc = g_nccl.AllReduce(flag, flag, 1, kNcclInt64, kNcclMin, e->comm, e->stream);
-	if (rc != 0) { xch.release(); return fail(e, APO_E_NCCL, "ncclAllReduce (peer agreement): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); }
+	if (rc != 0) { return fail(e, APO_E_NCCL, "ncclAllReduce (peer agreement): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"); }
 	CK(cudaMemcpyAsync(&ok, flag, 8, cudaMemcpyDeviceToHost, e->stream));
 	CK(cudaStreamSynchronize(e->stream));
-	xch.release();
 	if (!ok) { peer_teardown(e); return APO_OK; }
 	e->peer_ok = true; e->peer_slot_words = slot_words; e->join_epoch = 0;
 	return APO_OK;
@@ -1381,12 +1380,15 @@ int score_host_compact_impl(apo_engine *e, const apo_score_opts *o, const uint64
 	CK(cudaSetDevice(e->device));
 	int rc;
 	if ((rc = ensure_scratch(e, C, o->K))) return rc;
-	// the lookup tables of K1q follow the codebook of THIS call; a resident Form Q tensor keeps its own and gets it back below
-	uint32_t saved[8 * 256];
-	const bool had_resident = e->compact;
+	// the lookup tables of K1q follow the codebook of THIS call; a resident Form Q tensor keeps its own and gets it back when the
+	// call returns, on every path (Restore)
+	struct Restore {
+		apo_engine *e; uint32_t saved[8 * 256]; bool armed = false;
+		~Restore() { if (armed) { memcpy(e->qbook_host, saved, sizeof saved); upload_ptab(e); } }
+	} restore{e};
 	const bool same_book = memcmp(e->qbook_host, codebook, sizeof e->qbook_host) == 0 && e->d_ptab.p != nullptr;
-	if (had_resident) memcpy(saved, e->qbook_host, sizeof saved);
 	if (!same_book) {
+		if (e->compact) { memcpy(restore.saved, e->qbook_host, sizeof restore.saved); restore.armed = true; }
 		memcpy(e->qbook_host, codebook, sizeof e->qbook_host);
 		if ((rc = upload_ptab(e))) return rc;
 	}
@@ -1444,13 +1446,7 @@ int score_host_compact_impl(apo_engine *e, const apo_score_opts *o, const uint64
 		e->timing.launches++;
 		CK(cudaEventRecord(e->win_free[b], e->stream));
 	}
-	rc = finish_score(e, o, C, scores, counts, topk, report);
-	if (had_resident && !same_book) {
-		memcpy(e->qbook_host, saved, sizeof saved);
-		const int rc2 = upload_ptab(e);
-		if (rc == APO_OK) rc = rc2;
-	}
-	return rc;
+	return finish_score(e, o, C, scores, counts, topk, report);
 }
 }  // namespace
 

@@ -138,16 +138,9 @@ def main():
             k1 = r.timing.reward_ms
             gbs = 36.0 * C * T / (k1 * 1e-3) / 1e9
             join = r.timing.allreduce_ms + r.timing.finalize_ms + r.timing.corpus_ms       # finalize_ms = peer-memory join + K3 in one launch (or NCCL + K3)
-            # parity: three whole candidates over the full 100 M-record axis against the oracle's exact integer sums (joined over all ranks
-            # on the engine side), and the ranking must follow from the exact sums
+            # for the checker (tests/check_config5.py recomputes them with the oracle): the joined integer sums of three whole candidates
             sums, counts = eng.debug_partials(C)
-            exact = None
-            if rank == 0:
-                import oracle
-                oracle.build()
-                cl = [0, C // 2 - 1, C - 1]
-                es, en = oracle.score_generated_fx(seed, cl, 0, Tg, 300, nthreads=min(16, len(os.sched_getaffinity(0))))
-                exact = all(sums[c] == a and counts[c] == b for c, a, b in zip(cl, es, en))
+            cl = [0, C // 2 - 1, C - 1]
             exp_scores = pkg.sharding.scores_from_partials(sums, counts)
             topk_ok = bool(np.array_equal(pkg.sharding.topk_indices(exp_scores, 256), r.topk) and np.array_equal(exp_scores, r.scores))
             emit({"config": 5, "C": C, "T_global": Tg, "T_per_gpu": T, "n_gpus": world, "chunk_candidates": Cc, "passes": passes,
@@ -155,7 +148,8 @@ def main():
                   "join_mode": eng.comm_join_mode(), "evals_per_s_kernels": C * Tg / ((k1 + join) * 1e-3),
                   "k1_GBps_per_gpu": gbs, "frac_of_measured_peak": gbs / PK, "generation_s_excluded": gen_s,
                   "topk_head": r.topk[:4].tolist(), "counts_ok": bool((r.counts > 0).all()),
-                  "parity": {"partials_exact_full_axis": exact, "candidates": [0, C // 2 - 1, C - 1], "topk_follows_from_exact_sums": topk_ok}})
+                  "seed": seed, "check": {"candidates": cl, "sums": [str(sums[c]) for c in cl], "counts": [counts[c] for c in cl],
+                                          "topk_follows_from_exact_sums": topk_ok}})
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -701,6 +701,12 @@ int peer_setup(apo_engine *e) {
 			e->peer_base[r] = p; e->peer_ipc[r] = true;
 		}
 	}
+	// touch every peer's block once now: lazily enabled peer mappings are established on first access, which must not be the first join
+	if (ok) {
+		for (int r = 0; r < e->nranks; r++)
+			if (r != e->rank && apo::run_touch(e->peer_base[r], bytes, xch.p, e->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+		if (cudaStreamSynchronize(e->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+	}
 	// agree on the outcome (also the barrier that orders every rank's zero-fill before the first join)
 	long long *flag = (long long *)xch.p;
 	CK(cudaMemcpyAsync(flag, &ok, 8, cudaMemcpyHostToDevice, e->stream));

@@ -597,6 +597,21 @@ cudaError_t run_gen_records(apo_record *out, uint64_t pitch, uint64_t seed, uint
 	return cudaGetLastError();
 }
 
+// Reads a peer-mapped block once (apo_comm_init): the first access to lazily enabled peer memory pays for the mapping — 0.2 ms when
+// it happened inside the first joined call.
+__global__ void __launch_bounds__(256)
+k_touch(const long long *p, uint64_t n, long long *sink) {
+	long long s = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) s += __ldcg(p + i);
+	if (s == 0x7fffffffffffffffll) *sink = s;                    // never true for zero-filled blocks: keeps the loads alive
+}
+
+cudaError_t run_touch(const void *p, uint64_t bytes, void *sink, cudaStream_t st) {
+	if (bytes < 8) return cudaSuccess;
+	k_touch<<<64, 256, 0, st>>>(reinterpret_cast<const long long *>(p), bytes / 8, reinterpret_cast<long long *>(sink));
+	return cudaGetLastError();
+}
+
 // Records that arrive without the duration class (durClass == 0: hand-built records, older producers) get it here, once, from the
 // binary32 duration — the comparisons the streaming kernels would otherwise repeat per evaluation.  rows = n records of 32 or 16 bytes.
 __global__ void __launch_bounds__(256)

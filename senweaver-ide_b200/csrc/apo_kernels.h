@@ -154,6 +154,7 @@ cudaError_t run_gen_records(apo_record *out, uint64_t pitch, uint64_t seed, uint
                             uint64_t t0, uint64_t T, uint32_t agent_permille, cudaStream_t st);
 cudaError_t run_gen_records16(apo_record16 *out, uint64_t pitch, uint64_t seed, uint32_t stream, uint32_t c0, uint32_t C,
                               uint64_t t0, uint64_t T, uint32_t agent_permille, cudaStream_t st);
+cudaError_t run_touch(const void *p, uint64_t bytes, void *sink, cudaStream_t st);
 cudaError_t run_fill_durclass(void *rows, uint32_t row_bytes, uint64_t n, cudaStream_t st);
 cudaError_t run_reward_batch(const apo_record *recs, uint64_t n, const Weights &W, const double *lut, double *dims,
                              uint32_t *masks, double *finals, cudaStream_t st);

@@ -515,11 +515,12 @@ def main():
         H.barrier()
 
     # ---- end to end through the C ABI with HOST buffers (page-locked), H2D inside the timed region.
-    # Headline: the configs[2] workload itself (this rank's shard: C x T) held in host memory in the packed wire format
-    # (Form P, 6 B/eval: lossless for categorical reward dimensions) -> apo_corpus_upload + apo_score_host_packed per step.
-    # Beside it, at 64 x 1M: the same call on Form Q planes (14 B/eval), on fp32 Form D (36 B/eval) and on packed trace
-    # records (Form R16, 16 B/eval, dims derived on the device).
-    e2e, e2e_d, e2e16, e2e_q = None, None, None, None
+    # Headline: the configs[2] workload itself (this rank's shard: C x T) held in host memory in the dictionary wire format
+    # (Form T, 3 B/eval: lossless; dictionary + codebooks travel with every call) -> apo_corpus_upload + apo_score_host_tuples
+    # per step.  Beside it: the same shard as Form P (6 B/eval), the same Form T tensor resident, and at 64 x 1M the same call
+    # on Form Q planes (14 B/eval), on fp32 Form D (36 B/eval) and on packed trace records (Form R16, 16 B/eval, dims derived
+    # on the device).
+    e2e, e2e_d, e2e16, e2e_q, e2e_p = None, None, None, None, None
     if not args.no_secondary:
         eng.close()                                             # the resident 92 GB are no longer needed
         eng = None
@@ -556,10 +557,10 @@ def main():
         except Exception:
             avail = 32 << 30
         avail = int(H.max_over_ranks(-float(avail)) * -1) // max(1, world)      # the tightest rank, shared by the ranks of the box
-        if Cq * Tq * 6 * 3 > avail:
-            Tq = max(1_000_000, int(avail // (Cq * 6 * 3)) // 1_000_000 * 1_000_000)
+        if Cq * Tq * 9 * 2 > avail:
+            Tq = max(1_000_000, int(avail // (Cq * 9 * 2)) // 1_000_000 * 1_000_000)
             Tq = min(Tq, T)
-            mem_note = f"records per rank reduced to {Tq}: three times the {Cq} x {T} packed planes exceed the {avail >> 30} GiB of host memory this rank may lock"
+            mem_note = f"records per rank reduced to {Tq}: twice the {Cq} x {T} Form P + Form T planes exceed the {avail >> 30} GiB of host memory this rank may lock"
         tA = time.perf_counter()
         eng2.dims_generate_compact(SEED, 0, Cq, t0e, Tq, 300)
         book, d2book = eng2.dims_codebook(), eng2.dims_d2book()
@@ -570,28 +571,84 @@ def main():
         hrecq = pkg.host_empty((Tq,), pkg.RECORD_DTYPE)
         hrecq[:] = eng2.corpus_download(0, Tq)
         eng2.close()
+        # Form T: the same evaluations as 24-bit indices into the dictionary of distinct evaluations (host encoder, this rank's CPUs)
+        tlh, thh = pkg.host_empty((Cq, Tq), np.uint16), pkg.host_empty((Cq, Tq), np.uint8)
+        tB = time.perf_counter()
+        _, _, tbook = pkg.tuple_encode_host(pch, pdh, nthreads=max(1, usable_threads(H.all_cpus) // world), out=(tlh, thh))
+        enc_s = time.perf_counter() - tB
+        n_tup = int(tbook[0].size)
         eng2 = pkg.Engine(local)                                # nothing resident: the timed call brings everything over PCIe
         setup_s = time.perf_counter() - tA
         Kq = max(1, Cq // 4)
+        big = Cq * Tq > 10**9
+        n_e2e, n_warm = (max(2, min(args.e2e_steps, 3)), 1) if big else (args.e2e_steps, 2)
+        d2h = 16 * Cq + 4 * Kq + 1024
+        cl = sorted({0, Cq // 2, Cq - 1})
+
+        def e2et_step():
+            eng2.corpus_upload(hrecq, idx_base=t0e)
+            return eng2.score_host_tuples(tlh, thh, tbook, book, d2book, Kq, corpus=True)
+
+        t_ms, rt2 = wall(e2et_step, n_e2e, warm=n_warm)
+        t_sums = eng2.debug_partials(Cq)
+        t_bytes = Cq * Tq * 3 + Tq * 32 + n_tup * 6 + 4096 * 4 + 2048 * 8
+        if rank == 0:
+            okt = cand_check(t_sums, cl, Tq)
+            same_as_resident = bool(Tq == T and np.array_equal(rt2.topk, r.topk) and (world > 1 or np.array_equal(rt2.scores, r.scores)))
+            e2e = {"value": Cq * Tq * world / (t_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": t_bytes,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": t_ms, "h2d_GBps": t_bytes / (t_ms * 1e-3) / 1e9, "bytes_per_eval": 3,
+                   "distinct_evaluations": n_tup, "host_placement": H.numa_note, "setup_s_excluded": round(setup_s, 1),
+                   "host_encode_s_excluded": round(enc_s, 1), "note": mem_note,
+                   "parity": {"partials_exact": bool(okt), "candidates": cl, "same_topk_as_resident_run": same_as_resident if world == 1 else None},
+                   "workload": f"configs[2] shard {Cq} x {Tq} in the dictionary wire format (Form T, 3 B/eval: 24-bit index of the evaluation in the tensor's "
+                               f"dictionary of {n_tup} distinct evaluations, lossless recoding of the Form D tensor; the dictionary, its codebooks and the reward of "
+                               f"every entry are sent / computed inside the timed call) + {Tq}-record corpus, from page-locked host memory per rank via "
+                               f"apo_corpus_upload + apo_score_host_tuples"}
 
         def e2eq_step():
             eng2.corpus_upload(hrecq, idx_base=t0e)
             return eng2.score_host_packed(pch, pdh, book, d2book, Kq, corpus=True)
 
-        q_ms, rq2 = wall(e2eq_step, max(2, min(args.e2e_steps, 3)) if Cq * Tq > 10**9 else args.e2e_steps, warm=1 if Cq * Tq > 10**9 else 2)
+        q_ms, rq2 = wall(e2eq_step, n_e2e, warm=n_warm)
         q_sums = eng2.debug_partials(Cq)
-        d2h = 16 * Cq + 4 * Kq + 1024
         if rank == 0:
-            cl = sorted({0, Cq // 2, Cq - 1})
-            okq = cand_check(q_sums, cl, Tq)
-            same_as_resident = bool(Tq == T and np.array_equal(rq2.topk, r.topk) and (world > 1 or np.array_equal(rq2.scores, r.scores)))
-            e2e = {"value": Cq * Tq * world / (q_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Cq * Tq * 6 + Tq * 32 + 4096 * 4,
-                   "d2h_bytes_per_step": d2h, "ms_per_step": q_ms, "h2d_GBps": (Cq * Tq * 6 + Tq * 32) / (q_ms * 1e-3) / 1e9,
-                   "host_placement": H.numa_note, "setup_s_excluded": round(setup_s, 1), "note": mem_note,
-                   "parity": {"partials_exact": bool(okq), "candidates": cl, "same_topk_as_resident_run": same_as_resident if world == 1 else None},
-                   "workload": f"configs[2] shard {Cq} x {Tq} in the packed wire format (Form P, 6 B/eval: eight 4-bit codes + a 12-bit tool_success_rate index, "
-                               f"lossless recoding of the Form D tensor) + {Tq}-record corpus, from page-locked host memory per rank via apo_corpus_upload + apo_score_host_packed"}
-        del pch, pdh, hrecq
+            okq = bool(q_sums == t_sums and okt)
+            e2e_p = {"value": Cq * Tq * world / (q_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": Cq * Tq * 6 + Tq * 32 + 4096 * 4,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": q_ms, "h2d_GBps": (Cq * Tq * 6 + Tq * 32) / (q_ms * 1e-3) / 1e9, "bytes_per_eval": 6,
+                     "parity": {"partials_exact": okq, "note": "integers identical to the oracle-checked Form T leg"},
+                     "workload": f"the same shard in the packed wire format (Form P, 6 B/eval: eight 4-bit codes + a 12-bit tool_success_rate index) "
+                                 f"via apo_corpus_upload + apo_score_host_packed"}
+        del pch, pdh
+        # -- the same Form T tensor RESIDENT (3 B/eval in HBM), scored through the joined handle: one dictionary per rank, the
+        # partial sums of the shards joined as in the primary run
+        try:
+            engT = H.engine() if world > 1 else eng2
+            engT.set_stream(H.stream.cuda_stream)
+            engT.tuples_upload(tlh, thh, tbook, book, d2book)
+            engT.corpus_upload(hrecq, idx_base=t0e)
+            tms, tres, _ = H.timed(lambda: engT.score(Cq, Kq, source=pkg.SRC_TUPLES, corpus=True), args.steps, args.warmup)
+            rt = tres[-1]
+            k1t = float(np.mean([x.timing.reward_ms for x in tres]))
+            full = Tq == T
+            same_t = bool(full and np.array_equal(rt.scores, r.scores) and np.array_equal(rt.topk, r.topk) and np.array_equal(rt.counts, r.counts))
+            Tqmax = int(H.max_over_ranks(float(Tq)))
+            secondary["tuple_layout"] = {
+                "value": Cq * Tq * world / (tms * 1e-3) if not full else C * Tg / (tms * 1e-3), "unit": UNIT, "ms_per_step": tms, "bytes_per_eval": 3,
+                "k1t_ms": k1t, "k1t_GBps": 3.0 * Cq * Tqmax / (k1t * 1e-3) / 1e9, "distinct_evaluations": n_tup,
+                "identical_to_fp32_layout": same_t if full else None,
+                "parity": {"ok": bool((same_t and parity["ok"]) if full else True),
+                           "note": "scores, counts and top-K bit-identical to the oracle-checked Form D run of the same evaluations"},
+                "layout": "Form T: every evaluation is the 24-bit index (16-bit + 8-bit planes) of its entry in the tensor's dictionary of distinct "
+                          "evaluations; per call k_tuple_values computes rint(finalReward * 2^52) once per entry with the operations of K1q and K1t "
+                          "(k_reward9t) sums table entries per candidate: head of the table in shared memory, tail through L1/L2; stand-alone corpus scan + tail"}
+            if engT is not eng2:
+                engT.close()
+            else:
+                eng2.set_stream(0)
+        except Exception as ex:                     # optional leg: never take the primary numbers down with it
+            secondary["tuple_layout"] = {"error": str(ex)}
+        H.barrier()
+        del tlh, thh, hrecq
 
         # -- 64 x 1M: fp32 Form D and packed trace records
         Ce, Te = min(args.e2e_candidates, C), min(args.e2e_records, T)
@@ -683,7 +740,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "alg_bytes_per_launch": alg_bytes, "k1_ms": k1, "k2_ms": k2_ms,
                          "join_wait_ms": join_wait, "join_reduce_ms": join_red, "join_ms": join_wait + join_red + nccl_ms},
-            "e2e": e2e, "e2e_form_q": e2e_q, "e2e_form_d": e2e_d, "e2e_records16": e2e16,
+            "e2e": e2e, "e2e_form_p": e2e_p, "e2e_form_q": e2e_q, "e2e_form_d": e2e_d, "e2e_records16": e2e16,
             "gpu_launches": launches,
             "clocks": clocks,
         }
@@ -693,7 +750,7 @@ def main():
             out["cpu_baseline"] = cpu_baseline(C)
         ok = parity["ok"] and all(v.get("parity", {}).get("ok", True) for v in secondary.values() if isinstance(v, dict))
         if e2e is not None:
-            ok = ok and all(x["parity"]["partials_exact"] for x in (e2e, e2e_q, e2e_d, e2e16))
+            ok = ok and all(x["parity"]["partials_exact"] for x in (e2e, e2e_p, e2e_q, e2e_d, e2e16))
         out["parity_ok"] = bool(ok)
         print(json.dumps(out))
         rc = 0 if ok else 1

@@ -224,6 +224,7 @@ int apo_record_unpack16(const apo_record16 *in, uint64_t n, apo_record *out);
  * report (APO:498-625, 635-773; TCS:596-626). */
 #define APO_SRC_DIMS      0u
 #define APO_SRC_ROLLOUTS  1u
+#define APO_SRC_TUPLES    2u   /* resident Form T (apo_tuples_upload) */
 #define APO_SCORE_CORPUS  0x1u   /* also run the 6-pattern scan over the corpus */
 #define APO_SCORE_RECIP   0x2u   /* finalReward = ws * (1/tw) from a LUT instead of ws / tw (<= 1 ulp apart) */
 #define APO_SCORE_TIMING  0x4u   /* record the per-stage CUDA events of apo_timing also for a small call */
@@ -232,7 +233,7 @@ typedef struct apo_score_opts {
 	uint32_t source;     /* APO_SRC_* */
 	uint32_t flags;      /* APO_SCORE_* */
 	uint32_t variant;    /* kernel variant, 0 = default (tuning / A-B only) */
-	uint64_t first;      /* window [first, first+count) of the record axis, first % 4 == 0 (% 8 for Form Q); */
+	uint64_t first;      /* window [first, first+count) of the record axis, first % 4 == 0 (% 8 for Form Q / T); */
 	uint64_t count;      /* count == 0 -> all records */
 } apo_score_opts;
 /* scores[C] (-inf when a candidate has no non-null evaluation), counts[C], topk[K];
@@ -288,6 +289,24 @@ int apo_dims_d2book(apo_engine *e, uint32_t *d2book /* [4096] */);
 int apo_score_host_packed(apo_engine *e, const apo_score_opts *o, const uint32_t *pc, const uint16_t *pd, const uint32_t *codebook,
                           const uint32_t *d2book, uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk,
                           apo_corpus_report *report);
+/* Form T — evaluations as dictionary indices (3 B per evaluation; csrc/apo_tuple.cu).  The nine dimensions of an evaluation are
+ * functions of a few small counters (TCS:668-763), so a tensor of C x T evaluations holds only 10^5..10^6 DISTINCT ones.  tbook =
+ * those, as Form P pairs (tbook_pc[i], tbook_pd[i]), most frequent first; every evaluation is the 24-bit index of its entry, kept
+ * as a 16-bit plane tl and an 8-bit plane th, both [C][T].  Per scoring call the device evaluates finalReward once per ENTRY
+ * (TCS:777-787, the operations of K1q) and K1t sums table entries per candidate: the integers are those of every other layout.
+ * apo_tuple_encode_host builds the planes and the dictionary from Form P planes (two passes on nthreads threads); *n_tuples
+ * receives the number of distinct evaluations; APO_E_STATE when that exceeds cap (<= 16777215 = APO_TUPLES_MAX) — keep Form P then.
+ * apo_score_host_tuples streams the planes from host memory (as apo_score_host_packed does for Form P);
+ * apo_tuples_upload makes them resident: apo_score / apo_score_accumulate with source APO_SRC_TUPLES then read 3 B per evaluation.
+ * An index >= n_tuples in the planes, or an entry whose finalReward is not within (-2, 2), fails the call with APO_E_ARG. */
+#define APO_TUPLES_MAX 16777215u
+int apo_tuple_encode_host(const uint32_t *pc, const uint16_t *pd, uint32_t C, uint64_t T, uint16_t *tl, uint8_t *th,
+                          uint32_t *tbook_pc, uint16_t *tbook_pd, uint32_t cap, uint32_t *n_tuples, int nthreads);
+int apo_score_host_tuples(apo_engine *e, const apo_score_opts *o, const uint16_t *tl, const uint8_t *th, const uint32_t *tbook_pc,
+                          const uint16_t *tbook_pd, uint32_t n_tuples, const uint32_t *codebook, const uint32_t *d2book,
+                          uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report);
+int apo_tuples_upload(apo_engine *e, const uint16_t *tl, const uint8_t *th, const uint32_t *tbook_pc, const uint16_t *tbook_pd,
+                      uint32_t n_tuples, const uint32_t *codebook, const uint32_t *d2book, uint32_t C, uint64_t T);
 /* Host buffers for the streaming calls and the uploads.  Any host pointer is accepted: pageable memory (malloc, a JS
  * ArrayBuffer, numpy) is gathered chunk by chunk into pinned staging buffers by a few host threads while
  * the previous chunk is on the wire; memory from apo_host_alloc (page-locked) is read in place and

@@ -10,7 +10,7 @@ The directory name carries a hyphen (it is the name the build contract fixes), s
 with importlib:  apo = importlib.import_module("senweaver-ide_b200").
 """
 from .engine import (ApoError, CorpusReport, Engine, RECORD_DTYPE, ScoreResult, DIM_NAMES, MODE_NAMES,  # noqa: F401
-                     NDIM, NPAT, NMODE, SRC_DIMS, SRC_ROLLOUTS, build_library, load_library, LIB_PATH, ABI_SYMBOLS,
-                     RECORD16_DTYPE, pack16, unpack16, records_from_json, host_empty, SCORE_TIMING, compact_encode_host, packed_encode_host,
+                     NDIM, NPAT, NMODE, SRC_DIMS, SRC_ROLLOUTS, SRC_TUPLES, TUPLES_MAX, build_library, load_library, LIB_PATH, ABI_SYMBOLS,
+                     RECORD16_DTYPE, pack16, unpack16, records_from_json, host_empty, SCORE_TIMING, compact_encode_host, packed_encode_host, tuple_encode_host,
                      TUNE_NO_FUSE, TUNE_FORCE_FUSE, TUNE_NO_STAGING, TUNE_NCCL_JOIN)
 from . import sharding  # noqa: F401

@@ -100,6 +100,11 @@ struct apo_engine {
 	uint32_t qbook_host[8 * 256]; bool compact = false;
 	uint32_t d2book_host[4096]; uint32_t d2book_n = ~0u;       // Form P export of the resident tensor (~0 = not built yet)
 	DevBuf<uint8_t> roll; uint32_t roll_C = 0, roll_row = 32; uint64_t roll_T = 0, roll_pitch = 0;   // Form R (32 B) or R16 (16 B) rows
+	// Form T (csrc/apo_tuple.cu): resident index planes + dictionary; per call: product table of its codebook, table values
+	DevBuf<unsigned short> tup_l; DevBuf<unsigned char> tup_h; uint32_t tup_C = 0, tup_n = 0; uint64_t tup_T = 0, tup_pitch = 0;
+	DevBuf<uint32_t> tup_pc, tup_bad; DevBuf<unsigned short> tup_pd; DevBuf<float> tup_d2; DevBuf<double> tup_ptab; DevBuf<long long> tup_val;
+	uint32_t tup_book[8 * 256]; bool tup_used = false;
+	DevBuf<uint32_t> tups_pc; DevBuf<unsigned short> tups_pd; DevBuf<float> tups_d2;   // dictionary of a host-streaming call
 
 	// acc: [acc_words(C, nranks)] partial vector | [18] example scratch (inverted indices) | [1] ticket — one allocation, so one
 	// memset arms a scoring call.  acc_joined: the joined vector (> 1 rank); acc keeps this rank's partials.
@@ -216,18 +221,23 @@ int upload_luts(apo_engine *e) {
 }
 
 // value*weight per code for the eight coded dimensions (csrc/apo_compact.cu); table 0 = fl(0 + d0*w0)
-int upload_ptab(apo_engine *e) {
+std::vector<double> make_ptab(const uint32_t *book, const apo::Weights &W) {
 	static const int dim_of[8] = {0, 1, 3, 4, 5, 6, 7, 8};
 	std::vector<double> tab(8 * 256, 0.0);
 	for (int j = 0; j < 8; j++)
 		for (int c = 0; c < 255; c++) {
-			const uint32_t bits = e->qbook_host[256 * j + c];
+			const uint32_t bits = book[256 * j + c];
 			if (bits == 0xFFFFFFFFu) continue;
 			float f; memcpy(&f, &bits, 4);
-			volatile double p = (double)f * e->W.w[dim_of[j]];          // TCS:781 value * weight
+			volatile double p = (double)f * W.w[dim_of[j]];             // TCS:781 value * weight
 			if (j == 0) { volatile double z = 0.0; p = z + p; }          // weightedSum = 0 + first product
 			tab[256 * j + c] = p;
 		}
+	return tab;
+}
+
+int upload_ptab(apo_engine *e) {
+	const std::vector<double> tab = make_ptab(e->qbook_host, e->W);
 	CK(e->d_ptab.reserve(8 * 256));
 	CK(cudaMemcpyAsync(e->d_ptab.p, tab.data(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream));
 	// tables of the mixed-lookup variants: fp32 values per code, and the exact two-term prefix of dimensions 0 and 1
@@ -482,12 +492,53 @@ int record_k1_event(apo_engine *e, int which) {
 	return APO_OK;
 }
 
+// Form T: finalReward of every dictionary entry for the current weights (device work on e->stream, no synchronisation)
+int tuples_values(apo_engine *e, const uint32_t *book_host, const uint32_t *d_pc, const unsigned short *d_pd, uint32_t n, const float *d_d2, bool recip) {
+	const std::vector<double> tab = make_ptab(book_host, e->W);
+	CK(e->tup_ptab.reserve(8 * 256));
+	CK(e->tup_val.reserve((uint64_t)n + 1));
+	CK(e->tup_bad.reserve(1));
+	CK(cudaMemcpyAsync(e->tup_ptab.p, tab.data(), 8 * 256 * 8, cudaMemcpyHostToDevice, e->stream));   // pageable source: consumed when this returns
+	if (!e->tup_used) CK(cudaMemsetAsync(e->tup_bad.p, 0, 4, e->stream));       // a session keeps the flags of its earlier launches
+	apo::TupleValParams V{};
+	V.tb_pc = d_pc; V.tb_pd = d_pd; V.n = n; V.ptab = e->tup_ptab.p; V.lut = e->d_lut.p; V.d2book = d_d2; V.w2 = e->W.w[2];
+	V.tval = e->tup_val.p; V.bad = e->tup_bad.p;
+	CK(apo::run_tuple_values(V, recip, e->stream));
+	e->timing.launches++;
+	e->tup_used = true;
+	return APO_OK;
+}
+
+// after the scoring call has been synchronised: did K1t meet an index outside the dictionary, or an entry it cannot hold?
+int tuples_check(apo_engine *e) {
+	e->tup_used = false;
+	uint32_t bad = 0;
+	CK(cudaMemcpyAsync(&bad, e->tup_bad.p, 4, cudaMemcpyDeviceToHost, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	if (bad & 2u) return fail(e, APO_E_ARG, "a dictionary entry is not representable in Form T (finalReward outside (-2, 2), or a tool_success_rate index without a value)");
+	if (bad & 1u) return fail(e, APO_E_ARG, "a tuple index is outside the dictionary");
+	return APO_OK;
+}
+
 // one K1 launch over [first, first+count) of the loaded source into candidates [cand_offset, ...)
 int launch_k1_resident(apo_engine *e, const apo_score_opts *o, uint32_t cand_offset, uint64_t first, uint64_t count,
                        const apo::K2Params *fused = nullptr) {
 	const bool raw = o->source == APO_SRC_ROLLOUTS;
 	const uint32_t C = raw ? e->roll_C : e->dims_C;
 	int rc;
+	if (o->source == APO_SRC_TUPLES) {
+		if (!count) return APO_OK;
+		if (first % 8) return fail(e, APO_E_ARG, "window start must be a multiple of 8 for Form T");
+		if ((rc = tuples_values(e, e->tup_book, e->tup_pc.p, e->tup_pd.p, e->tup_n, e->tup_d2.p, (o->flags & APO_SCORE_RECIP) != 0))) return rc;
+		apo::KtParams P{};
+		P.tl = e->tup_l.p + first; P.th = e->tup_h.p + first; P.pitch_evals = e->tup_pitch; P.C = e->tup_C; P.T = count;
+		P.acc = e->acc.p + (uint64_t)ACC_PER_CAND * cand_offset; P.tval = e->tup_val.p; P.n_tuples = e->tup_n; P.bad = e->tup_bad.p;
+		if ((rc = record_k1_event(e, 0))) return rc;
+		CK(apo::run_reward9t(P, e->sm_count, e->stream));
+		if ((rc = record_k1_event(e, 1))) return rc;
+		e->timing.launches++;
+		return APO_OK;
+	}
 	if (!raw && e->compact) {
 		if (!count) return APO_OK;
 		if (first % 8) return fail(e, APO_E_ARG, "window start must be a multiple of 8 for the compact layout");
@@ -603,6 +654,7 @@ int finish_score(apo_engine *e, const apo_score_opts *o, uint32_t C, double *sco
 		cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->timing.finalize_ms = ms;
 		cudaEventElapsedTime(&ms, e->ev[0], e->ev[4]); e->timing.total_ms = ms;
 	}
+	if (e->tup_used) return tuples_check(e);
 	return APO_OK;
 }
 
@@ -789,6 +841,8 @@ extern "C" void apo_destroy(apo_engine *e) {
 	e->q8.release(); e->qd2.release(); e->qli.release(); e->qbook.release(); e->d_ptab.release(); e->d_pair.release(); e->d_cbf.release(); e->d_d2book.release(); e->d_d2stream.release(); e->stage.release();
 	e->d_lut.release(); e->corpus.release(); e->dims.release(); e->roll.release(); e->acc.release(); e->acc_joined.release(); e->acc_snapshot.release(); e->misc.release();
 	e->result.release(); e->keys.release(); e->sel_key.release(); e->sel_idx.release();
+	e->tups_pc.release(); e->tups_pd.release(); e->tups_d2.release();
+	e->tup_l.release(); e->tup_h.release(); e->tup_pc.release(); e->tup_pd.release(); e->tup_bad.release(); e->tup_d2.release(); e->tup_ptab.release(); e->tup_val.release();
 	e->win[0].release(); e->win[1].release(); e->batch_in.release(); e->batch_out.release(); e->batch_mask.release();
 	if (e->h_result) cudaFreeHost(e->h_result);
 	for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -1115,7 +1169,12 @@ extern "C" int apo_record_unpack16(const apo_record16 *in, uint64_t n, apo_recor
 // =============================================================================== scoring
 static int source_shape(apo_engine *e, const apo_score_opts *o, uint32_t *C, uint64_t *T) {
 	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
-	if (o->source > APO_SRC_ROLLOUTS) return fail(e, APO_E_ARG, "unknown source %u", o->source);
+	if (o->source > APO_SRC_TUPLES) return fail(e, APO_E_ARG, "unknown source %u", o->source);
+	if (o->source == APO_SRC_TUPLES) {
+		if (e->tup_l.p == nullptr || e->tup_C == 0) return fail(e, APO_E_STATE, "no tuples loaded");
+		*C = e->tup_C; *T = e->tup_T;
+		return APO_OK;
+	}
 	const bool raw = o->source == APO_SRC_ROLLOUTS;
 	if (raw ? (e->roll.p == nullptr || e->roll_C == 0) : ((e->dims_ptr == nullptr && !e->compact) || e->dims_C == 0))
 		return fail(e, APO_E_STATE, "no %s loaded", raw ? "rollouts" : "dims");
@@ -1168,7 +1227,8 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	if ((rc = check_opts(e, o, C, T, &first, &count))) return rc;
 	CK(cudaSetDevice(e->device));
 	if ((rc = ensure_scratch(e, C, o->K))) return rc;
-	const double row_bytes = o->source == APO_SRC_ROLLOUTS ? (double)e->roll_row : (e->compact ? 14.0 : 36.0);
+	const bool tup = o->source == APO_SRC_TUPLES;      // gather-and-add kernel: stand-alone corpus scan + tail
+	const double row_bytes = tup ? 3.0 : o->source == APO_SRC_ROLLOUTS ? (double)e->roll_row : (e->compact ? 14.0 : 36.0);
 	const double stream_bytes = (double)C * (double)count * row_bytes;
 	choose_timing(e, o, (uint64_t)stream_bytes);
 	if (peer_join_active(e, C)) e->join_epoch++;          // counts joined calls only: consecutive joins alternate between the two export slots
@@ -1180,13 +1240,13 @@ extern "C" int apo_score(apo_engine *e, const apo_score_opts *o, double *scores,
 	const bool one_launch = e->nranks == 1 || peer_join_active(e, C);
 	// ... or when it is tiny anyway (the IDE's real corpora, <= 1000 traces): at most 16 records per lane of the corpus warps,
 	// a few microseconds, against a second launch
-	const int tile_evals = (o->source == APO_SRC_DIMS && e->compact) ? apo::kq_tile_evals((int)o->variant) : apo::k1_tile_evals((int)row_bytes, (int)o->variant);
+	const int tile_evals = tup ? apo::kt_tile_evals() : (o->source == APO_SRC_DIMS && e->compact) ? apo::kq_tile_evals((int)o->variant) : apo::k1_tile_evals((int)row_bytes, (int)o->variant);
 	const uint64_t tiles = (uint64_t)C * ((count + (uint64_t)tile_evals - 1) / (uint64_t)tile_evals);
 	const uint64_t ctas = tiles < (uint64_t)e->sm_count ? tiles : (uint64_t)e->sm_count;
 	const bool small_scan = e->corpus_T <= 16ull * 32ull * ctas;
-	const bool fuse = wants_corpus(e, o) && count > 0 && !e->env_no_fuse && (k1_ms > 1.3 * scan_ms || small_scan || e->env_force_fuse);
+	const bool fuse = !tup && wants_corpus(e, o) && count > 0 && !e->env_no_fuse && (k1_ms > 1.3 * scan_ms || small_scan || e->env_force_fuse);
 	// without a corpus request the same tail still saves the K3 launch: an empty scan, then the last CTA finalises
-	const bool tail_only = !wants_corpus(e, o) && one_launch && count > 0 && !e->env_no_fuse;
+	const bool tail_only = !tup && !wants_corpus(e, o) && one_launch && count > 0 && !e->env_no_fuse;
 	if (fuse || tail_only) {
 		if ((rc = begin_score(e, C, true))) return rc;
 		apo::FinalizeParams F = make_fin(e, C, o->K, fuse ? 1 : 0);
@@ -1473,6 +1533,106 @@ extern "C" int apo_score_host_packed(apo_engine *e, const apo_score_opts *o, con
 	const int rc = score_host_compact_impl(e, o, nullptr, nullptr, nullptr, pc, pd, d2book, codebook, C, T, scores, counts, topk, report);
 	if (rc) { cudaStreamSynchronize(e->copy_stream); cudaStreamSynchronize(e->stream); }
 	return rc;
+}
+
+// =============================================================================== Form T (dictionary indices, 3 B / evaluation)
+namespace {
+int tuples_args(apo_engine *e, const uint16_t *tl, const uint8_t *th, const uint32_t *tb_pc, const uint16_t *tb_pd, uint32_t n,
+                const uint32_t *codebook, const uint32_t *d2book, uint32_t C, uint64_t T) {
+	if (C == 0) return fail(e, APO_E_ARG, "C == 0");
+	if (!codebook || !d2book || (n && (!tb_pc || !tb_pd)) || (T && (!tl || !th))) return fail(e, APO_E_ARG, "input is NULL");
+	if (n > APO_TUPLES_MAX) return fail(e, APO_E_ARG, "n_tuples=%u exceeds %u", n, APO_TUPLES_MAX);
+	if (T && n == 0) return fail(e, APO_E_ARG, "evaluations without a dictionary");
+	return APO_OK;
+}
+
+// Streams the two index planes [C][T] through two device windows, H2D of chunk i+1 overlapped with K1t on chunk i.
+int score_host_tuples_impl(apo_engine *e, const apo_score_opts *o, const uint16_t *tl, const uint8_t *th, const uint32_t *tb_pc,
+                           const uint16_t *tb_pd, uint32_t n_tuples, const uint32_t *codebook, const uint32_t *d2book, uint32_t C, uint64_t T,
+                           double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+	if (!o) return fail(e, APO_E_ARG, "opts is NULL");
+	int rc;
+	if ((rc = tuples_args(e, tl, th, tb_pc, tb_pd, n_tuples, codebook, d2book, C, T))) return rc;
+	if (o->K > C) return fail(e, APO_E_ARG, "K=%u exceeds the number of candidates C=%u", o->K, C);
+	if (o->K > kMaxK) return fail(e, APO_E_ARG, "K=%u exceeds the supported beam width %u", o->K, kMaxK);
+	if (o->first || o->count) return fail(e, APO_E_ARG, "windows are not supported by the host-streaming calls");
+	CK(cudaSetDevice(e->device));
+	if ((rc = ensure_scratch(e, C, o->K))) return rc;
+	const int tile = apo::kt_tile_evals();
+	uint64_t Tc = (256ull << 20) / ((uint64_t)C * 3);
+	Tc = Tc / tile * tile;
+	if (Tc < (uint64_t)tile) Tc = tile;
+	if (Tc > round_up(T ? T : 1, tile)) Tc = round_up(T ? T : 1, tile);
+	for (int i = 0; i < 2; i++) CK(e->win[i].reserve((uint64_t)C * Tc * 3));
+	CK(e->tups_pc.reserve(n_tuples ? n_tuples : 1));
+	CK(e->tups_pd.reserve(n_tuples ? n_tuples : 1));
+	CK(e->tups_d2.reserve(4096));
+	choose_timing(e, o, (uint64_t)C * T * 3);
+	if (peer_join_active(e, C)) e->join_epoch++;
+	if ((rc = begin_score(e, C))) return rc;
+	if (n_tuples) {
+		CK(cudaMemcpyAsync(e->tups_pc.p, tb_pc, (uint64_t)n_tuples * 4, cudaMemcpyHostToDevice, e->stream));
+		CK(cudaMemcpyAsync(e->tups_pd.p, tb_pd, (uint64_t)n_tuples * 2, cudaMemcpyHostToDevice, e->stream));
+	}
+	CK(cudaMemcpyAsync(e->tups_d2.p, d2book, 4096 * 4, cudaMemcpyHostToDevice, e->stream));   // bit patterns: unused slots are NaNs, flagged if an entry names one
+	if ((rc = tuples_values(e, codebook, e->tups_pc.p, e->tups_pd.p, n_tuples, e->tups_d2.p, (o->flags & APO_SCORE_RECIP) != 0))) return rc;
+	int nchunk = 0;
+	for (uint64_t t0 = 0; t0 < T; t0 += Tc, nchunk++) {
+		const int b = nchunk & 1;
+		const uint64_t n = T - t0 < Tc ? T - t0 : Tc;
+		unsigned short *wl = (unsigned short *)e->win[b].p;
+		unsigned char *wh = e->win[b].p + (uint64_t)C * Tc * 2;
+		if (nchunk >= 2) CK(cudaStreamWaitEvent(e->copy_stream, e->win_free[b], 0));
+		if ((rc = copy_rows_h2d(e, wl, Tc * 2, tl + t0, T * 2, n * 2, C, e->copy_stream))) return rc;
+		if ((rc = copy_rows_h2d(e, wh, Tc, th + t0, T, n, C, e->copy_stream))) return rc;
+		CK(cudaEventRecord(e->win_ready[b], e->copy_stream));
+		CK(cudaStreamWaitEvent(e->stream, e->win_ready[b], 0));
+		apo::KtParams P{};
+		P.tl = wl; P.th = wh; P.pitch_evals = Tc; P.C = C; P.T = n; P.acc = e->acc.p;
+		P.tval = e->tup_val.p; P.n_tuples = n_tuples; P.bad = e->tup_bad.p;
+		if ((rc = record_k1_event(e, 0))) return rc;
+		CK(apo::run_reward9t(P, e->sm_count, e->stream));
+		if ((rc = record_k1_event(e, 1))) return rc;
+		e->timing.launches++;
+		CK(cudaEventRecord(e->win_free[b], e->stream));
+	}
+	return finish_score(e, o, C, scores, counts, topk, report);
+}
+}  // namespace
+
+extern "C" int apo_score_host_tuples(apo_engine *e, const apo_score_opts *o, const uint16_t *tl, const uint8_t *th, const uint32_t *tbook_pc,
+                                     const uint16_t *tbook_pd, uint32_t n_tuples, const uint32_t *codebook, const uint32_t *d2book,
+                                     uint32_t C, uint64_t T, double *scores, uint64_t *counts, int32_t *topk, apo_corpus_report *report) {
+	if (!e) return APO_E_ARG;
+	const int rc = score_host_tuples_impl(e, o, tl, th, tbook_pc, tbook_pd, n_tuples, codebook, d2book, C, T, scores, counts, topk, report);
+	if (rc) { cudaStreamSynchronize(e->copy_stream); cudaStreamSynchronize(e->stream); e->tup_used = false; }
+	return rc;
+}
+
+extern "C" int apo_tuples_upload(apo_engine *e, const uint16_t *tl, const uint8_t *th, const uint32_t *tbook_pc, const uint16_t *tbook_pd,
+                                 uint32_t n_tuples, const uint32_t *codebook, const uint32_t *d2book, uint32_t C, uint64_t T) {
+	if (!e) return APO_E_ARG;
+	int rc;
+	if ((rc = tuples_args(e, tl, th, tbook_pc, tbook_pd, n_tuples, codebook, d2book, C, T))) return rc;
+	CK(cudaSetDevice(e->device));
+	e->tup_C = 0; e->tup_T = 0; e->tup_n = 0;
+	const uint64_t pitch = round_up(T ? T : 1, 64);                // rows start 16-byte aligned in both planes
+	CK(e->tup_l.reserve((uint64_t)C * pitch));
+	CK(e->tup_h.reserve((uint64_t)C * pitch));
+	CK(e->tup_pc.reserve(n_tuples ? n_tuples : 1));
+	CK(e->tup_pd.reserve(n_tuples ? n_tuples : 1));
+	CK(e->tup_d2.reserve(4096));
+	if ((rc = h2d_rows(e, e->tup_l.p, pitch * 2, tl, T * 2, T * 2, C, e->stream))) { cudaStreamSynchronize(e->stream); return rc; }
+	if ((rc = h2d_rows(e, e->tup_h.p, pitch, th, T, T, C, e->stream))) { cudaStreamSynchronize(e->stream); return rc; }
+	if (n_tuples) {
+		CK(cudaMemcpyAsync(e->tup_pc.p, tbook_pc, (uint64_t)n_tuples * 4, cudaMemcpyHostToDevice, e->stream));
+		CK(cudaMemcpyAsync(e->tup_pd.p, tbook_pd, (uint64_t)n_tuples * 2, cudaMemcpyHostToDevice, e->stream));
+	}
+	CK(cudaMemcpyAsync(e->tup_d2.p, d2book, 4096 * 4, cudaMemcpyHostToDevice, e->stream));
+	CK(cudaStreamSynchronize(e->stream));
+	memcpy(e->tup_book, codebook, sizeof e->tup_book);
+	e->tup_C = C; e->tup_T = T; e->tup_pitch = pitch; e->tup_n = n_tuples;
+	return APO_OK;
 }
 
 extern "C" int apo_host_alloc(uint64_t bytes, void **out) {

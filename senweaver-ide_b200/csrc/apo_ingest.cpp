@@ -453,3 +453,90 @@ extern "C" int apo_packed_encode_host(const float *dims, uint32_t C, uint64_t T,
 	});
 	return APO_OK;
 }
+
+// ---- Form T: Form P planes -> 24-bit dictionary indices (csrc/apo_tuple.cu) -------------------------------------------
+namespace {
+// open addressing over 44-bit keys (code word | tool_success_rate index << 32); EMPTY is not a key (bits 44.. set)
+struct TupleMap {
+	static constexpr uint64_t EMPTY = ~0ull;
+	std::vector<uint64_t> key, val;
+	uint64_t mask = 0, used = 0;
+	explicit TupleMap(uint64_t slots = 1u << 16) { reset(slots); }
+	void reset(uint64_t slots) { key.assign(slots, EMPTY); val.assign(slots, 0); mask = slots - 1; used = 0; }
+	static uint64_t hash(uint64_t k) { k ^= k >> 29; k *= 0xBF58476D1CE4E5B9ull; k ^= k >> 32; return k; }
+	void grow() {
+		std::vector<uint64_t> ok, ov;
+		ok.swap(key); ov.swap(val);
+		reset((mask + 1) * 4);
+		for (size_t i = 0; i < ok.size(); i++) if (ok[i] != EMPTY) *slot(ok[i]) = ov[i];
+	}
+	// value cell of k, inserted with 0 when new
+	uint64_t *slot(uint64_t k) {
+		if ((used + 1) * 2 > mask + 1) grow();
+		uint64_t h = hash(k) & mask;
+		for (;;) {
+			if (key[h] == k) return &val[h];
+			if (key[h] == EMPTY) { key[h] = k; used++; return &val[h]; }
+			h = (h + 1) & mask;
+		}
+	}
+	const uint64_t *find(uint64_t k) const {
+		uint64_t h = hash(k) & mask;
+		for (;;) {
+			if (key[h] == k) return &val[h];
+			if (key[h] == EMPTY) return nullptr;
+			h = (h + 1) & mask;
+		}
+	}
+};
+inline uint64_t tuple_key(uint32_t pc, uint16_t pd) { return (uint64_t)pc | ((uint64_t)(pd & 4095u) << 32); }
+}  // namespace
+
+extern "C" int apo_tuple_encode_host(const uint32_t *pc, const uint16_t *pd, uint32_t C, uint64_t T, uint16_t *tl, uint8_t *th,
+                                     uint32_t *tbook_pc, uint16_t *tbook_pd, uint32_t cap, uint32_t *n_tuples, int nthreads) {
+	if (!n_tuples || (cap && (!tbook_pc || !tbook_pd)) || (C && T && (!pc || !pd || !tl || !th))) return APO_E_ARG;
+	*n_tuples = 0;
+	if (nthreads < 1) nthreads = 1;
+	if (nthreads > 256) nthreads = 256;
+	if (cap > 0xFFFFFFu) cap = 0xFFFFFFu;
+	const uint64_t N = (uint64_t)C * T;
+	// ---- pass 1: distinct evaluations and how often each occurs, per thread
+	std::vector<TupleMap> maps((size_t)nthreads);
+	run_threads(nthreads, [&](int k, int n) {
+		TupleMap &m = maps[(size_t)k];
+		const uint64_t a = N * (uint64_t)k / (uint64_t)n, b = N * (uint64_t)(k + 1) / (uint64_t)n;
+		for (uint64_t i = a; i < b; i++) ++*m.slot(tuple_key(pc[i], pd[i]));
+	});
+	TupleMap all(1u << 18);
+	for (int k = 0; k < nthreads; k++) {
+		const TupleMap &m = maps[(size_t)k];
+		for (size_t i = 0; i < m.key.size(); i++) if (m.key[i] != TupleMap::EMPTY) *all.slot(m.key[i]) += m.val[i];
+		maps[(size_t)k].reset(2);
+	}
+	if (all.used > cap) { *n_tuples = all.used > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)all.used; return APO_E_STATE; }
+	// ---- dictionary order: most frequent first (the head of the table lives in shared memory), ties by key: deterministic
+	std::vector<std::pair<uint64_t, uint64_t>> order;              // (count, key)
+	order.reserve(all.used);
+	for (size_t i = 0; i < all.key.size(); i++) if (all.key[i] != TupleMap::EMPTY) order.push_back({all.val[i], all.key[i]});
+	std::sort(order.begin(), order.end(), [](const std::pair<uint64_t, uint64_t> &x, const std::pair<uint64_t, uint64_t> &y) {
+		if (x.first != y.first) return x.first > y.first;
+		return x.second < y.second;
+	});
+	for (size_t r = 0; r < order.size(); r++) {
+		tbook_pc[r] = (uint32_t)order[r].second;
+		tbook_pd[r] = (uint16_t)(order[r].second >> 32);
+		*all.slot(order[r].second) = r;                               // count -> index
+	}
+	*n_tuples = (uint32_t)order.size();
+	// ---- pass 2: encode
+	const TupleMap &index = all;
+	run_threads(nthreads, [&](int k, int n) {
+		const uint64_t a = N * (uint64_t)k / (uint64_t)n, b = N * (uint64_t)(k + 1) / (uint64_t)n;
+		for (uint64_t i = a; i < b; i++) {
+			const uint64_t r = *index.find(tuple_key(pc[i], pd[i]));
+			tl[i] = (uint16_t)r;
+			th[i] = (uint8_t)(r >> 16);
+		}
+	});
+	return APO_OK;
+}

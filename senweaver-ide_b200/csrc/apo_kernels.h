@@ -144,6 +144,39 @@ cudaError_t run_pack_p(const unsigned long long *q8, const float *d2, const unsi
                        uint32_t *pc, unsigned short *pd, uint32_t *bad, cudaStream_t st);
 cudaError_t run_decode(const unsigned long long *q8, const float *d2, const unsigned short *li, uint64_t n, const uint32_t *codebook, float *out, cudaStream_t st);
 
+// ---- Form T (csrc/apo_tuple.cu): every evaluation is a 24-bit index into a per-tensor dictionary of distinct
+// evaluations; the reward of a dictionary entry is computed once (k_tuple_values), K1t sums table entries.
+constexpr uint32_t KT_TUPLES_MAX = 0xFFFFFFu;      // dictionary entries addressable by lo16 | hi8 << 16
+constexpr int KT_VALID_SHIFT = 58;                 // table entry = rint(finalReward * 2^52) + (counted << 58)
+struct KtParams {
+	const unsigned short *tl;       // [C][pitch] low 16 bits of the tuple index
+	const unsigned char *th;        // [C][pitch] high 8 bits
+	uint64_t pitch_evals;           // multiple of 8; tl / th 16-byte aligned
+	uint32_t C;
+	uint32_t tiles_per_cand;
+	uint64_t T;
+	uint64_t total_tiles;
+	long long *acc;
+	const long long *tval;          // [n_tuples + 1]; the last entry is the zero sentinel out-of-range indices are clamped to
+	uint32_t n_tuples;
+	uint32_t hot;                   // entries [0, hot) are served from shared memory
+	uint32_t *bad;                  // bit 0: an index >= n_tuples was met
+};
+struct TupleValParams {
+	const uint32_t *tb_pc;          // [n] Form P code word of the entry (eight 4-bit codes, 15 = absent)
+	const unsigned short *tb_pd;    // [n] 12-bit tool_success_rate index (4095 = absent)
+	uint32_t n;
+	const double *ptab;             // [8][256] as KqParams::ptab
+	const double *lut;              // as K1Params::lut
+	const float *d2book;            // [4096]
+	double w2;
+	long long *tval;                // [n + 1] out
+	uint32_t *bad;                  // bit 1: an entry is not representable (|reward| >= 2, NaN tool_success_rate)
+};
+int kt_tile_evals();
+cudaError_t run_tuple_values(const TupleValParams &P, bool recip, cudaStream_t st);
+cudaError_t run_reward9t(KtParams P, int sm_count, cudaStream_t st);
+
 int k1_tile_evals(int row, int variant);
 cudaError_t run_reward9(K1Params P, int row, int variant, bool recip, int sm_count, cudaStream_t st);
 cudaError_t run_detect6(const K2Params &P, int sm_count, cudaStream_t st);

@@ -17,7 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libapo_b200.so")
 
 NDIM, NPAT, NMODE = 9, 6, 5
-SRC_DIMS, SRC_ROLLOUTS = 0, 1
+SRC_DIMS, SRC_ROLLOUTS, SRC_TUPLES = 0, 1, 2
+TUPLES_MAX = 0xFFFFFF
 SCORE_CORPUS, SCORE_RECIP, SCORE_TIMING = 0x1, 0x2, 0x4
 TUNE_NO_FUSE, TUNE_FORCE_FUSE, TUNE_NO_STAGING, TUNE_NCCL_JOIN = 0x1, 0x2, 0x4, 0x8
 F_ERRORS, F_ENDED, F_VALID, F_FAILSPAN = 0x01, 0x02, 0x08, 0x10
@@ -90,7 +91,8 @@ ABI_SYMBOLS = (
     "apo_rollouts_upload", "apo_rollouts_generate", "apo_rollouts_download", "apo_rollouts16_upload",
     "apo_rollouts16_generate", "apo_rollouts16_download", "apo_record_pack16", "apo_record_unpack16", "apo_duration_class", "apo_score",
     "apo_score_begin", "apo_score_accumulate", "apo_score_finish", "apo_score_host", "apo_score_host_records", "apo_score_host_compact", "apo_compact_encode_host",
-    "apo_dims_compact_download", "apo_dims_codebook", "apo_packed_encode_host", "apo_score_host_packed", "apo_dims_packed_download", "apo_dims_d2book", "apo_host_alloc", "apo_host_free",
+    "apo_dims_compact_download", "apo_dims_codebook", "apo_packed_encode_host", "apo_score_host_packed", "apo_dims_packed_download", "apo_dims_d2book",
+    "apo_tuple_encode_host", "apo_score_host_tuples", "apo_tuples_upload", "apo_host_alloc", "apo_host_free",
     "apo_last_timing", "apo_debug_partials", "apo_comm_unique_id", "apo_comm_init", "apo_comm_destroy", "apo_comm_join_mode",
 )
 
@@ -166,6 +168,9 @@ def load_library() -> C.CDLL:
     L.apo_dims_packed_download.argtypes = [vp, vp, vp, u32, u64, u64]
     L.apo_dims_d2book.argtypes = [vp, vp]
     L.apo_score_host_packed.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp, u32, u64, vp, vp, vp, vp]
+    L.apo_tuple_encode_host.argtypes = [vp, vp, u32, u64, vp, vp, vp, vp, u32, vp, i32]
+    L.apo_score_host_tuples.argtypes = [vp, C.POINTER(ScoreOpts), vp, vp, vp, vp, u32, vp, vp, u32, u64, vp, vp, vp, vp]
+    L.apo_tuples_upload.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, u32, u64]
     L.apo_dims_compact_download.argtypes = [vp, vp, vp, vp, u32, u64, u64]
     L.apo_dims_codebook.argtypes = [vp, vp]
     L.apo_last_timing.argtypes = [vp, C.POINTER(Timing)]
@@ -498,6 +503,36 @@ class Engine:
                                                _p(topk), C.byref(rep) if rep is not None else None))
         return ScoreResult(scores, counts, topk, rep, self.last_timing())
 
+    @staticmethod
+    def _tuple_args(tl, th, tbook, codebook, d2book):
+        tb_pc, tb_pd = tbook
+        assert tl.dtype == np.uint16 and th.dtype == np.uint8 and tl.shape == th.shape and tl.ndim == 2 and tl.flags.c_contiguous and th.flags.c_contiguous
+        tb_pc, tb_pd = np.ascontiguousarray(tb_pc, np.uint32), np.ascontiguousarray(tb_pd, np.uint16)
+        codebook, d2book = np.ascontiguousarray(codebook, np.uint32), np.ascontiguousarray(d2book, np.uint32)
+        assert tb_pc.shape == tb_pd.shape and tb_pc.ndim == 1 and codebook.size == 2048 and d2book.size == 4096
+        return tb_pc, tb_pd, codebook, d2book
+
+    def score_host_tuples(self, tl: np.ndarray, th: np.ndarray, tbook, codebook: np.ndarray, d2book: np.ndarray, K: int, corpus: bool = False,
+                          recip: bool = False) -> ScoreResult:
+        """Form T: tl uint16 [C][T] + th uint8 [C][T] (24-bit dictionary indices), tbook = (pc uint32 [n], pd uint16 [n]) the distinct
+        evaluations as Form P pairs, + the two codebooks of Form P."""
+        tb_pc, tb_pd, codebook, d2book = self._tuple_args(tl, th, tbook, codebook, d2book)
+        Cn, T = tl.shape
+        o = self._opts(K, SRC_DIMS, corpus, recip, 0, 0, 0)
+        scores = np.empty(Cn, np.float64)
+        counts = np.empty(Cn, np.uint64)
+        topk = np.empty(K, np.int32)
+        rep = CorpusReport() if corpus else None
+        self._ck(self._L.apo_score_host_tuples(self._h, C.byref(o), _p(tl), _p(th), _p(tb_pc), _p(tb_pd), tb_pc.size, _p(codebook), _p(d2book), Cn, T,
+                                               _p(scores), _p(counts), _p(topk), C.byref(rep) if rep is not None else None))
+        return ScoreResult(scores, counts, topk, rep, self.last_timing())
+
+    def tuples_upload(self, tl: np.ndarray, th: np.ndarray, tbook, codebook: np.ndarray, d2book: np.ndarray):
+        """Make a Form T tensor resident: score(C, K, source=SRC_TUPLES) then reads 3 B per evaluation."""
+        tb_pc, tb_pd, codebook, d2book = self._tuple_args(tl, th, tbook, codebook, d2book)
+        Cn, T = tl.shape
+        self._ck(self._L.apo_tuples_upload(self._h, _p(tl), _p(th), _p(tb_pc), _p(tb_pd), tb_pc.size, _p(codebook), _p(d2book), Cn, T))
+
     def last_timing(self) -> Timing:
         t = Timing()
         self._ck(self._L.apo_last_timing(self._h, C.byref(t)))
@@ -561,6 +596,24 @@ def packed_encode_host(dims: np.ndarray, nthreads: int = 8, out=None):
     if rc != 0:
         raise ApoError(rc, "evaluations do not fit the 4-bit / 12-bit codes of Form P" if rc == -3 else "bad argument")
     return pc, pd, book, d2book
+
+
+def tuple_encode_host(pc: np.ndarray, pd: np.ndarray, nthreads: int = 8, out=None, cap: int = TUPLES_MAX):
+    """Form P planes (pc uint32 [C][T], pd uint16 [C][T]) -> (tl, th, (tbook_pc, tbook_pd)): the 3-byte dictionary form
+    (apo_tuple_encode_host).  out=(tl, th) fills existing (pinned) buffers.  Raises ApoError(APO_E_STATE) when the tensor holds
+    more than `cap` distinct evaluations."""
+    L = load_library()
+    assert pc.dtype == np.uint32 and pd.dtype == np.uint16 and pc.shape == pd.shape and pc.ndim == 2 and pc.flags.c_contiguous and pd.flags.c_contiguous
+    Cn, T = pc.shape
+    tl, th = out if out is not None else (np.empty((Cn, T), np.uint16), np.empty((Cn, T), np.uint8))
+    assert tl.dtype == np.uint16 and th.dtype == np.uint8 and tl.shape == pc.shape and th.shape == pc.shape and tl.flags.c_contiguous and th.flags.c_contiguous
+    cap = min(int(cap), TUPLES_MAX, max(1, Cn * T))
+    tb_pc, tb_pd = np.empty(cap, np.uint32), np.empty(cap, np.uint16)
+    n = C.c_uint32(0)
+    rc = L.apo_tuple_encode_host(_p(pc), _p(pd), Cn, T, _p(tl), _p(th), _p(tb_pc), _p(tb_pd), cap, C.addressof(n), nthreads)
+    if rc != 0:
+        raise ApoError(rc, f"{n.value} distinct evaluations exceed the dictionary capacity {cap}" if rc == -3 else "bad argument")
+    return tl, th, (tb_pc[:n.value].copy(), tb_pd[:n.value].copy())
 
 
 def pack16(recs: np.ndarray) -> np.ndarray:

@@ -106,3 +106,37 @@ def test_packed_host_encoder_is_lossless(apo, orc):
     assert np.all(np.diff(used) >= 0) and len(used) < 4095
     one = apo.packed_encode_host(dims, nthreads=1)
     assert all(np.array_equal(x, y) for x, y in zip(one, (pc, pd, book.reshape(-1), d2book)))
+
+
+def test_tuple_host_encoder_is_lossless(apo, orc):
+    """apo_tuple_encode_host (host-format code, no GPU): every evaluation becomes the 24-bit index (tl | th << 16) of its Form P pair
+    in the dictionary; entries are distinct, ordered most frequent first (ties by key); any thread count gives the same bytes; a
+    tensor with more distinct evaluations than the capacity is refused with the count reported."""
+    import numpy as np
+    dims = orc.gen_dims(0x5EED00CB, 2, 6, 10, 70_003, 350, 4)
+    pc, pd, _, _ = apo.packed_encode_host(dims, nthreads=3)
+    tl, th, (tpc, tpd) = apo.tuple_encode_host(pc, pd, nthreads=3)
+    idx = tl.astype(np.int64) | (th.astype(np.int64) << 16)
+    n = len(tpc)
+    assert 1000 < n < pc.size and idx.max() == n - 1
+    assert np.array_equal(tpc[idx], pc) and np.array_equal(tpd[idx], pd)                 # lossless
+    keys = tpc.astype(np.uint64) | (tpd.astype(np.uint64) << np.uint64(32))
+    assert len(np.unique(keys)) == n                                                      # distinct entries
+    cnt = np.bincount(idx.ravel(), minlength=n)
+    assert cnt.min() >= 1 and np.all(np.diff(cnt) <= 0)                                   # most frequent first
+    ties = np.diff(cnt) == 0
+    assert np.all(keys[1:][ties] > keys[:-1][ties])                                       # ties by key: deterministic
+    one = apo.tuple_encode_host(pc, pd, nthreads=1)
+    assert np.array_equal(one[0], tl) and np.array_equal(one[1], th) and np.array_equal(one[2][0], tpc) and np.array_equal(one[2][1], tpd)
+    with pytest.raises(apo.ApoError) as ei:
+        apo.tuple_encode_host(pc, pd, cap=1000)
+    assert ei.value.code == -3 and str(n) in str(ei.value)
+    # the whole range of a 16-bit low plane and a non-zero high plane
+    big_pc = np.arange(70_000, dtype=np.uint32).reshape(1, -1)
+    big_pd = np.full(big_pc.shape, 4095, np.uint16)
+    l, h, (bp, bd) = apo.tuple_encode_host(big_pc, big_pd)
+    i2 = l.astype(np.int64) | (h.astype(np.int64) << 16)
+    assert len(bp) == 70_000 and h.max() == 1 and np.array_equal(bp[i2], big_pc)
+    # empty record axis
+    l, h, (bp, bd) = apo.tuple_encode_host(np.empty((3, 0), np.uint32), np.empty((3, 0), np.uint16))
+    assert l.shape == (3, 0) and len(bp) == 0

@@ -218,3 +218,73 @@ def test_packed_wire_format_six_bytes_per_evaluation(engine, orc, apo):
     many[1, :5000, 2] = np.linspace(-1, 1, 5000, dtype=np.float32)
     with pytest.raises(apo.ApoError):
         apo.packed_encode_host(many)
+
+
+def test_tuple_dictionary_form_three_bytes_per_evaluation(engine, orc, apo):
+    """Form T (3 B / evaluation): dictionary indices + one finalReward per distinct evaluation (k_tuple_values, the operations
+    of K1q) + K1t's gather-and-add give the integers of the Form D tensor — streamed from host memory and resident, with the
+    dictionary tail beyond the shared-memory head, ragged rows, windows, sessions and changed weights."""
+    seed, C, T = 0x5EED00D1, 8, 300_011                                   # > 24576 distinct evaluations: head + tail of the table
+    dims = orc.gen_dims(seed, 3, C, 1000, T, 400, 8)
+    exp = orc.score_dims_fx(dims)
+    pc, pd, book, d2book = apo.packed_encode_host(dims, nthreads=4)
+    tl, th, tbook = apo.tuple_encode_host(pc, pd, nthreads=4)
+    assert len(tbook[0]) > 24576
+    recs = orc.gen_records(seed, orc.STREAM_CORPUS, 0, 1, 0, 20_000, 300, 8).reshape(-1)
+    engine.corpus_upload(recs)
+    engine.dims_upload(dims)
+    ref = engine.score(C, 3, corpus=True)
+    assert engine.debug_partials(C) == exp
+    # -- streamed from host memory (pageable, then page-locked)
+    r = engine.score_host_tuples(tl, th, tbook, book, d2book, 3, corpus=True)
+    assert engine.debug_partials(C) == exp
+    assert np.array_equal(r.scores, ref.scores) and np.array_equal(r.counts, ref.counts) and np.array_equal(r.topk, ref.topk)
+    assert r.report.bad == ref.report.bad and r.report.total == ref.report.total
+    ptl, pth = apo.host_empty(tl.shape, np.uint16), apo.host_empty(th.shape, np.uint8)
+    ptl[:], pth[:] = tl, th
+    engine.score_host_tuples(ptl, pth, tbook, book, d2book, 3)
+    assert engine.debug_partials(C) == exp
+    # -- resident
+    engine.tuples_upload(tl, th, tbook, book, d2book)
+    r = engine.score(C, 3, source=apo.SRC_TUPLES, corpus=True)
+    assert engine.debug_partials(C) == exp
+    assert np.array_equal(r.scores, ref.scores) and np.array_equal(r.topk, ref.topk) and r.report.bad == ref.report.bad
+    r = engine.score(C, 3, source=apo.SRC_TUPLES, recip=True)
+    rr = engine.score(C, 3, recip=True)
+    assert np.array_equal(r.scores, rr.scores)
+    engine.score(C, 1, source=apo.SRC_TUPLES, first=8000, count=100_003)
+    assert engine.debug_partials(C) == orc.score_dims_fx(dims[:, 8000:108_003])
+    with pytest.raises(apo.ApoError):
+        engine.score(C, 1, source=apo.SRC_TUPLES, first=4, count=100)       # windows start on multiples of 8
+    engine.score_begin(C + 2)
+    engine.score_accumulate(2, source=apo.SRC_TUPLES, count=150_000)
+    engine.score_accumulate(2, source=apo.SRC_TUPLES, first=150_000)
+    r = engine.score_finish(C + 2, 3)
+    assert r.counts[0] == 0 and r.counts[1] == 0 and engine.debug_partials(C + 2)[0][2:] == exp[0]
+    # -- another weight vector: the table is rebuilt per call
+    w = np.array([0.3, 0.05, 0.1, 0.05, 0.1, 0.1, 0.1, 0.1, 0.1])
+    engine.set_weights(w)
+    engine.score(C, 2, source=apo.SRC_TUPLES)
+    got = engine.debug_partials(C)
+    engine.score(C, 2)
+    assert got == engine.debug_partials(C) == orc.score_dims_fx(dims, w=w)
+    engine.set_weights(orc.weights())
+    # -- small dictionary (everything in shared memory), tiny tensors, empty record axis
+    for Cs, Ts in ((3, 1), (2, 7), (5, 8192), (4, 8193), (1, 20_000)):
+        d = orc.gen_dims(seed + Ts, 0, Cs, 0, Ts, 300, 8)
+        p1, p2, b1, b2 = apo.packed_encode_host(d)
+        t1, t2, tb = apo.tuple_encode_host(p1, p2)
+        engine.score_host_tuples(t1, t2, tb, b1, b2, 1)
+        assert engine.debug_partials(Cs) == orc.score_dims_fx(d)
+        engine.tuples_upload(t1, t2, tb, b1, b2)
+        engine.score(Cs, 1, source=apo.SRC_TUPLES)
+        assert engine.debug_partials(Cs) == orc.score_dims_fx(d)
+    # -- an index outside the dictionary is refused, not read
+    bad = tl.copy()
+    bad[2, 77] = 0xFFFF
+    badh = th.copy()
+    badh[2, 77] = 0xFF
+    with pytest.raises(apo.ApoError):
+        engine.score_host_tuples(bad, badh, tbook, book, d2book, 1)
+    engine.score_host_tuples(tl, th, tbook, book, d2book, 1)               # and the handle stays usable
+    assert engine.debug_partials(C) == exp

@@ -76,6 +76,15 @@ assert e.debug_partials(C) == exp
 e.dims_upload_compact(dims)
 a, b = e.dims_packed_download(1, 0, T)                            # k_collect_d2 + k_pack_p
 assert np.array_equal(a, pc[1]) and np.array_equal(b, pd[1])
+# Form T: k_tuple_values + K1t, full tiles (8192 evaluations) and ragged row ends, streamed and resident
+dt = orc.gen_dims(seed, 0, 3, 0, 2 * 8192 + 77, 400, 4)
+pt, pdt, bkt, d2t = pkg.packed_encode_host(dt, nthreads=2)
+tl, th, tbook = pkg.tuple_encode_host(pt, pdt, nthreads=2)
+e.score_host_tuples(tl, th, tbook, bkt, d2t, 2, corpus=True)
+assert e.debug_partials(3) == orc.score_dims_fx(dt)
+e.tuples_upload(tl, th, tbook, bkt, d2t)
+e.score(3, 2, source=pkg.SRC_TUPLES, first=8, count=8192 + 100)
+assert e.debug_partials(3) == orc.score_dims_fx(dt[:, 8:8192 + 108])
 for Cn in ((3, 1500, 3000) if not os.environ.get("SMOKE_NO_MANY_CANDIDATES") else ()):       # counting top-K (<= 2048 keys in shared memory) and the radix select
     e.dims_generate(seed, 0, Cn, 0, 64, 300)
     r = e.score(Cn, min(Cn, 40))

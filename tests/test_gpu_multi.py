@@ -27,10 +27,23 @@ def worker(rank, world, uid_path, out_dir, layout):
         eng.set_tuning(pkg.TUNE_NCCL_JOIN)          # the fallback join: ncclAllReduce + k_finalize
     mode = eng.comm_join_mode()
     first, last = pkg.sharding.shard_range(T, world, rank)
-    (eng.dims_generate_compact if layout == "compact" else eng.dims_generate)(SEED, 0, C, first, last - first, 300)
+    (eng.dims_generate_compact if layout in ("compact", "tuples") else eng.dims_generate)(SEED, 0, C, first, last - first, 300)
     eng.corpus_generate(SEED, first, last - first, 300)
-    for _ in range(3):                              # consecutive joined calls alternate between the two export slots
-        res = eng.score(C, K, corpus=True)
+    if layout == "tuples":                          # Form T: every rank its own dictionary over its shard; the joined integers are the same
+        n = last - first
+        book, d2book = eng.dims_codebook(), eng.dims_d2book()
+        pc, pd = np.empty((C, n), np.uint32), np.empty((C, n), np.uint16)
+        for c in range(C):
+            eng.dims_packed_download(c, 0, n, out=(pc[c], pd[c]))
+        tl, th, tbook = pkg.tuple_encode_host(pc, pd, nthreads=2)
+        eng.tuples_upload(tl, th, tbook, book, d2book)
+        streamed = eng.score_host_tuples(tl, th, tbook, book, d2book, K, corpus=True)       # a joined host-streaming call
+        for _ in range(3):
+            res = eng.score(C, K, source=pkg.SRC_TUPLES, corpus=True)
+        assert np.array_equal(streamed.scores, res.scores) and np.array_equal(streamed.topk, res.topk)
+    else:
+        for _ in range(3):                          # consecutive joined calls alternate between the two export slots
+            res = eng.score(C, K, corpus=True)
     sums, counts = eng.debug_partials(C)            # after the join: the summed integers
     rep = res.report
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), scores=res.scores, counts=res.counts, topk=res.topk,
@@ -40,7 +53,7 @@ def worker(rank, world, uid_path, out_dir, layout):
     eng.close()
 
 
-@pytest.mark.parametrize("layout", ["fp32", "compact", "fp32-nccl-join"])
+@pytest.mark.parametrize("layout", ["fp32", "compact", "fp32-nccl-join", "tuples"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_score_equals_single_gpu(tmp_path, engine, orc, world, layout):
     if torch.cuda.device_count() < world:
@@ -64,6 +77,8 @@ def test_sharded_score_equals_single_gpu(tmp_path, engine, orc, world, layout):
             assert list(z["pat"][p]) == [ref.report.pat[p].count, *ref.report.pat[p].examples]
         if layout.endswith("nccl-join"):
             assert z["mode"][0] == 1 and z["launches"][0] in (3, 4)   # K1 (+ corpus scan when it can hide behind it, else K2), ncclAllReduce, K3
+        elif layout == "tuples":
+            assert z["mode"][0] == 2 and z["launches"][0] == 3        # k_tuple_values, K1t, K2 with the peer-memory join in its tail
         else:
             assert z["mode"][0] == 2 and z["launches"][0] in (1, 2)   # peer-memory join inside the scoring launch (or inside K2's tail)
     # and the single-GPU result itself is pinned to the oracle on a window

@@ -69,6 +69,18 @@ int apo_job_validate(apo_job *j)
 		if (j->row_bytes != 32 && j->row_bytes != 16) return bad(j, "rowBytes must be 32 or 16");
 		if (!fits(j->C, j->T, j->row_bytes, j->buf_bytes)) return bad(j, "records buffer is smaller than C*T*rowBytes");
 		break;
+	case APO_JOB_SCORE_HOST_TUPLES:
+		if (j->C == 0) return bad(j, "C must be > 0");
+		if (j->T && (!j->buf || !j->aux[0])) return bad(j, "index planes missing");
+		if (!fits(j->C, j->T, 2, j->buf_bytes)) return bad(j, "tl plane is smaller than C*T*2 bytes");
+		if (!fits(j->C, j->T, 1, j->aux_bytes[0])) return bad(j, "th plane is smaller than C*T bytes");
+		if (j->n_tuples > APO_TUPLES_MAX) return bad(j, "more than 16777215 dictionary entries");
+		if (j->T && j->n_tuples == 0) return bad(j, "evaluations without a dictionary");
+		if (j->n_tuples && (!j->aux[1] || !j->aux[2])) return bad(j, "dictionary missing");
+		if (j->aux_bytes[1] / 4 < j->n_tuples || j->aux_bytes[2] / 2 < j->n_tuples) return bad(j, "dictionary arrays are shorter than nTuples entries");
+		if (!j->aux[3] || j->aux_bytes[3] != 8u * 256u * 4u) return bad(j, "codebook must be 8 x 256 uint32");
+		if (!j->aux[4] || j->aux_bytes[4] != 4096u * 4u) return bad(j, "d2book must be 4096 uint32");
+		break;
 	case APO_JOB_CORPUS_UPLOAD:
 		if (!j->buf && j->buf_bytes) return bad(j, "corpus buffer missing");
 		if (j->buf_bytes % sizeof(apo_record)) return bad(j, "corpus byte length is not a multiple of 32");
@@ -77,7 +89,7 @@ int apo_job_validate(apo_job *j)
 		if (!j->buf) return bad(j, "json buffer missing");
 		break;
 	case APO_JOB_SCORE_RESIDENT:
-		if (j->source > APO_SRC_ROLLOUTS) return bad(j, "unknown source");
+		if (j->source > APO_SRC_TUPLES) return bad(j, "unknown source");
 		if (j->first % 4) return bad(j, "window start must be a multiple of 4");
 		break;
 	case APO_JOB_REWARD_BATCH:
@@ -92,7 +104,7 @@ int apo_job_validate(apo_job *j)
 	default:
 		return bad(j, "unknown job kind");
 	}
-	if (j->kind == APO_JOB_SCORE_HOST || j->kind == APO_JOB_SCORE_HOST_RECORDS) {
+	if (j->kind == APO_JOB_SCORE_HOST || j->kind == APO_JOB_SCORE_HOST_RECORDS || j->kind == APO_JOB_SCORE_HOST_TUPLES) {
 		if (j->K > j->C) return bad(j, "K exceeds the number of candidates");
 		if (j->corpus_bytes % sizeof(apo_record)) return bad(j, "corpus byte length is not a multiple of 32");
 		if (j->corpus_bytes && !j->corpus) return bad(j, "corpus buffer missing");
@@ -103,7 +115,7 @@ int apo_job_validate(apo_job *j)
 
 int apo_job_prepare(apo_job *j)
 {
-	if (j->kind == APO_JOB_SCORE_HOST || j->kind == APO_JOB_SCORE_HOST_RECORDS || j->kind == APO_JOB_SCORE_RESIDENT) {
+	if (j->kind == APO_JOB_SCORE_HOST || j->kind == APO_JOB_SCORE_HOST_RECORDS || j->kind == APO_JOB_SCORE_HOST_TUPLES || j->kind == APO_JOB_SCORE_RESIDENT) {
 		/* resident calls learn C from the handle: size for the largest C the handle may hold is unknown here, so the
 		 * caller passes C (the count it uploaded); the ABI re-checks K <= C against the loaded shape */
 		const uint32_t C = j->C ? j->C : 1, K = j->K ? j->K : 1;
@@ -161,6 +173,14 @@ static void execute(apo_serial *s, apo_job *j)
 			j->rc = j->kind == APO_JOB_SCORE_HOST
 			            ? apo_score_host(e, &o, (const float *)j->buf, j->C, j->T, j->scores, j->counts, j->topk, &j->report)
 			            : apo_score_host_records(e, &o, j->buf, j->row_bytes, j->C, j->T, j->scores, j->counts, j->topk, &j->report);
+		break;
+	case APO_JOB_SCORE_HOST_TUPLES:
+		o.source = APO_SRC_DIMS; o.first = 0; o.count = 0;
+		j->rc = APO_OK;
+		if (j->corpus_bytes) { j->rc = apo_corpus_upload(e, (const apo_record *)j->corpus, j->corpus_bytes / sizeof(apo_record), j->idx_base); o.flags |= APO_SCORE_CORPUS; }
+		if (j->rc == APO_OK)
+			j->rc = apo_score_host_tuples(e, &o, (const uint16_t *)j->buf, (const uint8_t *)j->aux[0], (const uint32_t *)j->aux[1], (const uint16_t *)j->aux[2],
+			                              j->n_tuples, (const uint32_t *)j->aux[3], (const uint32_t *)j->aux[4], j->C, j->T, j->scores, j->counts, j->topk, &j->report);
 		break;
 	case APO_JOB_REWARD_BATCH:
 		j->rc = apo_reward_batch(e, (const apo_record *)j->buf, j->n_out, j->dims_out, j->masks_out, j->finals_out);

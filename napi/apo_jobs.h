@@ -46,6 +46,7 @@ typedef enum {
 	APO_JOB_SCORE_RESIDENT,        /* scoreResident(handle, {K, source, corpus, first, count})   */
 	APO_JOB_SCORE_HOST,            /* score(handle, dims, C, T, corpus|null, K)                  */
 	APO_JOB_SCORE_HOST_RECORDS,    /* scoreHostRecords(handle, recs, rowBytes, C, T, corpus|null, K) */
+	APO_JOB_SCORE_HOST_TUPLES,     /* scoreHostTuples(handle, {tl, th, tbookPc, tbookPd, codebook, d2book}, C, T, corpus|null, K) */
 	APO_JOB_REWARD_BATCH,          /* rewardBatch(handle, recs apo_record[n])                    */
 	APO_JOB_COMM_INIT,             /* commInit(handle, nranks, rank, id[128])                    */
 	APO_JOB_TEST_HOOK              /* tests: calls hook(hook_arg) in its turn                    */
@@ -57,6 +58,8 @@ typedef struct apo_job {
 	/* inputs (host pointers stay owned and ref'd by the caller until the job completed) */
 	const void *buf; uint64_t buf_bytes;          /* dims / records / utf8 */
 	const void *corpus; uint64_t corpus_bytes;    /* optional apo_record[Tc] uploaded before a host scoring call */
+	const void *aux[5]; uint64_t aux_bytes[5];    /* Form T: th plane, tbook_pc, tbook_pd, codebook (8 x 256 u32), d2book (4096 u32); buf = tl plane */
+	uint32_t n_tuples;
 	uint32_t C, K, row_bytes, source, flags;
 	uint64_t T, first, count, idx_base;
 	int compact;

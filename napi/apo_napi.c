@@ -112,7 +112,7 @@ typedef struct {
 	apo_job job;
 	napi_deferred deferred;
 	napi_async_work work;
-	napi_ref keep[3];            /* handle, data buffer, corpus buffer */
+	napi_ref keep[9];            /* handle, data buffer, corpus buffer (+ the six arrays of a Form T call) */
 	int nkeep;
 } call_t;
 
@@ -148,7 +148,7 @@ static void call_complete(napi_env env, napi_status st, void *data)
 	} else {
 		napi_value out = NULL, v;
 		switch (j->kind) {
-		case APO_JOB_SCORE_RESIDENT: case APO_JOB_SCORE_HOST: case APO_JOB_SCORE_HOST_RECORDS:
+		case APO_JOB_SCORE_RESIDENT: case APO_JOB_SCORE_HOST: case APO_JOB_SCORE_HOST_RECORDS: case APO_JOB_SCORE_HOST_TUPLES:
 			out = blocks_of(env, j);
 			break;
 		case APO_JOB_REWARD_BATCH:
@@ -343,6 +343,113 @@ static napi_value score_host_common(napi_env env, napi_callback_info info, apo_j
 static napi_value Score(napi_env env, napi_callback_info info) { return score_host_common(env, info, APO_JOB_SCORE_HOST); }
 static napi_value ScoreHostRecords(napi_env env, napi_callback_info info) { return score_host_common(env, info, APO_JOB_SCORE_HOST_RECORDS); }
 
+/* encodeTuples(dims:ArrayBuffer f32[C][T][9], C, T, nthreads?) -> Promise<{tl, th, tbookPc, tbookPd, codebook, d2book, nTuples} | null>.
+ * Host-side format code (no engine, no GPU, off the JS thread): Form D -> Form P (apo_packed_encode_host) -> Form T
+ * (apo_tuple_encode_host), the 3-byte wire format of scoreHostTuples.  Resolves null when the tensor is not categorical enough
+ * for Form P / Form T (the caller keeps score()). */
+typedef struct {
+	napi_deferred deferred; napi_async_work work; napi_ref keep;
+	const float *dims; uint32_t C, nthreads, n; uint64_t T; int rc;
+	uint16_t *tl; uint8_t *th; uint32_t *tb_pc; uint16_t *tb_pd;
+	uint32_t book[8 * 256], d2book[4096];
+} enc_t;
+
+static void enc_execute(napi_env env, void *data)
+{
+	(void)env;
+	enc_t *q = (enc_t *)data;
+	const uint64_t N = (uint64_t)q->C * q->T, n1 = N ? N : 1;
+	const uint32_t cap = N < APO_TUPLES_MAX ? (uint32_t)n1 : APO_TUPLES_MAX;
+	uint32_t *pc = (uint32_t *)malloc((size_t)n1 * 4);
+	uint16_t *pd = (uint16_t *)malloc((size_t)n1 * 2);
+	q->tl = (uint16_t *)malloc((size_t)n1 * 2); q->th = (uint8_t *)malloc((size_t)n1);
+	q->tb_pc = (uint32_t *)malloc((size_t)cap * 4); q->tb_pd = (uint16_t *)malloc((size_t)cap * 2);
+	q->rc = APO_E_NOMEM;
+	if (pc && pd && q->tl && q->th && q->tb_pc && q->tb_pd) {
+		q->rc = apo_packed_encode_host(q->dims, q->C, q->T, pc, pd, q->book, q->d2book, (int)q->nthreads);
+		if (q->rc == APO_OK) q->rc = apo_tuple_encode_host(pc, pd, q->C, q->T, q->tl, q->th, q->tb_pc, q->tb_pd, cap, &q->n, (int)q->nthreads);
+	}
+	free(pc); free(pd);
+}
+
+static void free_finalize(napi_env env, void *data, void *hint) { (void)env; (void)hint; free(data); }
+
+static void enc_complete(napi_env env, napi_status st, void *data)
+{
+	(void)st;
+	enc_t *q = (enc_t *)data;
+	napi_value out = NULL, v;
+	napi_get_null(env, &out);
+	if (q->rc == APO_OK) {
+		const uint64_t N = (uint64_t)q->C * q->T;
+		napi_value vtl = NULL, vth = NULL;
+		/* the planes are handed to JS without a copy; everything else is small */
+		if (napi_create_external_arraybuffer(env, q->tl, (size_t)N * 2, free_finalize, NULL, &vtl) == napi_ok) q->tl = NULL;
+		if (napi_create_external_arraybuffer(env, q->th, (size_t)N, free_finalize, NULL, &vth) == napi_ok) q->th = NULL;
+		if (vtl && vth) {
+			napi_create_object(env, &out);
+			napi_set_named_property(env, out, "tl", vtl); napi_set_named_property(env, out, "th", vth);
+			if ((v = copy_out(env, q->tb_pc, (size_t)q->n * 4))) napi_set_named_property(env, out, "tbookPc", v);
+			if ((v = copy_out(env, q->tb_pd, (size_t)q->n * 2))) napi_set_named_property(env, out, "tbookPd", v);
+			if ((v = copy_out(env, q->book, sizeof q->book))) napi_set_named_property(env, out, "codebook", v);
+			if ((v = copy_out(env, q->d2book, sizeof q->d2book))) napi_set_named_property(env, out, "d2book", v);
+			napi_create_double(env, (double)q->n, &v); napi_set_named_property(env, out, "nTuples", v);
+		}
+	}
+	napi_resolve_deferred(env, q->deferred, out);
+	napi_delete_reference(env, q->keep);
+	napi_delete_async_work(env, q->work);
+	free(q->tl); free(q->th); free(q->tb_pc); free(q->tb_pd);
+	free(q);
+}
+
+static napi_value EncodeTuples(napi_env env, napi_callback_info info)
+{
+	ARGS(4)
+	const void *dims = NULL; uint64_t bytes = 0, T = 0; uint32_t C = 0, nthreads = 4;
+	if (argc < 3 || !get_buffer(env, argv[0], &dims, &bytes) || !get_u32(env, argv[1], &C) || !get_u64(env, argv[2], &T) ||
+	    (argc >= 4 && argv[3] && !is_nullish(env, argv[3]) && !get_u32(env, argv[3], &nthreads)))
+		return reject_now(env, "encodeTuples(dims:ArrayBuffer, C:uint32, T:uint53, nthreads?:uint32)");
+	if (C == 0 || (T && (uint64_t)C > UINT64_MAX / 36 / T) || (uint64_t)C * T * 36 > bytes) return reject_now(env, "encodeTuples: dims buffer is smaller than C*T*36 bytes");
+	enc_t *q = (enc_t *)calloc(1, sizeof *q);
+	if (!q) return reject_now(env, "encodeTuples: out of host memory");
+	q->dims = (const float *)dims; q->C = C; q->T = T; q->nthreads = nthreads ? nthreads : 1;
+	napi_value promise = NULL, rname;
+	napi_create_promise(env, &q->deferred, &promise);
+	napi_create_reference(env, argv[0], 1, &q->keep);                /* the encoder reads the caller's buffer on a worker thread */
+	napi_create_string_utf8(env, "apo_tuple_encode_host", NAPI_AUTO_LENGTH, &rname);
+	napi_create_async_work(env, NULL, rname, enc_execute, enc_complete, q, &q->work);
+	napi_queue_async_work(env, q->work);
+	return promise;
+}
+
+/* scoreHostTuples(h, {tl, th, tbookPc, tbookPd, codebook, d2book, nTuples}, C, T, corpus|null, K) -> Promise<{scores, counts, topk, report}>:
+ * the evaluations travel as 3-byte dictionary indices (Form T) instead of 36-byte fp32 rows; same integers, same result. */
+static napi_value ScoreHostTuples(napi_env env, napi_callback_info info)
+{
+	static const char *names[6] = {"tl", "th", "tbookPc", "tbookPd", "codebook", "d2book"};
+	ARGS(6)
+	call_t *c = argc >= 1 ? new_call(env, argv[0], APO_JOB_SCORE_HOST_TUPLES) : NULL;
+	if (!c) return reject_now(env, "scoreHostTuples: invalid handle");
+	napi_valuetype t;
+	napi_value arr[6] = {NULL, NULL, NULL, NULL, NULL, NULL}, corpus = NULL;
+	int ok = argc >= 6 && napi_typeof(env, argv[1], &t) == napi_ok && t == napi_object;
+	for (int i = 0; ok && i < 6; i++) {
+		ok = napi_get_named_property(env, argv[1], names[i], &arr[i]) == napi_ok &&
+		     (i == 0 ? get_buffer(env, arr[i], &c->job.buf, &c->job.buf_bytes) : get_buffer(env, arr[i], &c->job.aux[i - 1], &c->job.aux_bytes[i - 1]));
+		if (!ok) arr[i] = NULL;
+	}
+	if (ok) ok = opt_u32(env, argv[1], "nTuples", &c->job.n_tuples) && get_u32(env, argv[2], &c->job.C) && get_u64(env, argv[3], &c->job.T) && get_u32(env, argv[5], &c->job.K);
+	if (ok && !is_nullish(env, argv[4])) {
+		ok = get_buffer(env, argv[4], &c->job.corpus, &c->job.corpus_bytes);
+		corpus = ok ? argv[4] : NULL;
+	}
+	if (!ok) arg_error(c, "scoreHostTuples(handle, {tl, th, tbookPc, tbookPd, codebook, d2book: ArrayBuffer, nTuples:uint32}, C:uint32, T:uint53, corpus:ArrayBuffer|null, K:uint32)");
+	for (int i = 1; i < 6; i++)                                      /* the job reads these on a worker thread: keep them alive */
+		if (arr[i]) napi_create_reference(env, arr[i], 1, &c->keep[c->nkeep++]);
+	return submit(env, c, argv[0], arr[0], corpus, "apo_score_host_tuples");
+}
+
 /* rewardBatch(h, recs) -> Promise<{dims, masks, finals}> = TraceCollectorService._computeRewardSignals for n traces
  * (TCS:668-788).  Async like everything else; the TS service micro-batches the single-trace calls of one tick. */
 static napi_value RewardBatch(napi_env env, napi_callback_info info)
@@ -419,6 +526,8 @@ NAPI_MODULE_INIT()
 	    {"scoreResident", NULL, ScoreResident, NULL, NULL, NULL, napi_default, NULL},
 	    {"score", NULL, Score, NULL, NULL, NULL, napi_default, NULL},
 	    {"scoreHostRecords", NULL, ScoreHostRecords, NULL, NULL, NULL, napi_default, NULL},
+	    {"encodeTuples", NULL, EncodeTuples, NULL, NULL, NULL, napi_default, NULL},
+	    {"scoreHostTuples", NULL, ScoreHostTuples, NULL, NULL, NULL, napi_default, NULL},
 	    {"rewardBatch", NULL, RewardBatch, NULL, NULL, NULL, napi_default, NULL},
 	    {"commUniqueId", NULL, CommUniqueId, NULL, NULL, NULL, napi_default, NULL},
 	    {"commInit", NULL, CommInit, NULL, NULL, NULL, napi_default, NULL},

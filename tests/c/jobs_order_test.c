@@ -90,6 +90,23 @@ int main(void)
 	{ apo_job b = j; b.kind = APO_JOB_SCORE_HOST_RECORDS; b.row_bytes = 32; b.T = 5; fails += expect_bad(b, "records buffer shorter than C*T*32"); }
 	{ apo_job b = j; b.kind = APO_JOB_REWARD_BATCH; b.buf_bytes = 40; fails += expect_bad(b, "record bytes not a multiple of 32"); }
 	{ apo_job b = j; b.kind = APO_JOB_COMM_INIT; b.nranks = 2; b.rank = 2; fails += expect_bad(b, "rank >= nranks"); }
+	{
+		/* Form T: 1 x 4 evaluations, two dictionary entries */
+		static uint16_t tl[4]; static uint8_t th[4]; static uint32_t tpc[2], book[8 * 256], d2b[4096]; static uint16_t tpd[2];
+		apo_job t; memset(&t, 0, sizeof t);
+		t.kind = APO_JOB_SCORE_HOST_TUPLES; t.C = 1; t.T = 4; t.K = 1; t.n_tuples = 2;
+		t.buf = tl; t.buf_bytes = sizeof tl; t.aux[0] = th; t.aux_bytes[0] = sizeof th; t.aux[1] = tpc; t.aux_bytes[1] = sizeof tpc;
+		t.aux[2] = tpd; t.aux_bytes[2] = sizeof tpd; t.aux[3] = book; t.aux_bytes[3] = sizeof book; t.aux[4] = d2b; t.aux_bytes[4] = sizeof d2b;
+		if (apo_job_validate(&t) != APO_OK) { printf("FAIL: valid Form T job rejected: %s\n", t.err); fails++; }
+		{ apo_job b = t; b.T = 5; fails += expect_bad(b, "tl plane shorter than C*T*2"); }
+		{ apo_job b = t; b.aux_bytes[0] = 3; fails += expect_bad(b, "th plane shorter than C*T"); }
+		{ apo_job b = t; b.n_tuples = 3; fails += expect_bad(b, "dictionary shorter than nTuples"); }
+		{ apo_job b = t; b.n_tuples = 0; fails += expect_bad(b, "evaluations without a dictionary"); }
+		{ apo_job b = t; b.n_tuples = 1u << 24; fails += expect_bad(b, "too many dictionary entries"); }
+		{ apo_job b = t; b.aux_bytes[3] = 100; fails += expect_bad(b, "codebook of the wrong size"); }
+		{ apo_job b = t; b.aux[4] = NULL; fails += expect_bad(b, "d2book missing"); }
+		{ apo_job b = t; b.K = 2; fails += expect_bad(b, "K exceeds C"); }
+	}
 	{ apo_job b = j; b.kind = APO_JOB_SCORE_RESIDENT; b.first = 3; fails += expect_bad(b, "window start not a multiple of 4"); }
 	{ apo_job b = j; b.kind = APO_JOB_SCORE_RESIDENT; b.first = 0; b.K = 20000; b.C = 30000; fails += expect_bad(b, "K above the beam-width limit"); }
 	{ apo_job b = j; b.kind = (apo_job_kind)99; fails += expect_bad(b, "unknown kind"); }

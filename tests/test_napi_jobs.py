@@ -19,11 +19,11 @@ def test_addon_compiles_against_the_napi_prototypes():
 def test_addon_exports_cover_the_resident_path_and_comm():
     src = open(os.path.join(ROOT, "napi", "apo_napi.c")).read()
     for name in ("create", "lastCreateError", "dimsUpload", "rolloutsUpload", "corpusUpload", "corpusUploadJson", "scoreResident", "score",
-                 "scoreHostRecords", "rewardBatch", "commUniqueId", "commInit", "allocPinned", "recordsFromJson"):
+                 "scoreHostRecords", "encodeTuples", "scoreHostTuples", "rewardBatch", "commUniqueId", "commInit", "allocPinned", "recordsFromJson"):
         assert f'{{"{name}", NULL,' in src, name
     assert "napi_throw_error" not in src                      # never throws into the caller (TCS:438)
     ts = open(os.path.join(ROOT, "ts", "apoScoringMainService.ts")).read()
-    for name in ("dimsUpload", "corpusUpload", "scoreResident", "scoreHostRecords", "rewardBatch"):
+    for name in ("dimsUpload", "corpusUpload", "scoreResident", "scoreHostRecords", "encodeTuples", "scoreHostTuples", "rewardBatch"):
         assert name in ts, name
 
 

@@ -32,11 +32,20 @@ interface ApoAddon {
 	scoreResident(handle: unknown, query: ApoResidentQuery): Promise<Blocks>;
 	score(handle: unknown, dims: ArrayBuffer, C: number, T: number, corpus: ArrayBuffer | null, K: number): Promise<Blocks>;
 	scoreHostRecords(handle: unknown, records: ArrayBuffer, rowBytes: number, C: number, T: number, corpus: ArrayBuffer | null, K: number): Promise<Blocks>;
+	/** Form D -> Form T on worker threads of the addon (no GPU): 3 bytes per evaluation instead of 36; null = not categorical. */
+	encodeTuples(dims: ArrayBuffer, C: number, T: number, nthreads?: number): Promise<ApoTuples | null>;
+	scoreHostTuples(handle: unknown, tuples: ApoTuples, C: number, T: number, corpus: ArrayBuffer | null, K: number): Promise<Blocks>;
 	rewardBatch(handle: unknown, records: ArrayBuffer): Promise<{ dims: ArrayBuffer; masks: ArrayBuffer; finals: ArrayBuffer }>;
 	recordsFromJson(utf8: ArrayBuffer): ArrayBuffer | null;
 }
 
+/** Form T (include/apo_b200.h): 24-bit dictionary index per evaluation as two planes + the dictionary of distinct evaluations. */
+interface ApoTuples { tl: ArrayBuffer; th: ArrayBuffer; tbookPc: ArrayBuffer; tbookPd: ArrayBuffer; codebook: ArrayBuffer; d2book: ArrayBuffer; nTuples: number }
+
 const RECORD_BYTES = 32;
+/** From this many evaluations on, score() re-encodes the fp32 tensor as dictionary indices before it crosses PCIe: the encode
+ *  (two threaded passes over host memory) costs less than the 33 bytes per evaluation it keeps off the bus. */
+const TUPLE_TRANSPORT_MIN_EVALS = 1 << 20;
 
 function ab(buf: VSBuffer): ArrayBuffer {
 	const u8 = buf.buffer;
@@ -157,7 +166,14 @@ export class ApoScoringMainService implements IApoScoringService {
 
 	// ---- one-shot path ------------------------------------------------------------------------
 	async score(dims: VSBuffer, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks> {
-		return wrapBlocks(await (await this._need()).score(this._handle, ab(dims), C, T, corpus ? ab(corpus) : null, K));
+		const addon = await this._need();
+		const host = ab(dims), rec = corpus ? ab(corpus) : null;
+		if (C * T >= TUPLE_TRANSPORT_MIN_EVALS) {
+			// same integers, same result: only the bytes on the wire differ (DESIGN.md section 3, Form T)
+			const tuples = await addon.encodeTuples(host, C, T);
+			if (tuples) { return wrapBlocks(await addon.scoreHostTuples(this._handle, tuples, C, T, rec, K)); }
+		}
+		return wrapBlocks(await addon.score(this._handle, host, C, T, rec, K));
 	}
 
 	async scoreHostRecords(records: VSBuffer, rowBytes: 32 | 16, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks> {

@@ -502,16 +502,24 @@ extern "C" int apo_tuple_encode_host(const uint32_t *pc, const uint16_t *pd, uin
 	const uint64_t N = (uint64_t)C * T;
 	// ---- pass 1: distinct evaluations and how often each occurs, per thread
 	std::vector<TupleMap> maps((size_t)nthreads);
+	std::vector<uint64_t> over((size_t)nthreads, 0);
 	run_threads(nthreads, [&](int k, int n) {
 		TupleMap &m = maps[(size_t)k];
 		const uint64_t a = N * (uint64_t)k / (uint64_t)n, b = N * (uint64_t)(k + 1) / (uint64_t)n;
-		for (uint64_t i = a; i < b; i++) ++*m.slot(tuple_key(pc[i], pd[i]));
+		for (uint64_t i = a; i < b; i++) {
+			++*m.slot(tuple_key(pc[i], pd[i]));
+			// not categorical (free-form data): stop before the maps grow with the tensor; the count reported is a lower bound
+			if (m.used > cap) { over[(size_t)k] = m.used; return; }
+		}
 	});
+	for (int k = 0; k < nthreads; k++)
+		if (over[(size_t)k]) { *n_tuples = over[(size_t)k] > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)over[(size_t)k]; return APO_E_STATE; }
 	TupleMap all(1u << 18);
 	for (int k = 0; k < nthreads; k++) {
 		const TupleMap &m = maps[(size_t)k];
 		for (size_t i = 0; i < m.key.size(); i++) if (m.key[i] != TupleMap::EMPTY) *all.slot(m.key[i]) += m.val[i];
 		maps[(size_t)k].reset(2);
+		if (all.used > cap) break;
 	}
 	if (all.used > cap) { *n_tuples = all.used > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)all.used; return APO_E_STATE; }
 	// ---- dictionary order: most frequent first (the head of the table lives in shared memory), ties by key: deterministic

@@ -65,13 +65,15 @@ class JSFunction:
 
 
 class NativeFunction:
-    def __init__(self, fn):
+    def __init__(self, fn, props=None):
         self.fn = fn
+        self.props = props or {}                       # static members (`Number.isNaN`), constructors called through `new`
 
 
 # ------------------------------------------------------------------------------------------------ tokenizer
-PUNCT = ["===", "!==", "...", "=>", ">=", "<=", "&&", "||", "??", "?.", "++", "--", "+=", "-=", "*=", "/=", "==", "!=",
-         "{", "}", "(", ")", "[", "]", ";", ",", "<", ">", "+", "-", "*", "/", "%", "!", "?", ":", "=", ".", "|", "&"]
+PUNCT = ["===", "!==", "...", ">>>", "=>", ">=", "<=", "&&", "||", "??", "?.", "++", "--", "+=", "-=", "*=", "/=", "|=", "&=", "==", "!=",
+         "<<", ">>", "{", "}", "(", ")", "[", "]", ";", ",", "<", ">", "+", "-", "*", "/", "%", "!", "?", ":", "=", ".", "|", "&", "^"]
+_hex = re.compile(r"0[xX][0-9a-fA-F]+")
 _num = re.compile(r"(?:\d+\.\d*|\.\d+|\d+)(?:[eE][+-]?\d+)?")
 _ident = re.compile(r"[A-Za-z_$][A-Za-z0-9_$]*")
 
@@ -92,6 +94,11 @@ def tokenize(src: str):
             if j < 0:
                 raise JSUnsupported("unterminated comment")
             i = j + 2
+            continue
+        m = _hex.match(src, i)
+        if m:
+            toks.append(("num", int(m.group(0), 16)))
+            i = m.end()
             continue
         m = _num.match(src, i)
         if m and (c.isdigit() or (c == "." and i + 1 < n and src[i + 1].isdigit())):
@@ -195,6 +202,9 @@ class Parser:
                 raise JSUnsupported("unterminated type")
             if tk[0] == "p":
                 v = tk[1]
+                if v in (">>", ">>>"):                  # inside a type these are closing angle brackets, not shifts
+                    self.t[self.i:self.i + 1] = [("p", ">")] * len(v)
+                    continue
                 if depth == 0 and v in stop:
                     return
                 if v in "({[<":
@@ -432,7 +442,7 @@ class Parser:
         if tk == ("p", "(") and self.is_arrow_ahead():
             return self.arrow()
         left = self.ternary()
-        for op in ("=", "+=", "-=", "*=", "/="):
+        for op in ("=", "+=", "-=", "*=", "/=", "|=", "&="):
             if self.at(op) and self.peek()[0] == "p":
                 self.i += 1
                 right = self.assignment()
@@ -466,10 +476,31 @@ class Parser:
         return e
 
     def logical_and(self):
-        e = self.equality()
+        e = self.bit_or()
         while self.at("&&"):
             self.i += 1
-            e = ("and", e, self.equality())
+            e = ("and", e, self.bit_or())
+        return e
+
+    def bit_or(self):
+        e = self.bit_xor()
+        while self.at("|") and self.peek()[0] == "p":
+            self.i += 1
+            e = ("bin", "|", e, self.bit_xor())
+        return e
+
+    def bit_xor(self):
+        e = self.bit_and()
+        while self.at("^") and self.peek()[0] == "p":
+            self.i += 1
+            e = ("bin", "^", e, self.bit_and())
+        return e
+
+    def bit_and(self):
+        e = self.equality()
+        while self.at("&") and self.peek()[0] == "p":
+            self.i += 1
+            e = ("bin", "&", e, self.equality())
         return e
 
     def equality(self):
@@ -480,13 +511,21 @@ class Parser:
             e = ("bin", op, e, self.relational())
         return e
 
-    def relational(self):
+    def shift(self):
         e = self.additive()
+        while self.peek()[0] == "p" and self.peek()[1] in ("<<", ">>", ">>>"):
+            op = self.peek()[1]
+            self.i += 1
+            e = ("bin", op, e, self.additive())
+        return e
+
+    def relational(self):
+        e = self.shift()
         while True:
             tk = self.peek()
             if tk[0] == "p" and tk[1] in ("<", ">", "<=", ">="):
                 self.i += 1
-                e = ("bin", tk[1], e, self.additive())
+                e = ("bin", tk[1], e, self.shift())
             elif tk == ("id", "as"):
                 self.i += 1
                 self.skip_type((",", ")", "]", "}", ";", "?", ":", "||", "&&", "??", "===", "!==", "=", "=>", "+", "-"))
@@ -695,7 +734,9 @@ def parse_method(src: str):
         b = p.binding()
         p.eat("?")
         if p.eat(":"):
-            p.skip_type((",", ")"))
+            p.skip_type((",", ")", "="))
+        if p.eat("="):
+            b = ("defpat", b, p.assignment())           # parameter default: evaluated in the callee's scope when the argument is undefined
         params.append(b)
         if not p.eat(","):
             break
@@ -817,6 +858,18 @@ def to_fixed(x, digits):
     return ("-" if x < 0 else "") + s          # the sign is that of x (ECMAScript step 5): (-0.0004).toFixed(3) is "-0.000"
 
 
+def to_int32(v):
+    x = to_number(v)
+    if isinstance(x, bool):
+        x = int(x)
+    if isinstance(x, float):
+        if math.isnan(x) or math.isinf(x):
+            return 0
+        x = int(x)                                        # truncation toward zero
+    x &= 0xFFFFFFFF
+    return x - (1 << 32) if x & 0x80000000 else x
+
+
 def strict_equal(a, b):
     if is_num(a) and is_num(b):
         return float(a) == float(b)
@@ -850,7 +903,9 @@ class Interp:
                                entries=NativeFunction(lambda t, o: JSArray(JSArray([k, v]) for k, v in o.items()))),
             "Array": JSObject(**{"from": NativeFunction(lambda t, it: JSArray(self.iterate(it))),
                                  "isArray": NativeFunction(lambda t, v: isinstance(v, JSArray))}),
-            "Number": NativeFunction(lambda t, v=0: to_number(v)),
+            "Number": NativeFunction(lambda t, v=0: to_number(v),
+                                     {"isNaN": NativeFunction(lambda t, v=undefined: isinstance(v, float) and math.isnan(v)),
+                                      "isFinite": NativeFunction(lambda t, v=undefined: is_num(v) and math.isfinite(v))}),
             "String": NativeFunction(lambda t, v="": to_string(v)),
             "Boolean": NativeFunction(lambda t, v=False: truthy(v)),
         })
@@ -912,6 +967,8 @@ class Interp:
         elif pat[0] == "objpat":
             for key, target in pat[1]:
                 self.bind(env, target, self.get(value, key), kind)
+        elif pat[0] == "defpat":
+            self.bind(env, pat[1], self.ev_top(pat[2], env, undefined) if value is undefined else value, kind)
         else:
             raise JSUnsupported(pat[0])
 
@@ -957,6 +1014,10 @@ class Interp:
             if key == "toString":
                 return NativeFunction(lambda this: num_to_string(obj))
             raise JSUnsupported(f"Number.prototype.{key}")
+        if isinstance(obj, NativeFunction):
+            if key in obj.props:
+                return obj.props[key]
+            raise JSUnsupported(f"property {key!r} of a native function")
         if isinstance(obj, JSMap):
             if key == "size":
                 return len(obj.d)
@@ -1199,6 +1260,22 @@ class Interp:
                 if (isinstance(a, float) and math.isnan(a)) or (isinstance(b, float) and math.isnan(b)):
                     return False
             return {"<": a < b, ">": a > b, "<=": a <= b, ">=": a >= b}[op]
+        if op in ("|", "&", "^", "<<", ">>", ">>>"):
+            x, y = to_int32(a), to_int32(b)
+            if op == "|":
+                r = x | y
+            elif op == "&":
+                r = x & y
+            elif op == "^":
+                r = x ^ y
+            elif op == "<<":
+                r = x << (y & 31)
+            elif op == ">>":
+                r = x >> (y & 31)
+            else:
+                return (x & 0xFFFFFFFF) >> (y & 31)
+            r &= 0xFFFFFFFF
+            return r - (1 << 32) if r & 0x80000000 else r
         if op == "===":
             return strict_equal(a, b)
         if op == "!==":
@@ -1335,6 +1412,11 @@ class Interp:
             if ctor == ("name", "Map"):
                 args = [self.ev_top(a, env, this) for a in node[2]]
                 return JSMap((e[0], e[1]) for e in (args[0] if args else []))
+            if ctor[0] == "name":
+                scope = env.lookup(ctor[1])
+                fn = scope.vars[ctor[1]] if scope is not None else None
+                if isinstance(fn, NativeFunction):         # host-provided constructor (DataView in the codec tests)
+                    return fn.fn(undefined, *[self.ev_top(a, env, this) for a in node[2]])
             raise JSUnsupported(f"new {ctor}")
         raise JSUnsupported(f"expression {k}")
 

@@ -64,6 +64,13 @@ class JSFunction:
         self.params, self.body, self.env, self.is_expr, self.this = params, body, env, is_expr, this
 
 
+class SyncPromise:
+    """A settled promise for code that is run synchronously: `then` calls its callback at once, `await` yields the value.
+    Enough for data-flow checks of async service methods (the order of microtasks is not modelled)."""
+    def __init__(self, value=None, error=None, rejected=False):
+        self.value, self.error, self.rejected = value, error, rejected
+
+
 class NativeFunction:
     def __init__(self, fn, props=None):
         self.fn = fn
@@ -529,7 +536,10 @@ class Parser:
             elif tk == ("id", "as"):
                 self.i += 1
                 self.skip_type((",", ")", "]", "}", ";", "?", ":", "||", "&&", "??", "===", "!==", "=", "=>", "+", "-"))
-            elif tk == ("id", "instanceof") or tk == ("id", "in"):
+            elif tk == ("id", "instanceof"):
+                self.i += 1
+                e = ("instanceof", e, self.shift())
+            elif tk == ("id", "in"):
                 raise JSUnsupported(tk[1])
             else:
                 return e
@@ -562,7 +572,10 @@ class Parser:
         if tk == ("id", "typeof"):
             self.i += 1
             return ("typeof", self.unary())
-        if tk[0] == "id" and tk[1] in ("await", "delete", "void", "yield"):
+        if tk == ("id", "await"):
+            self.i += 1
+            return ("await", self.unary())
+        if tk[0] == "id" and tk[1] in ("delete", "void", "yield"):
             raise JSUnsupported(tk[1])
         e = self.postfix()
         while self.at("!") and self.peek(1)[0] == "p" and self.peek(1)[1] in (".", ")", ",", ";", "]", "["):
@@ -724,9 +737,7 @@ def parse_method(src: str):
     """`[private] name(params): T { body }` -> (name, [param patterns], body block).  Types are skipped."""
     p = Parser(src)
     while p.peek()[0] == "id" and p.peek()[1] in ("private", "public", "protected", "async", "static", "readonly"):
-        if p.peek()[1] == "async":
-            raise JSUnsupported("async method")
-        p.i += 1
+        p.i += 1                                        # `async`: the body runs synchronously, `await` unwraps a SyncPromise
     name = p.ident()
     p.need("(")
     params = []
@@ -1014,6 +1025,19 @@ class Interp:
             if key == "toString":
                 return NativeFunction(lambda this: num_to_string(obj))
             raise JSUnsupported(f"Number.prototype.{key}")
+        if isinstance(obj, SyncPromise):
+            def then(this, f=undefined, g=undefined):
+                try:
+                    if obj.rejected:
+                        return obj if g is undefined else SyncPromise(self.call(g, undefined, [obj.error]))
+                    return obj if f is undefined else SyncPromise(self.call(f, undefined, [obj.value]))
+                except JSThrow as e:
+                    return SyncPromise(error=e.v, rejected=True)
+            if key == "then":
+                return NativeFunction(then)
+            if key == "catch":
+                return NativeFunction(lambda this, g=undefined: then(this, undefined, g))
+            raise JSUnsupported(f"Promise.prototype.{key}")
         if isinstance(obj, NativeFunction):
             if key in obj.props:
                 return obj.props[key]
@@ -1377,6 +1401,17 @@ class Interp:
                 return not truthy(v)
             v = to_number(v)
             return -v if node[1] == "-" else v
+        if k == "await":
+            v = self.ev_top(node[1], env, this)
+            if isinstance(v, SyncPromise):
+                if v.rejected:
+                    raise JSThrow(v.error)
+                return v.value
+            return v
+        if k == "instanceof":
+            v = self.ev_top(node[1], env, this)
+            ctor = self.ev_top(node[2], env, this)
+            return isinstance(v, JSObject) and v.get("__ctor__", undefined) is ctor
         if k == "typeof":
             v = self.ev_top(node[1], env, this)
             if v is undefined:

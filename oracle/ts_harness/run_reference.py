@@ -46,7 +46,7 @@ def extract_method(text: str, name: str):
     """Source text and 1-based line range of the class method `name` (declaration at one tab of indentation)."""
     import re
     m, i, j = None, 0, 0
-    for cand in re.finditer(r"^\t(?:(?:private|public|protected)\s+)?" + re.escape(name) + r"\s*\(", text, re.M):
+    for cand in re.finditer(r"^\t(?:(?:private|public|protected)\s+)?(?:async\s+)?" + re.escape(name) + r"\s*\(", text, re.M):
         i = text.index("(", cand.start())
         depth = 0
         while True:                                   # parameter list: balanced parentheses

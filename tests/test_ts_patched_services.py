@@ -1,0 +1,87 @@
+"""The TypeScript drop-in, executed: a senweaver-ide checkout with ts/patches/*.ed applied is run end to end on the CPU
+(oracle/ts_harness/run_patched.py) — the PATCHED `_computeRewardSignals`, `_refreshEngineStats`, `getStats`, `_buildReport`,
+`_analyzePatterns` and the functions of ts/traceRecordCodec.ts, unmodified, in the in-repo TypeScript-subset interpreter, with
+`IApoScoringService` answered by byte blocks in the C ABI's formats (computed by the oracle; in the IDE: by the B200 engine).
+Everything they return must equal what the UNPATCHED reference returned for the same inputs (tests/golden/ref_*.json, the parity
+pin): the per-trace reward dimensions and finalReward bit for bit, the whole PromptEffectivenessReport object (tallies, per-mode
+stats in first-appearance order, the six patterns with ids / severities / example previews, the dimension-low patterns, every
+generated suggestion), and the collector / APO stats.  Needs the reference checkout (the patches apply to it)."""
+import json
+import math
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "src/vs/workbench/contrib/senweaver/common/apoService.ts")),
+                                reason="reference checkout not present")
+
+
+def num(v):
+    """fixture number: binary64 as a hex string, JS integer literals as JSON integers"""
+    if isinstance(v, str) and (v == "nan" or v.lstrip("-").startswith("0x")):
+        return math.nan if v == "nan" else float.fromhex(v)
+    return v
+
+
+def same(a, b, tol=0.0, path=""):
+    """deep equality; numbers by value (0 == 0.0: one JS Number), optionally within a relative tolerance"""
+    a, b = num(a), num(b)
+    if isinstance(a, bool) or isinstance(b, bool) or a is None or b is None or isinstance(a, str) or isinstance(b, str):
+        assert a == b and type(a) is type(b), (path, a, b)
+    elif isinstance(a, (int, float)) and isinstance(b, (int, float)):
+        if isinstance(a, float) and math.isnan(a):
+            assert isinstance(b, float) and math.isnan(b), (path, a, b)
+        else:
+            assert a == b or (tol and abs(a - b) <= tol * max(1.0, abs(a), abs(b))), (path, a, b)
+    elif isinstance(a, dict):
+        assert isinstance(b, dict) and list(a) == list(b), (path, list(a), list(b) if isinstance(b, dict) else b)      # key ORDER too
+        for k in a:
+            same(a[k], b[k], tol, f"{path}/{k}")
+    else:
+        assert isinstance(a, list) and isinstance(b, list) and len(a) == len(b), (path, a, b)
+        for i, (x, y) in enumerate(zip(a, b)):
+            same(x, y, tol, f"{path}[{i}]")
+
+
+@pytest.fixture(scope="module")
+def outputs(orc):
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ts_harness"))
+    import run_patched as rp
+    return rp.build_outputs(REF)
+
+
+def test_the_patched_methods_are_the_ones_that_ran(outputs):
+    _, _, calls, lines = outputs
+    assert calls["rewardBatch"] > 431 and calls["score"] > 11          # every reward and every report went through the service
+    sys.path.insert(0, os.path.join(ROOT, "ts", "patches"))
+    import make_patches as mp
+    tcs, apo = mp.patched_text(REF, mp.TCS).split("\n"), mp.patched_text(REF, mp.APO).split("\n")
+    for key, text in (("TCS._computeRewardSignals", tcs), ("TCS._refreshEngineStats", tcs), ("APO._buildReport", apo)):
+        a, b = lines[key]
+        assert "this._scoring." in "\n".join(text[a - 1:b]), key
+    a, b = lines["APO._analyzePatterns"]
+    assert "R.patterns.forEach" in "\n".join(apo[a - 1:b])
+
+
+def test_patched_reward_signals_equal_the_reference_bit_for_bit(outputs):
+    cases = outputs[0]
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_reward_cases.json")))["cases"]
+    assert len(cases) == len(want) == 431
+    for c, w in zip(cases, want):
+        assert c["name"] == w["name"] and c["dims"] == w["dims"] and c["finalReward"] == w["finalReward"], c["name"]
+
+
+def test_patched_reports_and_stats_equal_the_reference(outputs):
+    reports = outputs[1]
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_report_cases.json")))["corpora"]
+    assert set(reports) == set(want) and len(reports) == 11
+    for cname, got in reports.items():
+        w = want[cname]
+        same(got["report"], w["report"], 0.0, f"{cname}/report")               # the object APOService returns: exact
+        # what _buildReport hands to _generateLocalSuggestions: the engine's sums are exact integers / 2^52, the reference adds
+        # doubles in trace order -> equal to ~1e-15 relative, and equal in everything derived from them above
+        same(got["locals"], w["locals"], 1e-12, f"{cname}/locals")
+        same(got["stats"], w["stats"], 1e-12, f"{cname}/stats")

@@ -239,8 +239,17 @@ def test_minijs_semantics_known_javascript_results():
     assert run("Object.entries(o).map(([k, v]) => k + v)", o={"b": 1, "a": 2}) == ["b1", "a2"]                        # insertion order
     assert run("null === undefined") is False and run("x !== null", x=None) is False and run("typeof y", y=1.5) == "number"
     assert run("s.substring(0, 3)", s="abcdef") == "abc" and run("[1,2,3,4].slice(0, 3)") == [1, 2, 3]
-    with pytest.raises(js.JSUnsupported):
-        run("a instanceof b", a=1, b=2)
+    # constructs the codec / the patched services add (tests/test_ts_codec.py, tests/test_ts_patched_services.py)
+    assert run("0x80 | (d > 0 ? 0x04 : 0) | (d > 15000 ? 0x08 : 0)", d=20000.5) == 0x8C and run("(m >> 2) & 1", m=0b1101) == 1
+    assert run("1 << 31") == -2147483648 and run("(1 << 31) >>> 0") == 2147483648 and run("5 ^ 3") == 6 and run("-1 >>> 28") == 15
+    assert run("a | b === 1", a=2, b=1) == 3 and run("(4294967296 + 7) | 0") == 7 and run("x instanceof y", x=1, y=2) is False
+    assert run("await p", p=js.SyncPromise(41)) == 41 and run("await 5") == 5
+    assert run("p.then(v => v + 1).then(v => v * 2)", p=js.SyncPromise(20)).value == 42
+    assert run("p.then(v => v + 1).catch(e => 'caught ' + e)", p=js.SyncPromise(error="boom", rejected=True)).value == "caught boom"
+    name, fn = I.make_method("f(a: number, b = a * 2, c: string = 'z'): string { return a + b + c; }", js.undefined)
+    assert I.call(fn, js.undefined, [1]) == "3z" and I.call(fn, js.undefined, [1, 5, "y"]) == "6y"
+    with pytest.raises(js.JSUnsupported):                    # what the interpreter does not model fails loudly instead of guessing
+        run("'k' in o", o={})
 
 
 # ------------------------------------------------------------------------------------------------ the CUDA engine

@@ -2,8 +2,8 @@
 """Runs the PATCHED reference services — what a senweaver-ide checkout looks like after ts/patches/*.ed — end to end on the CPU.
 
 Test infrastructure (like everything under oracle/): the method texts of the patched traceCollectorService.ts / apoService.ts
-(`_computeRewardSignals`, `_refreshEngineStats`, `getStats`; `_buildReport`, `_analyzePatterns` + the untouched `_extractMode`,
-`_generateLocalSuggestions`, `getStats`) and the functions of ts/traceRecordCodec.ts are executed unmodified by
+(`_computeRewardSignals`, `_refreshEngineStats`, `getStats`; `_buildReport`, `_analyzePatterns`, `_evaluateBeam`, `_applyBeamUpdate` + the
+untouched `_extractMode`, `_generateLocalSuggestions`, `getStats`) and the functions of ts/traceRecordCodec.ts are executed unmodified by
 oracle/ts_harness/minijs.py; `IApoScoringService` is a stand-in that answers `rewardBatch` / `score` with the byte blocks the
 C ABI returns (apo_reward_batch's dims / masks / finals, struct apo_corpus_report), computed here by the ORACLE — so the whole
 TypeScript data flow (trace -> 32-byte record -> service call -> result block -> decoded numbers -> report object) runs, and its
@@ -45,8 +45,18 @@ class ByteBuf:
 
 def uint8array(this, arg=0, offset=0, length=js.undefined):
     buf = arg if isinstance(arg, ByteBuf) else ByteBuf(int(js.to_number(arg)))
-    n = len(buf.b) - int(offset) if length is js.undefined else int(length)
-    return js.JSObject(buffer=buf, byteOffset=int(offset), byteLength=n, length=n)
+    off = int(offset)
+    n = len(buf.b) - off if length is js.undefined else int(length)
+    copy = js.NativeFunction(lambda this: uint8array(None, ByteBuf(buf.b[off:off + n])))       # .slice(): a copy with its own ArrayBuffer
+    return js.JSObject(buffer=buf, byteOffset=off, byteLength=n, length=n, slice=copy)
+
+
+def typed_array(fmt: str, size: int):
+    """new Float64Array(arrayBuffer) / new Int32Array(arrayBuffer): little endian like every platform the IDE runs on"""
+    def ctor(this, buf):
+        assert isinstance(buf, ByteBuf) and len(buf.b) % size == 0
+        return js.JSArray(struct.unpack(f"<{len(buf.b) // size}{fmt}", bytes(buf.b)))
+    return js.NativeFunction(ctor)
 
 
 def data_view(this, buf, offset=0, length=js.undefined):
@@ -127,11 +137,15 @@ class OracleScoring:
 
     def score(self, this, dims, C, T, corpus=js.undefined, K=0):
         self.calls["score"] += 1
-        assert C == 1 and T == 4, "the services only make report-only calls here"
+        C, T, K = int(C), int(T), int(K)
         recs = np.frombuffer(vsbuffer_bytes(corpus), dtype=oracle.RECORD_DTYPE) if corpus is not js.undefined and corpus is not None else np.empty(0, oracle.RECORD_DTYPE)
         rep = oracle.report(recs)
-        return js.SyncPromise(js.JSObject(scores=vsbuffer(struct.pack("<d", float("-inf"))), counts=vsbuffer(bytes(8)), topk=vsbuffer(b""),
-                                          report=vsbuffer(bytes(rep))))
+        d = np.frombuffer(vsbuffer_bytes(dims), dtype=np.float32)
+        assert d.size == C * T * 9, "dims block is not float32[C][T][9]"
+        scores, counts = oracle.score_dims(d.reshape(C, T, 9))
+        topk = oracle.topk(scores, K) if K else np.empty(0, np.int32)
+        return js.SyncPromise(js.JSObject(scores=vsbuffer(np.asarray(scores, "<f8").tobytes()), counts=vsbuffer(np.asarray(counts, "<u8").tobytes()),
+                                          topk=vsbuffer(np.asarray(topk, "<i4").tobytes()), report=vsbuffer(bytes(rep))))
 
 
 # ------------------------------------------------------------------------------------------------ patched services
@@ -151,6 +165,7 @@ class Patched(rr.Reference):
             r"^(?:export )?const (?:APO_RECORD_BYTES|F_ERRORS|MODE_CODE|U32_MAX|SEV|MODES|u64)\b.*$", src, re.M))
         consts += "\n" + re.search(r"^export (const DIM_NAMES = \[.*?\] as const;)", src, re.M | re.S).group(1)
         g.update({"DataView": js.NativeFunction(data_view), "Uint8Array": js.NativeFunction(uint8array),
+                  "Float64Array": typed_array("d", 8), "Int32Array": typed_array("i", 4),
                   "VSBuffer": js.JSObject(wrap=js.NativeFunction(lambda this, u8: js.JSObject(buffer=u8))),
                   "queueMicrotask": js.NativeFunction(lambda this, f: self.interp.call(f, js.undefined, [])),
                   "EMPTY_DIMS": vsbuffer(np.full(36, np.nan, np.float32).tobytes())})
@@ -163,7 +178,17 @@ class Patched(rr.Reference):
         self.tcs.update(_scoring=svc, _engineStats=None, _dirty=False, _onDidChangeState=fire,
                         _saveToStorage=js.NativeFunction(lambda this: js.undefined))
         self.tcs["_refreshEngineStats"] = self._method(self.tcs_text, "TCS", "_refreshEngineStats", self.tcs)
-        self.apo.update(_scoring=svc)
+        self.adopted = []                               # prompts handed to _applyBeamBestPrompt (APO:1161: auto-apply of a new best)
+        self.apo.update(_scoring=svc, _dirty=False, _onDidChangeState=fire, _config=js.JSObject(beamWidth=4, beamRounds=3),
+                        _applyBeamBestPrompt=js.NativeFunction(lambda this, p: self.adopted.append(js.from_js(p)) or js.undefined))
+        for name in ("_applyBeamUpdate", "_evaluateBeam"):
+            self.apo[name] = self._method(self.apo_text, "APO", name, self.apo)
+
+    def evaluate_beam(self, candidates: list, dims: np.ndarray):
+        """patched APOService._evaluateBeam(candidates, evaluations float32[C][T][9], T) -> the beam state it leaves"""
+        C, T, _ = dims.shape
+        self.interp.call(self.apo["_evaluateBeam"], self.apo, [js.to_js(candidates), vsbuffer(np.ascontiguousarray(dims, "<f4").tobytes()), T])
+        return js.from_js(self.apo["_beamState"])
 
     def stats(self, traces):
         self.tcs["_traces"] = js.JSMap((t["id"], js.to_js(t)) for t in traces)

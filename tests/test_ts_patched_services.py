@@ -85,3 +85,35 @@ def test_patched_reports_and_stats_equal_the_reference(outputs):
         # doubles in trace order -> equal to ~1e-15 relative, and equal in everything derived from them above
         same(got["locals"], w["locals"], 1e-12, f"{cname}/locals")
         same(got["stats"], w["stats"], 1e-12, f"{cname}/stats")
+
+
+def test_patched_evaluate_beam_feeds_the_strict_greater_adoption(orc):
+    """`_evaluateBeam` (new) + `_applyBeamUpdate` (the reference's inline bookkeeping of APO:1138-1166, moved into a method by the
+    patch): scores and top-K come back as little-endian blocks, the beam is the candidates in top-K order with their scores, a new
+    best is adopted only on a strictly greater score, the round counter advances per evaluation."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ts_harness"))
+    import run_patched as rp
+    P = rp.Patched(REF)
+    C, T = 6, 300
+    dims = orc.gen_dims(0x5EED00B7, 0, C, 0, T, 300, 2)
+    scores, _ = orc.score_dims(dims)
+    order = [int(c) for c in orc.topk(scores, 4)]
+    cands = [{"id": f"p{c}", "version": c + 1, "content": f"prompt {c}"} for c in range(C)]
+    st = P.evaluate_beam(cands, dims)
+    assert [b["id"] for b in st["beam"]] == [f"p{c}" for c in order]                        # K = min(beamWidth 4, C)
+    assert [b["score"] for b in st["beam"]] == [float(scores[c]) for c in order] and st["beam"][0]["content"] == f"prompt {order[0]}"
+    assert st["currentRound"] == 1 and st["totalRounds"] == 3 and st["historyBestScore"] == float(scores[order[0]])
+    assert st["historyBestPrompt"]["id"] == f"p{order[0]}" and [a["id"] for a in P.adopted] == [f"p{order[0]}"]
+    st = P.evaluate_beam(cands, dims)                                                         # same scores again: not strictly greater
+    assert st["currentRound"] == 2 and len(P.adopted) == 1
+    worse = dims.copy()
+    worse[order[0]] = -1.0                                                                    # the former best drops to the bottom
+    st = P.evaluate_beam(cands, worse)
+    assert st["currentRound"] == 3 and len(P.adopted) == 1 and st["beam"][0]["id"] == f"p{order[1]}"
+    assert st["historyBestPrompt"]["id"] == f"p{order[0]}"                                   # history keeps the best ever seen
+    better = dims.copy()
+    better[order[3]] = 1.0
+    st = P.evaluate_beam(cands, better)
+    assert [a["id"] for a in P.adopted] == [f"p{order[0]}", f"p{order[3]}"] and st["historyBestScore"] == 1.0
+    assert P.evaluate_beam([], dims[:0]) == st                                                # no candidates: nothing happens

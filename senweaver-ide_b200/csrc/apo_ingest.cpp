@@ -287,12 +287,38 @@ namespace {
 inline uint32_t fbits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
 inline int dim_of(int j) { return j < 2 ? j : j + 1; }
 
+// Distinct fp32 bit patterns of one coded dimension (<= 255) with a value: open addressing over 1024 slots, so that the hit every
+// evaluation after the first few takes is one predictable probe (a linear scan of the list ended at a random position: one branch
+// mispredict per dimension and evaluation).  0xFFFFFFFF = free slot: a NaN pattern, and NaNs (absent) never get here.
 struct DistinctSet {
+	static constexpr uint32_t FREE = 0xFFFFFFFFu;
 	uint32_t v[256]; int n = 0; bool overflow = false;
+	uint32_t key[1024]; uint8_t val[1024];
+	DistinctSet() { memset(key, 0xFF, sizeof key); }
+	static inline uint32_t slot(uint32_t b) { return (b * 2654435761u) >> 22; }
 	inline void add(uint32_t b) {
-		for (int i = 0; i < n; i++) if (v[i] == b) return;
-		if (n == 255) { overflow = true; return; }
-		v[n++] = b;
+		uint32_t i = slot(b);
+		while (key[i] != b) {
+			if (key[i] == FREE) {
+				if (n == 255) { overflow = true; return; }
+				key[i] = b; val[i] = (uint8_t)n; v[n++] = b;
+				return;
+			}
+			i = (i + 1) & 1023u;
+		}
+	}
+	// value -> code map of a finished codebook column (codes = positions in `dense`)
+	void assign(const std::vector<uint32_t> &dense) {
+		memset(key, 0xFF, sizeof key); n = 0; overflow = false;
+		for (size_t c = 0; c < dense.size(); c++) { add(dense[c]); }
+	}
+	inline uint32_t code_of(uint32_t b, uint32_t absent) const {
+		uint32_t i = slot(b);
+		while (key[i] != b) {
+			if (key[i] == FREE) return absent;
+			i = (i + 1) & 1023u;
+		}
+		return val[i];
 	}
 };
 
@@ -340,6 +366,8 @@ extern "C" int apo_compact_encode_host(const float *dims, uint32_t C, uint64_t T
 		for (int c = 0; c < 256; c++) codebook[256 * j + c] = c < (int)dense[j].size() ? dense[j][c] : 0xFFFFFFFFu;
 	}
 	// ---- pass 2: encode
+	std::vector<DistinctSet> codes(8);
+	for (int j = 0; j < 8; j++) codes[(size_t)j].assign(dense[j]);
 	run_threads(nthreads, [&](int k, int n) {
 		const uint64_t a = N * (uint64_t)k / (uint64_t)n, b = N * (uint64_t)(k + 1) / (uint64_t)n;
 		for (uint64_t i = a; i < b; i++) {
@@ -349,9 +377,7 @@ extern "C" int apo_compact_encode_host(const float *dims, uint32_t C, uint64_t T
 				const float f = row[dim_of(j)];
 				uint32_t code = 255u;
 				if (f == f) {
-					const uint32_t bits = fbits(f);
-					const std::vector<uint32_t> &dv = dense[j];
-					for (uint32_t c = 0; c < dv.size(); c++) if (dv[c] == bits) { code = c; break; }
+					code = codes[(size_t)j].code_of(fbits(f), 255u);
 					mask |= 1u << dim_of(j);
 				}
 				q |= (uint64_t)code << (8 * j);
@@ -428,7 +454,17 @@ extern "C" int apo_packed_encode_host(const float *dims, uint32_t C, uint64_t T,
 	d2all.erase(std::unique(d2all.begin(), d2all.end()), d2all.end());
 	if (d2all.size() > 4095) return APO_E_STATE;
 	for (size_t c = 0; c < 4096; c++) d2book[c] = c < d2all.size() ? d2all[c] : 0xFFFFFFFFu;
-	// ---- pass 2: encode
+	// ---- pass 2: encode (value -> code through hash maps: the binary search of the sorted ratios mispredicted ~11 branches per
+	// evaluation)
+	std::vector<DistinctSet> codes(8);
+	for (int j = 0; j < 8; j++) codes[(size_t)j].assign(dense[j]);
+	std::vector<uint32_t> d2key(16384, 0xFFFFFFFFu);
+	std::vector<uint16_t> d2val(16384, 4095);
+	for (size_t c = 0; c < d2all.size(); c++) {
+		uint32_t h = (d2all[c] * 2654435761u) >> 18;
+		while (d2key[h] != 0xFFFFFFFFu) h = (h + 1) & 16383u;
+		d2key[h] = d2all[c]; d2val[h] = (uint16_t)c;
+	}
 	run_threads(nthreads, [&](int k, int n) {
 		const uint64_t a = N * (uint64_t)k / (uint64_t)n, b = N * (uint64_t)(k + 1) / (uint64_t)n;
 		for (uint64_t i = a; i < b; i++) {
@@ -436,17 +472,17 @@ extern "C" int apo_packed_encode_host(const float *dims, uint32_t C, uint64_t T,
 			uint32_t w = 0;
 			for (int j = 0; j < 8; j++) {
 				const float f = row[dim_of(j)];
-				uint32_t code = 15u;
-				if (f == f) {
-					const uint32_t bits = fbits(f);
-					const std::vector<uint32_t> &dv = dense[j];
-					for (uint32_t c = 0; c < dv.size(); c++) if (dv[c] == bits) { code = c; break; }
-				}
+				const uint32_t code = f == f ? codes[(size_t)j].code_of(fbits(f), 15u) : 15u;
 				w |= code << (4 * j);
 			}
 			const float f2 = row[2];
 			uint16_t k2 = 4095;
-			if (f2 == f2) k2 = (uint16_t)(std::lower_bound(d2all.begin(), d2all.end(), fbits(f2), by_value) - d2all.begin());
+			if (f2 == f2) {
+				const uint32_t bits = fbits(f2);
+				uint32_t h = (bits * 2654435761u) >> 18;
+				while (d2key[h] != bits) h = (h + 1) & 16383u;                // present by construction (pass 1 saw every value)
+				k2 = d2val[h];
+			}
 			pc[i] = w;
 			pd[i] = k2;
 		}

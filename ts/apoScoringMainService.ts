@@ -18,7 +18,7 @@
  *  upload -> scoreResident sequence keeps its meaning without any promise chaining here.
  *--------------------------------------------------------------------------------------------*/
 import { VSBuffer } from '../../../../base/common/buffer.js';
-import { ApoResidentQuery, ApoScoreBlocks, IApoScoringService } from '../common/apoScoringService.js';
+import { ApoResidentQuery, ApoScoreBlocks, ApoTupleBuffers, IApoScoringService } from '../common/apoScoringService.js';
 
 type Blocks = { scores: ArrayBuffer; counts: ArrayBuffer; topk: ArrayBuffer; report: ArrayBuffer };
 
@@ -43,9 +43,6 @@ interface ApoAddon {
 interface ApoTuples { tl: ArrayBuffer; th: ArrayBuffer; tbookPc: ArrayBuffer; tbookPd: ArrayBuffer; codebook: ArrayBuffer; d2book: ArrayBuffer; nTuples: number }
 
 const RECORD_BYTES = 32;
-/** From this many evaluations on, score() re-encodes the fp32 tensor as dictionary indices before it crosses PCIe: the encode
- *  (two threaded passes over host memory) costs less than the 33 bytes per evaluation it keeps off the bus. */
-const TUPLE_TRANSPORT_MIN_EVALS = 1 << 20;
 
 function ab(buf: VSBuffer): ArrayBuffer {
 	const u8 = buf.buffer;
@@ -166,14 +163,24 @@ export class ApoScoringMainService implements IApoScoringService {
 
 	// ---- one-shot path ------------------------------------------------------------------------
 	async score(dims: VSBuffer, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks> {
-		const addon = await this._need();
-		const host = ab(dims), rec = corpus ? ab(corpus) : null;
-		if (C * T >= TUPLE_TRANSPORT_MIN_EVALS) {
-			// same integers, same result: only the bytes on the wire differ (DESIGN.md section 3, Form T)
-			const tuples = await addon.encodeTuples(host, C, T);
-			if (tuples) { return wrapBlocks(await addon.scoreHostTuples(this._handle, tuples, C, T, rec, K)); }
-		}
-		return wrapBlocks(await addon.score(this._handle, host, C, T, rec, K));
+		return wrapBlocks(await (await this._need()).score(this._handle, ab(dims), C, T, corpus ? ab(corpus) : null, K));
+	}
+
+	/** fp32 evaluations -> Form T (3 bytes per evaluation + the dictionary of distinct evaluations); undefined when the tensor is not
+	 *  categorical enough.  Encoding reads the 36-byte rows twice on the addon's worker threads — several times the cost of sending
+	 *  them over PCIe once — so it pays for evaluations that are scored MORE THAN ONCE (beam rounds over the same rollouts, weight
+	 *  sweeps), kept, or shipped between processes; a one-shot score() of fp32 rows stays the cheaper call. */
+	async encodeTuples(dims: VSBuffer, C: number, T: number): Promise<ApoTupleBuffers | undefined> {
+		const t = await (await this._need()).encodeTuples(ab(dims), C, T);
+		if (!t) { return undefined; }
+		const w = (b: ArrayBuffer) => VSBuffer.wrap(new Uint8Array(b));
+		return { tl: w(t.tl), th: w(t.th), tbookPc: w(t.tbookPc), tbookPd: w(t.tbookPd), codebook: w(t.codebook), d2book: w(t.d2book), nTuples: t.nTuples };
+	}
+
+	/** Same result as score() on the tensor the tuples were encoded from; 12x fewer bytes over IPC and PCIe. */
+	async scoreTuples(t: ApoTupleBuffers, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks> {
+		const raw: ApoTuples = { tl: ab(t.tl), th: ab(t.th), tbookPc: ab(t.tbookPc), tbookPd: ab(t.tbookPd), codebook: ab(t.codebook), d2book: ab(t.d2book), nTuples: t.nTuples };
+		return wrapBlocks(await (await this._need()).scoreHostTuples(this._handle, raw, C, T, corpus ? ab(corpus) : null, K));
 	}
 
 	async scoreHostRecords(records: VSBuffer, rowBytes: 32 | 16, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks> {

@@ -26,6 +26,13 @@ export interface ApoScoreBlocks {
 	report: VSBuffer;   // struct apo_corpus_report (784 bytes)
 }
 
+/** Form T of a float32[C][T][9] tensor (include/apo_b200.h): tl uint16[C][T] | th uint8[C][T] = the 24-bit dictionary index of every
+ *  evaluation; tbookPc uint32[n] / tbookPd uint16[n] = the n distinct evaluations as Form P pairs; codebook uint32[8][256], d2book
+ *  uint32[4096] = the fp32 bit patterns the codes stand for. */
+export interface ApoTupleBuffers {
+	tl: VSBuffer; th: VSBuffer; tbookPc: VSBuffer; tbookPd: VSBuffer; codebook: VSBuffer; d2book: VSBuffer; nTuples: number;
+}
+
 /** What a resident scoring call selects (apo_score_opts of include/apo_b200.h). */
 export interface ApoResidentQuery {
 	C: number;              // candidates uploaded with dimsUpload / rolloutsUpload
@@ -63,6 +70,10 @@ export interface IApoScoringService {
 	score(dims: VSBuffer, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks>;
 	/** [C][T] trace records (the IDE's own representation): 2.2x fewer PCIe bytes than fp32 dims with 16-byte rows. */
 	scoreHostRecords(records: VSBuffer, rowBytes: 32 | 16, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks>;
+	/** fp32 evaluations -> Form T (include/apo_b200.h): a 24-bit dictionary index per evaluation (3 bytes instead of 36) + the
+	 *  dictionary of distinct evaluations.  For evaluations that are scored more than once, kept, or moved between processes. */
+	encodeTuples(dims: VSBuffer, C: number, T: number): Promise<ApoTupleBuffers | undefined>;
+	scoreTuples(tuples: ApoTupleBuffers, C: number, T: number, corpus: VSBuffer | undefined, K: number): Promise<ApoScoreBlocks>;
 }
 
 export const IApoScoringService = createDecorator<IApoScoringService>('senweaverApoScoringService');
@@ -88,6 +99,8 @@ export class ApoScoringService implements IApoScoringService {
 	scoreHostRecords(records: VSBuffer, rowBytes: 32 | 16, C: number, T: number, corpus: VSBuffer | undefined, K: number) {
 		return this._proxy.scoreHostRecords(records, rowBytes, C, T, corpus, K);
 	}
+	encodeTuples(dims: VSBuffer, C: number, T: number) { return this._proxy.encodeTuples(dims, C, T); }
+	scoreTuples(tuples: ApoTupleBuffers, C: number, T: number, corpus: VSBuffer | undefined, K: number) { return this._proxy.scoreTuples(tuples, C, T, corpus, K); }
 }
 
 registerSingleton(IApoScoringService, ApoScoringService, InstantiationType.Delayed);

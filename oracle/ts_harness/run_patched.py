@@ -48,7 +48,15 @@ def uint8array(this, arg=0, offset=0, length=js.undefined):
     off = int(offset)
     n = len(buf.b) - off if length is js.undefined else int(length)
     copy = js.NativeFunction(lambda this: uint8array(None, ByteBuf(buf.b[off:off + n])))       # .slice(): a copy with its own ArrayBuffer
-    return js.JSObject(buffer=buf, byteOffset=off, byteLength=n, length=n, slice=copy)
+
+    def set_(this, src, at=0):                                                                 # .set(typedArray, offset)
+        data = bytes(src["buffer"].b[src["byteOffset"]:src["byteOffset"] + src["byteLength"]])
+        at = int(at)
+        if at < 0 or at + len(data) > n:
+            raise js.JSThrow("RangeError: offset is out of bounds")
+        buf.b[off + at:off + at + len(data)] = data
+        return js.undefined
+    return js.JSObject(buffer=buf, byteOffset=off, byteLength=n, length=n, slice=copy, set=js.NativeFunction(set_))
 
 
 def typed_array(fmt: str, size: int):

@@ -117,3 +117,48 @@ def test_patched_evaluate_beam_feeds_the_strict_greater_adoption(orc):
     st = P.evaluate_beam(cands, better)
     assert [a["id"] for a in P.adopted] == [f"p{order[0]}", f"p{order[3]}"] and st["historyBestScore"] == 1.0
     assert P.evaluate_beam([], dims[:0]) == st                                                # no candidates: nothing happens
+
+
+def test_main_service_micro_batches_single_trace_rewards(orc):
+    """ts/apoScoringMainService.ts `_flushRewards`, executed: the single-trace reward requests of one tick are concatenated into ONE
+    addon call and the three result blocks are sliced back per caller (72 / 4 / 8 bytes per record) — each caller must receive exactly
+    what a call of its own would have returned, whatever the mix of request sizes."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ts_harness"))
+    import minijs as js
+    import run_patched as rp
+    import run_reference as rr
+    src = open(os.path.join(ROOT, "ts", "apoScoringMainService.ts"), encoding="utf-8").read()
+    text, _ = rr.extract_method(src, "_flushRewards")
+    interp = js.Interp({"Uint8Array": js.NativeFunction(rp.uint8array), "RECORD_BYTES": 32,
+                        "VSBuffer": js.JSObject(wrap=js.NativeFunction(lambda this, u8: js.JSObject(buffer=u8)))})
+    scoring = rp.OracleScoring()
+    seen = []
+
+    def addon_reward_batch(this, handle, array_buffer):
+        assert isinstance(array_buffer, rp.ByteBuf) and handle == "H"
+        seen.append(len(array_buffer.b) // 32)
+        r = scoring.reward_batch(None, js.JSObject(buffer=rp.uint8array(None, array_buffer))).value
+        # the addon hands back plain ArrayBuffers
+        return js.SyncPromise(js.JSObject(dims=r["dims"]["buffer"]["buffer"], masks=r["masks"]["buffer"]["buffer"], finals=r["finals"]["buffer"]["buffer"]))
+
+    recs = orc.gen_records(0x5EED00C3, orc.STREAM_CORPUS, 0, 1, 0, 11, 400, 1).reshape(-1)
+    sizes = [1, 3, 1, 2, 4]                                           # five callers in one tick
+    got, chunks, at = {}, [], 0
+    this = js.JSObject(_addon=js.JSObject(rewardBatch=js.NativeFunction(addon_reward_batch)), _handle="H", _pendingRewards=js.JSArray())
+    for k, n in enumerate(sizes):
+        chunk = recs[at:at + n]
+        at += n
+        chunks.append(chunk)
+        u8 = rp.uint8array(None, rp.ByteBuf(b"\xEE" * 5 + chunk.tobytes() + b"\xEE" * 3), 5, 32 * n)        # a view into a larger buffer
+        this["_pendingRewards"].append(js.JSObject(records=u8, resolve=js.NativeFunction(lambda t, v, k=k: got.__setitem__(k, v)),
+                                                   reject=js.NativeFunction(lambda t, e: (_ for _ in ()).throw(AssertionError(e)))))
+    _, fn = interp.make_method(text, this)
+    interp.call(fn, this, [])
+    assert seen == [sum(sizes)] and len(this["_pendingRewards"]) == 0 and sorted(got) == list(range(len(sizes)))
+    for k, chunk in enumerate(chunks):
+        want = scoring.reward_batch(None, rp.vsbuffer(chunk.tobytes())).value
+        for block in ("dims", "masks", "finals"):
+            assert rp.vsbuffer_bytes(got[k][block]) == rp.vsbuffer_bytes(want[block]), (k, block)
+    interp.call(fn, this, [])                                          # nothing pending: no call
+    assert seen == [sum(sizes)]

@@ -23,11 +23,32 @@ def free_port():
         return s.getsockname()[1]
 
 
-def local_vector(sh, orc, rank, world):
+def tuple_partials(pkg, orc, dims):
+    """Form T on this shard, as the engine scores it: the shard's OWN dictionary, one reward per distinct evaluation, then sums of
+    table entries per candidate (csrc/apo_tuple.cu) — dictionaries differ from rank to rank, the integers they sum to do not."""
+    pc, pd, book, d2book = pkg.packed_encode_host(dims, nthreads=2)
+    tl, th, (tpc, tpd) = pkg.tuple_encode_host(pc, pd, nthreads=2)
+    n = len(tpc)
+    entries = np.full((n, 9), np.nan, np.float32)
+    for j, dim in enumerate([0, 1, 3, 4, 5, 6, 7, 8]):
+        code = ((tpc >> np.uint32(4 * j)) & np.uint32(15)).astype(np.int64)
+        entries[code != 15, dim] = book.reshape(8, 256)[j][code[code != 15]].view(np.float32)
+    entries[tpd != 4095, 2] = d2book[tpd[tpd != 4095].astype(np.int64)].view(np.float32)
+    fx, counted = orc.score_dims_fx(entries.reshape(n, 1, 9)) if n else ([], [])
+    idx = tl.astype(np.int64) | (th.astype(np.int64) << 16)
+    sums, counts = [], []
+    for c in range(dims.shape[0]):
+        occ = np.bincount(idx[c], minlength=n)
+        sums.append(sum(int(o) * int(v) for o, v in zip(occ, fx) if o))
+        counts.append(sum(int(o) * int(k) for o, k in zip(occ, counted) if o))
+    return sums, counts
+
+
+def local_vector(sh, orc, rank, world, layout="fp32"):
     first, last = sh.shard_range(T, world, rank)
     vec = np.zeros(sh.acc_words(C, world), np.int64)
     dims = orc.gen_dims(SEED, 0, C, first, last - first, 300, 2)
-    sums, counts = orc.score_dims_fx(dims)
+    sums, counts = tuple_partials(import_module("senweaver-ide_b200"), orc, dims) if layout == "tuples" else orc.score_dims_fx(dims)
     sh.pack_candidate_partials(vec, sums, counts)
     recs = orc.gen_records(SEED, orc.STREAM_CORPUS, 0, 1, first, last - first, 300, 2).reshape(-1)
     rep = orc.report(recs, idx_base=first)
@@ -46,22 +67,22 @@ def local_vector(sh, orc, rank, world):
     return vec
 
 
-def worker(rank, world, port, out_dir):
+def worker(rank, world, port, out_dir, layout="fp32"):
     sys.path.insert(0, ROOT)
     import oracle as orc
     sh = import_module("senweaver-ide_b200").sharding
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    t = torch.from_numpy(local_vector(sh, orc, rank, world))
+    t = torch.from_numpy(local_vector(sh, orc, rank, world, layout))
     dist.all_reduce(t, op=dist.ReduceOp.SUM)              # the single join
     np.save(os.path.join(out_dir, f"joined_{rank}.npy"), t.numpy())
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_join_equals_unsharded(tmp_path, orc, world):
+@pytest.mark.parametrize("world,layout", [(2, "fp32"), (3, "fp32"), (2, "tuples")])
+def test_sharded_join_equals_unsharded(tmp_path, orc, world, layout):
     sh = import_module("senweaver-ide_b200").sharding
     port = free_port()
-    mp.spawn(worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(worker, args=(world, port, str(tmp_path), layout), nprocs=world, join=True)
     joined = [np.load(tmp_path / f"joined_{r}.npy") for r in range(world)]
     for r in range(1, world):
         assert np.array_equal(joined[0], joined[r])        # every rank finalizes from identical input
